@@ -1,0 +1,633 @@
+// Tensor-core convolution kernels for sm_100a: implicit GEMM on tcgen05.mma with TMEM accumulators,
+// operands staged in shared memory by TMA (4-D tiled boxes give the im2col view without materialising it).
+//
+//   conv_igemm_kernel : fprop / dgrad / 1x1 / linear.  A = activation box (K-major, 128B swizzle),
+//                       B = packed filter [tap][cout][cin] (K-major).  Persistent, warp-specialised:
+//                       warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+//   conv_wgrad_kernel : filter gradient.  Both operands are MN-major (channels contiguous, pixels = K),
+//                       split over pixel ranges; partials reduced by splitk_reduce_kernel.
+//
+// Replaces tf.nn.conv2d and its two gradients (reference common/ops/conv2d.py:181-187).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ganb {
+
+constexpr int BM = 128;                      // UMMA M: output pixels (igemm) / input channels (wgrad)
+constexpr int BK = 64;                       // bf16 elements per 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+struct IgemmParams {
+  int N, Ho, Wo, Cout;
+  int taps, kw;
+  int stride, pad_t, pad_l;
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n, tiles_co, num_tiles;
+  int kchunks, flip;
+  const float* alpha;
+  const float* bias;
+  const float* residual;
+  void* out;
+  int out_bf16, act;
+};
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NC]);
+
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&r)[32]) {
+  tmem_ld_32x32(taddr, r);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == GANB_ACT_TANH) return tanhf(v);
+  if (act == GANB_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == GANB_ACT_LRELU) return v >= 0.f ? v : 0.2f * v;
+  return v;
+}
+
+// One thread owns one output pixel (TMEM lane) and NC consecutive channels held in registers.
+template <int NC>
+__device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_t (&r)[NC], float alpha,
+                                             int64_t pix, int co_base) {
+  const int cout = p.Cout;
+  const int64_t off = pix * cout + co_base;
+  const bool vec = (cout % 4 == 0);
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      const int co = co_base + j;
+      if (co >= cout) break;
+      float4 v = make_float4(__uint_as_float(r[j]) * alpha, __uint_as_float(r[j + 1]) * alpha,
+                             __uint_as_float(r[j + 2]) * alpha, __uint_as_float(r[j + 3]) * alpha);
+      if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (p.residual) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off + j));
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      if (p.act) {
+        v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+        v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+      }
+      if (p.out_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + j) = pk;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + j) = v;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int co = co_base + j;
+      if (co < cout) {
+        float v = __uint_as_float(r[j]) * alpha;
+        if (p.bias) v += __ldg(p.bias + co);
+        if (p.residual) v += __ldg(p.residual + off + j);
+        v = apply_act(v, p.act);
+        if (p.out_bf16)
+          reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16_rn(v);
+        else
+          reinterpret_cast<float*>(p.out)[off + j] = v;
+      }
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const IgemmParams p) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int ACC_STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN) < 32 ? 32 : (ACC_STAGES * BN);
+  constexpr int NC = BN < 32 ? BN : 32;  // columns per tcgen05.ld
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kiters = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tco = t % p.tiles_co; t /= p.tiles_co;
+        const int tw = t % p.tiles_w;   t /= p.tiles_w;
+        const int th = t % p.tiles_h;   t /= p.tiles_h;
+        const int tn = t;
+        const int w0 = tw * p.bw * p.stride - p.pad_l;
+        const int h0 = th * p.bh * p.stride - p.pad_t;
+        const int n0 = tn * p.bn;
+        const int co0 = tco * BN;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * BK, w0 + s, h0 + r, n0);
+            tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kc * BK, co0, tap_b);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kit > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;
+    const int iw = m % p.bw;
+    const int ih = (m / p.bw) % p.bh;
+    const int in_ = m / (p.bw * p.bh);
+    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tco = t % p.tiles_co; t /= p.tiles_co;
+      const int tw = t % p.tiles_w;   t /= p.tiles_w;
+      const int th = t % p.tiles_h;   t /= p.tiles_h;
+      const int tn = t;
+      const int wo = tw * p.bw + iw, ho = th * p.bh + ih, n = tn * p.bn + in_;
+      const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
+      const int64_t pix = (static_cast<int64_t>(n) * p.Ho + ho) * p.Wo + wo;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / NC; ++c) {
+        uint32_t r[NC];
+        tmem_ld_cols<NC>(trow + c * NC, r);
+        tmem_ld_wait();
+        if (valid) epilogue_row<NC>(p, r, alpha, pix, tco * BN + c * NC);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[ci, co] = sum_pixels X[pixel + tap, ci] * dY[pixel, co]; channels are contiguous in NHWC so both
+// operands are MN-major.  One CTA = (tap, ci tile of 128, co tile of BN, pixel split).
+// ------------------------------------------------------------------------------------------------
+constexpr int PB = 64;  // pixels per pipeline stage (4 UMMA K-steps of 16)
+
+struct WgradParams {
+  int N, Ho, Wo;  // dy spatial extent
+  int Cin, Cout;
+  int kw, taps, pad_t, pad_l;
+  int bw, bh, bn;          // pixel box, bw*bh*bn == PB
+  int pb_w, pb_h, pb_n;    // pixel blocks per dim
+  int num_pb, splits, pb_per_split;
+  int ci_tiles, co_tiles;
+  float* partial;  // [splits][taps][Cin][Cout]
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const WgradParams p) {
+  constexpr int A_BYTES = PB * BM * 2;  // two 64-channel boxes of PB pixel rows
+  constexpr int B_BYTES = PB * BN * 2;
+  constexpr int BOX_BYTES = PB * 128;   // one 64-channel box
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int u = blockIdx.x;
+  const int tco = u % p.co_tiles; u /= p.co_tiles;
+  const int tci = u % p.ci_tiles; u /= p.ci_tiles;
+  const int tap = u % p.taps;     u /= p.taps;
+  const int split = u;
+  const int r = tap / p.kw, s = tap - r * p.kw;
+  const int pb_begin = split * p.pb_per_split;
+  const int pb_end = min(p.num_pb, pb_begin + p.pb_per_split);
+  const int ci0 = tci * BM, co0 = tco * BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        int t = pb;
+        const int bwi = t % p.pb_w; t /= p.pb_w;
+        const int bhi = t % p.pb_h; t /= p.pb_h;
+        const int w0 = bwi * p.bw, h0 = bhi * p.bh, n0 = t * p.bn;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+        uint8_t* a = sA + stage * A_BYTES;
+        uint8_t* b = sB + stage * B_BYTES;
+#pragma unroll
+        for (int j = 0; j < BM / 64; ++j)
+          tma_load_4d(a + j * BOX_BYTES, &tmX, &full[stage], ci0 + 64 * j, w0 + s - p.pad_l, h0 + r - p.pad_t, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(b + j * BOX_BYTES, &tmDY, &full[stage], co0 + 64 * j, w0, h0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        // MN-major, 128B swizzle: 64 channels per row, 8-pixel groups 1024 B apart (SBO),
+        // next 64-channel box BOX_BYTES away (LBO).
+        const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), BOX_BYTES, 1024);
+        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), BOX_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < PB / 16; ++k) {
+          // 16 pixels = 16 rows of 128 B = 2048 B -> +128 in 16-byte units
+          umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, (first && k == 0) ? 0u : 1u);
+        }
+        first = false;
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int ci = ci0 + q * 32 + lane;
+    float* out = p.partial + ((static_cast<int64_t>(split) * p.taps + tap) * p.Cin + ci) * p.Cout;
+    const bool has_work = pb_end > pb_begin;
+    if (has_work) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      if (has_work) {
+        tmem_ld_32x32(trow + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (ci < p.Cin) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int co = co0 + c * 32 + j;
+          if (co < p.Cout) {  // Cout % 8 == 0 so groups of 4 never straddle the edge
+            *reinterpret_cast<float4*>(out + co) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// dw = beta*dw + scale * sum_s partial[s]
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int64_t n4,
+                                     int splits, const float* __restrict__ scale, float beta) {
+  const float sc = scale ? __ldg(scale) : 1.0f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + s * n4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4 o = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+    if (beta != 0.f) {
+      const float4 d = reinterpret_cast<const float4*>(dw)[i];
+      o.x += beta * d.x; o.y += beta * d.y; o.z += beta * d.z; o.w += beta * d.w;
+    }
+    reinterpret_cast<float4*>(dw)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Splits `total` (a power of two) pixels into a bn x bh x bw box that tiles an image of size H x W.
+static void pick_box(int total, int H, int W, int* bw, int* bh, int* bn) {
+  int w = pow2_ceil(W);
+  if (w > total) w = total;
+  int h = pow2_ceil(H);
+  if (h > total / w) h = total / w;
+  *bw = w;
+  *bh = h;
+  *bn = total / (w * h);
+}
+
+template <int BN, int STAGES>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+  static bool configured = false;
+  auto kern = conv_igemm_kernel<BN, STAGES>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "igemm smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  p.tiles_co = ceil_div(p.Cout, BN);
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  GANB_CHECK_LAUNCH("conv_igemm_kernel");
+  return 0;
+}
+
+}  // namespace ganb
+
+using namespace ganb;
+
+extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho,
+                                 int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
+                                 int flip_taps, const float* alpha, const float* bias, const float* residual,
+                                 int act, int out_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !wp || !y) return fail(GANB_E_BADARG, "conv2d_igemm: null buffer");
+  if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || ho <= 0 || wo <= 0 || cout <= 0 || kh <= 0 || kw <= 0)
+    return fail(GANB_E_BADARG, "conv2d_igemm: non-positive dimension");
+  if (cin % 8 != 0) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm: cin=%d must be a multiple of 8", cin);
+  if (stride != 1) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm: stride=%d not supported yet", stride);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15)
+    return fail(GANB_E_BADARG, "conv2d_igemm: x / wp must be 16-byte aligned");
+
+  IgemmParams p;
+  p.N = n; p.Ho = ho; p.Wo = wo; p.Cout = cout;
+  p.taps = kh * kw; p.kw = kw;
+  p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+  pick_box(BM, ho, wo, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = ceil_div(wo, p.bw);
+  p.tiles_h = ceil_div(ho, p.bh);
+  p.tiles_n = ceil_div(n, p.bn);
+  p.kchunks = ceil_div(cin, BK);
+  p.flip = flip_taps;
+  p.alpha = alpha; p.bias = bias; p.residual = residual;
+  p.out = y; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
+
+  // choose the N tile: whole Cout when it fits, shrunk while the grid cannot fill the machine
+  int bn_tile = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  while (bn_tile > 64 && m_tiles * ceil_div(cout, bn_tile) < sm_count()) bn_tile >>= 1;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    const uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = encode_tmap_bf16(&tmA, x, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)(kh * kw)};
+    const uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)cin * cout * 2};
+    const uint32_t box[3] = {BK, (uint32_t)bn_tile, 1};
+    int rc = encode_tmap_bf16(&tmB, wp, 3, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  switch (bn_tile) {
+    case 16: return launch_igemm<16, 8>(tmA, tmB, p, stream);
+    case 32: return launch_igemm<32, 8>(tmA, tmB, p, stream);
+    case 64: return launch_igemm<64, 8>(tmA, tmB, p, stream);
+    case 128: return launch_igemm<128, 6>(tmA, tmB, p, stream);
+    default: return launch_igemm<256, 4>(tmA, tmB, p, stream);
+  }
+}
+
+namespace ganb {
+
+struct WgradPlan {
+  WgradParams p;
+  int bn_tile;
+  int grid;
+};
+
+static void plan_wgrad(int n, int ho, int wo, int cin, int cout, int kh, int kw, WgradPlan* plan) {
+  WgradParams& p = plan->p;
+  p.N = n; p.Ho = ho; p.Wo = wo; p.Cin = cin; p.Cout = cout;
+  p.kw = kw; p.taps = kh * kw;
+  pick_box(PB, ho, wo, &p.bw, &p.bh, &p.bn);
+  p.pb_w = ceil_div(wo, p.bw);
+  p.pb_h = ceil_div(ho, p.bh);
+  p.pb_n = ceil_div(n, p.bn);
+  p.num_pb = p.pb_w * p.pb_h * p.pb_n;
+  plan->bn_tile = cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
+  p.ci_tiles = ceil_div(cin, BM);
+  p.co_tiles = ceil_div(cout, plan->bn_tile);
+  const int units = p.taps * p.ci_tiles * p.co_tiles;
+  int splits = ceil_div(sm_count(), units);
+  // keep at least 4 pixel blocks per split so the pipeline has something to overlap
+  const int max_splits = p.num_pb / 4 > 0 ? p.num_pb / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 64) splits = 64;
+  p.pb_per_split = ceil_div(p.num_pb, splits);
+  p.splits = ceil_div(p.num_pb, p.pb_per_split);
+  plan->grid = units * p.splits;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, int grid,
+                        cudaStream_t stream) {
+  constexpr int smem = STAGES * (PB * BM * 2 + PB * BN * 2) + 1024 + 256;
+  static bool configured = false;
+  auto kern = conv_wgrad_kernel<BN, STAGES>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "wgrad smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, smem, stream>>>(tmX, tmDY, p);
+  GANB_CHECK_LAUNCH("conv_wgrad_kernel");
+  return 0;
+}
+
+}  // namespace ganb
+
+extern "C" int64_t ganb_conv2d_wgrad_workspace(int n, int h, int w, int cin, int ho, int wo, int cout, int kh,
+                                               int kw) {
+  (void)h; (void)w;
+  WgradPlan plan;
+  plan_wgrad(n, ho, wo, cin, cout, kh, kw, &plan);
+  return static_cast<int64_t>(plan.p.splits) * kh * kw * cin * cout * 4;
+}
+
+extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace, int n, int h, int w,
+                                 int cin, int ho, int wo, int cout, int kh, int kw, int pad_t, int pad_l,
+                                 const float* scale, float beta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !dy || !dw || !workspace) return fail(GANB_E_BADARG, "conv2d_wgrad: null buffer");
+  if (cin % 8 != 0 || cout % 8 != 0)
+    return fail(GANB_E_UNSUPPORTED, "conv2d_wgrad: cin=%d and cout=%d must be multiples of 8", cin, cout);
+  WgradPlan plan;
+  plan_wgrad(n, ho, wo, cin, cout, kh, kw, &plan);
+  WgradParams& p = plan.p;
+  p.pad_t = pad_t; p.pad_l = pad_l;
+  p.partial = static_cast<float*>(workspace);
+
+  CUtensorMap tmX, tmDY;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = encode_tmap_bf16(&tmX, x, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)wo, (uint64_t)ho, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cout * 2, (uint64_t)wo * cout * 2, (uint64_t)ho * wo * cout * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = encode_tmap_bf16(&tmDY, dy, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  int rc;
+  switch (plan.bn_tile) {
+    case 64: rc = launch_wgrad<64, 6>(tmX, tmDY, p, plan.grid, stream); break;
+    case 128: rc = launch_wgrad<128, 6>(tmX, tmDY, p, plan.grid, stream); break;
+    default: rc = launch_wgrad<256, 4>(tmX, tmDY, p, plan.grid, stream); break;
+  }
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(kh) * kw * cin * cout;
+  const int64_t n4 = total / 4;  // cout % 8 == 0
+  int blocks = static_cast<int>(ceil_div64(n4, 256));
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, dw, n4, p.splits, scale, beta);
+  GANB_CHECK_LAUNCH("splitk_reduce_kernel");
+  return 0;
+}
