@@ -1,0 +1,283 @@
+"""SNGAN CIFAR-10 ResNet (conditional) on the B200 layer ops: same Generator / Discriminator / losses / optimiser
+as the reference script SNGAN/gan_cifar_resnet.py, restated as an eager step that can be captured into CUDA graphs.
+
+Reference structure kept:
+  * constants (:38-68), Generator (:237-263), Discriminator (:266-313), hinge losses (:376-378, :492),
+    LR decay (:454-457), two Adam(beta1=0, beta2=0.9) optimisers (:521-526), loop order (:599-620):
+    G-step (skipped at iteration 0) then N_CRITIC D-steps;
+  * the two per-device towers (DEVICES always has two entries, :70-75) are batched into one call whose batch
+    statistics are computed per tower (`stat_towers(2)`), which is what the reference's per-tower tf.nn.moments do.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import functional as F
+from .. import kernels as K
+from ..common import resnet_block as rb
+from ..common.ops import conv2d as conv2d_ops
+from ..common.ops import embedding as embedding_ops
+from ..common.ops import linear as linear_ops
+from ..framework import Var, get_store
+
+BATCH_SIZE = 64  # Critic batch size
+GEN_BS_MULTIPLE = 2  # Generator batch size, as a multiple of BATCH_SIZE
+ITERS = 100000
+DIM_G = 128
+DIM_D = 128
+NORMALIZATION_G = True
+NORMALIZATION_D = False
+OUTPUT_DIM = 3072
+LR = 0.0002
+DECAY = True
+N_CRITIC = 5
+CONDITIONAL = True
+ACGAN = False
+VOCAB_SIZE = 10
+EMBEDDING_DIM = 300
+N_TOWERS = 2  # len(DEVICES) is always 2 in the reference (:73-75)
+
+BF16 = torch.bfloat16
+
+
+def _normalize_kind(name, labels):
+    """The script's own Normalize dispatch (gan_cifar_resnet.py:88-109)."""
+    if not CONDITIONAL:
+        labels = None
+    if CONDITIONAL and ACGAN and ('D.' in name):
+        labels = None
+    if ('D.' in name) and NORMALIZATION_D:
+        raise NotImplementedError('layer_norm in D (NORMALIZATION_D=True) is not built')
+    elif ('G.' in name) and NORMALIZATION_G:
+        return 'cbn' if labels is not None else 'bn'
+    return None
+
+
+def _block(inputs, input_dim, output_dim, filter_size, name, labels=None, **kw):
+    return rb.ResidualBlock(inputs, input_dim, output_dim, filter_size, name, labels=labels,
+                            normalize_kind=lambda nm: _normalize_kind(nm, labels), **kw)
+
+
+def Generator(n_samples_, labels, noise=None, reuse=False):
+    """gan_cifar_resnet.py:237-263. Returns Var [n, 3072] (NHWC-flattened images in (-1, 1))."""
+    store = get_store()
+    with store.variable_scope("Generator", reuse=reuse):
+        if noise is None:
+            noise = torch.randn(n_samples_, 128, device=store.device)
+        noise = F.as_var(noise)
+        output = linear_ops.Linear(noise, 128, 4 * 4 * DIM_G * 8, 'G.Input')
+        output = F.reshape(output, (-1, 4, 4, DIM_G * 8))
+        output = _block(output, DIM_G * 8, DIM_G * 2, 3, 'G.Block.1', resample='up', labels=labels, biases=True)
+        output = _block(output, DIM_G * 2, DIM_G * 2, 3, 'G.Block.2', resample='up', labels=labels, biases=True)
+        output = _block(output, DIM_G * 2, DIM_G * 2, 3, 'G.Block.3', resample='up', labels=labels, biases=True)
+        output, _ = rb._norm_act('G.OutputNorm', output, labels, _normalize_kind('G.OutputNorm', labels), 'relu')
+        output = conv2d_ops.Conv2D(output, DIM_G * 2, 3, 3, 1, 'G.Output', he_init=False)
+        output = F.activation(output, 'tanh')
+        return F.reshape(output, (-1, OUTPUT_DIM))
+
+
+def Discriminator(inputs, labels, update_collection=None, reuse=False):
+    """gan_cifar_resnet.py:266-313. Returns (output_wgan Var [n], None)."""
+    store = get_store()
+    with store.variable_scope("Discriminator", reuse=reuse):
+        output = F.reshape(F.as_var(inputs), (-1, 32, 32, 3))
+        output = rb.OptimizedResBlockDisc1(output, DIM_D=DIM_D, spectral_normed=True,
+                                           update_collection=update_collection, biases=True,
+                                           name_prefix='D.Block.1')
+        # embedding labels, and concatenate to 'output'.
+        embedding_y = embedding_ops.embed_y(labels, VOCAB_SIZE, EMBEDDING_DIM)
+        embedding_y = linear_ops.Linear(embedding_y, EMBEDDING_DIM, DIM_D, 'D.Embedding_y', spectral_normed=True,
+                                        update_collection=update_collection, biases=True)  # (N, DIM_D)
+        pre = F.concat_label_map(output, embedding_y, act='relu')
+        output = _block(None, DIM_D * 2, DIM_D, 3, 'D.Block.2', spectral_normed=True,
+                        update_collection=update_collection, resample='down', labels=labels, biases=True,
+                        pre_activated=pre)
+        output = _block(output, DIM_D, DIM_D, 3, 'D.Block.3', spectral_normed=True,
+                        update_collection=update_collection, resample=None, labels=labels, biases=True)
+        output = _block(output, DIM_D, DIM_D, 3, 'D.Block.4', spectral_normed=True,
+                        update_collection=update_collection, resample=None, labels=labels, biases=True)
+        output = F.act_mean_hw(output, 'relu')
+        output_wgan = linear_ops.Linear(output, DIM_D, 1, 'D.Output', spectral_normed=True,
+                                        update_collection=update_collection)
+        output_wgan = F.reshape(output_wgan, (-1,))
+        return output_wgan, None
+
+
+def lr_decay(iteration: int) -> float:
+    """gan_cifar_resnet.py:454-457"""
+    if not DECAY:
+        return 1.0
+    return max(0.0, 1.0 - iteration / 100000.0) if iteration < 50000 else 0.5
+
+
+class AdamState:
+    """tf.train.AdamOptimizer(lr, beta1=0., beta2=0.9) over one network's flat buffers."""
+
+    def __init__(self, flat, beta1=0.0, beta2=0.9, eps=1e-8):
+        self.flat, self.beta1, self.beta2, self.eps = flat, beta1, beta2, eps
+        self.t = 0
+        self.lr_t = torch.zeros(1, dtype=torch.float32, device=flat.params.device)
+        self._host = torch.zeros(1, dtype=torch.float32)
+        if flat.params.is_cuda:
+            self._host = self._host.pin_memory()
+
+    def set_lr(self, lr: float) -> None:
+        """Advances the step count and uploads lr_t = lr * sqrt(1-b2^t) / (1-b1^t)."""
+        self.t += 1
+        val = lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+        self._host[0] = val
+        self.lr_t.copy_(self._host, non_blocking=True)
+
+    def apply(self, grad_scale: float = 1.0) -> None:
+        K.adam(self.flat.params, self.flat.grads, self.flat.m, self.flat.v, self.lr_t, self.beta1, self.beta2,
+               self.eps, grad_scale)
+
+
+class Trainer:
+    """Builds the variables in the reference's graph-construction order and runs D / G training steps."""
+
+    def __init__(self, batch_size: int = BATCH_SIZE, seed: int | None = 0, store=None, world_size: int = 1,
+                 grad_allreduce=None):
+        self.store = store or get_store()
+        self.batch = batch_size
+        self.gen_batch = GEN_BS_MULTIPLE * batch_size
+        self.world_size = world_size
+        self.grad_allreduce = grad_allreduce  # callable(flat_grads) -> None, sums over ranks (NCCL)
+        dev = self.store.device
+        if seed is not None:
+            np.random.seed(seed)
+        self._build()
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        # static step inputs (also the CUDA-graph placeholders)
+        self.real_int = torch.zeros(batch_size, OUTPUT_DIM, **i32)
+        self.real_labels = torch.zeros(batch_size, **i32)
+        self.deq_noise = torch.zeros(batch_size, OUTPUT_DIM, **f32)
+        self.z_d = torch.zeros(batch_size, 128, **f32)
+        self.z_g = torch.zeros(self.gen_batch, 128, **f32)
+        self.fake_labels = torch.zeros(self.gen_batch, **i32)
+        self.d_in = torch.zeros(2 * batch_size, OUTPUT_DIM, **f32)
+        self.d_labels = torch.zeros(2 * batch_size, **i32)
+        self.d_loss = torch.zeros(1, **f32)
+        self.g_loss = torch.zeros(1, **f32)
+        self.gen_opt = AdamState(self.store.flat['Generator'])
+        self.disc_opt = AdamState(self.store.flat['Discriminator'])
+        self._graphs = {}
+
+    # ------------------------------------------------------------------------------------------ build
+    def _build(self):
+        """Variable creation in reference order: G tower 0, G tower 1 (reuse), D, then the
+        G-step towers (reuse) -- every reuse call draws and discards its NumPy initial values."""
+        st = self.store
+        dev = st.device
+        z = torch.zeros(2, 128, device=dev)
+        lab = torch.zeros(2, dtype=torch.int32, device=dev)
+        with st.building():
+            fake = Generator(2, lab, noise=z)
+            Generator(2, lab, noise=z, reuse=True)
+            Discriminator(fake, lab, update_collection="NO_OPS")
+            for _ in range(N_TOWERS):
+                Discriminator(Generator(2, lab, noise=z, reuse=True), lab, update_collection="NO_OPS", reuse=True)
+        st.finalize()
+
+    # ------------------------------------------------------------------------------------------ inputs
+    def set_real_batch(self, data_int, labels):
+        """data_int: int32 [B, 3072] CHW-flattened pixels (host or device), labels int32 [B]."""
+        self.real_int.copy_(torch.as_tensor(data_int, dtype=torch.int32), non_blocking=True)
+        self.real_labels.copy_(torch.as_tensor(labels, dtype=torch.int32), non_blocking=True)
+
+    def sample_noise(self):
+        """tf.random_normal / tf.random_uniform stand-ins (gan_cifar_resnet.py:240, 335, 467)."""
+        self.z_d.normal_()
+        self.z_g.normal_()
+        self.deq_noise.uniform_(0.0, 1.0 / 128)
+        self.fake_labels.copy_((torch.rand(self.gen_batch, device=self.store.device) * 10).to(torch.int32))
+
+    # ------------------------------------------------------------------------------------------ steps
+    def _d_body(self):
+        st = self.store
+        b = self.batch
+        st.zero_grad('Discriminator')
+        with st.stat_towers(N_TOWERS):
+            fake = Generator(b, self.real_labels, noise=self.z_d, reuse=True)  # no tape: var_list = disc_params
+        real = K.preprocess_real(self.real_int, self.deq_noise, b, 1024)
+        self.d_in[:b].copy_(real)
+        self.d_in[b:].copy_(fake.data)
+        self.d_labels[:b].copy_(self.real_labels)
+        self.d_labels[b:].copy_(self.real_labels)
+        with st.gradient_tape() as tape, st.frozen_scopes('Generator'):
+            disc_all, _ = Discriminator(Var(self.d_in), self.d_labels, update_collection=None, reuse=True)
+            loss = F.gan_loss(disc_all, 'hinge_d', n_real=b)
+            tape.backward(loss)
+        self.d_loss.copy_(loss.data)
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(st.flat['Discriminator'].grads)
+        self.disc_opt.apply(1.0 / self.world_size)
+        st.bump('Discriminator')
+
+    def _g_body(self):
+        st = self.store
+        st.zero_grad('Generator')
+        with st.gradient_tape() as tape, st.frozen_scopes('Discriminator'):
+            with st.stat_towers(N_TOWERS):
+                fake = Generator(self.gen_batch, self.fake_labels, noise=self.z_g, reuse=True)
+            disc_fake, _ = Discriminator(fake, self.fake_labels, update_collection="NO_OPS", reuse=True)
+            loss = F.gan_loss(disc_fake, 'gen')
+            tape.backward(loss)
+        self.g_loss.copy_(loss.data)
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(st.flat['Generator'].grads)
+        self.gen_opt.apply(1.0 / self.world_size)
+        st.bump('Generator')
+
+    def _invalidate_caches(self):
+        for g in self.store.sn_groups.values():
+            g.valid_for = None
+            g.fresh_for = None
+        for g in self.store.pack_groups.values():
+            g.valid_for = None
+
+    def capture(self):
+        """Captures the D-step and the G-step into CUDA graphs (static shapes; launch latency is first-order at
+        batch 64).  Must be called after at least one eager D-step and G-step (all workspaces / tables exist)."""
+        if self.grad_allreduce is not None:
+            raise RuntimeError("graph capture with an in-step collective is not supported; run eagerly")
+        for name, body in (("d", self._d_body), ("g", self._g_body)):
+            self._invalidate_caches()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[name] = g
+        self._invalidate_caches()
+
+    def d_step(self, iteration: int):
+        self.disc_opt.set_lr(LR * lr_decay(iteration))
+        if "d" in self._graphs:
+            self._graphs["d"].replay()
+        else:
+            self._d_body()
+        return self.d_loss
+
+    def g_step(self, iteration: int):
+        self.gen_opt.set_lr(LR * lr_decay(iteration))
+        if "g" in self._graphs:
+            self._graphs["g"].replay()
+        else:
+            self._g_body()
+        return self.g_loss
+
+    def train_iteration(self, iteration: int, batches):
+        """One reference iteration (gan_cifar_resnet.py:599-620): G-step if iteration > 0, then N_CRITIC D-steps.
+        `batches` yields (data_int, labels)."""
+        if iteration > 0:
+            self.sample_noise()
+            self.g_step(iteration)
+        for _ in range(N_CRITIC):
+            data, labels = next(batches)
+            self.set_real_batch(data, labels)
+            self.sample_noise()
+            self.d_step(iteration)
+        return self.d_loss, self.g_loss

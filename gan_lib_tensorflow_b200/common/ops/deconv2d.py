@@ -1,0 +1,50 @@
+"""Transposed convolution with the reference's signature (common/ops/deconv2d.py:29-118).
+
+The reference has no call-site for it; the op is the data gradient of a stride-2 convolution, which needs the
+strided tensor-core path that is not built yet.  Variables are created with the reference's
+initialisation so that checkpoints keep their names and shapes; the arithmetic raises."""
+from __future__ import annotations
+
+import numpy as np
+
+from ...framework import get_store
+
+_default_weightnorm = False
+_weights_stdev = None
+
+
+def enable_default_weightnorm():
+    global _default_weightnorm
+    _default_weightnorm = True
+
+
+def set_weights_stdev(weights_stdev):
+    global _weights_stdev
+    _weights_stdev = weights_stdev
+
+
+def unset_weights_stdev():
+    global _weights_stdev
+    _weights_stdev = None
+
+
+def Deconv2D(inputs, in_channels, output_channels, filter_size, stride=2, padding='SAME', he_init=True,
+             weight_norm=None, gain=1., mask_type=None, biases=True, name='Deconv2D'):
+    store = get_store()
+    with store.variable_scope(name):
+        if mask_type is not None:
+            raise Exception('Unsupported configuration in Deconv2D!')
+        if stride != 2:
+            raise ValueError('Deconv2D always produces a 2x output (deconv2d.py:99-100); stride must be 2')
+        fan_in = in_channels * filter_size ** 2 / (stride ** 2)
+        fan_out = output_channels * filter_size ** 2
+        stdev = np.sqrt((4. if he_init else 2.) / (fan_in + fan_out))
+        if _weights_stdev is not None:
+            stdev = _weights_stdev
+        store.get_variable(name='Filters', initializer=lambda _s: np.random.uniform(
+            low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3),
+            size=(filter_size, filter_size, output_channels, in_channels)).astype('float32') * np.float32(gain))
+        if biases:
+            store.get_variable(name='Biases', shape=[output_channels, ],
+                               initializer=lambda s: np.zeros(s, dtype='float32'))
+        raise NotImplementedError('Deconv2D arithmetic needs the stride-2 dgrad kernel (SURVEY 8(f)); not built yet')

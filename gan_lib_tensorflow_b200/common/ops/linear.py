@@ -1,0 +1,83 @@
+"""Dense layer with the reference's signature (common/ops/linear.py:38-182)."""
+from __future__ import annotations
+
+import numpy as np
+
+from ... import functional as F
+from ...framework import get_store
+from .conv2d import _memo
+from .sn import spectral_normed_weight
+
+_default_weightnorm = False
+
+
+def disable_default_weightnorm():
+    global _default_weightnorm
+    _default_weightnorm = False
+
+
+_weights_stdev = None
+
+
+def unset_weights_stdev():
+    global _weights_stdev
+    _weights_stdev = None
+
+
+def Linear(inputs, input_dim, output_dim, name,
+           spectral_normed=False, update_collection=None, reuse=False, inputs_norm=False,
+           biases=True, initialization=None, weightnorm=None, gain=1.):
+    """
+    initialization: None, `lecun`, 'glorot', `he`, 'glorot_he', `orthogonal`, `("uniform", range)`
+    """
+    store = get_store()
+    inputs = F.as_var(inputs)
+    with store.variable_scope(name):
+        if inputs_norm:
+            raise NotImplementedError('inputs_norm is not wired yet (PGGAN, SURVEY 8(f))')
+
+        def uniform(stdev, size):
+            if _weights_stdev is not None:
+                stdev = _weights_stdev
+            return np.random.uniform(low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3), size=size).astype('float32')
+
+        def draw():
+            if initialization == 'lecun':
+                wv = uniform(np.sqrt(1. / input_dim), (input_dim, output_dim))
+            elif initialization == 'glorot' or initialization == 'xavier' or (initialization is None):
+                wv = uniform(np.sqrt(2. / (input_dim + output_dim)), (input_dim, output_dim))
+            elif initialization == 'he':
+                wv = uniform(np.sqrt(2. / input_dim), (input_dim, output_dim))
+            elif initialization == 'glorot_he':
+                wv = uniform(np.sqrt(4. / (input_dim + output_dim)), (input_dim, output_dim))
+            elif initialization == 'orthogonal':
+                a = np.random.normal(0.0, 1.0, (input_dim, output_dim))
+                u, _, v = np.linalg.svd(a, full_matrices=False)
+                q = u if u.shape == (input_dim, output_dim) else v
+                wv = q.reshape((input_dim, output_dim)).astype('float32')
+            elif initialization[0] == 'uniform':
+                wv = np.random.uniform(low=-initialization[1], high=initialization[1],
+                                       size=(input_dim, output_dim)).astype('float32')
+            else:
+                raise Exception('Invalid initialization!')
+            return wv * np.float32(gain)
+
+        weight_values = _memo(draw)
+        weight = store.get_variable(name='W', initializer=lambda _s: weight_values())
+        if weightnorm is None:
+            weightnorm = _default_weightnorm
+        if weightnorm:
+            raise NotImplementedError('weight-norm is not built (SURVEY 8(f) rank 4)')
+        sn_entry = None
+        if spectral_normed:
+            sn_entry = spectral_normed_weight(weight, update_collection=update_collection).entry
+        _biases = None
+        if biases:
+            _biases = store.get_variable(name='b', shape=[output_dim, ],
+                                         initializer=lambda s: np.zeros(s, dtype='float32'))
+        if len(inputs.shape) == 2:
+            return F.linear(inputs, weight, _biases, sn=sn_entry)
+        lead = inputs.shape[:-1]
+        flat = F.reshape(inputs, (-1, input_dim))
+        result = F.linear(flat, weight, _biases, sn=sn_entry)
+        return F.reshape(result, tuple(lead) + (output_dim,))

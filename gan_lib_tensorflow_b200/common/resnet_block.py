@@ -1,0 +1,188 @@
+"""Residual-block library with the reference's names and arguments (common/resnet_block.py:20-184).
+
+Same graph as the reference (pre-activation ResNet blocks; sub-layers named name+'.Shortcut' / '.N1' / '.Conv1' /
+'.N2' / '.Conv2'), scheduled for B200:
+  * Normalize + nonlinearity (+ nearest upsample) + bf16 cast run as one bandwidth-bound kernel whose output is
+    directly the tensor-core operand of the next convolution;
+  * 1x1 shortcut convolutions commute with nearest-upsampling / mean-pooling and are evaluated at the low
+    resolution (4x fewer FLOPs, identical dot products);
+  * the residual sum is folded into the epilogue of Conv2, and one mean-pool serves shortcut + main path.
+"""
+from __future__ import annotations
+
+import functools
+
+import torch
+
+from .. import functional as F
+from ..framework import Var, get_store
+from . import ops as _ops  # noqa: F401  (keeps `lib.ops.<module>` attribute access working)
+from .ops import conv2d as _conv2d
+from .ops import normalization as _norm
+
+NORMALIZATION_G = True
+NORMALIZATION_D = True
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def nonlinearity(x, activation_fn='relu', leakiness=0.2):
+    """common/resnet_block.py:24-29 (the reference silently returns None for unknown names; this raises)."""
+    if activation_fn == 'relu':
+        return F.activation(F.as_var(x), 'relu')
+    if activation_fn == 'lrelu':
+        assert 0 < leakiness <= 1, "leakiness must be <= 1"
+        if leakiness != 0.2:
+            raise NotImplementedError('only leakiness=0.2 (the value every reference call-site uses) is built')
+        return F.activation(F.as_var(x), 'lrelu')
+    raise ValueError('unknown activation_fn {!r}'.format(activation_fn))
+
+
+def _normalize_kind(name, labels, spectral_normed):
+    """Dispatch of common/resnet_block.py:32-50 on the SUBSTRING of the layer name."""
+    if ('D.' in name) and NORMALIZATION_D:
+        return None if spectral_normed else 'bn'
+    elif ('G.' in name) and NORMALIZATION_G:
+        return 'cbn' if labels is not None else 'bn'
+    return None
+
+
+def _norm_act(name, inputs, labels, kind, act, upsample=False, want_raw=False, out_dtype=BF16):
+    """Normalize(name, inputs) followed by nonlinearity(), fused. Returns (out, raw_bf16_or_None)."""
+    store = get_store()
+    with store.variable_scope(name):
+        if kind == 'cbn':
+            res = _norm.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=10, act=act,
+                                       upsample=upsample, out_dtype=out_dtype, want_raw=want_raw)
+        elif kind == 'bn':
+            res = _norm.batch_norm(inputs, fused=True, act=act, upsample=upsample, out_dtype=out_dtype,
+                                   want_raw=want_raw)
+        else:
+            return F.norm_act(inputs, stats=None, act=act, upsample=upsample, out_dtype=out_dtype, want_raw=want_raw)
+    return res if want_raw else (res, None)
+
+
+def Normalize(name, inputs, labels=None, spectral_normed=True):
+    """common/resnet_block.py:32-50, un-fused (fp32 in, fp32 out)."""
+    inputs = F.as_var(inputs)
+    kind = _normalize_kind(name, labels, spectral_normed)
+    if kind is None:
+        with get_store().variable_scope(name):
+            return inputs
+    out, _ = _norm_act(name, inputs, labels, kind, None, out_dtype=F32)
+    return out
+
+
+def ConvMeanPool(inputs, output_dim, filter_size=3, stride=1, name=None,
+                 spectral_normed=False, update_collection=None, inputs_norm=False,
+                 he_init=True, biases=True):
+    """common/resnet_block.py:53-64"""
+    inputs = F.as_var(inputs)
+    output = _conv2d.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name,
+                            spectral_normed=spectral_normed, update_collection=update_collection,
+                            inputs_norm=inputs_norm, he_init=he_init, biases=biases, out_grad_dtype=BF16)
+    return F.meanpool2(output)
+
+
+def MeanPoolConv(inputs, output_dim, filter_size=3, stride=1, name=None,
+                 spectral_normed=False, update_collection=None, inputs_norm=False,
+                 he_init=True, biases=True):
+    """common/resnet_block.py:67-80"""
+    inputs = F.as_var(inputs)
+    output = F.meanpool2(inputs if inputs.dtype == F32 else F.cast(inputs, F32))
+    return _conv2d.Conv2D(output, output.shape[-1], output_dim, filter_size, stride, name,
+                          spectral_normed=spectral_normed, update_collection=update_collection,
+                          inputs_norm=inputs_norm, he_init=he_init, biases=biases)
+
+
+def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None,
+                 spectral_normed=False, update_collection=None, inputs_norm=False,
+                 he_init=True, biases=True):
+    """common/resnet_block.py:83-97"""
+    inputs = F.as_var(inputs)
+    output = F.upsample2(inputs, out_dtype=BF16 if inputs.shape[-1] > 8 else None)
+    return _conv2d.Conv2D(output, output.shape[-1], output_dim, filter_size, stride, name,
+                          spectral_normed=spectral_normed, update_collection=update_collection,
+                          inputs_norm=inputs_norm, he_init=he_init, biases=biases)
+
+
+def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
+                  spectral_normed=False, update_collection=None, inputs_norm=False,
+                  resample=None, labels=None, biases=True, activation_fn='relu',
+                  normalize_kind=None, pre_activated=None):
+    """resample: None, 'down', or 'up' -- common/resnet_block.py:100-156.
+
+    normalize_kind overrides the name-based Normalize dispatch (used by the SNGAN scripts' own Normalize).
+    pre_activated = (raw_bf16, act_bf16) lets a producer that already emitted both operands (the label-map
+    concat of D) skip the block's first activation pass."""
+    if resample not in (None, 'down', 'up'):
+        raise Exception('invalid resample value')
+    if activation_fn not in ('relu', 'lrelu'):
+        raise ValueError('unknown activation_fn {!r}'.format(activation_fn))
+    conv = functools.partial(_conv2d.Conv2D, filter_size=filter_size, spectral_normed=spectral_normed,
+                             update_collection=update_collection, inputs_norm=inputs_norm, biases=biases)
+    kind = normalize_kind if normalize_kind is not None else (
+        lambda nm: _normalize_kind(nm, labels, spectral_normed))
+    identity_shortcut = (output_dim == input_dim and resample is None)
+
+    # ---- N1 + nonlinearity (+ upsample), and the raw bf16 copy feeding the 1x1 shortcut
+    if pre_activated is not None:
+        raw, a1 = pre_activated
+        x32 = None
+    else:
+        x32 = F.as_var(inputs)
+        a1, raw = _norm_act(name + '.N1', x32, labels, kind(name + '.N1'), activation_fn,
+                            upsample=(resample == 'up'), want_raw=not identity_shortcut)
+
+    # ---- shortcut (reference order: the shortcut variables are created before Conv1's)
+    if identity_shortcut:
+        shortcut = x32
+    else:
+        # ConvMeanPool / UpsampleConv / Conv2D with a 1x1 filter, he_init=False (resnet_block.py:123-127)
+        shortcut = _conv2d.Conv2D(raw, input_dim, output_dim, 1, 1, name + '.Shortcut',
+                                  spectral_normed=spectral_normed, update_collection=update_collection,
+                                  inputs_norm=inputs_norm, he_init=False, biases=biases,
+                                  out_grad_dtype=BF16 if resample == 'down' else None)
+        if resample == 'up':
+            shortcut = F.upsample2(shortcut)  # conv1x1(upsample(x)) == upsample(conv1x1(x))
+
+    # ---- Conv1
+    mid_dim = input_dim if resample == 'down' else output_dim
+    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True)
+
+    # ---- N2 + nonlinearity
+    a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn)
+
+    # ---- Conv2 (+ residual in the epilogue) [+ mean-pool of the sum]
+    if resample == 'down':
+        t = conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut,
+                 out_grad_dtype=BF16)
+        return F.meanpool2(t)  # meanpool(conv2) + meanpool(shortcut) == meanpool(conv2 + shortcut)
+    return conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut)
+
+
+def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
+                           spectral_normed=False, update_collection=None, inputs_norm=False,
+                           biases=True, name_prefix='D.DownBlock.1'):
+    """common/resnet_block.py:159-184.  name_prefix='D.Block.1' gives the SNGAN script's copy
+    (SNGAN/gan_cifar_resnet.py:212-234)."""
+    inputs = F.as_var(inputs)
+    cin = inputs.shape[-1]
+    shortcut = MeanPoolConv(inputs=inputs, output_dim=DIM_D, filter_size=1, name=name_prefix + '.Shortcut',
+                            spectral_normed=spectral_normed, update_collection=update_collection,
+                            inputs_norm=inputs_norm, he_init=False, biases=biases)
+    output = _conv2d.Conv2D(inputs, cin, DIM_D, 3, 1, name_prefix + '.Conv1', spectral_normed=spectral_normed,
+                            update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
+                            biases=biases)
+    output, _ = F.norm_act(output, stats=None, act=activation_fn, out_dtype=BF16)
+    output = _conv2d.Conv2D(output, DIM_D, DIM_D, 3, 1, name_prefix + '.Conv2', spectral_normed=spectral_normed,
+                            update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
+                            biases=biases, out_grad_dtype=BF16)
+    return F.meanpool2(output, addend=shortcut)
+
+
+# ######## ######## PGGAN ######## ######## #
+def get_dim(stage):
+    """common/resnet_block.py:188-189 (returns a float under Python 3 in the reference; int here)."""
+    return int(min(2048 / (2 ** stage), 512))

@@ -1,0 +1,1058 @@
+// Bandwidth-bound kernels of the hot path: batch statistics, (conditional) normalise + activation + resample
+// forward/backward, pooling, casts, bias gradients, label-map concat, global pooling, losses, Adam.
+// All activations are NHWC; float4 / bf16x4 vectorised along the channel dimension (C % 4 == 0 fast path).
+//
+// Reference call-sites replaced: common/ops/normalization.py:8-59,105-140 (moments, batch_normalization,
+// embedding_lookup of gamma/beta), common/resnet_block.py:24-29,62-63,71-72,87-88 (relu / leaky relu,
+// mean-pool, nearest upsample), SNGAN/gan_cifar_resnet.py:282-284,301,334-337,376-378,492,521-526.
+#include "host_common.h"
+
+#include <cuda_bf16.h>
+
+namespace ganb {
+
+// ------------------------------------------------------------------------------------------------ helpers
+struct alignas(8) bf16x4 {
+  __nv_bfloat162 lo, hi;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const bf16x4 v = *reinterpret_cast<const bf16x4*>(p);
+  const float2 a = __bfloat1622float2(v.lo), b = __bfloat1622float2(v.hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  bf16x4 o;
+  o.lo = __floats2bfloat162_rn(v.x, v.y);
+  o.hi = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<bf16x4*>(p) = o;
+}
+__device__ __forceinline__ float act_f(float v, int act) {
+  if (act == GANB_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == GANB_ACT_LRELU) return v >= 0.f ? v : 0.2f * v;
+  if (act == GANB_ACT_TANH) return tanhf(v);
+  return v;
+}
+// derivative of the activation expressed with the PRE-activation value y
+__device__ __forceinline__ float dact_f(float y, int act) {
+  if (act == GANB_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == GANB_ACT_LRELU) return y >= 0.f ? 1.f : 0.2f;
+  if (act == GANB_ACT_TANH) { const float t = tanhf(y); return 1.f - t * t; }
+  return 1.f;
+}
+#define F4_OP(r, a, expr_x, expr_y, expr_z, expr_w) \
+  float4 r = make_float4(expr_x, expr_y, expr_z, expr_w)
+
+static inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+  int64_t b = ceil_div64(work_items, threads);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * max_blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------------------------------------ bn stats
+// partial[(g*chunks + chunk)*2*C + {0,1}*C + c] = sum / sum of squares over the chunk's rows.
+__global__ void __launch_bounds__(256)
+bn_stats_partial_kernel(const float* __restrict__ x, int rows_per_group, int c, int chunks, int rows_per_chunk,
+                        float* __restrict__ partial) {
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int v = c >> 2;                          // float4 columns
+  const int lanes = max(1, 256 / min(v, 256));   // row lanes per column block
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(rows_per_group, r0 + rows_per_chunk);
+  const float* xg = x + static_cast<int64_t>(g) * rows_per_group * c;
+  __shared__ float4 sh_s[256], sh_q[256];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    if (col < v && ry < lanes) {
+      for (int r = r0 + ry; r < r1; r += lanes) {
+        const float4 a = ld4(xg + static_cast<int64_t>(r) * c + col * 4);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        q.x += a.x * a.x; q.y += a.y * a.y; q.z += a.z * a.z; q.w += a.w * a.w;
+      }
+    }
+    sh_s[threadIdx.x] = s;
+    sh_q[threadIdx.x] = q;
+    __syncthreads();
+    if (ry == 0 && col < v) {
+      for (int l = 1; l < lanes; ++l) {
+        const float4 a = sh_s[l * cols_per_pass + cx], b = sh_q[l * cols_per_pass + cx];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+      }
+      float* out = partial + (static_cast<int64_t>(g) * chunks + chunk) * 2 * c;
+      st4(out + col * 4, s);
+      st4(out + c + col * 4, q);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int c, int groups, int chunks,
+                                         float inv_count, float eps, float* __restrict__ mean,
+                                         float* __restrict__ rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * c) return;
+  const int g = i / c, ch = i - g * c;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    const float* p = partial + (static_cast<int64_t>(g) * chunks + k) * 2 * c;
+    s += p[ch];
+    q += p[c + ch];
+  }
+  const double m = s * inv_count;
+  double var = q * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = static_cast<float>(m);
+  rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ------------------------------------------------------------------------------------------------ norm+act fwd
+struct NormActFwd {
+  const float* x;
+  int n, h, w, c;
+  const float* mean; const float* rstd; int groups;       // mean == nullptr: no normalisation
+  const float* gamma; const float* beta; const int* labels;  // tables [n_labels, c]; labels == nullptr: row 0
+  int act, upsample;
+  void* out; int out_bf16; int out_cstride;               // channel stride of the output pixel (>= c)
+  __nv_bfloat16* out_raw; int raw_cstride;                 // optional bf16 copy of x at input resolution
+};
+
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p) {
+  const int v = p.c >> 2;
+  const int64_t total = static_cast<int64_t>(p.n) * p.h * p.w * v;
+  const int n_per_group = p.n / p.groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int wi = static_cast<int>(pix % p.w);
+    const int hi = static_cast<int>((pix / p.w) % p.h);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(p.w) * p.h));
+    const float4 a = ld4(p.x + pix * p.c + c4);
+    float4 y = a;
+    if (p.mean) {
+      const int g = ni / n_per_group;
+      const float4 m = ld4(p.mean + g * p.c + c4), r = ld4(p.rstd + g * p.c + c4);
+      float4 ga = make_float4(1, 1, 1, 1), be = make_float4(0, 0, 0, 0);
+      if (p.gamma) {
+        const int row = p.labels ? __ldg(p.labels + ni) : 0;
+        ga = ld4(p.gamma + static_cast<int64_t>(row) * p.c + c4);
+        be = ld4(p.beta + static_cast<int64_t>(row) * p.c + c4);
+      }
+      // tf.nn.batch_normalization: inv = rsqrt(var+eps)*gamma; y = x*inv + (beta - mean*inv)
+      const float4 inv = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
+      y = make_float4(a.x * inv.x + (be.x - m.x * inv.x), a.y * inv.y + (be.y - m.y * inv.y),
+                      a.z * inv.z + (be.z - m.z * inv.z), a.w * inv.w + (be.w - m.w * inv.w));
+    }
+    y = make_float4(act_f(y.x, p.act), act_f(y.y, p.act), act_f(y.z, p.act), act_f(y.w, p.act));
+    if (p.out_raw) st4(p.out_raw + pix * p.raw_cstride + c4, a);
+    if (!p.upsample) {
+      const int64_t o = pix * p.out_cstride + c4;
+      if (p.out_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.out) + o, y);
+      else st4(reinterpret_cast<float*>(p.out) + o, y);
+    } else {
+      const int ow = 2 * p.w;
+      const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int64_t o = (base + dy * ow + dx) * p.out_cstride + c4;
+          if (p.out_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.out) + o, y);
+          else st4(reinterpret_cast<float*>(p.out) + o, y);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ norm+act bwd
+struct NormActBwd {
+  const float* x;                 // forward input (pre-normalisation), [n,h,w,c]
+  const void* dz; int dz_bf16; int dz_cstride;   // gradient of the forward OUTPUT ([n,(2)h,(2)w,*])
+  int n, h, w, c;
+  const float* mean; const float* rstd; int groups;
+  const float* gamma; const float* beta; const int* labels;
+  int act, upsample;
+  // reduce outputs: per-sample sums
+  float* part;    // [n][chunks][2][c]
+  int chunks, pix_per_chunk;
+  // apply inputs/outputs
+  const float* s1; const float* s2;   // [groups, c]  sum(dxhat), sum(dxhat*xhat)
+  float inv_count;
+  const float* add;                   // optional fp32 tensor added to dx (second gradient path)
+  void* dx; int dx_bf16;
+};
+
+// returns dL/dy (gradient w.r.t. the normalised, pre-activation value) and xhat for one float4 of channels
+__device__ __forceinline__ void norm_act_bwd_point(const NormActBwd& p, int ni, int hi, int wi, int c4, int g,
+                                                   float4 a, float4& dy, float4& xhat, float4& ga) {
+  // upstream gradient (sum over the 2x2 replicas when the forward upsampled)
+  float4 dz;
+  if (!p.upsample) {
+    const int64_t o = ((static_cast<int64_t>(ni) * p.h + hi) * p.w + wi) * p.dz_cstride + c4;
+    dz = p.dz_bf16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.dz) + o) : ld4(reinterpret_cast<const float*>(p.dz) + o);
+  } else {
+    const int ow = 2 * p.w;
+    const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
+    dz = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+      for (int dxx = 0; dxx < 2; ++dxx) {
+        const int64_t o = (base + dyy * ow + dxx) * p.dz_cstride + c4;
+        const float4 t = p.dz_bf16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.dz) + o)
+                                   : ld4(reinterpret_cast<const float*>(p.dz) + o);
+        dz.x += t.x; dz.y += t.y; dz.z += t.z; dz.w += t.w;
+      }
+  }
+  float4 y = a;
+  xhat = a;
+  ga = make_float4(1, 1, 1, 1);
+  if (p.mean) {
+    const float4 m = ld4(p.mean + g * p.c + c4), r = ld4(p.rstd + g * p.c + c4);
+    xhat = make_float4((a.x - m.x) * r.x, (a.y - m.y) * r.y, (a.z - m.z) * r.z, (a.w - m.w) * r.w);
+    float4 be = make_float4(0, 0, 0, 0);
+    if (p.gamma) {
+      const int row = p.labels ? __ldg(p.labels + ni) : 0;
+      ga = ld4(p.gamma + static_cast<int64_t>(row) * p.c + c4);
+      be = ld4(p.beta + static_cast<int64_t>(row) * p.c + c4);
+    }
+    y = make_float4(xhat.x * ga.x + be.x, xhat.y * ga.y + be.y, xhat.z * ga.z + be.z, xhat.w * ga.w + be.w);
+  }
+  dy = make_float4(dz.x * dact_f(y.x, p.act), dz.y * dact_f(y.y, p.act), dz.z * dact_f(y.z, p.act),
+                   dz.w * dact_f(y.w, p.act));
+}
+
+// grid (chunks, n); per-sample partial sums A = sum dy, B = sum dy*xhat
+__global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(const NormActBwd p) {
+  const int ni = blockIdx.y, chunk = blockIdx.x;
+  const int v = p.c >> 2;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int hw = p.h * p.w;
+  const int p0 = chunk * p.pix_per_chunk, p1 = min(hw, p0 + p.pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  __shared__ float4 sh_a[256], sh_b[256];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float4 sa = make_float4(0, 0, 0, 0), sb = make_float4(0, 0, 0, 0);
+    if (col < v && ry < lanes) {
+      for (int px = p0 + ry; px < p1; px += lanes) {
+        const int hi = px / p.w, wi = px - hi * p.w;
+        const float4 a = ld4(p.x + (static_cast<int64_t>(ni) * hw + px) * p.c + col * 4);
+        float4 dy, xh, ga;
+        norm_act_bwd_point(p, ni, hi, wi, col * 4, g, a, dy, xh, ga);
+        sa.x += dy.x; sa.y += dy.y; sa.z += dy.z; sa.w += dy.w;
+        sb.x += dy.x * xh.x; sb.y += dy.y * xh.y; sb.z += dy.z * xh.z; sb.w += dy.w * xh.w;
+      }
+    }
+    sh_a[threadIdx.x] = sa;
+    sh_b[threadIdx.x] = sb;
+    __syncthreads();
+    if (ry == 0 && col < v) {
+      for (int l = 1; l < lanes; ++l) {
+        const float4 a = sh_a[l * cols_per_pass + cx], b = sh_b[l * cols_per_pass + cx];
+        sa.x += a.x; sa.y += a.y; sa.z += a.z; sa.w += a.w;
+        sb.x += b.x; sb.y += b.y; sb.z += b.z; sb.w += b.w;
+      }
+      float* out = p.part + (static_cast<int64_t>(ni) * p.chunks + chunk) * 2 * p.c;
+      st4(out + col * 4, sa);
+      st4(out + p.c + col * 4, sb);
+    }
+    __syncthreads();
+  }
+}
+
+// one thread per channel walks all samples in order: deterministic scatter of dgamma/dbeta by label and the
+// group sums S1 = sum gamma*A, S2 = sum gamma*B needed by the apply pass.
+__global__ void norm_act_bwd_finalize_kernel(const float* __restrict__ part, int n, int c, int chunks, int groups,
+                                             const float* __restrict__ gamma, const int* __restrict__ labels,
+                                             float* __restrict__ s1, float* __restrict__ s2,
+                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const int n_per_group = n / groups;
+  for (int g = 0; g < groups; ++g) {
+    float acc1 = 0.f, acc2 = 0.f;
+    for (int ni = g * n_per_group; ni < (g + 1) * n_per_group; ++ni) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < chunks; ++k) {
+        const float* q = part + (static_cast<int64_t>(ni) * chunks + k) * 2 * c;
+        a += q[ch];
+        b += q[c + ch];
+      }
+      float ga = 1.f;
+      if (gamma) {
+        const int row = labels ? labels[ni] : 0;
+        ga = gamma[static_cast<int64_t>(row) * c + ch];
+        if (dgamma) {
+          dgamma[static_cast<int64_t>(row) * c + ch] += b;
+          dbeta[static_cast<int64_t>(row) * c + ch] += a;
+        }
+      }
+      acc1 += ga * a;
+      acc2 += ga * b;
+    }
+    s1[g * c + ch] = acc1;
+    s2[g * c + ch] = acc2;
+  }
+}
+
+__global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(const NormActBwd p) {
+  const int v = p.c >> 2;
+  const int64_t total = static_cast<int64_t>(p.n) * p.h * p.w * v;
+  const int n_per_group = p.n / p.groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int wi = static_cast<int>(pix % p.w);
+    const int hi = static_cast<int>((pix / p.w) % p.h);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(p.w) * p.h));
+    const int g = ni / n_per_group;
+    const float4 a = ld4(p.x + pix * p.c + c4);
+    float4 dy, xh, ga;
+    norm_act_bwd_point(p, ni, hi, wi, c4, g, a, dy, xh, ga);
+    float4 dx = dy;
+    if (p.mean) {
+      const float4 r = ld4(p.rstd + g * p.c + c4);
+      const float4 t1 = ld4(p.s1 + g * p.c + c4), t2 = ld4(p.s2 + g * p.c + c4);
+      const float k = p.inv_count;
+      dx = make_float4(r.x * (ga.x * dy.x - k * t1.x - xh.x * k * t2.x), r.y * (ga.y * dy.y - k * t1.y - xh.y * k * t2.y),
+                       r.z * (ga.z * dy.z - k * t1.z - xh.z * k * t2.z), r.w * (ga.w * dy.w - k * t1.w - xh.w * k * t2.w));
+    }
+    if (p.add) {
+      const float4 q = ld4(p.add + pix * p.c + c4);
+      dx.x += q.x; dx.y += q.y; dx.z += q.z; dx.w += q.w;
+    }
+    if (p.dx_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.dx) + pix * p.c + c4, dx);
+    else st4(reinterpret_cast<float*>(p.dx) + pix * p.c + c4, dx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+// out[n,h/2,w/2,c] = mean of the 2x2 block (+ add[n,h/2,w/2,c])
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+meanpool2_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ add, TOut* __restrict__ out, int n, int ho,
+                     int wo, int c) {
+  const int v = c >> 2;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * v;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int wi = static_cast<int>(pix % wo);
+    const int hi = static_cast<int>((pix / wo) % ho);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(wo) * ho));
+    const int64_t base = ((static_cast<int64_t>(ni) * 2 * ho + 2 * hi) * (2 * wo) + 2 * wi) * c + c4;
+    const int64_t rowstride = static_cast<int64_t>(2 * wo) * c;
+    // same summation order as tf.add_n([x[::2,::2], x[1::2,::2], x[::2,1::2], x[1::2,1::2]]) / 4
+    const float4 a = ld4(x + base), b = ld4(x + base + rowstride), d = ld4(x + base + c), e = ld4(x + base + rowstride + c);
+    float4 r = make_float4((a.x + b.x + d.x + e.x) * 0.25f, (a.y + b.y + d.y + e.y) * 0.25f,
+                           (a.z + b.z + d.z + e.z) * 0.25f, (a.w + b.w + d.w + e.w) * 0.25f);
+    if (add) {
+      const float4 q = ld4(add + pix * c + c4);
+      r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+    }
+    st4(out + pix * c + c4, r);
+  }
+}
+
+// dx[n,2h,2w,c] = scale * dz[n,h,w,c]   (scale = 0.25: mean-pool backward; scale = 1: nearest-upsample forward)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+expand2_kernel(const TIn* __restrict__ dz, TOut* __restrict__ dx, int n, int h, int w, int c, float scale) {
+  const int v = c >> 2;
+  const int64_t total = static_cast<int64_t>(n) * h * w * v;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int wi = static_cast<int>(pix % w);
+    const int hi = static_cast<int>((pix / w) % h);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(w) * h));
+    float4 g = ld4(dz + pix * c + c4);
+    g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+    const int64_t base = ((static_cast<int64_t>(ni) * 2 * h + 2 * hi) * (2 * w) + 2 * wi) * c + c4;
+    const int64_t rowstride = static_cast<int64_t>(2 * w) * c;
+    st4(dx + base, g);
+    st4(dx + base + c, g);
+    st4(dx + base + rowstride, g);
+    st4(dx + base + rowstride + c, g);
+  }
+}
+
+// out[n,h,w,c] = scale * sum of the 2x2 block of x[n,2h,2w,c]  (nearest-upsample backward when scale = 1)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+sum2x2_kernel(const TIn* __restrict__ x, TOut* __restrict__ out, int n, int ho, int wo, int c, float scale) {
+  const int v = c >> 2;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * v;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int wi = static_cast<int>(pix % wo);
+    const int hi = static_cast<int>((pix / wo) % ho);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(wo) * ho));
+    const int64_t base = ((static_cast<int64_t>(ni) * 2 * ho + 2 * hi) * (2 * wo) + 2 * wi) * c + c4;
+    const int64_t rowstride = static_cast<int64_t>(2 * wo) * c;
+    const float4 a = ld4(x + base), b = ld4(x + base + rowstride), d = ld4(x + base + c), e = ld4(x + base + rowstride + c);
+    st4(out + pix * c + c4, make_float4((a.x + b.x + d.x + e.x) * scale, (a.y + b.y + d.y + e.y) * scale,
+                                         (a.z + b.z + d.z + e.z) * scale, (a.w + b.w + d.w + e.w) * scale));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ casts / axpy
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) cast_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int64_t n4, float scale) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 a = ld4(x + i * 4);
+    a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+    st4(y + i * 4, a);
+  }
+}
+template <typename TIn, typename TOut>
+__global__ void cast_tail_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int64_t begin, int64_t n, float scale) {
+  const int64_t i = begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) y[i] = static_cast<TOut>(static_cast<float>(x[i]) * scale);
+}
+
+// y = a*x + b*y  (fp32, flat)
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float a, float b) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 u = ld4(x + i * 4);
+    float4 w = ld4(y + i * 4);
+    w.x = a * u.x + b * w.x; w.y = a * u.y + b * w.y; w.z = a * u.z + b * w.z; w.w = a * u.w + b * w.w;
+    st4(y + i * 4, w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    y[i] = a * x[i] + b * y[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// partial[chunk][c] = sum over the chunk's rows of x[row][c]; finalize: out[c] = beta*out[c] + sum partial
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_per_chunk, float* __restrict__ partial) {
+  const int chunk = blockIdx.x;
+  const int v = c >> 2;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int64_t r0 = static_cast<int64_t>(chunk) * rows_per_chunk;
+  const int64_t r1 = min(rows, r0 + rows_per_chunk);
+  __shared__ float4 sh[256];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float4 s = make_float4(0, 0, 0, 0);
+    if (col < v && ry < lanes)
+      for (int64_t r = r0 + ry; r < r1; r += lanes) {
+        const float4 a = ld4(x + r * c + col * 4);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (ry == 0 && col < v) {
+      for (int l = 1; l < lanes; ++l) {
+        const float4 a = sh[l * cols_per_pass + cx];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+      st4(partial + static_cast<int64_t>(chunk) * c + col * 4, s);
+    }
+    __syncthreads();
+  }
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, float beta, float* __restrict__ out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += partial[static_cast<int64_t>(k) * c + ch];
+  out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
+}
+
+// channel counts that are not a multiple of 4 (RGB bias, scalar heads): one block per channel
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+colsum_scalar_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, float* __restrict__ out) {
+  const int ch = blockIdx.x;
+  __shared__ float sh[256];
+  float s = 0.f;
+  for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) s += static_cast<float>(x[r * c + ch]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------ label map
+// out[n, hw, coff + j] = e[n, j] (raw and, optionally, activated) : tf.tile + tf.concat of the embedded label
+__global__ void __launch_bounds__(256)
+bcast_channels_kernel(const float* __restrict__ e, int n, int hw, int c2, int coff, int cstride, int act,
+                      __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act) {
+  const int v = c2 >> 2;
+  const int64_t total = static_cast<int64_t>(n) * hw * v;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int ni = static_cast<int>(pix / hw);
+    const float4 a = ld4(e + static_cast<int64_t>(ni) * c2 + c4);
+    if (out_raw) st4(out_raw + pix * cstride + coff + c4, a);
+    if (out_act)
+      st4(out_act + pix * cstride + coff + c4,
+          make_float4(act_f(a.x, act), act_f(a.y, act), act_f(a.z, act), act_f(a.w, act)));
+  }
+}
+// de[n, j] = sum_hw ( d_raw[n,hw,coff+j] + dact(e[n,j]) * d_act[n,hw,coff+j] );  grid (n), block = c2/4 x lanes
+__global__ void __launch_bounds__(256)
+bcast_channels_bwd_kernel(const float* __restrict__ e, int hw, int c2, int coff, int cstride, int act,
+                          const __nv_bfloat16* __restrict__ d_raw, const __nv_bfloat16* __restrict__ d_act,
+                          float* __restrict__ de) {
+  const int ni = blockIdx.x;
+  const int v = c2 >> 2;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  __shared__ float4 sh[256];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float4 s = make_float4(0, 0, 0, 0);
+    if (col < v && ry < lanes) {
+      const float4 ev = ld4(e + static_cast<int64_t>(ni) * c2 + col * 4);
+      const float4 m = make_float4(dact_f(ev.x, act), dact_f(ev.y, act), dact_f(ev.z, act), dact_f(ev.w, act));
+      for (int px = ry; px < hw; px += lanes) {
+        const int64_t o = (static_cast<int64_t>(ni) * hw + px) * cstride + coff + col * 4;
+        if (d_raw) { const float4 a = ld4(d_raw + o); s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+        if (d_act) { const float4 a = ld4(d_act + o); s.x += m.x * a.x; s.y += m.y * a.y; s.z += m.z * a.z; s.w += m.w * a.w; }
+      }
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (ry == 0 && col < v) {
+      for (int l = 1; l < lanes; ++l) {
+        const float4 a = sh[l * cols_per_pass + cx];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+      st4(de + static_cast<int64_t>(ni) * c2 + col * 4, s);
+    }
+    __syncthreads();
+  }
+}
+
+// dx[n,hw,0:c1] = d_raw[..., 0:c1] + dact(x) * d_act[..., 0:c1]   (wide bf16 gradients -> fp32 dx)
+__global__ void __launch_bounds__(256)
+concat_bwd_x_kernel(const float* __restrict__ x, int64_t pixels, int c1, int cstride, int act,
+                    const __nv_bfloat16* __restrict__ d_raw, const __nv_bfloat16* __restrict__ d_act,
+                    float* __restrict__ dx) {
+  const int v = c1 >> 2;
+  const int64_t total = pixels * v;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const float4 a = ld4(x + pix * c1 + c4);
+    float4 s = make_float4(0, 0, 0, 0);
+    if (d_raw) s = ld4(d_raw + pix * cstride + c4);
+    if (d_act) {
+      const float4 g = ld4(d_act + pix * cstride + c4);
+      s.x += dact_f(a.x, act) * g.x; s.y += dact_f(a.y, act) * g.y;
+      s.z += dact_f(a.z, act) * g.z; s.w += dact_f(a.w, act) * g.w;
+    }
+    st4(dx + pix * c1 + c4, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ global pool
+// out[n,c] = mean_hw act(x[n,hw,c]) ; grid (n)
+__global__ void __launch_bounds__(256)
+act_mean_hw_fwd_kernel(const float* __restrict__ x, int hw, int c, int act, float* __restrict__ out) {
+  const int ni = blockIdx.x;
+  const int v = c >> 2;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  __shared__ float4 sh[256];
+  const float inv = 1.0f / hw;
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float4 s = make_float4(0, 0, 0, 0);
+    if (col < v && ry < lanes)
+      for (int px = ry; px < hw; px += lanes) {
+        const float4 a = ld4(x + (static_cast<int64_t>(ni) * hw + px) * c + col * 4);
+        s.x += act_f(a.x, act); s.y += act_f(a.y, act); s.z += act_f(a.z, act); s.w += act_f(a.w, act);
+      }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (ry == 0 && col < v) {
+      for (int l = 1; l < lanes; ++l) {
+        const float4 a = sh[l * cols_per_pass + cx];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+      st4(out + static_cast<int64_t>(ni) * c + col * 4, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
+    }
+    __syncthreads();
+  }
+}
+// dx[n,hw,c] = dact(x) * dout[n,c] / hw
+__global__ void __launch_bounds__(256)
+act_mean_hw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, int n, int hw, int c, int act,
+                       float* __restrict__ dx) {
+  const int v = c >> 2;
+  const int64_t total = static_cast<int64_t>(n) * hw * v;
+  const float inv = 1.0f / hw;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int ni = static_cast<int>(pix / hw);
+    const float4 a = ld4(x + pix * c + c4);
+    const float4 g = ld4(dout + static_cast<int64_t>(ni) * c + c4);
+    st4(dx + pix * c + c4, make_float4(dact_f(a.x, act) * g.x * inv, dact_f(a.y, act) * g.y * inv,
+                                        dact_f(a.z, act) * g.z * inv, dact_f(a.w, act) * g.w * inv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ losses
+// mode 0: hinge D loss = mean(relu(1 - d[0:n_real])) + mean(relu(1 + d[n_real:n]))   (gan_cifar_resnet.py:376-378)
+// mode 1: G loss = -mean(d[0:n])                                                      (gan_cifar_resnet.py:492)
+// loss_out[0] (+)= scale * loss ; dlogits = scale * dloss/dd
+__global__ void __launch_bounds__(256)
+gan_loss_kernel(const float* __restrict__ d, int n, int n_real, int mode, float scale, int accumulate,
+                float* __restrict__ loss_out, float* __restrict__ dlogits) {
+  __shared__ float sh[256];
+  float acc = 0.f;
+  const int n_fake = n - n_real;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = d[i];
+    float l, g;
+    if (mode == 0) {
+      if (i < n_real) { const float t = 1.f - v; l = t > 0.f ? t / n_real : 0.f; g = t > 0.f ? -1.f / n_real : 0.f; }
+      else { const float t = 1.f + v; l = t > 0.f ? t / n_fake : 0.f; g = t > 0.f ? 1.f / n_fake : 0.f; }
+    } else {
+      l = -v / n; g = -1.f / n;
+    }
+    acc += l;
+    dlogits[i] = g * scale;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (accumulate ? loss_out[0] : 0.f) + scale * sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// tf.train.AdamOptimizer: theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) given as a device
+// scalar.  One flat buffer per network = "multi-tensor".
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, const float* __restrict__ lr_t, float b1, float b2, float eps, float grad_scale) {
+  const float lr = __ldg(lr_t);
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 pp = ld4(p + i * 4), gg = ld4(g + i * 4), mm = ld4(m + i * 4), vv = ld4(v + i * 4);
+    gg.x *= grad_scale; gg.y *= grad_scale; gg.z *= grad_scale; gg.w *= grad_scale;
+    mm.x = b1 * mm.x + (1.f - b1) * gg.x; mm.y = b1 * mm.y + (1.f - b1) * gg.y;
+    mm.z = b1 * mm.z + (1.f - b1) * gg.z; mm.w = b1 * mm.w + (1.f - b1) * gg.w;
+    vv.x = b2 * vv.x + (1.f - b2) * gg.x * gg.x; vv.y = b2 * vv.y + (1.f - b2) * gg.y * gg.y;
+    vv.z = b2 * vv.z + (1.f - b2) * gg.z * gg.z; vv.w = b2 * vv.w + (1.f - b2) * gg.w * gg.w;
+    pp.x -= lr * mm.x / (sqrtf(vv.x) + eps); pp.y -= lr * mm.y / (sqrtf(vv.y) + eps);
+    pp.z -= lr * mm.z / (sqrtf(vv.z) + eps); pp.w -= lr * mm.w / (sqrtf(vv.w) + eps);
+    st4(p + i * 4, pp); st4(m + i * 4, mm); st4(v + i * 4, vv);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float gg = g[i] * grad_scale;
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    m[i] = mm; v[i] = vv;
+    p[i] -= lr * mm / (sqrtf(vv) + eps);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ input edge
+// gan_cifar_resnet.py:334-337: int32 [B, 3*H*W] CHW -> 2*(x/256 - .5) + noise -> NHWC fp32
+__global__ void __launch_bounds__(256)
+preprocess_real_kernel(const int* __restrict__ data, const float* __restrict__ noise, int b, int hw, float* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(b) * hw * 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % 3);
+    const int64_t pix = i / 3;
+    const int px = static_cast<int>(pix % hw);
+    const int64_t ni = pix / hw;
+    const int64_t src = (ni * 3 + ch) * hw + px;
+    float v = 2.f * (static_cast<float>(data[src]) / 256.f - 0.5f);
+    if (noise) v += noise[src];
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+__global__ void embedding_fwd_kernel(const float* __restrict__ table, const int* __restrict__ labels, int n, int dim,
+                                     float* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(n) * dim;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ni = static_cast<int>(i / dim), j = static_cast<int>(i % dim);
+    out[i] = table[static_cast<int64_t>(labels[ni]) * dim + j];
+  }
+}
+// dtable[row, j] += sum_{n: labels[n]==row} dout[n, j]   (IndexedSlices summed by index; deterministic)
+__global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ labels, int n, int dim,
+                                     int vocab, float* __restrict__ dtable) {
+  const int64_t total = static_cast<int64_t>(vocab) * dim;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / dim), j = static_cast<int>(i % dim);
+    float s = 0.f;
+    for (int ni = 0; ni < n; ++ni)
+      if (labels[ni] == row) s += dout[static_cast<int64_t>(ni) * dim + j];
+    dtable[i] += s;
+  }
+}
+
+}  // namespace ganb
+
+using namespace ganb;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+// ================================================================================================ C ABI
+extern "C" int64_t ganb_bn_stats_workspace(int n, int hw, int c, int groups) {
+  (void)n; (void)hw;
+  return static_cast<int64_t>(groups) * 1024 * 2 * c * 4;
+}
+
+static int stats_chunks(int rows_per_group, int groups) {
+  int chunks = ceil_div(4 * sm_count(), groups);
+  const int max_chunks = ceil_div(rows_per_group, 32);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > 1024) chunks = 1024;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+extern "C" int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, float eps, float* mean, float* rstd,
+                             void* workspace, void* stream) {
+  if (!x || !mean || !rstd || !workspace) return fail(GANB_E_BADARG, "bn_stats: null buffer");
+  if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "bn_stats: c=%d must be a multiple of 4", c);
+  if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "bn_stats: n=%d not divisible by groups=%d", n, groups);
+  const int rows_per_group = (n / groups) * hw;
+  const int chunks = stats_chunks(rows_per_group, groups);
+  const int rows_per_chunk = ceil_div(rows_per_group, chunks);
+  const int used = ceil_div(rows_per_group, rows_per_chunk);
+  bn_stats_partial_kernel<<<dim3(used, groups), 256, 0, STREAM>>>(x, rows_per_group, c, used, rows_per_chunk,
+                                                                  static_cast<float*>(workspace));
+  GANB_CHECK_LAUNCH("bn_stats_partial_kernel");
+  bn_stats_finalize_kernel<<<ceil_div(groups * c, 256), 256, 0, STREAM>>>(
+      static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
+  GANB_CHECK_LAUNCH("bn_stats_finalize_kernel");
+  return 0;
+}
+
+extern "C" int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, const float* mean, const float* rstd,
+                                 int groups, const float* gamma, const float* beta, const int* labels, int act,
+                                 int upsample, void* out, int out_dtype, int out_cstride, void* out_raw_bf16,
+                                 int raw_cstride, void* stream) {
+  if (!x || !out) return fail(GANB_E_BADARG, "norm_act_fwd: null buffer");
+  if (c % 4 != 0 || out_cstride % 4 != 0) return fail(GANB_E_UNSUPPORTED, "norm_act_fwd: c=%d, stride=%d must be multiples of 4", c, out_cstride);
+  if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "norm_act_fwd: bad groups");
+  NormActFwd p;
+  p.x = x; p.n = n; p.h = h; p.w = w; p.c = c;
+  p.mean = mean; p.rstd = rstd; p.groups = groups;
+  p.gamma = gamma; p.beta = beta; p.labels = labels;
+  p.act = act; p.upsample = upsample;
+  p.out = out; p.out_bf16 = (out_dtype == GANB_BF16); p.out_cstride = out_cstride > 0 ? out_cstride : c;
+  p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
+  const int64_t items = static_cast<int64_t>(n) * h * w * (c / 4);
+  norm_act_fwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(p);
+  GANB_CHECK_LAUNCH("norm_act_fwd_kernel");
+  return 0;
+}
+
+static int bwd_chunks(int n, int hw) {
+  int chunks = ceil_div(4 * sm_count(), n);
+  const int max_chunks = ceil_div(hw, 16);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+extern "C" int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups) {
+  const int chunks = bwd_chunks(n, hw);
+  return (static_cast<int64_t>(n) * chunks * 2 * c + 2LL * groups * c) * 4;
+}
+
+extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w,
+                                 int c, const float* mean, const float* rstd, int groups, const float* gamma,
+                                 const float* beta, const int* labels, int act, int upsample, float* dgamma,
+                                 float* dbeta, const float* add, void* dx, int dx_dtype, void* workspace,
+                                 void* stream) {
+  if (!x || !dz || !dx) return fail(GANB_E_BADARG, "norm_act_bwd: null buffer");
+  if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "norm_act_bwd: c=%d must be a multiple of 4", c);
+  if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "norm_act_bwd: bad groups");
+  NormActBwd p;
+  p.x = x; p.dz = dz; p.dz_bf16 = (dz_dtype == GANB_BF16); p.dz_cstride = dz_cstride > 0 ? dz_cstride : c;
+  p.n = n; p.h = h; p.w = w; p.c = c;
+  p.mean = mean; p.rstd = rstd; p.groups = groups;
+  p.gamma = gamma; p.beta = beta; p.labels = labels;
+  p.act = act; p.upsample = upsample;
+  p.add = add; p.dx = dx; p.dx_bf16 = (dx_dtype == GANB_BF16);
+  p.part = nullptr; p.s1 = nullptr; p.s2 = nullptr; p.chunks = 0; p.pix_per_chunk = 0; p.inv_count = 0.f;
+  if (mean) {
+    if (!workspace) return fail(GANB_E_BADARG, "norm_act_bwd: workspace required with normalisation");
+    const int hw = h * w;
+    const int chunks = bwd_chunks(n, hw);
+    p.pix_per_chunk = ceil_div(hw, chunks);
+    p.chunks = ceil_div(hw, p.pix_per_chunk);
+    p.part = static_cast<float*>(workspace);
+    float* s1 = p.part + static_cast<int64_t>(n) * chunks * 2 * c;
+    float* s2 = s1 + static_cast<int64_t>(groups) * c;
+    norm_act_bwd_reduce_kernel<<<dim3(p.chunks, n), 256, 0, STREAM>>>(p);
+    GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
+    norm_act_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, STREAM>>>(p.part, n, c, p.chunks, groups, gamma, labels, s1,
+                                                                       s2, dgamma, dbeta);
+    GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
+    p.s1 = s1; p.s2 = s2;
+    p.inv_count = 1.0f / (static_cast<float>(n / groups) * hw);
+  }
+  const int64_t items = static_cast<int64_t>(n) * h * w * (c / 4);
+  norm_act_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(p);
+  GANB_CHECK_LAUNCH("norm_act_bwd_apply_kernel");
+  return 0;
+}
+
+template <typename TIn, typename TOut>
+static int launch_meanpool(const void* x, const float* add, void* out, int n, int ho, int wo, int c, cudaStream_t s) {
+  const int64_t items = static_cast<int64_t>(n) * ho * wo * (c / 4);
+  meanpool2_fwd_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), add,
+                                                                       static_cast<TOut*>(out), n, ho, wo, c);
+  GANB_CHECK_LAUNCH("meanpool2_fwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, void* out, int out_dtype, int n,
+                                  int h, int w, int c, void* stream) {
+  if (!x || !out) return fail(GANB_E_BADARG, "meanpool2_fwd: null buffer");
+  if (c % 4 != 0 || (h & 1) || (w & 1)) return fail(GANB_E_UNSUPPORTED, "meanpool2_fwd: c %% 4 and even h,w required");
+  const int ho = h / 2, wo = w / 2;
+  if (x_dtype == GANB_F32 && out_dtype == GANB_F32) return launch_meanpool<float, float>(x, add, out, n, ho, wo, c, STREAM);
+  if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_meanpool<float, __nv_bfloat16>(x, add, out, n, ho, wo, c, STREAM);
+  if (x_dtype == GANB_BF16 && out_dtype == GANB_BF16) return launch_meanpool<__nv_bfloat16, __nv_bfloat16>(x, add, out, n, ho, wo, c, STREAM);
+  return launch_meanpool<__nv_bfloat16, float>(x, add, out, n, ho, wo, c, STREAM);
+}
+
+template <typename TIn, typename TOut>
+static int launch_expand(const void* x, void* out, int n, int h, int w, int c, float scale, cudaStream_t s) {
+  const int64_t items = static_cast<int64_t>(n) * h * w * (c / 4);
+  expand2_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(out), n, h, w, c, scale);
+  GANB_CHECK_LAUNCH("expand2_kernel");
+  return 0;
+}
+
+// out[n,2h,2w,c] = scale * x[n,h,w,c] replicated 2x2 (upsample fwd: scale 1; mean-pool bwd: scale 0.25)
+extern "C" int ganb_expand2(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c,
+                            float scale, void* stream) {
+  if (!x || !out) return fail(GANB_E_BADARG, "expand2: null buffer");
+  if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "expand2: c=%d must be a multiple of 4", c);
+  if (x_dtype == GANB_F32 && out_dtype == GANB_F32) return launch_expand<float, float>(x, out, n, h, w, c, scale, STREAM);
+  if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_expand<float, __nv_bfloat16>(x, out, n, h, w, c, scale, STREAM);
+  if (x_dtype == GANB_BF16 && out_dtype == GANB_BF16) return launch_expand<__nv_bfloat16, __nv_bfloat16>(x, out, n, h, w, c, scale, STREAM);
+  return launch_expand<__nv_bfloat16, float>(x, out, n, h, w, c, scale, STREAM);
+}
+
+template <typename TIn, typename TOut>
+static int launch_sum2x2(const void* x, void* out, int n, int ho, int wo, int c, float scale, cudaStream_t s) {
+  const int64_t items = static_cast<int64_t>(n) * ho * wo * (c / 4);
+  sum2x2_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(out), n, ho, wo, c, scale);
+  GANB_CHECK_LAUNCH("sum2x2_kernel");
+  return 0;
+}
+
+// out[n,h/2,w/2,c] = scale * (sum of each 2x2 block of x[n,h,w,c])   (upsample bwd: scale 1)
+extern "C" int ganb_sum2x2(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c,
+                           float scale, void* stream) {
+  if (!x || !out) return fail(GANB_E_BADARG, "sum2x2: null buffer");
+  if (c % 4 != 0 || (h & 1) || (w & 1)) return fail(GANB_E_UNSUPPORTED, "sum2x2: c %% 4 and even h,w required");
+  const int ho = h / 2, wo = w / 2;
+  if (x_dtype == GANB_F32 && out_dtype == GANB_F32) return launch_sum2x2<float, float>(x, out, n, ho, wo, c, scale, STREAM);
+  if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_sum2x2<float, __nv_bfloat16>(x, out, n, ho, wo, c, scale, STREAM);
+  if (x_dtype == GANB_BF16 && out_dtype == GANB_BF16) return launch_sum2x2<__nv_bfloat16, __nv_bfloat16>(x, out, n, ho, wo, c, scale, STREAM);
+  return launch_sum2x2<__nv_bfloat16, float>(x, out, n, ho, wo, c, scale, STREAM);
+}
+
+template <typename TIn, typename TOut>
+static int launch_cast(const void* x, void* y, int64_t n, float scale, cudaStream_t s) {
+  const int64_t n4 = n / 4;
+  if (n4 > 0) {
+    cast_kernel<TIn, TOut><<<grid_for(n4, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(y), n4, scale);
+    GANB_CHECK_LAUNCH("cast_kernel");
+  }
+  if (n % 4) {
+    cast_tail_kernel<TIn, TOut><<<1, 32, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(y), n4 * 4, n, scale);
+    GANB_CHECK_LAUNCH("cast_tail_kernel");
+  }
+  return 0;
+}
+
+extern "C" int ganb_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t count, float scale, void* stream) {
+  if (!x || !y) return fail(GANB_E_BADARG, "cast: null buffer");
+  if (x_dtype == GANB_F32 && y_dtype == GANB_BF16) return launch_cast<float, __nv_bfloat16>(x, y, count, scale, STREAM);
+  if (x_dtype == GANB_BF16 && y_dtype == GANB_F32) return launch_cast<__nv_bfloat16, float>(x, y, count, scale, STREAM);
+  if (x_dtype == GANB_F32 && y_dtype == GANB_F32) return launch_cast<float, float>(x, y, count, scale, STREAM);
+  return launch_cast<__nv_bfloat16, __nv_bfloat16>(x, y, count, scale, STREAM);
+}
+
+extern "C" int ganb_axpby(const float* x, float* y, int64_t count, float a, float b, void* stream) {
+  if (!x || !y) return fail(GANB_E_BADARG, "axpby: null buffer");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return fail(GANB_E_BADARG, "axpby: buffers must be 16-byte aligned");
+  axpby_kernel<<<grid_for(count / 4 + 1, 256), 256, 0, STREAM>>>(x, y, count, a, b);
+  GANB_CHECK_LAUNCH("axpby_kernel");
+  return 0;
+}
+
+extern "C" int64_t ganb_colsum_workspace(int64_t rows, int c) {
+  (void)rows;
+  return static_cast<int64_t>(1024) * c * 4;
+}
+
+// out[c] = beta*out[c] + sum_rows x[row][c]    (bias gradient: tf.nn.bias_add backward)
+extern "C" int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, float beta, float* out, void* workspace,
+                           void* stream) {
+  if (!x || !out || !workspace) return fail(GANB_E_BADARG, "colsum: null buffer");
+  if (c % 4 != 0) {
+    if (x_dtype == GANB_BF16)
+      colsum_scalar_kernel<__nv_bfloat16><<<c, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows, c, beta, out);
+    else
+      colsum_scalar_kernel<float><<<c, 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, beta, out);
+    GANB_CHECK_LAUNCH("colsum_scalar_kernel");
+    return 0;
+  }
+  int chunks = 4 * sm_count();
+  const int64_t max_chunks = ceil_div64(rows, 32);
+  if (chunks > max_chunks) chunks = static_cast<int>(max_chunks);
+  if (chunks > 1024) chunks = 1024;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = static_cast<int>(ceil_div64(rows, chunks));
+  const int used = static_cast<int>(ceil_div64(rows, rows_per_chunk));
+  if (x_dtype == GANB_BF16)
+    colsum_partial_kernel<__nv_bfloat16><<<used, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows, c, rows_per_chunk, static_cast<float*>(workspace));
+  else
+    colsum_partial_kernel<float><<<used, 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, rows_per_chunk, static_cast<float*>(workspace));
+  GANB_CHECK_LAUNCH("colsum_partial_kernel");
+  colsum_finalize_kernel<<<ceil_div(c, 128), 128, 0, STREAM>>>(static_cast<float*>(workspace), c, used, beta, out);
+  GANB_CHECK_LAUNCH("colsum_finalize_kernel");
+  return 0;
+}
+
+extern "C" int ganb_bcast_channels_fwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
+                                       void* out_raw_bf16, void* out_act_bf16, void* stream) {
+  if (!e) return fail(GANB_E_BADARG, "bcast_channels_fwd: null buffer");
+  if (c2 % 4 || coff % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "bcast_channels_fwd: channel counts must be multiples of 4");
+  const int64_t items = static_cast<int64_t>(n) * hw * (c2 / 4);
+  bcast_channels_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(e, n, hw, c2, coff, cstride, act,
+                                                                  static_cast<__nv_bfloat16*>(out_raw_bf16),
+                                                                  static_cast<__nv_bfloat16*>(out_act_bf16));
+  GANB_CHECK_LAUNCH("bcast_channels_kernel");
+  return 0;
+}
+
+extern "C" int ganb_bcast_channels_bwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
+                                       const void* d_raw_bf16, const void* d_act_bf16, float* de, void* stream) {
+  if (!e || !de) return fail(GANB_E_BADARG, "bcast_channels_bwd: null buffer");
+  if (c2 % 4 || coff % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "bcast_channels_bwd: channel counts must be multiples of 4");
+  bcast_channels_bwd_kernel<<<n, 256, 0, STREAM>>>(e, hw, c2, coff, cstride, act,
+                                                   static_cast<const __nv_bfloat16*>(d_raw_bf16),
+                                                   static_cast<const __nv_bfloat16*>(d_act_bf16), de);
+  GANB_CHECK_LAUNCH("bcast_channels_bwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw_bf16,
+                                 const void* d_act_bf16, float* dx, void* stream) {
+  if (!x || !dx) return fail(GANB_E_BADARG, "concat_bwd_x: null buffer");
+  if (c1 % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "concat_bwd_x: channel counts must be multiples of 4");
+  concat_bwd_x_kernel<<<grid_for(pixels * (c1 / 4), 256), 256, 0, STREAM>>>(
+      x, pixels, c1, cstride, act, static_cast<const __nv_bfloat16*>(d_raw_bf16),
+      static_cast<const __nv_bfloat16*>(d_act_bf16), dx);
+  GANB_CHECK_LAUNCH("concat_bwd_x_kernel");
+  return 0;
+}
+
+extern "C" int ganb_act_mean_hw_fwd(const float* x, int n, int hw, int c, int act, float* out, void* stream) {
+  if (!x || !out) return fail(GANB_E_BADARG, "act_mean_hw_fwd: null buffer");
+  if (c % 4) return fail(GANB_E_UNSUPPORTED, "act_mean_hw_fwd: c=%d must be a multiple of 4", c);
+  act_mean_hw_fwd_kernel<<<n, 256, 0, STREAM>>>(x, hw, c, act, out);
+  GANB_CHECK_LAUNCH("act_mean_hw_fwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, int hw, int c, int act, float* dx,
+                                    void* stream) {
+  if (!x || !dout || !dx) return fail(GANB_E_BADARG, "act_mean_hw_bwd: null buffer");
+  if (c % 4) return fail(GANB_E_UNSUPPORTED, "act_mean_hw_bwd: c=%d must be a multiple of 4", c);
+  act_mean_hw_bwd_kernel<<<grid_for(static_cast<int64_t>(n) * hw * (c / 4), 256), 256, 0, STREAM>>>(x, dout, n, hw, c, act, dx);
+  GANB_CHECK_LAUNCH("act_mean_hw_bwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_gan_loss(const float* logits, int n, int n_real, int mode, float scale, int accumulate,
+                             float* loss_out, float* dlogits, void* stream) {
+  if (!logits || !loss_out || !dlogits) return fail(GANB_E_BADARG, "gan_loss: null buffer");
+  if (mode != 0 && mode != 1) return fail(GANB_E_UNSUPPORTED, "gan_loss: mode %d", mode);
+  if (mode == 0 && (n_real <= 0 || n_real >= n)) return fail(GANB_E_BADARG, "gan_loss: hinge needs 0 < n_real < n");
+  gan_loss_kernel<<<1, 256, 0, STREAM>>>(logits, n, n_real, mode, scale, accumulate, loss_out, dlogits);
+  GANB_CHECK_LAUNCH("gan_loss_kernel");
+  return 0;
+}
+
+extern "C" int ganb_adam(float* params, const float* grads, float* m, float* v, int64_t count, const float* lr_t,
+                         float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!params || !grads || !m || !v || !lr_t) return fail(GANB_E_BADARG, "adam: null buffer");
+  adam_kernel<<<grid_for(count / 4 + 1, 256), 256, 0, STREAM>>>(params, grads, m, v, count, lr_t, beta1, beta2, eps, grad_scale);
+  GANB_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}
+
+extern "C" int ganb_preprocess_real(const int* data, const float* noise, int b, int hw, float* out, void* stream) {
+  if (!data || !out) return fail(GANB_E_BADARG, "preprocess_real: null buffer");
+  preprocess_real_kernel<<<grid_for(static_cast<int64_t>(b) * hw * 3, 256), 256, 0, STREAM>>>(data, noise, b, hw, out);
+  GANB_CHECK_LAUNCH("preprocess_real_kernel");
+  return 0;
+}
+
+extern "C" int ganb_embedding_fwd(const float* table, const int* labels, int n, int dim, float* out, void* stream) {
+  if (!table || !labels || !out) return fail(GANB_E_BADARG, "embedding_fwd: null buffer");
+  embedding_fwd_kernel<<<grid_for(static_cast<int64_t>(n) * dim, 256), 256, 0, STREAM>>>(table, labels, n, dim, out);
+  GANB_CHECK_LAUNCH("embedding_fwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_embedding_bwd(const float* dout, const int* labels, int n, int dim, int vocab, float* dtable,
+                                  void* stream) {
+  if (!dout || !labels || !dtable) return fail(GANB_E_BADARG, "embedding_bwd: null buffer");
+  embedding_bwd_kernel<<<grid_for(static_cast<int64_t>(vocab) * dim, 256), 256, 0, STREAM>>>(dout, labels, n, dim, vocab, dtable);
+  GANB_CHECK_LAUNCH("embedding_bwd_kernel");
+  return 0;
+}

@@ -1,0 +1,494 @@
+"""Host-side state that the reference keeps inside TensorFlow: scope-named variables, reuse, the gradient tape,
+spectral-norm `u` state and flat optimiser buffers.
+
+Reference behaviour mirrored here
+  * tf.variable_scope(name, reuse=) / tf.get_variable(name, ...) naming: "Discriminator/D.Block.2.Conv1/Filters"
+    (common/ops/conv2d.py:59,142,213; linear.py:45,140,177; sn.py:28,32; normalization.py:43,49,51;
+    embedding.py:28,40) and tf.trainable_variables() filtered by substring (SNGAN/gan_cifar_resnet.py:507,512);
+  * NumPy initial values are drawn on EVERY layer call while the graph is being built, also when the variable
+    already exists (conv2d.py:124-144) -- `building()` turns that on so the RNG stream matches the reference;
+  * tf.gradients(...) -> Tape.backward(); there is no torch.autograd on this path.
+
+torch supplies device memory and streams; all arithmetic runs in libganb200 kernels (kernels.py).
+"""
+from __future__ import annotations
+
+import contextlib
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import kernels as K
+
+_ALIGN = 64  # floats: every variable starts on a 256-byte boundary inside the flat buffers
+
+
+class Var:
+    """A value on the tape: `data` is a device tensor, `grad` is filled by Tape.backward()."""
+
+    __slots__ = ("data", "grad", "requires_grad", "grad_dtype")
+
+    def __init__(self, data: torch.Tensor, requires_grad: bool = False, grad_dtype=None):
+        self.data = data
+        self.grad = None
+        self.requires_grad = requires_grad
+        self.grad_dtype = grad_dtype  # dtype producers should use for this value's gradient (None: data dtype)
+
+    @property
+    def gdtype(self):
+        return self.grad_dtype if self.grad_dtype is not None else self.data.dtype
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+    def accum(self, g: torch.Tensor) -> None:
+        """Adds a gradient contribution (takes ownership of `g` when it is the first one)."""
+        if self.grad is None:
+            self.grad = g
+        else:
+            if g.dtype != torch.float32 or self.grad.dtype != torch.float32:
+                a, b = K.cast(self.grad, torch.float32), K.cast(g, torch.float32)
+                K.axpby(b, a, 1.0, 1.0)
+                self.grad = K.cast(a, self.grad.dtype) if self.grad.dtype != torch.float32 else a
+            else:
+                K.axpby(g, self.grad, 1.0, 1.0)
+
+    def numpy(self):
+        return self.data.float().cpu().numpy()
+
+
+class Variable(Var):
+    """A named, persistent tensor (tf.Variable)."""
+
+    __slots__ = ("key", "trainable", "root", "store")
+
+    def __init__(self, key, data, trainable, store):
+        super().__init__(data, requires_grad=trainable)
+        self.key = key
+        self.trainable = trainable
+        self.root = key.split("/")[0]
+        self.store = store
+
+    @property
+    def name(self):
+        return self.key + ":0"
+
+    @property
+    def needs_grad(self):
+        return self.trainable and self.root not in self.store.frozen
+
+    def add_grad(self, writer) -> None:
+        """`writer(dst, beta)` must compute dst = beta*dst + contribution. Gradients of variables accumulate."""
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.data)
+        writer(self.grad, 1.0)
+
+
+class Tape:
+    """Records backward closures in execution order; backward() replays them in reverse."""
+
+    def __init__(self, store):
+        self.nodes = []
+        self.store = store
+        self.pending_sn = OrderedDict()  # root -> list of SN entries whose G buffer has been written
+
+    def record(self, fn) -> None:
+        self.nodes.append(fn)
+
+    def backward(self, loss: Var, grad: torch.Tensor | None = None) -> None:
+        if grad is not None:
+            loss.accum(grad)
+        for fn in reversed(self.nodes):
+            fn()
+        self.nodes.clear()
+        for root, entries in self.pending_sn.items():
+            self.store.sn_groups[root].backward(entries)
+        self.pending_sn.clear()
+
+
+class FlatGroup:
+    """All trainable variables of one network in flat params / grads / Adam-slot buffers."""
+
+    def __init__(self, variables, device):
+        self.variables = variables
+        off = 0
+        self.offsets = []
+        for v in variables:
+            self.offsets.append(off)
+            off += -(-v.data.numel() // _ALIGN) * _ALIGN
+        self.size = off
+        self.params = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        for v, o in zip(variables, self.offsets):
+            n = v.data.numel()
+            self.params[o:o + n].copy_(v.data.reshape(-1))
+            v.data = self.params[o:o + n].view(v.data.shape)
+            v.grad = self.grads[o:o + n].view(v.data.shape)
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+
+class SNEntry:
+    """Per-weight spectral-norm state: u (persistent), the vectors of the last evaluation and the G buffer."""
+
+    def __init__(self, w: Variable, u: Variable):
+        dev = w.data.device
+        self.w, self.u = w, u
+        self.c = w.data.shape[-1]
+        self.k = w.data.numel() // self.c
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.u_out = torch.zeros(self.c, **f32)
+        self.u_used = torch.zeros(self.c, **f32)
+        self.v = torch.zeros(self.k, **f32)
+        self.b = torch.zeros(self.c, **f32)
+        self.scal = torch.zeros(4, **f32)            # sigma, 1/sigma, |Wu|, |b|
+        self.g = torch.zeros(self.k, self.c, **f32)  # dL/d(W/sigma), written by the layer's wgrad
+        self.g_written = False
+        self.fresh = False
+
+    @property
+    def inv_sigma(self):
+        return self.scal[1:2]
+
+    @property
+    def sigma(self):
+        return self.scal[0:1]
+
+
+class SNGroup:
+    """All spectrally-normalised weights of one network: evaluated by ONE grouped launch per weight version."""
+
+    def __init__(self, store, root):
+        self.store, self.root = store, root
+        self.entries: "OrderedDict[str, SNEntry]" = OrderedDict()
+        self.table = None
+        self.table_ptrs = None
+        self.valid_for = None
+        self.fresh_for = None
+
+    def entry(self, w: Variable, u: Variable) -> SNEntry:
+        e = self.entries.get(w.key)
+        if e is None:
+            e = SNEntry(w, u)
+            self.entries[w.key] = e
+            self.table = None
+            self.valid_for = None
+            self.fresh_for = None
+        return e
+
+    def _build_table(self, entries):
+        items = []
+        for e in entries:
+            if e.w.grad is None:
+                e.w.grad = torch.zeros_like(e.w.data)
+            items.append(K.SnLayerStruct(e.w.data.data_ptr(), e.u.data.data_ptr(), e.u_out.data_ptr(),
+                                         e.u_used.data_ptr(), e.v.data_ptr(), e.b.data_ptr(), e.scal.data_ptr(),
+                                         e.g.data_ptr(), e.w.grad.data_ptr(), e.k, e.c))
+        dev = entries[0].w.data.device
+        return K.struct_array_to_device(items, dev), max(e.k for e in entries), max(e.c for e in entries)
+
+    def _ptrs(self):
+        return tuple((e.w.data.data_ptr(), e.u.data.data_ptr(), 0 if e.w.grad is None else e.w.grad.data_ptr())
+                     for e in self.entries.values())
+
+    def _run(self, assign: bool) -> None:
+        entries = list(self.entries.values())
+        if self.table is None or self.table_ptrs != self._ptrs():
+            self.table, self.max_k, self.max_c = self._build_table(entries)
+            self.table_ptrs = self._ptrs()
+        K.sn_power_iter(self.table, len(entries), self.max_k, self.max_c, assign)
+
+    def acquire(self, e: SNEntry, assign: bool) -> None:
+        """Makes e.scal / e.v / e.u_used current for this evaluation of the network.
+
+        assign=True  (update_collection=None): ONE power iteration per forward pass of the network, u <- u'.
+                     The first layer that finds its entry already consumed starts a new pass for all layers.
+        assign=False (NO_OPS): a fresh iteration from the stored u, cached until weights or u change."""
+        ver = self.store.version(self.root)
+        if assign:
+            if not (e.fresh and self.fresh_for == ver):
+                self._run(True)
+                self.store.bump_u(self.root)
+                self.valid_for = None
+                self.fresh_for = ver
+                for x in self.entries.values():
+                    x.fresh = True
+            e.fresh = False
+        else:
+            key = (ver, self.store.u_version(self.root))
+            if self.valid_for != key:
+                self._run(False)
+                self.valid_for = key
+                for x in self.entries.values():
+                    x.fresh = False
+
+    def backward(self, entries) -> None:
+        all_entries = list(self.entries.values())
+        if len(entries) == len(all_entries) and self.table is not None and self.table_ptrs == self._ptrs():
+            K.sn_bwd(self.table, len(all_entries), self.max_k, self.max_c)
+        else:
+            table, mk, mc = self._build_table(entries)
+            K.sn_bwd(table, len(entries), mk, mc)
+        for e in entries:
+            e.g_written = False
+
+
+class PackEntry:
+    def __init__(self, w: Variable):
+        shape = w.data.shape
+        self.w = w
+        self.co = shape[-1]
+        self.ci = shape[-2]
+        self.taps = w.data.numel() // (self.ci * self.co)
+        dev = w.data.device
+        self.wn = torch.empty(self.taps, self.ci, self.co, dtype=torch.bfloat16, device=dev)  # [tap][ci][co]
+        self.wt = torch.empty(self.taps, self.co, self.ci, dtype=torch.bfloat16, device=dev)  # [tap][co][ci]
+
+
+class PackGroup:
+    """bf16 operand copies of every tensor-core weight of one network, refreshed by one grouped launch."""
+
+    def __init__(self, store, root):
+        self.store, self.root = store, root
+        self.entries: "OrderedDict[str, PackEntry]" = OrderedDict()
+        self.table = None
+        self.table_ptrs = None
+        self.valid_for = None
+
+    def entry(self, w: Variable) -> PackEntry:
+        e = self.entries.get(w.key)
+        if e is None:
+            e = PackEntry(w)
+            self.entries[w.key] = e
+            self.table = None
+            self.valid_for = None
+        return e
+
+    def _ptrs(self):
+        return tuple(e.w.data.data_ptr() for e in self.entries.values())
+
+    def refresh(self) -> None:
+        ver = self.store.version(self.root)
+        if self.valid_for == ver:
+            return
+        entries = list(self.entries.values())
+        if self.table is None or self.table_ptrs != self._ptrs():
+            items, tiles = [], 0
+            for e in entries:
+                items.append(K.PackLayerStruct(e.w.data.data_ptr(), e.wn.data_ptr(), e.wt.data_ptr(), e.taps, e.ci,
+                                               e.co, tiles))
+                tiles += e.taps * (-(-e.ci // 32)) * (-(-e.co // 32))
+            self.table = K.struct_array_to_device(items, entries[0].w.data.device)
+            self.total_tiles = tiles
+            self.table_ptrs = self._ptrs()
+        K.pack_weights(self.table, len(entries), self.total_tiles)
+        self.valid_for = ver
+
+
+class VariableStore:
+    def __init__(self, device="cuda", u_seed: int = 2):
+        self.device = torch.device(device)
+        self.vars: "OrderedDict[str, Variable]" = OrderedDict()
+        self._scopes: list[tuple[str, bool | None]] = []
+        self.draw_on_reuse = False
+        self.frozen: set[str] = set()
+        self._versions: dict[str, int] = {}
+        self._u_versions: dict[str, int] = {}
+        self.sn_groups: dict[str, SNGroup] = {}
+        self.pack_groups: dict[str, PackGroup] = {}
+        self.flat: dict[str, FlatGroup] = {}
+        self.u_rng = np.random.RandomState(u_seed)
+        self.tape: Tape | None = None
+        self.stat_groups = 1
+
+    # -- scopes ---------------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def variable_scope(self, name, reuse=None):
+        self._scopes.append((name, reuse))
+        try:
+            yield
+        finally:
+            self._scopes.pop()
+
+    def scope_name(self) -> str:
+        return "/".join(s for s, _ in self._scopes if s)
+
+    def _reuse(self) -> bool:
+        return any(r for _, r in self._scopes)
+
+    def root(self) -> str:
+        for s, _ in self._scopes:
+            if s:
+                return s
+        return ""
+
+    # -- variables ------------------------------------------------------------------------------
+    def get_variable(self, name, shape=None, initializer=None, trainable=True) -> Variable:
+        key = "/".join([s for s, _ in self._scopes if s] + [name])
+        v = self.vars.get(key)
+        if v is not None:
+            if self.draw_on_reuse and callable(initializer):
+                initializer(shape)  # the reference draws and discards on every reuse call
+            return v
+        if self._reuse():
+            raise ValueError(f"Variable {key} does not exist, but reuse=True was requested")
+        if initializer is None:
+            raise ValueError(f"Variable {key} needs an initializer")
+        value = initializer(shape) if callable(initializer) else initializer
+        arr = np.ascontiguousarray(np.asarray(value, dtype=np.float32))
+        if shape is not None and tuple(arr.shape) != tuple(shape):
+            arr = np.broadcast_to(arr, shape).copy()
+        data = torch.from_numpy(arr).to(self.device)
+        v = Variable(key, data, bool(trainable), self)
+        self.vars[key] = v
+        return v
+
+    def trainable_variables(self, substring: str = ""):
+        return [v for v in self.vars.values() if v.trainable and substring in v.name]
+
+    def global_variables(self):
+        return list(self.vars.values())
+
+    # -- build / finalize -----------------------------------------------------------------------
+    @contextlib.contextmanager
+    def building(self):
+        """Graph-construction phase: reuse calls draw (and discard) their NumPy initial values."""
+        self.draw_on_reuse = True
+        try:
+            yield
+        finally:
+            self.draw_on_reuse = False
+
+    def finalize(self) -> None:
+        """Moves the trainable variables of every root scope into flat buffers (params / grads / Adam slots)."""
+        roots = OrderedDict()
+        for v in self.vars.values():
+            if v.trainable and v.root not in self.flat:
+                roots.setdefault(v.root, []).append(v)
+        for root, variables in roots.items():
+            self.flat[root] = FlatGroup(variables, self.device)
+            self.bump(root)
+
+    # -- versions -------------------------------------------------------------------------------
+    def version(self, root):
+        return self._versions.get(root, 0)
+
+    def bump(self, root):
+        self._versions[root] = self._versions.get(root, 0) + 1
+
+    def u_version(self, root):
+        return self._u_versions.get(root, 0)
+
+    def bump_u(self, root):
+        self._u_versions[root] = self._u_versions.get(root, 0) + 1
+
+    # -- helpers --------------------------------------------------------------------------------
+    def sn_group(self, root) -> SNGroup:
+        g = self.sn_groups.get(root)
+        if g is None:
+            g = self.sn_groups[root] = SNGroup(self, root)
+        return g
+
+    def pack_group(self, root) -> PackGroup:
+        g = self.pack_groups.get(root)
+        if g is None:
+            g = self.pack_groups[root] = PackGroup(self, root)
+        return g
+
+    @contextlib.contextmanager
+    def gradient_tape(self):
+        prev = self.tape
+        self.tape = Tape(self)
+        try:
+            yield self.tape
+        finally:
+            self.tape = prev
+
+    @contextlib.contextmanager
+    def frozen_scopes(self, *roots):
+        """Variables under these root scopes receive no gradient (var_list of the other optimiser)."""
+        prev = set(self.frozen)
+        self.frozen |= set(roots)
+        try:
+            yield
+        finally:
+            self.frozen = prev
+
+    @contextlib.contextmanager
+    def stat_towers(self, groups: int):
+        """Batch-statistic groups: the reference builds `groups` towers that each normalise their own
+        slice of the batch (SNGAN/gan_cifar_resnet.py:326-332, 464-482)."""
+        prev = self.stat_groups
+        self.stat_groups = groups
+        try:
+            yield
+        finally:
+            self.stat_groups = prev
+
+    def zero_grad(self, root=None):
+        for r, f in self.flat.items():
+            if root is None or r == root:
+                f.zero_grad()
+
+    def state_dict(self):
+        return {k: v.data.detach().cpu().numpy().copy() for k, v in self.vars.items()}
+
+    def load_state_dict(self, state, strict=False):
+        """optimistic_restore semantics (common/misc.py:275-307): only name AND shape matches are restored."""
+        restored = []
+        for k, arr in state.items():
+            v = self.vars.get(k)
+            if v is not None and tuple(v.data.shape) == tuple(arr.shape):
+                v.data.copy_(torch.from_numpy(np.asarray(arr, dtype=np.float32)).to(self.device))
+                restored.append(k)
+            elif strict:
+                raise KeyError(k)
+        for root in {k.split("/")[0] for k in restored}:
+            self.bump(root)
+            self.bump_u(root)
+        return restored
+
+
+def truncated_normal(shape, rng: np.random.RandomState):
+    """tf.truncated_normal_initializer(): standard normal, values beyond 2 sigma re-drawn (sn.py:32)."""
+    out = rng.standard_normal(size=shape)
+    bad = np.abs(out) > 2
+    while bad.any():
+        out[bad] = rng.standard_normal(size=int(bad.sum()))
+        bad = np.abs(out) > 2
+    return out.astype("float32")
+
+
+_default_store: VariableStore | None = None
+
+
+def get_store() -> VariableStore:
+    global _default_store
+    if _default_store is None:
+        if K.host_logic_only():
+            _default_store = VariableStore("cpu")
+        elif not torch.cuda.is_available():
+            raise RuntimeError("gan_lib_tensorflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        else:
+            _default_store = VariableStore("cuda")
+    return _default_store
+
+
+def set_store(store: VariableStore | None) -> None:
+    global _default_store
+    _default_store = store
+
+
+def reset_default_graph(device="cuda", u_seed: int = 2) -> VariableStore:
+    """tf.reset_default_graph(): drops every variable."""
+    set_store(VariableStore(device, u_seed))
+    return get_store()

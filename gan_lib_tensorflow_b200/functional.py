@@ -1,0 +1,416 @@
+"""Differentiable building blocks over framework.Var: each forward launches libganb200 kernels and records a
+backward closure on the current tape.  These are the fused primitives that the reference-compatible layer
+functions (common/ops/*.py, common/resnet_block.py) are assembled from.
+
+Dtype convention: residual-stream / pre-normalisation tensors are fp32, tensor-core operands are bf16,
+accumulation is always fp32.  A value's gradient uses Var.gdtype.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as K
+from .framework import Var, Variable, get_store
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _tape():
+    return get_store().tape
+
+
+def _rg(*xs) -> bool:
+    tape = _tape()
+    if tape is None:
+        return False
+    for x in xs:
+        if x is None:
+            continue
+        if isinstance(x, Variable):
+            if x.needs_grad:
+                return True
+        elif x.requires_grad:
+            return True
+    return False
+
+
+def as_var(x) -> Var:
+    return x if isinstance(x, Var) else Var(x)
+
+
+# ------------------------------------------------------------------------------------------------ basics
+def reshape(x: Var, shape) -> Var:
+    out = Var(x.data.reshape(shape), grad_dtype=x.grad_dtype)
+    if _rg(x):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                x.accum(out.grad.reshape(x.data.shape))
+        _tape().record(bwd)
+    return out
+
+
+def cast(x: Var, dtype) -> Var:
+    if x.data.dtype == dtype:
+        return x
+    out = Var(K.cast(x.data, dtype))
+    if _rg(x):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                g = out.grad
+                x.accum(g if g.dtype == x.gdtype else K.cast(g, x.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def add(a: Var, b: Var) -> Var:
+    """fp32 a + b (gradient accumulation / explicit residual sums)."""
+    assert a.data.dtype == F32 and b.data.dtype == F32 and a.shape == b.shape
+    data = K.cast(a.data, F32)  # copy
+    K.axpby(b.data, data, 1.0, 1.0)
+    out = Var(data)
+    if _rg(a, b):
+        out.requires_grad = True
+
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            if a.requires_grad:
+                a.accum(g if g.dtype == a.gdtype else K.cast(g, a.gdtype))
+            if b.requires_grad:
+                gb = K.cast(g, b.gdtype) if (g.dtype != b.gdtype or a.requires_grad) else g
+                b.accum(gb)
+        _tape().record(bwd)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def _pads(padding, h, w, kh, kw, stride):
+    if padding == "SAME":
+        pt, _, ho = K.same_pads(h, kh, stride)
+        pl, _, wo = K.same_pads(w, kw, stride)
+    elif padding == "VALID":
+        pt = pl = 0
+        ho = (h - kh) // stride + 1
+        wo = (w - kw) // stride + 1
+    else:
+        raise ValueError(f"unknown padding {padding!r}")
+    return pt, pl, ho, wo
+
+
+def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: int = 1, padding: str = "SAME",
+           sn=None, residual: Var | None = None, out_grad_dtype=None, in_scale: float | None = None) -> Var:
+    """NHWC x HWIO cross-correlation (tf.nn.conv2d, common/ops/conv2d.py:181-187) + bias (+ residual), fp32 out.
+
+    `sn` is a framework.SNEntry whose 1/sigma multiplies the accumulator (W/sigma is never materialised).
+    in_scale folds the PGGAN `inputs_norm` constant (conv2d.py:93-95) into the same epilogue factor."""
+    if stride != 1:
+        raise NotImplementedError("strided convolutions are not built yet (SURVEY 8(f)); stride must be 1")
+    store = get_store()
+    n, h, w, cin = x.shape
+    cout = W.data.shape[-1]
+    pt, pl, ho, wo = _pads(padding, h, w, kh, kw, stride)
+    alpha = sn.inv_sigma if sn is not None else None
+    if in_scale is not None:
+        raise NotImplementedError("inputs_norm is not wired into the convolution epilogue yet")
+    bias = b.data if b is not None else None
+    res = residual.data if residual is not None else None
+    small_in = cin <= 8
+    pack = None
+    if small_in:
+        if res is not None:
+            raise NotImplementedError("residual with <=8 input channels")
+        xin = x if x.data.dtype == F32 else cast(x, F32)
+        y = K.conv_smallcin(xin.data, W.data, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, False, alpha, bias,
+                            None, F32)
+    else:
+        if cin % 8:
+            raise NotImplementedError(f"cin={cin}: tensor-core path needs cin % 8 == 0")
+        xin = x if x.data.dtype == BF16 else cast(x, BF16)
+        group = store.pack_group(W.root)
+        pack = group.entry(W)
+        group.refresh()
+        y = K.conv_igemm(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res,
+                         None, F32)
+    out = Var(y, grad_dtype=out_grad_dtype)
+    need_w = W.needs_grad and _tape() is not None
+    need_b = b is not None and b.needs_grad and _tape() is not None
+    if _rg(xin, residual) or need_w or need_b:
+        out.requires_grad = True
+        tape = _tape()
+
+        def bwd():
+            gy = out.grad
+            if gy is None:
+                return
+            if residual is not None and residual.requires_grad:
+                residual.accum(gy if gy.dtype == residual.gdtype else K.cast(gy, residual.gdtype))
+            if need_b:
+                K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
+            small_out = cout <= 8
+            gy16 = None
+            if not small_out and (need_w or xin.requires_grad):
+                gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
+            if need_w:
+                if sn is not None:
+                    dst, beta, scale = sn.g, (1.0 if sn.g_written else 0.0), None
+                else:
+                    dst, beta, scale = W.grad, 1.0, None
+                if small_in:
+                    K.conv_small_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, +1, False,
+                                       scale, beta)
+                elif small_out:
+                    gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
+                    K.conv_small_wgrad(gy32, xin.data, dst, n, ho, wo, cout, h, w, cin, kh, kw, pt, pl, -1, True,
+                                       scale, beta)
+                else:
+                    K.conv_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, scale, beta)
+                if sn is not None:
+                    sn.g_written = True
+                    lst = tape.pending_sn.setdefault(W.root, [])
+                    if sn not in lst:
+                        lst.append(sn)
+            if xin.requires_grad:
+                gdt = xin.gdtype
+                if small_out:
+                    # dx = conv(dy, flipped W^T): dy has <=8 channels -> CUDA-core kernel, W is [tap][cl][cs]
+                    gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
+                    dx = K.conv_smallcin(gy32, W.data, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl,
+                                         True, True, alpha, None, None, gdt)
+                else:
+                    if pack is None:
+                        group2 = store.pack_group(W.root)
+                        pk = group2.entry(W)
+                        group2.refresh()
+                    else:
+                        pk = pack
+                    dx = K.conv_igemm(gy16, pk.wn, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
+                                      alpha, None, None, None, gdt)
+                xin.accum(dx)
+        tape.record(bwd)
+    return out
+
+
+def linear(x: Var, W: Variable, b: Variable | None, sn=None) -> Var:
+    """tf.matmul(x, W) + b (common/ops/linear.py:161-180) for 2-D x; large layers run as 1x1 convolutions on the
+    tensor cores, tiny ones (in % 8 != 0 or out < 8) on CUDA cores."""
+    m, kin = x.shape
+    kout = W.data.shape[1]
+    if kin % 8 == 0 and kout % 8 == 0 and kin * kout >= 65536:
+        x4 = reshape(x, (m, 1, 1, kin))
+        y4 = conv2d(x4, W, b, 1, 1, 1, "VALID", sn=sn)
+        return reshape(y4, (m, kout))
+    xin = x if x.data.dtype == F32 else cast(x, F32)
+    alpha = sn.inv_sigma if sn is not None else None
+    y = torch.empty((m, kout), dtype=F32, device=x.data.device)
+    K.sgemm_small(xin.data, W.data, y, m, kout, kin, False, False, alpha, b.data if b is not None else None, 0.0)
+    out = Var(y)
+    need_w = W.needs_grad and _tape() is not None
+    need_b = b is not None and b.needs_grad and _tape() is not None
+    if _rg(xin) or need_w or need_b:
+        out.requires_grad = True
+        tape = _tape()
+
+        def bwd():
+            gy = out.grad
+            if gy is None:
+                return
+            gy = gy if gy.dtype == F32 else K.cast(gy, F32)
+            if need_b:
+                K.colsum(gy, m, kout, b.grad, 1.0)
+            if need_w:
+                if sn is not None:
+                    K.sgemm_small(xin.data, gy, sn.g, kin, kout, m, True, False, None, None,
+                                  1.0 if sn.g_written else 0.0)
+                    sn.g_written = True
+                    lst = tape.pending_sn.setdefault(W.root, [])
+                    if sn not in lst:
+                        lst.append(sn)
+                else:
+                    K.sgemm_small(xin.data, gy, W.grad, kin, kout, m, True, False, None, None, 1.0)
+            if xin.requires_grad:
+                dx = torch.empty((m, kin), dtype=F32, device=gy.device)
+                K.sgemm_small(gy, W.data, dx, m, kin, kout, False, True, alpha, None, 0.0)
+                xin.accum(dx if xin.gdtype == F32 else K.cast(dx, xin.gdtype))
+        tape.record(bwd)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ norm + act
+def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | None = None,
+             beta: Variable | None = None, labels: torch.Tensor | None = None, act=None, upsample: bool = False,
+             out_dtype=BF16, want_raw: bool = False, groups: int | None = None, out_grad_dtype=None):
+    """act(normalise(x)) [-> nearest 2x upsample], optionally also the raw bf16 copy of x (shortcut operand).
+
+    stats: None (identity), 'batch' (moments over n,h,w per statistic group; cond. BN when labels given) or
+    'instance' (per-sample moments).  Returns (out, raw_or_None)."""
+    assert x.data.dtype == F32, "normalisation input must be fp32"
+    store = get_store()
+    n, h, w, c = x.shape
+    mean = rstd = None
+    g = 1
+    if stats == "batch":
+        g = groups if groups is not None else store.stat_groups
+        if n % g:
+            g = 1
+    elif stats == "instance":
+        g = n
+    elif stats is not None:
+        raise ValueError(stats)
+    if stats is not None:
+        mean, rstd = K.bn_stats(x.data, n, h * w, c, g, eps)
+    gam = gamma.data if gamma is not None else None
+    bet = beta.data if beta is not None else None
+    raw = torch.empty((n, h, w, c), dtype=BF16, device=x.data.device) if want_raw else None
+    y = K.norm_act_fwd(x.data, n, h, w, c, mean, rstd, g, gam, bet, labels, act, upsample, out_dtype, out_raw=raw)
+    out = Var(y, grad_dtype=out_grad_dtype)
+    raw_var = Var(raw, grad_dtype=F32) if want_raw else None
+    need_p = gamma is not None and gamma.needs_grad and _tape() is not None
+    if _rg(x) or need_p:
+        out.requires_grad = True
+        if raw_var is not None:
+            raw_var.requires_grad = x.requires_grad
+
+        def bwd():
+            gz = out.grad
+            extra = raw_var.grad if raw_var is not None else None
+            if gz is None:
+                if extra is not None and x.requires_grad:
+                    x.accum(extra)
+                return
+            dgam = gamma.grad if need_p else None
+            dbet = beta.grad if need_p else None
+            if not x.requires_grad and not need_p:
+                return
+            dx = K.norm_act_bwd(x.data, gz, 0, n, h, w, c, mean, rstd, g, gam, bet, labels, act, upsample, dgam, dbet,
+                                extra, x.gdtype)
+            if x.requires_grad:
+                x.accum(dx)
+        _tape().record(bwd)
+    return out, raw_var
+
+
+def activation(x: Var, act, out_dtype=None) -> Var:
+    """Stand-alone nonlinearity on a tensor of any shape (viewed as rows of 4)."""
+    shape = x.shape
+    total = x.data.numel()
+    if total % 4:
+        raise NotImplementedError("activation: element count must be a multiple of 4")
+    xin = x if x.data.dtype == F32 else cast(x, F32)
+    flat = reshape(xin, (1, 1, total // 4, 4))
+    y, _ = norm_act(flat, stats=None, act=act, out_dtype=out_dtype or F32)
+    return reshape(y, shape)
+
+
+def meanpool2(x: Var, addend: Var | None = None, in_grad_dtype=None) -> Var:
+    """2x2 mean pool (+ addend), fp32 out (common/resnet_block.py:62-63)."""
+    n, h, w, c = x.shape
+    y = K.meanpool2(x.data, addend.data if addend is not None else None, F32)
+    out = Var(y)
+    if _rg(x, addend):
+        out.requires_grad = True
+
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            if addend is not None and addend.requires_grad:
+                addend.accum(g if g.dtype == addend.gdtype else K.cast(g, addend.gdtype))
+            if x.requires_grad:
+                x.accum(K.expand2(g, 0.25, in_grad_dtype or x.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def upsample2(x: Var, out_dtype=None) -> Var:
+    """Nearest-neighbour 2x (tf.depth_to_space of four concatenated copies, common/resnet_block.py:87-88)."""
+    y = K.expand2(x.data, 1.0, out_dtype or x.data.dtype)
+    out = Var(y)
+    if _rg(x):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                x.accum(K.sum2x2(out.grad, 1.0, x.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def act_mean_hw(x: Var, act) -> Var:
+    """mean over (h, w) of act(x): nonlinearity + tf.reduce_mean(axis=[1,2])."""
+    assert x.data.dtype == F32
+    out = Var(K.act_mean_hw_fwd(x.data, act))
+    if _rg(x):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                x.accum(K.act_mean_hw_bwd(x.data, out.grad, act))
+        _tape().record(bwd)
+    return out
+
+
+def embedding(table: Variable, labels: torch.Tensor) -> Var:
+    """tf.nn.embedding_lookup (common/ops/embedding.py:51)."""
+    vocab, dim = table.data.shape
+    n = labels.numel()
+    out = Var(K.embedding_fwd(table.data, labels, n, dim))
+    if table.needs_grad and _tape() is not None:
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                K.embedding_bwd(out.grad, labels, n, dim, vocab, table.grad)
+        _tape().record(bwd)
+    return out
+
+
+def concat_label_map(x: Var, e: Var, act="relu"):
+    """tf.concat([x, tile(e[:,None,None,:])], axis=3) (SNGAN/gan_cifar_resnet.py:282-284), emitted directly as the
+    two bf16 operands the next residual block needs: the raw concat (shortcut) and act(concat) (Conv1 input)."""
+    n, h, w, c1 = x.shape
+    c2 = e.shape[1]
+    ct = c1 + c2
+    dev = x.data.device
+    raw = torch.empty((n, h, w, ct), dtype=BF16, device=dev)
+    actv = torch.empty((n, h, w, ct), dtype=BF16, device=dev)
+    K.norm_act_fwd(x.data, n, h, w, c1, None, None, 1, None, None, None, act, False, BF16, out=actv, out_cstride=ct,
+                   out_raw=raw, raw_cstride=ct)
+    K.bcast_channels_fwd(e.data, n, h * w, c2, c1, ct, act, raw, actv)
+    raw_v, act_v = Var(raw), Var(actv)
+    if _rg(x, e):
+        raw_v.requires_grad = act_v.requires_grad = True
+
+        def bwd():
+            d_raw, d_act = raw_v.grad, act_v.grad
+            if d_raw is None and d_act is None:
+                return
+            if e.requires_grad:
+                e.accum(K.bcast_channels_bwd(e.data, n, h * w, c2, c1, ct, act, d_raw, d_act))
+            if x.requires_grad:
+                x.accum(K.concat_bwd_x(x.data, n * h * w, c1, ct, act, d_raw, d_act))
+        _tape().record(bwd)
+    return raw_v, act_v
+
+
+def gan_loss(logits: Var, mode: str, n_real: int = 0, scale: float = 1.0, loss_out: torch.Tensor | None = None):
+    """hinge_d: mean(relu(1-d_real)) + mean(relu(1+d_fake)) ; gen: -mean(d)  (gan_cifar_resnet.py:376-378, 492).
+    Returns the device scalar (accumulated into loss_out when given)."""
+    code = {"hinge_d": 0, "gen": 1}[mode]
+    accumulate = loss_out is not None
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=F32, device=logits.data.device)
+    dlogits = K.gan_loss(logits.data.reshape(-1), n_real, code, scale, loss_out, accumulate)
+    out = Var(loss_out)
+    if _rg(logits):
+        out.requires_grad = True
+
+        def bwd():
+            logits.accum(dlogits.reshape(logits.data.shape))
+        _tape().record(bwd)
+    return out

@@ -1,0 +1,281 @@
+"""Thin tensor-level wrappers over the C ABI (include/ganb200.h).
+
+torch is used for device memory (caching allocator), dtypes and streams only; every arithmetic step is a
+libganb200 kernel.  All activations are contiguous NHWC.  No wrapper has a CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int, c_int64, c_void_p
+
+import torch
+
+from . import cabi
+from .cabi import BF16, F32, act_code, check, ptr
+
+_L = None
+
+
+class _NullLib:
+    """Host-logic test double (GANB_HOST_LOGIC_ONLY=1): every entry point is a no-op that reports success, so
+    variable naming / RNG order / tape wiring can be exercised on a machine without a GPU.  NO arithmetic is
+    performed and outputs stay uninitialised -- this is not a fallback and is never selected implicitly."""
+
+    def __getattr__(self, name):
+        if name.endswith("_workspace"):
+            return lambda *a: 16
+        return lambda *a: 0
+
+
+def host_logic_only() -> bool:
+    import os
+    return os.environ.get("GANB_HOST_LOGIC_ONLY") == "1"
+
+
+def L():
+    global _L
+    if _L is None:
+        if host_logic_only():
+            _L = _NullLib()
+            return _L
+        _L = cabi.lib()
+        for name in ("ganb_conv2d_wgrad_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
+                     "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
+            getattr(_L, name).restype = c_int64
+    return _L
+
+
+def _stream():
+    if host_logic_only():
+        return c_void_p(0)
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _tdtype(code: int):
+    return torch.bfloat16 if code == BF16 else torch.float32
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def same_pads(in_size: int, k: int, s: int):
+    """TF SAME padding: (before, after, out)."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return total // 2, total - total // 2, out
+
+
+# ------------------------------------------------------------------------------------------------ casts
+def cast(x: torch.Tensor, dtype, scale: float = 1.0) -> torch.Tensor:
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(L().ganb_cast(ptr(x), dt(x), ptr(y), dt(y), c_int64(x.numel()), c_float(scale), _stream()), "ganb_cast")
+    return y
+
+
+def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0) -> None:
+    """y = a*x + b*y (fp32)."""
+    assert x.dtype == torch.float32 and y.dtype == torch.float32 and x.numel() == y.numel()
+    check(L().ganb_axpby(ptr(x), ptr(y), c_int64(x.numel()), c_float(a), c_float(b), _stream()), "ganb_axpby")
+
+
+# ------------------------------------------------------------------------------------------------ conv (TC)
+def conv_igemm(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, alpha, bias, residual, act, out_dtype):
+    y = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
+    check(L().ganb_conv2d_igemm(ptr(x), ptr(wp), ptr(y), n, h, w, cin, ho, wo, cout, kh, kw, 1, pad_t, pad_l,
+                                int(flip), ptr(alpha), ptr(bias), ptr(residual), act_code(act),
+                                BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_conv2d_igemm")
+    return y
+
+
+def conv_wgrad(x, dy, dw, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, scale, beta):
+    nbytes = L().ganb_conv2d_wgrad_workspace(n, h, w, cin, ho, wo, cout, kh, kw)
+    ws = _ws(nbytes, x.device)
+    check(L().ganb_conv2d_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(ws), n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l,
+                                ptr(scale), c_float(beta), _stream()), "ganb_conv2d_wgrad")
+
+
+# ------------------------------------------------------------------------------------------------ conv (small)
+def conv_smallcin(x, w, n, h, w_in, cs, ho, wo, cl, kh, kw, pad_t, pad_l, flip, w_clcs, alpha, bias, act, out_dtype):
+    y = torch.empty((n, ho, wo, cl), dtype=out_dtype, device=x.device)
+    check(L().ganb_conv2d_smallcin(ptr(x), ptr(w), ptr(y), n, h, w_in, cs, ho, wo, cl, kh, kw, pad_t, pad_l,
+                                   int(flip), int(w_clcs), ptr(alpha), ptr(bias), act_code(act),
+                                   BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_conv2d_smallcin")
+    return y
+
+
+def conv_small_wgrad(xs, yl, dw, n, hs, ws_, cs, hl, wl, cl, kh, kw, pad_t, pad_l, sign, out_clcs, scale, beta):
+    nbytes = L().ganb_conv2d_small_wgrad_workspace(n, hl, wl, cs, cl, kh, kw)
+    ws = _ws(nbytes, xs.device)
+    check(L().ganb_conv2d_small_wgrad(ptr(xs), ptr(yl), dt(yl), ptr(dw), ptr(ws), n, hs, ws_, cs, hl, wl, cl, kh, kw,
+                                      pad_t, pad_l, sign, int(out_clcs), ptr(scale), c_float(beta), _stream()),
+          "ganb_conv2d_small_wgrad")
+
+
+def sgemm_small(a, b, c, m, n, k, trans_a, trans_b, alpha=None, bias=None, beta=0.0):
+    check(L().ganb_sgemm_small(ptr(a), ptr(b), ptr(c), m, n, k, int(trans_a), int(trans_b), ptr(alpha), ptr(bias),
+                               c_float(beta), _stream()), "ganb_sgemm_small")
+
+
+# ------------------------------------------------------------------------------------------------ norm / act
+def bn_stats(x, n, hw, c, groups, eps):
+    mean = torch.empty((groups, c), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((groups, c), dtype=torch.float32, device=x.device)
+    ws = _ws(L().ganb_bn_stats_workspace(n, hw, c, groups), x.device)
+    check(L().ganb_bn_stats(ptr(x), n, hw, c, groups, c_float(eps), ptr(mean), ptr(rstd), ptr(ws), _stream()),
+          "ganb_bn_stats")
+    return mean, rstd
+
+
+def norm_act_fwd(x, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, upsample, out_dtype, out=None,
+                 out_cstride=0, out_raw=None, raw_cstride=0):
+    if out is None:
+        s = 2 if upsample else 1
+        out = torch.empty((n, s * h, s * w, c), dtype=out_dtype, device=x.device)
+    check(L().ganb_norm_act_fwd(ptr(x), n, h, w, c, ptr(mean), ptr(rstd), groups, ptr(gamma), ptr(beta), ptr(labels),
+                                act_code(act), int(bool(upsample)), ptr(out), dt(out), out_cstride, ptr(out_raw),
+                                raw_cstride, _stream()), "ganb_norm_act_fwd")
+    return out
+
+
+def norm_act_bwd(x, dz, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, upsample, dgamma, dbeta,
+                 add, dx_dtype):
+    dx = torch.empty((n, h, w, c), dtype=dx_dtype, device=x.device)
+    ws = None
+    if mean is not None:
+        ws = _ws(L().ganb_norm_act_bwd_workspace(n, h * w, c, groups), x.device)
+    check(L().ganb_norm_act_bwd(ptr(x), ptr(dz), dt(dz), dz_cstride, n, h, w, c, ptr(mean), ptr(rstd), groups,
+                                ptr(gamma), ptr(beta), ptr(labels), act_code(act), int(bool(upsample)), ptr(dgamma),
+                                ptr(dbeta), ptr(add), ptr(dx), dt(dx), ptr(ws), _stream()), "ganb_norm_act_bwd")
+    return dx
+
+
+def meanpool2(x, add, out_dtype):
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=out_dtype, device=x.device)
+    check(L().ganb_meanpool2_fwd(ptr(x), dt(x), ptr(add), ptr(out), dt(out), n, h, w, c, _stream()),
+          "ganb_meanpool2_fwd")
+    return out
+
+
+def expand2(x, scale, out_dtype):
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=out_dtype, device=x.device)
+    check(L().ganb_expand2(ptr(x), dt(x), ptr(out), dt(out), n, h, w, c, c_float(scale), _stream()), "ganb_expand2")
+    return out
+
+
+def sum2x2(x, scale, out_dtype):
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=out_dtype, device=x.device)
+    check(L().ganb_sum2x2(ptr(x), dt(x), ptr(out), dt(out), n, h, w, c, c_float(scale), _stream()), "ganb_sum2x2")
+    return out
+
+
+def colsum(x2d, rows, c, out, beta):
+    ws = _ws(L().ganb_colsum_workspace(c_int64(rows), c), x2d.device)
+    check(L().ganb_colsum(ptr(x2d), dt(x2d), c_int64(rows), c, c_float(beta), ptr(out), ptr(ws), _stream()),
+          "ganb_colsum")
+
+
+def bcast_channels_fwd(e, n, hw, c2, coff, cstride, act, out_raw, out_act):
+    check(L().ganb_bcast_channels_fwd(ptr(e), n, hw, c2, coff, cstride, act_code(act), ptr(out_raw), ptr(out_act),
+                                      _stream()), "ganb_bcast_channels_fwd")
+
+
+def bcast_channels_bwd(e, n, hw, c2, coff, cstride, act, d_raw, d_act):
+    de = torch.empty((n, c2), dtype=torch.float32, device=e.device)
+    check(L().ganb_bcast_channels_bwd(ptr(e), n, hw, c2, coff, cstride, act_code(act), ptr(d_raw), ptr(d_act),
+                                      ptr(de), _stream()), "ganb_bcast_channels_bwd")
+    return de
+
+
+def concat_bwd_x(x, pixels, c1, cstride, act, d_raw, d_act):
+    dx = torch.empty_like(x)
+    check(L().ganb_concat_bwd_x(ptr(x), c_int64(pixels), c1, cstride, act_code(act), ptr(d_raw), ptr(d_act), ptr(dx),
+                                _stream()), "ganb_concat_bwd_x")
+    return dx
+
+
+def act_mean_hw_fwd(x, act):
+    n, h, w, c = x.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    check(L().ganb_act_mean_hw_fwd(ptr(x), n, h * w, c, act_code(act), ptr(out), _stream()), "ganb_act_mean_hw_fwd")
+    return out
+
+
+def act_mean_hw_bwd(x, dout, act):
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    check(L().ganb_act_mean_hw_bwd(ptr(x), ptr(dout), n, h * w, c, act_code(act), ptr(dx), _stream()),
+          "ganb_act_mean_hw_bwd")
+    return dx
+
+
+def gan_loss(logits, n_real, mode, scale, loss_out, accumulate):
+    n = logits.numel()
+    dlogits = torch.empty_like(logits)
+    check(L().ganb_gan_loss(ptr(logits), n, n_real, mode, c_float(scale), int(accumulate), ptr(loss_out),
+                            ptr(dlogits), _stream()), "ganb_gan_loss")
+    return dlogits
+
+
+def adam(params, grads, m, v, lr_t, beta1, beta2, eps, grad_scale=1.0):
+    check(L().ganb_adam(ptr(params), ptr(grads), ptr(m), ptr(v), c_int64(params.numel()), ptr(lr_t), c_float(beta1),
+                        c_float(beta2), c_float(eps), c_float(grad_scale), _stream()), "ganb_adam")
+
+
+def preprocess_real(data_int, noise, b, hw):
+    out = torch.empty((b, hw * 3), dtype=torch.float32, device=data_int.device)
+    check(L().ganb_preprocess_real(ptr(data_int), ptr(noise), b, hw, ptr(out), _stream()), "ganb_preprocess_real")
+    return out
+
+
+def embedding_fwd(table, labels, n, dim):
+    out = torch.empty((n, dim), dtype=torch.float32, device=table.device)
+    check(L().ganb_embedding_fwd(ptr(table), ptr(labels), n, dim, ptr(out), _stream()), "ganb_embedding_fwd")
+    return out
+
+
+def embedding_bwd(dout, labels, n, dim, vocab, dtable):
+    check(L().ganb_embedding_bwd(ptr(dout), ptr(labels), n, dim, vocab, ptr(dtable), _stream()), "ganb_embedding_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ grouped SN / pack
+class SnLayerStruct(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("u", c_void_p), ("u_out", c_void_p), ("u_used", c_void_p), ("v", c_void_p),
+                ("b", c_void_p),
+                ("scal", c_void_p), ("g", c_void_p), ("dw", c_void_p), ("k", ctypes.c_int32), ("c", ctypes.c_int32)]
+
+
+class PackLayerStruct(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("wn", c_void_p), ("wt", c_void_p), ("taps", ctypes.c_int32), ("ci", ctypes.c_int32),
+                ("co", ctypes.c_int32), ("tile_begin", ctypes.c_int32)]
+
+
+def struct_array_to_device(items, device) -> torch.Tensor:
+    """Copies a list of ctypes structures into a device byte tensor (the descriptor table of a grouped launch)."""
+    arr = (type(items[0]) * len(items))(*items)
+    raw = bytes(arr)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+def sn_power_iter(table_dev, count, max_k, max_c, assign):
+    check(L().ganb_sn_power_iter(ptr(table_dev), count, max_k, max_c, int(bool(assign)), _stream()),
+          "ganb_sn_power_iter")
+
+
+def sn_bwd(table_dev, count, max_k, max_c):
+    check(L().ganb_sn_bwd(ptr(table_dev), count, max_k, max_c, _stream()), "ganb_sn_bwd")
+
+
+def pack_weights(table_dev, count, total_tiles):
+    check(L().ganb_pack_weights(ptr(table_dev), count, total_tiles, _stream()), "ganb_pack_weights")

@@ -77,6 +77,140 @@ int ganb_conv2d_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, void* 
                       int cin, int ho, int wo, int cout, int kh, int kw, int pad_t, int pad_l,
                       const float* scale, float beta, void* stream);
 
+
+/* CUDA-core convolutions for layers with <= 8 channels on one side (RGB side of D.Block.1.*, G.Output):
+ * same arithmetic as ganb_conv2d_igemm / wgrad, bandwidth-bound on the large-channel tensor.
+ * Reference shapes: SNGAN/gan_cifar_resnet.py:212-234 (input_dim=3), :260 (output_dim=3).
+ *
+ * smallcin: y[n,ho,wo,cl] = act(alpha * sum x[n,ho+r-pad_t,wo+s-pad_l,cs] * w(t,cs,cl) + bias[cl]), x fp32 with
+ *   cs <= 8 channels; w is fp32 [tap][cs][cl] (w_layout_clcs=0) or [tap][cl][cs] (=1); flip_taps as in igemm.
+ * small_wgrad: dw = beta*dw + scale * sum_q xs[q + sign*(tap offset)][cs] * yl[q][cl];
+ *   sign=+1: xs = conv input, yl = output gradient; sign=-1: yl = conv input, xs = output gradient;
+ *   dw layout [tap][cs][cl] (out_layout_clcs=0) or [tap][cl][cs] (=1). taps*cs <= 27. */
+int ganb_conv2d_smallcin(const float* x, const float* w, void* y, int n, int h, int w_in, int cs, int ho, int wo,
+                         int cl, int kh, int kw, int pad_t, int pad_l, int flip_taps, int w_layout_clcs,
+                         const float* alpha, const float* bias, int act, int out_dtype, void* stream);
+int64_t ganb_conv2d_small_wgrad_workspace(int n, int hl, int wl, int cs, int cl, int kh, int kw);
+int ganb_conv2d_small_wgrad(const float* xs, const void* yl, int yl_dtype, float* dw, void* workspace, int n, int hs,
+                            int ws, int cs, int hl, int wl, int cl, int kh, int kw, int pad_t, int pad_l, int sign,
+                            int out_layout_clcs, const float* scale, float beta, void* stream);
+
+/* Tiny dense layers (tf.matmul, common/ops/linear.py:163-173, for shapes the TMA path cannot take):
+ * C[m,n] = beta*C + alpha * op(A)[m,k] * op(B)[k,n] + bias[n]; trans_a: A stored [k,m]; trans_b: B stored [n,k]. */
+int ganb_sgemm_small(const float* a, const float* b, float* c, int m, int n, int k, int trans_a, int trans_b,
+                     const float* alpha, const float* bias, float beta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral normalisation, common/ops/sn.py:15-69 (power iteration through tf.while_loop + 4 tf.matmul,
+ * and its autodiff: the reference has no stop_gradient).  Grouped: one launch handles `count` weights
+ * described by an array of ganb_sn_layer that lives in DEVICE memory.
+ *   fwd : v = l2n(W u), b = W^T v, u_out = l2n(b), scal = {sigma, 1/sigma, |W u|, |b|}     (W is [k, c])
+ *   bwd : dw += g/sigma + v (x) bbar + abar (x) u_used with g = dL/d(W/sigma)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ganb_sn_layer {
+  const float* w;   /* [k, c] fp32 weight (HWIO filter flattened to [kh*kw*cin, cout], or linear [in,out]) */
+  float* u;         /* [c]  persistent power-iteration vector (sn.py:32); overwritten with u_out when assign=1 */
+  float* u_out;     /* [c]  u after one iteration */
+  float* u_used;    /* [c]  the u this evaluation started from (needed by the backward pass) */
+  float* v;         /* [k]  */
+  float* b;         /* [c]  W^T v before normalisation */
+  float* scal;      /* [4]  sigma, 1/sigma, |W u|, |b| */
+  const float* g;   /* bwd only: [k, c] gradient w.r.t. W/sigma */
+  float* dw;        /* bwd only: [k, c] accumulated gradient w.r.t. W */
+  int32_t k, c;
+} ganb_sn_layer;
+/* assign=1 reproduces update_collection=None (u.assign(u_final) on every evaluation, sn.py:48-56);
+ * assign=0 reproduces update_collection="NO_OPS" (sn.py:62-64): u is left untouched. */
+int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, int max_k, int max_c, int assign, void* stream);
+int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int max_k, int max_c, void* stream);
+
+/* fp32 HWIO filters -> bf16 operands of the tensor-core kernels; wn = [tap][ci][co], wt = [tap][co][ci]
+ * (either may be NULL).  tile_begin = prefix sum of taps*ceil(ci/32)*ceil(co/32) over the layers. */
+typedef struct ganb_pack_layer {
+  const float* w;
+  void* wn;
+  void* wt;
+  int32_t taps, ci, co, tile_begin;
+} ganb_pack_layer;
+int ganb_pack_weights(const ganb_pack_layer* layers_dev, int count, int total_tiles, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation + activation + resampling (HBM-bound, float4 / bf16x4 vectorised; c % 4 == 0).
+ * Replaces tf.nn.moments + tf.nn.embedding_lookup x2 + tf.nn.batch_normalization
+ * (common/ops/normalization.py:47-57), tf.contrib.layers.batch_norm / instance_norm in training mode
+ * (:8-24, :105-122), tf.nn.relu / tf.maximum(x,0.2x) (common/resnet_block.py:24-29) and the nearest
+ * upsample tf.depth_to_space(concat x4) (:87-88) that follows them in every generator block.
+ *
+ * `groups` splits the batch into contiguous chunks with separate statistics: 1 = BatchNorm over the call,
+ * 2 = the reference's two per-device towers batched into one call, n = instance norm.
+ * gamma/beta are tables [n_labels, c] indexed by labels[n] (labels NULL -> row 0; gamma NULL -> 1/0).
+ * mean == NULL skips normalisation (pure activation + cast + resample).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ganb_bn_stats_workspace(int n, int hw, int c, int groups);
+int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, float eps, float* mean, float* rstd,
+                  void* workspace, void* stream);
+/* out[n,(2)h,(2)w, out_cstride] (f32/bf16) = act(norm(x)), optionally replicated 2x2; out_raw (bf16, input
+ * resolution, optional) = x.  cstride arguments of 0 mean "c". */
+int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, const float* mean, const float* rstd, int groups,
+                      const float* gamma, const float* beta, const int* labels, int act, int upsample, void* out,
+                      int out_dtype, int out_cstride, void* out_raw_bf16, int raw_cstride, void* stream);
+/* dx = d(loss)/dx given dz = d(loss)/d(out); dgamma/dbeta (tables, may be NULL) are accumulated;
+ * `add` (fp32, optional) is added to dx. */
+int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups);
+int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w, int c,
+                      const float* mean, const float* rstd, int groups, const float* gamma, const float* beta,
+                      const int* labels, int act, int upsample, float* dgamma, float* dbeta, const float* add,
+                      void* dx, int dx_dtype, void* workspace, void* stream);
+
+/* 2x2 mean-pool written as in common/resnet_block.py:62-63 (add_n of four strided slices / 4), + optional add */
+int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, void* out, int out_dtype, int n, int h, int w,
+                       int c, void* stream);
+/* out[n,2h,2w,c] = scale * x replicated 2x2 (nearest upsample: scale 1; mean-pool backward: scale 0.25) */
+int ganb_expand2(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c, float scale,
+                 void* stream);
+/* out[n,h/2,w/2,c] = scale * sum of each 2x2 block (nearest-upsample backward: scale 1) */
+int ganb_sum2x2(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c, float scale,
+                void* stream);
+int ganb_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t count, float scale, void* stream);
+int ganb_axpby(const float* x, float* y, int64_t count, float a, float b, void* stream); /* y = a*x + b*y */
+/* out[c] = beta*out[c] + sum_rows x[row][c]: gradient of tf.nn.bias_add (conv2d.py:216, linear.py:180) */
+int64_t ganb_colsum_workspace(int64_t rows, int c);
+int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, float beta, float* out, void* workspace,
+                void* stream);
+
+/* Label conditioning of D: tf.tile + tf.concat of the embedded label (SNGAN/gan_cifar_resnet.py:282-284).
+ * fwd writes e[n, 0:c2] into channels [coff, coff+c2) of every pixel of bf16 tensors with pixel stride cstride
+ * (raw and/or activated copy); bwd reduces the two wide gradients back to de[n, c2];
+ * concat_bwd_x gathers the gradient of the first c1 channels: dx = d_raw + act'(x) * d_act. */
+int ganb_bcast_channels_fwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
+                            void* out_raw_bf16, void* out_act_bf16, void* stream);
+int ganb_bcast_channels_bwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
+                            const void* d_raw_bf16, const void* d_act_bf16, float* de, void* stream);
+int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw_bf16,
+                      const void* d_act_bf16, float* dx, void* stream);
+
+/* out[n,c] = mean_hw act(x) : nonlinearity + tf.reduce_mean(axis=[1,2]) (gan_cifar_resnet.py:299-301) */
+int ganb_act_mean_hw_fwd(const float* x, int n, int hw, int c, int act, float* out, void* stream);
+int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, int hw, int c, int act, float* dx, void* stream);
+
+/* mode 0: hinge D loss mean(relu(1-d[:n_real])) + mean(relu(1+d[n_real:])) (gan_cifar_resnet.py:376-378)
+ * mode 1: G loss -mean(d) (:492).  loss_out[0] (+)= scale*loss; dlogits = scale * dloss/dd. */
+int ganb_gan_loss(const float* logits, int n, int n_real, int mode, float scale, int accumulate, float* loss_out,
+                  float* dlogits, void* stream);
+
+/* tf.train.AdamOptimizer update (gan_cifar_resnet.py:521-526) over one flat parameter buffer:
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps); lr_t is a DEVICE scalar that
+ * already includes sqrt(1-b2^t)/(1-b1^t).  g is read as grad_scale * grads. */
+int ganb_adam(float* params, const float* grads, float* m, float* v, int64_t count, const float* lr_t, float beta1,
+              float beta2, float eps, float grad_scale, void* stream);
+
+/* int32 [B, 3*hw] CHW pixels -> 2*(x/256 - .5) + noise -> NHWC fp32 (gan_cifar_resnet.py:334-337) */
+int ganb_preprocess_real(const int* data, const float* noise, int b, int hw, float* out, void* stream);
+
+/* tf.nn.embedding_lookup (common/ops/embedding.py:51) and its IndexedSlices gradient summed by index */
+int ganb_embedding_fwd(const float* table, const int* labels, int n, int dim, float* out, void* stream);
+int ganb_embedding_bwd(const float* dout, const int* labels, int n, int dim, int vocab, float* dtable, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,354 @@
+"""Oracle restatement of the reference layer ops (common/ops/*.py) with torch CPU tensors.
+
+Tensors are NHWC like the reference (conv2d.py:186); filters HWIO (conv2d.py:111); linear weights
+[in,out] (linear.py:67).  `g` is an oracle.tfshim.Graph that plays the role of the TF default graph.
+TF-1.x library semantics that the repository does not show are encoded here once:
+
+  conv2d SAME padding ....... out=ceil(in/s), pad_total=max((out-1)s+k-in,0), before=total//2, rest after
+  tf.nn.moments ............. population (biased) variance
+  tf.nn.batch_normalization . inv = rsqrt(var+eps)*gamma ; y = x*inv + (beta - mean*inv)
+  depth_to_space(concat x4) . nearest-neighbour 2x upsample
+  relu / maximum(x,0.2x) .... slope 0 at exactly 0 for relu; slope 1 at exactly 0 for the leaky form
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import tfshim
+
+NO_OPS = "NO_OPS"
+
+# module-level switches of conv2d.py:10-28 / linear.py:12-35 / deconv2d.py:8-26
+_default_weightnorm = False
+_weights_stdev = None
+
+
+def enable_default_weightnorm():
+    global _default_weightnorm
+    _default_weightnorm = True
+
+
+def disable_default_weightnorm():
+    global _default_weightnorm
+    _default_weightnorm = False
+
+
+def set_weights_stdev(weights_stdev):
+    global _weights_stdev
+    _weights_stdev = weights_stdev
+
+
+def unset_weights_stdev():
+    global _weights_stdev
+    _weights_stdev = None
+
+
+# ---------------------------------------------------------------------------------------------- helpers
+def same_pads(in_size: int, k: int, s: int):
+    """TF 'SAME' padding for one spatial dim -> (before, after, out)."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    before = total // 2
+    return before, total - before, out
+
+
+def conv2d_nhwc(x, filt, stride=1, padding="SAME"):
+    """tf.nn.conv2d(NHWC, HWIO): cross-correlation, TF padding rules (conv2d.py:181-187)."""
+    kh, kw = filt.shape[0], filt.shape[1]
+    xc = x.permute(0, 3, 1, 2)
+    if padding == "SAME":
+        pt, pb, _ = same_pads(x.shape[1], kh, stride)
+        pl, pr, _ = same_pads(x.shape[2], kw, stride)
+        xc = F.pad(xc, (pl, pr, pt, pb))
+    elif padding != "VALID":
+        raise ValueError(padding)
+    y = F.conv2d(xc, filt.permute(3, 2, 0, 1), stride=stride)
+    return y.permute(0, 2, 3, 1)
+
+
+def conv2d_transpose_nhwc(x, filt, stride=2, padding="SAME"):
+    """tf.nn.conv2d_transpose with output [N, 2H, 2W, Cout] (deconv2d.py:99-109).
+
+    filt is [k, k, Cout, Cin]; the op is the input-gradient of conv2d([N,2H,2W,Cout] -> [N,H,W,Cin])."""
+    k = filt.shape[0]
+    n, h, w, _ = x.shape
+    oh, ow = 2 * h, 2 * w
+    full = F.conv_transpose2d(x.permute(0, 3, 1, 2), filt.permute(3, 2, 0, 1), stride=stride)
+    if padding == "SAME":
+        pt, _, _ = same_pads(oh, k, stride)
+        pl, _, _ = same_pads(ow, k, stride)
+    else:
+        pt = pl = 0
+    fh, fw = full.shape[2], full.shape[3]
+    # the forward conv may leave trailing rows unused; pad so the crop below is always in range
+    full = F.pad(full, (0, max(0, pl + ow - fw), 0, max(0, pt + oh - fh)))
+    return full[:, :, pt:pt + oh, pl:pl + ow].permute(0, 2, 3, 1)
+
+
+def _memo(fn):
+    """Evaluates fn at most once (initial values are drawn lazily, see tfshim.Graph.draw_on_reuse)."""
+    box = []
+
+    def get():
+        if not box:
+            box.append(fn())
+        return box[0]
+
+    return get
+
+
+def _uniform(stdev, size):
+    """np.random.uniform(+-stdev*sqrt(3)) as float32 -- conv2d.py:83-88, linear.py:53-60."""
+    return np.random.uniform(low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3), size=size).astype("float32")
+
+
+# ---------------------------------------------------------------------------------------------- sn.py
+def _l2normalize(v, eps=1e-12):
+    """common/ops/sn.py:11-12"""
+    return v / (torch.sum(v ** 2) ** 0.5 + eps)
+
+
+def spectral_normed_weight(g, W, u=None, num_iters=1, update_collection=None, with_sigma=False, reuse=False):
+    """common/ops/sn.py:15-69.  No stop_gradient anywhere: gradients flow through the power iteration."""
+    with g.variable_scope("spectral_norm"):
+        W_shape = list(W.shape)
+        W_reshaped = W.reshape(-1, W_shape[-1])                      # sn.py:30
+        if u is None:                                                 # sn.py:31-32
+            u = g.get_variable("u", initializer=lambda s: tfshim.truncated_normal(s, g.u_rng),
+                               shape=[1, W_shape[-1]], trainable=False)
+        u_i = u.detach().clone()  # u is non-trainable state; the clone keeps u.assign() out of the tape
+        v_i = torch.zeros(1, W_reshaped.shape[0], dtype=W.dtype)
+        for _ in range(num_iters):                                    # sn.py:34-47 (tf.while_loop)
+            v_i = _l2normalize(u_i @ W_reshaped.t())
+            u_i = _l2normalize(v_i @ W_reshaped)
+        u_final, v_final = u_i, v_i
+        sigma = ((v_final @ W_reshaped) @ u_final.t())[0, 0]          # sn.py:52 / :58
+        W_bar = (W_reshaped / sigma).reshape(W_shape)
+        if update_collection is None:                                 # sn.py:48-56
+            g.assign(u, u_final)
+        elif update_collection != NO_OPS:                             # sn.py:64-65
+            g.add_to_collection(update_collection, (u, u_final.detach().clone()))
+    if with_sigma:
+        return W_bar, sigma
+    return W_bar
+
+
+# ---------------------------------------------------------------------------------------------- conv2d.py
+def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv2D", conv_type="conv2d",
+           channel_multiplier=0, padding="SAME", spectral_normed=False, update_collection=None,
+           inputs_norm=False, he_init=True, mask_type=None, weightnorm=None, biases=True, gain=1.0, reuse=None):
+    """common/ops/conv2d.py:31-218 (conv2d_.py adds the ignored `reuse` keyword)."""
+    if conv_type != "conv2d":
+        raise NotImplementedError("{0} is not supported by the oracle".format(conv_type))
+    if mask_type is not None:
+        raise NotImplementedError("PixelCNN masks are out of scope (SURVEY 8(f) rank 4)")
+    with g.variable_scope(name):
+        fan_in = input_dim * filter_size ** 2                         # conv2d.py:90
+        fan_out = output_dim * filter_size ** 2 / (stride ** 2)       # conv2d.py:91
+        if inputs_norm:                                               # conv2d.py:93-97
+            inputs_ = inputs * float(np.sqrt(2.0 / fan_in))
+        else:
+            inputs_ = inputs
+        if he_init:                                                   # conv2d.py:103-106
+            filters_stdev = np.sqrt(4.0 / (fan_in + fan_out))
+        else:
+            filters_stdev = np.sqrt(2.0 / (fan_in + fan_out))
+        stdev = _weights_stdev if _weights_stdev is not None else filters_stdev
+        fv = _memo(lambda: _uniform(stdev, (filter_size, filter_size, input_dim, output_dim)) * np.float32(gain))
+        filters = g.get_variable("Filters", initializer=lambda _s: fv())   # conv2d.py:124-144
+        if weightnorm is None:
+            weightnorm = _default_weightnorm
+        if weightnorm:                                                # conv2d.py:153-163
+            norm_values = np.sqrt(np.sum(np.square(fv()), axis=(0, 1, 2)))
+            target_norms = g.get_variable("g", initializer=norm_values)
+            norms = torch.sqrt(torch.sum(filters ** 2, dim=(0, 1, 2)))
+            filters = filters * (target_norms / norms)
+        if spectral_normed:                                           # conv2d.py:169-171
+            with g.variable_scope("filters"):
+                filters = spectral_normed_weight(g, filters, update_collection=update_collection)
+        result = conv2d_nhwc(inputs_, filters, stride, padding)       # conv2d.py:181-187
+        if biases:                                                    # conv2d.py:212-216
+            b = g.get_variable("Biases", initializer=tfshim.constant_initializer(0.0), shape=[output_dim])
+            result = result + b
+        return result
+
+
+# ---------------------------------------------------------------------------------------------- deconv2d.py
+def Deconv2D(g, inputs, in_channels, output_channels, filter_size, stride=2, padding="SAME", he_init=True,
+             weight_norm=None, gain=1.0, mask_type=None, biases=True, name="Deconv2D"):
+    """common/ops/deconv2d.py:29-118"""
+    with g.variable_scope(name):
+        if mask_type is not None:
+            raise Exception("Unsupported configuration in Deconv2D!")
+        fan_in = in_channels * filter_size ** 2 / (stride ** 2)       # deconv2d.py:62
+        fan_out = output_channels * filter_size ** 2                  # deconv2d.py:63
+        if he_init:
+            filters_stdev = np.sqrt(4.0 / (fan_in + fan_out))
+        else:
+            filters_stdev = np.sqrt(2.0 / (fan_in + fan_out))
+        stdev = _weights_stdev if _weights_stdev is not None else filters_stdev
+        fv = _memo(lambda: _uniform(stdev, (filter_size, filter_size, output_channels, in_channels))
+                   * np.float32(gain))
+        filters = g.get_variable("Filters", initializer=lambda _s: fv())
+        if weight_norm is None:
+            weight_norm = _default_weightnorm
+        if weight_norm:                                               # deconv2d.py:87-96
+            norm_values = np.sqrt(np.sum(np.square(fv()), axis=(0, 1, 3)))
+            target_norms = g.get_variable("g", initializer=norm_values)
+            norms = torch.sqrt(torch.sum(filters ** 2, dim=(0, 1, 3)))
+            filters = filters * (target_norms / norms).unsqueeze(1)
+        result = conv2d_transpose_nhwc(inputs, filters, stride, padding)  # deconv2d.py:99-109
+        if biases:
+            b = g.get_variable("Biases", initializer=tfshim.constant_initializer(0.0), shape=[output_channels])
+            result = result + b
+        return result
+
+
+# ---------------------------------------------------------------------------------------------- linear.py
+def Linear(g, inputs, input_dim, output_dim, name, spectral_normed=False, update_collection=None, reuse=False,
+           inputs_norm=False, biases=True, initialization=None, weightnorm=None, gain=1.0):
+    """common/ops/linear.py:38-182"""
+    with g.variable_scope(name):
+        if inputs_norm:                                               # linear.py:47-51
+            inputs_ = inputs * float(np.sqrt(2.0 / input_dim))
+        else:
+            inputs_ = inputs
+
+        def uniform(stdev, size):                                     # linear.py:53-60
+            if _weights_stdev is not None:
+                stdev = _weights_stdev
+            return _uniform(stdev, size)
+
+        def draw():
+            if initialization == "lecun":
+                wv = uniform(np.sqrt(1.0 / input_dim), (input_dim, output_dim))
+            elif initialization in ("glorot", "xavier") or initialization is None:  # linear.py:76 (None lands here)
+                wv = uniform(np.sqrt(2.0 / (input_dim + output_dim)), (input_dim, output_dim))
+            elif initialization == "he":
+                wv = uniform(np.sqrt(2.0 / input_dim), (input_dim, output_dim))
+            elif initialization == "glorot_he":
+                wv = uniform(np.sqrt(4.0 / (input_dim + output_dim)), (input_dim, output_dim))
+            elif initialization == "orthogonal":                      # linear.py:112-128
+                a = np.random.normal(0.0, 1.0, (input_dim, output_dim))
+                uu, _, vv = np.linalg.svd(a, full_matrices=False)
+                q = uu if uu.shape == (input_dim, output_dim) else vv
+                wv = q.reshape((input_dim, output_dim)).astype("float32")
+            elif initialization[0] == "uniform":
+                wv = np.random.uniform(low=-initialization[1], high=initialization[1],
+                                       size=(input_dim, output_dim)).astype("float32")
+            else:
+                raise Exception("Invalid initialization!")
+            return wv * np.float32(gain)                              # linear.py:138
+
+        wv_memo = _memo(draw)
+        weight = g.get_variable("W", initializer=lambda _s: wv_memo())
+        if weightnorm is None:
+            weightnorm = _default_weightnorm
+        if weightnorm:                                                # linear.py:143-155
+            norm_values = np.sqrt(np.sum(np.square(wv_memo()), axis=0))
+            target_norms = g.get_variable("g", initializer=norm_values)
+            norms = torch.sqrt(torch.sum(weight ** 2, dim=0))
+            weight = weight * (target_norms / norms)
+        w_eff = spectral_normed_weight(g, weight, update_collection=update_collection) if spectral_normed else weight
+        if inputs_.dim() == 2:                                        # linear.py:161-165
+            result = inputs_ @ w_eff
+        else:                                                         # linear.py:166-174
+            result = (inputs_.reshape(-1, input_dim) @ w_eff).reshape(*inputs_.shape[:-1], output_dim)
+        if biases:                                                    # linear.py:176-180
+            b = g.get_variable("b", initializer=tfshim.constant_initializer(0.0), shape=[output_dim])
+            result = result + b
+        return result
+
+
+# ---------------------------------------------------------------------------------------------- normalization.py
+def batch_norm(g, inputs, decay=0.9, epsilon=1e-5, is_training=True, fused=True):
+    """common/ops/normalization.py:8-24: contrib fused BN, always training mode -> batch statistics.
+
+    Moving statistics are write-only state in every shipped caller; they are updated here with the plain
+    EMA (population mean, Bessel-corrected variance) and no zero-debias slots."""
+    with g.variable_scope("BatchNorm"):
+        c = inputs.shape[-1]
+        beta = g.get_variable("beta", initializer=tfshim.constant_initializer(0.0), shape=[c])
+        gamma = g.get_variable("gamma", initializer=tfshim.constant_initializer(1.0), shape=[c])
+        mm = g.get_variable("moving_mean", initializer=tfshim.constant_initializer(0.0), shape=[c], trainable=False)
+        mv = g.get_variable("moving_variance", initializer=tfshim.constant_initializer(1.0), shape=[c],
+                            trainable=False)
+        red = tuple(range(inputs.dim() - 1))
+        mean = inputs.mean(dim=red)
+        var = inputs.var(dim=red, unbiased=False)
+        y = (inputs - mean) * torch.rsqrt(var + epsilon) * gamma + beta
+        if is_training:
+            cnt = inputs.numel() // c
+            with torch.no_grad():
+                mm.mul_(decay).add_((1 - decay) * mean.detach())
+                mv.mul_(decay).add_((1 - decay) * var.detach() * (cnt / max(cnt - 1, 1)))
+        return y
+
+
+def cond_batchnorm(g, name, axes, inputs, is_training=None, stats_iter=None, update_moving_stats=True, fused=True,
+                   labels=None, n_labels=None):
+    """common/ops/normalization.py:27-59"""
+    with g.variable_scope("CondBatchNorm"):
+        if axes != [0, 1, 2]:
+            raise Exception("Axes is not supported in Conditional BatchNorm!")
+        mean = inputs.mean(dim=(0, 1, 2), keepdim=True)               # tf.nn.moments -> population variance
+        var = inputs.var(dim=(0, 1, 2), unbiased=False, keepdim=True)
+        c = inputs.shape[3]
+        offset_m = g.get_variable("offset", initializer=tfshim.constant_initializer(0.0), shape=[n_labels, c])
+        scale_m = g.get_variable("scale", initializer=tfshim.constant_initializer(1.0), shape=[n_labels, c])
+        offset = offset_m[labels.long()]                              # embedding_lookup, normalization.py:54-55
+        scale = scale_m[labels.long()]
+        inv = torch.rsqrt(var + 1e-5) * scale[:, None, None, :]       # tf.nn.batch_normalization
+        return inputs * inv + (offset[:, None, None, :] - mean * inv)
+
+
+def layer_norm(g, name, norm_axes, inputs):
+    """common/ops/normalization.py:62-82: contrib layer_norm, begin_norm_axis=1, begin_params_axis=-1."""
+    with g.variable_scope(name):
+        c = inputs.shape[-1]
+        beta = g.get_variable("beta", initializer=tfshim.constant_initializer(0.0), shape=[c])
+        gamma = g.get_variable("gamma", initializer=tfshim.constant_initializer(1.0), shape=[c])
+        red = tuple(range(1, inputs.dim()))
+        mean = inputs.mean(dim=red, keepdim=True)
+        var = inputs.var(dim=red, unbiased=False, keepdim=True)
+        return (inputs - mean) * torch.rsqrt(var + 1e-12) * gamma + beta
+
+
+def instance_norm(g, inputs, epsilon=1e-06):
+    """common/ops/normalization.py:105-122: per-(n,c) moments over H,W."""
+    with g.variable_scope("InstanceNorm"):
+        c = inputs.shape[-1]
+        beta = g.get_variable("beta", initializer=tfshim.constant_initializer(0.0), shape=[c])
+        gamma = g.get_variable("gamma", initializer=tfshim.constant_initializer(1.0), shape=[c])
+        mean = inputs.mean(dim=(1, 2), keepdim=True)
+        var = inputs.var(dim=(1, 2), unbiased=False, keepdim=True)
+        return (inputs - mean) * torch.rsqrt(var + epsilon) * gamma + beta
+
+
+def pixel_norm(inputs, eps=1e-8):
+    """common/ops/normalization.py:125-140"""
+    alpha = 1.0 / torch.sqrt(torch.mean(inputs * inputs, dim=3, keepdim=True) + eps)
+    return alpha * inputs
+
+
+# ---------------------------------------------------------------------------------------------- embedding.py
+def embed_y(g, inputs, vocab_size=1000, embedding_dim=300, word2vec_file=None, spectral_normed=False,
+            update_collection=None, reuse=False):
+    """common/ops/embedding.py:12-51"""
+    with g.variable_scope("Embedding.Label"):
+        if word2vec_file is None:
+            embedding_map = g.get_variable(
+                "embedding_map", trainable=True,
+                initializer=lambda _s: np.random.uniform(low=-0.08, high=0.08,
+                                                         size=(vocab_size, embedding_dim)).astype("float32"))
+        else:
+            embedding_map = g.get_variable("embedding_map", initializer=word2vec_file, trainable=False)
+        return embedding_map[inputs.long()]
+
+
+def _silence():
+    warnings.filterwarnings("ignore")
