@@ -94,23 +94,33 @@ bn_stats_partial_kernel(const float* __restrict__ x, int rows_per_group, int c, 
   }
 }
 
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int c, int groups, int chunks,
-                                         float inv_count, float eps, float* __restrict__ mean,
-                                         float* __restrict__ rstd) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= groups * c) return;
-  const int g = i / c, ch = i - g * c;
+// 256 threads = 32 channels x 8 chunk lanes; lanes are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+bn_stats_finalize_kernel(const float* __restrict__ partial, int c, int groups, int chunks, float inv_count, float eps,
+                         float* __restrict__ mean, float* __restrict__ rstd) {
+  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cx;  // flat (group, channel)
+  __shared__ double sh_s[8][32], sh_q[8][32];
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    const float* p = partial + (static_cast<int64_t>(g) * chunks + k) * 2 * c;
-    s += p[ch];
-    q += p[c + ch];
+  if (i < groups * c) {
+    const int g = i / c, ch = i - g * c;
+    for (int k = lane; k < chunks; k += 8) {
+      const float* p = partial + (static_cast<int64_t>(g) * chunks + k) * 2 * c;
+      s += p[ch];
+      q += p[c + ch];
+    }
   }
-  const double m = s * inv_count;
-  double var = q * inv_count - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[i] = static_cast<float>(m);
-  rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  sh_s[lane][cx] = s;
+  sh_q[lane][cx] = q;
+  __syncthreads();
+  if (lane == 0 && i < groups * c) {
+    for (int l = 1; l < 8; ++l) { s += sh_s[l][cx]; q += sh_q[l][cx]; }
+    const double m = s * inv_count;
+    double var = q * inv_count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[i] = static_cast<float>(m);
+    rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ norm+act fwd
@@ -271,39 +281,61 @@ __global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(const NormActB
   }
 }
 
-// one thread per channel walks all samples in order: deterministic scatter of dgamma/dbeta by label and the
-// group sums S1 = sum gamma*A, S2 = sum gamma*B needed by the apply pass.
-__global__ void norm_act_bwd_finalize_kernel(const float* __restrict__ part, int n, int c, int chunks, int groups,
-                                             const float* __restrict__ gamma, const int* __restrict__ labels,
-                                             float* __restrict__ s1, float* __restrict__ s2,
-                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+// Stage 1: per-sample sums A_n = sum_chunks, B_n, and the group sums S1 = sum gamma*A, S2 = sum gamma*B.
+// 256 threads = 32 channels x 8 sample lanes, combined in a fixed order (deterministic). grid (c/32, groups).
+__global__ void __launch_bounds__(256)
+norm_act_bwd_finalize_kernel(const float* __restrict__ part, int n, int c, int chunks, int groups,
+                             const float* __restrict__ gamma, const int* __restrict__ labels,
+                             float* __restrict__ sums /*[n][2][c]*/, float* __restrict__ s1, float* __restrict__ s2) {
+  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
+  const int g = blockIdx.y;
   const int n_per_group = n / groups;
-  for (int g = 0; g < groups; ++g) {
-    float acc1 = 0.f, acc2 = 0.f;
-    for (int ni = g * n_per_group; ni < (g + 1) * n_per_group; ++ni) {
+  __shared__ float sh1[8][32], sh2[8][32];
+  float acc1 = 0.f, acc2 = 0.f;
+  if (ch < c) {
+    for (int ni = g * n_per_group + lane; ni < (g + 1) * n_per_group; ni += 8) {
       float a = 0.f, b = 0.f;
       for (int k = 0; k < chunks; ++k) {
         const float* q = part + (static_cast<int64_t>(ni) * chunks + k) * 2 * c;
         a += q[ch];
         b += q[c + ch];
       }
+      sums[(static_cast<int64_t>(ni) * 2) * c + ch] = a;
+      sums[(static_cast<int64_t>(ni) * 2 + 1) * c + ch] = b;
       float ga = 1.f;
-      if (gamma) {
-        const int row = labels ? labels[ni] : 0;
-        ga = gamma[static_cast<int64_t>(row) * c + ch];
-        if (dgamma) {
-          dgamma[static_cast<int64_t>(row) * c + ch] += b;
-          dbeta[static_cast<int64_t>(row) * c + ch] += a;
-        }
-      }
+      if (gamma) ga = gamma[static_cast<int64_t>(labels ? labels[ni] : 0) * c + ch];
       acc1 += ga * a;
       acc2 += ga * b;
     }
+  }
+  sh1[lane][cx] = acc1;
+  sh2[lane][cx] = acc2;
+  __syncthreads();
+  if (lane == 0 && ch < c) {
+    for (int l = 1; l < 8; ++l) { acc1 += sh1[l][cx]; acc2 += sh2[l][cx]; }
     s1[g * c + ch] = acc1;
     s2[g * c + ch] = acc2;
   }
+}
+
+// Stage 2: dgamma[row, ch] += sum_{n: label_n == row} B_n ; dbeta likewise with A_n. One thread per (row, ch)
+// walks the samples in order (deterministic scatter of tf.nn.embedding_lookup's gradient).
+__global__ void norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int n, int c, int n_rows,
+                                            const int* __restrict__ labels, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * c) return;
+  const int row = i / c, ch = i - row * c;
+  float a = 0.f, b = 0.f;
+  for (int ni = 0; ni < n; ++ni) {
+    if ((labels ? labels[ni] : 0) == row) {
+      a += sums[(static_cast<int64_t>(ni) * 2) * c + ch];
+      b += sums[(static_cast<int64_t>(ni) * 2 + 1) * c + ch];
+    }
+  }
+  dbeta[i] += a;
+  dgamma[i] += b;
 }
 
 __global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(const NormActBwd p) {
@@ -412,6 +444,45 @@ sum2x2_kernel(const TIn* __restrict__ x, TOut* __restrict__ out, int n, int ho, 
   }
 }
 
+// ---- scalar variants for channel counts that are not a multiple of 4 (RGB images)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+pool2_scalar_kernel(const TIn* __restrict__ x, const float* __restrict__ add, TOut* __restrict__ out, int n, int ho,
+                    int wo, int c, float scale) {
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const int64_t pix = i / c;
+    const int wi = static_cast<int>(pix % wo);
+    const int hi = static_cast<int>((pix / wo) % ho);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(wo) * ho));
+    const int64_t base = ((static_cast<int64_t>(ni) * 2 * ho + 2 * hi) * (2 * wo) + 2 * wi) * c + ch;
+    const int64_t rowstride = static_cast<int64_t>(2 * wo) * c;
+    float r = (static_cast<float>(x[base]) + static_cast<float>(x[base + rowstride]) + static_cast<float>(x[base + c]) +
+               static_cast<float>(x[base + rowstride + c])) * scale;
+    if (add) r += add[i];
+    out[i] = static_cast<TOut>(r);
+  }
+}
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+expand2_scalar_kernel(const TIn* __restrict__ dz, TOut* __restrict__ dx, int n, int h, int w, int c, float scale) {
+  const int64_t total = static_cast<int64_t>(n) * h * w * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const int64_t pix = i / c;
+    const int wi = static_cast<int>(pix % w);
+    const int hi = static_cast<int>((pix / w) % h);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(w) * h));
+    const TOut g = static_cast<TOut>(static_cast<float>(dz[i]) * scale);
+    const int64_t base = ((static_cast<int64_t>(ni) * 2 * h + 2 * hi) * (2 * w) + 2 * wi) * c + ch;
+    const int64_t rowstride = static_cast<int64_t>(2 * w) * c;
+    dx[base] = g; dx[base + c] = g; dx[base + rowstride] = g; dx[base + rowstride + c] = g;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ casts / axpy
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) cast_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int64_t n4, float scale) {
@@ -477,12 +548,20 @@ colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_p
     __syncthreads();
   }
 }
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, float beta, float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, float beta, float* __restrict__ out) {
+  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
+  __shared__ float sh[8][32];
   float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += partial[static_cast<int64_t>(k) * c + ch];
-  out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
+  if (ch < c)
+    for (int k = lane; k < chunks; k += 8) s += partial[static_cast<int64_t>(k) * c + ch];
+  sh[lane][cx] = s;
+  __syncthreads();
+  if (lane == 0 && ch < c) {
+    for (int l = 1; l < 8; ++l) s += sh[l][cx];
+    out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
+  }
 }
 
 // channel counts that are not a multiple of 4 (RGB bias, scalar heads): one block per channel
@@ -522,9 +601,10 @@ bcast_channels_kernel(const float* __restrict__ e, int n, int hw, int c2, int co
   }
 }
 // de[n, j] = sum_hw ( d_raw[n,hw,coff+j] + dact(e[n,j]) * d_act[n,hw,coff+j] );  grid (n), block = c2/4 x lanes
+template <typename TG>
 __global__ void __launch_bounds__(256)
 bcast_channels_bwd_kernel(const float* __restrict__ e, int hw, int c2, int coff, int cstride, int act,
-                          const __nv_bfloat16* __restrict__ d_raw, const __nv_bfloat16* __restrict__ d_act,
+                          const TG* __restrict__ d_raw, const TG* __restrict__ d_act,
                           float* __restrict__ de) {
   const int ni = blockIdx.x;
   const int v = c2 >> 2;
@@ -558,9 +638,10 @@ bcast_channels_bwd_kernel(const float* __restrict__ e, int hw, int c2, int coff,
 }
 
 // dx[n,hw,0:c1] = d_raw[..., 0:c1] + dact(x) * d_act[..., 0:c1]   (wide bf16 gradients -> fp32 dx)
+template <typename TG>
 __global__ void __launch_bounds__(256)
 concat_bwd_x_kernel(const float* __restrict__ x, int64_t pixels, int c1, int cstride, int act,
-                    const __nv_bfloat16* __restrict__ d_raw, const __nv_bfloat16* __restrict__ d_act,
+                    const TG* __restrict__ d_raw, const TG* __restrict__ d_act,
                     float* __restrict__ dx) {
   const int v = c1 >> 2;
   const int64_t total = pixels * v;
@@ -765,7 +846,7 @@ extern "C" int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, f
   bn_stats_partial_kernel<<<dim3(used, groups), 256, 0, STREAM>>>(x, rows_per_group, c, used, rows_per_chunk,
                                                                   static_cast<float*>(workspace));
   GANB_CHECK_LAUNCH("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<ceil_div(groups * c, 256), 256, 0, STREAM>>>(
+  bn_stats_finalize_kernel<<<ceil_div(groups * c, 32), 256, 0, STREAM>>>(
       static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
   GANB_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return 0;
@@ -801,14 +882,14 @@ static int bwd_chunks(int n, int hw) {
 
 extern "C" int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups) {
   const int chunks = bwd_chunks(n, hw);
-  return (static_cast<int64_t>(n) * chunks * 2 * c + 2LL * groups * c) * 4;
+  return (static_cast<int64_t>(n) * chunks * 2 * c + 2LL * n * c + 2LL * groups * c) * 4;
 }
 
 extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w,
                                  int c, const float* mean, const float* rstd, int groups, const float* gamma,
-                                 const float* beta, const int* labels, int act, int upsample, float* dgamma,
-                                 float* dbeta, const float* add, void* dx, int dx_dtype, void* workspace,
-                                 void* stream) {
+                                 const float* beta, const int* labels, int n_rows, int act, int upsample,
+                                 float* dgamma, float* dbeta, const float* add, void* dx, int dx_dtype,
+                                 void* workspace, void* stream) {
   if (!x || !dz || !dx) return fail(GANB_E_BADARG, "norm_act_bwd: null buffer");
   if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "norm_act_bwd: c=%d must be a multiple of 4", c);
   if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "norm_act_bwd: bad groups");
@@ -827,13 +908,19 @@ extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, i
     p.pix_per_chunk = ceil_div(hw, chunks);
     p.chunks = ceil_div(hw, p.pix_per_chunk);
     p.part = static_cast<float*>(workspace);
-    float* s1 = p.part + static_cast<int64_t>(n) * chunks * 2 * c;
+    float* sums = p.part + static_cast<int64_t>(n) * chunks * 2 * c;
+    float* s1 = sums + 2LL * n * c;
     float* s2 = s1 + static_cast<int64_t>(groups) * c;
     norm_act_bwd_reduce_kernel<<<dim3(p.chunks, n), 256, 0, STREAM>>>(p);
     GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
-    norm_act_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, STREAM>>>(p.part, n, c, p.chunks, groups, gamma, labels, s1,
-                                                                       s2, dgamma, dbeta);
+    norm_act_bwd_finalize_kernel<<<dim3(ceil_div(c, 32), groups), 256, 0, STREAM>>>(p.part, n, c, p.chunks, groups, gamma,
+                                                                                  labels, sums, s1, s2);
     GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
+    if (gamma && dgamma && dbeta) {
+      const int rows = (labels && n_rows > 0) ? n_rows : 1;
+      norm_act_bwd_scatter_kernel<<<ceil_div(rows * c, 256), 256, 0, STREAM>>>(sums, n, c, rows, labels, dgamma, dbeta);
+      GANB_CHECK_LAUNCH("norm_act_bwd_scatter_kernel");
+    }
     p.s1 = s1; p.s2 = s2;
     p.inv_count = 1.0f / (static_cast<float>(n / groups) * hw);
   }
@@ -845,6 +932,12 @@ extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, i
 
 template <typename TIn, typename TOut>
 static int launch_meanpool(const void* x, const float* add, void* out, int n, int ho, int wo, int c, cudaStream_t s) {
+  if (c % 4 != 0) {
+    pool2_scalar_kernel<TIn, TOut><<<grid_for(static_cast<int64_t>(n) * ho * wo * c, 256), 256, 0, s>>>(
+        static_cast<const TIn*>(x), add, static_cast<TOut*>(out), n, ho, wo, c, 0.25f);
+    GANB_CHECK_LAUNCH("pool2_scalar_kernel");
+    return 0;
+  }
   const int64_t items = static_cast<int64_t>(n) * ho * wo * (c / 4);
   meanpool2_fwd_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), add,
                                                                        static_cast<TOut*>(out), n, ho, wo, c);
@@ -855,7 +948,7 @@ static int launch_meanpool(const void* x, const float* add, void* out, int n, in
 extern "C" int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, void* out, int out_dtype, int n,
                                   int h, int w, int c, void* stream) {
   if (!x || !out) return fail(GANB_E_BADARG, "meanpool2_fwd: null buffer");
-  if (c % 4 != 0 || (h & 1) || (w & 1)) return fail(GANB_E_UNSUPPORTED, "meanpool2_fwd: c %% 4 and even h,w required");
+  if ((h & 1) || (w & 1)) return fail(GANB_E_UNSUPPORTED, "meanpool2_fwd: even h,w required");
   const int ho = h / 2, wo = w / 2;
   if (x_dtype == GANB_F32 && out_dtype == GANB_F32) return launch_meanpool<float, float>(x, add, out, n, ho, wo, c, STREAM);
   if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_meanpool<float, __nv_bfloat16>(x, add, out, n, ho, wo, c, STREAM);
@@ -865,6 +958,12 @@ extern "C" int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, 
 
 template <typename TIn, typename TOut>
 static int launch_expand(const void* x, void* out, int n, int h, int w, int c, float scale, cudaStream_t s) {
+  if (c % 4 != 0) {
+    expand2_scalar_kernel<TIn, TOut><<<grid_for(static_cast<int64_t>(n) * h * w * c, 256), 256, 0, s>>>(
+        static_cast<const TIn*>(x), static_cast<TOut*>(out), n, h, w, c, scale);
+    GANB_CHECK_LAUNCH("expand2_scalar_kernel");
+    return 0;
+  }
   const int64_t items = static_cast<int64_t>(n) * h * w * (c / 4);
   expand2_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(out), n, h, w, c, scale);
   GANB_CHECK_LAUNCH("expand2_kernel");
@@ -875,7 +974,6 @@ static int launch_expand(const void* x, void* out, int n, int h, int w, int c, f
 extern "C" int ganb_expand2(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c,
                             float scale, void* stream) {
   if (!x || !out) return fail(GANB_E_BADARG, "expand2: null buffer");
-  if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "expand2: c=%d must be a multiple of 4", c);
   if (x_dtype == GANB_F32 && out_dtype == GANB_F32) return launch_expand<float, float>(x, out, n, h, w, c, scale, STREAM);
   if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_expand<float, __nv_bfloat16>(x, out, n, h, w, c, scale, STREAM);
   if (x_dtype == GANB_BF16 && out_dtype == GANB_BF16) return launch_expand<__nv_bfloat16, __nv_bfloat16>(x, out, n, h, w, c, scale, STREAM);
@@ -884,6 +982,12 @@ extern "C" int ganb_expand2(const void* x, int x_dtype, void* out, int out_dtype
 
 template <typename TIn, typename TOut>
 static int launch_sum2x2(const void* x, void* out, int n, int ho, int wo, int c, float scale, cudaStream_t s) {
+  if (c % 4 != 0) {
+    pool2_scalar_kernel<TIn, TOut><<<grid_for(static_cast<int64_t>(n) * ho * wo * c, 256), 256, 0, s>>>(
+        static_cast<const TIn*>(x), nullptr, static_cast<TOut*>(out), n, ho, wo, c, scale);
+    GANB_CHECK_LAUNCH("pool2_scalar_kernel");
+    return 0;
+  }
   const int64_t items = static_cast<int64_t>(n) * ho * wo * (c / 4);
   sum2x2_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(out), n, ho, wo, c, scale);
   GANB_CHECK_LAUNCH("sum2x2_kernel");
@@ -894,7 +998,7 @@ static int launch_sum2x2(const void* x, void* out, int n, int ho, int wo, int c,
 extern "C" int ganb_sum2x2(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c,
                            float scale, void* stream) {
   if (!x || !out) return fail(GANB_E_BADARG, "sum2x2: null buffer");
-  if (c % 4 != 0 || (h & 1) || (w & 1)) return fail(GANB_E_UNSUPPORTED, "sum2x2: c %% 4 and even h,w required");
+  if ((h & 1) || (w & 1)) return fail(GANB_E_UNSUPPORTED, "sum2x2: even h,w required");
   const int ho = h / 2, wo = w / 2;
   if (x_dtype == GANB_F32 && out_dtype == GANB_F32) return launch_sum2x2<float, float>(x, out, n, ho, wo, c, scale, STREAM);
   if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_sum2x2<float, __nv_bfloat16>(x, out, n, ho, wo, c, scale, STREAM);
@@ -961,7 +1065,7 @@ extern "C" int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, floa
   else
     colsum_partial_kernel<float><<<used, 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, rows_per_chunk, static_cast<float*>(workspace));
   GANB_CHECK_LAUNCH("colsum_partial_kernel");
-  colsum_finalize_kernel<<<ceil_div(c, 128), 128, 0, STREAM>>>(static_cast<float*>(workspace), c, used, beta, out);
+  colsum_finalize_kernel<<<ceil_div(c, 32), 256, 0, STREAM>>>(static_cast<float*>(workspace), c, used, beta, out);
   GANB_CHECK_LAUNCH("colsum_finalize_kernel");
   return 0;
 }
@@ -979,23 +1083,31 @@ extern "C" int ganb_bcast_channels_fwd(const float* e, int n, int hw, int c2, in
 }
 
 extern "C" int ganb_bcast_channels_bwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
-                                       const void* d_raw_bf16, const void* d_act_bf16, float* de, void* stream) {
+                                       const void* d_raw, const void* d_act, int d_dtype, float* de, void* stream) {
   if (!e || !de) return fail(GANB_E_BADARG, "bcast_channels_bwd: null buffer");
   if (c2 % 4 || coff % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "bcast_channels_bwd: channel counts must be multiples of 4");
-  bcast_channels_bwd_kernel<<<n, 256, 0, STREAM>>>(e, hw, c2, coff, cstride, act,
-                                                   static_cast<const __nv_bfloat16*>(d_raw_bf16),
-                                                   static_cast<const __nv_bfloat16*>(d_act_bf16), de);
+  if (d_dtype == GANB_BF16)
+    bcast_channels_bwd_kernel<__nv_bfloat16><<<n, 256, 0, STREAM>>>(e, hw, c2, coff, cstride, act,
+                                                                    static_cast<const __nv_bfloat16*>(d_raw),
+                                                                    static_cast<const __nv_bfloat16*>(d_act), de);
+  else
+    bcast_channels_bwd_kernel<float><<<n, 256, 0, STREAM>>>(e, hw, c2, coff, cstride, act,
+                                                            static_cast<const float*>(d_raw),
+                                                            static_cast<const float*>(d_act), de);
   GANB_CHECK_LAUNCH("bcast_channels_bwd_kernel");
   return 0;
 }
 
-extern "C" int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw_bf16,
-                                 const void* d_act_bf16, float* dx, void* stream) {
+extern "C" int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw,
+                                 const void* d_act, int d_dtype, float* dx, void* stream) {
   if (!x || !dx) return fail(GANB_E_BADARG, "concat_bwd_x: null buffer");
   if (c1 % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "concat_bwd_x: channel counts must be multiples of 4");
-  concat_bwd_x_kernel<<<grid_for(pixels * (c1 / 4), 256), 256, 0, STREAM>>>(
-      x, pixels, c1, cstride, act, static_cast<const __nv_bfloat16*>(d_raw_bf16),
-      static_cast<const __nv_bfloat16*>(d_act_bf16), dx);
+  if (d_dtype == GANB_BF16)
+    concat_bwd_x_kernel<__nv_bfloat16><<<grid_for(pixels * (c1 / 4), 256), 256, 0, STREAM>>>(
+        x, pixels, c1, cstride, act, static_cast<const __nv_bfloat16*>(d_raw), static_cast<const __nv_bfloat16*>(d_act), dx);
+  else
+    concat_bwd_x_kernel<float><<<grid_for(pixels * (c1 / 4), 256), 256, 0, STREAM>>>(
+        x, pixels, c1, cstride, act, static_cast<const float*>(d_raw), static_cast<const float*>(d_act), dx);
   GANB_CHECK_LAUNCH("concat_bwd_x_kernel");
   return 0;
 }

@@ -210,6 +210,73 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const SgemmParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core route for the <=8-channel layers: an explicit bf16 im2col of the SMALL tensor (kh*kw*cs <= kpad
+// columns, 64 bytes per pixel for kpad = 32) turns fprop / wgrad / dgrad into 1x1 GEMMs for conv_tc.cu.
+//   out[(n,ho,wo)][(r*kw+s)*cs + c] = xs[n, ho + sign*(r-pad_t), wo + sign*(s-pad_l), c]   (0 outside / padding)
+__global__ void __launch_bounds__(256)
+im2col_small_kernel(const float* __restrict__ xs, __nv_bfloat16* __restrict__ out, int n, int hs, int ws, int cs,
+                    int ho, int wo, int kh, int kw, int pad_t, int pad_l, int sign, int kpad) {
+  const int groups = kpad >> 3;  // 8 bf16 = 16 bytes per thread
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * groups;
+  const int kvalid = kh * kw * cs;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int gq = static_cast<int>(i % groups);
+    const int64_t pix = i / groups;
+    const int w0 = static_cast<int>(pix % wo);
+    const int h0 = static_cast<int>((pix / wo) % ho);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(wo) * ho));
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = gq * 8 + e;
+      float val = 0.f;
+      if (j < kvalid) {
+        const int tap = j / cs, c = j - tap * cs;
+        const int r = tap / kw, sx = tap - r * kw;
+        const int hx = h0 + sign * (r - pad_t), wx = w0 + sign * (sx - pad_l);
+        if (hx >= 0 && hx < hs && wx >= 0 && wx < ws)
+          val = __ldg(xs + ((static_cast<int64_t>(ni) * hs + hx) * ws + wx) * cs + c);
+      }
+      v[e] = __float2bfloat16_rn(val);
+    }
+    *reinterpret_cast<uint4*>(out + pix * kpad + gq * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// out[l][tap*cs + c] (row stride kpad, zero padded) from the HWIO fp32 filter:
+//   small_is_ci: l = co, c = ci -> W[tap][c][l]   (fprop operand of a small-cin layer)
+//   otherwise  : l = ci, c = co -> W[tap][l][c]   (dgrad operand of a small-cout layer)
+__global__ void pack_small_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int ci,
+                                  int co, int small_is_ci, int kpad) {
+  const int nl = small_is_ci ? co : ci, cs = small_is_ci ? ci : co;
+  const int total = nl * kpad;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int l = i / kpad, j = i - l * kpad;
+  float v = 0.f;
+  if (j < taps * cs) {
+    const int tap = j / cs, c = j - tap * cs;
+    v = small_is_ci ? w[(static_cast<int64_t>(tap) * ci + c) * co + l] : w[(static_cast<int64_t>(tap) * ci + l) * co + c];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+// dw[tap][cs][cl] (or [tap][cl][cs] when out_clcs) = beta*dw + scale * r[tap*cs + c][l],  r is [kpad][cl] fp32
+__global__ void small_wgrad_scatter_kernel(const float* __restrict__ r, float* __restrict__ dw, int taps, int cs,
+                                           int cl, int out_clcs, const float* __restrict__ scale, float beta) {
+  const int total = taps * cs * cl;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int l = i % cl, j = i / cl;  // j = tap*cs + c
+  float v = r[static_cast<int64_t>(j) * cl + l];
+  if (scale) v *= __ldg(scale);
+  const int tap = j / cs, c = j - tap * cs;
+  const int64_t o = out_clcs ? (static_cast<int64_t>(tap) * cl + l) * cs + c : i;
+  dw[o] = (beta != 0.f ? beta * dw[o] : 0.f) + v;
+}
+
 }  // namespace ganb
 
 using namespace ganb;
@@ -292,5 +359,37 @@ extern "C" int ganb_sgemm_small(const float* a, const float* b, float* c, int m,
   p.alpha = alpha; p.bias = bias; p.beta = beta;
   sgemm_small_kernel<<<dim3(ceil_div(n, 16), ceil_div(m, 16)), 256, 0, STREAM>>>(p);
   GANB_CHECK_LAUNCH("sgemm_small_kernel");
+  return 0;
+}
+
+extern "C" int ganb_im2col_small(const float* xs, void* out_bf16, int n, int hs, int ws, int cs, int ho, int wo, int kh,
+                                 int kw, int pad_t, int pad_l, int sign, int kpad, void* stream) {
+  if (!xs || !out_bf16) return fail(GANB_E_BADARG, "im2col_small: null buffer");
+  if (kpad % 8 != 0 || kh * kw * cs > kpad) return fail(GANB_E_BADARG, "im2col_small: kh*kw*cs=%d does not fit kpad=%d", kh * kw * cs, kpad);
+  if (sign != 1 && sign != -1) return fail(GANB_E_BADARG, "im2col_small: sign must be +-1");
+  const int64_t items = static_cast<int64_t>(n) * ho * wo * (kpad / 8);
+  int64_t blocks = ceil_div64(items, 256);
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  im2col_small_kernel<<<static_cast<int>(blocks), 256, 0, STREAM>>>(xs, static_cast<__nv_bfloat16*>(out_bf16), n, hs, ws, cs,
+                                                                   ho, wo, kh, kw, pad_t, pad_l, sign, kpad);
+  GANB_CHECK_LAUNCH("im2col_small_kernel");
+  return 0;
+}
+
+extern "C" int ganb_pack_small(const float* w_hwio, void* out_bf16, int taps, int ci, int co, int small_is_ci, int kpad,
+                               void* stream) {
+  if (!w_hwio || !out_bf16) return fail(GANB_E_BADARG, "pack_small: null buffer");
+  const int nl = small_is_ci ? co : ci;
+  pack_small_kernel<<<ceil_div(nl * kpad, 256), 256, 0, STREAM>>>(w_hwio, static_cast<__nv_bfloat16*>(out_bf16), taps, ci, co,
+                                                                 small_is_ci, kpad);
+  GANB_CHECK_LAUNCH("pack_small_kernel");
+  return 0;
+}
+
+extern "C" int ganb_small_wgrad_scatter(const float* r, float* dw, int taps, int cs, int cl, int out_layout_clcs,
+                                        const float* scale, float beta, void* stream) {
+  if (!r || !dw) return fail(GANB_E_BADARG, "small_wgrad_scatter: null buffer");
+  small_wgrad_scatter_kernel<<<ceil_div(taps * cs * cl, 256), 256, 0, STREAM>>>(r, dw, taps, cs, cl, out_layout_clcs, scale, beta);
+  GANB_CHECK_LAUNCH("small_wgrad_scatter_kernel");
   return 0;
 }

@@ -1,5 +1,6 @@
 // Spectral normalisation (reference common/ops/sn.py:15-69) as grouped, bandwidth-bound warp-shuffle kernels:
-// one launch processes every spectrally-normalised weight of a network (one CTA per weight).
+// one launch sequence processes every spectrally-normalised weight of a network; each weight is split into
+// CTAs of 64 rows so that all SMs stream W (a single CTA per weight is DRAM-latency bound).
 //
 //   forward : a = W u ; v = a/(|a|+eps) ; b = W^T v ; u' = b/(|b|+eps) ; sigma = b.u' = |b|^2/(|b|+eps)
 //             (one power iteration, sn.py:34-47; sigma as at sn.py:52/58).  W/sigma is never materialised:
@@ -16,7 +17,8 @@
 namespace ganb {
 
 constexpr float SN_EPS = 1e-12f;  // sn.py:11
-constexpr int SN_THREADS = 1024;
+constexpr int SN_THREADS = 256;
+constexpr int SN_ROWS = 64;       // rows of W per CTA
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -42,84 +44,102 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;
 }
 
-// out_k = sum_c W[k,c] * x_c for all k: one warp per row, lanes stride the contiguous c dimension.
-__device__ __forceinline__ void rows_dot(const float* __restrict__ W, int K, int C, const float* __restrict__ xs,
-                                         float* __restrict__ out_s) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int k = warp; k < K; k += nwarps) {
-    const float* row = W + static_cast<int64_t>(k) * C;
-    float acc = 0.f;
+__device__ __forceinline__ int find_layer(const ganb_sn_layer* __restrict__ layers, int count, int blk) {
+  int l = 0;
+  while (l + 1 < count && blk >= layers[l + 1].blk_begin) ++l;
+  return l;
+}
+
+__device__ __forceinline__ float row_dot(const float* __restrict__ row, const float* __restrict__ xs, int C, int lane) {
+  float acc = 0.f;
+  if ((C & 3) == 0) {
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 w = *reinterpret_cast<const float4*>(row + c);
+      acc += w.x * xs[c] + w.y * xs[c + 1] + w.z * xs[c + 2] + w.w * xs[c + 3];
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) acc += row[c] * xs[c];
+  }
+  return warp_sum(acc);
+}
+
+// Forward, stage 1 (one pass over W, rows independent): a_k = row_k . u ; bt += a_k * row_k ; sa += a_k^2.
+// Since b = W^T v = W^T (a / (|a|+eps)), the un-normalised bt = W^T a is all that the second stage needs.
+// work layout per CTA of the layer: [C] partial bt, then 1 float partial sa (stride C + 4).
+__global__ void __launch_bounds__(SN_THREADS) sn_fwd_rows_kernel(const ganb_sn_layer* __restrict__ layers, int count) {
+  const int li = find_layer(layers, count, blockIdx.x);
+  const ganb_sn_layer L = layers[li];
+  const int K = L.k, C = L.c;
+  const int blk = blockIdx.x - L.blk_begin;
+  extern __shared__ float sm[];
+  float* u_s = sm;                 // [C]
+  float* bt_s = u_s + C;           // [8][C] per-warp partials
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) u_s[c] = L.u[c];
+  for (int i = threadIdx.x; i < 8 * C; i += blockDim.x) bt_s[i] = 0.f;
+  __syncthreads();
+  float* bt = bt_s + warp * C;
+  float sa = 0.f;
+  const int r0 = blk * SN_ROWS, r1 = min(K, r0 + SN_ROWS);
+  for (int k = r0 + warp; k < r1; k += 8) {
+    const float* row = L.w + static_cast<int64_t>(k) * C;
+    const float a = row_dot(row, u_s, C, lane);
+    if (lane == 0) L.v[k] = a;  // normalised in place by the finish kernel
+    sa += a * a;
     if ((C & 3) == 0) {
       for (int c = lane * 4; c < C; c += 128) {
         const float4 w = *reinterpret_cast<const float4*>(row + c);
-        acc += w.x * xs[c] + w.y * xs[c + 1] + w.z * xs[c + 2] + w.w * xs[c + 3];
+        bt[c] += a * w.x; bt[c + 1] += a * w.y; bt[c + 2] += a * w.z; bt[c + 3] += a * w.w;
       }
     } else {
-      for (int c = lane; c < C; c += 32) acc += row[c] * xs[c];
+      for (int c = lane; c < C; c += 32) bt[c] += a * row[c];
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out_s[k] = acc;
   }
+  __syncthreads();
+  float* out = L.work + static_cast<int64_t>(blk) * (C + 4);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += bt_s[w8 * C + c];
+    out[c] = t;
+  }
+  // sa is identical across the lanes of a warp; count it once per warp
+  const float tot = block_sum(lane == 0 ? sa : 0.f, red);
+  if (threadIdx.x == 0) out[C] = tot;
 }
 
-// out_c = sum_k W[k,c] * y_k for all c: threads own columns (coalesced along c), k split over row lanes.
-// `scratch` needs blockDim.x floats; result left in out_s[0..C).
-__device__ __forceinline__ void cols_dot(const float* __restrict__ W, int K, int C, const float* __restrict__ ys,
-                                         float* __restrict__ out_s, float* __restrict__ scratch) {
-  const int cols = min(C, static_cast<int>(blockDim.x));
-  const int lanes = blockDim.x / cols;
-  const int cx = threadIdx.x % cols, kl = threadIdx.x / cols;
-  for (int cb = 0; cb < C; cb += cols) {
-    const int c = cb + cx;
-    float acc = 0.f;
-    if (c < C && kl < lanes)
-      for (int k = kl; k < K; k += lanes) acc += W[static_cast<int64_t>(k) * C + c] * ys[k];
-    scratch[threadIdx.x] = acc;
-    __syncthreads();
-    if (kl == 0 && c < C) {
-      for (int l = 1; l < lanes; ++l) acc += scratch[l * cols + cx];
-      out_s[c] = acc;
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(SN_THREADS) sn_fwd_kernel(const ganb_sn_layer* __restrict__ layers, int assign) {
+// Forward, stage 2 (one CTA per weight): reduce the partials, normalise, emit u', sigma.
+__global__ void __launch_bounds__(SN_THREADS) sn_fwd_finish_kernel(const ganb_sn_layer* __restrict__ layers, int assign) {
   const ganb_sn_layer L = layers[blockIdx.x];
   const int K = L.k, C = L.c;
+  const int nblk = (K + SN_ROWS - 1) / SN_ROWS;
   extern __shared__ float sm[];
-  float* a_s = sm;              // [K]  a, then v
-  float* u_s = a_s + K;         // [C]  u, later b
-  float* b_s = u_s + C;         // [C]
-  float* scratch = b_s + C;     // [blockDim]
-  float* red = scratch + blockDim.x;  // [32]
-
-  for (int c = threadIdx.x; c < C; c += blockDim.x) u_s[c] = L.u[c];
-  __syncthreads();
-  rows_dot(L.w, K, C, u_s, a_s);
-  __syncthreads();
-  float part = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) part += a_s[k] * a_s[k];
-  const float na = sqrtf(block_sum(part, red));
+  float* b_s = sm;  // [C]
+  __shared__ float red[32];
+  float sa = 0.f;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) sa += L.work[static_cast<int64_t>(i) * (C + 4) + C];
+  const float na = sqrtf(block_sum(sa, red));
   const float inv_a = 1.f / (na + SN_EPS);
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float v = a_s[k] * inv_a;
-    a_s[k] = v;
-    L.v[k] = v;
+  float part = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int i = 0; i < nblk; ++i) t += L.work[static_cast<int64_t>(i) * (C + 4) + c];
+    t *= inv_a;  // b = W^T v
+    b_s[c] = t;
+    part += t * t;
   }
-  __syncthreads();
-  cols_dot(L.w, K, C, a_s, b_s, scratch);
-  part = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) part += b_s[c] * b_s[c];
   const float nb2 = block_sum(part, red);
   const float nb = sqrtf(nb2);
   const float inv_b = 1.f / (nb + SN_EPS);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) L.v[k] *= inv_a;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float un = b_s[c] * inv_b;
+    const float uo = L.u[c];
     L.b[c] = b_s[c];
     L.u_out[c] = un;
-    L.u_used[c] = u_s[c];
-    if (assign) L.u[c] = un;  // every read of u happened before the first block-wide barrier
+    L.u_used[c] = uo;
+    if (assign) L.u[c] = un;
   }
   if (threadIdx.x == 0) {
     const float sigma = nb2 * inv_b;
@@ -130,68 +150,109 @@ __global__ void __launch_bounds__(SN_THREADS) sn_fwd_kernel(const ganb_sn_layer*
   }
 }
 
-__global__ void __launch_bounds__(SN_THREADS) sn_bwd_kernel(const ganb_sn_layer* __restrict__ layers) {
+// Backward, stage 1 (rows independent): partial <G,W>, t_k = row_k . b, partial sum v_k t_k.
+__global__ void __launch_bounds__(SN_THREADS) sn_bwd_rows_kernel(const ganb_sn_layer* __restrict__ layers, int count) {
+  const int li = find_layer(layers, count, blockIdx.x);
+  const ganb_sn_layer L = layers[li];
+  const int K = L.k, C = L.c;
+  const int blk = blockIdx.x - L.blk_begin;
+  extern __shared__ float sm[];
+  float* b_s = sm;  // [C]
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) b_s[c] = L.b[c];
+  __syncthreads();
+  float gw = 0.f, vt = 0.f;
+  const int r0 = blk * SN_ROWS, r1 = min(K, r0 + SN_ROWS);
+  for (int k = r0 + warp; k < r1; k += 8) {
+    const float* row = L.w + static_cast<int64_t>(k) * C;
+    const float* grow = L.g + static_cast<int64_t>(k) * C;
+    const float t = row_dot(row, b_s, C, lane);
+    float acc = 0.f;
+    if ((C & 3) == 0) {
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 w = *reinterpret_cast<const float4*>(row + c);
+        const float4 g = *reinterpret_cast<const float4*>(grow + c);
+        acc += w.x * g.x + w.y * g.y + w.z * g.z + w.w * g.w;
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) acc += row[c] * grow[c];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      L.t[k] = t;
+      gw += acc;
+      vt += L.v[k] * t;
+    }
+  }
+  const float gw_tot = block_sum(gw, red);
+  const float vt_tot = block_sum(vt, red);
+  if (threadIdx.x == 0) {
+    float* out = L.work + static_cast<int64_t>(blk) * (C + 4);
+    out[C + 1] = gw_tot;
+    out[C + 2] = vt_tot;
+  }
+}
+
+// Backward, stage 2 (one small CTA per weight): scal[4] = coef (bbar = coef*b), scal[5] = sum v_k t_k.
+__global__ void __launch_bounds__(SN_THREADS) sn_bwd_finish_kernel(const ganb_sn_layer* __restrict__ layers) {
   const ganb_sn_layer L = layers[blockIdx.x];
   const int K = L.k, C = L.c;
-  const int64_t total = static_cast<int64_t>(K) * C;
-  extern __shared__ float sm[];
-  float* v_s = sm;              // [K]
-  float* ab_s = v_s + K;        // [K]  vbar then abar
-  float* bb_s = ab_s + K;       // [C]  bbar
-  float* u_s = bb_s + C;        // [C]
-  float* scratch = u_s + C;
-  float* red = scratch + blockDim.x;
-
-  const float sigma = L.scal[0], inv_sigma = L.scal[1], na = L.scal[2], nb = L.scal[3];
-  for (int k = threadIdx.x; k < K; k += blockDim.x) v_s[k] = L.v[k];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) u_s[c] = L.u_used[c];
-
-  // <G, W>
-  float part = 0.f;
-  if ((total & 3) == 0) {
-    const float4* g4 = reinterpret_cast<const float4*>(L.g);
-    const float4* w4 = reinterpret_cast<const float4*>(L.w);
-    for (int64_t i = threadIdx.x; i < (total >> 2); i += blockDim.x) {
-      const float4 g = g4[i], w = w4[i];
-      part += g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
-    }
-  } else {
-    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) part += L.g[i] * L.w[i];
+  const int nblk = (K + SN_ROWS - 1) / SN_ROWS;
+  __shared__ float red[32];
+  float gw = 0.f, vt = 0.f;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    gw += L.work[static_cast<int64_t>(i) * (C + 4) + C + 1];
+    vt += L.work[static_cast<int64_t>(i) * (C + 4) + C + 2];
   }
-  const float gw = block_sum(part, red);
-  const float gs = -gw * inv_sigma * inv_sigma;                   // dL/dsigma
-  const float den = nb + SN_EPS;
-  const float dsig_dnb = (nb * nb + 2.f * nb * SN_EPS) / (den * den);
-  const float coef = gs * dsig_dnb / nb;                          // bbar = coef * b
-  for (int c = threadIdx.x; c < C; c += blockDim.x) bb_s[c] = coef * L.b[c];
-  __syncthreads();
-  rows_dot(L.w, K, C, bb_s, ab_s);                                // vbar = W bbar
-  __syncthreads();
-  part = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) part += v_s[k] * ab_s[k];
-  const float vv = block_sum(part, red);
+  gw = block_sum(gw, red);
+  vt = block_sum(vt, red);
+  if (threadIdx.x == 0) {
+    const float inv_sigma = L.scal[1], nb = L.scal[3];
+    const float gs = -gw * inv_sigma * inv_sigma;  // dL/dsigma
+    const float den = nb + SN_EPS;
+    const float dsig_dnb = (nb * nb + 2.f * nb * SN_EPS) / (den * den);
+    L.scal[4] = gs * dsig_dnb / nb;
+    L.scal[5] = vt;
+  }
+}
+
+// Backward, stage 3 (rows independent): dW += G/sigma + v (x) bbar + abar (x) u_used.
+__global__ void __launch_bounds__(SN_THREADS) sn_bwd_apply_kernel(const ganb_sn_layer* __restrict__ layers, int count) {
+  const int li = find_layer(layers, count, blockIdx.x);
+  const ganb_sn_layer L = layers[li];
+  const int K = L.k, C = L.c;
+  const int blk = blockIdx.x - L.blk_begin;
+  extern __shared__ float sm[];
+  float* bb_s = sm;        // [C] bbar
+  float* u_s = bb_s + C;   // [C]
+  const float inv_sigma = L.scal[1], na = L.scal[2], coef = L.scal[4], vt = L.scal[5];
   const float inv_a = 1.f / (na + SN_EPS);
-  for (int k = threadIdx.x; k < K; k += blockDim.x) ab_s[k] = ab_s[k] * inv_a - v_s[k] * vv / na;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    bb_s[c] = coef * L.b[c];
+    u_s[c] = L.u_used[c];
+  }
   __syncthreads();
-  (void)sigma;
-  // dW += G/sigma + v (x) bbar + abar (x) u
-  if ((C & 3) == 0) {
-    const int c4n = C >> 2;
-    for (int64_t i = threadIdx.x; i < (total >> 2); i += blockDim.x) {
-      const int k = static_cast<int>(i / c4n), c = static_cast<int>(i % c4n) * 4;
-      const float4 g = reinterpret_cast<const float4*>(L.g)[i];
-      float4 d = reinterpret_cast<float4*>(L.dw)[i];
-      const float vk = v_s[k], ak = ab_s[k];
-      d.x += g.x * inv_sigma + vk * bb_s[c] + ak * u_s[c];
-      d.y += g.y * inv_sigma + vk * bb_s[c + 1] + ak * u_s[c + 1];
-      d.z += g.z * inv_sigma + vk * bb_s[c + 2] + ak * u_s[c + 2];
-      d.w += g.w * inv_sigma + vk * bb_s[c + 3] + ak * u_s[c + 3];
-      reinterpret_cast<float4*>(L.dw)[i] = d;
-    }
-  } else {
-    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-      const int k = static_cast<int>(i / C), c = static_cast<int>(i % C);
-      L.dw[i] += L.g[i] * inv_sigma + v_s[k] * bb_s[c] + ab_s[k] * u_s[c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = blk * SN_ROWS, r1 = min(K, r0 + SN_ROWS);
+  for (int k = r0 + warp; k < r1; k += 8) {
+    const float vk = L.v[k];
+    // vbar_k = coef * t_k ; abar_k = vbar_k/(|a|+eps) - v_k (v.vbar)/|a|
+    const float ak = coef * (L.t[k] * inv_a - vk * vt / na);
+    const float* grow = L.g + static_cast<int64_t>(k) * C;
+    float* drow = L.dw + static_cast<int64_t>(k) * C;
+    if ((C & 3) == 0) {
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 g = *reinterpret_cast<const float4*>(grow + c);
+        float4 d = *reinterpret_cast<float4*>(drow + c);
+        d.x += g.x * inv_sigma + vk * bb_s[c] + ak * u_s[c];
+        d.y += g.y * inv_sigma + vk * bb_s[c + 1] + ak * u_s[c + 1];
+        d.z += g.z * inv_sigma + vk * bb_s[c + 2] + ak * u_s[c + 2];
+        d.w += g.w * inv_sigma + vk * bb_s[c + 3] + ak * u_s[c + 3];
+        *reinterpret_cast<float4*>(drow + c) = d;
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) drow[c] += grow[c] * inv_sigma + vk * bb_s[c] + ak * u_s[c];
     }
   }
 }
@@ -234,31 +295,30 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ganb_pack_layer
 using namespace ganb;
 #define STREAM static_cast<cudaStream_t>(stream)
 
-static int sn_smem_bytes(int max_k, int max_c, bool bwd) {
-  const int floats = bwd ? (2 * max_k + 2 * max_c) : (max_k + 2 * max_c);
-  return (floats + SN_THREADS + 32) * 4;
-}
-
-extern "C" int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, int max_k, int max_c, int assign,
+extern "C" int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, int total_blocks, int max_c, int assign,
                                   void* stream) {
-  if (!layers_dev || count <= 0) return fail(GANB_E_BADARG, "sn_power_iter: no layers");
-  const int smem = sn_smem_bytes(max_k, max_c, false);
-  if (smem > 200 * 1024) return fail(GANB_E_UNSUPPORTED, "sn_power_iter: K=%d too large for one CTA", max_k);
-  cudaError_t e = cudaFuncSetAttribute(sn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "sn_power_iter: %s", cudaGetErrorString(e));
-  sn_fwd_kernel<<<count, SN_THREADS, smem, STREAM>>>(layers_dev, assign);
-  GANB_CHECK_LAUNCH("sn_fwd_kernel");
+  if (!layers_dev || count <= 0 || total_blocks <= 0) return fail(GANB_E_BADARG, "sn_power_iter: no layers");
+  const int smem1 = 9 * max_c * 4;
+  if (smem1 > 200 * 1024) return fail(GANB_E_UNSUPPORTED, "sn_power_iter: c=%d too large", max_c);
+  if (smem1 > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sn_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "sn_power_iter: %s", cudaGetErrorString(e));
+  }
+  sn_fwd_rows_kernel<<<total_blocks, SN_THREADS, smem1, STREAM>>>(layers_dev, count);
+  GANB_CHECK_LAUNCH("sn_fwd_rows_kernel");
+  sn_fwd_finish_kernel<<<count, SN_THREADS, max_c * 4, STREAM>>>(layers_dev, assign);
+  GANB_CHECK_LAUNCH("sn_fwd_finish_kernel");
   return 0;
 }
 
-extern "C" int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int max_k, int max_c, void* stream) {
-  if (!layers_dev || count <= 0) return fail(GANB_E_BADARG, "sn_bwd: no layers");
-  const int smem = sn_smem_bytes(max_k, max_c, true);
-  if (smem > 200 * 1024) return fail(GANB_E_UNSUPPORTED, "sn_bwd: K=%d too large for one CTA", max_k);
-  cudaError_t e = cudaFuncSetAttribute(sn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "sn_bwd: %s", cudaGetErrorString(e));
-  sn_bwd_kernel<<<count, SN_THREADS, smem, STREAM>>>(layers_dev);
-  GANB_CHECK_LAUNCH("sn_bwd_kernel");
+extern "C" int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int total_blocks, int max_c, void* stream) {
+  if (!layers_dev || count <= 0 || total_blocks <= 0) return fail(GANB_E_BADARG, "sn_bwd: no layers");
+  sn_bwd_rows_kernel<<<total_blocks, SN_THREADS, max_c * 4, STREAM>>>(layers_dev, count);
+  GANB_CHECK_LAUNCH("sn_bwd_rows_kernel");
+  sn_bwd_finish_kernel<<<count, SN_THREADS, 0, STREAM>>>(layers_dev);
+  GANB_CHECK_LAUNCH("sn_bwd_finish_kernel");
+  sn_bwd_apply_kernel<<<total_blocks, SN_THREADS, 2 * max_c * 4, STREAM>>>(layers_dev, count);
+  GANB_CHECK_LAUNCH("sn_bwd_apply_kernel");
   return 0;
 }
 

@@ -21,6 +21,7 @@ import torch
 
 from . import kernels as K
 
+SMALL_K = 32  # im2col width (bf16 columns) of the <=8-channel tensor-core route
 _ALIGN = 64  # floats: every variable starts on a 256-byte boundary inside the flat buffers
 
 
@@ -33,11 +34,13 @@ class Var:
         self.data = data
         self.grad = None
         self.requires_grad = requires_grad
-        self.grad_dtype = grad_dtype  # dtype producers should use for this value's gradient (None: data dtype)
+        self.grad_dtype = grad_dtype  # dtype producers should use for this value's gradient (None: fp32)
 
     @property
     def gdtype(self):
-        return self.grad_dtype if self.grad_dtype is not None else self.data.dtype
+        # Gradients are kept in fp32 unless a consumer asks for the bf16 tensor-core operand directly: the
+        # batch-norm backward subtracts the per-channel mean of the gradient, which amplifies bf16 rounding.
+        return self.grad_dtype if self.grad_dtype is not None else torch.float32
 
     @property
     def shape(self):
@@ -150,7 +153,10 @@ class SNEntry:
         self.u_used = torch.zeros(self.c, **f32)
         self.v = torch.zeros(self.k, **f32)
         self.b = torch.zeros(self.c, **f32)
-        self.scal = torch.zeros(4, **f32)            # sigma, 1/sigma, |Wu|, |b|
+        self.scal = torch.zeros(8, **f32)            # sigma, 1/sigma, |Wu|, |b|, bwd scratch
+        self.nblk = -(-self.k // 64)
+        self.t = torch.zeros(self.k, **f32)
+        self.work = torch.zeros(self.nblk * (self.c + 4), **f32)
         self.g = torch.zeros(self.k, self.c, **f32)  # dL/d(W/sigma), written by the layer's wgrad
         self.g_written = False
         self.fresh = False
@@ -186,15 +192,17 @@ class SNGroup:
         return e
 
     def _build_table(self, entries):
-        items = []
+        items, blocks = [], 0
         for e in entries:
             if e.w.grad is None:
                 e.w.grad = torch.zeros_like(e.w.data)
             items.append(K.SnLayerStruct(e.w.data.data_ptr(), e.u.data.data_ptr(), e.u_out.data_ptr(),
                                          e.u_used.data_ptr(), e.v.data_ptr(), e.b.data_ptr(), e.scal.data_ptr(),
-                                         e.g.data_ptr(), e.w.grad.data_ptr(), e.k, e.c))
+                                         e.g.data_ptr(), e.w.grad.data_ptr(), e.t.data_ptr(), e.work.data_ptr(),
+                                         e.k, e.c, blocks, 0))
+            blocks += e.nblk
         dev = entries[0].w.data.device
-        return K.struct_array_to_device(items, dev), max(e.k for e in entries), max(e.c for e in entries)
+        return K.struct_array_to_device(items, dev), blocks, max(e.c for e in entries)
 
     def _ptrs(self):
         return tuple((e.w.data.data_ptr(), e.u.data.data_ptr(), 0 if e.w.grad is None else e.w.grad.data_ptr())
@@ -203,9 +211,9 @@ class SNGroup:
     def _run(self, assign: bool) -> None:
         entries = list(self.entries.values())
         if self.table is None or self.table_ptrs != self._ptrs():
-            self.table, self.max_k, self.max_c = self._build_table(entries)
+            self.table, self.blocks, self.max_c = self._build_table(entries)
             self.table_ptrs = self._ptrs()
-        K.sn_power_iter(self.table, len(entries), self.max_k, self.max_c, assign)
+        K.sn_power_iter(self.table, len(entries), self.blocks, self.max_c, assign)
 
     def acquire(self, e: SNEntry, assign: bool) -> None:
         """Makes e.scal / e.v / e.u_used current for this evaluation of the network.
@@ -234,10 +242,10 @@ class SNGroup:
     def backward(self, entries) -> None:
         all_entries = list(self.entries.values())
         if len(entries) == len(all_entries) and self.table is not None and self.table_ptrs == self._ptrs():
-            K.sn_bwd(self.table, len(all_entries), self.max_k, self.max_c)
+            K.sn_bwd(self.table, len(all_entries), self.blocks, self.max_c)
         else:
-            table, mk, mc = self._build_table(entries)
-            K.sn_bwd(table, len(entries), mk, mc)
+            table, blocks, mc = self._build_table(entries)
+            K.sn_bwd(table, len(entries), blocks, mc)
         for e in entries:
             e.g_written = False
 
@@ -252,6 +260,15 @@ class PackEntry:
         dev = w.data.device
         self.wn = torch.empty(self.taps, self.ci, self.co, dtype=torch.bfloat16, device=dev)  # [tap][ci][co]
         self.wt = torch.empty(self.taps, self.co, self.ci, dtype=torch.bfloat16, device=dev)  # [tap][co][ci]
+        # <=8-channel side: [large channel][tap*cs + c] padded to SMALL_K columns (operand of the im2col route)
+        self.small = None
+        self.ws = None
+        if self.ci <= 8 and self.taps * self.ci <= SMALL_K:
+            self.small = "ci"
+            self.ws = torch.empty(self.co, SMALL_K, dtype=torch.bfloat16, device=dev)
+        elif self.co <= 8 and self.taps * self.co <= SMALL_K:
+            self.small = "co"
+            self.ws = torch.empty(self.ci, SMALL_K, dtype=torch.bfloat16, device=dev)
 
 
 class PackGroup:
@@ -291,6 +308,9 @@ class PackGroup:
             self.total_tiles = tiles
             self.table_ptrs = self._ptrs()
         K.pack_weights(self.table, len(entries), self.total_tiles)
+        for e in entries:
+            if e.small is not None:
+                K.pack_small(e.w.data, e.ws, e.taps, e.ci, e.co, e.small == "ci", SMALL_K)
         self.valid_for = ver
 
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from . import kernels as K
-from .framework import Var, Variable, get_store
+from .framework import SMALL_K, Var, Variable, get_store
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -108,33 +108,43 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     """NHWC x HWIO cross-correlation (tf.nn.conv2d, common/ops/conv2d.py:181-187) + bias (+ residual), fp32 out.
 
     `sn` is a framework.SNEntry whose 1/sigma multiplies the accumulator (W/sigma is never materialised).
-    in_scale folds the PGGAN `inputs_norm` constant (conv2d.py:93-95) into the same epilogue factor."""
+    Every shape runs on the tensor cores: layers with <= 8 channels on one side go through a bf16 im2col of the
+    small tensor (kh*kw*c <= 32 columns) and become 1x1 GEMMs; larger small-channel filters fall back to the
+    CUDA-core kernels of smallconv.cu."""
     if stride != 1:
         raise NotImplementedError("strided convolutions are not built yet (SURVEY 8(f)); stride must be 1")
+    if in_scale is not None:
+        raise NotImplementedError("inputs_norm is not wired into the convolution epilogue yet")
     store = get_store()
     n, h, w, cin = x.shape
     cout = W.data.shape[-1]
+    taps = kh * kw
     pt, pl, ho, wo = _pads(padding, h, w, kh, kw, stride)
     alpha = sn.inv_sigma if sn is not None else None
-    if in_scale is not None:
-        raise NotImplementedError("inputs_norm is not wired into the convolution epilogue yet")
     bias = b.data if b is not None else None
     res = residual.data if residual is not None else None
-    small_in = cin <= 8
-    pack = None
+    small_in, small_out = cin <= 8, cout <= 8
+    route_in = small_in and taps * cin <= SMALL_K and cout % 8 == 0
+    route_out = (not small_in) and small_out and taps * cout <= SMALL_K and cin % 8 == 0
+    group = store.pack_group(W.root)
+    pack = group.entry(W)
+    group.refresh()
+    xcol = None
     if small_in:
-        if res is not None:
-            raise NotImplementedError("residual with <=8 input channels")
         xin = x if x.data.dtype == F32 else cast(x, F32)
-        y = K.conv_smallcin(xin.data, W.data, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, False, alpha, bias,
-                            None, F32)
+        if route_in:
+            xcol = K.im2col_small(xin.data, n, h, w, cin, ho, wo, kh, kw, pt, pl, +1, SMALL_K)
+            y = K.conv_igemm(xcol, pack.ws, n, ho, wo, SMALL_K, ho, wo, cout, 1, 1, 0, 0, False, alpha, bias, res,
+                             None, F32)
+        else:
+            if res is not None:
+                raise NotImplementedError("residual on the CUDA-core small-channel path")
+            y = K.conv_smallcin(xin.data, W.data, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, False, alpha,
+                                bias, None, F32)
     else:
         if cin % 8:
             raise NotImplementedError(f"cin={cin}: tensor-core path needs cin % 8 == 0")
         xin = x if x.data.dtype == BF16 else cast(x, BF16)
-        group = store.pack_group(W.root)
-        pack = group.entry(W)
-        group.refresh()
         y = K.conv_igemm(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res,
                          None, F32)
     out = Var(y, grad_dtype=out_grad_dtype)
@@ -152,44 +162,54 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                 residual.accum(gy if gy.dtype == residual.gdtype else K.cast(gy, residual.gdtype))
             if need_b:
                 K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
-            small_out = cout <= 8
+            need_x = xin.requires_grad
+            if not (need_w or need_x):
+                return
             gy16 = None
-            if not small_out and (need_w or xin.requires_grad):
+            if not small_out:
                 gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
+            dycol = None
+            if route_out:
+                gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
+                dycol = K.im2col_small(gy32, n, ho, wo, cout, h, w, kh, kw, pt, pl, -1, SMALL_K)
             if need_w:
                 if sn is not None:
-                    dst, beta, scale = sn.g, (1.0 if sn.g_written else 0.0), None
+                    dst, beta = sn.g, (1.0 if sn.g_written else 0.0)
                 else:
-                    dst, beta, scale = W.grad, 1.0, None
-                if small_in:
+                    dst, beta = W.grad, 1.0
+                if route_in:
+                    r = torch.empty((SMALL_K, cout), dtype=F32, device=gy.device)
+                    K.conv_wgrad(xcol, gy16, r, n, ho, wo, SMALL_K, ho, wo, cout, 1, 1, 0, 0, None, 0.0)
+                    K.small_wgrad_scatter(r, dst, taps, cin, cout, False, None, beta)
+                elif route_out:
+                    r = torch.empty((SMALL_K, cin), dtype=F32, device=gy.device)
+                    K.conv_wgrad(dycol, xin.data, r, n, h, w, SMALL_K, h, w, cin, 1, 1, 0, 0, None, 0.0)
+                    K.small_wgrad_scatter(r, dst, taps, cout, cin, True, None, beta)
+                elif small_in:
                     K.conv_small_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, +1, False,
-                                       scale, beta)
+                                       None, beta)
                 elif small_out:
                     gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
                     K.conv_small_wgrad(gy32, xin.data, dst, n, ho, wo, cout, h, w, cin, kh, kw, pt, pl, -1, True,
-                                       scale, beta)
+                                       None, beta)
                 else:
-                    K.conv_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, scale, beta)
+                    K.conv_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, None, beta)
                 if sn is not None:
                     sn.g_written = True
                     lst = tape.pending_sn.setdefault(W.root, [])
                     if sn not in lst:
                         lst.append(sn)
-            if xin.requires_grad:
+            if need_x:
                 gdt = xin.gdtype
-                if small_out:
-                    # dx = conv(dy, flipped W^T): dy has <=8 channels -> CUDA-core kernel, W is [tap][cl][cs]
+                if route_out:
+                    dx = K.conv_igemm(dycol, pack.ws, n, h, w, SMALL_K, h, w, cin, 1, 1, 0, 0, False, alpha, None,
+                                      None, None, gdt)
+                elif small_out:
                     gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
                     dx = K.conv_smallcin(gy32, W.data, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl,
                                          True, True, alpha, None, None, gdt)
                 else:
-                    if pack is None:
-                        group2 = store.pack_group(W.root)
-                        pk = group2.entry(W)
-                        group2.refresh()
-                    else:
-                        pk = pack
-                    dx = K.conv_igemm(gy16, pk.wn, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
+                    dx = K.conv_igemm(gy16, pack.wn, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
                                       alpha, None, None, None, gdt)
                 xin.accum(dx)
         tape.record(bwd)
@@ -390,6 +410,8 @@ def concat_label_map(x: Var, e: Var, act="relu"):
             d_raw, d_act = raw_v.grad, act_v.grad
             if d_raw is None and d_act is None:
                 return
+            if d_raw is not None and d_act is not None and d_raw.dtype != d_act.dtype:
+                d_raw, d_act = K.cast(d_raw, F32), K.cast(d_act, F32)
             if e.requires_grad:
                 e.accum(K.bcast_channels_bwd(e.data, n, h * w, c2, c1, ct, act, d_raw, d_act))
             if x.requires_grad:

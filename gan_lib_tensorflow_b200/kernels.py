@@ -120,6 +120,23 @@ def conv_small_wgrad(xs, yl, dw, n, hs, ws_, cs, hl, wl, cl, kh, kw, pad_t, pad_
           "ganb_conv2d_small_wgrad")
 
 
+def im2col_small(xs, n, hs, ws_, cs, ho, wo, kh, kw, pad_t, pad_l, sign, kpad=32):
+    out = torch.empty((n, ho, wo, kpad), dtype=torch.bfloat16, device=xs.device)
+    check(L().ganb_im2col_small(ptr(xs), ptr(out), n, hs, ws_, cs, ho, wo, kh, kw, pad_t, pad_l, sign, kpad, _stream()),
+          "ganb_im2col_small")
+    return out
+
+
+def pack_small(w, out, taps, ci, co, small_is_ci, kpad=32):
+    check(L().ganb_pack_small(ptr(w), ptr(out), taps, ci, co, int(bool(small_is_ci)), kpad, _stream()),
+          "ganb_pack_small")
+
+
+def small_wgrad_scatter(r, dw, taps, cs, cl, out_clcs, scale, beta):
+    check(L().ganb_small_wgrad_scatter(ptr(r), ptr(dw), taps, cs, cl, int(bool(out_clcs)), ptr(scale), c_float(beta),
+                                       _stream()), "ganb_small_wgrad_scatter")
+
+
 def sgemm_small(a, b, c, m, n, k, trans_a, trans_b, alpha=None, bias=None, beta=0.0):
     check(L().ganb_sgemm_small(ptr(a), ptr(b), ptr(c), m, n, k, int(trans_a), int(trans_b), ptr(alpha), ptr(bias),
                                c_float(beta), _stream()), "ganb_sgemm_small")
@@ -152,8 +169,9 @@ def norm_act_bwd(x, dz, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta,
     ws = None
     if mean is not None:
         ws = _ws(L().ganb_norm_act_bwd_workspace(n, h * w, c, groups), x.device)
+    n_rows = int(gamma.shape[0]) if (gamma is not None and gamma.dim() == 2) else 1
     check(L().ganb_norm_act_bwd(ptr(x), ptr(dz), dt(dz), dz_cstride, n, h, w, c, ptr(mean), ptr(rstd), groups,
-                                ptr(gamma), ptr(beta), ptr(labels), act_code(act), int(bool(upsample)), ptr(dgamma),
+                                ptr(gamma), ptr(beta), ptr(labels), n_rows, act_code(act), int(bool(upsample)), ptr(dgamma),
                                 ptr(dbeta), ptr(add), ptr(dx), dt(dx), ptr(ws), _stream()), "ganb_norm_act_bwd")
     return dx
 
@@ -193,15 +211,17 @@ def bcast_channels_fwd(e, n, hw, c2, coff, cstride, act, out_raw, out_act):
 
 def bcast_channels_bwd(e, n, hw, c2, coff, cstride, act, d_raw, d_act):
     de = torch.empty((n, c2), dtype=torch.float32, device=e.device)
-    check(L().ganb_bcast_channels_bwd(ptr(e), n, hw, c2, coff, cstride, act_code(act), ptr(d_raw), ptr(d_act),
+    gd = dt(d_raw if d_raw is not None else d_act)
+    check(L().ganb_bcast_channels_bwd(ptr(e), n, hw, c2, coff, cstride, act_code(act), ptr(d_raw), ptr(d_act), gd,
                                       ptr(de), _stream()), "ganb_bcast_channels_bwd")
     return de
 
 
 def concat_bwd_x(x, pixels, c1, cstride, act, d_raw, d_act):
     dx = torch.empty_like(x)
-    check(L().ganb_concat_bwd_x(ptr(x), c_int64(pixels), c1, cstride, act_code(act), ptr(d_raw), ptr(d_act), ptr(dx),
-                                _stream()), "ganb_concat_bwd_x")
+    gd = dt(d_raw if d_raw is not None else d_act)
+    check(L().ganb_concat_bwd_x(ptr(x), c_int64(pixels), c1, cstride, act_code(act), ptr(d_raw), ptr(d_act), gd,
+                                ptr(dx), _stream()), "ganb_concat_bwd_x")
     return dx
 
 
@@ -252,8 +272,9 @@ def embedding_bwd(dout, labels, n, dim, vocab, dtable):
 # ------------------------------------------------------------------------------------------------ grouped SN / pack
 class SnLayerStruct(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("u", c_void_p), ("u_out", c_void_p), ("u_used", c_void_p), ("v", c_void_p),
-                ("b", c_void_p),
-                ("scal", c_void_p), ("g", c_void_p), ("dw", c_void_p), ("k", ctypes.c_int32), ("c", ctypes.c_int32)]
+                ("b", c_void_p), ("scal", c_void_p), ("g", c_void_p), ("dw", c_void_p), ("t", c_void_p),
+                ("work", c_void_p), ("k", ctypes.c_int32), ("c", ctypes.c_int32), ("blk_begin", ctypes.c_int32),
+                ("pad_", ctypes.c_int32)]
 
 
 class PackLayerStruct(ctypes.Structure):
@@ -268,13 +289,13 @@ def struct_array_to_device(items, device) -> torch.Tensor:
     return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
 
 
-def sn_power_iter(table_dev, count, max_k, max_c, assign):
-    check(L().ganb_sn_power_iter(ptr(table_dev), count, max_k, max_c, int(bool(assign)), _stream()),
+def sn_power_iter(table_dev, count, total_blocks, max_c, assign):
+    check(L().ganb_sn_power_iter(ptr(table_dev), count, total_blocks, max_c, int(bool(assign)), _stream()),
           "ganb_sn_power_iter")
 
 
-def sn_bwd(table_dev, count, max_k, max_c):
-    check(L().ganb_sn_bwd(ptr(table_dev), count, max_k, max_c, _stream()), "ganb_sn_bwd")
+def sn_bwd(table_dev, count, total_blocks, max_c):
+    check(L().ganb_sn_bwd(ptr(table_dev), count, total_blocks, max_c, _stream()), "ganb_sn_bwd")
 
 
 def pack_weights(table_dev, count, total_tiles):

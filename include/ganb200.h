@@ -95,6 +95,18 @@ int ganb_conv2d_small_wgrad(const float* xs, const void* yl, int yl_dtype, float
                             int ws, int cs, int hl, int wl, int cl, int kh, int kw, int pad_t, int pad_l, int sign,
                             int out_layout_clcs, const float* scale, float beta, void* stream);
 
+/* Tensor-core route for the same <=8-channel layers: bf16 im2col of the small tensor (kh*kw*cs <= kpad columns)
+ * makes fprop / wgrad / dgrad 1x1 GEMMs for ganb_conv2d_igemm / ganb_conv2d_wgrad.
+ *   im2col_small : out[(n,ho,wo)][(r*kw+s)*cs + c] = xs[n, ho + sign*(r-pad_t), wo + sign*(s-pad_l), c], zero padded
+ *   pack_small   : out[l][tap*cs + c] (row stride kpad): small_is_ci ? W[tap][c][l] : W[tap][l][c]
+ *   small_wgrad_scatter : dw[tap][cs][cl] (or [tap][cl][cs]) = beta*dw + scale * r[tap*cs + c][l], r = [kpad][cl] */
+int ganb_im2col_small(const float* xs, void* out_bf16, int n, int hs, int ws, int cs, int ho, int wo, int kh, int kw,
+                      int pad_t, int pad_l, int sign, int kpad, void* stream);
+int ganb_pack_small(const float* w_hwio, void* out_bf16, int taps, int ci, int co, int small_is_ci, int kpad,
+                    void* stream);
+int ganb_small_wgrad_scatter(const float* r, float* dw, int taps, int cs, int cl, int out_layout_clcs,
+                             const float* scale, float beta, void* stream);
+
 /* Tiny dense layers (tf.matmul, common/ops/linear.py:163-173, for shapes the TMA path cannot take):
  * C[m,n] = beta*C + alpha * op(A)[m,k] * op(B)[k,n] + bias[n]; trans_a: A stored [k,m]; trans_b: B stored [n,k]. */
 int ganb_sgemm_small(const float* a, const float* b, float* c, int m, int n, int k, int trans_a, int trans_b,
@@ -114,15 +126,20 @@ typedef struct ganb_sn_layer {
   float* u_used;    /* [c]  the u this evaluation started from (needed by the backward pass) */
   float* v;         /* [k]  */
   float* b;         /* [c]  W^T v before normalisation */
-  float* scal;      /* [4]  sigma, 1/sigma, |W u|, |b| */
+  float* scal;      /* [8]  sigma, 1/sigma, |W u|, |b|, (bwd scratch: coef, v.t), -, - */
   const float* g;   /* bwd only: [k, c] gradient w.r.t. W/sigma */
   float* dw;        /* bwd only: [k, c] accumulated gradient w.r.t. W */
+  float* t;         /* [k]  bwd scratch (W b) */
+  float* work;      /* [ceil(k/64) * (c + 4)] per-CTA partials */
   int32_t k, c;
+  int32_t blk_begin; /* prefix sum of ceil(k/64) over the preceding layers */
+  int32_t pad_;
 } ganb_sn_layer;
 /* assign=1 reproduces update_collection=None (u.assign(u_final) on every evaluation, sn.py:48-56);
  * assign=0 reproduces update_collection="NO_OPS" (sn.py:62-64): u is left untouched. */
-int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, int max_k, int max_c, int assign, void* stream);
-int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int max_k, int max_c, void* stream);
+int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, int total_blocks, int max_c, int assign,
+                       void* stream);
+int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int total_blocks, int max_c, void* stream);
 
 /* fp32 HWIO filters -> bf16 operands of the tensor-core kernels; wn = [tap][ci][co], wt = [tap][co][ci]
  * (either may be NULL).  tile_begin = prefix sum of taps*ceil(ci/32)*ceil(co/32) over the layers. */
@@ -154,13 +171,13 @@ int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, float eps, f
 int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, const float* mean, const float* rstd, int groups,
                       const float* gamma, const float* beta, const int* labels, int act, int upsample, void* out,
                       int out_dtype, int out_cstride, void* out_raw_bf16, int raw_cstride, void* stream);
-/* dx = d(loss)/dx given dz = d(loss)/d(out); dgamma/dbeta (tables, may be NULL) are accumulated;
+/* dx = d(loss)/dx given dz = d(loss)/d(out); dgamma/dbeta (tables of n_rows rows, may be NULL) are accumulated;
  * `add` (fp32, optional) is added to dx. */
 int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups);
 int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w, int c,
                       const float* mean, const float* rstd, int groups, const float* gamma, const float* beta,
-                      const int* labels, int act, int upsample, float* dgamma, float* dbeta, const float* add,
-                      void* dx, int dx_dtype, void* workspace, void* stream);
+                      const int* labels, int n_rows, int act, int upsample, float* dgamma, float* dbeta,
+                      const float* add, void* dx, int dx_dtype, void* workspace, void* stream);
 
 /* 2x2 mean-pool written as in common/resnet_block.py:62-63 (add_n of four strided slices / 4), + optional add */
 int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, void* out, int out_dtype, int n, int h, int w,
@@ -185,9 +202,9 @@ int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, float beta, flo
 int ganb_bcast_channels_fwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
                             void* out_raw_bf16, void* out_act_bf16, void* stream);
 int ganb_bcast_channels_bwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
-                            const void* d_raw_bf16, const void* d_act_bf16, float* de, void* stream);
-int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw_bf16,
-                      const void* d_act_bf16, float* dx, void* stream);
+                            const void* d_raw, const void* d_act, int d_dtype, float* de, void* stream);
+int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw,
+                      const void* d_act, int d_dtype, float* dx, void* stream);
 
 /* out[n,c] = mean_hw act(x) : nonlinearity + tf.reduce_mean(axis=[1,2]) (gan_cifar_resnet.py:299-301) */
 int ganb_act_mean_hw_fwd(const float* x, int n, int hw, int c, int act, float* out, void* stream);

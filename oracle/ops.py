@@ -22,6 +22,45 @@ from . import tfshim
 
 NO_OPS = "NO_OPS"
 
+# When True the oracle rounds the operands of every convolution / large matmul to bf16 at exactly the points
+# where the B200 kernels do (activations, raw filters, output gradients; fp32 accumulation everywhere).  This
+# separates "is the implementation right" (bf16-operand oracle vs product: ~1e-5) from "how far is bf16 from
+# fp32" (fp32 oracle vs product: the <=1e-2 per-layer tolerance of the north star).
+BF16_OPERANDS = False
+
+
+def _r16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def _ste_r16(t):
+    """bf16 rounding with a straight-through gradient."""
+    return t + (_r16(t) - t).detach()
+
+
+class _ConvRoundedOperands(torch.autograd.Function):
+    """y = conv(r16(x), w): forward rounds the activation; backward rounds dy and uses the rounded x:
+    dw = wgrad(r16(x), r16(dy)), dx = dgrad(r16(dy), w) -- the operand roundings of conv_tc.cu."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding):
+        xr = _r16(x)
+        ctx.save_for_backward(xr, w)
+        ctx.cfg = (stride, padding)
+        return conv2d_nhwc(xr, w, stride, padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, w = ctx.saved_tensors
+        stride, padding = ctx.cfg
+        gyr = _r16(gy)
+        with torch.enable_grad():
+            x_ = xr.detach().requires_grad_(True)
+            w_ = w.detach().requires_grad_(True)
+            y = conv2d_nhwc(x_, w_, stride, padding)
+            dx, dw = torch.autograd.grad(y, (x_, w_), gyr)
+        return dx, dw, None, None
+
 # module-level switches of conv2d.py:10-28 / linear.py:12-35 / deconv2d.py:8-26
 _default_weightnorm = False
 _weights_stdev = None
@@ -167,10 +206,18 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
             target_norms = g.get_variable("g", initializer=norm_values)
             norms = torch.sqrt(torch.sum(filters ** 2, dim=(0, 1, 2)))
             filters = filters * (target_norms / norms)
+        raw_filters = filters
         if spectral_normed:                                           # conv2d.py:169-171
             with g.variable_scope("filters"):
-                filters = spectral_normed_weight(g, filters, update_collection=update_collection)
-        result = conv2d_nhwc(inputs_, filters, stride, padding)       # conv2d.py:181-187
+                filters, sigma = spectral_normed_weight(g, filters, update_collection=update_collection,
+                                                        with_sigma=True)
+        if BF16_OPERANDS:
+            wq = _ste_r16(raw_filters)
+            if spectral_normed:
+                wq = wq / sigma
+            result = _ConvRoundedOperands.apply(inputs_, wq, stride, padding)
+        else:
+            result = conv2d_nhwc(inputs_, filters, stride, padding)   # conv2d.py:181-187
         if biases:                                                    # conv2d.py:212-216
             b = g.get_variable("Biases", initializer=tfshim.constant_initializer(0.0), shape=[output_dim])
             result = result + b
@@ -254,7 +301,13 @@ def Linear(g, inputs, input_dim, output_dim, name, spectral_normed=False, update
             norms = torch.sqrt(torch.sum(weight ** 2, dim=0))
             weight = weight * (target_norms / norms)
         w_eff = spectral_normed_weight(g, weight, update_collection=update_collection) if spectral_normed else weight
-        if inputs_.dim() == 2:                                        # linear.py:161-165
+        if (BF16_OPERANDS and inputs_.dim() == 2 and input_dim % 8 == 0 and output_dim % 8 == 0
+                and input_dim * output_dim >= 65536 and not spectral_normed):
+            # the product runs this layer as a 1x1 convolution on the tensor cores
+            x4 = inputs_.reshape(-1, 1, 1, input_dim)
+            w4 = _ste_r16(weight).reshape(1, 1, input_dim, output_dim)
+            result = _ConvRoundedOperands.apply(x4, w4, 1, "VALID").reshape(-1, output_dim)
+        elif inputs_.dim() == 2:                                      # linear.py:161-165
             result = inputs_ @ w_eff
         else:                                                         # linear.py:166-174
             result = (inputs_.reshape(-1, input_dim) @ w_eff).reshape(*inputs_.shape[:-1], output_dim)

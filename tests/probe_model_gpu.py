@@ -25,42 +25,49 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
 
 
+def run_oracle(bf16, data, labels, z_d, deq, z_g, fl):
+    O_ops.BF16_OPERANDS = bf16
+    np.random.seed(0)
+    om = O.SNGANCifar(dtype=torch.float32, u_seed=2)
+    om.build()
+    lab_t = torch.tensor(labels).long()
+    res = {"om": om}
+    with torch.no_grad():
+        f0 = O.Generator(om.g, 32, lab_t[:32], torch.from_numpy(z_d[:32]), reuse=True)
+        f1 = O.Generator(om.g, 32, lab_t[32:], torch.from_numpy(z_d[32:]), reuse=True)
+        res["fake"] = torch.cat([f0, f1]).numpy()
+    cost_o, params_o, grads_o = om.disc_grads(torch.tensor(data), lab_t,
+                                              [torch.from_numpy(z_d[:32]), torch.from_numpy(z_d[32:])],
+                                              torch.from_numpy(deq), update_collection=None)
+    res["d_cost"] = cost_o.item()
+    res["d_grads"] = {n: g.numpy() for (n, _), g in zip(params_o, grads_o) if g is not None}
+    res["u"] = {n: v.detach().numpy().copy() for n, v in om.g.vars.items() if n.endswith("/u")}
+    cost_g, params_g, grads_g = om.gen_grads([torch.from_numpy(z_g[:64]), torch.from_numpy(z_g[64:])],
+                                             [torch.from_numpy(fl[:64]).long(), torch.from_numpy(fl[64:]).long()])
+    res["g_cost"] = cost_g.item()
+    res["g_grads"] = {n: g.numpy() for (n, _), g in zip(params_g, grads_g) if g is not None}
+    O_ops.BF16_OPERANDS = False
+    return res
+
+
+def compare(tag, prod, ref, floor):
+    worst = 0.0
+    lines = []
+    for name, g in ref.items():
+        gn = float(np.linalg.norm(g))
+        if gn < floor:  # gradients that are analytically zero (biases in front of a batch norm)
+            continue
+        r = rel(prod[name], g)
+        worst = max(worst, r)
+        lines.append(f"    {name:58s} rel={r:.3e} |g|={gn:.3e}")
+    print(f"  {tag}: worst rel err {worst:.3e}")
+    return worst, lines
+
+
 def main():
     torch.manual_seed(0)
     dev = torch.device("cuda:0")
     print(torch.cuda.get_device_name(0))
-
-    # ---------------- oracle
-    np.random.seed(0)
-    om = O.SNGANCifar(dtype=torch.float32, u_seed=2)
-    om.build()
-
-    # ---------------- product
-    store = framework.reset_default_graph("cuda", u_seed=2)
-    t0 = time.time()
-    tr = P.Trainer(batch_size=64, seed=0)
-    torch.cuda.synchronize()
-    print(f"product build {time.time() - t0:.2f}s; variables: {len(store.vars)}")
-
-    # init parity (NumPy stream consumed in reference order)
-    bad = 0
-    for name, ov in om.g.vars.items():
-        pv = store.vars.get(name)
-        if pv is None:
-            print("  MISSING in product:", name)
-            bad += 1
-            continue
-        r = rel(pv.data.cpu().numpy().reshape(-1), ov.detach().numpy().reshape(-1))
-        if r > 1e-6:
-            print(f"  init mismatch {name}: rel={r:.3e}")
-            bad += 1
-    for name in store.vars:
-        if name not in om.g.vars:
-            print("  EXTRA in product:", name)
-            bad += 1
-    print("init parity:", "OK" if bad == 0 else f"{bad} problems")
-
-    # ---------------- inputs
     data, labels = O.synthetic_batch(seed=0)
     rs = np.random.RandomState(1)
     z_d = rs.standard_normal((64, 128)).astype("float32")
@@ -68,71 +75,48 @@ def main():
     z_g = rs.standard_normal((128, 128)).astype("float32")
     fl = rs.randint(0, 10, size=128).astype("int32")
 
+    t0 = time.time()
+    ref32 = run_oracle(False, data, labels, z_d, deq, z_g, fl)
+    ref16 = run_oracle(True, data, labels, z_d, deq, z_g, fl)
+    print(f"oracles done in {time.time() - t0:.1f}s")
+
+    store = framework.reset_default_graph("cuda", u_seed=2)
+    tr = P.Trainer(batch_size=64, seed=0)
+    torch.cuda.synchronize()
+    om = ref32["om"]
+    bad = [n for n in om.g.vars if n not in store.vars] + [n for n in store.vars if n not in om.g.vars]
+    print("variable name parity:", "OK" if not bad else bad)
+
     tr.set_real_batch(data, labels)
     tr.z_d.copy_(torch.from_numpy(z_d))
     tr.deq_noise.copy_(torch.from_numpy(deq))
     tr.z_g.copy_(torch.from_numpy(z_g))
     tr.fake_labels.copy_(torch.from_numpy(fl))
 
-    # ---------------- forward parity: G and D
     with store.stat_towers(2):
         fake_p = P.Generator(64, tr.real_labels, noise=tr.z_d, reuse=True)
-    lab_t = torch.tensor(labels).long()
-    with torch.no_grad():
-        f0 = O.Generator(om.g, 32, lab_t[:32], torch.from_numpy(z_d[:32]), reuse=True)
-        f1 = O.Generator(om.g, 32, lab_t[32:], torch.from_numpy(z_d[32:]), reuse=True)
-        fake_o = torch.cat([f0, f1]).numpy()
-    print(f"G forward rel err: {rel(fake_p.data.cpu().numpy(), fake_o):.3e}")
-    with torch.no_grad():
-        d_o, _ = O.Discriminator(om.g, torch.from_numpy(fake_o), lab_t, update_collection=O_ops.NO_OPS, reuse=True)
-    d_p, _ = P.Discriminator(F.Var(torch.from_numpy(fake_o).to(dev)), tr.real_labels, update_collection="NO_OPS",
-                             reuse=True)
-    print(f"D forward rel err: {rel(d_p.data.cpu().numpy(), d_o.numpy()):.3e}  (oracle |d| max {np.abs(d_o.numpy()).max():.3e})")
-    for key, e in store.sn_groups["Discriminator"].entries.items():
-        pass
-    sig_p = {k: e.scal[0].item() for k, e in store.sn_groups["Discriminator"].entries.items()}
-    print("sigma (product) first 4:", list(sig_p.items())[:4])
+    fp = fake_p.data.cpu().numpy()
+    print(f"G forward rel err: vs fp32 oracle {rel(fp, ref32['fake']):.3e}   vs bf16-operand oracle {rel(fp, ref16['fake']):.3e}")
 
-    # ---------------- D-step gradients
-    cost_o, params_o, grads_o = om.disc_grads(torch.tensor(data), lab_t, [torch.from_numpy(z_d[:32]), torch.from_numpy(z_d[32:])],
-                                              torch.from_numpy(deq), update_collection=None)
-    # product: run the body but stop before Adam -> emulate by lr 0
     tr.disc_opt.set_lr(0.0)
     tr._d_body()
     torch.cuda.synchronize()
-    print(f"D loss product {tr.d_loss.item():.6f} oracle {cost_o.item():.6f}")
-    worst = 0.0
-    for (name, _), g in zip(params_o, grads_o):
-        pv = store.vars[name]
-        if g is None:
-            continue
-        r = rel(pv.grad.cpu().numpy(), g.numpy())
-        worst = max(worst, r)
-        print(f"  dD {name:55s} rel={r:.3e} |g|={float(g.norm()):.3e}")
-    print(f"D-step worst grad rel err {worst:.3e}")
-    # u parity after the assign
-    worst_u = 0.0
-    for name, ov in om.g.vars.items():
-        if name.endswith("/u"):
-            worst_u = max(worst_u, rel(store.vars[name].data.cpu().numpy(), ov.detach().numpy()))
-    print(f"u after D-step: worst rel err {worst_u:.3e}")
+    print(f"D loss product {tr.d_loss.item():.6f}  fp32 oracle {ref32['d_cost']:.6f}  bf16 oracle {ref16['d_cost']:.6f}")
+    prod = {n: v.grad.cpu().numpy().copy() for n, v in store.vars.items() if v.trainable and v.grad is not None}
+    compare("D-step grads vs fp32 oracle", prod, ref32["d_grads"], 1e-7)
+    w16, lines = compare("D-step grads vs bf16-operand oracle", prod, ref16["d_grads"], 1e-7)
+    print("\n".join(lines))
+    wu = max(rel(store.vars[n].data.cpu().numpy(), u) for n, u in ref32["u"].items())
+    print(f"  u after the D-step: worst rel err {wu:.3e}")
 
-    # ---------------- G-step gradients
-    cost_g, params_g, grads_g = om.gen_grads([torch.from_numpy(z_g[:64]), torch.from_numpy(z_g[64:])],
-                                             [torch.from_numpy(fl[:64]).long(), torch.from_numpy(fl[64:]).long()])
     tr.gen_opt.set_lr(0.0)
     tr._g_body()
     torch.cuda.synchronize()
-    print(f"G loss product {tr.g_loss.item():.6f} oracle {cost_g.item():.6f}")
-    worst = 0.0
-    for (name, _), g in zip(params_g, grads_g):
-        pv = store.vars[name]
-        if g is None:
-            continue
-        r = rel(pv.grad.cpu().numpy(), g.numpy())
-        worst = max(worst, r)
-        print(f"  dG {name:55s} rel={r:.3e} |g|={float(g.norm()):.3e}")
-    print(f"G-step worst grad rel err {worst:.3e}")
+    print(f"G loss product {tr.g_loss.item():.6f}  fp32 oracle {ref32['g_cost']:.6f}  bf16 oracle {ref16['g_cost']:.6f}")
+    prod = {n: v.grad.cpu().numpy().copy() for n, v in store.vars.items() if v.trainable and v.grad is not None}
+    compare("G-step grads vs fp32 oracle", prod, ref32["g_grads"], 1e-7)
+    w16, lines = compare("G-step grads vs bf16-operand oracle", prod, ref16["g_grads"], 1e-7)
+    print("\n".join(lines))
 
     # ---------------- timing, eager then graphs
     def run_pairs(k):
