@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Headline benchmark: SNGAN-CIFAR ResNet (conditional) D+G training pairs per second at batch 64 per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's B200 path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A "step" is one D+G pair (unit U1 of SURVEY.md 8(d)): one critic step (G forward 2x32, D forward+backward on
+64 real + 64 fake, Adam) followed by one generator step (G forward+backward 2x64, D forward + data-gradient,
+Adam), on synthetic CIFAR-shaped inputs.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SNGAN-CIFAR D+G train iters/sec (bs64)"
+UNIT = "D+G pairs/s (batch 64 per pair, summed over GPUs)"
+WORKLOAD = "SNGAN CIFAR-10 ResNet conditional (gan_cifar_resnet.py), 1 D-step + 1 G-step, batch 64 per GPU"
+PAIR_GFLOP = 2167.4  # algorithmic conv/linear FLOPs of one D+G pair, BASELINE.md section 2
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"bf16_burst": float(d["bf16_tflops"]), "bf16_sustained": float(d["bf16_tflops_sustained"]),
+                "hbm": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:  # noqa: BLE001
+        return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0,
+                "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Polls nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.sm, self.sm_max, self.reasons = [], [], set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.sm.append(float(parts[0]))
+                    self.sm_max.append(float(parts[1]))
+                    for nm, val in zip(names, parts[2:6]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": max(self.sm_max), "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_pairs_per_s(steps: int, warmup: int, budget_s: float):
+    """Times the oracle (CPU restatement of the reference; TensorFlow is not installable) on all host threads.
+    Returns (pairs_per_s at batch-64 equivalence, cores, sample description)."""
+    import numpy as np
+    import torch
+
+    from oracle import sngan_cifar as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    np.random.seed(0)
+    model = O.SNGANCifar(dtype=torch.float32)
+    model.build()
+    rs = np.random.RandomState(1)
+
+    def one_pair(batch):
+        data, labels = O.synthetic_batch(seed=0, batch=batch)
+        half = batch // 2
+        z = [torch.from_numpy(rs.standard_normal((half, 128)).astype("float32")) for _ in range(2)]
+        deq = torch.from_numpy(rs.uniform(0, 1 / 128, size=(batch, 3072)).astype("float32"))
+        zg = [torch.from_numpy(rs.standard_normal((batch, 128)).astype("float32")) for _ in range(2)]
+        fl = [torch.from_numpy(rs.randint(0, 10, size=batch)).long() for _ in range(2)]
+        O.BATCH_SIZE = batch
+        model.disc_train_op(1, torch.from_numpy(data), torch.from_numpy(labels).long(), z, deq)
+        model.gen_train_op(1, zg, fl)
+
+    batch = 64
+    t0 = time.perf_counter()
+    one_pair(batch)  # also serves as the first warm-up
+    t_pair = time.perf_counter() - t0
+    total = steps + max(warmup - 1, 0)
+    if total * t_pair > budget_s:  # bound the sample: smaller batch, same graph
+        batch = max(8, int(64 * budget_s / (total * t_pair)) // 8 * 8)
+        one_pair(batch)
+    for _ in range(max(warmup - 1, 0)):
+        one_pair(batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pair(batch)
+    dt = time.perf_counter() - t0
+    O.BATCH_SIZE = 64
+    pairs = steps * batch / 64.0
+    sample = (f"{steps} D+G pairs at batch {batch} (fp32 torch-CPU restatement of the reference graph, "
+              f"{cores} threads; H2D/data loading excluded)")
+    return pairs / dt, cores, sample, dt / steps * 1e3
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return 0
+    v, cores, sample, ms = cpu_pairs_per_s(args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path: TensorFlow 1.5 is not installable here, so the "
+                   "oracle (line-by-line torch-CPU restatement of the reference graph) is timed"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def time_dominant_kernel(torch, K, reps=20):
+    """conv_igemm_kernel<256,4> on its largest problem of the step: G.Block.3 3x3 256->256 at 128x32x32
+    (M = 131072, K = 2304, N = 256).  Operands + output (67 + 1.2 + 134 MB) exceed the 126 MB L2."""
+    n, h, w, cin, cout, k = 128, 32, 32, 256, 256, 3
+    dev = torch.device("cuda")
+    x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
+    wp = (torch.randn(k * k, cout, cin, device=dev) * 0.02).to(torch.bfloat16)
+    bias = torch.zeros(cout, device=dev)
+    for _ in range(3):
+        K.conv_igemm(x, wp, n, h, w, cin, h, w, cout, k, k, 1, 1, False, None, bias, None, None, torch.float32)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        y = K.conv_igemm(x, wp, n, h, w, cin, h, w, cout, k, k, 1, 1, False, None, bias, None, None, torch.float32)
+    e1.record()
+    torch.cuda.synchronize()
+    del y
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * n * h * w * cin * k * k * cout
+    return ms, flops
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import numpy as np
+    import torch
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "bench.py needs a CUDA device (B200); there is no CPU fallback for the product path"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200 import kernels as K
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+
+    store = framework.reset_default_graph("cuda")
+    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    tr = P.Trainer(batch_size=64, seed=0, world_size=world, grad_allreduce=allreduce)
+
+    # synthetic inputs of SURVEY 8(d): int32 [64, 3072] uniform 0..255 (CHW-flattened), labels uniform 0..9;
+    # every rank draws its own shard.
+    rs = np.random.RandomState(1000 + rank)
+    host_data = torch.from_numpy(rs.randint(0, 256, size=(64, 3072)).astype("int32")).pin_memory()
+    host_labels = torch.from_numpy(rs.randint(0, 10, size=(64,)).astype("int32")).pin_memory()
+    host_losses = torch.zeros(2, dtype=torch.float32).pin_memory()
+    tr.set_real_batch(host_data, host_labels)
+
+    def pair(it):
+        tr.sample_noise()
+        tr.d_step(it)
+        tr.g_step(it)
+
+    for it in range(2):  # eager warm-up: creates descriptor tables / workspaces
+        pair(it + 1)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        tr.capture()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for it in range(args.warmup):
+        pair(it + 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- device-resident timing ("value"): inputs already in HBM
+    barrier()
+    e0.record()
+    for it in range(args.steps):
+        pair(it + 1)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- end-to-end ("e2e"): pinned host batch -> device every step, losses read back every step
+    barrier()
+    e0.record()
+    for it in range(args.steps):
+        tr.set_real_batch(host_data, host_labels)
+        pair(it + 1)
+        host_losses[0:1].copy_(tr.d_loss, non_blocking=True)
+        host_losses[1:2].copy_(tr.g_loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    d_loss, g_loss = float(host_losses[0]), float(host_losses[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = _peaks()
+    k_ms, k_flops = time_dominant_kernel(torch, K)
+    achieved = k_flops / (k_ms * 1e-3) / 1e12
+    ms_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD, "per_gpu_batch": 64, "global_batch": 64 * world, "parallelism": f"dp{world}",
+            "images_per_s": value * 64,
+            "l2": "no explicit flush: one step streams ~3 GB of activations, >> 126 MB L2",
+            "step_tflops_algorithmic": PAIR_GFLOP / ms_step / 1e3 * 1.0,
+            "cuda_graphs": True, "final_d_loss": d_loss, "final_g_loss": g_loss,
+            "value_counts": "batch-64 D+G pairs per second summed over ranks (global images/s / 64)",
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_data.numel() * 4 + host_labels.numel() * 4),
+                "d2h_bytes_per_step": 8},
+        "gpu_launches": int(args.steps * tr.launches_per_pair()),
+        "clocks": sampler.summary(),
+        "roofline": {
+            "kernel": "ganb::conv_igemm_kernel<256,4> (tcgen05 implicit GEMM), G.Block.3 3x3 256->256 @128x32x32",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["source"] + ", burst figure "
+            "(kernel timed alone)", "flops_per_launch": k_flops, "ms_per_launch": k_ms,
+        },
+    }
+    if world == 1:
+        v, cores, sample, _ = cpu_pairs_per_s(steps=2, warmup=1, budget_s=30.0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE=1 found)"}))
+        return 2
+    return run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -197,7 +197,8 @@ class Trainer:
         self.fake_labels.copy_((torch.rand(self.gen_batch, device=self.store.device) * 10).to(torch.int32))
 
     # ------------------------------------------------------------------------------------------ steps
-    def _d_body(self):
+    def _d_compute(self):
+        """Forward + backward of the critic step (gan_cifar_resnet.py:322-381, 524): gradients of disc_cost."""
         st = self.store
         b = self.batch
         st.zero_grad('Discriminator')
@@ -213,12 +214,13 @@ class Trainer:
             loss = F.gan_loss(disc_all, 'hinge_d', n_real=b)
             tape.backward(loss)
         self.d_loss.copy_(loss.data)
-        if self.grad_allreduce is not None:
-            self.grad_allreduce(st.flat['Discriminator'].grads)
-        self.disc_opt.apply(1.0 / self.world_size)
-        st.bump('Discriminator')
 
-    def _g_body(self):
+    def _d_update(self):
+        self.disc_opt.apply(1.0 / self.world_size)
+        self.store.bump('Discriminator')
+
+    def _g_compute(self):
+        """Forward + backward of the generator step (gan_cifar_resnet.py:462-498, 523): gradients of gen_cost."""
         st = self.store
         st.zero_grad('Generator')
         with st.gradient_tape() as tape, st.frozen_scopes('Discriminator'):
@@ -228,10 +230,22 @@ class Trainer:
             loss = F.gan_loss(disc_fake, 'gen')
             tape.backward(loss)
         self.g_loss.copy_(loss.data)
-        if self.grad_allreduce is not None:
-            self.grad_allreduce(st.flat['Generator'].grads)
+
+    def _g_update(self):
         self.gen_opt.apply(1.0 / self.world_size)
-        st.bump('Generator')
+        self.store.bump('Generator')
+
+    def _d_body(self):
+        self._d_compute()
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(self.store.flat['Discriminator'].grads)
+        self._d_update()
+
+    def _g_body(self):
+        self._g_compute()
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(self.store.flat['Generator'].grads)
+        self._g_update()
 
     def _invalidate_caches(self):
         for g in self.store.sn_groups.values():
@@ -241,33 +255,48 @@ class Trainer:
             g.valid_for = None
 
     def capture(self):
-        """Captures the D-step and the G-step into CUDA graphs (static shapes; launch latency is first-order at
-        batch 64).  Must be called after at least one eager D-step and G-step (all workspaces / tables exist)."""
-        if self.grad_allreduce is not None:
-            raise RuntimeError("graph capture with an in-step collective is not supported; run eagerly")
-        for name, body in (("d", self._d_body), ("g", self._g_body)):
+        """Captures the training ops into CUDA graphs (static shapes; launch latency is first-order at batch 64).
+        Must be called after at least one eager D-step and G-step (all workspaces / descriptor tables exist).
+        With a gradient collective the compute and update halves are captured separately and the all-reduce
+        runs between them on the same stream."""
+        parts = (("d_compute", self._d_compute), ("d_update", self._d_update),
+                 ("g_compute", self._g_compute), ("g_update", self._g_update))
+        self.graph_launches = {}
+        for name, body in parts:
             self._invalidate_caches()
+            before = K.launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 body()
             self._graphs[name] = g
+            self.graph_launches[name] = K.launch_count() - before
         self._invalidate_caches()
+
+    def _run(self, which):
+        if (which + "_compute") in self._graphs:
+            self._graphs[which + "_compute"].replay()
+            if self.grad_allreduce is not None:
+                root = 'Discriminator' if which == 'd' else 'Generator'
+                self.grad_allreduce(self.store.flat[root].grads)
+            self._graphs[which + "_update"].replay()
+        elif which == 'd':
+            self._d_body()
+        else:
+            self._g_body()
 
     def d_step(self, iteration: int):
         self.disc_opt.set_lr(LR * lr_decay(iteration))
-        if "d" in self._graphs:
-            self._graphs["d"].replay()
-        else:
-            self._d_body()
+        self._run('d')
         return self.d_loss
 
     def g_step(self, iteration: int):
         self.gen_opt.set_lr(LR * lr_decay(iteration))
-        if "g" in self._graphs:
-            self._graphs["g"].replay()
-        else:
-            self._g_body()
+        self._run('g')
         return self.g_loss
+
+    def launches_per_pair(self) -> int:
+        """libganb200 kernels in one D-step + one G-step (valid after capture())."""
+        return sum(self.graph_launches.values())
 
     def train_iteration(self, iteration: int, batches):
         """One reference iteration (gan_cifar_resnet.py:599-620): G-step if iteration > 0, then N_CRITIC D-steps.

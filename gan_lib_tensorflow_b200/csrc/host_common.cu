@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace ganb {
@@ -16,6 +17,9 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached = 0;
@@ -76,6 +80,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 extern "C" const char* ganb_last_error(void) { return ganb::g_err; }
 
 extern "C" int ganb_abi_version(void) { return GANB_ABI_VERSION; }
+
+extern "C" int64_t ganb_launch_count(void) { return static_cast<int64_t>(ganb::g_launches.load()); }
 
 extern "C" int ganb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

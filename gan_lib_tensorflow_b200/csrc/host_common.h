@@ -20,10 +20,14 @@ int sm_count();
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 
+// Counts every kernel launch issued by the library (exported as ganb_launch_count()).
+void count_launch();
+
 #define GANB_CHECK_LAUNCH(name)                                                          \
   do {                                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                \
     if (e__ != cudaSuccess) return ::ganb::fail(GANB_E_LAUNCH, "%s: %s", name, cudaGetErrorString(e__)); \
+    ::ganb::count_launch();                                                              \
   } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

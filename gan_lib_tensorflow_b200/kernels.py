@@ -39,7 +39,7 @@ def L():
             _L = _NullLib()
             return _L
         _L = cabi.lib()
-        for name in ("ganb_conv2d_wgrad_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
+        for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
     return _L
@@ -49,6 +49,11 @@ def _stream():
     if host_logic_only():
         return c_void_p(0)
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    """Kernels launched by libganb200 so far in this process."""
+    return int(L().ganb_launch_count())
 
 
 def dt(t: torch.Tensor) -> int:

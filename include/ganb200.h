@@ -44,6 +44,9 @@ extern "C" {
 const char* ganb_last_error(void);
 int ganb_abi_version(void);
 int ganb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of CUDA kernels this library has launched in the calling process (launches recorded into a CUDA graph
+ * count once, at capture time) */
+int64_t ganb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core convolution (tcgen05 / TMEM implicit GEMM, TMA-fed, BF16 inputs, FP32 accumulation).

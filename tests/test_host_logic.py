@@ -1,0 +1,312 @@
+"""CPU tier: the C-ABI library loads and exports everything include/ganb200.h declares (no compute calls), the
+ctypes mirrors of its structs match the C layout, and the host-side mirror of the reference interface (variable
+scopes, reuse, NumPy-RNG order, spectral-norm update_collection bookkeeping, optimistic restore) behaves like the
+reference.  Layer functions run with GANB_HOST_LOGIC_ONLY=1: every kernel call is a recorded no-op, so nothing
+here computes -- arithmetic is only ever checked on the GPU tier against the oracle."""
+import ctypes
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class RecordingLib:
+    """Stands in for libganb200 on a machine without a GPU: records (name, args) and reports success."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name.endswith("_workspace"):
+            return lambda *a: 16
+        if name == "ganb_launch_count":
+            return lambda *a: len(self.calls)
+
+        def fn(*a):
+            self.calls.append((name, a))
+            return 0
+        return fn
+
+    def names(self):
+        return [c[0] for c in self.calls]
+
+
+@pytest.fixture()
+def host(monkeypatch):
+    monkeypatch.setenv("GANB_HOST_LOGIC_ONLY", "1")
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200 import kernels as K
+
+    rec = RecordingLib()
+    monkeypatch.setattr(K, "_L", rec)
+    store = framework.reset_default_graph("cpu", u_seed=2)
+    yield store, rec
+    framework.set_store(None)
+    monkeypatch.setattr(K, "_L", None)
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    from gan_lib_tensorflow_b200 import cabi
+
+    lib = cabi.lib()
+    syms = cabi.header_symbols()
+    assert len(syms) >= 35
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.ganb_abi_version() == 1
+    assert isinstance(lib.ganb_last_error(), bytes)
+
+
+def test_struct_mirrors_match_the_c_layout():
+    from gan_lib_tensorflow_b200 import kernels as K
+
+    src = '#include "ganb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+          'sizeof(ganb_sn_layer), offsetof(ganb_sn_layer, k), offsetof(ganb_sn_layer, blk_begin),' \
+          'sizeof(ganb_pack_layer), offsetof(ganb_pack_layer, tile_begin));}'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        with open(c, "w") as fh:
+            fh.write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = subprocess.check_output([exe]).decode().split()
+    got = [ctypes.sizeof(K.SnLayerStruct), K.SnLayerStruct.k.offset, K.SnLayerStruct.blk_begin.offset,
+           ctypes.sizeof(K.PackLayerStruct), K.PackLayerStruct.tile_begin.offset]
+    assert [int(v) for v in out] == got
+
+
+def test_no_cpu_fallback_when_library_or_gpu_is_missing(monkeypatch):
+    from gan_lib_tensorflow_b200 import cabi, framework
+
+    monkeypatch.delenv("GANB_HOST_LOGIC_ONLY", raising=False)
+    monkeypatch.setattr(cabi, "_lib", None)
+    monkeypatch.setattr(cabi, "LIB_PATH", "/nonexistent/libganb200.so")
+    with pytest.raises(cabi.GanbError):
+        cabi.lib()
+    framework.set_store(None)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            framework.get_store()
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gan_lib_tensorflow_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+# ------------------------------------------------------------------------------------------------ variables
+def test_variable_names_reuse_and_trainable_filter(host):
+    store, _ = host
+    from gan_lib_tensorflow_b200.common.ops import conv2d, linear
+    from gan_lib_tensorflow_b200.framework import Var
+
+    x = Var(torch.zeros(2, 8, 8, 16))
+    with store.variable_scope("Discriminator"):
+        conv2d.Conv2D(x, 16, 8, 3, 1, "D.Block.2.Conv1", spectral_normed=True, update_collection="NO_OPS")
+        linear.Linear(Var(torch.zeros(2, 16)), 16, 4, "D.Output", spectral_normed=True, update_collection="NO_OPS")
+    names = list(store.vars)
+    assert names == ["Discriminator/D.Block.2.Conv1/Filters",
+                     "Discriminator/D.Block.2.Conv1/filters/spectral_norm/u",      # conv2d.py:170 + sn.py:28,32
+                     "Discriminator/D.Block.2.Conv1/Biases",
+                     "Discriminator/D.Output/W", "Discriminator/D.Output/spectral_norm/u", "Discriminator/D.Output/b"]
+    assert store.vars[names[1]].trainable is False and tuple(store.vars[names[1]].data.shape) == (1, 8)
+    assert [v.name for v in store.trainable_variables("Discriminator")] == [n + ":0" for n in names if "/u" not in n]
+    # reuse=True on a missing variable raises, on an existing one returns the same object
+    with store.variable_scope("Discriminator", reuse=True):
+        conv2d.Conv2D(x, 16, 8, 3, 1, "D.Block.2.Conv1", spectral_normed=True, update_collection="NO_OPS")
+        with pytest.raises(ValueError):
+            conv2d.Conv2D(x, 16, 8, 3, 1, "D.Block.9.Conv1")
+    assert len(store.vars) == 6
+    with pytest.raises(ValueError):
+        conv2d.Conv2D(x, 32, 8, 3, 1, "bad")        # input_dim does not match the tensor
+
+
+def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
+    store, _ = host
+    from gan_lib_tensorflow_b200.common import resnet_block
+    from gan_lib_tensorflow_b200.common.ops import conv2d_, pixelnorm
+    from gan_lib_tensorflow_b200.framework import Var
+
+    conv2d_.Conv2D(Var(torch.zeros(1, 4, 4, 8)), 8, 8, 3, 1, "L", spectral_normed=True, update_collection="NO_OPS",
+                   reuse=False)
+    assert "L/spectral_norm/u" in store.vars            # conv2d_.py: no 'filters/' level
+    assert callable(pixelnorm.Pixelnorm)                # model_nvidia.py:63 resolves
+    assert resnet_block.get_dim(1) == 512 and isinstance(resnet_block.get_dim(3), int) and resnet_block.get_dim(3) == 256
+
+
+def test_numpy_rng_stream_and_initial_values_match_the_oracle(host):
+    """Variables are created in the reference's graph-construction order, including the draws that every reuse
+    call makes and discards (conv2d.py:124-144); names, shapes and values must equal the oracle's."""
+    store, _ = host
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+    from oracle import sngan_cifar as O
+
+    P.Trainer(batch_size=64, seed=0, store=store)
+    state_after_product = np.random.get_state()[1].copy()
+    np.random.seed(0)
+    om = O.SNGANCifar(dtype=torch.float32, u_seed=2)
+    om.build()
+    assert np.array_equal(np.random.get_state()[1], state_after_product)       # same number of draws consumed
+    assert set(om.g.vars) == set(store.vars)
+    for name, ov in om.g.vars.items():
+        pv = store.vars[name]
+        assert tuple(pv.data.shape) == tuple(ov.shape), name
+        assert torch.equal(pv.data, ov.detach()), name
+        assert pv.trainable == om.g.trainable[name], name
+    flat = store.flat["Generator"]
+    assert sum(v.data.numel() for v in flat.variables) == 7875587
+    assert sum(v.data.numel() for v in store.flat["Discriminator"].variables) == 1701689
+    for v in flat.variables:                                                    # views into the flat buffers
+        off = v.data.data_ptr() - flat.params.data_ptr()
+        assert off >= 0 and off % 256 == 0                                     # 16-byte rule of the TMA path
+        assert v.grad.data_ptr() - flat.grads.data_ptr() == off
+
+
+def test_spectral_norm_update_collection_bookkeeping(host):
+    """update_collection=None: ONE grouped power iteration per forward pass of the network, with assign;
+    NO_OPS: re-evaluated only when weights or u changed; a named collection defers the assignment."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.common.ops import conv2d, sn
+    from gan_lib_tensorflow_b200.framework import Var
+
+    x = Var(torch.zeros(1, 4, 4, 8))
+
+    def net(mode):
+        with store.variable_scope("D", reuse=len(store.vars) > 0):
+            conv2d.Conv2D(x, 8, 8, 3, 1, "a", spectral_normed=True, update_collection=mode)
+            conv2d.Conv2D(x, 8, 8, 3, 1, "b", spectral_normed=True, update_collection=mode)
+
+    net("NO_OPS")                       # build: two registrations
+    rec.calls.clear()
+    net("NO_OPS")
+    assert rec.names().count("ganb_sn_power_iter") == 0          # cached: nothing changed
+    net(None)
+    calls = [c for c in rec.calls if c[0] == "ganb_sn_power_iter"]
+    assert len(calls) == 1 and calls[0][1][4] == 1                # one grouped launch for both layers, assign=1
+    assert calls[0][1][1] == 2
+    net(None)
+    assert rec.names().count("ganb_sn_power_iter") == 2           # a new forward pass iterates again
+    net("NO_OPS")
+    calls = [c for c in rec.calls if c[0] == "ganb_sn_power_iter"]
+    assert len(calls) == 3 and calls[-1][1][4] == 0               # u changed -> fresh evaluation, no assign
+    store.bump("D")
+    net("NO_OPS")
+    assert rec.names().count("ganb_sn_power_iter") == 4           # weights changed
+    net("my_update_ops")
+    assert len(sn.get_collection("my_update_ops")) == 2
+    sn.run_update_collection("my_update_ops")
+    assert sn.get_collection("my_update_ops") == []
+    with pytest.raises(NotImplementedError):
+        sn.spectral_normed_weight(store.vars["D/a/Filters"], num_iters=2)
+
+
+def test_training_step_call_sequence_and_freezing(host):
+    """D-step: generator runs without a tape (var_list=disc_params) -> no wgrad for G; G-step: D is frozen."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+
+    tr = P.Trainer(batch_size=64, seed=0, store=store)
+    rec.calls.clear()
+    tr.d_step(0)
+    d_names = rec.names()
+    n_wgrad_d = d_names.count("ganb_conv2d_wgrad")
+    assert n_wgrad_d == 10                                        # the 10 D convolutions (SN weights)
+    assert d_names.count("ganb_sn_bwd") == 1 and d_names.count("ganb_adam") == 1
+    assert d_names.count("ganb_bn_stats") == 7                    # G forward only
+    assert "ganb_norm_act_bwd" in d_names                         # D's own activations
+    rec.calls.clear()
+    tr.g_step(1)
+    g_names = rec.names()
+    assert g_names.count("ganb_sn_bwd") == 0                      # D frozen: no SN backward, no D wgrad
+    assert g_names.count("ganb_conv2d_wgrad") == 11               # 10 G convolutions + G.Input
+    assert g_names.count("ganb_adam") == 1
+    stats = [c for c in rec.calls if c[0] == "ganb_bn_stats"]
+    assert len(stats) == 7 and all(c[1][4] == 2 for c in stats)   # two statistic towers of 64 (reference towers)
+    assert tr.disc_opt.t == 1 and tr.gen_opt.t == 1
+    assert P.lr_decay(0) == 1.0 and P.lr_decay(60000) == 0.5
+
+
+def test_optimistic_restore_matches_name_and_shape_only(host):
+    store, _ = host
+    from gan_lib_tensorflow_b200.common.ops import linear
+    from gan_lib_tensorflow_b200.framework import Var
+
+    with store.variable_scope("Generator"):
+        linear.Linear(Var(torch.zeros(2, 16)), 16, 8, "G.Input")
+    state = {"Generator/G.Input/W": np.ones((16, 8), "float32"), "Generator/G.Input/b": np.ones((9,), "float32"),
+             "Generator/Unknown": np.ones((3,), "float32")}
+    restored = store.load_state_dict(state)
+    assert restored == ["Generator/G.Input/W"]                    # common/misc.py:275-307 semantics
+    assert float(store.vars["Generator/G.Input/W"].data.sum()) == 128.0
+
+
+def test_same_padding_helper():
+    from gan_lib_tensorflow_b200 import kernels as K
+
+    assert K.same_pads(32, 3, 1) == (1, 1, 32)
+    assert K.same_pads(256, 4, 1) == (1, 2, 256)
+    assert K.same_pads(256, 4, 2) == (1, 1, 128)
+    assert K.same_pads(8, 3, 2) == (0, 1, 4)
+
+
+# ------------------------------------------------------------------------------------------------ 2 ranks, gloo
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+os.environ["GANB_HOST_LOGIC_ONLY"] = "1"
+import torch, torch.distributed as dist
+from gan_lib_tensorflow_b200 import framework
+from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+store = framework.reset_default_graph("cpu")
+seen = []
+def allreduce(g):
+    seen.append(float(g[0]))
+    dist.all_reduce(g)
+tr = P.Trainer(batch_size=64, seed=0, store=store, world_size=2, grad_allreduce=allreduce)
+orig = tr._d_compute
+def fake_compute():
+    orig()
+    store.flat["Discriminator"].grads.fill_(rank + 1.0)     # stand-in for the rank's local gradient
+tr._d_compute = fake_compute
+tr.d_step(0)
+g = store.flat["Discriminator"].grads
+assert torch.all(g == 3.0), g[:4]                           # 1 + 2 summed over the two ranks
+assert seen == [rank + 1.0]
+# replicated weights and u need no exchange: identical initial values on both ranks
+w = store.vars["Discriminator/D.Output/W"].data.clone()
+ws = [torch.zeros_like(w) for _ in range(2)]
+dist.all_gather(ws, w)
+assert torch.equal(ws[0], ws[1])
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gradient_allreduce_gloo():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    code = _WORKER.format(root=ROOT, port=port)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out.decode()[-2000:]

@@ -1,0 +1,200 @@
+"""CPU tier: self-checks that pin the oracle (the reference ships no tests or golden vectors).
+
+Each check compares the oracle with an INDEPENDENT statement of the same TF-1.x semantics: a NumPy loop
+convolution with explicit SAME padding, numpy.linalg.svd, finite differences in float64, closed-form identities
+and a hand-computed Adam vector.  The committed golden vectors under tests/golden/ freeze the oracle's outputs.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+from oracle import resnet_block as RB
+from oracle import sngan_cifar as S
+from oracle import tfshim
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def naive_conv2d_same(x, w, stride):
+    """Loop convolution with the TF SAME rule written out independently: out = ceil(in/s),
+    pad_total = max((out-1)*s + k - in, 0), pad_before = pad_total // 2 (the extra pixel goes after)."""
+    n, h, wd, cin = x.shape
+    kh, kw, _, cout = w.shape
+    oh, ow = -(-h // stride), -(-wd // stride)
+    pth = max((oh - 1) * stride + kh - h, 0)
+    ptw = max((ow - 1) * stride + kw - wd, 0)
+    pt, pl = pth // 2, ptw // 2
+    y = np.zeros((n, oh, ow, cout))
+    for i in range(oh):
+        for j in range(ow):
+            for r in range(kh):
+                for s in range(kw):
+                    hi, wi = i * stride + r - pt, j * stride + s - pl
+                    if 0 <= hi < h and 0 <= wi < wd:
+                        y[:, i, j, :] += x[:, hi, wi, :] @ w[r, s]
+    return y
+
+
+@pytest.mark.parametrize("h,k,stride", [(8, 3, 1), (8, 4, 1), (8, 3, 2), (7, 3, 2), (8, 4, 2), (5, 1, 1)])
+def test_conv_same_padding_matches_loop_conv(h, k, stride):
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((2, h, h + 1, 3))
+    w = rs.standard_normal((k, k, 3, 4))
+    got = O.conv2d_nhwc(torch.from_numpy(x), torch.from_numpy(w), stride, "SAME").numpy()
+    np.testing.assert_allclose(got, naive_conv2d_same(x, w, stride), rtol=1e-10, atol=1e-10)
+    # asymmetric cases called out in SURVEY 8(c): 4x4 s1 pads (1,2); 3x3 s2 on even input pads (0,1)
+    assert O.same_pads(8, 4, 1)[:2] == (1, 2)
+    assert O.same_pads(8, 3, 2)[:2] == (0, 1)
+
+
+def test_conv_transpose_is_the_input_gradient_of_conv():
+    rs = np.random.RandomState(1)
+    x = torch.from_numpy(rs.standard_normal((2, 4, 4, 5)))          # deconv input  [N,H,W,Cin]
+    filt = torch.from_numpy(rs.standard_normal((4, 4, 3, 5)))       # [k,k,Cout,Cin]
+    got = O.conv2d_transpose_nhwc(x, filt, 2, "SAME")
+    z = torch.zeros(2, 8, 8, 3, dtype=torch.float64, requires_grad=True)
+    y = O.conv2d_nhwc(z, filt, 2, "SAME")                           # [N,4,4,Cin]
+    (ref,) = torch.autograd.grad(y, z, x)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-10, atol=1e-10)
+
+
+def test_sigma_converges_to_largest_singular_value():
+    rs = np.random.RandomState(2)
+    g = tfshim.Graph(dtype=torch.float64)
+    W = torch.from_numpy(rs.standard_normal((3, 3, 16, 24)))
+    for _ in range(200):
+        _, sigma = O.spectral_normed_weight(g, W, update_collection=None, with_sigma=True)
+    s_true = np.linalg.svd(W.numpy().reshape(-1, 24), compute_uv=False)[0]
+    assert abs(sigma.item() - s_true) < 1e-6 * s_true
+    # NO_OPS leaves u untouched; None assigns (sn.py:48-65)
+    u_before = g.vars["spectral_norm/u"].clone()
+    O.spectral_normed_weight(g, W, update_collection=O.NO_OPS)
+    assert torch.equal(g.vars["spectral_norm/u"], u_before)
+    O.spectral_normed_weight(g, W, update_collection="my_ops")
+    assert len(g.collections["my_ops"]) == 1 and torch.equal(g.vars["spectral_norm/u"], u_before)
+
+
+def test_gradient_flows_through_the_power_iteration():
+    """no stop_gradient in sn.py. Finite differences in float64 against autograd."""
+    rs = np.random.RandomState(3)
+    W0 = rs.standard_normal((6, 5)) * 0.3
+    G = torch.from_numpy(rs.standard_normal((6, 5)))
+    u0 = rs.standard_normal((1, 5))
+
+    def f(wnp):
+        g = tfshim.Graph(dtype=torch.float64)
+        g.get_variable("spectral_norm/u", initializer=u0, trainable=False)
+        W = torch.from_numpy(wnp).requires_grad_(True)
+        wb = O.spectral_normed_weight(g, W, update_collection=O.NO_OPS)
+        return (wb * G).sum(), W
+
+    loss, W = f(W0.copy())
+    (grad,) = torch.autograd.grad(loss, W)
+    num = np.zeros_like(W0)
+    eps = 1e-6
+    for i in range(6):
+        for j in range(5):
+            wp, wm = W0.copy(), W0.copy()
+            wp[i, j] += eps
+            wm[i, j] -= eps
+            num[i, j] = (f(wp)[0].item() - f(wm)[0].item()) / (2 * eps)
+    np.testing.assert_allclose(grad.numpy(), num, rtol=1e-6, atol=1e-8)
+
+
+def test_cond_batchnorm_with_equal_labels_is_batchnorm_and_uses_population_variance():
+    rs = np.random.RandomState(4)
+    x = torch.from_numpy(rs.standard_normal((4, 3, 3, 6)) * 2 + 1)
+    g = tfshim.Graph(dtype=torch.float64)
+    y = O.cond_batchnorm(g, "n", [0, 1, 2], x, labels=torch.zeros(4, dtype=torch.int64), n_labels=10)
+    xn = x.numpy()
+    mean = xn.mean(axis=(0, 1, 2))
+    var = xn.var(axis=(0, 1, 2))  # biased, tf.nn.moments
+    np.testing.assert_allclose(y.detach().numpy(), (xn - mean) / np.sqrt(var + 1e-5), rtol=1e-10, atol=1e-10)
+    g2 = tfshim.Graph(dtype=torch.float64)
+    yb = O.batch_norm(g2, x)
+    np.testing.assert_allclose(y.detach().numpy(), yb.detach().numpy(), rtol=1e-10, atol=1e-10)
+    with pytest.raises(Exception):
+        O.cond_batchnorm(g, "n", [0, 1], x, labels=torch.zeros(4, dtype=torch.int64), n_labels=10)
+
+
+def test_resampling_identities():
+    rs = np.random.RandomState(5)
+    x = rs.standard_normal((2, 4, 4, 3))
+    up = RB.upsample2(torch.from_numpy(x)).numpy()
+    np.testing.assert_array_equal(up, np.repeat(np.repeat(x, 2, axis=1), 2, axis=2))   # depth_to_space(concat x4)
+    pooled = RB.mean_pool2(torch.from_numpy(x)).numpy()
+    np.testing.assert_allclose(pooled, x.reshape(2, 2, 2, 2, 2, 3).mean(axis=(2, 4)), rtol=1e-12)
+    # UpsampleConv == conv(np.repeat); ConvMeanPool == avg-pool(conv) with the same variables
+    np.random.seed(0)
+    g = tfshim.Graph(dtype=torch.float64)
+    y1 = RB.UpsampleConv(g, torch.from_numpy(x), 5, 3, 1, "U")
+    y2 = O.conv2d_nhwc(torch.from_numpy(up), g.vars["U/Filters"], 1, "SAME") + g.vars["U/Biases"]
+    np.testing.assert_allclose(y1.detach().numpy(), y2.detach().numpy(), rtol=1e-12)
+    y3 = RB.ConvMeanPool(g, torch.from_numpy(x), 5, 3, 1, "C")
+    y4 = RB.mean_pool2(O.conv2d_nhwc(torch.from_numpy(x), g.vars["C/Filters"], 1, "SAME") + g.vars["C/Biases"])
+    np.testing.assert_allclose(y3.detach().numpy(), y4.detach().numpy(), rtol=1e-12)
+
+
+def test_activation_gradients_at_zero():
+    x = torch.tensor([-1.0, 0.0, 2.0], dtype=torch.float64, requires_grad=True)
+    (g,) = torch.autograd.grad(RB.nonlinearity(x, "relu").sum(), x)
+    assert g.tolist() == [0.0, 0.0, 1.0]                       # tf.nn.relu: slope 0 at exactly 0
+    (g,) = torch.autograd.grad(RB.nonlinearity(x, "lrelu").sum(), x)
+    assert g.tolist() == [0.2, 1.0, 1.0]                       # tf.maximum(x, 0.2x): MaximumGrad -> first arg at ties
+    with pytest.raises(ValueError):
+        RB.nonlinearity(x, "swish")
+
+
+def test_adam_three_steps_by_hand():
+    """tf.train.AdamOptimizer with beta1=0, beta2=0.9, eps=1e-8 on a scalar, computed by hand."""
+    p = torch.tensor([1.0], dtype=torch.float64)
+    opt = S.Adam(0.0, 0.9, 1e-8)
+    grads = [0.5, -0.25, 0.125]
+    v = 0.0
+    expect = 1.0
+    for t, gval in enumerate(grads, start=1):
+        v = 0.9 * v + 0.1 * gval * gval
+        lr_t = 2e-4 * np.sqrt(1 - 0.9 ** t) / (1 - 0.0 ** t)
+        expect -= lr_t * gval / (np.sqrt(v) + 1e-8)
+        opt.apply([("p", p)], [torch.tensor([gval], dtype=torch.float64)], 2e-4)
+    assert abs(p.item() - expect) < 1e-15
+    assert S.lr_decay(0) == 1.0 and abs(S.lr_decay(25000) - 0.75) < 1e-12 and S.lr_decay(50000) == 0.5
+
+
+def test_preprocess_real_layout():
+    data = np.arange(2 * 3072, dtype=np.int32).reshape(2, 3072) % 256
+    out = S.preprocess_real(torch.from_numpy(data), torch.zeros(2, 3072, dtype=torch.float64), torch.float64).numpy()
+    img = data.reshape(2, 3, 32, 32).transpose(0, 2, 3, 1)            # CHW -> HWC (gan_cifar_resnet.py:336-337)
+    np.testing.assert_allclose(out.reshape(2, 32, 32, 3), 2 * (img / 256.0 - 0.5), rtol=1e-12)
+
+
+def test_variable_manifest_and_parameter_counts():
+    """names, shapes and totals of SNGAN-CIFAR."""
+    np.random.seed(0)
+    m = S.SNGANCifar(dtype=torch.float32)
+    m.build()
+    gen = sum(v.numel() for _, v in m.g.trainable_variables("Generator"))
+    disc = sum(v.numel() for _, v in m.g.trainable_variables("Discriminator"))
+    assert gen == 7875587 and disc == 1701689
+    assert tuple(m.g.vars["Discriminator/D.Block.2.Conv1/filters/spectral_norm/u"].shape) == (1, 256)
+    assert tuple(m.g.vars["Discriminator/D.Embedding_y/spectral_norm/u"].shape) == (1, 128)
+    assert tuple(m.g.vars["Generator/G.Block.1.N1/CondBatchNorm/scale"].shape) == (10, 1024)
+    assert "Discriminator/D.Block.3.Shortcut/Filters" not in m.g.vars        # identity shortcut
+    n_u = sum(v.numel() for n, v in m.g.vars.items() if n.endswith("/u"))
+    assert n_u == 1537
+
+
+def test_golden_vectors():
+    """Frozen outputs of the oracle on fixed seeded inputs (tests/golden/make_golden.py regenerates them)."""
+    path = os.path.join(GOLDEN, "oracle_golden.json")
+    with open(path) as fh:
+        gold = json.load(fh)
+    from tests.golden import make_golden
+
+    now = make_golden.compute()
+    for key, val in gold.items():
+        np.testing.assert_allclose(np.asarray(now[key]), np.asarray(val), rtol=2e-5, atol=1e-7, err_msg=key)
