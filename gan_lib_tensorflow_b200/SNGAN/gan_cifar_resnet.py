@@ -120,16 +120,14 @@ class AdamState:
         self.flat, self.beta1, self.beta2, self.eps = flat, beta1, beta2, eps
         self.t = 0
         self.lr_t = torch.zeros(1, dtype=torch.float32, device=flat.params.device)
-        self._host = torch.zeros(1, dtype=torch.float32)
-        if flat.params.is_cuda:
-            self._host = self._host.pin_memory()
 
     def set_lr(self, lr: float) -> None:
         """Advances the step count and uploads lr_t = lr * sqrt(1-b2^t) / (1-b1^t)."""
         self.t += 1
         val = lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
-        self._host[0] = val
-        self.lr_t.copy_(self._host, non_blocking=True)
+        # the value travels as a kernel argument: no host buffer that a run-ahead CPU could overwrite before
+        # the stream consumes it (the training ops themselves are CUDA-graph replays)
+        self.lr_t.fill_(val)
 
     def apply(self, grad_scale: float = 1.0) -> None:
         K.adam(self.flat.params, self.flat.grads, self.flat.m, self.flat.v, self.lr_t, self.beta1, self.beta2,

@@ -552,7 +552,9 @@ static void plan_wgrad(int n, int ho, int wo, int cin, int cout, int kh, int kw,
   p.ci_tiles = ceil_div(cin, BM);
   p.co_tiles = ceil_div(cout, plan->bn_tile);
   const int units = p.taps * p.ci_tiles * p.co_tiles;
-  int splits = ceil_div(sm_count(), units);
+  // one CTA per SM and a single wave: a second, nearly empty wave would idle most of the machine
+  int splits = sm_count() / units;
+  if (splits < 1) splits = 1;
   // keep at least 4 pixel blocks per split so the pipeline has something to overlap
   const int max_splits = p.num_pb / 4 > 0 ? p.num_pb / 4 : 1;
   if (splits > max_splits) splits = max_splits;

@@ -134,21 +134,24 @@ struct NormActFwd {
   __nv_bfloat16* out_raw; int raw_cstride;                 // optional bf16 copy of x at input resolution
 };
 
-__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p) {
+// grid (pixel chunks, n): a thread owns one float4 of channels, so scale/shift (and the label lookup) are
+// computed once and the loop streams x with several independent 16-byte loads in flight.
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p, int pix_per_chunk) {
+  const int ni = blockIdx.y;
   const int v = p.c >> 2;
-  const int64_t total = static_cast<int64_t>(p.n) * p.h * p.w * v;
-  const int n_per_group = p.n / p.groups;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c4 = static_cast<int>(i % v) * 4;
-    const int64_t pix = i / v;
-    const int wi = static_cast<int>(pix % p.w);
-    const int hi = static_cast<int>((pix / p.w) % p.h);
-    const int ni = static_cast<int>(pix / (static_cast<int64_t>(p.w) * p.h));
-    const float4 a = ld4(p.x + pix * p.c + c4);
-    float4 y = a;
+  const int cols = min(v, 256);
+  const int lanes = 256 / cols;
+  const int cx = threadIdx.x % cols, ly = threadIdx.x / cols;
+  if (ly >= lanes) return;
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * pix_per_chunk, p1 = min(hw, p0 + pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  for (int cb = 0; cb < v; cb += cols) {
+    const int col = cb + cx;
+    if (col >= v) continue;
+    const int c4 = col * 4;
+    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
     if (p.mean) {
-      const int g = ni / n_per_group;
       const float4 m = ld4(p.mean + g * p.c + c4), r = ld4(p.rstd + g * p.c + c4);
       float4 ga = make_float4(1, 1, 1, 1), be = make_float4(0, 0, 0, 0);
       if (p.gamma) {
@@ -157,27 +160,44 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p) {
         be = ld4(p.beta + static_cast<int64_t>(row) * p.c + c4);
       }
       // tf.nn.batch_normalization: inv = rsqrt(var+eps)*gamma; y = x*inv + (beta - mean*inv)
-      const float4 inv = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
-      y = make_float4(a.x * inv.x + (be.x - m.x * inv.x), a.y * inv.y + (be.y - m.y * inv.y),
-                      a.z * inv.z + (be.z - m.z * inv.z), a.w * inv.w + (be.w - m.w * inv.w));
+      sc = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
+      sh = make_float4(be.x - m.x * sc.x, be.y - m.y * sc.y, be.z - m.z * sc.z, be.w - m.w * sc.w);
     }
-    y = make_float4(act_f(y.x, p.act), act_f(y.y, p.act), act_f(y.z, p.act), act_f(y.w, p.act));
-    if (p.out_raw) st4(p.out_raw + pix * p.raw_cstride + c4, a);
-    if (!p.upsample) {
-      const int64_t o = pix * p.out_cstride + c4;
-      if (p.out_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.out) + o, y);
-      else st4(reinterpret_cast<float*>(p.out) + o, y);
-    } else {
-      const int ow = 2 * p.w;
-      const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
+    const float* xb = p.x + static_cast<int64_t>(ni) * hw * p.c + c4;
+    constexpr int U = 4;
+    for (int px = p0 + ly; px < p1; px += lanes * U) {
+      float4 a[U];
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+      for (int u = 0; u < U; ++u) {
+        const int q = px + u * lanes;
+        if (q < p1) a[u] = ld4(xb + static_cast<int64_t>(q) * p.c);
+      }
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int64_t o = (base + dy * ow + dx) * p.out_cstride + c4;
+      for (int u = 0; u < U; ++u) {
+        const int q = px + u * lanes;
+        if (q >= p1) break;
+        const float4 y = make_float4(act_f(a[u].x * sc.x + sh.x, p.act), act_f(a[u].y * sc.y + sh.y, p.act),
+                                     act_f(a[u].z * sc.z + sh.z, p.act), act_f(a[u].w * sc.w + sh.w, p.act));
+        const int64_t pix = static_cast<int64_t>(ni) * hw + q;
+        if (p.out_raw) st4(p.out_raw + pix * p.raw_cstride + c4, a[u]);
+        if (!p.upsample) {
+          const int64_t o = pix * p.out_cstride + c4;
           if (p.out_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.out) + o, y);
           else st4(reinterpret_cast<float*>(p.out) + o, y);
+        } else {
+          const int hi = q / p.w, wi = q - hi * p.w;
+          const int ow = 2 * p.w;
+          const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int64_t o = (base + dy * ow + dx) * p.out_cstride + c4;
+              if (p.out_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.out) + o, y);
+              else st4(reinterpret_cast<float*>(p.out) + o, y);
+            }
         }
+      }
     }
   }
 }
@@ -338,35 +358,46 @@ __global__ void norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int 
   dgamma[i] += b;
 }
 
-__global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(const NormActBwd p) {
+__global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(const NormActBwd p, int pix_per_chunk) {
+  const int ni = blockIdx.y;
   const int v = p.c >> 2;
-  const int64_t total = static_cast<int64_t>(p.n) * p.h * p.w * v;
-  const int n_per_group = p.n / p.groups;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c4 = static_cast<int>(i % v) * 4;
-    const int64_t pix = i / v;
-    const int wi = static_cast<int>(pix % p.w);
-    const int hi = static_cast<int>((pix / p.w) % p.h);
-    const int ni = static_cast<int>(pix / (static_cast<int64_t>(p.w) * p.h));
-    const int g = ni / n_per_group;
-    const float4 a = ld4(p.x + pix * p.c + c4);
-    float4 dy, xh, ga;
-    norm_act_bwd_point(p, ni, hi, wi, c4, g, a, dy, xh, ga);
-    float4 dx = dy;
+  const int cols = min(v, 256);
+  const int lanes = 256 / cols;
+  const int cx = threadIdx.x % cols, ly = threadIdx.x / cols;
+  if (ly >= lanes) return;
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * pix_per_chunk, p1 = min(hw, p0 + pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  const float k = p.inv_count;
+  for (int cb = 0; cb < v; cb += cols) {
+    const int col = cb + cx;
+    if (col >= v) continue;
+    const int c4 = col * 4;
+    float4 r = make_float4(1, 1, 1, 1), t1 = make_float4(0, 0, 0, 0), t2 = make_float4(0, 0, 0, 0);
     if (p.mean) {
-      const float4 r = ld4(p.rstd + g * p.c + c4);
-      const float4 t1 = ld4(p.s1 + g * p.c + c4), t2 = ld4(p.s2 + g * p.c + c4);
-      const float k = p.inv_count;
-      dx = make_float4(r.x * (ga.x * dy.x - k * t1.x - xh.x * k * t2.x), r.y * (ga.y * dy.y - k * t1.y - xh.y * k * t2.y),
-                       r.z * (ga.z * dy.z - k * t1.z - xh.z * k * t2.z), r.w * (ga.w * dy.w - k * t1.w - xh.w * k * t2.w));
+      r = ld4(p.rstd + g * p.c + c4);
+      t1 = ld4(p.s1 + g * p.c + c4);
+      t2 = ld4(p.s2 + g * p.c + c4);
+      t1 = make_float4(k * t1.x, k * t1.y, k * t1.z, k * t1.w);
+      t2 = make_float4(k * t2.x, k * t2.y, k * t2.z, k * t2.w);
     }
-    if (p.add) {
-      const float4 q = ld4(p.add + pix * p.c + c4);
-      dx.x += q.x; dx.y += q.y; dx.z += q.z; dx.w += q.w;
+    for (int px = p0 + ly; px < p1; px += lanes) {
+      const int hi = px / p.w, wi = px - hi * p.w;
+      const int64_t pix = static_cast<int64_t>(ni) * hw + px;
+      const float4 a = ld4(p.x + pix * p.c + c4);
+      float4 dy, xh, ga;
+      norm_act_bwd_point(p, ni, hi, wi, c4, g, a, dy, xh, ga);
+      float4 dx = dy;
+      if (p.mean)
+        dx = make_float4(r.x * (ga.x * dy.x - t1.x - xh.x * t2.x), r.y * (ga.y * dy.y - t1.y - xh.y * t2.y),
+                         r.z * (ga.z * dy.z - t1.z - xh.z * t2.z), r.w * (ga.w * dy.w - t1.w - xh.w * t2.w));
+      if (p.add) {
+        const float4 q = ld4(p.add + pix * p.c + c4);
+        dx.x += q.x; dx.y += q.y; dx.z += q.z; dx.w += q.w;
+      }
+      if (p.dx_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.dx) + pix * p.c + c4, dx);
+      else st4(reinterpret_cast<float*>(p.dx) + pix * p.c + c4, dx);
     }
-    if (p.dx_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.dx) + pix * p.c + c4, dx);
-    else st4(reinterpret_cast<float*>(p.dx) + pix * p.c + c4, dx);
   }
 }
 
@@ -562,6 +593,16 @@ colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, flo
     for (int l = 1; l < 8; ++l) s += sh[l][cx];
     out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
   }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+colsum_wide_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, float* __restrict__ out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float s = 0.f;
+  for (int64_t r = 0; r < rows; ++r) s += static_cast<float>(x[r * c + ch]);
+  out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
 }
 
 // channel counts that are not a multiple of 4 (RGB bias, scalar heads): one block per channel
@@ -852,6 +893,14 @@ extern "C" int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, f
   return 0;
 }
 
+static int bwd_chunks(int n, int hw) {
+  int chunks = ceil_div(8 * sm_count(), n);
+  const int max_chunks = ceil_div(hw, 16);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
 extern "C" int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, const float* mean, const float* rstd,
                                  int groups, const float* gamma, const float* beta, const int* labels, int act,
                                  int upsample, void* out, int out_dtype, int out_cstride, void* out_raw_bf16,
@@ -866,18 +915,11 @@ extern "C" int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, con
   p.act = act; p.upsample = upsample;
   p.out = out; p.out_bf16 = (out_dtype == GANB_BF16); p.out_cstride = out_cstride > 0 ? out_cstride : c;
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
-  const int64_t items = static_cast<int64_t>(n) * h * w * (c / 4);
-  norm_act_fwd_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(p);
+  const int chunks = bwd_chunks(n, h * w);
+  const int ppc = ceil_div(h * w, chunks);
+  norm_act_fwd_kernel<<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
   GANB_CHECK_LAUNCH("norm_act_fwd_kernel");
   return 0;
-}
-
-static int bwd_chunks(int n, int hw) {
-  int chunks = ceil_div(4 * sm_count(), n);
-  const int max_chunks = ceil_div(hw, 16);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  return chunks;
 }
 
 extern "C" int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups) {
@@ -924,8 +966,11 @@ extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, i
     p.s1 = s1; p.s2 = s2;
     p.inv_count = 1.0f / (static_cast<float>(n / groups) * hw);
   }
-  const int64_t items = static_cast<int64_t>(n) * h * w * (c / 4);
-  norm_act_bwd_apply_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(p);
+  {
+    const int chunks2 = bwd_chunks(n, h * w);
+    const int ppc = ceil_div(h * w, chunks2);
+    norm_act_bwd_apply_kernel<<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
+  }
   GANB_CHECK_LAUNCH("norm_act_bwd_apply_kernel");
   return 0;
 }
@@ -1045,6 +1090,14 @@ extern "C" int64_t ganb_colsum_workspace(int64_t rows, int c) {
 extern "C" int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, float beta, float* out, void* workspace,
                            void* stream) {
   if (!x || !out || !workspace) return fail(GANB_E_BADARG, "colsum: null buffer");
+  if (rows <= 512 && c >= 1024) {  // dense-layer bias gradients: coalesced over columns, short serial loop over rows
+    if (x_dtype == GANB_BF16)
+      colsum_wide_kernel<__nv_bfloat16><<<ceil_div(c, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows, c, beta, out);
+    else
+      colsum_wide_kernel<float><<<ceil_div(c, 256), 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, beta, out);
+    GANB_CHECK_LAUNCH("colsum_wide_kernel");
+    return 0;
+  }
   if (c % 4 != 0) {
     if (x_dtype == GANB_BF16)
       colsum_scalar_kernel<__nv_bfloat16><<<c, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows, c, beta, out);

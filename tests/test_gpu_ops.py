@@ -342,8 +342,9 @@ def test_embedding_and_label_concat(env):
     loss = (cat * torch.from_numpy(cot[0])).sum() + (torch.relu(cat) * torch.from_numpy(cot[1])).sum()
     dx, dtab = torch.autograd.grad(loss, [xt, tab])
     assert rel(raw.data.float().cpu().numpy(), cat.detach().numpy()) < 4e-3      # bf16 storage of the operands
-    assert rel(xv.grad.cpu().numpy(), dx.numpy()) < 1e-5
-    assert rel(table.grad.cpu().numpy(), dtab.numpy()) < 1e-5
+    # the two wide operands are bf16 tensor-core inputs, so their gradients are stored in bf16 (2^-9 rounding)
+    assert rel(xv.grad.cpu().numpy(), dx.numpy()) < 4e-3
+    assert rel(table.grad.cpu().numpy(), dtab.numpy()) < 4e-3
 
 
 def test_gan_losses_adam_and_preprocess(env):
