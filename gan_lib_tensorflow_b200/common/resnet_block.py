@@ -149,7 +149,8 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
 
     # ---- Conv1
     mid_dim = input_dim if resample == 'down' else output_dim
-    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True)
+    # h1 is only consumed by N2 + nonlinearity, whose backward can emit the bf16 tensor-core operand directly
+    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16)
 
     # ---- N2 + nonlinearity
     a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn)
@@ -174,7 +175,7 @@ def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
                             inputs_norm=inputs_norm, he_init=False, biases=biases)
     output = _conv2d.Conv2D(inputs, cin, DIM_D, 3, 1, name_prefix + '.Conv1', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
-                            biases=biases)
+                            biases=biases, out_grad_dtype=BF16)
     output, _ = F.norm_act(output, stats=None, act=activation_fn, out_dtype=BF16)
     output = _conv2d.Conv2D(output, DIM_D, DIM_D, 3, 1, name_prefix + '.Conv2', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,

@@ -59,57 +59,125 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // One thread owns one output pixel (TMEM lane) and NC consecutive channels held in registers.
+// All loads (bias from shared memory, residual from global) are issued BEFORE the first store: the output pointer
+// may alias the inputs as far as the compiler knows, so interleaving them would serialise one memory round trip
+// per float4 (this was the limiter of the first version of this kernel, profiles/r01_*).
 template <int NC>
 __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_t (&r)[NC], float alpha,
-                                             int64_t pix, int co_base) {
+                                             int64_t pix, int co_base, const float* __restrict__ bias_s) {
   const int cout = p.Cout;
   const int64_t off = pix * cout + co_base;
-  const bool vec = (cout % 4 == 0);
-  if (vec) {
+  if (cout % 4 == 0) {
+    float4 v[NC / 4];
+#pragma unroll
+    for (int j = 0; j < NC; j += 4)
+      v[j / 4] = make_float4(__uint_as_float(r[j]) * alpha, __uint_as_float(r[j + 1]) * alpha,
+                             __uint_as_float(r[j + 2]) * alpha, __uint_as_float(r[j + 3]) * alpha);
+    if (p.residual) {
+      float4 q[NC / 4];
+#pragma unroll
+      for (int j = 0; j < NC; j += 4)
+        q[j / 4] = (co_base + j < cout) ? __ldg(reinterpret_cast<const float4*>(p.residual + off + j))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) { v[j].x += q[j].x; v[j].y += q[j].y; v[j].z += q[j].z; v[j].w += q[j].w; }
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + j);
+        v[j / 4].x += b.x; v[j / 4].y += b.y; v[j / 4].z += b.z; v[j / 4].w += b.w;
+      }
+    }
+    if (p.act) {
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) {
+        v[j].x = apply_act(v[j].x, p.act); v[j].y = apply_act(v[j].y, p.act);
+        v[j].z = apply_act(v[j].z, p.act); v[j].w = apply_act(v[j].w, p.act);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
-      const int co = co_base + j;
-      if (co >= cout) break;
-      float4 v = make_float4(__uint_as_float(r[j]) * alpha, __uint_as_float(r[j + 1]) * alpha,
-                             __uint_as_float(r[j + 2]) * alpha, __uint_as_float(r[j + 3]) * alpha);
-      if (p.bias) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-      }
-      if (p.residual) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off + j));
-        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-      }
-      if (p.act) {
-        v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-        v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-      }
+      if (co_base + j >= cout) break;
       if (p.out_bf16) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[j / 4].x, v[j / 4].y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v[j / 4].z, v[j / 4].w);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + j) = pk;
       } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + j) = v;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + j) = v[j / 4];
       }
     }
   } else {
+    float v[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      const int co = co_base + j;
-      if (co < cout) {
-        float v = __uint_as_float(r[j]) * alpha;
-        if (p.bias) v += __ldg(p.bias + co);
-        if (p.residual) v += __ldg(p.residual + off + j);
-        v = apply_act(v, p.act);
-        if (p.out_bf16)
-          reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16_rn(v);
-        else
-          reinterpret_cast<float*>(p.out)[off + j] = v;
+      v[j] = __uint_as_float(r[j]) * alpha;
+      if (co_base + j < cout) {
+        if (p.residual) v[j] += __ldg(p.residual + off + j);
+        if (p.bias) v[j] += bias_s[j];
+        v[j] = apply_act(v[j], p.act);
       }
     }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if (co_base + j < cout) {
+        if (p.out_bf16)
+          reinterpret_cast<__nv_bfloat16*>(p.out)[off + j] = __float2bfloat16_rn(v[j]);
+        else
+          reinterpret_cast<float*>(p.out)[off + j] = v[j];
+      }
+    }
+  }
+}
+
+// Epilogue warps: TMEM -> registers -> (alpha, bias, residual, activation) -> global, one output pixel per thread.
+template <int BN>
+__device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tmem_base, uint64_t* tfull,
+                                              uint64_t* tempty, int warp, int lane) {
+  constexpr int ACC_STAGES = 2;
+  constexpr int NC = BN < 32 ? BN : 32;  // columns per tcgen05.ld
+  __shared__ __align__(16) float bias_s[ACC_STAGES][BN];
+  const int q = warp & 3;  // TMEM lane quadrant this warp may access
+  const int m = q * 32 + lane;
+  const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);  // 0..127 among the epilogue threads
+  const int iw = m % p.bw;
+  const int ih = (m / p.bw) % p.bh;
+  const int in_ = m / (p.bw * p.bh);
+  const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int t = tile;
+    const int tco = t % p.tiles_co; t /= p.tiles_co;
+    const int tw = t % p.tiles_w;   t /= p.tiles_w;
+    const int th = t % p.tiles_h;   t /= p.tiles_h;
+    const int tn = t;
+    const int wo = tw * p.bw + iw, ho = th * p.bh + ih, n = tn * p.bn + in_;
+    const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
+    const int64_t pix = (static_cast<int64_t>(n) * p.Ho + ho) * p.Wo + wo;
+    if (p.bias) {  // stage this tile's bias slice; the two buffers alternate with the accumulator stage
+      for (int c = et; c < BN; c += EPI_THREADS) {
+        const int co = tco * BN + c;
+        bias_s[as][c] = co < p.Cout ? __ldg(p.bias + co) : 0.f;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+    mbar_wait(&tfull[as], aphase);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+    for (int c = 0; c < BN / NC; ++c) {
+      uint32_t r[NC];
+      tmem_ld_cols<NC>(trow + c * NC, r);
+      tmem_ld_wait();
+      if (valid) epilogue_row<NC>(p, r, alpha, pix, tco * BN + c * NC, &bias_s[as][c * NC]);
+    }
+    tc_fence_before();
+    mbar_arrive(&tempty[as]);
+    if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
   }
 }
 
@@ -219,37 +287,138 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int m = q * 32 + lane;
-    const int iw = m % p.bw;
-    const int ih = (m / p.bw) % p.bh;
-    const int in_ = m / (p.bw * p.bh);
-    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int tco = t % p.tiles_co; t /= p.tiles_co;
-      const int tw = t % p.tiles_w;   t /= p.tiles_w;
-      const int th = t % p.tiles_h;   t /= p.tiles_h;
-      const int tn = t;
-      const int wo = tw * p.bw + iw, ho = th * p.bh + ih, n = tn * p.bn + in_;
-      const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
-      const int64_t pix = (static_cast<int64_t>(n) * p.Ho + ho) * p.Wo + wo;
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / NC; ++c) {
-        uint32_t r[NC];
-        tmem_ld_cols<NC>(trow + c * NC, r);
-        tmem_ld_wait();
-        if (valid) epilogue_row<NC>(p, r, alpha, pix, tco * BN + c * NC);
+    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo variant for kh x kw > 1x1, stride 1: ONE TMA box of (bh+kh-1) x (bw+kw-1) input pixels x 64 channels is
+// loaded per channel chunk and all kh*kw taps read it through shifted UMMA descriptors
+//   start = halo + (r*(bw+kw-1) + s) * 128 B,  SBO = (bw+kw-1) * 128 B,  base_offset = 0
+// which is valid because the 128B swizzle is a function of absolute shared-memory address bits
+// (profiles/r01_halo_descriptor_experiment.log).  Per 128-pixel tile this cuts the activation bytes that cross
+// L2->SMEM from taps x 16 KiB to ~23 KiB per 64 channels; the filter tiles travel through their own ring.
+// Tile = 16 rows x 8 columns of one image (8-pixel row groups are what makes the descriptor regular).
+constexpr int HALO_BW = 8, HALO_BH = 16;
+
+template <int BN, int SA, int SB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const IgemmParams p, int a_stage_bytes, int halo_w, int halo_bytes) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int ACC_STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN) < 32 ? 32 : (ACC_STAGES * BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + SA * a_stage_bytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + SB * B_STAGE_BYTES);
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* tfull = emptyB + SB;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      // Halo loads run one channel chunk ahead of the filter loads: chunk q+1 is requested a few taps into
+      // chunk q so that it has landed when the MMA warp gets there.
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int a_tile = blockIdx.x, a_kc = 0;  // next halo to request
+      auto issue_halo = [&]() {
+        if (a_tile >= p.num_tiles) return;
+        int t = a_tile / p.tiles_co;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        mbar_wait(&emptyA[sa], pa ^ 1);
+        mbar_arrive_expect_tx(&fullA[sa], halo_bytes);
+        tma_load_4d(sA + sa * a_stage_bytes, &tmA, &fullA[sa], a_kc * BK, tw * p.bw - p.pad_l, th * p.bh - p.pad_t, t);
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+        if (++a_kc == p.kchunks) { a_kc = 0; a_tile += gridDim.x; }
+      };
+      issue_halo();
+      const int ahead_tap = p.taps > 2 ? 2 : 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int co0 = (tile % p.tiles_co) * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (tap == ahead_tap) issue_halo();
+            const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
+            mbar_wait(&emptyB[sb], pb ^ 1);
+            mbar_arrive_expect_tx(&fullB[sb], B_STAGE_BYTES);
+            tma_load_3d(sB + sb * B_STAGE_BYTES, &tmB, &fullB[sb], kc * BK, co0, tap_b);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
-      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&fullA[sa], pa);
+          const uint32_t a_base = smem_u32(sA + sa * a_stage_bytes);
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            mbar_wait(&fullB[sb], pb);
+            tc_fence_after();
+            const uint64_t adesc = umma_smem_desc_sw128(a_base + (r * halo_w + s) * 128, 16, sbo);
+            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + sb * B_STAGE_BYTES), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&emptyB[sb]);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(&emptyA[sa]);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane);
   }
 
   tc_fence_before();
@@ -472,6 +641,26 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPar
   return 0;
 }
 
+template <int BN, int SA, int SB>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, int a_stage_bytes, int halo_w,
+                       int halo_bytes, cudaStream_t stream) {
+  const int smem = SA * a_stage_bytes + SB * BN * BK * 2 + 1024 + 512;
+  if (smem > 232448) return fail(GANB_E_UNSUPPORTED, "conv halo kernel: %d bytes of shared memory needed", smem);
+  auto kern = conv_halo_kernel<BN, SA, SB>;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "halo smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  p.tiles_co = ceil_div(p.Cout, BN);
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
+  GANB_CHECK_LAUNCH("conv_halo_kernel");
+  return 0;
+}
+
 }  // namespace ganb
 
 using namespace ganb;
@@ -493,7 +682,13 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   p.N = n; p.Ho = ho; p.Wo = wo; p.Cout = cout;
   p.taps = kh * kw; p.kw = kw;
   p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
-  pick_box(BM, ho, wo, &p.bw, &p.bh, &p.bn);
+  // halo path: every tap reads one shared-memory halo tile (needs 8-pixel row groups: 16 x 8 tiles per image)
+  const bool halo = (kh * kw > 1) && ho >= HALO_BH && wo >= HALO_BW && (kh + HALO_BH - 1) <= 256;
+  if (halo) {
+    p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1;
+  } else {
+    pick_box(BM, ho, wo, &p.bw, &p.bh, &p.bn);
+  }
   p.tiles_w = ceil_div(wo, p.bw);
   p.tiles_h = ceil_div(ho, p.bh);
   p.tiles_n = ceil_div(n, p.bn);
@@ -508,10 +703,11 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   while (bn_tile > 64 && m_tiles * ceil_div(cout, bn_tile) < sm_count()) bn_tile >>= 1;
 
   CUtensorMap tmA, tmB;
+  const int halo_w = p.bw + kw - 1, halo_h = p.bh + kh - 1;
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
-    const uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    const uint32_t box[4] = {BK, (uint32_t)(halo ? halo_w : p.bw), (uint32_t)(halo ? halo_h : p.bh), (uint32_t)p.bn};
     int rc = encode_tmap_bf16(&tmA, x, 4, dims, strides, box, nullptr);
     if (rc) return rc;
   }
@@ -521,6 +717,17 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
     const uint32_t box[3] = {BK, (uint32_t)bn_tile, 1};
     int rc = encode_tmap_bf16(&tmB, wp, 3, dims, strides, box, nullptr);
     if (rc) return rc;
+  }
+  if (halo) {
+    const int halo_bytes = halo_w * halo_h * 128;
+    const int a_stage = (halo_bytes + 1023) / 1024 * 1024;
+    switch (bn_tile) {
+      case 16: return launch_halo<16, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 32: return launch_halo<32, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 64: return launch_halo<64, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 128: return launch_halo<128, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      default: return launch_halo<256, 2, 5>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+    }
   }
   switch (bn_tile) {
     case 16: return launch_igemm<16, 8>(tmA, tmB, p, stream);

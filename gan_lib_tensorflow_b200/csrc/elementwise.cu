@@ -94,27 +94,35 @@ bn_stats_partial_kernel(const float* __restrict__ x, int rows_per_group, int c, 
   }
 }
 
-// 256 threads = 32 channels x 8 chunk lanes; lanes are combined in a fixed order (deterministic).
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per (group, channel): the 32 lanes split the chunk partials and combine with a fixed shuffle tree
+// (deterministic); 8 channels per 256-thread block.
 __global__ void __launch_bounds__(256)
 bn_stats_finalize_kernel(const float* __restrict__ partial, int c, int groups, int chunks, float inv_count, float eps,
                          float* __restrict__ mean, float* __restrict__ rstd) {
-  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + cx;  // flat (group, channel)
-  __shared__ double sh_s[8][32], sh_q[8][32];
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);  // flat (group, channel)
+  if (i >= groups * c) return;
+  const int g = i / c, ch = i - g * c;
   double s = 0.0, q = 0.0;
-  if (i < groups * c) {
-    const int g = i / c, ch = i - g * c;
-    for (int k = lane; k < chunks; k += 8) {
-      const float* p = partial + (static_cast<int64_t>(g) * chunks + k) * 2 * c;
-      s += p[ch];
-      q += p[c + ch];
-    }
+  for (int k = lane; k < chunks; k += 32) {
+    const float* p = partial + (static_cast<int64_t>(g) * chunks + k) * 2 * c;
+    s += p[ch];
+    q += p[c + ch];
   }
-  sh_s[lane][cx] = s;
-  sh_q[lane][cx] = q;
-  __syncthreads();
-  if (lane == 0 && i < groups * c) {
-    for (int l = 1; l < 8; ++l) { s += sh_s[l][cx]; q += sh_q[l][cx]; }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane == 0) {
     const double m = s * inv_count;
     double var = q * inv_count - m * m;
     if (var < 0.0) var = 0.0;
@@ -220,48 +228,64 @@ struct NormActBwd {
   void* dx; int dx_bf16;
 };
 
-// returns dL/dy (gradient w.r.t. the normalised, pre-activation value) and xhat for one float4 of channels
-__device__ __forceinline__ void norm_act_bwd_point(const NormActBwd& p, int ni, int hi, int wi, int c4, int g,
-                                                   float4 a, float4& dy, float4& xhat, float4& ga) {
-  // upstream gradient (sum over the 2x2 replicas when the forward upsampled)
-  float4 dz;
-  if (!p.upsample) {
-    const int64_t o = ((static_cast<int64_t>(ni) * p.h + hi) * p.w + wi) * p.dz_cstride + c4;
-    dz = p.dz_bf16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.dz) + o) : ld4(reinterpret_cast<const float*>(p.dz) + o);
-  } else {
-    const int ow = 2 * p.w;
-    const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
-    dz = make_float4(0, 0, 0, 0);
-#pragma unroll
-    for (int dyy = 0; dyy < 2; ++dyy)
-#pragma unroll
-      for (int dxx = 0; dxx < 2; ++dxx) {
-        const int64_t o = (base + dyy * ow + dxx) * p.dz_cstride + c4;
-        const float4 t = p.dz_bf16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.dz) + o)
-                                   : ld4(reinterpret_cast<const float*>(p.dz) + o);
-        dz.x += t.x; dz.y += t.y; dz.z += t.z; dz.w += t.w;
-      }
+// upstream gradient of one float4 of channels (summed over the 2x2 replicas when the forward upsampled);
+// `px` is the pixel index inside the sample
+template <bool UPS, bool DZ16>
+__device__ __forceinline__ float4 norm_act_bwd_load_dz(const NormActBwd& p, int ni, int px, int c4) {
+  if (!UPS) {
+    const int64_t o = (static_cast<int64_t>(ni) * p.h * p.w + px) * p.dz_cstride + c4;
+    return DZ16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.dz) + o) : ld4(reinterpret_cast<const float*>(p.dz) + o);
   }
-  float4 y = a;
-  xhat = a;
-  ga = make_float4(1, 1, 1, 1);
-  if (p.mean) {
-    const float4 m = ld4(p.mean + g * p.c + c4), r = ld4(p.rstd + g * p.c + c4);
-    xhat = make_float4((a.x - m.x) * r.x, (a.y - m.y) * r.y, (a.z - m.z) * r.z, (a.w - m.w) * r.w);
-    float4 be = make_float4(0, 0, 0, 0);
+  const int hi = px / p.w, wi = px - hi * p.w;
+  const int ow = 2 * p.w;
+  const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
+  float4 t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t o = (base + (k >> 1) * ow + (k & 1)) * p.dz_cstride + c4;
+    t[k] = DZ16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(p.dz) + o) : ld4(reinterpret_cast<const float*>(p.dz) + o);
+  }
+  return make_float4(t[0].x + t[1].x + t[2].x + t[3].x, t[0].y + t[1].y + t[2].y + t[3].y,
+                     t[0].z + t[1].z + t[2].z + t[3].z, t[0].w + t[1].w + t[2].w + t[3].w);
+}
+
+// per-thread constants of the backward pass for one float4 of channels of one sample
+struct NormActBwdConst {
+  float4 m, r, ga, be;
+};
+template <bool NORM>
+__device__ __forceinline__ NormActBwdConst norm_act_bwd_const(const NormActBwd& p, int ni, int g, int c4) {
+  NormActBwdConst k;
+  k.m = make_float4(0, 0, 0, 0); k.r = make_float4(1, 1, 1, 1);
+  k.ga = make_float4(1, 1, 1, 1); k.be = make_float4(0, 0, 0, 0);
+  if (NORM) {
+    k.m = ld4(p.mean + g * p.c + c4);
+    k.r = ld4(p.rstd + g * p.c + c4);
     if (p.gamma) {
       const int row = p.labels ? __ldg(p.labels + ni) : 0;
-      ga = ld4(p.gamma + static_cast<int64_t>(row) * p.c + c4);
-      be = ld4(p.beta + static_cast<int64_t>(row) * p.c + c4);
+      k.ga = ld4(p.gamma + static_cast<int64_t>(row) * p.c + c4);
+      k.be = ld4(p.beta + static_cast<int64_t>(row) * p.c + c4);
     }
-    y = make_float4(xhat.x * ga.x + be.x, xhat.y * ga.y + be.y, xhat.z * ga.z + be.z, xhat.w * ga.w + be.w);
+  }
+  return k;
+}
+// dy = dz * act'(y) and xhat, from the forward input a and the upstream gradient dz
+template <bool NORM>
+__device__ __forceinline__ void norm_act_bwd_math(const NormActBwd& p, const NormActBwdConst& k, float4 a, float4 dz,
+                                                  float4& dy, float4& xhat) {
+  float4 y = a;
+  xhat = a;
+  if (NORM) {
+    xhat = make_float4((a.x - k.m.x) * k.r.x, (a.y - k.m.y) * k.r.y, (a.z - k.m.z) * k.r.z, (a.w - k.m.w) * k.r.w);
+    y = make_float4(xhat.x * k.ga.x + k.be.x, xhat.y * k.ga.y + k.be.y, xhat.z * k.ga.z + k.be.z, xhat.w * k.ga.w + k.be.w);
   }
   dy = make_float4(dz.x * dact_f(y.x, p.act), dz.y * dact_f(y.y, p.act), dz.z * dact_f(y.z, p.act),
                    dz.w * dact_f(y.w, p.act));
 }
 
 // grid (chunks, n); per-sample partial sums A = sum dy, B = sum dy*xhat
-__global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(const NormActBwd p) {
+template <bool UPS, bool DZ16>
+__global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(const NormActBwd p) {
   const int ni = blockIdx.y, chunk = blockIdx.x;
   const int v = p.c >> 2;
   const int lanes = max(1, 256 / min(v, 256));
@@ -275,13 +299,26 @@ __global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(const NormActB
     const int col = cb + cx;
     float4 sa = make_float4(0, 0, 0, 0), sb = make_float4(0, 0, 0, 0);
     if (col < v && ry < lanes) {
-      for (int px = p0 + ry; px < p1; px += lanes) {
-        const int hi = px / p.w, wi = px - hi * p.w;
-        const float4 a = ld4(p.x + (static_cast<int64_t>(ni) * hw + px) * p.c + col * 4);
-        float4 dy, xh, ga;
-        norm_act_bwd_point(p, ni, hi, wi, col * 4, g, a, dy, xh, ga);
-        sa.x += dy.x; sa.y += dy.y; sa.z += dy.z; sa.w += dy.w;
-        sb.x += dy.x * xh.x; sb.y += dy.y * xh.y; sb.z += dy.z * xh.z; sb.w += dy.w * xh.w;
+      const NormActBwdConst kc = norm_act_bwd_const<true>(p, ni, g, col * 4);
+      constexpr int U = 4;
+      for (int px = p0 + ry; px < p1; px += lanes * U) {
+        float4 a[U], dz[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int qx = px + u * lanes;
+          if (qx < p1) {
+            a[u] = ld4(p.x + (static_cast<int64_t>(ni) * hw + qx) * p.c + col * 4);
+            dz[u] = norm_act_bwd_load_dz<UPS, DZ16>(p, ni, qx, col * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (px + u * lanes >= p1) break;
+          float4 dy, xh;
+          norm_act_bwd_math<true>(p, kc, a[u], dz[u], dy, xh);
+          sa.x += dy.x; sa.y += dy.y; sa.z += dy.z; sa.w += dy.w;
+          sb.x += dy.x * xh.x; sb.y += dy.y * xh.y; sb.z += dy.z * xh.z; sb.w += dy.w * xh.w;
+        }
       }
     }
     sh_a[threadIdx.x] = sa;
@@ -302,63 +339,65 @@ __global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(const NormActB
 }
 
 // Stage 1: per-sample sums A_n = sum_chunks, B_n, and the group sums S1 = sum gamma*A, S2 = sum gamma*B.
-// 256 threads = 32 channels x 8 sample lanes, combined in a fixed order (deterministic). grid (c/32, groups).
+// One warp per (group, channel): lanes split the samples, fixed shuffle tree (deterministic). grid (c/8, groups).
 __global__ void __launch_bounds__(256)
 norm_act_bwd_finalize_kernel(const float* __restrict__ part, int n, int c, int chunks, int groups,
                              const float* __restrict__ gamma, const int* __restrict__ labels,
                              float* __restrict__ sums /*[n][2][c]*/, float* __restrict__ s1, float* __restrict__ s2) {
-  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int ch = blockIdx.x * 32 + cx;
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int g = blockIdx.y;
+  if (ch >= c) return;
   const int n_per_group = n / groups;
-  __shared__ float sh1[8][32], sh2[8][32];
   float acc1 = 0.f, acc2 = 0.f;
-  if (ch < c) {
-    for (int ni = g * n_per_group + lane; ni < (g + 1) * n_per_group; ni += 8) {
-      float a = 0.f, b = 0.f;
-      for (int k = 0; k < chunks; ++k) {
-        const float* q = part + (static_cast<int64_t>(ni) * chunks + k) * 2 * c;
-        a += q[ch];
-        b += q[c + ch];
-      }
-      sums[(static_cast<int64_t>(ni) * 2) * c + ch] = a;
-      sums[(static_cast<int64_t>(ni) * 2 + 1) * c + ch] = b;
-      float ga = 1.f;
-      if (gamma) ga = gamma[static_cast<int64_t>(labels ? labels[ni] : 0) * c + ch];
-      acc1 += ga * a;
-      acc2 += ga * b;
+  for (int ni = g * n_per_group + lane; ni < (g + 1) * n_per_group; ni += 32) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < chunks; ++k) {
+      const float* q = part + (static_cast<int64_t>(ni) * chunks + k) * 2 * c;
+      a += q[ch];
+      b += q[c + ch];
     }
+    sums[(static_cast<int64_t>(ni) * 2) * c + ch] = a;
+    sums[(static_cast<int64_t>(ni) * 2 + 1) * c + ch] = b;
+    float ga = 1.f;
+    if (gamma) ga = gamma[static_cast<int64_t>(labels ? labels[ni] : 0) * c + ch];
+    acc1 += ga * a;
+    acc2 += ga * b;
   }
-  sh1[lane][cx] = acc1;
-  sh2[lane][cx] = acc2;
-  __syncthreads();
-  if (lane == 0 && ch < c) {
-    for (int l = 1; l < 8; ++l) { acc1 += sh1[l][cx]; acc2 += sh2[l][cx]; }
+  acc1 = warp_sum_f(acc1);
+  acc2 = warp_sum_f(acc2);
+  if (lane == 0) {
     s1[g * c + ch] = acc1;
     s2[g * c + ch] = acc2;
   }
 }
 
-// Stage 2: dgamma[row, ch] += sum_{n: label_n == row} B_n ; dbeta likewise with A_n. One thread per (row, ch)
-// walks the samples in order (deterministic scatter of tf.nn.embedding_lookup's gradient).
-__global__ void norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int n, int c, int n_rows,
-                                            const int* __restrict__ labels, float* __restrict__ dgamma,
-                                            float* __restrict__ dbeta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Stage 2: dgamma[row, ch] += sum_{n: label_n == row} B_n ; dbeta likewise with A_n. One warp per (row, ch): lanes
+// split the samples and combine with a fixed shuffle tree (deterministic scatter of the lookup's gradient).
+__global__ void __launch_bounds__(256)
+norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int n, int c, int n_rows, const int* __restrict__ labels,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= n_rows * c) return;
   const int row = i / c, ch = i - row * c;
   float a = 0.f, b = 0.f;
-  for (int ni = 0; ni < n; ++ni) {
+  for (int ni = lane; ni < n; ni += 32) {
     if ((labels ? labels[ni] : 0) == row) {
       a += sums[(static_cast<int64_t>(ni) * 2) * c + ch];
       b += sums[(static_cast<int64_t>(ni) * 2 + 1) * c + ch];
     }
   }
-  dbeta[i] += a;
-  dgamma[i] += b;
+  a = warp_sum_f(a);
+  b = warp_sum_f(b);
+  if (lane == 0) {
+    dbeta[i] += a;
+    dgamma[i] += b;
+  }
 }
 
-__global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(const NormActBwd p, int pix_per_chunk) {
+template <bool NORM, bool UPS, bool DZ16>
+__global__ void __launch_bounds__(256, 3) norm_act_bwd_apply_kernel(const NormActBwd p, int pix_per_chunk) {
   const int ni = blockIdx.y;
   const int v = p.c >> 2;
   const int cols = min(v, 256);
@@ -373,30 +412,44 @@ __global__ void __launch_bounds__(256) norm_act_bwd_apply_kernel(const NormActBw
     const int col = cb + cx;
     if (col >= v) continue;
     const int c4 = col * 4;
-    float4 r = make_float4(1, 1, 1, 1), t1 = make_float4(0, 0, 0, 0), t2 = make_float4(0, 0, 0, 0);
-    if (p.mean) {
-      r = ld4(p.rstd + g * p.c + c4);
+    float4 t1 = make_float4(0, 0, 0, 0), t2 = make_float4(0, 0, 0, 0);
+    if (NORM) {
       t1 = ld4(p.s1 + g * p.c + c4);
       t2 = ld4(p.s2 + g * p.c + c4);
       t1 = make_float4(k * t1.x, k * t1.y, k * t1.z, k * t1.w);
       t2 = make_float4(k * t2.x, k * t2.y, k * t2.z, k * t2.w);
     }
-    for (int px = p0 + ly; px < p1; px += lanes) {
-      const int hi = px / p.w, wi = px - hi * p.w;
-      const int64_t pix = static_cast<int64_t>(ni) * hw + px;
-      const float4 a = ld4(p.x + pix * p.c + c4);
-      float4 dy, xh, ga;
-      norm_act_bwd_point(p, ni, hi, wi, c4, g, a, dy, xh, ga);
-      float4 dx = dy;
-      if (p.mean)
-        dx = make_float4(r.x * (ga.x * dy.x - t1.x - xh.x * t2.x), r.y * (ga.y * dy.y - t1.y - xh.y * t2.y),
-                         r.z * (ga.z * dy.z - t1.z - xh.z * t2.z), r.w * (ga.w * dy.w - t1.w - xh.w * t2.w));
-      if (p.add) {
-        const float4 q = ld4(p.add + pix * p.c + c4);
-        dx.x += q.x; dx.y += q.y; dx.z += q.z; dx.w += q.w;
+    const NormActBwdConst kc = norm_act_bwd_const<NORM>(p, ni, g, c4);
+    // loads of a whole batch are issued before its stores (the output may alias the inputs for the compiler)
+    constexpr int U = 4;
+    for (int px = p0 + ly; px < p1; px += lanes * U) {
+      float4 a[U], dz[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int qx = px + u * lanes;
+        if (qx < p1) {
+          a[u] = ld4(p.x + (static_cast<int64_t>(ni) * hw + qx) * p.c + c4);
+          dz[u] = norm_act_bwd_load_dz<UPS, DZ16>(p, ni, qx, c4);
+        }
       }
-      if (p.dx_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.dx) + pix * p.c + c4, dx);
-      else st4(reinterpret_cast<float*>(p.dx) + pix * p.c + c4, dx);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int qx = px + u * lanes;
+        if (qx >= p1) break;
+        const int64_t pix = static_cast<int64_t>(ni) * hw + qx;
+        float4 dy, xh;
+        norm_act_bwd_math<NORM>(p, kc, a[u], dz[u], dy, xh);
+        float4 dx = dy;
+        if (NORM)
+          dx = make_float4(kc.r.x * (kc.ga.x * dy.x - t1.x - xh.x * t2.x), kc.r.y * (kc.ga.y * dy.y - t1.y - xh.y * t2.y),
+                           kc.r.z * (kc.ga.z * dy.z - t1.z - xh.z * t2.z), kc.r.w * (kc.ga.w * dy.w - t1.w - xh.w * t2.w));
+        if (p.add) {
+          const float4 q = ld4(p.add + pix * p.c + c4);
+          dx.x += q.x; dx.y += q.y; dx.z += q.z; dx.w += q.w;
+        }
+        if (p.dx_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.dx) + pix * p.c + c4, dx);
+        else st4(reinterpret_cast<float*>(p.dx) + pix * p.c + c4, dx);
+      }
     }
   }
 }
@@ -581,18 +634,13 @@ colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_p
 }
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, float beta, float* __restrict__ out) {
-  const int cx = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int ch = blockIdx.x * 32 + cx;
-  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ch >= c) return;
   float s = 0.f;
-  if (ch < c)
-    for (int k = lane; k < chunks; k += 8) s += partial[static_cast<int64_t>(k) * c + ch];
-  sh[lane][cx] = s;
-  __syncthreads();
-  if (lane == 0 && ch < c) {
-    for (int l = 1; l < 8; ++l) s += sh[l][cx];
-    out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
-  }
+  for (int k = lane; k < chunks; k += 32) s += partial[static_cast<int64_t>(k) * c + ch];
+  s = warp_sum_f(s);
+  if (lane == 0) out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
 }
 
 template <typename TIn>
@@ -887,7 +935,7 @@ extern "C" int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, f
   bn_stats_partial_kernel<<<dim3(used, groups), 256, 0, STREAM>>>(x, rows_per_group, c, used, rows_per_chunk,
                                                                   static_cast<float*>(workspace));
   GANB_CHECK_LAUNCH("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<ceil_div(groups * c, 32), 256, 0, STREAM>>>(
+  bn_stats_finalize_kernel<<<ceil_div(groups * c, 8), 256, 0, STREAM>>>(
       static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
   GANB_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return 0;
@@ -953,14 +1001,20 @@ extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, i
     float* sums = p.part + static_cast<int64_t>(n) * chunks * 2 * c;
     float* s1 = sums + 2LL * n * c;
     float* s2 = s1 + static_cast<int64_t>(groups) * c;
-    norm_act_bwd_reduce_kernel<<<dim3(p.chunks, n), 256, 0, STREAM>>>(p);
+    {
+      const dim3 grid(p.chunks, n);
+      if (upsample && p.dz_bf16) norm_act_bwd_reduce_kernel<true, true><<<grid, 256, 0, STREAM>>>(p);
+      else if (upsample) norm_act_bwd_reduce_kernel<true, false><<<grid, 256, 0, STREAM>>>(p);
+      else if (p.dz_bf16) norm_act_bwd_reduce_kernel<false, true><<<grid, 256, 0, STREAM>>>(p);
+      else norm_act_bwd_reduce_kernel<false, false><<<grid, 256, 0, STREAM>>>(p);
+    }
     GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
-    norm_act_bwd_finalize_kernel<<<dim3(ceil_div(c, 32), groups), 256, 0, STREAM>>>(p.part, n, c, p.chunks, groups, gamma,
+    norm_act_bwd_finalize_kernel<<<dim3(ceil_div(c, 8), groups), 256, 0, STREAM>>>(p.part, n, c, p.chunks, groups, gamma,
                                                                                   labels, sums, s1, s2);
     GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
     if (gamma && dgamma && dbeta) {
       const int rows = (labels && n_rows > 0) ? n_rows : 1;
-      norm_act_bwd_scatter_kernel<<<ceil_div(rows * c, 256), 256, 0, STREAM>>>(sums, n, c, rows, labels, dgamma, dbeta);
+      norm_act_bwd_scatter_kernel<<<ceil_div(rows * c, 8), 256, 0, STREAM>>>(sums, n, c, rows, labels, dgamma, dbeta);
       GANB_CHECK_LAUNCH("norm_act_bwd_scatter_kernel");
     }
     p.s1 = s1; p.s2 = s2;
@@ -969,7 +1023,18 @@ extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, i
   {
     const int chunks2 = bwd_chunks(n, h * w);
     const int ppc = ceil_div(h * w, chunks2);
-    norm_act_bwd_apply_kernel<<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
+    const dim3 grid(ceil_div(h * w, ppc), n);
+    const int idx = (mean ? 4 : 0) | (upsample ? 2 : 0) | (p.dz_bf16 ? 1 : 0);
+    switch (idx) {
+      case 0: norm_act_bwd_apply_kernel<false, false, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+      case 1: norm_act_bwd_apply_kernel<false, false, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+      case 2: norm_act_bwd_apply_kernel<false, true, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+      case 3: norm_act_bwd_apply_kernel<false, true, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+      case 4: norm_act_bwd_apply_kernel<true, false, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+      case 5: norm_act_bwd_apply_kernel<true, false, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+      case 6: norm_act_bwd_apply_kernel<true, true, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+      default: norm_act_bwd_apply_kernel<true, true, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
+    }
   }
   GANB_CHECK_LAUNCH("norm_act_bwd_apply_kernel");
   return 0;
@@ -1118,7 +1183,7 @@ extern "C" int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, floa
   else
     colsum_partial_kernel<float><<<used, 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, rows_per_chunk, static_cast<float*>(workspace));
   GANB_CHECK_LAUNCH("colsum_partial_kernel");
-  colsum_finalize_kernel<<<ceil_div(c, 32), 256, 0, STREAM>>>(static_cast<float*>(workspace), c, used, beta, out);
+  colsum_finalize_kernel<<<ceil_div(c, 8), 256, 0, STREAM>>>(static_cast<float*>(workspace), c, used, beta, out);
   GANB_CHECK_LAUNCH("colsum_finalize_kernel");
   return 0;
 }

@@ -106,7 +106,9 @@ def check(prod, refs, tol_impl=TOL_IMPL, tol_fp32=TOL_BF16, tag=""):
             errs["dx"] = rel(prod["dx"], ref["dx"])
         gmax = max([np.linalg.norm(g) for g in ref["params"].values()] + [1e-30])
         for name, gr in ref["params"].items():
-            denom = max(np.linalg.norm(gr), 1e-3 * gmax)
+            # analytically-zero gradients (a bias in front of a batch norm) hold only rounding residue: they are
+            # measured against 5% of the largest parameter gradient of the op
+            denom = max(np.linalg.norm(gr), 5e-2 * gmax)
             errs[name] = float(np.linalg.norm(prod["params"][name].astype(np.float64) - gr) / denom)
         _report(f"{test} {tag} vs {mode}-oracle (tol {tol:g}): " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
         for k, v in errs.items():
