@@ -93,7 +93,7 @@ def MeanPoolConv(inputs, output_dim, filter_size=3, stride=1, name=None,
     output = F.meanpool2(inputs if inputs.dtype == F32 else F.cast(inputs, F32))
     return _conv2d.Conv2D(output, output.shape[-1], output_dim, filter_size, stride, name,
                           spectral_normed=spectral_normed, update_collection=update_collection,
-                          inputs_norm=inputs_norm, he_init=he_init, biases=biases)
+                          inputs_norm=inputs_norm, he_init=he_init, biases=biases, out_grad_dtype=BF16)
 
 
 def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None,
@@ -142,10 +142,8 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
         # ConvMeanPool / UpsampleConv / Conv2D with a 1x1 filter, he_init=False (resnet_block.py:123-127)
         shortcut = _conv2d.Conv2D(raw, input_dim, output_dim, 1, 1, name + '.Shortcut',
                                   spectral_normed=spectral_normed, update_collection=update_collection,
-                                  inputs_norm=inputs_norm, he_init=False, biases=biases,
-                                  out_grad_dtype=BF16 if resample == 'down' else None)
-        if resample == 'up':
-            shortcut = F.upsample2(shortcut)  # conv1x1(upsample(x)) == upsample(conv1x1(x))
+                                  inputs_norm=inputs_norm, he_init=False, biases=biases, out_grad_dtype=BF16)
+        # 'up': conv1x1(upsample(x)) == upsample(conv1x1(x)); the upsample itself happens inside Conv2's epilogue
 
     # ---- Conv1
     mid_dim = input_dim if resample == 'down' else output_dim
@@ -159,8 +157,12 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     if resample == 'down':
         t = conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut,
                  out_grad_dtype=BF16)
-        return F.meanpool2(t)  # meanpool(conv2) + meanpool(shortcut) == meanpool(conv2 + shortcut)
-    return conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut)
+        # meanpool(conv2) + meanpool(shortcut) == meanpool(conv2 + shortcut)
+        return F.meanpool2(t, out_grad_dtype=BF16)
+    # the block output feeds the next block's normalise/activation kernel and (through 1x1 / identity shortcuts)
+    # convolutions only: its gradient is a tensor-core operand, so it is produced in bf16 directly
+    return conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut,
+                residual_up2=(resample == 'up' and not identity_shortcut), out_grad_dtype=BF16)
 
 
 def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
@@ -180,7 +182,7 @@ def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
     output = _conv2d.Conv2D(output, DIM_D, DIM_D, 3, 1, name_prefix + '.Conv2', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
                             biases=biases, out_grad_dtype=BF16)
-    return F.meanpool2(output, addend=shortcut)
+    return F.meanpool2(output, addend=shortcut, out_grad_dtype=BF16)
 
 
 # ######## ######## PGGAN ######## ######## #

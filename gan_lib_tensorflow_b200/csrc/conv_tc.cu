@@ -29,6 +29,7 @@ struct IgemmParams {
   const float* alpha;
   const float* bias;
   const float* residual;
+  int res_up2;   // residual is stored at half resolution [N, Ho/2, Wo/2, Cout] and read through a nearest-2x upsample
   void* out;
   int out_bf16, act;
 };
@@ -64,9 +65,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // per float4 (this was the limiter of the first version of this kernel, profiles/r01_*).
 template <int NC>
 __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_t (&r)[NC], float alpha,
-                                             int64_t pix, int co_base, const float* __restrict__ bias_s) {
+                                             int64_t pix, int64_t res_pix, int co_base,
+                                             const float* __restrict__ bias_s) {
   const int cout = p.Cout;
   const int64_t off = pix * cout + co_base;
+  const int64_t roff = res_pix * cout + co_base;
   if (cout % 4 == 0) {
     float4 v[NC / 4];
 #pragma unroll
@@ -77,7 +80,7 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
       float4 q[NC / 4];
 #pragma unroll
       for (int j = 0; j < NC; j += 4)
-        q[j / 4] = (co_base + j < cout) ? __ldg(reinterpret_cast<const float4*>(p.residual + off + j))
+        q[j / 4] = (co_base + j < cout) ? __ldg(reinterpret_cast<const float4*>(p.residual + roff + j))
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < NC / 4; ++j) { v[j].x += q[j].x; v[j].y += q[j].y; v[j].z += q[j].z; v[j].w += q[j].w; }
@@ -116,7 +119,7 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
     for (int j = 0; j < NC; ++j) {
       v[j] = __uint_as_float(r[j]) * alpha;
       if (co_base + j < cout) {
-        if (p.residual) v[j] += __ldg(p.residual + off + j);
+        if (p.residual) v[j] += __ldg(p.residual + roff + j);
         if (p.bias) v[j] += bias_s[j];
         v[j] = apply_act(v[j], p.act);
       }
@@ -158,6 +161,8 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
     const int wo = tw * p.bw + iw, ho = th * p.bh + ih, n = tn * p.bn + in_;
     const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
     const int64_t pix = (static_cast<int64_t>(n) * p.Ho + ho) * p.Wo + wo;
+    const int64_t res_pix =
+        p.res_up2 ? (static_cast<int64_t>(n) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1) : pix;
     if (p.bias) {  // stage this tile's bias slice; the two buffers alternate with the accumulator stage
       for (int c = et; c < BN; c += EPI_THREADS) {
         const int co = tco * BN + c;
@@ -173,7 +178,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
       uint32_t r[NC];
       tmem_ld_cols<NC>(trow + c * NC, r);
       tmem_ld_wait();
-      if (valid) epilogue_row<NC>(p, r, alpha, pix, tco * BN + c * NC, &bias_s[as][c * NC]);
+      if (valid) epilogue_row<NC>(p, r, alpha, pix, res_pix, tco * BN + c * NC, &bias_s[as][c * NC]);
     }
     tc_fence_before();
     mbar_arrive(&tempty[as]);
@@ -230,60 +235,71 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int kiters = p.taps * p.kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int tco = t % p.tiles_co; t /= p.tiles_co;
-        const int tw = t % p.tiles_w;   t /= p.tiles_w;
-        const int th = t % p.tiles_h;   t /= p.tiles_h;
-        const int tn = t;
-        const int w0 = tw * p.bw * p.stride - p.pad_l;
-        const int h0 = th * p.bh * p.stride - p.pad_t;
-        const int n0 = tn * p.bn;
-        const int co0 = tco * BN;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int r = tap / p.kw, s = tap - r * p.kw;
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int kh = p.taps / p.kw;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tco = t % p.tiles_co; t /= p.tiles_co;
+      const int tw = t % p.tiles_w;   t /= p.tiles_w;
+      const int th = t % p.tiles_h;   t /= p.tiles_h;
+      const int tn = t;
+      const int w0 = tw * p.bw * p.stride - p.pad_l;
+      const int h0 = th * p.bh * p.stride - p.pad_t;
+      const int n0 = tn * p.bn;
+      const int co0 = tco * BN;
+      int tap = 0;
+      for (int r = 0; r < kh; ++r) {
+        for (int s2 = 0; s2 < p.kw; ++s2, ++tap) {
           const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * BK, w0 + s, h0 + r, n0);
-            tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kc * BK, co0, tap_b);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+              tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * BK, w0 + s2, h0 + r, n0);
+              tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kc * BK, co0, tap_b);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform registers and lets
+    // the compiler emit one predicated UTCHMMA per MMA); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint64_t desc_base = umma_desc_base_sw128(16, 1024);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      uint32_t acc = 0;
+      for (int kit = 0; kit < kiters; ++kit) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kit = 0; kit < kiters; ++kit) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES), 16, 1024);
+        if (elect_one()) {
+          const uint64_t adesc = umma_desc_at(desc_base, sA_addr + stage * A_STAGE_BYTES);
+          const uint64_t bdesc = umma_desc_at(desc_base, sB_addr + stage * B_STAGE_BYTES);
+          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+          umma_bf16(tmem_d, adesc, bdesc, IDESC, acc);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kit > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 1; k < BK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);
-        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        acc = 1u;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -308,8 +324,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Tile = 16 rows x 8 columns of one image (8-pixel row groups are what makes the descriptor regular).
 constexpr int HALO_BW = 8, HALO_BH = 16;
 
+constexpr int HALO_A_WARP = NUM_THREADS / 32;     // extra warp after the epilogue warps
+constexpr int HALO_THREADS = NUM_THREADS + 32;
+
 template <int BN, int SA, int SB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const IgemmParams p, int a_stage_bytes, int halo_w, int halo_bytes) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -351,71 +370,84 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      // Halo loads run one channel chunk ahead of the filter loads: chunk q+1 is requested a few taps into
-      // chunk q so that it has landed when the MMA warp gets there.
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int a_tile = blockIdx.x, a_kc = 0;  // next halo to request
-      auto issue_halo = [&]() {
-        if (a_tile >= p.num_tiles) return;
-        int t = a_tile / p.tiles_co;
-        const int tw = t % p.tiles_w; t /= p.tiles_w;
-        const int th = t % p.tiles_h; t /= p.tiles_h;
-        mbar_wait(&emptyA[sa], pa ^ 1);
-        mbar_arrive_expect_tx(&fullA[sa], halo_bytes);
-        tma_load_4d(sA + sa * a_stage_bytes, &tmA, &fullA[sa], a_kc * BK, tw * p.bw - p.pad_l, th * p.bh - p.pad_t, t);
-        if (++sa == SA) { sa = 0; pa ^= 1; }
-        if (++a_kc == p.kchunks) { a_kc = 0; a_tile += gridDim.x; }
-      };
-      issue_halo();
-      const int ahead_tap = p.taps > 2 ? 2 : 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int co0 = (tile % p.tiles_co) * BN;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int tap = 0; tap < p.taps; ++tap) {
-            if (tap == ahead_tap) issue_halo();
-            const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
-            mbar_wait(&emptyB[sb], pb ^ 1);
+    // ===================== TMA producer: filter tiles (warp-uniform loop, elected lane issues) =====================
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int co0 = (tile % p.tiles_co) * BN;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
+          mbar_wait(&emptyB[sb], pb ^ 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&fullB[sb], B_STAGE_BYTES);
             tma_load_3d(sB + sb * B_STAGE_BYTES, &tmB, &fullB[sb], kc * BK, co0, tap_b);
-            if (++sb == SB) { sb = 0; pb ^= 1; }
           }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; pb ^= 1; }
         }
       }
     }
+  } else if (warp == HALO_A_WARP) {
+    // ===================== TMA producer: activation halos =====================
+    // Own warp so that halo requests run as far ahead as the SA-deep ring allows, independent of the filter ring.
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile / p.tiles_co;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&emptyA[sa], pa ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&fullA[sa], halo_bytes);
+          tma_load_4d(sA + sa * a_stage_bytes, &tmA, &fullA[sa], kc * BK, tw * p.bw - p.pad_l, th * p.bh - p.pad_t, t);
+        }
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+    }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      int sa = 0, sb = 0, as = 0;
-      uint32_t pa = 0, pb = 0, aphase = 0;
-      const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&fullA[sa], pa);
-          const uint32_t a_base = smem_u32(sA + sa * a_stage_bytes);
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int r = tap / p.kw, s = tap - r * p.kw;
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    int sa = 0, sb = 0, as = 0;
+    uint32_t pa = 0, pb = 0, aphase = 0;
+    const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;
+    const uint64_t adesc_base = umma_desc_base_sw128(16, sbo);
+    const uint64_t bdesc_base = umma_desc_base_sw128(16, 1024);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    const int kw = p.kw, kh = p.taps / p.kw;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      uint32_t acc = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&fullA[sa], pa);
+        uint32_t a_row = sA_addr + sa * a_stage_bytes;   // halo row r of this stage
+        for (int r = 0; r < kh; ++r, a_row += sbo) {
+          for (int s2 = 0; s2 < kw; ++s2) {
             mbar_wait(&fullB[sb], pb);
             tc_fence_after();
-            const uint64_t adesc = umma_smem_desc_sw128(a_base + (r * halo_w + s) * 128, 16, sbo);
-            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + sb * B_STAGE_BYTES), 16, 1024);
+            if (elect_one()) {
+              const uint64_t adesc = umma_desc_at(adesc_base, a_row + s2 * 128);
+              const uint64_t bdesc = umma_desc_at(bdesc_base, sB_addr + sb * B_STAGE_BYTES);
+              umma_bf16(tmem_d, adesc, bdesc, IDESC, acc);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&emptyB[sb]);
+              for (int k = 1; k < BK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+              umma_commit(&emptyB[sb]);
+            }
+            __syncwarp();
+            acc = 1u;
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
-          umma_commit(&emptyA[sa]);
-          if (++sa == SA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(&tfull[as]);
-        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        if (elect_one()) umma_commit(&emptyA[sa]);
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else {
     epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane);
@@ -499,15 +531,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int ci0 = tci * BM, co0 = tco * BN;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int pb = pb_begin; pb < pb_end; ++pb) {
-        int t = pb;
-        const int bwi = t % p.pb_w; t /= p.pb_w;
-        const int bhi = t % p.pb_h; t /= p.pb_h;
-        const int w0 = bwi * p.bw, h0 = bhi * p.bh, n0 = t * p.bn;
-        mbar_wait(&empty[stage], phase ^ 1);
+    // TMA producer: warp-uniform loop, one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    int bwi = pb_begin % p.pb_w, bhi = (pb_begin / p.pb_w) % p.pb_h, bni = pb_begin / (p.pb_w * p.pb_h);
+    for (int pb = pb_begin; pb < pb_end; ++pb) {
+      const int w0 = bwi * p.bw, h0 = bhi * p.bh, n0 = bni * p.bn;
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
         uint8_t* a = sA + stage * A_BYTES;
         uint8_t* b = sB + stage * B_BYTES;
@@ -517,32 +548,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
           tma_load_4d(b + j * BOX_BYTES, &tmDY, &full[stage], co0 + 64 * j, w0, h0, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (++bwi == p.pb_w) { bwi = 0; if (++bhi == p.pb_h) { bhi = 0; ++bni; } }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool first = true;
-      for (int pb = pb_begin; pb < pb_end; ++pb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        // MN-major, 128B swizzle: 64 channels per row, 8-pixel groups 1024 B apart (SBO),
-        // next 64-channel box BOX_BYTES away (LBO).
-        const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), BOX_BYTES, 1024);
-        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), BOX_BYTES, 1024);
+    // MMA issuer: warp-uniform loop, one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc = 0;
+    // MN-major, 128B swizzle: 64 channels per row, 8-pixel groups 1024 B apart (SBO),
+    // next 64-channel box BOX_BYTES away (LBO).
+    const uint64_t desc_base = umma_desc_base_sw128(BOX_BYTES, 1024);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    for (int pb = pb_begin; pb < pb_end; ++pb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = umma_desc_at(desc_base, sA_addr + stage * A_BYTES);
+        const uint64_t bdesc = umma_desc_at(desc_base, sB_addr + stage * B_BYTES);
+        // 16 pixels = 16 rows of 128 B = 2048 B -> +128 in 16-byte units
+        umma_bf16(tmem_base, adesc, bdesc, IDESC, acc);
 #pragma unroll
-        for (int k = 0; k < PB / 16; ++k) {
-          // 16 pixels = 16 rows of 128 B = 2048 B -> +128 in 16-byte units
-          umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, (first && k == 0) ? 0u : 1u);
-        }
-        first = false;
+        for (int k = 1; k < PB / 16; ++k) umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, 1u);
         umma_commit(&empty[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull);
+      __syncwarp();
+      acc = 1u;
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(tfull);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int ci = ci0 + q * 32 + lane;
@@ -656,7 +693,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
+  kern<<<grid, HALO_THREADS, smem, stream>>>(tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
   GANB_CHECK_LAUNCH("conv_halo_kernel");
   return 0;
 }
@@ -668,7 +705,7 @@ using namespace ganb;
 extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho,
                                  int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
                                  int flip_taps, const float* alpha, const float* bias, const float* residual,
-                                 int act, int out_dtype, void* stream_) {
+                                 int residual_up2, int act, int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !wp || !y) return fail(GANB_E_BADARG, "conv2d_igemm: null buffer");
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || ho <= 0 || wo <= 0 || cout <= 0 || kh <= 0 || kw <= 0)
@@ -695,6 +732,8 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   p.kchunks = ceil_div(cin, BK);
   p.flip = flip_taps;
   p.alpha = alpha; p.bias = bias; p.residual = residual;
+  p.res_up2 = (residual && residual_up2) ? 1 : 0;
+  if (p.res_up2 && ((ho | wo) & 1)) return fail(GANB_E_BADARG, "conv2d_igemm: upsampled residual needs even ho, wo");
   p.out = y; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
 
   // choose the N tile: whole Cout when it fits, shrunk while the grid cannot fill the machine
@@ -722,9 +761,9 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
     const int halo_bytes = halo_w * halo_h * 128;
     const int a_stage = (halo_bytes + 1023) / 1024 * 1024;
     switch (bn_tile) {
-      case 16: return launch_halo<16, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
-      case 32: return launch_halo<32, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
-      case 64: return launch_halo<64, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 16: return launch_halo<16, 7, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 32: return launch_halo<32, 6, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 64: return launch_halo<64, 5, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
       case 128: return launch_halo<128, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
       default: return launch_halo<256, 2, 5>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
     }

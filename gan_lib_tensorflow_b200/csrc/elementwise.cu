@@ -54,10 +54,22 @@ static inline int grid_for(int64_t work_items, int threads, int max_blocks_per_s
 }
 
 // ------------------------------------------------------------------------------------------------ bn stats
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // partial[(g*chunks + chunk)*2*C + {0,1}*C + c] = sum / sum of squares over the chunk's rows.
+template <typename TX>
 __global__ void __launch_bounds__(256)
-bn_stats_partial_kernel(const float* __restrict__ x, int rows_per_group, int c, int chunks, int rows_per_chunk,
-                        float* __restrict__ partial) {
+bn_stats_partial_kernel(const TX* __restrict__ x, int rows_per_group, int c, int chunks, int rows_per_chunk,
+                float* __restrict__ partial) {
   const int g = blockIdx.y, chunk = blockIdx.x;
   const int v = c >> 2;                          // float4 columns
   const int lanes = max(1, 256 / min(v, 256));   // row lanes per column block
@@ -65,16 +77,24 @@ bn_stats_partial_kernel(const float* __restrict__ x, int rows_per_group, int c, 
   const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
   const int r0 = chunk * rows_per_chunk;
   const int r1 = min(rows_per_group, r0 + rows_per_chunk);
-  const float* xg = x + static_cast<int64_t>(g) * rows_per_group * c;
+  const TX* xg = x + static_cast<int64_t>(g) * rows_per_group * c;
   __shared__ float4 sh_s[256], sh_q[256];
   for (int cb = 0; cb < v; cb += cols_per_pass) {
     const int col = cb + cx;
     float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
     if (col < v && ry < lanes) {
-      for (int r = r0 + ry; r < r1; r += lanes) {
-        const float4 a = ld4(xg + static_cast<int64_t>(r) * c + col * 4);
-        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-        q.x += a.x * a.x; q.y += a.y * a.y; q.z += a.z * a.z; q.w += a.w * a.w;
+      constexpr int U = 4;
+      for (int r = r0 + ry; r < r1; r += lanes * U) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          a[u] = (r + u * lanes < r1) ? ld4(xg + static_cast<int64_t>(r + u * lanes) * c + col * 4)
+                                      : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w;
+          q.x += a[u].x * a[u].x; q.y += a[u].y * a[u].y; q.z += a[u].z * a[u].z; q.w += a[u].w * a[u].w;
+        }
       }
     }
     sh_s[threadIdx.x] = s;
@@ -92,17 +112,6 @@ bn_stats_partial_kernel(const float* __restrict__ x, int rows_per_group, int c, 
     }
     __syncthreads();
   }
-}
-
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
 }
 
 // one warp per (group, channel): the 32 lanes split the chunk partials and combine with a fixed shuffle tree
@@ -133,7 +142,7 @@ bn_stats_finalize_kernel(const float* __restrict__ partial, int c, int groups, i
 
 // ------------------------------------------------------------------------------------------------ norm+act fwd
 struct NormActFwd {
-  const float* x;
+  const void* x; int x_bf16;
   int n, h, w, c;
   const float* mean; const float* rstd; int groups;       // mean == nullptr: no normalisation
   const float* gamma; const float* beta; const int* labels;  // tables [n_labels, c]; labels == nullptr: row 0
@@ -144,6 +153,7 @@ struct NormActFwd {
 
 // grid (pixel chunks, n): a thread owns one float4 of channels, so scale/shift (and the label lookup) are
 // computed once and the loop streams x with several independent 16-byte loads in flight.
+template <typename TX>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p, int pix_per_chunk) {
   const int ni = blockIdx.y;
   const int v = p.c >> 2;
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p, i
       sc = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
       sh = make_float4(be.x - m.x * sc.x, be.y - m.y * sc.y, be.z - m.z * sc.z, be.w - m.w * sc.w);
     }
-    const float* xb = p.x + static_cast<int64_t>(ni) * hw * p.c + c4;
+    const TX* xb = static_cast<const TX*>(p.x) + static_cast<int64_t>(ni) * hw * p.c + c4;
     constexpr int U = 4;
     for (int px = p0 + ly; px < p1; px += lanes * U) {
       float4 a[U];
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p, i
 
 // ------------------------------------------------------------------------------------------------ norm+act bwd
 struct NormActBwd {
-  const float* x;                 // forward input (pre-normalisation), [n,h,w,c]
+  const void* x; int x_bf16;      // forward input (pre-normalisation), [n,h,w,c], fp32 or bf16
   const void* dz; int dz_bf16; int dz_cstride;   // gradient of the forward OUTPUT ([n,(2)h,(2)w,*])
   int n, h, w, c;
   const float* mean; const float* rstd; int groups;
@@ -224,7 +234,7 @@ struct NormActBwd {
   // apply inputs/outputs
   const float* s1; const float* s2;   // [groups, c]  sum(dxhat), sum(dxhat*xhat)
   float inv_count;
-  const float* add;                   // optional fp32 tensor added to dx (second gradient path)
+  const void* add; int add_bf16;      // optional fp32 / bf16 tensor added to dx (second gradient path)
   void* dx; int dx_bf16;
 };
 
@@ -284,7 +294,7 @@ __device__ __forceinline__ void norm_act_bwd_math(const NormActBwd& p, const Nor
 }
 
 // grid (chunks, n); per-sample partial sums A = sum dy, B = sum dy*xhat
-template <bool UPS, bool DZ16>
+template <bool UPS, bool DZ16, typename TX>
 __global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(const NormActBwd p) {
   const int ni = blockIdx.y, chunk = blockIdx.x;
   const int v = p.c >> 2;
@@ -293,7 +303,9 @@ __global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(const NormA
   const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
   const int hw = p.h * p.w;
   const int p0 = chunk * p.pix_per_chunk, p1 = min(hw, p0 + p.pix_per_chunk);
-  const int g = ni / (p.n / p.groups);
+  const int n_per_group = p.n / p.groups;
+  const int g = ni / n_per_group;
+  const TX* xp = static_cast<const TX*>(p.x);
   __shared__ float4 sh_a[256], sh_b[256];
   for (int cb = 0; cb < v; cb += cols_per_pass) {
     const int col = cb + cx;
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(const NormA
         for (int u = 0; u < U; ++u) {
           const int qx = px + u * lanes;
           if (qx < p1) {
-            a[u] = ld4(p.x + (static_cast<int64_t>(ni) * hw + qx) * p.c + col * 4);
+            a[u] = ld4(xp + (static_cast<int64_t>(ni) * hw + qx) * p.c + col * 4);
             dz[u] = norm_act_bwd_load_dz<UPS, DZ16>(p, ni, qx, col * 4);
           }
         }
@@ -396,9 +408,10 @@ norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int n, int c, int n_
   }
 }
 
-template <bool NORM, bool UPS, bool DZ16>
+template <bool NORM, bool UPS, bool DZ16, typename TX>
 __global__ void __launch_bounds__(256, 3) norm_act_bwd_apply_kernel(const NormActBwd p, int pix_per_chunk) {
   const int ni = blockIdx.y;
+  const TX* xp = static_cast<const TX*>(p.x);
   const int v = p.c >> 2;
   const int cols = min(v, 256);
   const int lanes = 256 / cols;
@@ -428,7 +441,7 @@ __global__ void __launch_bounds__(256, 3) norm_act_bwd_apply_kernel(const NormAc
       for (int u = 0; u < U; ++u) {
         const int qx = px + u * lanes;
         if (qx < p1) {
-          a[u] = ld4(p.x + (static_cast<int64_t>(ni) * hw + qx) * p.c + c4);
+          a[u] = ld4(xp + (static_cast<int64_t>(ni) * hw + qx) * p.c + c4);
           dz[u] = norm_act_bwd_load_dz<UPS, DZ16>(p, ni, qx, c4);
         }
       }
@@ -444,7 +457,8 @@ __global__ void __launch_bounds__(256, 3) norm_act_bwd_apply_kernel(const NormAc
           dx = make_float4(kc.r.x * (kc.ga.x * dy.x - t1.x - xh.x * t2.x), kc.r.y * (kc.ga.y * dy.y - t1.y - xh.y * t2.y),
                            kc.r.z * (kc.ga.z * dy.z - t1.z - xh.z * t2.z), kc.r.w * (kc.ga.w * dy.w - t1.w - xh.w * t2.w));
         if (p.add) {
-          const float4 q = ld4(p.add + pix * p.c + c4);
+          const float4 q = p.add_bf16 ? ld4(static_cast<const __nv_bfloat16*>(p.add) + pix * p.c + c4)
+                                      : ld4(static_cast<const float*>(p.add) + pix * p.c + c4);
           dx.x += q.x; dx.y += q.y; dx.z += q.z; dx.w += q.w;
         }
         if (p.dx_bf16) st4(reinterpret_cast<__nv_bfloat16*>(p.dx) + pix * p.c + c4, dx);
@@ -600,7 +614,8 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x,
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// partial[chunk][c] = sum over the chunk's rows of x[row][c]; finalize: out[c] = beta*out[c] + sum partial
+// out[c] = beta*out[c] + sum_rows x[row][c].  Every block sums a row chunk into partial[chunk][c]; the last block to
+// finish adds the chunk partials in chunk order (deterministic) -- one launch instead of partial + finalize.
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_per_chunk, float* __restrict__ partial) {
@@ -615,11 +630,17 @@ colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_p
   for (int cb = 0; cb < v; cb += cols_per_pass) {
     const int col = cb + cx;
     float4 s = make_float4(0, 0, 0, 0);
-    if (col < v && ry < lanes)
-      for (int64_t r = r0 + ry; r < r1; r += lanes) {
-        const float4 a = ld4(x + r * c + col * 4);
-        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    if (col < v && ry < lanes) {
+      constexpr int U = 4;
+      for (int64_t r = r0 + ry; r < r1; r += lanes * U) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          a[u] = (r + u * lanes < r1) ? ld4(x + (r + u * lanes) * c + col * 4) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w; }
       }
+    }
     sh[threadIdx.x] = s;
     __syncthreads();
     if (ry == 0 && col < v) {
@@ -643,6 +664,36 @@ colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, flo
   if (lane == 0) out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
 }
 
+
+// Narrow tensors (c <= 8, e.g. the RGB bias or a scalar head): a thread walks rows and keeps all c sums in registers.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+colsum_narrow_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_per_chunk, float* __restrict__ partial) {
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_chunk;
+  const int64_t r1 = min(rows, r0 + rows_per_chunk);
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < c) s[j] += static_cast<float>(x[r * c + j]);
+  }
+  __shared__ float shn[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float t = warp_sum_f(s[j]);
+    if (lane == 0) shn[warp][j] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < c) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += shn[w][threadIdx.x];
+    partial[static_cast<int64_t>(blockIdx.x) * c + threadIdx.x] = t;
+  }
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 colsum_wide_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, float* __restrict__ out) {
@@ -653,7 +704,7 @@ colsum_wide_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, f
   out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
 }
 
-// channel counts that are not a multiple of 4 (RGB bias, scalar heads): one block per channel
+// any other channel count: one block per channel
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 colsum_scalar_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, float* __restrict__ out) {
@@ -727,11 +778,11 @@ bcast_channels_bwd_kernel(const float* __restrict__ e, int hw, int c2, int coff,
 }
 
 // dx[n,hw,0:c1] = d_raw[..., 0:c1] + dact(x) * d_act[..., 0:c1]   (wide bf16 gradients -> fp32 dx)
-template <typename TG>
+template <typename TG, typename TOut>
 __global__ void __launch_bounds__(256)
 concat_bwd_x_kernel(const float* __restrict__ x, int64_t pixels, int c1, int cstride, int act,
                     const TG* __restrict__ d_raw, const TG* __restrict__ d_act,
-                    float* __restrict__ dx) {
+                    TOut* __restrict__ dx) {
   const int v = c1 >> 2;
   const int64_t total = pixels * v;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -782,9 +833,10 @@ act_mean_hw_fwd_kernel(const float* __restrict__ x, int hw, int c, int act, floa
   }
 }
 // dx[n,hw,c] = dact(x) * dout[n,c] / hw
+template <typename TOut>
 __global__ void __launch_bounds__(256)
 act_mean_hw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, int n, int hw, int c, int act,
-                       float* __restrict__ dx) {
+                       TOut* __restrict__ dx) {
   const int v = c >> 2;
   const int64_t total = static_cast<int64_t>(n) * hw * v;
   const float inv = 1.0f / hw;
@@ -923,8 +975,8 @@ static int stats_chunks(int rows_per_group, int groups) {
   return chunks;
 }
 
-extern "C" int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, float eps, float* mean, float* rstd,
-                             void* workspace, void* stream) {
+extern "C" int ganb_bn_stats(const void* x, int x_dtype, int n, int hw, int c, int groups, float eps, float* mean,
+                             float* rstd, void* workspace, void* stream) {
   if (!x || !mean || !rstd || !workspace) return fail(GANB_E_BADARG, "bn_stats: null buffer");
   if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "bn_stats: c=%d must be a multiple of 4", c);
   if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "bn_stats: n=%d not divisible by groups=%d", n, groups);
@@ -932,8 +984,13 @@ extern "C" int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, f
   const int chunks = stats_chunks(rows_per_group, groups);
   const int rows_per_chunk = ceil_div(rows_per_group, chunks);
   const int used = ceil_div(rows_per_group, rows_per_chunk);
-  bn_stats_partial_kernel<<<dim3(used, groups), 256, 0, STREAM>>>(x, rows_per_group, c, used, rows_per_chunk,
-                                                                  static_cast<float*>(workspace));
+  const dim3 grid(used, groups);
+  if (x_dtype == GANB_BF16)
+    bn_stats_partial_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows_per_group, c,
+                                                                      used, rows_per_chunk, static_cast<float*>(workspace));
+  else
+    bn_stats_partial_kernel<float><<<grid, 256, 0, STREAM>>>(static_cast<const float*>(x), rows_per_group, c, used,
+                                                              rows_per_chunk, static_cast<float*>(workspace));
   GANB_CHECK_LAUNCH("bn_stats_partial_kernel");
   bn_stats_finalize_kernel<<<ceil_div(groups * c, 8), 256, 0, STREAM>>>(
       static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
@@ -949,7 +1006,7 @@ static int bwd_chunks(int n, int hw) {
   return chunks;
 }
 
-extern "C" int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, const float* mean, const float* rstd,
+extern "C" int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w, int c, const float* mean, const float* rstd,
                                  int groups, const float* gamma, const float* beta, const int* labels, int act,
                                  int upsample, void* out, int out_dtype, int out_cstride, void* out_raw_bf16,
                                  int raw_cstride, void* stream) {
@@ -957,7 +1014,7 @@ extern "C" int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, con
   if (c % 4 != 0 || out_cstride % 4 != 0) return fail(GANB_E_UNSUPPORTED, "norm_act_fwd: c=%d, stride=%d must be multiples of 4", c, out_cstride);
   if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "norm_act_fwd: bad groups");
   NormActFwd p;
-  p.x = x; p.n = n; p.h = h; p.w = w; p.c = c;
+  p.x = x; p.x_bf16 = (x_dtype == GANB_BF16); p.n = n; p.h = h; p.w = w; p.c = c;
   p.mean = mean; p.rstd = rstd; p.groups = groups;
   p.gamma = gamma; p.beta = beta; p.labels = labels;
   p.act = act; p.upsample = upsample;
@@ -965,7 +1022,8 @@ extern "C" int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, con
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
   const int chunks = bwd_chunks(n, h * w);
   const int ppc = ceil_div(h * w, chunks);
-  norm_act_fwd_kernel<<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
+  if (p.x_bf16) norm_act_fwd_kernel<__nv_bfloat16><<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
+  else norm_act_fwd_kernel<float><<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
   GANB_CHECK_LAUNCH("norm_act_fwd_kernel");
   return 0;
 }
@@ -975,21 +1033,46 @@ extern "C" int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups)
   return (static_cast<int64_t>(n) * chunks * 2 * c + 2LL * n * c + 2LL * groups * c) * 4;
 }
 
-extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w,
-                                 int c, const float* mean, const float* rstd, int groups, const float* gamma,
+namespace ganb {
+template <typename TX>
+static void launch_bwd_reduce(const NormActBwd& p, dim3 grid, cudaStream_t s) {
+  if (p.upsample && p.dz_bf16) norm_act_bwd_reduce_kernel<true, true, TX><<<grid, 256, 0, s>>>(p);
+  else if (p.upsample) norm_act_bwd_reduce_kernel<true, false, TX><<<grid, 256, 0, s>>>(p);
+  else if (p.dz_bf16) norm_act_bwd_reduce_kernel<false, true, TX><<<grid, 256, 0, s>>>(p);
+  else norm_act_bwd_reduce_kernel<false, false, TX><<<grid, 256, 0, s>>>(p);
+}
+template <typename TX>
+static void launch_bwd_apply(const NormActBwd& p, bool norm, dim3 grid, int ppc, cudaStream_t s) {
+  const int idx = (norm ? 4 : 0) | (p.upsample ? 2 : 0) | (p.dz_bf16 ? 1 : 0);
+  switch (idx) {
+    case 0: norm_act_bwd_apply_kernel<false, false, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    case 1: norm_act_bwd_apply_kernel<false, false, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    case 2: norm_act_bwd_apply_kernel<false, true, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    case 3: norm_act_bwd_apply_kernel<false, true, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    case 4: norm_act_bwd_apply_kernel<true, false, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    case 5: norm_act_bwd_apply_kernel<true, false, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    case 6: norm_act_bwd_apply_kernel<true, true, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    default: norm_act_bwd_apply_kernel<true, true, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+  }
+}
+}  // namespace ganb
+
+extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int dz_dtype, int dz_cstride, int n, int h,
+                                 int w, int c, const float* mean, const float* rstd, int groups, const float* gamma,
                                  const float* beta, const int* labels, int n_rows, int act, int upsample,
-                                 float* dgamma, float* dbeta, const float* add, void* dx, int dx_dtype,
+                                 float* dgamma, float* dbeta, const void* add, int add_dtype, void* dx, int dx_dtype,
                                  void* workspace, void* stream) {
   if (!x || !dz || !dx) return fail(GANB_E_BADARG, "norm_act_bwd: null buffer");
   if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "norm_act_bwd: c=%d must be a multiple of 4", c);
   if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "norm_act_bwd: bad groups");
   NormActBwd p;
-  p.x = x; p.dz = dz; p.dz_bf16 = (dz_dtype == GANB_BF16); p.dz_cstride = dz_cstride > 0 ? dz_cstride : c;
+  p.x = x; p.x_bf16 = (x_dtype == GANB_BF16);
+  p.dz = dz; p.dz_bf16 = (dz_dtype == GANB_BF16); p.dz_cstride = dz_cstride > 0 ? dz_cstride : c;
   p.n = n; p.h = h; p.w = w; p.c = c;
   p.mean = mean; p.rstd = rstd; p.groups = groups;
   p.gamma = gamma; p.beta = beta; p.labels = labels;
   p.act = act; p.upsample = upsample;
-  p.add = add; p.dx = dx; p.dx_bf16 = (dx_dtype == GANB_BF16);
+  p.add = add; p.add_bf16 = (add_dtype == GANB_BF16); p.dx = dx; p.dx_bf16 = (dx_dtype == GANB_BF16);
   p.part = nullptr; p.s1 = nullptr; p.s2 = nullptr; p.chunks = 0; p.pix_per_chunk = 0; p.inv_count = 0.f;
   if (mean) {
     if (!workspace) return fail(GANB_E_BADARG, "norm_act_bwd: workspace required with normalisation");
@@ -1001,13 +1084,9 @@ extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, i
     float* sums = p.part + static_cast<int64_t>(n) * chunks * 2 * c;
     float* s1 = sums + 2LL * n * c;
     float* s2 = s1 + static_cast<int64_t>(groups) * c;
-    {
-      const dim3 grid(p.chunks, n);
-      if (upsample && p.dz_bf16) norm_act_bwd_reduce_kernel<true, true><<<grid, 256, 0, STREAM>>>(p);
-      else if (upsample) norm_act_bwd_reduce_kernel<true, false><<<grid, 256, 0, STREAM>>>(p);
-      else if (p.dz_bf16) norm_act_bwd_reduce_kernel<false, true><<<grid, 256, 0, STREAM>>>(p);
-      else norm_act_bwd_reduce_kernel<false, false><<<grid, 256, 0, STREAM>>>(p);
-    }
+    const dim3 grid(p.chunks, n);
+    if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
+    else launch_bwd_reduce<float>(p, grid, STREAM);
     GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
     norm_act_bwd_finalize_kernel<<<dim3(ceil_div(c, 8), groups), 256, 0, STREAM>>>(p.part, n, c, p.chunks, groups, gamma,
                                                                                   labels, sums, s1, s2);
@@ -1024,17 +1103,8 @@ extern "C" int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, i
     const int chunks2 = bwd_chunks(n, h * w);
     const int ppc = ceil_div(h * w, chunks2);
     const dim3 grid(ceil_div(h * w, ppc), n);
-    const int idx = (mean ? 4 : 0) | (upsample ? 2 : 0) | (p.dz_bf16 ? 1 : 0);
-    switch (idx) {
-      case 0: norm_act_bwd_apply_kernel<false, false, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-      case 1: norm_act_bwd_apply_kernel<false, false, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-      case 2: norm_act_bwd_apply_kernel<false, true, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-      case 3: norm_act_bwd_apply_kernel<false, true, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-      case 4: norm_act_bwd_apply_kernel<true, false, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-      case 5: norm_act_bwd_apply_kernel<true, false, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-      case 6: norm_act_bwd_apply_kernel<true, true, false><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-      default: norm_act_bwd_apply_kernel<true, true, true><<<grid, 256, 0, STREAM>>>(p, ppc); break;
-    }
+    if (p.x_bf16) launch_bwd_apply<__nv_bfloat16>(p, mean != nullptr, grid, ppc, STREAM);
+    else launch_bwd_apply<float>(p, mean != nullptr, grid, ppc, STREAM);
   }
   GANB_CHECK_LAUNCH("norm_act_bwd_apply_kernel");
   return 0;
@@ -1151,41 +1221,47 @@ extern "C" int64_t ganb_colsum_workspace(int64_t rows, int c) {
   return static_cast<int64_t>(1024) * c * 4;
 }
 
-// out[c] = beta*out[c] + sum_rows x[row][c]    (bias gradient: tf.nn.bias_add backward)
-extern "C" int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, float beta, float* out, void* workspace,
-                           void* stream) {
-  if (!x || !out || !workspace) return fail(GANB_E_BADARG, "colsum: null buffer");
+namespace ganb {
+template <typename TIn>
+static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float* out, void* workspace, cudaStream_t s) {
+  const TIn* x = static_cast<const TIn*>(xv);
   if (rows <= 512 && c >= 1024) {  // dense-layer bias gradients: coalesced over columns, short serial loop over rows
-    if (x_dtype == GANB_BF16)
-      colsum_wide_kernel<__nv_bfloat16><<<ceil_div(c, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows, c, beta, out);
-    else
-      colsum_wide_kernel<float><<<ceil_div(c, 256), 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, beta, out);
+    colsum_wide_kernel<TIn><<<ceil_div(c, 256), 256, 0, s>>>(x, rows, c, beta, out);
     GANB_CHECK_LAUNCH("colsum_wide_kernel");
     return 0;
   }
-  if (c % 4 != 0) {
-    if (x_dtype == GANB_BF16)
-      colsum_scalar_kernel<__nv_bfloat16><<<c, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows, c, beta, out);
-    else
-      colsum_scalar_kernel<float><<<c, 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, beta, out);
+  if (c % 4 != 0 && c > 8) {
+    colsum_scalar_kernel<TIn><<<c, 256, 0, s>>>(x, rows, c, beta, out);
     GANB_CHECK_LAUNCH("colsum_scalar_kernel");
     return 0;
   }
-  int chunks = 4 * sm_count();
-  const int64_t max_chunks = ceil_div64(rows, 32);
+  const bool narrow = (c % 4 != 0);
+  int chunks = narrow ? sm_count() : 4 * sm_count();
+  const int64_t max_chunks = ceil_div64(rows, narrow ? 256 : 32);
   if (chunks > max_chunks) chunks = static_cast<int>(max_chunks);
   if (chunks > 1024) chunks = 1024;
   if (chunks < 1) chunks = 1;
   const int rows_per_chunk = static_cast<int>(ceil_div64(rows, chunks));
   const int used = static_cast<int>(ceil_div64(rows, rows_per_chunk));
-  if (x_dtype == GANB_BF16)
-    colsum_partial_kernel<__nv_bfloat16><<<used, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows, c, rows_per_chunk, static_cast<float*>(workspace));
-  else
-    colsum_partial_kernel<float><<<used, 256, 0, STREAM>>>(static_cast<const float*>(x), rows, c, rows_per_chunk, static_cast<float*>(workspace));
-  GANB_CHECK_LAUNCH("colsum_partial_kernel");
-  colsum_finalize_kernel<<<ceil_div(c, 8), 256, 0, STREAM>>>(static_cast<float*>(workspace), c, used, beta, out);
+  if (narrow) {
+    colsum_narrow_kernel<TIn><<<used, 256, 0, s>>>(x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
+    GANB_CHECK_LAUNCH("colsum_narrow_kernel");
+  } else {
+    colsum_partial_kernel<TIn><<<used, 256, 0, s>>>(x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
+    GANB_CHECK_LAUNCH("colsum_partial_kernel");
+  }
+  colsum_finalize_kernel<<<ceil_div(c, 8), 256, 0, s>>>(static_cast<float*>(workspace), c, used, beta, out);
   GANB_CHECK_LAUNCH("colsum_finalize_kernel");
   return 0;
+}
+}  // namespace ganb
+
+// out[c] = beta*out[c] + sum_rows x[row][c]    (bias gradient: tf.nn.bias_add backward)
+extern "C" int ganb_colsum(const void* x, int x_dtype, int64_t rows, int c, float beta, float* out, void* workspace,
+                           void* stream) {
+  if (!x || !out || !workspace) return fail(GANB_E_BADARG, "colsum: null buffer");
+  if (x_dtype == GANB_BF16) return launch_colsum<__nv_bfloat16>(x, rows, c, beta, out, workspace, STREAM);
+  return launch_colsum<float>(x, rows, c, beta, out, workspace, STREAM);
 }
 
 extern "C" int ganb_bcast_channels_fwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
@@ -1216,16 +1292,24 @@ extern "C" int ganb_bcast_channels_bwd(const float* e, int n, int hw, int c2, in
   return 0;
 }
 
+namespace ganb {
+template <typename TG, typename TOut>
+static void launch_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw,
+                                const void* d_act, void* dx, cudaStream_t s) {
+  concat_bwd_x_kernel<TG, TOut><<<grid_for(pixels * (c1 / 4), 256), 256, 0, s>>>(
+      x, pixels, c1, cstride, act, static_cast<const TG*>(d_raw), static_cast<const TG*>(d_act), static_cast<TOut*>(dx));
+}
+}  // namespace ganb
+
 extern "C" int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw,
-                                 const void* d_act, int d_dtype, float* dx, void* stream) {
+                                 const void* d_act, int d_dtype, void* dx, int dx_dtype, void* stream) {
   if (!x || !dx) return fail(GANB_E_BADARG, "concat_bwd_x: null buffer");
   if (c1 % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "concat_bwd_x: channel counts must be multiples of 4");
-  if (d_dtype == GANB_BF16)
-    concat_bwd_x_kernel<__nv_bfloat16><<<grid_for(pixels * (c1 / 4), 256), 256, 0, STREAM>>>(
-        x, pixels, c1, cstride, act, static_cast<const __nv_bfloat16*>(d_raw), static_cast<const __nv_bfloat16*>(d_act), dx);
-  else
-    concat_bwd_x_kernel<float><<<grid_for(pixels * (c1 / 4), 256), 256, 0, STREAM>>>(
-        x, pixels, c1, cstride, act, static_cast<const float*>(d_raw), static_cast<const float*>(d_act), dx);
+  const bool g16 = d_dtype == GANB_BF16, o16 = dx_dtype == GANB_BF16;
+  if (g16 && o16) launch_concat_bwd_x<__nv_bfloat16, __nv_bfloat16>(x, pixels, c1, cstride, act, d_raw, d_act, dx, STREAM);
+  else if (g16) launch_concat_bwd_x<__nv_bfloat16, float>(x, pixels, c1, cstride, act, d_raw, d_act, dx, STREAM);
+  else if (o16) launch_concat_bwd_x<float, __nv_bfloat16>(x, pixels, c1, cstride, act, d_raw, d_act, dx, STREAM);
+  else launch_concat_bwd_x<float, float>(x, pixels, c1, cstride, act, d_raw, d_act, dx, STREAM);
   GANB_CHECK_LAUNCH("concat_bwd_x_kernel");
   return 0;
 }
@@ -1238,11 +1322,15 @@ extern "C" int ganb_act_mean_hw_fwd(const float* x, int n, int hw, int c, int ac
   return 0;
 }
 
-extern "C" int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, int hw, int c, int act, float* dx,
-                                    void* stream) {
+extern "C" int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, int hw, int c, int act, void* dx,
+                                    int dx_dtype, void* stream) {
   if (!x || !dout || !dx) return fail(GANB_E_BADARG, "act_mean_hw_bwd: null buffer");
   if (c % 4) return fail(GANB_E_UNSUPPORTED, "act_mean_hw_bwd: c=%d must be a multiple of 4", c);
-  act_mean_hw_bwd_kernel<<<grid_for(static_cast<int64_t>(n) * hw * (c / 4), 256), 256, 0, STREAM>>>(x, dout, n, hw, c, act, dx);
+  const int grid = grid_for(static_cast<int64_t>(n) * hw * (c / 4), 256);
+  if (dx_dtype == GANB_BF16)
+    act_mean_hw_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(x, dout, n, hw, c, act, static_cast<__nv_bfloat16*>(dx));
+  else
+    act_mean_hw_bwd_kernel<float><<<grid, 256, 0, STREAM>>>(x, dout, n, hw, c, act, static_cast<float*>(dx));
   GANB_CHECK_LAUNCH("act_mean_hw_bwd_kernel");
   return 0;
 }

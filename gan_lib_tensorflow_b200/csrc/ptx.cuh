@@ -155,6 +155,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// The same descriptor split into its constant part and the start-address field, so that the single-thread MMA issue
+// loop only does one shift + or per operand (the loop is issue-latency bound: profiles/r01 source-level samples).
+__device__ __forceinline__ uint64_t umma_desc_base_sw128(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_smem_desc_sw128(0, lbo_bytes, sbo_bytes);
+}
+__device__ __forceinline__ uint64_t umma_desc_at(uint64_t base, uint32_t smem_addr) {
+  return base | static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+}
+
 // Instruction descriptor for kind::f16 with BF16 inputs and FP32 accumulation.
 //   [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format
 //   bit 15 A major (0 = K, 1 = MN)  bit 16 B major  [17,23) N >> 3  [24,29) M >> 4

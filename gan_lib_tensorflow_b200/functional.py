@@ -104,10 +104,13 @@ def _pads(padding, h, w, kh, kw, stride):
 
 
 def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: int = 1, padding: str = "SAME",
-           sn=None, residual: Var | None = None, out_grad_dtype=None, in_scale: float | None = None) -> Var:
+           sn=None, residual: Var | None = None, out_grad_dtype=None, in_scale: float | None = None,
+           residual_up2: bool = False, out_dtype=F32) -> Var:
     """NHWC x HWIO cross-correlation (tf.nn.conv2d, common/ops/conv2d.py:181-187) + bias (+ residual), fp32 out.
 
     `sn` is a framework.SNEntry whose 1/sigma multiplies the accumulator (W/sigma is never materialised).
+    `residual_up2`: the residual is given at half resolution and added through a nearest-2x upsample inside the
+    GEMM epilogue (shortcut of an 'up' block); its gradient is the 2x2 block sum of the output gradient.
     Every shape runs on the tensor cores: layers with <= 8 channels on one side go through a bf16 im2col of the
     small tensor (kh*kw*c <= 32 columns) and become 1x1 GEMMs; larger small-channel filters fall back to the
     CUDA-core kernels of smallconv.cu."""
@@ -135,7 +138,7 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
         if route_in:
             xcol = K.im2col_small(xin.data, n, h, w, cin, ho, wo, kh, kw, pt, pl, +1, SMALL_K)
             y = K.conv_igemm(xcol, pack.ws, n, ho, wo, SMALL_K, ho, wo, cout, 1, 1, 0, 0, False, alpha, bias, res,
-                             None, F32)
+                             None, out_dtype, residual_up2=residual_up2)
         else:
             if res is not None:
                 raise NotImplementedError("residual on the CUDA-core small-channel path")
@@ -146,7 +149,7 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
             raise NotImplementedError(f"cin={cin}: tensor-core path needs cin % 8 == 0")
         xin = x if x.data.dtype == BF16 else cast(x, BF16)
         y = K.conv_igemm(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res,
-                         None, F32)
+                         None, out_dtype, residual_up2=residual_up2)
     out = Var(y, grad_dtype=out_grad_dtype)
     need_w = W.needs_grad and _tape() is not None
     need_b = b is not None and b.needs_grad and _tape() is not None
@@ -159,7 +162,10 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
             if gy is None:
                 return
             if residual is not None and residual.requires_grad:
-                residual.accum(gy if gy.dtype == residual.gdtype else K.cast(gy, residual.gdtype))
+                if residual_up2:
+                    residual.accum(K.sum2x2(gy, 1.0, residual.gdtype))
+                else:
+                    residual.accum(gy if gy.dtype == residual.gdtype else K.cast(gy, residual.gdtype))
             if need_b:
                 K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
             need_x = xin.requires_grad
@@ -269,7 +275,6 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
 
     stats: None (identity), 'batch' (moments over n,h,w per statistic group; cond. BN when labels given) or
     'instance' (per-sample moments).  Returns (out, raw_or_None)."""
-    assert x.data.dtype == F32, "normalisation input must be fp32"
     store = get_store()
     n, h, w, c = x.shape
     mean = rstd = None
@@ -289,7 +294,7 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
     raw = torch.empty((n, h, w, c), dtype=BF16, device=x.data.device) if want_raw else None
     y = K.norm_act_fwd(x.data, n, h, w, c, mean, rstd, g, gam, bet, labels, act, upsample, out_dtype, out_raw=raw)
     out = Var(y, grad_dtype=out_grad_dtype)
-    raw_var = Var(raw, grad_dtype=F32) if want_raw else None
+    raw_var = Var(raw) if want_raw else None  # bf16 value, bf16 gradient
     need_p = gamma is not None and gamma.needs_grad and _tape() is not None
     if _rg(x) or need_p:
         out.requires_grad = True
@@ -307,6 +312,10 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
             dbet = beta.grad if need_p else None
             if not x.requires_grad and not need_p:
                 return
+            # a second gradient path into x (shortcut operand, or an identity-shortcut residual already accumulated
+            # in x.grad) is added inside the same kernel instead of a separate read-modify-write pass
+            if extra is None and x.grad is not None and x.requires_grad and x.grad.shape == x.data.shape:
+                extra, x.grad = x.grad, None
             dx = K.norm_act_bwd(x.data, gz, 0, n, h, w, c, mean, rstd, g, gam, bet, labels, act, upsample, dgam, dbet,
                                 extra, x.gdtype)
             if x.requires_grad:
@@ -327,11 +336,11 @@ def activation(x: Var, act, out_dtype=None) -> Var:
     return reshape(y, shape)
 
 
-def meanpool2(x: Var, addend: Var | None = None, in_grad_dtype=None) -> Var:
+def meanpool2(x: Var, addend: Var | None = None, in_grad_dtype=None, out_grad_dtype=None) -> Var:
     """2x2 mean pool (+ addend), fp32 out (common/resnet_block.py:62-63)."""
     n, h, w, c = x.shape
     y = K.meanpool2(x.data, addend.data if addend is not None else None, F32)
-    out = Var(y)
+    out = Var(y, grad_dtype=out_grad_dtype)
     if _rg(x, addend):
         out.requires_grad = True
 
@@ -370,7 +379,7 @@ def act_mean_hw(x: Var, act) -> Var:
 
         def bwd():
             if out.grad is not None:
-                x.accum(K.act_mean_hw_bwd(x.data, out.grad, act))
+                x.accum(K.act_mean_hw_bwd(x.data, out.grad, act, x.gdtype))
         _tape().record(bwd)
     return out
 
@@ -415,7 +424,7 @@ def concat_label_map(x: Var, e: Var, act="relu"):
             if e.requires_grad:
                 e.accum(K.bcast_channels_bwd(e.data, n, h * w, c2, c1, ct, act, d_raw, d_act))
             if x.requires_grad:
-                x.accum(K.concat_bwd_x(x.data, n * h * w, c1, ct, act, d_raw, d_act))
+                x.accum(K.concat_bwd_x(x.data, n * h * w, c1, ct, act, d_raw, d_act, x.gdtype))
         _tape().record(bwd)
     return raw_v, act_v
 

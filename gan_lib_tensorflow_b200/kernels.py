@@ -93,10 +93,11 @@ def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0) -> N
 
 
 # ------------------------------------------------------------------------------------------------ conv (TC)
-def conv_igemm(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, alpha, bias, residual, act, out_dtype):
+def conv_igemm(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, alpha, bias, residual, act, out_dtype,
+               residual_up2=False):
     y = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
     check(L().ganb_conv2d_igemm(ptr(x), ptr(wp), ptr(y), n, h, w, cin, ho, wo, cout, kh, kw, 1, pad_t, pad_l,
-                                int(flip), ptr(alpha), ptr(bias), ptr(residual), act_code(act),
+                                int(flip), ptr(alpha), ptr(bias), ptr(residual), int(bool(residual_up2)), act_code(act),
                                 BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_conv2d_igemm")
     return y
 
@@ -152,7 +153,7 @@ def bn_stats(x, n, hw, c, groups, eps):
     mean = torch.empty((groups, c), dtype=torch.float32, device=x.device)
     rstd = torch.empty((groups, c), dtype=torch.float32, device=x.device)
     ws = _ws(L().ganb_bn_stats_workspace(n, hw, c, groups), x.device)
-    check(L().ganb_bn_stats(ptr(x), n, hw, c, groups, c_float(eps), ptr(mean), ptr(rstd), ptr(ws), _stream()),
+    check(L().ganb_bn_stats(ptr(x), dt(x), n, hw, c, groups, c_float(eps), ptr(mean), ptr(rstd), ptr(ws), _stream()),
           "ganb_bn_stats")
     return mean, rstd
 
@@ -162,7 +163,7 @@ def norm_act_fwd(x, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, up
     if out is None:
         s = 2 if upsample else 1
         out = torch.empty((n, s * h, s * w, c), dtype=out_dtype, device=x.device)
-    check(L().ganb_norm_act_fwd(ptr(x), n, h, w, c, ptr(mean), ptr(rstd), groups, ptr(gamma), ptr(beta), ptr(labels),
+    check(L().ganb_norm_act_fwd(ptr(x), dt(x), n, h, w, c, ptr(mean), ptr(rstd), groups, ptr(gamma), ptr(beta), ptr(labels),
                                 act_code(act), int(bool(upsample)), ptr(out), dt(out), out_cstride, ptr(out_raw),
                                 raw_cstride, _stream()), "ganb_norm_act_fwd")
     return out
@@ -175,9 +176,10 @@ def norm_act_bwd(x, dz, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta,
     if mean is not None:
         ws = _ws(L().ganb_norm_act_bwd_workspace(n, h * w, c, groups), x.device)
     n_rows = int(gamma.shape[0]) if (gamma is not None and gamma.dim() == 2) else 1
-    check(L().ganb_norm_act_bwd(ptr(x), ptr(dz), dt(dz), dz_cstride, n, h, w, c, ptr(mean), ptr(rstd), groups,
+    check(L().ganb_norm_act_bwd(ptr(x), dt(x), ptr(dz), dt(dz), dz_cstride, n, h, w, c, ptr(mean), ptr(rstd), groups,
                                 ptr(gamma), ptr(beta), ptr(labels), n_rows, act_code(act), int(bool(upsample)), ptr(dgamma),
-                                ptr(dbeta), ptr(add), ptr(dx), dt(dx), ptr(ws), _stream()), "ganb_norm_act_bwd")
+                                ptr(dbeta), ptr(add), dt(add) if add is not None else F32, ptr(dx), dt(dx), ptr(ws),
+                                _stream()), "ganb_norm_act_bwd")
     return dx
 
 
@@ -222,11 +224,11 @@ def bcast_channels_bwd(e, n, hw, c2, coff, cstride, act, d_raw, d_act):
     return de
 
 
-def concat_bwd_x(x, pixels, c1, cstride, act, d_raw, d_act):
-    dx = torch.empty_like(x)
+def concat_bwd_x(x, pixels, c1, cstride, act, d_raw, d_act, dx_dtype=torch.float32):
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
     gd = dt(d_raw if d_raw is not None else d_act)
     check(L().ganb_concat_bwd_x(ptr(x), c_int64(pixels), c1, cstride, act_code(act), ptr(d_raw), ptr(d_act), gd,
-                                ptr(dx), _stream()), "ganb_concat_bwd_x")
+                                ptr(dx), dt(dx), _stream()), "ganb_concat_bwd_x")
     return dx
 
 
@@ -237,10 +239,10 @@ def act_mean_hw_fwd(x, act):
     return out
 
 
-def act_mean_hw_bwd(x, dout, act):
+def act_mean_hw_bwd(x, dout, act, dx_dtype=torch.float32):
     n, h, w, c = x.shape
-    dx = torch.empty_like(x)
-    check(L().ganb_act_mean_hw_bwd(ptr(x), ptr(dout), n, h * w, c, act_code(act), ptr(dx), _stream()),
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    check(L().ganb_act_mean_hw_bwd(ptr(x), ptr(dout), n, h * w, c, act_code(act), ptr(dx), dt(dx), _stream()),
           "ganb_act_mean_hw_bwd")
     return dx
 

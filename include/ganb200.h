@@ -63,11 +63,13 @@ int64_t ganb_launch_count(void);
  * the same kernel into the data gradient of a stride-1 convolution when x := dy, wp := HWIO filter viewed
  * as [kh*kw][cin_fwd][cout_fwd], pad := k-1-pad.
  * Requirements: cin % 8 == 0, x and wp 16-byte aligned. alpha (device scalar), bias, residual may be NULL.
+ * residual_up2 = 1: `residual` is [n, ho/2, wo/2, cout] and is read through a nearest-neighbour 2x upsample
+ * (the shortcut of an 'up' residual block, common/resnet_block.py:123-127, without materialising the upsampled map).
  * ---------------------------------------------------------------------------------------------- */
 int ganb_conv2d_igemm(const void* x_bf16, const void* wp_bf16, void* y, int n, int h, int w, int cin, int ho,
                       int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
-                      const float* alpha, const float* bias, const float* residual, int act, int out_dtype,
-                      void* stream);
+                      const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
+                      int out_dtype, void* stream);
 
 /* Filter gradient: partial[split][t][ci][co] = sum over the split's pixels of
  *     x[n, ho + r - pad_t, wo + s - pad_l, ci] * dy[n, ho, wo, co]          (stride 1)
@@ -167,20 +169,22 @@ int ganb_pack_weights(const ganb_pack_layer* layers_dev, int count, int total_ti
  * mean == NULL skips normalisation (pure activation + cast + resample).
  * ---------------------------------------------------------------------------------------------- */
 int64_t ganb_bn_stats_workspace(int n, int hw, int c, int groups);
-int ganb_bn_stats(const float* x, int n, int hw, int c, int groups, float eps, float* mean, float* rstd,
+/* x is fp32 or bf16 (x_dtype); statistics are accumulated in fp32 per chunk and fp64 across chunks. One launch:
+ * the last block of each group finalises mean / rstd. */
+int ganb_bn_stats(const void* x, int x_dtype, int n, int hw, int c, int groups, float eps, float* mean, float* rstd,
                   void* workspace, void* stream);
 /* out[n,(2)h,(2)w, out_cstride] (f32/bf16) = act(norm(x)), optionally replicated 2x2; out_raw (bf16, input
  * resolution, optional) = x.  cstride arguments of 0 mean "c". */
-int ganb_norm_act_fwd(const float* x, int n, int h, int w, int c, const float* mean, const float* rstd, int groups,
+int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w, int c, const float* mean, const float* rstd, int groups,
                       const float* gamma, const float* beta, const int* labels, int act, int upsample, void* out,
                       int out_dtype, int out_cstride, void* out_raw_bf16, int raw_cstride, void* stream);
 /* dx = d(loss)/dx given dz = d(loss)/d(out); dgamma/dbeta (tables of n_rows rows, may be NULL) are accumulated;
- * `add` (fp32, optional) is added to dx. */
+ * `add` (fp32 or bf16, optional) is added to dx. */
 int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups);
-int ganb_norm_act_bwd(const float* x, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w, int c,
+int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w, int c,
                       const float* mean, const float* rstd, int groups, const float* gamma, const float* beta,
                       const int* labels, int n_rows, int act, int upsample, float* dgamma, float* dbeta,
-                      const float* add, void* dx, int dx_dtype, void* workspace, void* stream);
+                      const void* add, int add_dtype, void* dx, int dx_dtype, void* workspace, void* stream);
 
 /* 2x2 mean-pool written as in common/resnet_block.py:62-63 (add_n of four strided slices / 4), + optional add */
 int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, void* out, int out_dtype, int n, int h, int w,
@@ -207,11 +211,12 @@ int ganb_bcast_channels_fwd(const float* e, int n, int hw, int c2, int coff, int
 int ganb_bcast_channels_bwd(const float* e, int n, int hw, int c2, int coff, int cstride, int act,
                             const void* d_raw, const void* d_act, int d_dtype, float* de, void* stream);
 int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw,
-                      const void* d_act, int d_dtype, float* dx, void* stream);
+                      const void* d_act, int d_dtype, void* dx, int dx_dtype, void* stream);
 
 /* out[n,c] = mean_hw act(x) : nonlinearity + tf.reduce_mean(axis=[1,2]) (gan_cifar_resnet.py:299-301) */
 int ganb_act_mean_hw_fwd(const float* x, int n, int hw, int c, int act, float* out, void* stream);
-int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, int hw, int c, int act, float* dx, void* stream);
+int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, int hw, int c, int act, void* dx, int dx_dtype,
+                         void* stream);
 
 /* mode 0: hinge D loss mean(relu(1-d[:n_real])) + mean(relu(1+d[n_real:])) (gan_cifar_resnet.py:376-378)
  * mode 1: G loss -mean(d) (:492).  loss_out[0] (+)= scale*loss; dlogits = scale * dloss/dd. */

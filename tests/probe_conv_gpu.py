@@ -57,7 +57,7 @@ def run_fprop(n, h, w, cin, cout, k, pad, flip=False, bias=True, res=False, alph
     wp = wt.permute(0, 1, 3, 2).contiguous().reshape(k * k, cout, cin)  # [tap][cout][cin]
     y = torch.full((n, ho, wo, cout), float("nan"), device=dev, dtype=torch.bfloat16 if bf16_out else torch.float32)
     rc = L.ganb_conv2d_igemm(cabi.ptr(x), cabi.ptr(wp), cabi.ptr(y), n, h, w, cin, ho, wo, cout, k, k, 1, pad, pad,
-                             0, cabi.ptr(a), cabi.ptr(b), cabi.ptr(r), act, 1 if bf16_out else 0, stream())
+                             0, cabi.ptr(a), cabi.ptr(b), cabi.ptr(r), 0, act, 1 if bf16_out else 0, stream())
     cabi.check(rc, "igemm")
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(3, 2, 0, 1), padding=pad).permute(0, 2, 3, 1)
@@ -81,7 +81,7 @@ def run_dgrad(n, h, w, cin, cout, k, pad):
     dx = torch.full((n, h, w, cin), float("nan"), device=dev)
     wp = wt.reshape(k * k, cin, cout)  # HWIO viewed as [tap][cin][cout]
     rc = L.ganb_conv2d_igemm(cabi.ptr(dy), cabi.ptr(wp), cabi.ptr(dx), n, ho, wo, cout, h, w, cin, k, k, 1,
-                             k - 1 - pad, k - 1 - pad, 1, None, None, None, 0, 0, stream())
+                             k - 1 - pad, k - 1 - pad, 1, None, None, None, 0, 0, 0, stream())
     cabi.check(rc, "dgrad")
     torch.cuda.synchronize()
     xx = torch.zeros(n, cin, h, w, device=dev, requires_grad=True)
@@ -132,7 +132,7 @@ def time_fprop(n, h, w, cin, cout, k, pad):
     wp = torch.randn(k * k, cout, cin, device=dev).to(torch.bfloat16)
     y = torch.empty(n, h, w, cout, device=dev)
     args = (cabi.ptr(x), cabi.ptr(wp), cabi.ptr(y), n, h, w, cin, h, w, cout, k, k, 1, pad, pad, 0, None, None, None,
-            0, 0)
+            0, 0, 0)
     for _ in range(3):
         L.ganb_conv2d_igemm(*args, stream())
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)

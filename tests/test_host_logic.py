@@ -231,7 +231,7 @@ def test_training_step_call_sequence_and_freezing(host):
     assert g_names.count("ganb_conv2d_wgrad") == 11               # 10 G convolutions + G.Input
     assert g_names.count("ganb_adam") == 1
     stats = [c for c in rec.calls if c[0] == "ganb_bn_stats"]
-    assert len(stats) == 7 and all(c[1][4] == 2 for c in stats)   # two statistic towers of 64 (reference towers)
+    assert len(stats) == 7 and all(c[1][5] == 2 for c in stats)   # two statistic towers of 64 (reference towers)
     assert tr.disc_opt.t == 1 and tr.gen_opt.t == 1
     assert P.lr_decay(0) == 1.0 and P.lr_decay(60000) == 0.5
 
