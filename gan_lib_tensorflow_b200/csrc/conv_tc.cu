@@ -11,6 +11,8 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ganb {
 
 constexpr int BM = 128;                      // UMMA M: output pixels (igemm) / input channels (wgrad)
@@ -462,6 +464,199 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the halo kernel (tcgen05 cta_group::2, UMMA M = 256): a cluster of two CTAs owns two adjacent
+// 16x8 pixel tiles and ONE filter tile of BN output channels.  Each CTA loads its own activation halo and the half of
+// the filter tile with rows [rank*BN/2, (rank+1)*BN/2); the leader (rank 0) issues the MMAs for both SMs.  Filter
+// bytes crossing L2->SMEM per SM are halved, which is what bounded the single-CTA kernel at ~60 % tensor-pipe
+// utilisation (10 TB/s of TMA traffic = the chip's L2 throughput, profiles/r01_halo_ncu_summary.txt).
+// Barriers: fullA / fullB live in the leader and count both CTAs' bytes; emptyA / emptyB / tfull are signalled in both
+// CTAs by a multicast commit; tempty lives in the leader and collects one arrival per epilogue warp of both CTAs.
+template <int BN, int SA, int SB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const IgemmParams p, int a_stage_bytes, int halo_w, int halo_bytes) {
+  constexpr int BH = BN / 2;                    // filter rows held by one CTA
+  constexpr int B_STAGE_BYTES = BH * BK * 2;
+  constexpr int ACC_STAGES = 2;
+  constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
+  constexpr int NC = 32;
+  constexpr uint32_t IDESC = umma_idesc_bf16(2 * BM, BN, 0, 0);
+  static_assert(BN == 128 || BN == 256, "pair kernel tiles 128 or 256 output channels");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + SA * a_stage_bytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + SB * B_STAGE_BYTES);
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* tfull = emptyB + SB;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pair_tiles = ((m_tiles + 1) >> 1) * p.tiles_co;   // work items of a cluster
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * (EPI_THREADS / 32)); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer's barriers are initialised and its TMEM is allocated before anything targets them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: this CTA's half of the filter tile =====================
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int tile = pair; tile < pair_tiles; tile += num_pairs) {
+      const int co0 = (tile % p.tiles_co) * BN + static_cast<int>(rank) * BH;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
+          mbar_wait(&emptyB[sb], pb ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&fullB[sb], 2 * B_STAGE_BYTES);
+            tma_load_3d_pair(sB + sb * B_STAGE_BYTES, &tmB, &fullB[sb], kc * BK, co0, tap_b);
+          }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == HALO_A_WARP) {
+    // ===================== TMA producer: this CTA's activation halo =====================
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = pair; tile < pair_tiles; tile += num_pairs) {
+      int t = 2 * (tile / p.tiles_co) + static_cast<int>(rank);   // pixel tile of this CTA
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;                // t = image; past the batch -> TMA zero fill
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&emptyA[sa], pa ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&fullA[sa], 2 * halo_bytes);
+          tma_load_4d_pair(sA + sa * a_stage_bytes, &tmA, &fullA[sa], kc * BK, tw * p.bw - p.pad_l,
+                           th * p.bh - p.pad_t, t);
+        }
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =====================
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;
+      const uint64_t adesc_base = umma_desc_base_sw128(16, sbo);
+      const uint64_t bdesc_base = umma_desc_base_sw128(16, 1024);
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      const int kw = p.kw, kh = p.taps / p.kw;
+      for (int tile = pair; tile < pair_tiles; tile += num_pairs) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&fullA[sa], pa);
+          uint32_t a_row = sA_addr + sa * a_stage_bytes;
+          for (int r = 0; r < kh; ++r, a_row += sbo) {
+            for (int s2 = 0; s2 < kw; ++s2) {
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t adesc = umma_desc_at(adesc_base, a_row + s2 * 128);
+                const uint64_t bdesc = umma_desc_at(bdesc_base, sB_addr + sb * B_STAGE_BYTES);
+                umma_bf16_pair(tmem_d, adesc, bdesc, IDESC, acc);
+#pragma unroll
+                for (int k = 1; k < BK / 16; ++k) umma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+                umma_commit_pair(&emptyB[sb]);
+              }
+              __syncwarp();
+              acc = 1u;
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
+          if (elect_one()) umma_commit_pair(&emptyA[sa]);
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+        if (elect_one()) umma_commit_pair(&tfull[as]);
+        __syncwarp();
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs): own 128 pixels x BN channels =====================
+    __shared__ __align__(16) float bias_s[ACC_STAGES][BN];
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);
+    const int iw = m % p.bw;
+    const int ih = (m / p.bw) % p.bh;
+    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    const uint32_t tempty_leader = map_to_cta(smem_u32(&tempty[0]), 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = pair; tile < pair_tiles; tile += num_pairs) {
+      const int tco = tile % p.tiles_co;
+      int t = 2 * (tile / p.tiles_co) + static_cast<int>(rank);
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int wo = tw * p.bw + iw, ho = th * p.bh + ih, n = t;
+      const bool valid = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
+      const int64_t pix = (static_cast<int64_t>(n) * p.Ho + ho) * p.Wo + wo;
+      const int64_t res_pix =
+          p.res_up2 ? (static_cast<int64_t>(n) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1) : pix;
+      if (p.bias) {
+        for (int c = et; c < BN; c += EPI_THREADS) {
+          const int co = tco * BN + c;
+          bias_s[as][c] = co < p.Cout ? __ldg(p.bias + co) : 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / NC; ++c) {
+        uint32_t r[NC];
+        tmem_ld_cols<NC>(trow + c * NC, r);
+        tmem_ld_wait();
+        if (valid) epilogue_row<NC>(p, r, alpha, pix, res_pix, tco * BN + c * NC, &bias_s[as][c * NC]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + as * 8);
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs are done with both TMEMs and with each other's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad: D[ci, co] = sum_pixels X[pixel + tap, ci] * dY[pixel, co]; channels are contiguous in NHWC so both
 // operands are MN-major.  One CTA = (tap, ci tile of 128, co tile of BN, pixel split).
 // ------------------------------------------------------------------------------------------------
@@ -698,6 +893,39 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
   return 0;
 }
 
+// GANB_PAIR=0 disables the cta_group::2 kernels (A/B comparison of the two code paths)
+static bool pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("GANB_PAIR");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode == 1;
+}
+
+template <int BN, int SA, int SB>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, int a_stage_bytes, int halo_w,
+                       int halo_bytes, cudaStream_t stream) {
+  const int smem = SA * a_stage_bytes + SB * (BN / 2) * BK * 2 + 1024 + 512;
+  if (smem > 232448) return fail(GANB_E_UNSUPPORTED, "conv pair kernel: %d bytes of shared memory needed", smem);
+  auto kern = conv_pair_kernel<BN, SA, SB>;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "pair smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  p.tiles_co = ceil_div(p.Cout, BN);
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int pair_tiles = ((m_tiles + 1) / 2) * p.tiles_co;
+  p.num_tiles = pair_tiles;
+  int clusters = sm_count() / 2;
+  if (clusters > pair_tiles) clusters = pair_tiles;
+  kern<<<2 * clusters, HALO_THREADS, smem, stream>>>(tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
+  GANB_CHECK_LAUNCH("conv_pair_kernel");
+  return 0;
+}
+
 }  // namespace ganb
 
 using namespace ganb;
@@ -741,6 +969,12 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   while (bn_tile > 64 && m_tiles * ceil_div(cout, bn_tile) < sm_count()) bn_tile >>= 1;
 
+  // CTA pairs (cta_group::2) halve the filter traffic per SM: used when there is at least one wave of pair tiles
+  const int pair_bn = cout > 128 ? 256 : 128;
+  const bool pair = halo && cout >= 128 && pair_mode() &&
+                    ((m_tiles + 1) / 2) * ceil_div(cout, pair_bn) >= sm_count() / 2;
+  if (pair) bn_tile = pair_bn;
+
   CUtensorMap tmA, tmB;
   const int halo_w = p.bw + kw - 1, halo_h = p.bh + kh - 1;
   {
@@ -753,13 +987,17 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   {
     const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)(kh * kw)};
     const uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)cin * cout * 2};
-    const uint32_t box[3] = {BK, (uint32_t)bn_tile, 1};
+    const uint32_t box[3] = {BK, (uint32_t)(pair ? bn_tile / 2 : bn_tile), 1};
     int rc = encode_tmap_bf16(&tmB, wp, 3, dims, strides, box, nullptr);
     if (rc) return rc;
   }
   if (halo) {
     const int halo_bytes = halo_w * halo_h * 128;
     const int a_stage = (halo_bytes + 1023) / 1024 * 1024;
+    if (pair) {
+      if (pair_bn == 256) return launch_pair<256, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      return launch_pair<128, 4, 12>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+    }
     switch (bn_tile) {
       case 16: return launch_halo<16, 7, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
       case 32: return launch_halo<32, 6, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);

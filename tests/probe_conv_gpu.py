@@ -166,6 +166,11 @@ def main():
     results.append(run_fprop(4, 32, 32, 256, 3, 3, 1, act=3))
     results.append(run_fprop(2, 32, 32, 128, 128, 3, 1, bf16_out=True))
     results.append(run_fprop(64, 32, 32, 256, 256, 3, 1))
+    # --- CTA-pair (cta_group::2) path: >= 74 pair tiles, Cout >= 128; odd tile count; residual / alpha / bf16 out
+    results.append(run_fprop(75, 16, 16, 128, 128, 3, 1, res=True, alpha=0.37))
+    results.append(run_fprop(151, 16, 8, 128, 256, 3, 1))
+    results.append(run_fprop(40, 32, 32, 64, 384, 3, 1, bf16_out=True))
+    results.append(run_dgrad(64, 32, 32, 256, 256, 3, 1))
     # --- dgrad through the same kernel
     results.append(run_dgrad(2, 8, 8, 64, 64, 3, 1))
     results.append(run_dgrad(4, 16, 16, 256, 128, 3, 1))
@@ -179,6 +184,9 @@ def main():
     print(f"checks: {sum(results)}/{len(results)} OK in {time.time() - t0:.1f}s")
     # --- timing
     time_fprop(64, 32, 32, 256, 256, 3, 1)
+    time_fprop(128, 32, 32, 256, 256, 3, 1)
+    time_fprop(128, 32, 32, 256, 3, 3, 1)
+    time_fprop(128, 16, 16, 256, 256, 3, 1)
     time_fprop(128, 32, 32, 128, 128, 3, 1)
     time_fprop(64, 16, 16, 256, 256, 3, 1)
     time_fprop(64, 8, 8, 1024, 256, 3, 1)
