@@ -47,7 +47,7 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
            conv_type='conv2d', channel_multiplier=0, padding='SAME',
            spectral_normed=False, update_collection=None, inputs_norm=False, he_init=True,
            mask_type=None, weightnorm=None, biases=True, gain=1., reuse=None,
-           residual=None, out_grad_dtype=None, residual_up2=False):
+           residual=None, out_grad_dtype=None, residual_up2=False, out_dtype=None):
     """
     Args mirror common/ops/conv2d.py:31-55 (`reuse` is the extra keyword of conv2d_.py:33, accepted and ignored).
     `residual` (fp32 Var added in the GEMM epilogue; `residual_up2`: given at half resolution) and `out_grad_dtype`
@@ -97,4 +97,4 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
                                          initializer=lambda s: np.zeros(s, dtype='float32'))
         return F.conv2d(inputs, filters, _biases, filter_size, filter_size, stride, padding, sn=sn_entry,
                         residual=residual, out_grad_dtype=out_grad_dtype, in_scale=in_scale,
-                        residual_up2=residual_up2)
+                        residual_up2=residual_up2, **({'out_dtype': out_dtype} if out_dtype is not None else {}))

@@ -26,7 +26,7 @@ def unset_weights_stdev():
 
 def Linear(inputs, input_dim, output_dim, name,
            spectral_normed=False, update_collection=None, reuse=False, inputs_norm=False,
-           biases=True, initialization=None, weightnorm=None, gain=1.):
+           biases=True, initialization=None, weightnorm=None, gain=1., out_dtype=None):
     """
     initialization: None, `lecun`, 'glorot', `he`, 'glorot_he', `orthogonal`, `("uniform", range)`
     """
@@ -76,7 +76,7 @@ def Linear(inputs, input_dim, output_dim, name,
             _biases = store.get_variable(name='b', shape=[output_dim, ],
                                          initializer=lambda s: np.zeros(s, dtype='float32'))
         if len(inputs.shape) == 2:
-            return F.linear(inputs, weight, _biases, sn=sn_entry)
+            return F.linear(inputs, weight, _biases, sn=sn_entry, **({'out_dtype': out_dtype} if out_dtype is not None else {}))
         lead = inputs.shape[:-1]
         flat = F.reshape(inputs, (-1, input_dim))
         result = F.linear(flat, weight, _biases, sn=sn_entry)

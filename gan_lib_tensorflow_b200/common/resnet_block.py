@@ -110,8 +110,11 @@ def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None,
 def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
                   spectral_normed=False, update_collection=None, inputs_norm=False,
                   resample=None, labels=None, biases=True, activation_fn='relu',
-                  normalize_kind=None, pre_activated=None):
+                  normalize_kind=None, pre_activated=None, out_dtype=None):
     """resample: None, 'down', or 'up' -- common/resnet_block.py:100-156.
+
+    out_dtype=torch.bfloat16 stores the block output (the input of the next block's normalisation) in bf16; the sum
+    conv2 + shortcut is formed in fp32 inside the GEMM epilogue and rounded once.
 
     normalize_kind overrides the name-based Normalize dispatch (used by the SNGAN scripts' own Normalize).
     pre_activated = (raw_bf16, act_bf16) lets a producer that already emitted both operands (the label-map
@@ -148,7 +151,9 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # ---- Conv1
     mid_dim = input_dim if resample == 'down' else output_dim
     # h1 is only consumed by N2 + nonlinearity, whose backward can emit the bf16 tensor-core operand directly
-    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16)
+    # and which is stored in bf16: it is only read by that kernel (rounding commutes with relu / leaky relu, so
+    # without a normalisation in between this is bit-identical to rounding after the activation)
+    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16, out_dtype=BF16)
 
     # ---- N2 + nonlinearity
     a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn)
@@ -162,7 +167,8 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # the block output feeds the next block's normalise/activation kernel and (through 1x1 / identity shortcuts)
     # convolutions only: its gradient is a tensor-core operand, so it is produced in bf16 directly
     return conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut,
-                residual_up2=(resample == 'up' and not identity_shortcut), out_grad_dtype=BF16)
+                residual_up2=(resample == 'up' and not identity_shortcut), out_grad_dtype=BF16,
+                **({'out_dtype': out_dtype} if out_dtype is not None else {}))
 
 
 def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
@@ -177,7 +183,7 @@ def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
                             inputs_norm=inputs_norm, he_init=False, biases=biases)
     output = _conv2d.Conv2D(inputs, cin, DIM_D, 3, 1, name_prefix + '.Conv1', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
-                            biases=biases, out_grad_dtype=BF16)
+                            biases=biases, out_grad_dtype=BF16, out_dtype=BF16)
     output, _ = F.norm_act(output, stats=None, act=activation_fn, out_dtype=BF16)
     output = _conv2d.Conv2D(output, DIM_D, DIM_D, 3, 1, name_prefix + '.Conv2', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,

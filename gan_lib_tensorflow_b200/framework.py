@@ -14,6 +14,7 @@ torch supplies device memory and streams; all arithmetic runs in libganb200 kern
 from __future__ import annotations
 
 import contextlib
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -97,22 +98,61 @@ class Variable(Var):
         writer(self.grad, 1.0)
 
 
+SIDE_STREAM = os.environ.get("GANB_SIDE_STREAM", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index or 0
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 class Tape:
-    """Records backward closures in execution order; backward() replays them in reverse."""
+    """Records backward closures in execution order; backward() replays them in reverse.
+
+    Work that is off the critical chain of the backward pass (filter gradients, bias gradients, their split
+    reductions) is issued on a second stream so that these launches overlap the data-gradient / normalisation chain:
+    a tensor-core kernel of one stream runs next to the bandwidth-bound kernels of the other.  Under CUDA-graph
+    capture the fork/join events become graph edges."""
 
     def __init__(self, store):
         self.nodes = []
         self.store = store
         self.pending_sn = OrderedDict()  # root -> list of SN entries whose G buffer has been written
+        self.keep = []       # temporaries read by side-stream launches: kept alive until the join
+        self._forked = False
 
     def record(self, fn) -> None:
         self.nodes.append(fn)
+
+    @contextlib.contextmanager
+    def offchain(self):
+        """Launches issued inside run on the side stream, ordered after everything queued on the current stream."""
+        if not SIDE_STREAM or K.host_logic_only():
+            yield
+            return
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device)
+        side.wait_stream(main)
+        self._forked = True
+        with torch.cuda.stream(side):
+            yield
+
+    def join(self) -> None:
+        if self._forked:
+            main = torch.cuda.current_stream()
+            main.wait_stream(_side_stream(main.device))
+            self._forked = False
+        self.keep.clear()
 
     def backward(self, loss: Var, grad: torch.Tensor | None = None) -> None:
         if grad is not None:
             loss.accum(grad)
         for fn in reversed(self.nodes):
             fn()
+        self.join()
         self.nodes.clear()
         for root, entries in self.pending_sn.items():
             self.store.sn_groups[root].backward(entries)

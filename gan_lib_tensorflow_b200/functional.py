@@ -166,19 +166,18 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                     residual.accum(K.sum2x2(gy, 1.0, residual.gdtype))
                 else:
                     residual.accum(gy if gy.dtype == residual.gdtype else K.cast(gy, residual.gdtype))
-            if need_b:
-                K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
             need_x = xin.requires_grad
-            if not (need_w or need_x):
+            if not (need_w or need_x or need_b):
                 return
             gy16 = None
-            if not small_out:
+            if not small_out and (need_w or need_x):
                 gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
             dycol = None
-            if route_out:
+            if route_out and (need_w or need_x):
                 gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
                 dycol = K.im2col_small(gy32, n, ho, wo, cout, h, w, kh, kw, pt, pl, -1, SMALL_K)
-            if need_w:
+
+            def _conv_wgrad():
                 if sn is not None:
                     dst, beta = sn.g, (1.0 if sn.g_written else 0.0)
                 else:
@@ -205,6 +204,15 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                     lst = tape.pending_sn.setdefault(W.root, [])
                     if sn not in lst:
                         lst.append(sn)
+
+            # ---- off the critical chain: bias and filter gradients (side stream; joined at the end of backward)
+            if need_b or need_w:
+                tape.keep.extend(t for t in (gy, gy16, dycol) if t is not None)
+                with tape.offchain():
+                    if need_b:
+                        K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
+                    if need_w:
+                        _conv_wgrad()
             if need_x:
                 gdt = xin.gdtype
                 if route_out:
@@ -222,15 +230,17 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     return out
 
 
-def linear(x: Var, W: Variable, b: Variable | None, sn=None) -> Var:
+def linear(x: Var, W: Variable, b: Variable | None, sn=None, out_dtype=F32) -> Var:
     """tf.matmul(x, W) + b (common/ops/linear.py:161-180) for 2-D x; large layers run as 1x1 convolutions on the
     tensor cores, tiny ones (in % 8 != 0 or out < 8) on CUDA cores."""
     m, kin = x.shape
     kout = W.data.shape[1]
     if kin % 8 == 0 and kout % 8 == 0 and kin * kout >= 65536:
         x4 = reshape(x, (m, 1, 1, kin))
-        y4 = conv2d(x4, W, b, 1, 1, 1, "VALID", sn=sn)
+        y4 = conv2d(x4, W, b, 1, 1, 1, "VALID", sn=sn, out_dtype=out_dtype)
         return reshape(y4, (m, kout))
+    if out_dtype != F32:
+        raise NotImplementedError("bf16 output is only built for the tensor-core linear path")
     xin = x if x.data.dtype == F32 else cast(x, F32)
     alpha = sn.inv_sigma if sn is not None else None
     y = torch.empty((m, kout), dtype=F32, device=x.data.device)
@@ -291,19 +301,21 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
         mean, rstd = K.bn_stats(x.data, n, h * w, c, g, eps)
     gam = gamma.data if gamma is not None else None
     bet = beta.data if beta is not None else None
-    raw = torch.empty((n, h, w, c), dtype=BF16, device=x.data.device) if want_raw else None
+    # the raw bf16 copy (1x1-shortcut operand) is x itself when x is already stored in bf16
+    share_raw = want_raw and x.data.dtype == BF16
+    raw = torch.empty((n, h, w, c), dtype=BF16, device=x.data.device) if (want_raw and not share_raw) else None
     y = K.norm_act_fwd(x.data, n, h, w, c, mean, rstd, g, gam, bet, labels, act, upsample, out_dtype, out_raw=raw)
     out = Var(y, grad_dtype=out_grad_dtype)
-    raw_var = Var(raw) if want_raw else None  # bf16 value, bf16 gradient
+    raw_var = x if share_raw else (Var(raw) if want_raw else None)  # bf16 value, bf16 gradient
     need_p = gamma is not None and gamma.needs_grad and _tape() is not None
     if _rg(x) or need_p:
         out.requires_grad = True
-        if raw_var is not None:
+        if raw_var is not None and not share_raw:
             raw_var.requires_grad = x.requires_grad
 
         def bwd():
             gz = out.grad
-            extra = raw_var.grad if raw_var is not None else None
+            extra = raw_var.grad if (raw_var is not None and not share_raw) else None
             if gz is None:
                 if extra is not None and x.requires_grad:
                     x.accum(extra)

@@ -324,6 +324,8 @@ def batch_norm(g, inputs, decay=0.9, epsilon=1e-5, is_training=True, fused=True)
     Moving statistics are write-only state in every shipped caller; they are updated here with the plain
     EMA (population mean, Bessel-corrected variance) and no zero-debias slots."""
     with g.variable_scope("BatchNorm"):
+        if BF16_OPERANDS:
+            inputs = _ste_r16(inputs)   # the B200 path stores every batch-norm input in bf16
         c = inputs.shape[-1]
         beta = g.get_variable("beta", initializer=tfshim.constant_initializer(0.0), shape=[c])
         gamma = g.get_variable("gamma", initializer=tfshim.constant_initializer(1.0), shape=[c])
@@ -348,6 +350,8 @@ def cond_batchnorm(g, name, axes, inputs, is_training=None, stats_iter=None, upd
     with g.variable_scope("CondBatchNorm"):
         if axes != [0, 1, 2]:
             raise Exception("Axes is not supported in Conditional BatchNorm!")
+        if BF16_OPERANDS:
+            inputs = _ste_r16(inputs)   # the B200 path stores every batch-norm input in bf16
         mean = inputs.mean(dim=(0, 1, 2), keepdim=True)               # tf.nn.moments -> population variance
         var = inputs.var(dim=(0, 1, 2), unbiased=False, keepdim=True)
         c = inputs.shape[3]

@@ -45,6 +45,11 @@ def env():
     framework.set_store(None)
 
 
+def _bf16_repr(x_np):
+    """Nearest bf16-representable fp32 array (inputs of layers whose operand the product stores in bf16)."""
+    return torch.from_numpy(x_np).to(torch.bfloat16).to(torch.float32).numpy()
+
+
 def _oracle_graph(tfshim):
     return tfshim.Graph(dtype=torch.float32, u_seed=2)
 
@@ -220,7 +225,7 @@ def test_cond_batchnorm_relu_fused(env, n, h, c, groups, upsample):
     from oracle import resnet_block as ORB
 
     labels = np.random.RandomState(7).randint(0, 10, size=n).astype("int32")
-    x = (np.random.RandomState(8).standard_normal((n, h, h, c)) * 1.7 + 0.3).astype("float32")
+    x = _bf16_repr((np.random.RandomState(8).standard_normal((n, h, h, c)) * 1.7 + 0.3).astype("float32"))
     lab_t = torch.from_numpy(labels).long()
     lab_p = torch.from_numpy(labels).cuda()
 
@@ -262,7 +267,7 @@ def test_batch_norm_and_instance_norm(env):
     from gan_lib_tensorflow_b200.common.ops import normalization as P
     from oracle import ops as O
 
-    x = (np.random.RandomState(11).standard_normal((6, 8, 8, 32)) * 2 - 0.5).astype("float32")
+    x = _bf16_repr((np.random.RandomState(11).standard_normal((6, 8, 8, 32)) * 2 - 0.5).astype("float32"))
     prod, refs = run_pair(store, tfshim, lambda xv: P.batch_norm(xv), lambda g, xt: O.batch_norm(g, xt), x, bf16=False)
     check(prod, refs, tol_fp32=5e-5)
     from gan_lib_tensorflow_b200 import framework
@@ -402,7 +407,8 @@ def test_residual_block_matches_oracle(env, resample, cin, cout, h, net):
     labels = np.random.RandomState(20).randint(0, 10, size=n).astype("int32")
     lab_p = torch.from_numpy(labels).cuda()
     lab_t = torch.from_numpy(labels).long()
-    x = np.random.RandomState(21).standard_normal((n, h, h, cin)).astype("float32")
+    # bf16-representable input: the product keeps the inputs of batch-norm layers (G's residual stream) in bf16
+    x = _bf16_repr(np.random.RandomState(21).standard_normal((n, h, h, cin)).astype("float32"))
     sn = net == "D"
     name = net + ".Block.X"
     prod, refs = run_pair(
