@@ -233,6 +233,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   const int kiters = p.taps * p.kchunks;
 
@@ -370,6 +371,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer: filter tiles (warp-uniform loop, elected lane issues) =====================
@@ -464,6 +466,138 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow-output variant of the halo kernel (Cout <= BN <= 32, e.g. G.Output 256 -> 3): the whole packed filter
+// (taps x kchunks tiles of BN x 64) is loaded into shared memory ONCE per CTA.  With a per-tap filter ring the 2 KiB
+// filter loads queue behind the 23 KiB halo loads in the SM's TMA FIFO and the MMA thread waits a ring revolution per
+// channel chunk (62 us for 128x32x32x256 -> 3, four times its activation-read time); resident, the loop has no
+// filter barriers at all.
+template <int BN, int SA>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const IgemmParams p, int a_stage_bytes, int halo_w, int halo_bytes) {
+  constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr int ACC_STAGES = 2;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN) < 32 ? 32 : (ACC_STAGES * BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int b_tiles = p.taps * p.kchunks;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + SA * a_stage_bytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + b_tiles * B_TILE_BYTES);
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* tfull = fullB + 1;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    mbar_init(fullB, 1);
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== filter: one-time load of every (channel chunk, tap) tile =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(fullB, b_tiles * B_TILE_BYTES);
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
+          tma_load_3d(sB + (kc * p.taps + tap) * B_TILE_BYTES, &tmB, fullB, kc * BK, 0, tap_b);
+        }
+    }
+    __syncwarp();
+  } else if (warp == HALO_A_WARP) {
+    // ===================== TMA producer: activation halos =====================
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&emptyA[sa], pa ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&fullA[sa], halo_bytes);
+          tma_load_4d(sA + sa * a_stage_bytes, &tmA, &fullA[sa], kc * BK, tw * p.bw - p.pad_l, th * p.bh - p.pad_t, t);
+        }
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int sa = 0, as = 0;
+    uint32_t pa = 0, aphase = 0;
+    const uint32_t sbo = static_cast<uint32_t>(halo_w) * 128u;
+    const uint64_t adesc_base = umma_desc_base_sw128(16, sbo);
+    const uint64_t bdesc_base = umma_desc_base_sw128(16, 1024);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    const int kw = p.kw, kh = p.taps / p.kw;
+    mbar_wait(fullB, 0);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      uint32_t acc = 0;
+      uint32_t b_addr = sB_addr;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&fullA[sa], pa);
+        tc_fence_after();
+        if (elect_one()) {
+          uint32_t a_row = sA_addr + sa * a_stage_bytes;
+          for (int r = 0; r < kh; ++r, a_row += sbo) {
+            for (int s2 = 0; s2 < kw; ++s2, b_addr += B_TILE_BYTES) {
+              const uint64_t adesc = umma_desc_at(adesc_base, a_row + s2 * 128);
+              const uint64_t bdesc = umma_desc_at(bdesc_base, b_addr);
+              umma_bf16(tmem_d, adesc, bdesc, IDESC, acc);
+#pragma unroll
+              for (int k = 1; k < BK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+              acc = 1u;
+            }
+          }
+          umma_commit(&emptyA[sa]);
+        }
+        __syncwarp();
+        b_addr = sB_addr + (kc + 1) * p.taps * B_TILE_BYTES;
+        acc = 1u;
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-pair variant of the halo kernel (tcgen05 cta_group::2, UMMA M = 256): a cluster of two CTAs owns two adjacent
 // 16x8 pixel tiles and ONE filter tile of BN output channels.  Each CTA loads its own activation halo and the half of
 // the filter tile with rows [rank*BN/2, (rank+1)*BN/2); the leader (rank 0) issues the MMAs for both SMs.  Filter
@@ -519,6 +653,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();   // the peer's barriers are initialised and its TMEM is allocated before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer: this CTA's half of the filter tile =====================
@@ -714,6 +849,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   int u = blockIdx.x;
   const int tco = u % p.co_tiles; u /= p.co_tiles;
@@ -820,6 +956,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 // dw = beta*dw + scale * sum_s partial[s]
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int64_t n4,
                                      int splits, const float* __restrict__ scale, float beta) {
+  pdl_wait();
   const float sc = scale ? __ldg(scale) : 1.0f;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -868,7 +1005,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPar
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
   GANB_CHECK_LAUNCH("conv_igemm_kernel");
   return 0;
 }
@@ -888,8 +1025,27 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  kern<<<grid, HALO_THREADS, smem, stream>>>(tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
+  launch_k(kern, grid, HALO_THREADS, smem, stream, tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
   GANB_CHECK_LAUNCH("conv_halo_kernel");
+  return 0;
+}
+
+template <int BN, int SA>
+static int launch_halo_narrow(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, int a_stage_bytes,
+                              int halo_w, int halo_bytes, cudaStream_t stream) {
+  const int smem = SA * a_stage_bytes + p.taps * p.kchunks * BN * BK * 2 + 1024 + 512;
+  auto kern = conv_halo_narrow_kernel<BN, SA>;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "narrow halo smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  p.tiles_co = 1;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  launch_k(kern, grid, HALO_THREADS, smem, stream, tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
+  GANB_CHECK_LAUNCH("conv_halo_narrow_kernel");
   return 0;
 }
 
@@ -921,7 +1077,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
   p.num_tiles = pair_tiles;
   int clusters = sm_count() / 2;
   if (clusters > pair_tiles) clusters = pair_tiles;
-  kern<<<2 * clusters, HALO_THREADS, smem, stream>>>(tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
+  launch_k(kern, 2 * clusters, HALO_THREADS, smem, stream, tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
   GANB_CHECK_LAUNCH("conv_pair_kernel");
   return 0;
 }
@@ -998,6 +1154,9 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
       if (pair_bn == 256) return launch_pair<256, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
       return launch_pair<128, 4, 12>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
     }
+    // narrow outputs: resident filter when it fits next to four halo stages
+    if (bn_tile == 16 && cout <= 16 && 4 * a_stage + p.taps * p.kchunks * 16 * BK * 2 + 2048 <= 232448)
+      return launch_halo_narrow<16, 4>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
     switch (bn_tile) {
       case 16: return launch_halo<16, 7, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
       case 32: return launch_halo<32, 6, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
@@ -1059,7 +1218,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
     if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "wgrad smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, smem, stream>>>(tmX, tmDY, p);
+  launch_k(kern, grid, NUM_THREADS, smem, stream, tmX, tmDY, p);
   GANB_CHECK_LAUNCH("conv_wgrad_kernel");
   return 0;
 }
@@ -1113,7 +1272,7 @@ extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void*
   const int64_t n4 = total / 4;  // cout % 8 == 0
   int blocks = static_cast<int>(ceil_div64(n4, 256));
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, dw, n4, p.splits, scale, beta);
+  launch_k(splitk_reduce_kernel, blocks, 256, 0, stream, p.partial, dw, n4, p.splits, scale, beta);
   GANB_CHECK_LAUNCH("splitk_reduce_kernel");
   return 0;
 }

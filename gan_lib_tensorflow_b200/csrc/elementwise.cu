@@ -70,6 +70,7 @@ template <typename TX>
 __global__ void __launch_bounds__(256)
 bn_stats_partial_kernel(const TX* __restrict__ x, int rows_per_group, int c, int chunks, int rows_per_chunk,
                 float* __restrict__ partial) {
+  pdl_wait();
   const int g = blockIdx.y, chunk = blockIdx.x;
   const int v = c >> 2;                          // float4 columns
   const int lanes = max(1, 256 / min(v, 256));   // row lanes per column block
@@ -119,6 +120,7 @@ bn_stats_partial_kernel(const TX* __restrict__ x, int rows_per_group, int c, int
 __global__ void __launch_bounds__(256)
 bn_stats_finalize_kernel(const float* __restrict__ partial, int c, int groups, int chunks, float inv_count, float eps,
                          float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);  // flat (group, channel)
   if (i >= groups * c) return;
@@ -155,6 +157,7 @@ struct NormActFwd {
 // computed once and the loop streams x with several independent 16-byte loads in flight.
 template <typename TX>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormActFwd p, int pix_per_chunk) {
+  pdl_wait();
   const int ni = blockIdx.y;
   const int v = p.c >> 2;
   const int cols = min(v, 256);
@@ -296,6 +299,7 @@ __device__ __forceinline__ void norm_act_bwd_math(const NormActBwd& p, const Nor
 // grid (chunks, n); per-sample partial sums A = sum dy, B = sum dy*xhat
 template <bool UPS, bool DZ16, typename TX>
 __global__ void __launch_bounds__(256, 3) norm_act_bwd_reduce_kernel(const NormActBwd p) {
+  pdl_wait();
   const int ni = blockIdx.y, chunk = blockIdx.x;
   const int v = p.c >> 2;
   const int lanes = max(1, 256 / min(v, 256));
@@ -356,6 +360,7 @@ __global__ void __launch_bounds__(256)
 norm_act_bwd_finalize_kernel(const float* __restrict__ part, int n, int c, int chunks, int groups,
                              const float* __restrict__ gamma, const int* __restrict__ labels,
                              float* __restrict__ sums /*[n][2][c]*/, float* __restrict__ s1, float* __restrict__ s2) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int g = blockIdx.y;
@@ -389,6 +394,7 @@ norm_act_bwd_finalize_kernel(const float* __restrict__ part, int n, int c, int c
 __global__ void __launch_bounds__(256)
 norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int n, int c, int n_rows, const int* __restrict__ labels,
                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= n_rows * c) return;
@@ -410,6 +416,7 @@ norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int n, int c, int n_
 
 template <bool NORM, bool UPS, bool DZ16, typename TX>
 __global__ void __launch_bounds__(256, 3) norm_act_bwd_apply_kernel(const NormActBwd p, int pix_per_chunk) {
+  pdl_wait();
   const int ni = blockIdx.y;
   const TX* xp = static_cast<const TX*>(p.x);
   const int v = p.c >> 2;
@@ -474,6 +481,7 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 meanpool2_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ add, TOut* __restrict__ out, int n, int ho,
                      int wo, int c) {
+  pdl_wait();
   const int v = c >> 2;
   const int64_t total = static_cast<int64_t>(n) * ho * wo * v;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -501,6 +509,7 @@ meanpool2_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ add, T
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 expand2_kernel(const TIn* __restrict__ dz, TOut* __restrict__ dx, int n, int h, int w, int c, float scale) {
+  pdl_wait();
   const int v = c >> 2;
   const int64_t total = static_cast<int64_t>(n) * h * w * v;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -525,6 +534,7 @@ expand2_kernel(const TIn* __restrict__ dz, TOut* __restrict__ dx, int n, int h, 
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 sum2x2_kernel(const TIn* __restrict__ x, TOut* __restrict__ out, int n, int ho, int wo, int c, float scale) {
+  pdl_wait();
   const int v = c >> 2;
   const int64_t total = static_cast<int64_t>(n) * ho * wo * v;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -547,6 +557,7 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 pool2_scalar_kernel(const TIn* __restrict__ x, const float* __restrict__ add, TOut* __restrict__ out, int n, int ho,
                     int wo, int c, float scale) {
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(n) * ho * wo * c;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -566,6 +577,7 @@ pool2_scalar_kernel(const TIn* __restrict__ x, const float* __restrict__ add, TO
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 expand2_scalar_kernel(const TIn* __restrict__ dz, TOut* __restrict__ dx, int n, int h, int w, int c, float scale) {
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(n) * h * w * c;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -584,6 +596,7 @@ expand2_scalar_kernel(const TIn* __restrict__ dz, TOut* __restrict__ dx, int n, 
 // ------------------------------------------------------------------------------------------------ casts / axpy
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) cast_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int64_t n4, float scale) {
+  pdl_wait();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 a = ld4(x + i * 4);
@@ -593,12 +606,14 @@ __global__ void __launch_bounds__(256) cast_kernel(const TIn* __restrict__ x, TO
 }
 template <typename TIn, typename TOut>
 __global__ void cast_tail_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int64_t begin, int64_t n, float scale) {
+  pdl_wait();
   const int64_t i = begin + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < n) y[i] = static_cast<TOut>(static_cast<float>(x[i]) * scale);
 }
 
 // y = a*x + b*y  (fp32, flat)
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float a, float b) {
+  pdl_wait();
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -619,6 +634,7 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x,
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_per_chunk, float* __restrict__ partial) {
+  pdl_wait();
   const int chunk = blockIdx.x;
   const int v = c >> 2;
   const int lanes = max(1, 256 / min(v, 256));
@@ -655,6 +671,7 @@ colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_p
 }
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, float beta, float* __restrict__ out) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (ch >= c) return;
@@ -669,6 +686,7 @@ colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, flo
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 colsum_narrow_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_per_chunk, float* __restrict__ partial) {
+  pdl_wait();
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_chunk;
   const int64_t r1 = min(rows, r0 + rows_per_chunk);
   float s[8];
@@ -697,6 +715,7 @@ colsum_narrow_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_pe
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 colsum_wide_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, float* __restrict__ out) {
+  pdl_wait();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   float s = 0.f;
@@ -708,6 +727,7 @@ colsum_wide_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, f
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 colsum_scalar_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta, float* __restrict__ out) {
+  pdl_wait();
   const int ch = blockIdx.x;
   __shared__ float sh[256];
   float s = 0.f;
@@ -726,6 +746,7 @@ colsum_scalar_kernel(const TIn* __restrict__ x, int64_t rows, int c, float beta,
 __global__ void __launch_bounds__(256)
 bcast_channels_kernel(const float* __restrict__ e, int n, int hw, int c2, int coff, int cstride, int act,
                       __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act) {
+  pdl_wait();
   const int v = c2 >> 2;
   const int64_t total = static_cast<int64_t>(n) * hw * v;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -746,6 +767,7 @@ __global__ void __launch_bounds__(256)
 bcast_channels_bwd_kernel(const float* __restrict__ e, int hw, int c2, int coff, int cstride, int act,
                           const TG* __restrict__ d_raw, const TG* __restrict__ d_act,
                           float* __restrict__ de) {
+  pdl_wait();
   const int ni = blockIdx.x;
   const int v = c2 >> 2;
   const int lanes = max(1, 256 / min(v, 256));
@@ -783,6 +805,7 @@ __global__ void __launch_bounds__(256)
 concat_bwd_x_kernel(const float* __restrict__ x, int64_t pixels, int c1, int cstride, int act,
                     const TG* __restrict__ d_raw, const TG* __restrict__ d_act,
                     TOut* __restrict__ dx) {
+  pdl_wait();
   const int v = c1 >> 2;
   const int64_t total = pixels * v;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -805,6 +828,7 @@ concat_bwd_x_kernel(const float* __restrict__ x, int64_t pixels, int c1, int cst
 // out[n,c] = mean_hw act(x[n,hw,c]) ; grid (n)
 __global__ void __launch_bounds__(256)
 act_mean_hw_fwd_kernel(const float* __restrict__ x, int hw, int c, int act, float* __restrict__ out) {
+  pdl_wait();
   const int ni = blockIdx.x;
   const int v = c >> 2;
   const int lanes = max(1, 256 / min(v, 256));
@@ -837,6 +861,7 @@ template <typename TOut>
 __global__ void __launch_bounds__(256)
 act_mean_hw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, int n, int hw, int c, int act,
                        TOut* __restrict__ dx) {
+  pdl_wait();
   const int v = c >> 2;
   const int64_t total = static_cast<int64_t>(n) * hw * v;
   const float inv = 1.0f / hw;
@@ -859,6 +884,7 @@ act_mean_hw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ do
 __global__ void __launch_bounds__(256)
 gan_loss_kernel(const float* __restrict__ d, int n, int n_real, int mode, float scale, int accumulate,
                 float* __restrict__ loss_out, float* __restrict__ dlogits) {
+  pdl_wait();
   __shared__ float sh[256];
   float acc = 0.f;
   const int n_fake = n - n_real;
@@ -889,6 +915,7 @@ gan_loss_kernel(const float* __restrict__ d, int n, int n_real, int mode, float 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, const float* __restrict__ lr_t, float b1, float b2, float eps, float grad_scale) {
+  pdl_wait();
   const float lr = __ldg(lr_t);
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -917,6 +944,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // gan_cifar_resnet.py:334-337: int32 [B, 3*H*W] CHW -> 2*(x/256 - .5) + noise -> NHWC fp32
 __global__ void __launch_bounds__(256)
 preprocess_real_kernel(const int* __restrict__ data, const float* __restrict__ noise, int b, int hw, float* __restrict__ out) {
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(b) * hw * 3;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -934,6 +962,7 @@ preprocess_real_kernel(const int* __restrict__ data, const float* __restrict__ n
 // ------------------------------------------------------------------------------------------------ embedding
 __global__ void embedding_fwd_kernel(const float* __restrict__ table, const int* __restrict__ labels, int n, int dim,
                                      float* __restrict__ out) {
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(n) * dim;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -944,6 +973,7 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ table, const int*
 // dtable[row, j] += sum_{n: labels[n]==row} dout[n, j]   (IndexedSlices summed by index; deterministic)
 __global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ labels, int n, int dim,
                                      int vocab, float* __restrict__ dtable) {
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(vocab) * dim;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -986,14 +1016,13 @@ extern "C" int ganb_bn_stats(const void* x, int x_dtype, int n, int hw, int c, i
   const int used = ceil_div(rows_per_group, rows_per_chunk);
   const dim3 grid(used, groups);
   if (x_dtype == GANB_BF16)
-    bn_stats_partial_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), rows_per_group, c,
+    launch_k(bn_stats_partial_kernel<__nv_bfloat16>, grid, 256, 0, STREAM, static_cast<const __nv_bfloat16*>(x), rows_per_group, c,
                                                                       used, rows_per_chunk, static_cast<float*>(workspace));
   else
-    bn_stats_partial_kernel<float><<<grid, 256, 0, STREAM>>>(static_cast<const float*>(x), rows_per_group, c, used,
+    launch_k(bn_stats_partial_kernel<float>, grid, 256, 0, STREAM, static_cast<const float*>(x), rows_per_group, c, used,
                                                               rows_per_chunk, static_cast<float*>(workspace));
   GANB_CHECK_LAUNCH("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<ceil_div(groups * c, 8), 256, 0, STREAM>>>(
-      static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
+  launch_k(bn_stats_finalize_kernel, ceil_div(groups * c, 8), 256, 0, STREAM, static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
   GANB_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return 0;
 }
@@ -1022,8 +1051,8 @@ extern "C" int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
   const int chunks = bwd_chunks(n, h * w);
   const int ppc = ceil_div(h * w, chunks);
-  if (p.x_bf16) norm_act_fwd_kernel<__nv_bfloat16><<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
-  else norm_act_fwd_kernel<float><<<dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM>>>(p, ppc);
+  if (p.x_bf16) launch_k(norm_act_fwd_kernel<__nv_bfloat16>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
+  else launch_k(norm_act_fwd_kernel<float>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
   GANB_CHECK_LAUNCH("norm_act_fwd_kernel");
   return 0;
 }
@@ -1036,23 +1065,23 @@ extern "C" int64_t ganb_norm_act_bwd_workspace(int n, int hw, int c, int groups)
 namespace ganb {
 template <typename TX>
 static void launch_bwd_reduce(const NormActBwd& p, dim3 grid, cudaStream_t s) {
-  if (p.upsample && p.dz_bf16) norm_act_bwd_reduce_kernel<true, true, TX><<<grid, 256, 0, s>>>(p);
-  else if (p.upsample) norm_act_bwd_reduce_kernel<true, false, TX><<<grid, 256, 0, s>>>(p);
-  else if (p.dz_bf16) norm_act_bwd_reduce_kernel<false, true, TX><<<grid, 256, 0, s>>>(p);
-  else norm_act_bwd_reduce_kernel<false, false, TX><<<grid, 256, 0, s>>>(p);
+  if (p.upsample && p.dz_bf16) launch_k(norm_act_bwd_reduce_kernel<true, true, TX>, grid, 256, 0, s, p);
+  else if (p.upsample) launch_k(norm_act_bwd_reduce_kernel<true, false, TX>, grid, 256, 0, s, p);
+  else if (p.dz_bf16) launch_k(norm_act_bwd_reduce_kernel<false, true, TX>, grid, 256, 0, s, p);
+  else launch_k(norm_act_bwd_reduce_kernel<false, false, TX>, grid, 256, 0, s, p);
 }
 template <typename TX>
 static void launch_bwd_apply(const NormActBwd& p, bool norm, dim3 grid, int ppc, cudaStream_t s) {
   const int idx = (norm ? 4 : 0) | (p.upsample ? 2 : 0) | (p.dz_bf16 ? 1 : 0);
   switch (idx) {
-    case 0: norm_act_bwd_apply_kernel<false, false, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
-    case 1: norm_act_bwd_apply_kernel<false, false, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
-    case 2: norm_act_bwd_apply_kernel<false, true, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
-    case 3: norm_act_bwd_apply_kernel<false, true, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
-    case 4: norm_act_bwd_apply_kernel<true, false, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
-    case 5: norm_act_bwd_apply_kernel<true, false, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
-    case 6: norm_act_bwd_apply_kernel<true, true, false, TX><<<grid, 256, 0, s>>>(p, ppc); break;
-    default: norm_act_bwd_apply_kernel<true, true, true, TX><<<grid, 256, 0, s>>>(p, ppc); break;
+    case 0: launch_k(norm_act_bwd_apply_kernel<false, false, false, TX>, grid, 256, 0, s, p, ppc); break;
+    case 1: launch_k(norm_act_bwd_apply_kernel<false, false, true, TX>, grid, 256, 0, s, p, ppc); break;
+    case 2: launch_k(norm_act_bwd_apply_kernel<false, true, false, TX>, grid, 256, 0, s, p, ppc); break;
+    case 3: launch_k(norm_act_bwd_apply_kernel<false, true, true, TX>, grid, 256, 0, s, p, ppc); break;
+    case 4: launch_k(norm_act_bwd_apply_kernel<true, false, false, TX>, grid, 256, 0, s, p, ppc); break;
+    case 5: launch_k(norm_act_bwd_apply_kernel<true, false, true, TX>, grid, 256, 0, s, p, ppc); break;
+    case 6: launch_k(norm_act_bwd_apply_kernel<true, true, false, TX>, grid, 256, 0, s, p, ppc); break;
+    default: launch_k(norm_act_bwd_apply_kernel<true, true, true, TX>, grid, 256, 0, s, p, ppc); break;
   }
 }
 }  // namespace ganb
@@ -1088,12 +1117,12 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
     if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
     else launch_bwd_reduce<float>(p, grid, STREAM);
     GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
-    norm_act_bwd_finalize_kernel<<<dim3(ceil_div(c, 8), groups), 256, 0, STREAM>>>(p.part, n, c, p.chunks, groups, gamma,
+    launch_k(norm_act_bwd_finalize_kernel, dim3(ceil_div(c, 8), groups), 256, 0, STREAM, p.part, n, c, p.chunks, groups, gamma,
                                                                                   labels, sums, s1, s2);
     GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
     if (gamma && dgamma && dbeta) {
       const int rows = (labels && n_rows > 0) ? n_rows : 1;
-      norm_act_bwd_scatter_kernel<<<ceil_div(rows * c, 8), 256, 0, STREAM>>>(sums, n, c, rows, labels, dgamma, dbeta);
+      launch_k(norm_act_bwd_scatter_kernel, ceil_div(rows * c, 8), 256, 0, STREAM, sums, n, c, rows, labels, dgamma, dbeta);
       GANB_CHECK_LAUNCH("norm_act_bwd_scatter_kernel");
     }
     p.s1 = s1; p.s2 = s2;
@@ -1113,13 +1142,12 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
 template <typename TIn, typename TOut>
 static int launch_meanpool(const void* x, const float* add, void* out, int n, int ho, int wo, int c, cudaStream_t s) {
   if (c % 4 != 0) {
-    pool2_scalar_kernel<TIn, TOut><<<grid_for(static_cast<int64_t>(n) * ho * wo * c, 256), 256, 0, s>>>(
-        static_cast<const TIn*>(x), add, static_cast<TOut*>(out), n, ho, wo, c, 0.25f);
+    launch_k(pool2_scalar_kernel<TIn, TOut>, grid_for(static_cast<int64_t>(n) * ho * wo * c, 256), 256, 0, s, static_cast<const TIn*>(x), add, static_cast<TOut*>(out), n, ho, wo, c, 0.25f);
     GANB_CHECK_LAUNCH("pool2_scalar_kernel");
     return 0;
   }
   const int64_t items = static_cast<int64_t>(n) * ho * wo * (c / 4);
-  meanpool2_fwd_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), add,
+  launch_k(meanpool2_fwd_kernel<TIn, TOut>, grid_for(items, 256), 256, 0, s, static_cast<const TIn*>(x), add,
                                                                        static_cast<TOut*>(out), n, ho, wo, c);
   GANB_CHECK_LAUNCH("meanpool2_fwd_kernel");
   return 0;
@@ -1139,13 +1167,12 @@ extern "C" int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, 
 template <typename TIn, typename TOut>
 static int launch_expand(const void* x, void* out, int n, int h, int w, int c, float scale, cudaStream_t s) {
   if (c % 4 != 0) {
-    expand2_scalar_kernel<TIn, TOut><<<grid_for(static_cast<int64_t>(n) * h * w * c, 256), 256, 0, s>>>(
-        static_cast<const TIn*>(x), static_cast<TOut*>(out), n, h, w, c, scale);
+    launch_k(expand2_scalar_kernel<TIn, TOut>, grid_for(static_cast<int64_t>(n) * h * w * c, 256), 256, 0, s, static_cast<const TIn*>(x), static_cast<TOut*>(out), n, h, w, c, scale);
     GANB_CHECK_LAUNCH("expand2_scalar_kernel");
     return 0;
   }
   const int64_t items = static_cast<int64_t>(n) * h * w * (c / 4);
-  expand2_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(out), n, h, w, c, scale);
+  launch_k(expand2_kernel<TIn, TOut>, grid_for(items, 256), 256, 0, s, static_cast<const TIn*>(x), static_cast<TOut*>(out), n, h, w, c, scale);
   GANB_CHECK_LAUNCH("expand2_kernel");
   return 0;
 }
@@ -1163,13 +1190,12 @@ extern "C" int ganb_expand2(const void* x, int x_dtype, void* out, int out_dtype
 template <typename TIn, typename TOut>
 static int launch_sum2x2(const void* x, void* out, int n, int ho, int wo, int c, float scale, cudaStream_t s) {
   if (c % 4 != 0) {
-    pool2_scalar_kernel<TIn, TOut><<<grid_for(static_cast<int64_t>(n) * ho * wo * c, 256), 256, 0, s>>>(
-        static_cast<const TIn*>(x), nullptr, static_cast<TOut*>(out), n, ho, wo, c, scale);
+    launch_k(pool2_scalar_kernel<TIn, TOut>, grid_for(static_cast<int64_t>(n) * ho * wo * c, 256), 256, 0, s, static_cast<const TIn*>(x), nullptr, static_cast<TOut*>(out), n, ho, wo, c, scale);
     GANB_CHECK_LAUNCH("pool2_scalar_kernel");
     return 0;
   }
   const int64_t items = static_cast<int64_t>(n) * ho * wo * (c / 4);
-  sum2x2_kernel<TIn, TOut><<<grid_for(items, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(out), n, ho, wo, c, scale);
+  launch_k(sum2x2_kernel<TIn, TOut>, grid_for(items, 256), 256, 0, s, static_cast<const TIn*>(x), static_cast<TOut*>(out), n, ho, wo, c, scale);
   GANB_CHECK_LAUNCH("sum2x2_kernel");
   return 0;
 }
@@ -1190,11 +1216,11 @@ template <typename TIn, typename TOut>
 static int launch_cast(const void* x, void* y, int64_t n, float scale, cudaStream_t s) {
   const int64_t n4 = n / 4;
   if (n4 > 0) {
-    cast_kernel<TIn, TOut><<<grid_for(n4, 256), 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(y), n4, scale);
+    launch_k(cast_kernel<TIn, TOut>, grid_for(n4, 256), 256, 0, s, static_cast<const TIn*>(x), static_cast<TOut*>(y), n4, scale);
     GANB_CHECK_LAUNCH("cast_kernel");
   }
   if (n % 4) {
-    cast_tail_kernel<TIn, TOut><<<1, 32, 0, s>>>(static_cast<const TIn*>(x), static_cast<TOut*>(y), n4 * 4, n, scale);
+    launch_k(cast_tail_kernel<TIn, TOut>, 1, 32, 0, s, static_cast<const TIn*>(x), static_cast<TOut*>(y), n4 * 4, n, scale);
     GANB_CHECK_LAUNCH("cast_tail_kernel");
   }
   return 0;
@@ -1211,7 +1237,7 @@ extern "C" int ganb_cast(const void* x, int x_dtype, void* y, int y_dtype, int64
 extern "C" int ganb_axpby(const float* x, float* y, int64_t count, float a, float b, void* stream) {
   if (!x || !y) return fail(GANB_E_BADARG, "axpby: null buffer");
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return fail(GANB_E_BADARG, "axpby: buffers must be 16-byte aligned");
-  axpby_kernel<<<grid_for(count / 4 + 1, 256), 256, 0, STREAM>>>(x, y, count, a, b);
+  launch_k(axpby_kernel, grid_for(count / 4 + 1, 256), 256, 0, STREAM, x, y, count, a, b);
   GANB_CHECK_LAUNCH("axpby_kernel");
   return 0;
 }
@@ -1226,12 +1252,12 @@ template <typename TIn>
 static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float* out, void* workspace, cudaStream_t s) {
   const TIn* x = static_cast<const TIn*>(xv);
   if (rows <= 512 && c >= 1024) {  // dense-layer bias gradients: coalesced over columns, short serial loop over rows
-    colsum_wide_kernel<TIn><<<ceil_div(c, 256), 256, 0, s>>>(x, rows, c, beta, out);
+    launch_k(colsum_wide_kernel<TIn>, ceil_div(c, 256), 256, 0, s, x, rows, c, beta, out);
     GANB_CHECK_LAUNCH("colsum_wide_kernel");
     return 0;
   }
   if (c % 4 != 0 && c > 8) {
-    colsum_scalar_kernel<TIn><<<c, 256, 0, s>>>(x, rows, c, beta, out);
+    launch_k(colsum_scalar_kernel<TIn>, c, 256, 0, s, x, rows, c, beta, out);
     GANB_CHECK_LAUNCH("colsum_scalar_kernel");
     return 0;
   }
@@ -1244,13 +1270,13 @@ static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float*
   const int rows_per_chunk = static_cast<int>(ceil_div64(rows, chunks));
   const int used = static_cast<int>(ceil_div64(rows, rows_per_chunk));
   if (narrow) {
-    colsum_narrow_kernel<TIn><<<used, 256, 0, s>>>(x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
+    launch_k(colsum_narrow_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
     GANB_CHECK_LAUNCH("colsum_narrow_kernel");
   } else {
-    colsum_partial_kernel<TIn><<<used, 256, 0, s>>>(x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
+    launch_k(colsum_partial_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
     GANB_CHECK_LAUNCH("colsum_partial_kernel");
   }
-  colsum_finalize_kernel<<<ceil_div(c, 8), 256, 0, s>>>(static_cast<float*>(workspace), c, used, beta, out);
+  launch_k(colsum_finalize_kernel, ceil_div(c, 8), 256, 0, s, static_cast<float*>(workspace), c, used, beta, out);
   GANB_CHECK_LAUNCH("colsum_finalize_kernel");
   return 0;
 }
@@ -1269,7 +1295,7 @@ extern "C" int ganb_bcast_channels_fwd(const float* e, int n, int hw, int c2, in
   if (!e) return fail(GANB_E_BADARG, "bcast_channels_fwd: null buffer");
   if (c2 % 4 || coff % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "bcast_channels_fwd: channel counts must be multiples of 4");
   const int64_t items = static_cast<int64_t>(n) * hw * (c2 / 4);
-  bcast_channels_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(e, n, hw, c2, coff, cstride, act,
+  launch_k(bcast_channels_kernel, grid_for(items, 256), 256, 0, STREAM, e, n, hw, c2, coff, cstride, act,
                                                                   static_cast<__nv_bfloat16*>(out_raw_bf16),
                                                                   static_cast<__nv_bfloat16*>(out_act_bf16));
   GANB_CHECK_LAUNCH("bcast_channels_kernel");
@@ -1281,11 +1307,11 @@ extern "C" int ganb_bcast_channels_bwd(const float* e, int n, int hw, int c2, in
   if (!e || !de) return fail(GANB_E_BADARG, "bcast_channels_bwd: null buffer");
   if (c2 % 4 || coff % 4 || cstride % 4) return fail(GANB_E_UNSUPPORTED, "bcast_channels_bwd: channel counts must be multiples of 4");
   if (d_dtype == GANB_BF16)
-    bcast_channels_bwd_kernel<__nv_bfloat16><<<n, 256, 0, STREAM>>>(e, hw, c2, coff, cstride, act,
+    launch_k(bcast_channels_bwd_kernel<__nv_bfloat16>, n, 256, 0, STREAM, e, hw, c2, coff, cstride, act,
                                                                     static_cast<const __nv_bfloat16*>(d_raw),
                                                                     static_cast<const __nv_bfloat16*>(d_act), de);
   else
-    bcast_channels_bwd_kernel<float><<<n, 256, 0, STREAM>>>(e, hw, c2, coff, cstride, act,
+    launch_k(bcast_channels_bwd_kernel<float>, n, 256, 0, STREAM, e, hw, c2, coff, cstride, act,
                                                             static_cast<const float*>(d_raw),
                                                             static_cast<const float*>(d_act), de);
   GANB_CHECK_LAUNCH("bcast_channels_bwd_kernel");
@@ -1296,8 +1322,7 @@ namespace ganb {
 template <typename TG, typename TOut>
 static void launch_concat_bwd_x(const float* x, int64_t pixels, int c1, int cstride, int act, const void* d_raw,
                                 const void* d_act, void* dx, cudaStream_t s) {
-  concat_bwd_x_kernel<TG, TOut><<<grid_for(pixels * (c1 / 4), 256), 256, 0, s>>>(
-      x, pixels, c1, cstride, act, static_cast<const TG*>(d_raw), static_cast<const TG*>(d_act), static_cast<TOut*>(dx));
+  launch_k(concat_bwd_x_kernel<TG, TOut>, grid_for(pixels * (c1 / 4), 256), 256, 0, s, x, pixels, c1, cstride, act, static_cast<const TG*>(d_raw), static_cast<const TG*>(d_act), static_cast<TOut*>(dx));
 }
 }  // namespace ganb
 
@@ -1317,7 +1342,7 @@ extern "C" int ganb_concat_bwd_x(const float* x, int64_t pixels, int c1, int cst
 extern "C" int ganb_act_mean_hw_fwd(const float* x, int n, int hw, int c, int act, float* out, void* stream) {
   if (!x || !out) return fail(GANB_E_BADARG, "act_mean_hw_fwd: null buffer");
   if (c % 4) return fail(GANB_E_UNSUPPORTED, "act_mean_hw_fwd: c=%d must be a multiple of 4", c);
-  act_mean_hw_fwd_kernel<<<n, 256, 0, STREAM>>>(x, hw, c, act, out);
+  launch_k(act_mean_hw_fwd_kernel, n, 256, 0, STREAM, x, hw, c, act, out);
   GANB_CHECK_LAUNCH("act_mean_hw_fwd_kernel");
   return 0;
 }
@@ -1328,9 +1353,9 @@ extern "C" int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, in
   if (c % 4) return fail(GANB_E_UNSUPPORTED, "act_mean_hw_bwd: c=%d must be a multiple of 4", c);
   const int grid = grid_for(static_cast<int64_t>(n) * hw * (c / 4), 256);
   if (dx_dtype == GANB_BF16)
-    act_mean_hw_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(x, dout, n, hw, c, act, static_cast<__nv_bfloat16*>(dx));
+    launch_k(act_mean_hw_bwd_kernel<__nv_bfloat16>, grid, 256, 0, STREAM, x, dout, n, hw, c, act, static_cast<__nv_bfloat16*>(dx));
   else
-    act_mean_hw_bwd_kernel<float><<<grid, 256, 0, STREAM>>>(x, dout, n, hw, c, act, static_cast<float*>(dx));
+    launch_k(act_mean_hw_bwd_kernel<float>, grid, 256, 0, STREAM, x, dout, n, hw, c, act, static_cast<float*>(dx));
   GANB_CHECK_LAUNCH("act_mean_hw_bwd_kernel");
   return 0;
 }
@@ -1340,7 +1365,7 @@ extern "C" int ganb_gan_loss(const float* logits, int n, int n_real, int mode, f
   if (!logits || !loss_out || !dlogits) return fail(GANB_E_BADARG, "gan_loss: null buffer");
   if (mode != 0 && mode != 1) return fail(GANB_E_UNSUPPORTED, "gan_loss: mode %d", mode);
   if (mode == 0 && (n_real <= 0 || n_real >= n)) return fail(GANB_E_BADARG, "gan_loss: hinge needs 0 < n_real < n");
-  gan_loss_kernel<<<1, 256, 0, STREAM>>>(logits, n, n_real, mode, scale, accumulate, loss_out, dlogits);
+  launch_k(gan_loss_kernel, 1, 256, 0, STREAM, logits, n, n_real, mode, scale, accumulate, loss_out, dlogits);
   GANB_CHECK_LAUNCH("gan_loss_kernel");
   return 0;
 }
@@ -1348,21 +1373,21 @@ extern "C" int ganb_gan_loss(const float* logits, int n, int n_real, int mode, f
 extern "C" int ganb_adam(float* params, const float* grads, float* m, float* v, int64_t count, const float* lr_t,
                          float beta1, float beta2, float eps, float grad_scale, void* stream) {
   if (!params || !grads || !m || !v || !lr_t) return fail(GANB_E_BADARG, "adam: null buffer");
-  adam_kernel<<<grid_for(count / 4 + 1, 256), 256, 0, STREAM>>>(params, grads, m, v, count, lr_t, beta1, beta2, eps, grad_scale);
+  launch_k(adam_kernel, grid_for(count / 4 + 1, 256), 256, 0, STREAM, params, grads, m, v, count, lr_t, beta1, beta2, eps, grad_scale);
   GANB_CHECK_LAUNCH("adam_kernel");
   return 0;
 }
 
 extern "C" int ganb_preprocess_real(const int* data, const float* noise, int b, int hw, float* out, void* stream) {
   if (!data || !out) return fail(GANB_E_BADARG, "preprocess_real: null buffer");
-  preprocess_real_kernel<<<grid_for(static_cast<int64_t>(b) * hw * 3, 256), 256, 0, STREAM>>>(data, noise, b, hw, out);
+  launch_k(preprocess_real_kernel, grid_for(static_cast<int64_t>(b) * hw * 3, 256), 256, 0, STREAM, data, noise, b, hw, out);
   GANB_CHECK_LAUNCH("preprocess_real_kernel");
   return 0;
 }
 
 extern "C" int ganb_embedding_fwd(const float* table, const int* labels, int n, int dim, float* out, void* stream) {
   if (!table || !labels || !out) return fail(GANB_E_BADARG, "embedding_fwd: null buffer");
-  embedding_fwd_kernel<<<grid_for(static_cast<int64_t>(n) * dim, 256), 256, 0, STREAM>>>(table, labels, n, dim, out);
+  launch_k(embedding_fwd_kernel, grid_for(static_cast<int64_t>(n) * dim, 256), 256, 0, STREAM, table, labels, n, dim, out);
   GANB_CHECK_LAUNCH("embedding_fwd_kernel");
   return 0;
 }
@@ -1370,7 +1395,7 @@ extern "C" int ganb_embedding_fwd(const float* table, const int* labels, int n, 
 extern "C" int ganb_embedding_bwd(const float* dout, const int* labels, int n, int dim, int vocab, float* dtable,
                                   void* stream) {
   if (!dout || !labels || !dtable) return fail(GANB_E_BADARG, "embedding_bwd: null buffer");
-  embedding_bwd_kernel<<<grid_for(static_cast<int64_t>(vocab) * dim, 256), 256, 0, STREAM>>>(dout, labels, n, dim, vocab, dtable);
+  launch_k(embedding_bwd_kernel, grid_for(static_cast<int64_t>(vocab) * dim, 256), 256, 0, STREAM, dout, labels, n, dim, vocab, dtable);
   GANB_CHECK_LAUNCH("embedding_bwd_kernel");
   return 0;
 }

@@ -2,6 +2,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -20,6 +21,15 @@ int fail(int code, const char* fmt, ...) {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("GANB_PDL");
+    mode = (e && e[0] == '1') ? 1 : 0;   // measured neutral inside captured graphs (profiles/r01 notes): opt-in
+  }
+  return mode == 1;
+}
 
 int sm_count() {
   static int cached = 0;

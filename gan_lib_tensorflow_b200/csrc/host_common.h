@@ -30,6 +30,37 @@ void count_launch();
     ::ganb::count_launch();                                                              \
   } while (0)
 
+// Every kernel of the library is launched through launch_k with programmatic dependent launch (PDL) allowed: the
+// kernel may be scheduled while its predecessor in the stream is still draining, runs its prologue (barrier init,
+// TMEM allocation, descriptor prefetch) and blocks in pdl_wait() until the predecessor's results are visible.  This
+// hides the ~1-2 us kernel-to-kernel gap of the ~300 launches of a training step (also inside captured CUDA graphs).
+// Opt-in with GANB_PDL=1 (measured neutral for the captured training step; plain stream-ordered launches otherwise).
+bool pdl_enabled();
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);
+}
+
+#ifdef __CUDACC__
+// Device side of PDL: wait until the grids this launch depends on have completed and their writes are visible, then
+// allow the next kernel of the stream to be scheduled.  Must precede the first access to global memory.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -45,6 +45,7 @@ struct SmallCinParams {
 };
 
 __global__ void __launch_bounds__(256) conv_smallcin_kernel(const SmallCinParams p) {
+  pdl_wait();
   extern __shared__ float wsm[];  // [taps][cs][cl]
   const int taps = p.kh * p.kw;
   const int wcount = taps * p.cs * p.cl;
@@ -108,6 +109,7 @@ struct SmallWgradParams {
 
 template <typename TL>
 __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(const SmallWgradParams p) {
+  pdl_wait();
   const int v = p.cl >> 2;
   const int cols = min(v, 256);
   const int lanes = 256 / cols;
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(const SmallWgradP
 __global__ void small_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int taps, int cs, int cl,
                                           int out_clcs, const float* __restrict__ scale, float beta,
                                           float* __restrict__ dw) {
+  pdl_wait();
   const int total = taps * cs * cl;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -189,6 +192,7 @@ struct SgemmParams {
 };
 
 __global__ void __launch_bounds__(256) sgemm_small_kernel(const SgemmParams p) {
+  pdl_wait();
   __shared__ float As[16][17], Bs[16][17];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const SgemmParams p) {
 __global__ void __launch_bounds__(256)
 im2col_small_kernel(const float* __restrict__ xs, __nv_bfloat16* __restrict__ out, int n, int hs, int ws, int cs,
                     int ho, int wo, int kh, int kw, int pad_t, int pad_l, int sign, int kpad) {
+  pdl_wait();
   const int groups = kpad >> 3;  // 8 bf16 = 16 bytes per thread
   const int64_t total = static_cast<int64_t>(n) * ho * wo * groups;
   const int kvalid = kh * kw * cs;
@@ -250,6 +255,7 @@ im2col_small_kernel(const float* __restrict__ xs, __nv_bfloat16* __restrict__ ou
 //   otherwise  : l = ci, c = co -> W[tap][l][c]   (dgrad operand of a small-cout layer)
 __global__ void pack_small_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps, int ci,
                                   int co, int small_is_ci, int kpad) {
+  pdl_wait();
   const int nl = small_is_ci ? co : ci, cs = small_is_ci ? ci : co;
   const int total = nl * kpad;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,6 +272,7 @@ __global__ void pack_small_kernel(const float* __restrict__ w, __nv_bfloat16* __
 // dw[tap][cs][cl] (or [tap][cl][cs] when out_clcs) = beta*dw + scale * r[tap*cs + c][l],  r is [kpad][cl] fp32
 __global__ void small_wgrad_scatter_kernel(const float* __restrict__ r, float* __restrict__ dw, int taps, int cs,
                                            int cl, int out_clcs, const float* __restrict__ scale, float beta) {
+  pdl_wait();
   const int total = taps * cs * cl;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -303,7 +310,7 @@ extern "C" int ganb_conv2d_smallcin(const float* x, const float* w, void* y, int
   int64_t blocks = ceil_div64(items, 256 * 4);
   if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
   if (blocks < 1) blocks = 1;
-  conv_smallcin_kernel<<<static_cast<int>(blocks), 256, smem, STREAM>>>(p);
+  launch_k(conv_smallcin_kernel, static_cast<int>(blocks), 256, smem, STREAM, p);
   GANB_CHECK_LAUNCH("conv_smallcin_kernel");
   return 0;
 }
@@ -339,11 +346,11 @@ extern "C" int ganb_conv2d_small_wgrad(const float* xs, const void* yl, int yl_d
   p.partial = static_cast<float*>(workspace);
   const int used = static_cast<int>(ceil_div64(total_pix, p.pix_per_chunk));
   const int smem = 256 * 16;
-  if (p.yl_bf16) conv_small_wgrad_kernel<__nv_bfloat16><<<used, 256, smem, STREAM>>>(p);
-  else conv_small_wgrad_kernel<float><<<used, 256, smem, STREAM>>>(p);
+  if (p.yl_bf16) launch_k(conv_small_wgrad_kernel<__nv_bfloat16>, used, 256, smem, STREAM, p);
+  else launch_k(conv_small_wgrad_kernel<float>, used, 256, smem, STREAM, p);
   GANB_CHECK_LAUNCH("conv_small_wgrad_kernel");
   const int total = kh * kw * cs * cl;
-  small_wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, STREAM>>>(p.partial, used, kh * kw, cs, cl, out_layout_clcs, scale, beta, dw);
+  launch_k(small_wgrad_reduce_kernel, ceil_div(total, 256), 256, 0, STREAM, p.partial, used, kh * kw, cs, cl, out_layout_clcs, scale, beta, dw);
   GANB_CHECK_LAUNCH("small_wgrad_reduce_kernel");
   return 0;
 }
@@ -357,7 +364,7 @@ extern "C" int ganb_sgemm_small(const float* a, const float* b, float* c, int m,
   p.a_sm = trans_a ? 1 : k; p.a_sk = trans_a ? m : 1;
   p.b_sk = trans_b ? 1 : n; p.b_sn = trans_b ? k : 1;
   p.alpha = alpha; p.bias = bias; p.beta = beta;
-  sgemm_small_kernel<<<dim3(ceil_div(n, 16), ceil_div(m, 16)), 256, 0, STREAM>>>(p);
+  launch_k(sgemm_small_kernel, dim3(ceil_div(n, 16), ceil_div(m, 16)), 256, 0, STREAM, p);
   GANB_CHECK_LAUNCH("sgemm_small_kernel");
   return 0;
 }
@@ -370,7 +377,7 @@ extern "C" int ganb_im2col_small(const float* xs, void* out_bf16, int n, int hs,
   const int64_t items = static_cast<int64_t>(n) * ho * wo * (kpad / 8);
   int64_t blocks = ceil_div64(items, 256);
   if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
-  im2col_small_kernel<<<static_cast<int>(blocks), 256, 0, STREAM>>>(xs, static_cast<__nv_bfloat16*>(out_bf16), n, hs, ws, cs,
+  launch_k(im2col_small_kernel, static_cast<int>(blocks), 256, 0, STREAM, xs, static_cast<__nv_bfloat16*>(out_bf16), n, hs, ws, cs,
                                                                    ho, wo, kh, kw, pad_t, pad_l, sign, kpad);
   GANB_CHECK_LAUNCH("im2col_small_kernel");
   return 0;
@@ -380,7 +387,7 @@ extern "C" int ganb_pack_small(const float* w_hwio, void* out_bf16, int taps, in
                                void* stream) {
   if (!w_hwio || !out_bf16) return fail(GANB_E_BADARG, "pack_small: null buffer");
   const int nl = small_is_ci ? co : ci;
-  pack_small_kernel<<<ceil_div(nl * kpad, 256), 256, 0, STREAM>>>(w_hwio, static_cast<__nv_bfloat16*>(out_bf16), taps, ci, co,
+  launch_k(pack_small_kernel, ceil_div(nl * kpad, 256), 256, 0, STREAM, w_hwio, static_cast<__nv_bfloat16*>(out_bf16), taps, ci, co,
                                                                  small_is_ci, kpad);
   GANB_CHECK_LAUNCH("pack_small_kernel");
   return 0;
@@ -389,7 +396,7 @@ extern "C" int ganb_pack_small(const float* w_hwio, void* out_bf16, int taps, in
 extern "C" int ganb_small_wgrad_scatter(const float* r, float* dw, int taps, int cs, int cl, int out_layout_clcs,
                                         const float* scale, float beta, void* stream) {
   if (!r || !dw) return fail(GANB_E_BADARG, "small_wgrad_scatter: null buffer");
-  small_wgrad_scatter_kernel<<<ceil_div(taps * cs * cl, 256), 256, 0, STREAM>>>(r, dw, taps, cs, cl, out_layout_clcs, scale, beta);
+  launch_k(small_wgrad_scatter_kernel, ceil_div(taps * cs * cl, 256), 256, 0, STREAM, r, dw, taps, cs, cl, out_layout_clcs, scale, beta);
   GANB_CHECK_LAUNCH("small_wgrad_scatter_kernel");
   return 0;
 }

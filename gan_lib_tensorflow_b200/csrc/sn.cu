@@ -67,6 +67,7 @@ __device__ __forceinline__ float row_dot(const float* __restrict__ row, const fl
 // Since b = W^T v = W^T (a / (|a|+eps)), the un-normalised bt = W^T a is all that the second stage needs.
 // work layout per CTA of the layer: [C] partial bt, then 1 float partial sa (stride C + 4).
 __global__ void __launch_bounds__(SN_THREADS) sn_fwd_rows_kernel(const ganb_sn_layer* __restrict__ layers, int count) {
+  pdl_wait();
   const int li = find_layer(layers, count, blockIdx.x);
   const ganb_sn_layer L = layers[li];
   const int K = L.k, C = L.c;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(SN_THREADS) sn_fwd_rows_kernel(const ganb_sn_l
 
 // Forward, stage 2 (one CTA per weight): reduce the partials, normalise, emit u', sigma.
 __global__ void __launch_bounds__(SN_THREADS) sn_fwd_finish_kernel(const ganb_sn_layer* __restrict__ layers, int assign) {
+  pdl_wait();
   const ganb_sn_layer L = layers[blockIdx.x];
   const int K = L.k, C = L.c;
   const int nblk = (K + SN_ROWS - 1) / SN_ROWS;
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(SN_THREADS) sn_fwd_finish_kernel(const ganb_sn
 
 // Backward, stage 1 (rows independent): partial <G,W>, t_k = row_k . b, partial sum v_k t_k.
 __global__ void __launch_bounds__(SN_THREADS) sn_bwd_rows_kernel(const ganb_sn_layer* __restrict__ layers, int count) {
+  pdl_wait();
   const int li = find_layer(layers, count, blockIdx.x);
   const ganb_sn_layer L = layers[li];
   const int K = L.k, C = L.c;
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(SN_THREADS) sn_bwd_rows_kernel(const ganb_sn_l
 
 // Backward, stage 2 (one small CTA per weight): scal[4] = coef (bbar = coef*b), scal[5] = sum v_k t_k.
 __global__ void __launch_bounds__(SN_THREADS) sn_bwd_finish_kernel(const ganb_sn_layer* __restrict__ layers) {
+  pdl_wait();
   const ganb_sn_layer L = layers[blockIdx.x];
   const int K = L.k, C = L.c;
   const int nblk = (K + SN_ROWS - 1) / SN_ROWS;
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(SN_THREADS) sn_bwd_finish_kernel(const ganb_sn
 
 // Backward, stage 3 (rows independent): dW += G/sigma + v (x) bbar + abar (x) u_used.
 __global__ void __launch_bounds__(SN_THREADS) sn_bwd_apply_kernel(const ganb_sn_layer* __restrict__ layers, int count) {
+  pdl_wait();
   const int li = find_layer(layers, count, blockIdx.x);
   const ganb_sn_layer L = layers[li];
   const int K = L.k, C = L.c;
@@ -259,6 +264,7 @@ __global__ void __launch_bounds__(SN_THREADS) sn_bwd_apply_kernel(const ganb_sn_
 
 // ------------------------------------------------------------------------------------------------ pack
 __global__ void __launch_bounds__(256) pack_weights_kernel(const ganb_pack_layer* __restrict__ layers, int nlayers) {
+  pdl_wait();
   __shared__ float tile[32][33];
   int l = 0;
   while (l + 1 < nlayers && static_cast<int>(blockIdx.x) >= layers[l + 1].tile_begin) ++l;
@@ -304,27 +310,27 @@ extern "C" int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, in
     cudaError_t e = cudaFuncSetAttribute(sn_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "sn_power_iter: %s", cudaGetErrorString(e));
   }
-  sn_fwd_rows_kernel<<<total_blocks, SN_THREADS, smem1, STREAM>>>(layers_dev, count);
+  launch_k(sn_fwd_rows_kernel, total_blocks, SN_THREADS, smem1, STREAM, layers_dev, count);
   GANB_CHECK_LAUNCH("sn_fwd_rows_kernel");
-  sn_fwd_finish_kernel<<<count, SN_THREADS, max_c * 4, STREAM>>>(layers_dev, assign);
+  launch_k(sn_fwd_finish_kernel, count, SN_THREADS, max_c * 4, STREAM, layers_dev, assign);
   GANB_CHECK_LAUNCH("sn_fwd_finish_kernel");
   return 0;
 }
 
 extern "C" int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int total_blocks, int max_c, void* stream) {
   if (!layers_dev || count <= 0 || total_blocks <= 0) return fail(GANB_E_BADARG, "sn_bwd: no layers");
-  sn_bwd_rows_kernel<<<total_blocks, SN_THREADS, max_c * 4, STREAM>>>(layers_dev, count);
+  launch_k(sn_bwd_rows_kernel, total_blocks, SN_THREADS, max_c * 4, STREAM, layers_dev, count);
   GANB_CHECK_LAUNCH("sn_bwd_rows_kernel");
-  sn_bwd_finish_kernel<<<count, SN_THREADS, 0, STREAM>>>(layers_dev);
+  launch_k(sn_bwd_finish_kernel, count, SN_THREADS, 0, STREAM, layers_dev);
   GANB_CHECK_LAUNCH("sn_bwd_finish_kernel");
-  sn_bwd_apply_kernel<<<total_blocks, SN_THREADS, 2 * max_c * 4, STREAM>>>(layers_dev, count);
+  launch_k(sn_bwd_apply_kernel, total_blocks, SN_THREADS, 2 * max_c * 4, STREAM, layers_dev, count);
   GANB_CHECK_LAUNCH("sn_bwd_apply_kernel");
   return 0;
 }
 
 extern "C" int ganb_pack_weights(const ganb_pack_layer* layers_dev, int count, int total_tiles, void* stream) {
   if (!layers_dev || count <= 0 || total_tiles <= 0) return fail(GANB_E_BADARG, "pack_weights: no layers");
-  pack_weights_kernel<<<total_tiles, 256, 0, STREAM>>>(layers_dev, count);
+  launch_k(pack_weights_kernel, total_tiles, 256, 0, STREAM, layers_dev, count);
   GANB_CHECK_LAUNCH("pack_weights_kernel");
   return 0;
 }
