@@ -101,18 +101,33 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
         v[j].z = apply_act(v[j].z, p.act); v[j].w = apply_act(v[j].w, p.act);
       }
     }
+    if (p.out_bf16 && (cout % 8 == 0) && (NC % 8 == 0)) {
+      // 16-byte stores: 8 bf16 channels per instruction (half the store instructions of the 8-byte form)
 #pragma unroll
-    for (int j = 0; j < NC; j += 4) {
-      if (co_base + j >= cout) break;
-      if (p.out_bf16) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v[j / 4].x, v[j / 4].y);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(v[j / 4].z, v[j / 4].w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + j) = pk;
-      } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + j) = v[j / 4];
+      for (int j = 0; j < NC; j += 8) {
+        if (co_base + j >= cout) break;
+        const float4 a = v[j / 4], b = v[j / 4 + 1];
+        __nv_bfloat162 q0 = __floats2bfloat162_rn(a.x, a.y), q1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 q2 = __floats2bfloat162_rn(b.x, b.y), q3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
+        pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + j) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        if (co_base + j >= cout) break;
+        if (p.out_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[j / 4].x, v[j / 4].y);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(v[j / 4].z, v[j / 4].w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + j) = pk;
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + j) = v[j / 4];
+        }
       }
     }
   } else {

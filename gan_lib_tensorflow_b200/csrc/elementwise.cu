@@ -475,6 +475,387 @@ __global__ void __launch_bounds__(256, 3) norm_act_bwd_apply_kernel(const NormAc
   }
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 x 8 paths
+// All-bf16 variants of the statistics / normalise kernels (input, upstream gradient and output in bf16, c % 8 == 0):
+// a thread owns 8 channels, i.e. one 16-byte load per tensor per pixel.  The generic kernels above move 8 bytes per
+// load on bf16 data and were bound by loads in flight, not by HBM (same time for bf16 as for fp32 inputs).
+__device__ __forceinline__ void cvt8(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return r;
+}
+__device__ __forceinline__ void ldf8(const float* p, float (&f)[8]) {
+  const float4 a = ld4(p), b = ld4(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// block-level sum over the `lanes` row lanes of 16 per-thread values; result valid in lane 0 threads (ry == 0)
+__device__ __forceinline__ void lanes_sum16(float (&a)[8], float (&b)[8], int lanes, int cols_per_pass, int cx, int ry,
+                                            float (*sh)[17]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sh[threadIdx.x][j] = a[j]; sh[threadIdx.x][8 + j] = b[j]; }
+  __syncthreads();
+  if (ry == 0) {
+    for (int l = 1; l < lanes; ++l) {
+      const float* o = sh[l * cols_per_pass + cx];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += o[j]; b[j] += o[8 + j]; }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+bn_stats_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int rows_per_group, int c, int chunks,
+                           int rows_per_chunk, float* __restrict__ partial) {
+  pdl_wait();
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int v = c >> 3;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(rows_per_group, r0 + rows_per_chunk);
+  const __nv_bfloat16* xg = x + static_cast<int64_t>(g) * rows_per_group * c;
+  __shared__ float sh[256][17];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (col < v && ry < lanes) {
+      constexpr int U = 4;
+      for (int r = r0 + ry; r < r1; r += lanes * U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          raw[u] = (r + u * lanes < r1) ? ldg16(xg + static_cast<int64_t>(r + u * lanes) * c + col * 8)
+                                        : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float a[8];
+          cvt8(raw[u], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s[j] += a[j]; q[j] += a[j] * a[j]; }
+        }
+      }
+    }
+    lanes_sum16(s, q, lanes, cols_per_pass, cx, ry, sh);
+    if (ry == 0 && col < v) {
+      float* out = partial + (static_cast<int64_t>(g) * chunks + chunk) * 2 * c;
+      st4(out + col * 8, make_float4(s[0], s[1], s[2], s[3]));
+      st4(out + col * 8 + 4, make_float4(s[4], s[5], s[6], s[7]));
+      st4(out + c + col * 8, make_float4(q[0], q[1], q[2], q[3]));
+      st4(out + c + col * 8 + 4, make_float4(q[4], q[5], q[6], q[7]));
+    }
+  }
+}
+
+template <bool UPS>
+__global__ void __launch_bounds__(256) norm_act_fwd_v8_kernel(const NormActFwd p, int pix_per_chunk) {
+  pdl_wait();
+  const int ni = blockIdx.y;
+  const int v = p.c >> 3;
+  const int cols = min(v, 256);
+  const int lanes = 256 / cols;
+  const int cx = threadIdx.x % cols, ly = threadIdx.x / cols;
+  if (ly >= lanes) return;
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * pix_per_chunk, p1 = min(hw, p0 + pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(p.x);
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out);
+  for (int cb = 0; cb < v; cb += cols) {
+    const int col = cb + cx;
+    if (col >= v) continue;
+    const int c8 = col * 8;
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sf[j] = 0.f; }
+    if (p.mean) {
+      float m[8], r[8];
+      ldf8(p.mean + g * p.c + c8, m);
+      ldf8(p.rstd + g * p.c + c8, r);
+      float ga[8], be[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ga[j] = 1.f; be[j] = 0.f; }
+      if (p.gamma) {
+        const int row = p.labels ? __ldg(p.labels + ni) : 0;
+        ldf8(p.gamma + static_cast<int64_t>(row) * p.c + c8, ga);
+        ldf8(p.beta + static_cast<int64_t>(row) * p.c + c8, be);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = r[j] * ga[j]; sf[j] = be[j] - m[j] * sc[j]; }
+    }
+    const __nv_bfloat16* xb = xp + static_cast<int64_t>(ni) * hw * p.c + c8;
+    constexpr int U = 4;
+    for (int px = p0 + ly; px < p1; px += lanes * U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = px + u * lanes;
+        raw[u] = (q < p1) ? ldg16(xb + static_cast<int64_t>(q) * p.c) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = px + u * lanes;
+        if (q >= p1) break;
+        float a[8];
+        cvt8(raw[u], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = act_f(a[j] * sc[j] + sf[j], p.act);
+        const uint4 y = pack8(a);
+        const int64_t pix = static_cast<int64_t>(ni) * hw + q;
+        if (!UPS) {
+          stg16(op + pix * p.out_cstride + c8, y);
+        } else {
+          const int hi = q / p.w, wi = q - hi * p.w;
+          const int ow = 2 * p.w;
+          const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
+          stg16(op + base * p.out_cstride + c8, y);
+          stg16(op + (base + 1) * p.out_cstride + c8, y);
+          stg16(op + (base + ow) * p.out_cstride + c8, y);
+          stg16(op + (base + ow + 1) * p.out_cstride + c8, y);
+        }
+      }
+    }
+  }
+}
+
+// per-thread constants of the backward pass for 8 channels of one sample: xhat = a*r - mr ; y = xhat*ga + be
+struct BwdConst8 {
+  float r[8], mr[8], ga[8], be[8];
+};
+template <bool NORM>
+__device__ __forceinline__ void bwd_const8(const NormActBwd& p, int ni, int g, int c8, BwdConst8& k) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { k.r[j] = 1.f; k.mr[j] = 0.f; k.ga[j] = 1.f; k.be[j] = 0.f; }
+  if (NORM) {
+    float m[8];
+    ldf8(p.mean + g * p.c + c8, m);
+    ldf8(p.rstd + g * p.c + c8, k.r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k.mr[j] = m[j] * k.r[j];
+    if (p.gamma) {
+      const int row = p.labels ? __ldg(p.labels + ni) : 0;
+      ldf8(p.gamma + static_cast<int64_t>(row) * p.c + c8, k.ga);
+      ldf8(p.beta + static_cast<int64_t>(row) * p.c + c8, k.be);
+    }
+  }
+}
+// raw upstream gradient of 8 channels at pixel px of sample ni (UPS: the four replicas, summed by the caller)
+template <bool UPS>
+__device__ __forceinline__ void bwd_load_dz8(const NormActBwd& p, int ni, int px, int c8, uint4 (&raw)[UPS ? 4 : 1]) {
+  const __nv_bfloat16* dz = static_cast<const __nv_bfloat16*>(p.dz);
+  if (!UPS) {
+    raw[0] = ldg16(dz + (static_cast<int64_t>(ni) * p.h * p.w + px) * p.dz_cstride + c8);
+  } else {
+    const int hi = px / p.w, wi = px - hi * p.w;
+    const int ow = 2 * p.w;
+    const int64_t base = (static_cast<int64_t>(ni) * 2 * p.h + 2 * hi) * ow + 2 * wi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      raw[k] = ldg16(dz + (base + (k >> 1) * ow + (k & 1)) * p.dz_cstride + c8);
+  }
+}
+template <bool UPS>
+__device__ __forceinline__ void bwd_sum_dz8(const uint4 (&raw)[UPS ? 4 : 1], float (&dz)[8]) {
+  cvt8(raw[0], dz);
+  if (UPS) {
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      float t[8];
+      cvt8(raw[k], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] += t[j];
+    }
+  }
+}
+
+template <bool UPS>
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_v8_kernel(const NormActBwd p) {
+  pdl_wait();
+  const int ni = blockIdx.y, chunk = blockIdx.x;
+  const int v = p.c >> 3;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int hw = p.h * p.w;
+  const int p0 = chunk * p.pix_per_chunk, p1 = min(hw, p0 + p.pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(p.x);
+  __shared__ float sh[256][17];
+  constexpr int U = UPS ? 2 : 4;
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float sa[8], sb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sa[j] = 0.f; sb[j] = 0.f; }
+    if (col < v && ry < lanes) {
+      BwdConst8 k;
+      bwd_const8<true>(p, ni, g, col * 8, k);
+      for (int px = p0 + ry; px < p1; px += lanes * U) {
+        uint4 xa[U];
+        uint4 dzr[U][UPS ? 4 : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int qx = px + u * lanes;
+          if (qx < p1) {
+            xa[u] = ldg16(xp + (static_cast<int64_t>(ni) * hw + qx) * p.c + col * 8);
+            bwd_load_dz8<UPS>(p, ni, qx, col * 8, dzr[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (px + u * lanes >= p1) break;
+          float a[8], dz[8];
+          cvt8(xa[u], a);
+          bwd_sum_dz8<UPS>(dzr[u], dz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = a[j] * k.r[j] - k.mr[j];
+            const float dy = dz[j] * dact_f(xh * k.ga[j] + k.be[j], p.act);
+            sa[j] += dy;
+            sb[j] += dy * xh;
+          }
+        }
+      }
+    }
+    lanes_sum16(sa, sb, lanes, cols_per_pass, cx, ry, sh);
+    if (ry == 0 && col < v) {
+      float* out = p.part + (static_cast<int64_t>(ni) * p.chunks + chunk) * 2 * p.c;
+      st4(out + col * 8, make_float4(sa[0], sa[1], sa[2], sa[3]));
+      st4(out + col * 8 + 4, make_float4(sa[4], sa[5], sa[6], sa[7]));
+      st4(out + p.c + col * 8, make_float4(sb[0], sb[1], sb[2], sb[3]));
+      st4(out + p.c + col * 8 + 4, make_float4(sb[4], sb[5], sb[6], sb[7]));
+    }
+  }
+}
+
+template <bool NORM, bool UPS>
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8_kernel(const NormActBwd p, int pix_per_chunk) {
+  pdl_wait();
+  const int ni = blockIdx.y;
+  const int v = p.c >> 3;
+  const int cols = min(v, 256);
+  const int lanes = 256 / cols;
+  const int cx = threadIdx.x % cols, ly = threadIdx.x / cols;
+  if (ly >= lanes) return;
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * pix_per_chunk, p1 = min(hw, p0 + pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(p.x);
+  const __nv_bfloat16* addp = static_cast<const __nv_bfloat16*>(p.add);
+  __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(p.dx);
+  constexpr int U = UPS ? 2 : 4;
+  for (int cb = 0; cb < v; cb += cols) {
+    const int col = cb + cx;
+    if (col >= v) continue;
+    const int c8 = col * 8;
+    float t1[8], t2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
+    if (NORM) {
+      ldf8(p.s1 + g * p.c + c8, t1);
+      ldf8(p.s2 + g * p.c + c8, t2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { t1[j] *= p.inv_count; t2[j] *= p.inv_count; }
+    }
+    BwdConst8 k;
+    bwd_const8<NORM>(p, ni, g, c8, k);
+    for (int px = p0 + ly; px < p1; px += lanes * U) {
+      uint4 xa[U], ad[U];
+      uint4 dzr[U][UPS ? 4 : 1];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int qx = px + u * lanes;
+        if (qx < p1) {
+          const int64_t pix = static_cast<int64_t>(ni) * hw + qx;
+          xa[u] = ldg16(xp + pix * p.c + c8);
+          bwd_load_dz8<UPS>(p, ni, qx, c8, dzr[u]);
+          if (addp) ad[u] = ldg16(addp + pix * p.c + c8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int qx = px + u * lanes;
+        if (qx >= p1) break;
+        const int64_t pix = static_cast<int64_t>(ni) * hw + qx;
+        float a[8], dz[8], dx[8];
+        cvt8(xa[u], a);
+        bwd_sum_dz8<UPS>(dzr[u], dz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = a[j] * k.r[j] - k.mr[j];
+          const float dy = dz[j] * dact_f(xh * k.ga[j] + k.be[j], p.act);
+          dx[j] = NORM ? k.r[j] * (k.ga[j] * dy - t1[j] - xh * t2[j]) : dy;
+        }
+        if (addp) {
+          float q[8];
+          cvt8(ad[u], q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dx[j] += q[j];
+        }
+        stg16(dxp + pix * p.c + c8, pack8(dx));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int c, int rows_per_chunk,
+                         float* __restrict__ partial) {
+  pdl_wait();
+  const int chunk = blockIdx.x;
+  const int v = c >> 3;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int64_t r0 = static_cast<int64_t>(chunk) * rows_per_chunk;
+  const int64_t r1 = min(rows, r0 + rows_per_chunk);
+  __shared__ float sh[256][17];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float s[8], z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; z[j] = 0.f; }
+    if (col < v && ry < lanes) {
+      constexpr int U = 4;
+      for (int64_t r = r0 + ry; r < r1; r += lanes * U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          raw[u] = (r + u * lanes < r1) ? ldg16(x + (r + u * lanes) * c + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float a[8];
+          cvt8(raw[u], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] += a[j];
+        }
+      }
+    }
+    lanes_sum16(s, z, lanes, cols_per_pass, cx, ry, sh);
+    if (ry == 0 && col < v) {
+      st4(partial + static_cast<int64_t>(chunk) * c + col * 8, make_float4(s[0], s[1], s[2], s[3]));
+      st4(partial + static_cast<int64_t>(chunk) * c + col * 8 + 4, make_float4(s[4], s[5], s[6], s[7]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ pooling
 // out[n,h/2,w/2,c] = mean of the 2x2 block (+ add[n,h/2,w/2,c])
 template <typename TIn, typename TOut>
@@ -1015,7 +1396,10 @@ extern "C" int ganb_bn_stats(const void* x, int x_dtype, int n, int hw, int c, i
   const int rows_per_chunk = ceil_div(rows_per_group, chunks);
   const int used = ceil_div(rows_per_group, rows_per_chunk);
   const dim3 grid(used, groups);
-  if (x_dtype == GANB_BF16)
+  if (x_dtype == GANB_BF16 && c % 8 == 0)
+    launch_k(bn_stats_partial_v8_kernel, grid, 256, 0, STREAM, static_cast<const __nv_bfloat16*>(x), rows_per_group, c, used,
+             rows_per_chunk, static_cast<float*>(workspace));
+  else if (x_dtype == GANB_BF16)
     launch_k(bn_stats_partial_kernel<__nv_bfloat16>, grid, 256, 0, STREAM, static_cast<const __nv_bfloat16*>(x), rows_per_group, c,
                                                                       used, rows_per_chunk, static_cast<float*>(workspace));
   else
@@ -1051,7 +1435,10 @@ extern "C" int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
   const int chunks = bwd_chunks(n, h * w);
   const int ppc = ceil_div(h * w, chunks);
-  if (p.x_bf16) launch_k(norm_act_fwd_kernel<__nv_bfloat16>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
+  const bool v8 = p.x_bf16 && p.out_bf16 && !p.out_raw && c % 8 == 0 && p.out_cstride % 8 == 0;
+  if (v8 && upsample) launch_k(norm_act_fwd_v8_kernel<true>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
+  else if (v8) launch_k(norm_act_fwd_v8_kernel<false>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
+  else if (p.x_bf16) launch_k(norm_act_fwd_kernel<__nv_bfloat16>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
   else launch_k(norm_act_fwd_kernel<float>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
   GANB_CHECK_LAUNCH("norm_act_fwd_kernel");
   return 0;
@@ -1103,6 +1490,8 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
   p.act = act; p.upsample = upsample;
   p.add = add; p.add_bf16 = (add_dtype == GANB_BF16); p.dx = dx; p.dx_bf16 = (dx_dtype == GANB_BF16);
   p.part = nullptr; p.s1 = nullptr; p.s2 = nullptr; p.chunks = 0; p.pix_per_chunk = 0; p.inv_count = 0.f;
+  // all-bf16 fast path: 8 channels per thread
+  const bool v8 = p.x_bf16 && p.dz_bf16 && p.dx_bf16 && (!add || p.add_bf16) && c % 8 == 0 && p.dz_cstride % 8 == 0;
   if (mean) {
     if (!workspace) return fail(GANB_E_BADARG, "norm_act_bwd: workspace required with normalisation");
     const int hw = h * w;
@@ -1114,7 +1503,9 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
     float* s1 = sums + 2LL * n * c;
     float* s2 = s1 + static_cast<int64_t>(groups) * c;
     const dim3 grid(p.chunks, n);
-    if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
+    if (v8 && upsample) launch_k(norm_act_bwd_reduce_v8_kernel<true>, grid, 256, 0, STREAM, p);
+    else if (v8) launch_k(norm_act_bwd_reduce_v8_kernel<false>, grid, 256, 0, STREAM, p);
+    else if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
     else launch_bwd_reduce<float>(p, grid, STREAM);
     GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
     launch_k(norm_act_bwd_finalize_kernel, dim3(ceil_div(c, 8), groups), 256, 0, STREAM, p.part, n, c, p.chunks, groups, gamma,
@@ -1132,7 +1523,15 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
     const int chunks2 = bwd_chunks(n, h * w);
     const int ppc = ceil_div(h * w, chunks2);
     const dim3 grid(ceil_div(h * w, ppc), n);
-    if (p.x_bf16) launch_bwd_apply<__nv_bfloat16>(p, mean != nullptr, grid, ppc, STREAM);
+    if (v8) {
+      const int idx = (mean ? 2 : 0) | (upsample ? 1 : 0);
+      switch (idx) {
+        case 0: launch_k(norm_act_bwd_apply_v8_kernel<false, false>, grid, 256, 0, STREAM, p, ppc); break;
+        case 1: launch_k(norm_act_bwd_apply_v8_kernel<false, true>, grid, 256, 0, STREAM, p, ppc); break;
+        case 2: launch_k(norm_act_bwd_apply_v8_kernel<true, false>, grid, 256, 0, STREAM, p, ppc); break;
+        default: launch_k(norm_act_bwd_apply_v8_kernel<true, true>, grid, 256, 0, STREAM, p, ppc); break;
+      }
+    } else if (p.x_bf16) launch_bwd_apply<__nv_bfloat16>(p, mean != nullptr, grid, ppc, STREAM);
     else launch_bwd_apply<float>(p, mean != nullptr, grid, ppc, STREAM);
   }
   GANB_CHECK_LAUNCH("norm_act_bwd_apply_kernel");
@@ -1273,7 +1672,11 @@ static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float*
     launch_k(colsum_narrow_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
     GANB_CHECK_LAUNCH("colsum_narrow_kernel");
   } else {
-    launch_k(colsum_partial_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
+    if (sizeof(TIn) == 2 && c % 8 == 0)
+      launch_k(colsum_partial_v8_kernel, used, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), rows, c, rows_per_chunk,
+               static_cast<float*>(workspace));
+    else
+      launch_k(colsum_partial_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
     GANB_CHECK_LAUNCH("colsum_partial_kernel");
   }
   launch_k(colsum_finalize_kernel, ceil_div(c, 8), 256, 0, s, static_cast<float*>(workspace), c, used, beta, out);

@@ -262,6 +262,60 @@ def test_cond_batchnorm_relu_fused(env, n, h, c, groups, upsample):
     check(prod, refs, tol_fp32=5e-5)
 
 
+@pytest.mark.parametrize("n,h,c,upsample,act", [(8, 8, 256, False, "relu"), (8, 4, 1024, True, "relu"),
+                                                  (6, 16, 128, True, "lrelu"), (4, 8, 64, False, None)])
+def test_cond_batchnorm_bf16_storage_paths(env, n, h, c, upsample, act):
+    """bf16-stored input, bf16 upstream gradient, bf16 dx (the 8-channels-per-thread kernels of the G path) against
+    fp64 math on the same bf16-representable values."""
+    store, _ = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.framework import Var
+
+    rs = np.random.RandomState(31)
+    x = _bf16_repr((rs.standard_normal((n, h, h, c)) * 1.3 + 0.4).astype("float32"))
+    labels = rs.randint(0, 10, size=n).astype("int32")
+    gam = (1.0 + 0.3 * rs.standard_normal((10, c))).astype("float32")
+    bet = (0.2 * rs.standard_normal((10, c))).astype("float32")
+    s = 2 if upsample else 1
+    cot = _bf16_repr(rs.standard_normal((n, s * h, s * h, c)).astype("float32"))
+    with store.variable_scope("T"):
+        g_v = store.get_variable("scale", initializer=lambda _s: gam)
+        b_v = store.get_variable("offset", initializer=lambda _s: bet)
+    for v in (g_v, b_v):
+        v.grad = torch.zeros_like(v.data)
+    xv = Var(torch.from_numpy(x).cuda().to(torch.bfloat16), requires_grad=True)
+    with store.stat_towers(2), store.gradient_tape() as tape:
+        out, _ = F.norm_act(xv, stats="batch", eps=1e-5, gamma=g_v, beta=b_v, labels=torch.from_numpy(labels).cuda(),
+                            act=act, upsample=upsample, out_dtype=torch.bfloat16)
+        tape.backward(out, grad=torch.from_numpy(cot).cuda().to(torch.bfloat16))
+    torch.cuda.synchronize()
+    # fp64 reference with two statistic towers
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    gt = torch.from_numpy(gam).double().requires_grad_(True)
+    bt = torch.from_numpy(bet).double().requires_grad_(True)
+    ys = []
+    for t in range(2):
+        sl = slice(t * n // 2, (t + 1) * n // 2)
+        xs = xt[sl]
+        mean = xs.mean(dim=(0, 1, 2), keepdim=True)
+        var = xs.var(dim=(0, 1, 2), unbiased=False, keepdim=True)
+        lab = torch.from_numpy(labels[sl]).long()
+        y = (xs - mean) * torch.rsqrt(var + 1e-5) * gt[lab][:, None, None, :] + bt[lab][:, None, None, :]
+        if act == "relu":
+            y = torch.relu(y)
+        elif act == "lrelu":
+            y = torch.where(y >= 0, y, 0.2 * y)
+        if upsample:
+            y = y.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+        ys.append(y)
+    yo = torch.cat(ys)
+    dx, dg, db = torch.autograd.grad(yo, [xt, gt, bt], torch.from_numpy(cot).double())
+    assert rel(out.data.float().cpu().numpy(), yo.detach().numpy()) < 4e-3          # bf16 output rounding
+    assert rel(xv.grad.float().cpu().numpy(), dx.numpy()) < 6e-3                    # bf16 dx rounding
+    assert rel(g_v.grad.cpu().numpy(), dg.numpy()) < 1e-4
+    assert rel(b_v.grad.cpu().numpy(), db.numpy()) < 1e-4
+
+
 def test_batch_norm_and_instance_norm(env):
     store, tfshim = env
     from gan_lib_tensorflow_b200.common.ops import normalization as P
