@@ -217,9 +217,17 @@ class Trainer:
             tape.backward(loss)
         self.d_loss.copy_(loss.data)
 
+    def _repack(self, root):
+        """bf16 operand copies of the updated network, refreshed right behind its Adam step (so the compute graphs
+        of later steps never re-pack a network that did not change, e.g. G during the N_CRITIC critic steps)."""
+        group = self.store.pack_groups.get(root)
+        if group is not None and group.entries:
+            group.refresh()
+
     def _d_update(self):
         self.disc_opt.apply(1.0 / self.world_size)
         self.store.bump('Discriminator')
+        self._repack('Discriminator')
 
     def _g_compute(self):
         """Forward + backward of the generator step (gan_cifar_resnet.py:462-498, 523): gradients of gen_cost."""
@@ -236,6 +244,7 @@ class Trainer:
     def _g_update(self):
         self.gen_opt.apply(1.0 / self.world_size)
         self.store.bump('Generator')
+        self._repack('Generator')
 
     def _d_body(self):
         self._d_compute()
@@ -249,12 +258,13 @@ class Trainer:
             self.grad_allreduce(self.store.flat['Generator'].grads)
         self._g_update()
 
-    def _invalidate_caches(self):
+    def _invalidate_caches(self, packs=True):
         for g in self.store.sn_groups.values():
             g.valid_for = None
             g.fresh_for = None
-        for g in self.store.pack_groups.values():
-            g.valid_for = None
+        if packs:
+            for g in self.store.pack_groups.values():
+                g.valid_for = None
 
     def capture(self):
         """Captures the training ops into CUDA graphs (static shapes; launch latency is first-order at batch 64).
@@ -264,15 +274,18 @@ class Trainer:
         parts = (("d_compute", self._d_compute), ("d_update", self._d_update),
                  ("g_compute", self._g_compute), ("g_update", self._g_update))
         self.graph_launches = {}
+        for root in ('Generator', 'Discriminator'):   # operand copies are current before any compute graph runs
+            self._repack(root)
         for name, body in parts:
-            self._invalidate_caches()
+            # spectral-norm state is re-evaluated inside every compute graph; weight packs only behind an update
+            self._invalidate_caches(packs=False)
             before = K.launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 body()
             self._graphs[name] = g
             self.graph_launches[name] = K.launch_count() - before
-        self._invalidate_caches()
+        self._invalidate_caches(packs=False)
 
     def _run(self, which):
         if (which + "_compute") in self._graphs:

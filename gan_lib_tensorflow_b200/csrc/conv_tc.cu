@@ -1135,10 +1135,29 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   if (p.res_up2 && ((ho | wo) & 1)) return fail(GANB_E_BADARG, "conv2d_igemm: upsampled residual needs even ho, wo");
   p.out = y; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
 
-  // choose the N tile: whole Cout when it fits, shrunk while the grid cannot fill the machine
+  // choose the N tile with a two-term cost model (cycles): tensor time = waves x k-iterations x MMA cycles of a tile,
+  // operand time = bytes crossing L2->SMEM / what the chip (~6500 B/clk measured) or the active SMs (~64 B/clk
+  // each) can ingest.  Small-M, deep-K layers (8x8 images, K = 9216) want FEW LARGE tiles even when that leaves SMs
+  // idle: halving BN doubles the activation re-reads.
   int bn_tile = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  while (bn_tile > 64 && m_tiles * ceil_div(cout, bn_tile) < sm_count()) bn_tile >>= 1;
+  if (bn_tile > 64) {
+    const double kit = static_cast<double>(kh) * kw * p.kchunks;
+    const double a_bytes = halo ? 16384.0 * 1.5 / (kh * kw) : 16384.0;   // per k-iteration of one tile
+    double best = 0;
+    int best_bn = bn_tile;
+    for (int bn = bn_tile; bn >= 64; bn >>= 1) {
+      const double tiles = static_cast<double>(m_tiles) * ceil_div(cout, bn);
+      const double active = tiles < sm_count() ? tiles : sm_count();
+      const double waves = ceil_div(static_cast<int>(tiles), sm_count());
+      const double t_mma = waves * kit * 4.0 * (bn / 2.0);
+      const double rate = 6500.0 < 64.0 * active ? 6500.0 : 64.0 * active;
+      const double t_l2 = tiles * kit * (a_bytes + bn * 128.0) / rate;
+      const double t = (t_mma > t_l2 ? t_mma : t_l2) + 3000.0 * waves;     // + per-tile epilogue / ramp
+      if (best == 0 || t < best) { best = t; best_bn = bn; }
+    }
+    bn_tile = best_bn;
+  }
 
   // CTA pairs (cta_group::2) halve the filter traffic per SM: used when there is at least one wave of pair tiles
   const int pair_bn = cout > 128 ? 256 : 128;

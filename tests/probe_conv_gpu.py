@@ -190,6 +190,11 @@ def main():
     time_fprop(128, 32, 32, 128, 128, 3, 1)
     time_fprop(64, 16, 16, 256, 256, 3, 1)
     time_fprop(64, 8, 8, 1024, 256, 3, 1)
+    time_fprop(128, 8, 8, 1024, 256, 3, 1)
+    time_fprop(128, 8, 8, 256, 256, 3, 1)
+    time_fprop(128, 8, 8, 128, 128, 3, 1)
+    time_fprop(128, 8, 8, 256, 1024, 3, 1)
+    time_fprop(128, 16, 16, 256, 128, 1, 0)
     return 0 if all(results) else 1
 
 
