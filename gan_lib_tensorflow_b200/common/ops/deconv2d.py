@@ -1,12 +1,13 @@
 """Transposed convolution with the reference's signature (common/ops/deconv2d.py:29-118).
 
-The reference has no call-site for it; the op is the data gradient of a stride-2 convolution, which needs the
-strided tensor-core path that is not built yet.  Variables are created with the reference's
-initialisation so that checkpoints keep their names and shapes; the arithmetic raises."""
+The reference has no call-site for it.  The op is the data gradient of a stride-2 convolution: it runs as the
+stride-1 tensor-core kernel over the zero-dilated input (functional.conv2d_transpose); its own backward uses the
+strided forward / filter-gradient kernels.  weight-norm (deconv2d.py:87-96) is not built."""
 from __future__ import annotations
 
 import numpy as np
 
+from ... import functional as F
 from ...framework import get_store
 
 _default_weightnorm = False
@@ -41,10 +42,15 @@ def Deconv2D(inputs, in_channels, output_channels, filter_size, stride=2, paddin
         stdev = np.sqrt((4. if he_init else 2.) / (fan_in + fan_out))
         if _weights_stdev is not None:
             stdev = _weights_stdev
-        store.get_variable(name='Filters', initializer=lambda _s: np.random.uniform(
+        filters = store.get_variable(name='Filters', initializer=lambda _s: np.random.uniform(
             low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3),
             size=(filter_size, filter_size, output_channels, in_channels)).astype('float32') * np.float32(gain))
+        if weight_norm is None:
+            weight_norm = _default_weightnorm
+        if weight_norm:
+            raise NotImplementedError('weight-norm is not built (SURVEY 8(f) rank 4)')
+        _biases = None
         if biases:
-            store.get_variable(name='Biases', shape=[output_channels, ],
-                               initializer=lambda s: np.zeros(s, dtype='float32'))
-        raise NotImplementedError('Deconv2D arithmetic needs the stride-2 dgrad kernel (SURVEY 8(f)); not built yet')
+            _biases = store.get_variable(name='Biases', shape=[output_channels, ],
+                                         initializer=lambda s: np.zeros(s, dtype='float32'))
+        return F.conv2d_transpose(F.as_var(inputs), filters, _biases, filter_size, filter_size, stride, padding)

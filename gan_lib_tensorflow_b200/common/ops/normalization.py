@@ -70,6 +70,7 @@ def instance_norm(inputs, epsilon=1e-06, act=None, upsample=False, out_dtype=tor
         return out
 
 
-def pixel_norm(inputs, eps=1e-8):
-    """common/ops/normalization.py:125-140 (PGGAN)."""
-    raise NotImplementedError('pixel_norm kernel is not built yet (PGGAN, SURVEY 8(f))')
+def pixel_norm(inputs, eps=1e-8, act=None, out_dtype=None):
+    """common/ops/normalization.py:125-140 (PGGAN): inputs * rsqrt(mean over channels of inputs^2 + eps).
+    `act` fuses the leaky ReLU that follows it in PGGAN/model_nvidia.py:63-68."""
+    return F.pixel_norm(F.as_var(inputs), eps=eps, act=act, out_dtype=out_dtype)

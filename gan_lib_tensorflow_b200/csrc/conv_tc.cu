@@ -815,7 +815,7 @@ constexpr int PB = 64;  // pixels per pipeline stage (4 UMMA K-steps of 16)
 struct WgradParams {
   int N, Ho, Wo;  // dy spatial extent
   int Cin, Cout;
-  int kw, taps, pad_t, pad_l;
+  int kw, taps, pad_t, pad_l, stride;
   int bw, bh, bn;          // pixel box, bw*bh*bn == PB
   int pb_w, pb_h, pb_n;    // pixel blocks per dim
   int num_pb, splits, pb_per_split;
@@ -890,7 +890,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint8_t* b = sB + stage * B_BYTES;
 #pragma unroll
         for (int j = 0; j < BM / 64; ++j)
-          tma_load_4d(a + j * BOX_BYTES, &tmX, &full[stage], ci0 + 64 * j, w0 + s - p.pad_l, h0 + r - p.pad_t, n0);
+          tma_load_4d(a + j * BOX_BYTES, &tmX, &full[stage], ci0 + 64 * j, w0 * p.stride + s - p.pad_l,
+                      h0 * p.stride + r - p.pad_t, n0);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
           tma_load_4d(b + j * BOX_BYTES, &tmDY, &full[stage], co0 + 64 * j, w0, h0, n0);
@@ -1110,7 +1111,7 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || ho <= 0 || wo <= 0 || cout <= 0 || kh <= 0 || kw <= 0)
     return fail(GANB_E_BADARG, "conv2d_igemm: non-positive dimension");
   if (cin % 8 != 0) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm: cin=%d must be a multiple of 8", cin);
-  if (stride != 1) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm: stride=%d not supported yet", stride);
+  if (stride < 1 || stride > 4) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm: stride=%d (1..4 supported)", stride);
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15)
     return fail(GANB_E_BADARG, "conv2d_igemm: x / wp must be 16-byte aligned");
 
@@ -1119,7 +1120,8 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   p.taps = kh * kw; p.kw = kw;
   p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
   // halo path: every tap reads one shared-memory halo tile (needs 8-pixel row groups: 16 x 8 tiles per image)
-  const bool halo = (kh * kw > 1) && ho >= HALO_BH && wo >= HALO_BW && (kh + HALO_BH - 1) <= 256;
+  // strided convolutions gather every stride-th pixel through the TMA element strides of the per-tap box
+  const bool halo = (kh * kw > 1) && stride == 1 && ho >= HALO_BH && wo >= HALO_BW && (kh + HALO_BH - 1) <= 256;
   if (halo) {
     p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1;
   } else {
@@ -1170,8 +1172,12 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
-    const uint32_t box[4] = {BK, (uint32_t)(halo ? halo_w : p.bw), (uint32_t)(halo ? halo_h : p.bh), (uint32_t)p.bn};
-    int rc = encode_tmap_bf16(&tmA, x, 4, dims, strides, box, nullptr);
+    // with element strides the box is given as the traversed extent: (b - 1) * stride + 1 input pixels -> b loaded
+    const uint32_t box[4] = {BK, (uint32_t)(halo ? halo_w : (p.bw - 1) * stride + 1),
+                             (uint32_t)(halo ? halo_h : (p.bh - 1) * stride + 1), (uint32_t)p.bn};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (box[1] > 256 || box[2] > 256) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm: tile extent %u x %u exceeds the TMA box limit", box[1], box[2]);
+    int rc = encode_tmap_bf16(&tmA, x, 4, dims, strides, box, stride > 1 ? estr : nullptr);
     if (rc) return rc;
   }
   {
@@ -1268,7 +1274,7 @@ extern "C" int64_t ganb_conv2d_wgrad_workspace(int n, int h, int w, int cin, int
 }
 
 extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void* workspace, int n, int h, int w,
-                                 int cin, int ho, int wo, int cout, int kh, int kw, int pad_t, int pad_l,
+                                 int cin, int ho, int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
                                  const float* scale, float beta, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !dy || !dw || !workspace) return fail(GANB_E_BADARG, "conv2d_wgrad: null buffer");
@@ -1276,16 +1282,18 @@ extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void*
     return fail(GANB_E_UNSUPPORTED, "conv2d_wgrad: cin=%d and cout=%d must be multiples of 8", cin, cout);
   WgradPlan plan;
   plan_wgrad(n, ho, wo, cin, cout, kh, kw, &plan);
+  if (stride < 1 || stride > 4) return fail(GANB_E_UNSUPPORTED, "conv2d_wgrad: stride=%d (1..4 supported)", stride);
   WgradParams& p = plan.p;
-  p.pad_t = pad_t; p.pad_l = pad_l;
+  p.pad_t = pad_t; p.pad_l = pad_l; p.stride = stride;
   p.partial = static_cast<float*>(workspace);
 
   CUtensorMap tmX, tmDY;
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    int rc = encode_tmap_bf16(&tmX, x, 4, dims, strides, box, nullptr);
+    const uint32_t box[4] = {64, (uint32_t)((p.bw - 1) * stride + 1), (uint32_t)((p.bh - 1) * stride + 1), (uint32_t)p.bn};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = encode_tmap_bf16(&tmX, x, 4, dims, strides, box, stride > 1 ? estr : nullptr);
     if (rc) return rc;
   }
   {

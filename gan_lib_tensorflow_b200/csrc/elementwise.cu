@@ -933,6 +933,27 @@ sum2x2_kernel(const TIn* __restrict__ x, TOut* __restrict__ out, int n, int ho, 
   }
 }
 
+// out[n, oh, ow, c]: x[n, i, j, c] at (i*stride, j*stride), zero elsewhere (one pass writes the whole output)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+dilate2d_kernel(const TIn* __restrict__ x, TOut* __restrict__ out, int n, int h, int w, int c, int stride, int oh, int ow) {
+  pdl_wait();
+  const int v = c >> 2;
+  const int64_t total = static_cast<int64_t>(n) * oh * ow * v;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % v) * 4;
+    const int64_t pix = i / v;
+    const int wi = static_cast<int>(pix % ow);
+    const int hi = static_cast<int>((pix / ow) % oh);
+    const int ni = static_cast<int>(pix / (static_cast<int64_t>(ow) * oh));
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hi % stride == 0 && wi % stride == 0 && hi / stride < h && wi / stride < w)
+      g = ld4(x + ((static_cast<int64_t>(ni) * h + hi / stride) * w + wi / stride) * c + c4);
+    st4(out + pix * c + c4, g);
+  }
+}
+
 // ---- scalar variants for channel counts that are not a multiple of 4 (RGB images)
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
@@ -1609,6 +1630,27 @@ extern "C" int ganb_sum2x2(const void* x, int x_dtype, void* out, int out_dtype,
   if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_sum2x2<float, __nv_bfloat16>(x, out, n, ho, wo, c, scale, STREAM);
   if (x_dtype == GANB_BF16 && out_dtype == GANB_BF16) return launch_sum2x2<__nv_bfloat16, __nv_bfloat16>(x, out, n, ho, wo, c, scale, STREAM);
   return launch_sum2x2<__nv_bfloat16, float>(x, out, n, ho, wo, c, scale, STREAM);
+}
+
+template <typename TIn, typename TOut>
+static int launch_dilate(const void* x, void* out, int n, int h, int w, int c, int stride, int oh, int ow, cudaStream_t s) {
+  const int64_t items = static_cast<int64_t>(n) * oh * ow * (c / 4);
+  launch_k(dilate2d_kernel<TIn, TOut>, grid_for(items, 256), 256, 0, s, static_cast<const TIn*>(x), static_cast<TOut*>(out),
+           n, h, w, c, stride, oh, ow);
+  GANB_CHECK_LAUNCH("dilate2d_kernel");
+  return 0;
+}
+
+extern "C" int ganb_dilate2d(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c, int stride,
+                             int out_h, int out_w, void* stream) {
+  if (!x || !out) return fail(GANB_E_BADARG, "dilate2d: null buffer");
+  if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "dilate2d: c=%d must be a multiple of 4", c);
+  if (stride < 1 || out_h < (h - 1) * stride + 1 || out_w < (w - 1) * stride + 1)
+    return fail(GANB_E_BADARG, "dilate2d: output %dx%d too small for %dx%d at stride %d", out_h, out_w, h, w, stride);
+  if (x_dtype == GANB_F32 && out_dtype == GANB_F32) return launch_dilate<float, float>(x, out, n, h, w, c, stride, out_h, out_w, STREAM);
+  if (x_dtype == GANB_F32 && out_dtype == GANB_BF16) return launch_dilate<float, __nv_bfloat16>(x, out, n, h, w, c, stride, out_h, out_w, STREAM);
+  if (x_dtype == GANB_BF16 && out_dtype == GANB_BF16) return launch_dilate<__nv_bfloat16, __nv_bfloat16>(x, out, n, h, w, c, stride, out_h, out_w, STREAM);
+  return launch_dilate<__nv_bfloat16, float>(x, out, n, h, w, c, stride, out_h, out_w, STREAM);
 }
 
 template <typename TIn, typename TOut>

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const SgemmParams p) {
 //   out[(n,ho,wo)][(r*kw+s)*cs + c] = xs[n, ho + sign*(r-pad_t), wo + sign*(s-pad_l), c]   (0 outside / padding)
 __global__ void __launch_bounds__(256)
 im2col_small_kernel(const float* __restrict__ xs, __nv_bfloat16* __restrict__ out, int n, int hs, int ws, int cs,
-                    int ho, int wo, int kh, int kw, int pad_t, int pad_l, int sign, int kpad) {
+                    int ho, int wo, int kh, int kw, int stride, int pad_t, int pad_l, int sign, int kpad) {
   pdl_wait();
   const int groups = kpad >> 3;  // 8 bf16 = 16 bytes per thread
   const int64_t total = static_cast<int64_t>(n) * ho * wo * groups;
@@ -240,7 +240,7 @@ im2col_small_kernel(const float* __restrict__ xs, __nv_bfloat16* __restrict__ ou
       if (j < kvalid) {
         const int tap = j / cs, c = j - tap * cs;
         const int r = tap / kw, sx = tap - r * kw;
-        const int hx = h0 + sign * (r - pad_t), wx = w0 + sign * (sx - pad_l);
+        const int hx = h0 * stride + sign * (r - pad_t), wx = w0 * stride + sign * (sx - pad_l);
         if (hx >= 0 && hx < hs && wx >= 0 && wx < ws)
           val = __ldg(xs + ((static_cast<int64_t>(ni) * hs + hx) * ws + wx) * cs + c);
       }
@@ -370,7 +370,7 @@ extern "C" int ganb_sgemm_small(const float* a, const float* b, float* c, int m,
 }
 
 extern "C" int ganb_im2col_small(const float* xs, void* out_bf16, int n, int hs, int ws, int cs, int ho, int wo, int kh,
-                                 int kw, int pad_t, int pad_l, int sign, int kpad, void* stream) {
+                                 int kw, int stride, int pad_t, int pad_l, int sign, int kpad, void* stream) {
   if (!xs || !out_bf16) return fail(GANB_E_BADARG, "im2col_small: null buffer");
   if (kpad % 8 != 0 || kh * kw * cs > kpad) return fail(GANB_E_BADARG, "im2col_small: kh*kw*cs=%d does not fit kpad=%d", kh * kw * cs, kpad);
   if (sign != 1 && sign != -1) return fail(GANB_E_BADARG, "im2col_small: sign must be +-1");
@@ -378,7 +378,7 @@ extern "C" int ganb_im2col_small(const float* xs, void* out_bf16, int n, int hs,
   int64_t blocks = ceil_div64(items, 256);
   if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
   launch_k(im2col_small_kernel, static_cast<int>(blocks), 256, 0, STREAM, xs, static_cast<__nv_bfloat16*>(out_bf16), n, hs, ws, cs,
-                                                                   ho, wo, kh, kw, pad_t, pad_l, sign, kpad);
+                                                                   ho, wo, kh, kw, stride, pad_t, pad_l, sign, kpad);
   GANB_CHECK_LAUNCH("im2col_small_kernel");
   return 0;
 }

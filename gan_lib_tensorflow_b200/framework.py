@@ -23,7 +23,15 @@ import torch
 from . import kernels as K
 
 ACT_GRAD_BF16 = True  # gradients of bf16 activations are stored in bf16
-SMALL_K = 32  # im2col width (bf16 columns) of the <=8-channel tensor-core route
+SMALL_K = 32  # narrowest im2col width (bf16 columns) of the <=8-channel tensor-core route
+
+
+def small_k(taps: int, c: int):
+    """im2col width for a <=8-channel operand: taps*c columns padded to 32 / 64 / 128 (None: does not fit)."""
+    for k in (32, 64, 128):
+        if taps * c <= k:
+            return k
+    return None
 _ALIGN = 64  # floats: every variable starts on a 256-byte boundary inside the flat buffers
 
 
@@ -307,12 +315,15 @@ class PackEntry:
         # <=8-channel side: [large channel][tap*cs + c] padded to SMALL_K columns (operand of the im2col route)
         self.small = None
         self.ws = None
-        if self.ci <= 8 and self.taps * self.ci <= SMALL_K:
+        self.kpad = None
+        if self.ci <= 8 and small_k(self.taps, self.ci) is not None:
             self.small = "ci"
-            self.ws = torch.empty(self.co, SMALL_K, dtype=torch.bfloat16, device=dev)
-        elif self.co <= 8 and self.taps * self.co <= SMALL_K:
+            self.kpad = small_k(self.taps, self.ci)
+            self.ws = torch.empty(self.co, self.kpad, dtype=torch.bfloat16, device=dev)
+        elif self.co <= 8 and small_k(self.taps, self.co) is not None:
             self.small = "co"
-            self.ws = torch.empty(self.ci, SMALL_K, dtype=torch.bfloat16, device=dev)
+            self.kpad = small_k(self.taps, self.co)
+            self.ws = torch.empty(self.ci, self.kpad, dtype=torch.bfloat16, device=dev)
 
 
 class PackGroup:
@@ -354,7 +365,7 @@ class PackGroup:
         K.pack_weights(self.table, len(entries), self.total_tiles)
         for e in entries:
             if e.small is not None:
-                K.pack_small(e.w.data, e.ws, e.taps, e.ci, e.co, e.small == "ci", SMALL_K)
+                K.pack_small(e.w.data, e.ws, e.taps, e.ci, e.co, e.small == "ci", e.kpad)
         self.valid_for = ver
 
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from . import kernels as K
-from .framework import SMALL_K, Var, Variable, get_store
+from .framework import Var, Variable, get_store, small_k
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -98,6 +98,11 @@ def _pads(padding, h, w, kh, kw, stride):
         pt = pl = 0
         ho = (h - kh) // stride + 1
         wo = (w - kw) // stride + 1
+    elif isinstance(padding, (tuple, list)) and len(padding) == 4:
+        # explicit (top, bottom, left, right): tf.pad followed by a VALID convolution (Pix2Pix/networks.py:287-354)
+        pt, pb, pl, pr = (int(v) for v in padding)
+        ho = (h + pt + pb - kh) // stride + 1
+        wo = (w + pl + pr - kw) // stride + 1
     else:
         raise ValueError(f"unknown padding {padding!r}")
     return pt, pl, ho, wo
@@ -113,9 +118,11 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     GEMM epilogue (shortcut of an 'up' block); its gradient is the 2x2 block sum of the output gradient.
     Every shape runs on the tensor cores: layers with <= 8 channels on one side go through a bf16 im2col of the
     small tensor (kh*kw*c <= 32 columns) and become 1x1 GEMMs; larger small-channel filters fall back to the
-    CUDA-core kernels of smallconv.cu."""
-    if stride != 1:
-        raise NotImplementedError("strided convolutions are not built yet (SURVEY 8(f)); stride must be 1")
+    CUDA-core kernels of smallconv.cu.
+
+    stride > 1 (Pix2Pix encoders / PatchGAN): the forward and filter-gradient kernels gather every stride-th pixel
+    through TMA element strides; the data gradient is the stride-1 kernel applied to the zero-dilated output
+    gradient (correct for any TF padding; the structural zeros cost stride^2 more MMA work than necessary)."""
     if in_scale is not None:
         raise NotImplementedError("inputs_norm is not wired into the convolution epilogue yet")
     store = get_store()
@@ -127,8 +134,11 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     bias = b.data if b is not None else None
     res = residual.data if residual is not None else None
     small_in, small_out = cin <= 8, cout <= 8
-    route_in = small_in and taps * cin <= SMALL_K and cout % 8 == 0
-    route_out = (not small_in) and small_out and taps * cout <= SMALL_K and cin % 8 == 0
+    kp_in, kp_out = small_k(taps, cin), small_k(taps, cout)
+    route_in = small_in and kp_in is not None and cout % 8 == 0
+    route_out = (not small_in) and small_out and kp_out is not None and cin % 8 == 0 and stride == 1
+    if stride != 1 and not (route_in or (cin % 8 == 0 and not small_out)):
+        raise NotImplementedError(f"stride {stride} with cin={cin}, cout={cout}: only the tensor-core routes are strided")
     group = store.pack_group(W.root)
     pack = group.entry(W)
     group.refresh()
@@ -136,8 +146,8 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     if small_in:
         xin = x if x.data.dtype == F32 else cast(x, F32)
         if route_in:
-            xcol = K.im2col_small(xin.data, n, h, w, cin, ho, wo, kh, kw, pt, pl, +1, SMALL_K)
-            y = K.conv_igemm(xcol, pack.ws, n, ho, wo, SMALL_K, ho, wo, cout, 1, 1, 0, 0, False, alpha, bias, res,
+            xcol = K.im2col_small(xin.data, n, h, w, cin, ho, wo, kh, kw, pt, pl, +1, kp_in, stride=stride)
+            y = K.conv_igemm(xcol, pack.ws, n, ho, wo, kp_in, ho, wo, cout, 1, 1, 0, 0, False, alpha, bias, res,
                              None, out_dtype, residual_up2=residual_up2)
         else:
             if res is not None:
@@ -149,7 +159,7 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
             raise NotImplementedError(f"cin={cin}: tensor-core path needs cin % 8 == 0")
         xin = x if x.data.dtype == BF16 else cast(x, BF16)
         y = K.conv_igemm(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res,
-                         None, out_dtype, residual_up2=residual_up2)
+                         None, out_dtype, residual_up2=residual_up2, stride=stride)
     out = Var(y, grad_dtype=out_grad_dtype)
     need_w = W.needs_grad and _tape() is not None
     need_b = b is not None and b.needs_grad and _tape() is not None
@@ -175,7 +185,7 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
             dycol = None
             if route_out and (need_w or need_x):
                 gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
-                dycol = K.im2col_small(gy32, n, ho, wo, cout, h, w, kh, kw, pt, pl, -1, SMALL_K)
+                dycol = K.im2col_small(gy32, n, ho, wo, cout, h, w, kh, kw, pt, pl, -1, kp_out)
 
             def _conv_wgrad():
                 if sn is not None:
@@ -183,12 +193,12 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                 else:
                     dst, beta = W.grad, 1.0
                 if route_in:
-                    r = torch.empty((SMALL_K, cout), dtype=F32, device=gy.device)
-                    K.conv_wgrad(xcol, gy16, r, n, ho, wo, SMALL_K, ho, wo, cout, 1, 1, 0, 0, None, 0.0)
+                    r = torch.empty((kp_in, cout), dtype=F32, device=gy.device)
+                    K.conv_wgrad(xcol, gy16, r, n, ho, wo, kp_in, ho, wo, cout, 1, 1, 0, 0, None, 0.0)
                     K.small_wgrad_scatter(r, dst, taps, cin, cout, False, None, beta)
                 elif route_out:
-                    r = torch.empty((SMALL_K, cin), dtype=F32, device=gy.device)
-                    K.conv_wgrad(dycol, xin.data, r, n, h, w, SMALL_K, h, w, cin, 1, 1, 0, 0, None, 0.0)
+                    r = torch.empty((kp_out, cin), dtype=F32, device=gy.device)
+                    K.conv_wgrad(dycol, xin.data, r, n, h, w, kp_out, h, w, cin, 1, 1, 0, 0, None, 0.0)
                     K.small_wgrad_scatter(r, dst, taps, cout, cin, True, None, beta)
                 elif small_in:
                     K.conv_small_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, +1, False,
@@ -198,7 +208,8 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                     K.conv_small_wgrad(gy32, xin.data, dst, n, ho, wo, cout, h, w, cin, kh, kw, pt, pl, -1, True,
                                        None, beta)
                 else:
-                    K.conv_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, None, beta)
+                    K.conv_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, None, beta,
+                                 stride=stride)
                 if sn is not None:
                     sn.g_written = True
                     lst = tape.pending_sn.setdefault(W.root, [])
@@ -216,15 +227,75 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
             if need_x:
                 gdt = xin.gdtype
                 if route_out:
-                    dx = K.conv_igemm(dycol, pack.ws, n, h, w, SMALL_K, h, w, cin, 1, 1, 0, 0, False, alpha, None,
+                    dx = K.conv_igemm(dycol, pack.ws, n, h, w, kp_out, h, w, cin, 1, 1, 0, 0, False, alpha, None,
                                       None, None, gdt)
                 elif small_out:
                     gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
                     dx = K.conv_smallcin(gy32, W.data, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl,
                                          True, True, alpha, None, None, gdt)
-                else:
+                elif stride == 1:
                     dx = K.conv_igemm(gy16, pack.wn, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
                                       alpha, None, None, None, gdt)
+                else:
+                    hd, wd = (ho - 1) * stride + 1, (wo - 1) * stride + 1
+                    gyd = K.dilate2d(gy16, stride, hd, wd)
+                    dx = K.conv_igemm(gyd, pack.wn, n, hd, wd, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
+                                      alpha, None, None, None, gdt)
+                xin.accum(dx)
+        tape.record(bwd)
+    return out
+
+
+def conv2d_transpose(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: int = 2,
+                     padding: str = "SAME", out_grad_dtype=None) -> Var:
+    """tf.nn.conv2d_transpose to [n, stride*h, stride*w, cout] (common/ops/deconv2d.py:99-109) + bias, fp32 out.
+
+    W is [kh, kw, cout, cin] (the HWIO filter of the forward convolution [n, s*h, s*w, cout] -> [n, h, w, cin] whose
+    input gradient this op is).  Forward = stride-1 tensor-core kernel over the zero-dilated input with the filter
+    taps flipped; backward: dx = the strided forward convolution of the output gradient, dW = its filter gradient
+    with the roles of activation and gradient exchanged."""
+    n, h, w, cin = x.shape
+    cout = W.data.shape[-2]
+    if W.data.shape[-1] != cin:
+        raise ValueError(f"conv2d_transpose: filter expects {W.data.shape[-1]} input channels, got {cin}")
+    if cin % 8 or cout % 8:
+        raise NotImplementedError("conv2d_transpose: channel counts must be multiples of 8")
+    oh, ow = stride * h, stride * w
+    pt, pl, ho_chk, wo_chk = _pads(padding, oh, ow, kh, kw, stride)   # pads of the forward conv on the big side
+    if (ho_chk, wo_chk) != (h, w):
+        raise ValueError("conv2d_transpose: padding does not map the 2x output back onto the input size")
+    store = get_store()
+    group = store.pack_group(W.root)
+    pack = group.entry(W)
+    group.refresh()
+    xin = x if x.data.dtype == BF16 else cast(x, BF16)
+    hd, wd = (h - 1) * stride + 1, (w - 1) * stride + 1
+    xd = K.dilate2d(xin.data, stride, hd, wd)
+    y = K.conv_igemm(xd, pack.wn, n, hd, wd, cin, oh, ow, cout, kh, kw, kh - 1 - pt, kw - 1 - pl, True, None,
+                     b.data if b is not None else None, None, None, F32)
+    out = Var(y, grad_dtype=out_grad_dtype)
+    need_w = W.needs_grad and _tape() is not None
+    need_b = b is not None and b.needs_grad and _tape() is not None
+    if _rg(xin) or need_w or need_b:
+        out.requires_grad = True
+        tape = _tape()
+
+        def bwd():
+            gy = out.grad
+            if gy is None:
+                return
+            gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
+            if need_b or need_w:
+                tape.keep.extend((gy, gy16))
+                with tape.offchain():
+                    if need_b:
+                        K.colsum(gy, n * oh * ow, cout, b.grad, 1.0)
+                    if need_w:   # filter gradient of the forward conv: "input" = gy (cout channels), "dy" = x
+                        K.conv_wgrad(gy16, xin.data, W.grad, n, oh, ow, cout, h, w, cin, kh, kw, pt, pl, None, 1.0,
+                                     stride=stride)
+            if xin.requires_grad:
+                dx = K.conv_igemm(gy16, pack.wt, n, oh, ow, cout, h, w, cin, kh, kw, pt, pl, False, None, None, None,
+                                  None, xin.gdtype, stride=stride)
                 xin.accum(dx)
         tape.record(bwd)
     return out
@@ -439,6 +510,81 @@ def concat_label_map(x: Var, e: Var, act="relu"):
                 x.accum(K.concat_bwd_x(x.data, n * h * w, c1, ct, act, d_raw, d_act, x.gdtype))
         _tape().record(bwd)
     return raw_v, act_v
+
+
+# ------------------------------------------------------------------------------------------------ PGGAN / Pix2Pix
+def pixel_norm(x: Var, eps: float = 1e-8, act=None, out_dtype=None) -> Var:
+    """act(x * rsqrt(mean_c(x^2) + eps)) -- common/ops/normalization.py:125-140 (+ the lrelu that follows it in
+    PGGAN/model_nvidia.py:63-68) as one kernel."""
+    out = Var(K.pixel_norm_fwd(x.data, eps, act, out_dtype or x.data.dtype))
+    if _rg(x):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                x.accum(K.pixel_norm_bwd(x.data, out.grad, eps, act, x.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def minibatch_std(x: Var) -> Var:
+    """tf.concat([x, tile(mean(sqrt(var_batch(x) + 1e-8)))], axis=3) -- PGGAN/model_nvidia.py:20-28."""
+    xin = x if x.data.dtype == F32 else cast(x, F32)
+    y, ws = K.minibatch_std_fwd(xin.data)
+    out = Var(y)
+    if _rg(xin):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                g = out.grad if out.grad.dtype == F32 else K.cast(out.grad, F32)
+                xin.accum(K.minibatch_std_bwd(xin.data, g, ws))
+        _tape().record(bwd)
+    return out
+
+
+def concat_channels(a: Var, b: Var, out_dtype=None) -> Var:
+    """tf.concat([a, b], axis=3) (U-Net skip connections, Pix2Pix/networks.py:268-270)."""
+    ca, cb = a.shape[-1], b.shape[-1]
+    assert a.shape[:-1] == b.shape[:-1]
+    dtype = out_dtype or a.data.dtype
+    y = torch.empty(tuple(a.shape[:-1]) + (ca + cb,), dtype=dtype, device=a.data.device)
+    K.copy_channels(a.data, 0, y, 0, ca)
+    K.copy_channels(b.data, 0, y, ca, cb)
+    out = Var(y)
+    if _rg(a, b):
+        out.requires_grad = True
+
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            for v, off, c in ((a, 0, ca), (b, ca, cb)):
+                if v.requires_grad:
+                    dv = torch.empty(v.data.shape, dtype=v.gdtype, device=g.device)
+                    K.copy_channels(g, off, dv, 0, c)
+                    v.accum(dv)
+        _tape().record(bwd)
+    return out
+
+
+def dropout(x: Var, keep_mask: torch.Tensor, keep_prob: float) -> Var:
+    """tf.nn.dropout with an explicit fp32 keep mask in {0, 1} (Pix2Pix/networks.py:263-264): x * mask / keep_prob.
+    The mask is an input because TF's op-level RNG cannot be reproduced."""
+    c = x.shape[-1]
+    y = torch.empty_like(x.data)
+    K.copy_channels(x.data, 0, y, 0, c, mask=keep_mask, scale=1.0 / keep_prob)
+    out = Var(y, grad_dtype=x.grad_dtype)
+    if _rg(x):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                dx = torch.empty(x.data.shape, dtype=x.gdtype, device=y.device)
+                K.copy_channels(out.grad, 0, dx, 0, c, mask=keep_mask, scale=1.0 / keep_prob)
+                x.accum(dx)
+        _tape().record(bwd)
+    return out
 
 
 def gan_loss(logits: Var, mode: str, n_real: int = 0, scale: float = 1.0, loss_out: torch.Tensor | None = None):

@@ -40,6 +40,7 @@ def L():
             return _L
         _L = cabi.lib()
         for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
+                     "ganb_minibatch_std_workspace",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
     return _L
@@ -94,18 +95,18 @@ def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0) -> N
 
 # ------------------------------------------------------------------------------------------------ conv (TC)
 def conv_igemm(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, alpha, bias, residual, act, out_dtype,
-               residual_up2=False):
+               residual_up2=False, stride=1):
     y = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
-    check(L().ganb_conv2d_igemm(ptr(x), ptr(wp), ptr(y), n, h, w, cin, ho, wo, cout, kh, kw, 1, pad_t, pad_l,
+    check(L().ganb_conv2d_igemm(ptr(x), ptr(wp), ptr(y), n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l,
                                 int(flip), ptr(alpha), ptr(bias), ptr(residual), int(bool(residual_up2)), act_code(act),
                                 BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_conv2d_igemm")
     return y
 
 
-def conv_wgrad(x, dy, dw, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, scale, beta):
+def conv_wgrad(x, dy, dw, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, scale, beta, stride=1):
     nbytes = L().ganb_conv2d_wgrad_workspace(n, h, w, cin, ho, wo, cout, kh, kw)
     ws = _ws(nbytes, x.device)
-    check(L().ganb_conv2d_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(ws), n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l,
+    check(L().ganb_conv2d_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(ws), n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l,
                                 ptr(scale), c_float(beta), _stream()), "ganb_conv2d_wgrad")
 
 
@@ -126,9 +127,10 @@ def conv_small_wgrad(xs, yl, dw, n, hs, ws_, cs, hl, wl, cl, kh, kw, pad_t, pad_
           "ganb_conv2d_small_wgrad")
 
 
-def im2col_small(xs, n, hs, ws_, cs, ho, wo, kh, kw, pad_t, pad_l, sign, kpad=32):
+def im2col_small(xs, n, hs, ws_, cs, ho, wo, kh, kw, pad_t, pad_l, sign, kpad=32, stride=1):
     out = torch.empty((n, ho, wo, kpad), dtype=torch.bfloat16, device=xs.device)
-    check(L().ganb_im2col_small(ptr(xs), ptr(out), n, hs, ws_, cs, ho, wo, kh, kw, pad_t, pad_l, sign, kpad, _stream()),
+    check(L().ganb_im2col_small(ptr(xs), ptr(out), n, hs, ws_, cs, ho, wo, kh, kw, stride, pad_t, pad_l, sign, kpad,
+                                _stream()),
           "ganb_im2col_small")
     return out
 
@@ -195,6 +197,15 @@ def expand2(x, scale, out_dtype):
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=out_dtype, device=x.device)
     check(L().ganb_expand2(ptr(x), dt(x), ptr(out), dt(out), n, h, w, c, c_float(scale), _stream()), "ganb_expand2")
+    return out
+
+
+def dilate2d(x, stride, out_h, out_w, out_dtype=None):
+    """out[n, i*stride, j*stride, c] = x[n, i, j, c], zero elsewhere."""
+    n, h, w, c = x.shape
+    out = torch.empty((n, out_h, out_w, c), dtype=out_dtype or x.dtype, device=x.device)
+    check(L().ganb_dilate2d(ptr(x), dt(x), ptr(out), dt(out), n, h, w, c, stride, out_h, out_w, _stream()),
+          "ganb_dilate2d")
     return out
 
 
@@ -274,6 +285,48 @@ def embedding_fwd(table, labels, n, dim):
 
 def embedding_bwd(dout, labels, n, dim, vocab, dtable):
     check(L().ganb_embedding_bwd(ptr(dout), ptr(labels), n, dim, vocab, ptr(dtable), _stream()), "ganb_embedding_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ PGGAN / Pix2Pix extras
+def pixel_norm_fwd(x, eps, act, out_dtype):
+    c = x.shape[-1]
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(L().ganb_pixel_norm_fwd(ptr(x), dt(x), ptr(y), dt(y), c_int64(x.numel() // c), c, c_float(eps), act_code(act),
+                                  _stream()), "ganb_pixel_norm_fwd")
+    return y
+
+
+def pixel_norm_bwd(x, dy, eps, act, dx_dtype):
+    c = x.shape[-1]
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    check(L().ganb_pixel_norm_bwd(ptr(x), dt(x), ptr(dy), dt(dy), ptr(dx), dt(dx), c_int64(x.numel() // c), c,
+                                  c_float(eps), act_code(act), _stream()), "ganb_pixel_norm_bwd")
+    return dx
+
+
+def minibatch_std_fwd(x, cs=None):
+    b, h, w, c = x.shape
+    cs = cs or (c + 1)
+    out = torch.empty((b, h, w, cs), dtype=torch.float32, device=x.device)
+    ws = _ws(L().ganb_minibatch_std_workspace(b, h, w, c), x.device)
+    check(L().ganb_minibatch_std_fwd(ptr(x), b, h, w, c, cs, ptr(out), ptr(ws), _stream()), "ganb_minibatch_std_fwd")
+    return out, ws
+
+
+def minibatch_std_bwd(x, dout, ws):
+    b, h, w, c = x.shape
+    cs = dout.shape[-1]
+    dx = torch.empty_like(x)
+    check(L().ganb_minibatch_std_bwd(ptr(x), ptr(dout), b, h, w, c, cs, ptr(dx), ptr(ws), _stream()),
+          "ganb_minibatch_std_bwd")
+    return dx
+
+
+def copy_channels(src, src_off, dst, dst_off, c, mask=None, scale=1.0):
+    """dst[..., dst_off:dst_off+c] = scale * mask * src[..., src_off:src_off+c] (NHWC, any leading dims)."""
+    pixels = src.numel() // src.shape[-1]
+    check(L().ganb_copy_channels(ptr(src), dt(src), src.shape[-1], src_off, ptr(dst), dt(dst), dst.shape[-1], dst_off,
+                                 c_int64(pixels), c, ptr(mask), c_float(scale), _stream()), "ganb_copy_channels")
 
 
 # ------------------------------------------------------------------------------------------------ grouped SN / pack

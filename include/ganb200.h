@@ -63,6 +63,8 @@ int64_t ganb_launch_count(void);
  * the same kernel into the data gradient of a stride-1 convolution when x := dy, wp := HWIO filter viewed
  * as [kh*kw][cin_fwd][cout_fwd], pad := k-1-pad.
  * Requirements: cin % 8 == 0, x and wp 16-byte aligned. alpha (device scalar), bias, residual may be NULL.
+ * stride in 1..4 (strided layers gather through TMA element strides; the data gradient of a strided convolution is
+ * this same entry applied to the zero-dilated output gradient, see ganb_dilate2d).
  * residual_up2 = 1: `residual` is [n, ho/2, wo/2, cout] and is read through a nearest-neighbour 2x upsample
  * (the shortcut of an 'up' residual block, common/resnet_block.py:123-127, without materialising the upsampled map).
  * ---------------------------------------------------------------------------------------------- */
@@ -72,14 +74,14 @@ int ganb_conv2d_igemm(const void* x_bf16, const void* wp_bf16, void* y, int n, i
                       int out_dtype, void* stream);
 
 /* Filter gradient: partial[split][t][ci][co] = sum over the split's pixels of
- *     x[n, ho + r - pad_t, wo + s - pad_l, ci] * dy[n, ho, wo, co]          (stride 1)
+ *     x[n, ho*stride + r - pad_t, wo*stride + s - pad_l, ci] * dy[n, ho, wo, co]
  * `workspace` must hold ganb_conv2d_wgrad_workspace() bytes; the reduction over splits, the optional
  * scale and the accumulation into dw (HWIO f32) are done by the same call (second kernel).
  *     dw = beta * dw + scale * sum_split partial
  * Requirements: cin % 8 == 0, cout % 8 == 0. */
 int64_t ganb_conv2d_wgrad_workspace(int n, int h, int w, int cin, int ho, int wo, int cout, int kh, int kw);
 int ganb_conv2d_wgrad(const void* x_bf16, const void* dy_bf16, float* dw, void* workspace, int n, int h, int w,
-                      int cin, int ho, int wo, int cout, int kh, int kw, int pad_t, int pad_l,
+                      int cin, int ho, int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
                       const float* scale, float beta, void* stream);
 
 
@@ -102,11 +104,11 @@ int ganb_conv2d_small_wgrad(const float* xs, const void* yl, int yl_dtype, float
 
 /* Tensor-core route for the same <=8-channel layers: bf16 im2col of the small tensor (kh*kw*cs <= kpad columns)
  * makes fprop / wgrad / dgrad 1x1 GEMMs for ganb_conv2d_igemm / ganb_conv2d_wgrad.
- *   im2col_small : out[(n,ho,wo)][(r*kw+s)*cs + c] = xs[n, ho + sign*(r-pad_t), wo + sign*(s-pad_l), c], zero padded
+ *   im2col_small : out[(n,ho,wo)][(r*kw+s)*cs + c] = xs[n, ho*stride + sign*(r-pad_t), wo*stride + sign*(s-pad_l), c], zero padded
  *   pack_small   : out[l][tap*cs + c] (row stride kpad): small_is_ci ? W[tap][c][l] : W[tap][l][c]
  *   small_wgrad_scatter : dw[tap][cs][cl] (or [tap][cl][cs]) = beta*dw + scale * r[tap*cs + c][l], r = [kpad][cl] */
 int ganb_im2col_small(const float* xs, void* out_bf16, int n, int hs, int ws, int cs, int ho, int wo, int kh, int kw,
-                      int pad_t, int pad_l, int sign, int kpad, void* stream);
+                      int stride, int pad_t, int pad_l, int sign, int kpad, void* stream);
 int ganb_pack_small(const float* w_hwio, void* out_bf16, int taps, int ci, int co, int small_is_ci, int kpad,
                     void* stream);
 int ganb_small_wgrad_scatter(const float* r, float* dw, int taps, int cs, int cl, int out_layout_clcs,
@@ -195,6 +197,11 @@ int ganb_expand2(const void* x, int x_dtype, void* out, int out_dtype, int n, in
 /* out[n,h/2,w/2,c] = scale * sum of each 2x2 block (nearest-upsample backward: scale 1) */
 int ganb_sum2x2(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c, float scale,
                 void* stream);
+/* out[n, i*stride, j*stride, c] = x[n, i, j, c], zero elsewhere; out is [n, (h-1)*stride+1+extra_h, (w-1)*stride+1+extra_w, c].
+ * The data gradient of a stride-s convolution (Conv2DBackpropInput) and tf.nn.conv2d_transpose (deconv2d.py:102) are
+ * stride-1 convolutions of this dilated tensor. c % 4 == 0. */
+int ganb_dilate2d(const void* x, int x_dtype, void* out, int out_dtype, int n, int h, int w, int c, int stride,
+                  int out_h, int out_w, void* stream);
 int ganb_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t count, float scale, void* stream);
 int ganb_axpby(const float* x, float* y, int64_t count, float a, float b, void* stream); /* y = a*x + b*y */
 /* out[c] = beta*out[c] + sum_rows x[row][c]: gradient of tf.nn.bias_add (conv2d.py:216, linear.py:180) */
@@ -235,6 +242,25 @@ int ganb_preprocess_real(const int* data, const float* noise, int b, int hw, flo
 /* tf.nn.embedding_lookup (common/ops/embedding.py:51) and its IndexedSlices gradient summed by index */
 int ganb_embedding_fwd(const float* table, const int* labels, int n, int dim, float* out, void* stream);
 int ganb_embedding_bwd(const float* dout, const int* labels, int n, int dim, int vocab, float* dtable, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PGGAN / Pix2Pix sides of the hot path (bandwidth-bound; c % 4 == 0).
+ * pixel_norm: y = act(x * rsqrt(mean_c(x^2) + eps)) -- common/ops/normalization.py:125-140 followed by lrelu
+ *   (PGGAN/model_nvidia.py:15-17, 63-68); bwd: dz = dy*act'(x r), dx = r dz - x r^3 mean_c(dz x).
+ * minibatch_std: PGGAN/model_nvidia.py:20-28; out = concat(x, mean_{h,w,c} sqrt(var_b(x) + 1e-8)), channel stride cs.
+ * copy_channels: dst[pix, dst_off + j] = scale * mask[pix, j] * src[pix, src_off + j]: tf.concat of U-Net skips and
+ *   its backward slice (Pix2Pix/networks.py:268-270), tf.nn.dropout with a given keep mask (:263-264).
+ * ---------------------------------------------------------------------------------------------- */
+int ganb_pixel_norm_fwd(const void* x, int x_dtype, void* y, int y_dtype, int64_t pixels, int c, float eps, int act,
+                        void* stream);
+int ganb_pixel_norm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype, int64_t pixels,
+                        int c, float eps, int act, void* stream);
+int64_t ganb_minibatch_std_workspace(int b, int h, int w, int c);
+int ganb_minibatch_std_fwd(const float* x, int b, int h, int w, int c, int cs, float* out, void* workspace, void* stream);
+int ganb_minibatch_std_bwd(const float* x, const float* dout, int b, int h, int w, int c, int cs, float* dx,
+                           void* workspace, void* stream);
+int ganb_copy_channels(const void* src, int src_dtype, int src_cstride, int src_off, void* dst, int dst_dtype,
+                       int dst_cstride, int dst_off, int64_t pixels, int c, const float* mask, float scale, void* stream);
 
 #ifdef __cplusplus
 }

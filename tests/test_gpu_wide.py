@@ -1,0 +1,151 @@
+"""GPU parity tests for the widened rows of SURVEY 8(a): strided / asymmetric-SAME / explicitly padded convolutions
+(Pix2Pix encoders and PatchGAN, a-3 / a-17), Deconv2D (a-4), pixel norm (+ leaky ReLU) and minibatch standard deviation
+(PGGAN, a-8 / a-16), U-Net channel concatenation and dropout masks (a-17).  Same protocol as test_gpu_ops.py: the
+CUDA path through the C ABI against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from tests.test_gpu_ops import TOL_F32, _bf16_repr, check, env, rel, run_pair  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ strided Conv2D
+@pytest.mark.parametrize("n,h,w,cin,cout,k,stride,sn", [
+    (4, 32, 32, 64, 128, 4, 2, False),    # Pix2Pix encoder: 4x4 s2 SAME (pads 1, 1)
+    (3, 16, 16, 128, 64, 3, 2, True),     # 3x3 s2 SAME on an even size: pads (0, 1) -- TF's asymmetric rule
+    (2, 16, 16, 64, 64, 4, 1, False),     # 4x4 s1 SAME: pads (1, 2) (Pix2Pix decoders)
+    (5, 9, 9, 72, 40, 3, 2, False),       # odd size, ragged channels
+    (4, 32, 32, 3, 64, 4, 2, False),      # RGB encoder_1: 48 im2col columns (64-wide route), stride 2
+    (2, 32, 32, 6, 64, 4, 2, True),       # PatchGAN input (image + target = 6 channels): 96 columns
+    (2, 16, 16, 128, 1, 4, 1, True),      # PatchGAN head: Cout = 1
+])
+def test_strided_conv2d_matches_oracle(env, n, h, w, cin, cout, k, stride, sn):
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+    from oracle import ops as O
+
+    x = np.random.RandomState(41).standard_normal((n, h, w, cin)).astype("float32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.Conv2D(xv, cin, cout, k, stride, "L", spectral_normed=sn, update_collection="NO_OPS"),
+        lambda g, xt: O.Conv2D(g, xt, cin, cout, k, stride, "L", spectral_normed=sn, update_collection=O.NO_OPS),
+        x)
+    check(prod, refs)
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_explicitly_padded_valid_conv(env, stride):
+    """tf.pad(x, 1) followed by a 4x4 VALID convolution (Pix2Pix/networks.py:287-354)."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+    from oracle import ops as O
+
+    x = np.random.RandomState(42).standard_normal((3, 16, 16, 64)).astype("float32")
+
+    def orc(g, xt):
+        xp = torch.nn.functional.pad(xt, (0, 0, 1, 1, 1, 1))
+        return O.Conv2D(g, xp, 64, 128, 4, stride, "L", padding="VALID")
+
+    prod, refs = run_pair(store, tfshim,
+                          lambda xv: P.Conv2D(xv, 64, 128, 4, stride, "L", padding=(1, 1, 1, 1)), orc, x)
+    check(prod, refs)
+
+
+# ------------------------------------------------------------------------------------------------ Deconv2D
+@pytest.mark.parametrize("n,h,cin,cout,k", [(4, 8, 128, 64, 4), (2, 16, 64, 64, 3), (3, 5, 72, 40, 4)])
+def test_deconv2d_matches_oracle(env, n, h, cin, cout, k):
+    """tf.nn.conv2d_transpose to [n, 2h, 2w, cout] (deconv2d.py:99-109): forward, dx, dFilters, dBiases.  Inputs,
+    filters and the cotangent are bf16-representable so the fp32 oracle is the exact reference of the bf16 kernels."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import deconv2d as P
+    from oracle import ops as O
+
+    x = _bf16_repr(np.random.RandomState(43).standard_normal((n, h, h, cin)).astype("float32"))
+    cot = _bf16_repr(np.random.RandomState(44).standard_normal((n, 2 * h, 2 * h, cout)).astype("float32"))
+    wv = _bf16_repr((np.random.RandomState(45).standard_normal((k, k, cout, cin)) * 0.05).astype("float32"))
+
+    def prod_fn(xv):
+        with store.variable_scope("L"):
+            store.get_variable("Filters", initializer=wv)
+        return P.Deconv2D(xv, cin, cout, k, name="L")
+
+    def orc_fn(g, xt):
+        with g.variable_scope("L"):
+            g.get_variable("Filters", initializer=wv)
+        return O.Deconv2D(g, xt, cin, cout, k, name="L")
+
+    prod, refs = run_pair(store, tfshim, prod_fn, orc_fn, x, cot_np=cot, bf16=False)
+    check(prod, refs, tol_fp32=2e-3)   # only the bf16 rounding of dx remains (everything else is exact products)
+
+
+# ------------------------------------------------------------------------------------------------ PGGAN pieces
+@pytest.mark.parametrize("shape,act", [((4, 8, 8, 512), "lrelu"), ((3, 5, 7, 64), None), ((2, 4, 4, 12), "lrelu")])
+def test_pixel_norm_lrelu(env, shape, act):
+    store, _ = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.common.ops import normalization as P
+    from oracle import ops as O
+
+    rs = np.random.RandomState(46)
+    x = (rs.standard_normal(shape) * 1.5).astype("float32")
+    cot = rs.standard_normal(shape).astype("float32")
+    xv = F.Var(torch.from_numpy(x).cuda(), requires_grad=True)
+    with store.gradient_tape() as tape:
+        out = P.pixel_norm(xv, act=act)
+        tape.backward(out, grad=torch.from_numpy(cot).cuda())
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    yo = O.pixel_norm(xt)
+    if act == "lrelu":
+        yo = torch.maximum(yo, 0.2 * yo)       # PGGAN/model_nvidia.py:15-17
+    (dx,) = torch.autograd.grad(yo, xt, torch.from_numpy(cot).double())
+    assert rel(out.data.cpu().numpy(), yo.detach().numpy()) < TOL_F32
+    assert rel(xv.grad.cpu().numpy(), dx.numpy()) < TOL_F32
+
+
+@pytest.mark.parametrize("b,h,c", [(16, 4, 512), (6, 8, 32), (4, 2, 3)])
+def test_minibatch_std(env, b, h, c):
+    """PGGAN/model_nvidia.py:20-28."""
+    store, _ = env
+    from gan_lib_tensorflow_b200 import functional as F
+
+    rs = np.random.RandomState(47)
+    x = rs.standard_normal((b, h, h, c)).astype("float32")
+    cot = rs.standard_normal((b, h, h, c + 1)).astype("float32")
+    xv = F.Var(torch.from_numpy(x).cuda(), requires_grad=True)
+    with store.gradient_tape() as tape:
+        out = F.minibatch_std(xv)
+        tape.backward(out, grad=torch.from_numpy(cot).cuda())
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    m = xt.mean(dim=0, keepdim=True)
+    v = ((xt - m) * (xt - m)).mean(dim=0, keepdim=True)
+    std = torch.sqrt(v + 1e-8).mean().reshape(1, 1, 1, 1).expand(b, h, h, 1)
+    yo = torch.cat([xt, std], dim=3)
+    (dx,) = torch.autograd.grad(yo, xt, torch.from_numpy(cot).double())
+    assert out.shape == (b, h, h, c + 1)
+    assert rel(out.data.cpu().numpy(), yo.detach().numpy()) < TOL_F32
+    assert rel(xv.grad.cpu().numpy(), dx.numpy()) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ Pix2Pix pieces
+def test_concat_channels_and_dropout(env):
+    store, _ = env
+    from gan_lib_tensorflow_b200 import functional as F
+
+    rs = np.random.RandomState(48)
+    a = rs.standard_normal((3, 8, 8, 64)).astype("float32")
+    b = _bf16_repr(rs.standard_normal((3, 8, 8, 32)).astype("float32"))
+    mask = (rs.uniform(size=(3, 8, 8, 96)) < 0.5).astype("float32")
+    cot = rs.standard_normal((3, 8, 8, 96)).astype("float32")
+    av = F.Var(torch.from_numpy(a).cuda(), requires_grad=True)
+    bv = F.Var(torch.from_numpy(b).cuda().to(torch.bfloat16), requires_grad=True)
+    with store.gradient_tape() as tape:
+        cat = F.concat_channels(av, bv, out_dtype=torch.float32)
+        out = F.dropout(cat, torch.from_numpy(mask).cuda(), 0.5)
+        tape.backward(out, grad=torch.from_numpy(cot).cuda())
+    ref = np.concatenate([a, b], axis=3) * mask / 0.5
+    dref = cot * mask / 0.5
+    assert rel(out.data.cpu().numpy(), ref) < 1e-7
+    assert rel(av.grad.cpu().numpy(), dref[..., :64]) < 1e-7
+    assert rel(bv.grad.float().cpu().numpy(), dref[..., 64:]) < 4e-3     # bf16 gradient storage
