@@ -212,6 +212,22 @@ copy_channels_kernel(const TIn* __restrict__ src, int src_cs, int src_off, TOut*
   }
 }
 
+// channel counts / offsets that are not multiples of 4 (RGB tensors)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+copy_channels_scalar_kernel(const TIn* __restrict__ src, int src_cs, int src_off, TOut* __restrict__ dst, int dst_cs,
+                            int dst_off, int64_t pixels, int c, const float* __restrict__ mask, float scale) {
+  pdl_wait();
+  const int64_t total = pixels * c;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int ch = static_cast<int>(i % c);
+    const int64_t pix = i / c;
+    float a = static_cast<float>(src[pix * src_cs + src_off + ch]);
+    if (mask) a *= mask[i];
+    dst[pix * dst_cs + dst_off + ch] = static_cast<TOut>(a * scale);
+  }
+}
+
 }  // namespace ganb
 
 using namespace ganb;
@@ -302,6 +318,11 @@ namespace ganb {
 template <typename TIn, typename TOut>
 static void launch_copy_channels(const void* src, int src_cs, int src_off, void* dst, int dst_cs, int dst_off,
                                  int64_t pixels, int c, const float* mask, float scale, cudaStream_t s) {
+  if (c % 4 || src_cs % 4 || dst_cs % 4 || src_off % 4 || dst_off % 4) {
+    launch_k(copy_channels_scalar_kernel<TIn, TOut>, egrid(pixels * c, 256), 256, 0, s, static_cast<const TIn*>(src), src_cs,
+             src_off, static_cast<TOut*>(dst), dst_cs, dst_off, pixels, c, mask, scale);
+    return;
+  }
   launch_k(copy_channels_kernel<TIn, TOut>, egrid(pixels * (c / 4), 256), 256, 0, s, static_cast<const TIn*>(src), src_cs, src_off,
            static_cast<TOut*>(dst), dst_cs, dst_off, pixels, c, mask, scale);
 }
@@ -311,8 +332,6 @@ extern "C" int ganb_copy_channels(const void* src, int src_dtype, int src_cstrid
                                   int dst_cstride, int dst_off, int64_t pixels, int c, const float* mask, float scale,
                                   void* stream) {
   if (!src || !dst) return fail(GANB_E_BADARG, "copy_channels: null buffer");
-  if (c % 4 || src_cstride % 4 || dst_cstride % 4 || src_off % 4 || dst_off % 4)
-    return fail(GANB_E_UNSUPPORTED, "copy_channels: channel counts / offsets must be multiples of 4");
   const bool si = src_dtype == GANB_BF16, di = dst_dtype == GANB_BF16;
   if (!si && !di) launch_copy_channels<float, float>(src, src_cstride, src_off, dst, dst_cstride, dst_off, pixels, c, mask, scale, STREAM);
   else if (!si) launch_copy_channels<float, __nv_bfloat16>(src, src_cstride, src_off, dst, dst_cstride, dst_off, pixels, c, mask, scale, STREAM);

@@ -316,11 +316,11 @@ class PackEntry:
         self.small = None
         self.ws = None
         self.kpad = None
-        if self.ci <= 8 and small_k(self.taps, self.ci) is not None:
+        if self.ci < 8 and small_k(self.taps, self.ci) is not None:
             self.small = "ci"
             self.kpad = small_k(self.taps, self.ci)
             self.ws = torch.empty(self.co, self.kpad, dtype=torch.bfloat16, device=dev)
-        elif self.co <= 8 and small_k(self.taps, self.co) is not None:
+        elif self.co < 8 and small_k(self.taps, self.co) is not None:
             self.small = "co"
             self.kpad = small_k(self.taps, self.co)
             self.ws = torch.empty(self.ci, self.kpad, dtype=torch.bfloat16, device=dev)

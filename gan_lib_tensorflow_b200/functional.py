@@ -133,7 +133,7 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     alpha = sn.inv_sigma if sn is not None else None
     bias = b.data if b is not None else None
     res = residual.data if residual is not None else None
-    small_in, small_out = cin <= 8, cout <= 8
+    small_in, small_out = cin < 8, cout < 8   # 8 channels already satisfy the 16-byte rows of the TMA path
     kp_in, kp_out = small_k(taps, cin), small_k(taps, cout)
     route_in = small_in and kp_in is not None and cout % 8 == 0
     route_out = (not small_in) and small_out and kp_out is not None and cin % 8 == 0 and stride == 1

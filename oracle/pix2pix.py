@@ -1,0 +1,80 @@
+"""TEST INFRASTRUCTURE -- CPU oracle (torch fp32/fp64) restating Pix2Pix/networks.py:25-43, 174-354 (unet_g, unet_d,
+norm_layer) line by line on top of oracle.ops.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg
+may import it.  Parity unpinned by the reference (no tests / golden vectors exist upstream, TensorFlow 1.5 is not
+installable here); dropout keep-masks are inputs because TF's op RNG cannot be restated.  The Self_Attn calls of the
+reference are unrunnable and are omitted, as in the product."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from . import resnet_block as rb
+
+
+def norm_layer(g, inputs, decay=0.9, epsilon=1e-5, is_training=True, norm_type="BN"):
+    """Pix2Pix/networks.py:25-43"""
+    if norm_type == "BN":
+        return ops.batch_norm(g, inputs, decay=decay, epsilon=epsilon, is_training=True)
+    if norm_type == "IN":
+        return ops.instance_norm(g, inputs, epsilon=epsilon)
+    raise NotImplementedError("Normalization [%s] is not implemented!" % norm_type)
+
+
+def _conv(g, x, out_channels, stride, padding, sn=False, uc=None):
+    return ops.Conv2D(g, x, x.shape[-1], out_channels, 4, stride, "Conv2D", padding=padding, spectral_normed=sn,
+                      update_collection=uc, inputs_norm=False, he_init=True, biases=True)
+
+
+def unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME", keep_masks=None):
+    """Pix2Pix/networks.py:174-284"""
+    layers = []
+    with g.variable_scope("encoder_1"):
+        layers.append(_conv(g, generator_inputs, ngf, 2, padding))                               # :178-185
+    for out_channels in (ngf * 2, ngf * 4, ngf * 8, ngf * 8, ngf * 8, ngf * 8, ngf * 8):         # :187-195
+        with g.variable_scope("encoder_%d" % (len(layers) + 1)):
+            rectified = rb.nonlinearity(layers[-1], "lrelu", 0.2)                                 # :199
+            convolved = _conv(g, rectified, out_channels, 2, padding)                            # :201-206
+            layers.append(norm_layer(g, convolved, epsilon=1e-5, norm_type="IN"))                # :207
+    layer_specs = [(ngf * 8, 0.5), (ngf * 8, 0.5), (ngf * 8, 0.5), (ngf * 8, 0.0), (ngf * 4, 0.0), (ngf * 2, 0.0),
+                   (ngf, 0.0)]                                                                   # :214-222
+    num_encoder_layers = len(layers)
+    for decoder_layer, (out_channels, dropout) in enumerate(layer_specs):
+        skip_layer = num_encoder_layers - decoder_layer - 1
+        with g.variable_scope("decoder_%d" % (skip_layer + 1)):
+            if decoder_layer == 0:
+                inputs = layers[-1]
+            else:
+                inputs = torch.cat([layers[-1], layers[skip_layer]], dim=3)                      # :233
+            rectified = torch.relu(inputs)                                                       # :235
+            resized = rb.upsample2(rectified)                                                    # :241-243 (nearest 2x)
+            output = _conv(g, resized, out_channels, 1, padding)                                 # :247-251
+            output = norm_layer(g, output, epsilon=1e-5, norm_type="IN")                         # :256
+            if dropout > 0.0 and keep_masks is not None:                                         # :263-264
+                output = output * keep_masks[decoder_layer] / (1.0 - dropout)
+            layers.append(output)
+    with g.variable_scope("decoder_1"):                                                          # :268-282
+        inputs = torch.cat([layers[-1], layers[0]], dim=3)
+        resized = rb.upsample2(torch.relu(inputs))
+        output = torch.tanh(_conv(g, resized, generator_outputs_channels, 1, padding))
+        layers.append(output)
+    unet_g.last_layers = layers   # kept for layer-by-layer parity probes
+    return layers[-1]
+
+
+def unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding="VALID"):
+    """Pix2Pix/networks.py:287-354"""
+    n_layers = 3
+    pad = lambda t: torch.nn.functional.pad(t, (0, 0, 1, 1, 1, 1))  # noqa: E731  tf.pad [[0,0],[1,1],[1,1],[0,0]]
+    inputs = torch.cat([discrim_inputs, discrim_targets], dim=3)                                  # :293
+    with g.variable_scope("layer_1"):                                                            # :296-307
+        convolved = _conv(g, pad(inputs), ndf, 2, padding, spectral_normed, update_collection)
+        layers = [rb.nonlinearity(convolved, "lrelu", 0.2)]
+    for i in range(n_layers):                                                                    # :312-337
+        with g.variable_scope("layer_%d" % (len(layers) + 1)):
+            out_channels_ = ndf * min(2 ** (i + 1), 8)
+            stride = 1 if i == n_layers - 1 else 2
+            convolved = _conv(g, pad(layers[-1]), out_channels_, stride, padding, spectral_normed, update_collection)
+            layers.append(rb.nonlinearity(convolved, "lrelu", 0.2))
+    with g.variable_scope("layer_%d" % (len(layers) + 1)):                                       # :340-352
+        layers.append(_conv(g, pad(layers[-1]), 1, 1, padding, spectral_normed, update_collection))
+    return layers[-1]

@@ -20,6 +20,9 @@ pytestmark = pytest.mark.gpu
     (4, 32, 32, 3, 64, 4, 2, False),      # RGB encoder_1: 48 im2col columns (64-wide route), stride 2
     (2, 32, 32, 6, 64, 4, 2, True),       # PatchGAN input (image + target = 6 channels): 96 columns
     (2, 16, 16, 128, 1, 4, 1, True),      # PatchGAN head: Cout = 1
+    (2, 32, 32, 16, 3, 4, 1, False),      # U-Net decoder_1: 4x4 s1 SAME to RGB (48 im2col columns on the gradient side)
+    (1, 64, 64, 8, 8, 4, 2, False),       # 8-channel layers (ngf = 8)
+    (1, 64, 64, 16, 8, 4, 1, False),
 ])
 def test_strided_conv2d_matches_oracle(env, n, h, w, cin, cout, k, stride, sn):
     store, tfshim = env
@@ -149,3 +152,70 @@ def test_concat_channels_and_dropout(env):
     assert rel(out.data.cpu().numpy(), ref) < 1e-7
     assert rel(av.grad.cpu().numpy(), dref[..., :64]) < 1e-7
     assert rel(bv.grad.float().cpu().numpy(), dref[..., 64:]) < 4e-3     # bf16 gradient storage
+
+
+# ------------------------------------------------------------------------------------------------ Pix2Pix networks
+def check_band(prod, refs, factor=2.0, floor=2e-3, tag=""):
+    """Deep composites (16 convolutions, instance norms in between): two bf16 implementations whose fp32 accumulators
+    differ by 1e-7 flip a few bf16 roundings per layer, the flips compound (x3-10 per layer, tests/probe_unet_layers.py)
+    and both end at the bf16 noise floor.  The band is therefore measured, not assumed: the product must be as close
+    to the fp32 oracle as the bf16-operand ORACLE is (x factor), tensor by tensor."""
+    from tests.test_gpu_ops import _report
+    f32, b16 = refs["fp32"], refs["bf16"]
+    pairs = [("out", prod["out"], b16["out"], f32["out"])]
+    if f32["dx"] is not None:
+        pairs.append(("dx", prod["dx"], b16["dx"], f32["dx"]))
+    gmax = max([np.linalg.norm(g) for g in f32["params"].values()] + [1e-30])
+    worst = []
+    for name, gr in f32["params"].items():
+        if np.linalg.norm(gr) < 5e-2 * gmax:
+            continue   # analytically-zero gradients (biases in front of a norm) hold rounding residue only
+        pairs.append((name, prod["params"][name], b16["params"][name], gr))
+    for name, p, b, f in pairs:
+        e_prod, e_orc = rel(p, f), rel(b, f)
+        worst.append((e_prod / (factor * e_orc + floor), name, e_prod, e_orc))
+    worst.sort(reverse=True)
+    _report(f"band {tag}: " + " ".join(f"{n}={ep:.2e}/{eo:.2e}" for _, n, ep, eo in worst[:8]))
+    ratio, name, e_prod, e_orc = worst[0]
+    assert ratio <= 1.0, (name, e_prod, e_orc)
+def test_pix2pix_unet_generator(env):
+    """Pix2Pix/networks.py:174-284, ngf = 8, with dropout masks, at 512x512 so that the bottleneck is 2x2: at the
+    256x256 of config 4 the instance norm of encoder_8 sees ONE pixel, its output is `beta` plus the rounding residue
+    of x*inv + (beta - mean*inv) (tf.nn.batch_normalization's formula), and the relu mask behind it is decided by that
+    residue -- no two implementations (TF included) agree there, so the parity test keeps every norm well-posed."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.Pix2Pix import networks as P
+    from oracle import pix2pix as OP
+
+    n, ngf, size = 1, 8, 512
+    rs = np.random.RandomState(51)
+    x = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    masks = [(rs.uniform(size=(n, s, s, ngf * 8)) < 0.5).astype("float32") for s in (4, 8, 16)]
+    cot = rs.standard_normal((n, size, size, 3)).astype("float32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.unet_g(xv, 3, ngf, keep_masks=[torch.from_numpy(m).cuda() for m in masks]),
+        lambda g, xt: OP.unet_g(g, xt, 3, ngf, keep_masks=[torch.from_numpy(m) for m in masks]),
+        x, cot_np=cot)
+    assert rel(prod["out"], refs["bf16"]["out"]) < 1e-2
+    check_band(prod, refs, tag="unet_g")
+
+
+def test_pix2pix_patchgan_discriminator(env):
+    """Pix2Pix/networks.py:287-354 at 64x64: [n,64,64,3]x2 -> [n,6,6,1], spectral-normed."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.Pix2Pix import networks as P
+    from oracle import ops as O
+    from oracle import pix2pix as OP
+
+    n, ndf = 3, 16
+    rs = np.random.RandomState(52)
+    x = rs.uniform(-1, 1, size=(n, 64, 64, 3)).astype("float32")
+    tgt = rs.uniform(-1, 1, size=(n, 64, 64, 3)).astype("float32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.unet_d(xv, F.Var(torch.from_numpy(tgt).cuda()), ndf, True, "NO_OPS"),
+        lambda g, xt: OP.unet_d(g, xt, torch.from_numpy(tgt), ndf, True, O.NO_OPS), x)
+    assert prod["out"].shape == (n, 6, 6, 1)
+    check(prod, refs, tol_impl=6e-3, tol_fp32=1e-1, tag="unet_d")   # 5 layers of lrelu-mask sensitivity vs fp32
