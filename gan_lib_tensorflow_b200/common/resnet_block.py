@@ -48,12 +48,14 @@ def _normalize_kind(name, labels, spectral_normed):
     return None
 
 
-def _norm_act(name, inputs, labels, kind, act, upsample=False, want_raw=False, out_dtype=BF16):
-    """Normalize(name, inputs) followed by nonlinearity(), fused. Returns (out, raw_bf16_or_None)."""
+def _norm_act(name, inputs, labels, kind, act, upsample=False, want_raw=False, out_dtype=BF16, n_labels=10):
+    """Normalize(name, inputs) followed by nonlinearity(), fused. Returns (out, raw_bf16_or_None).
+    n_labels: 10 is hard-wired in the library's Normalize (resnet_block.py:43) and the CIFAR script; the ImageNet
+    script's copy uses 1000 (gan_imagNet_resnet.py:104)."""
     store = get_store()
     with store.variable_scope(name):
         if kind == 'cbn':
-            res = _norm.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=10, act=act,
+            res = _norm.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=n_labels, act=act,
                                        upsample=upsample, out_dtype=out_dtype, want_raw=want_raw)
         elif kind == 'bn':
             res = _norm.batch_norm(inputs, fused=True, act=act, upsample=upsample, out_dtype=out_dtype,
@@ -110,7 +112,7 @@ def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None,
 def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
                   spectral_normed=False, update_collection=None, inputs_norm=False,
                   resample=None, labels=None, biases=True, activation_fn='relu',
-                  normalize_kind=None, pre_activated=None, out_dtype=None):
+                  normalize_kind=None, pre_activated=None, out_dtype=None, n_labels=10):
     """resample: None, 'down', or 'up' -- common/resnet_block.py:100-156.
 
     out_dtype=torch.bfloat16 stores the block output (the input of the next block's normalisation) in bf16; the sum
@@ -136,7 +138,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     else:
         x32 = F.as_var(inputs)
         a1, raw = _norm_act(name + '.N1', x32, labels, kind(name + '.N1'), activation_fn,
-                            upsample=(resample == 'up'), want_raw=not identity_shortcut)
+                            upsample=(resample == 'up'), want_raw=not identity_shortcut, n_labels=n_labels)
 
     # ---- shortcut (reference order: the shortcut variables are created before Conv1's)
     if identity_shortcut:
@@ -156,7 +158,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16, out_dtype=BF16)
 
     # ---- N2 + nonlinearity
-    a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn)
+    a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn, n_labels=n_labels)
 
     # ---- Conv2 (+ residual in the epilogue) [+ mean-pool of the sum]
     if resample == 'down':

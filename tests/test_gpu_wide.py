@@ -219,3 +219,54 @@ def test_pix2pix_patchgan_discriminator(env):
         lambda g, xt: OP.unet_d(g, xt, torch.from_numpy(tgt), ndf, True, O.NO_OPS), x)
     assert prod["out"].shape == (n, 6, 6, 1)
     check(prod, refs, tol_impl=6e-3, tol_fp32=1e-1, tag="unet_d")   # 5 layers of lrelu-mask sensitivity vs fp32
+
+
+# ------------------------------------------------------------------------------------------------ SNGAN ImageNet-128
+def test_imagenet_generator_forward_full_width(env):
+    """gan_imagNet_resnet.py:241-271 at the real widths (DIM_G = 128: 1024 -> 64 channels, 4x4 -> 128x128), 1000-class
+    conditional batch norm; forward against both oracles."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.SNGAN import gan_imagNet_resnet as P
+    from oracle import ops as O_ops
+    from oracle import sngan_imagenet as OI
+
+    n = 4
+    rs = np.random.RandomState(61)
+    z = rs.standard_normal((n, 128)).astype("float32")
+    labels = rs.randint(0, 1000, size=n).astype("int32")
+    np.random.seed(0)
+    out = P.Generator(n, torch.from_numpy(labels).cuda(), noise=torch.from_numpy(z).cuda())
+    got = out.data.float().cpu().numpy()
+    assert got.shape == (n, 49152)
+    errs = {}
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        np.random.seed(0)
+        g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+        with torch.no_grad():
+            ref = OI.Generator(g, n, torch.from_numpy(labels).long(), torch.from_numpy(z)).numpy()
+        errs[mode] = rel(got, ref)
+    O_ops.BF16_OPERANDS = False
+    assert errs[True] < 2e-2 and errs[False] < 3e-2, errs      # 16 bf16 layers deep, batch statistics over 4 samples
+    assert set(v.key for v in store.trainable_variables("Generator")) == set(n_ for n_, _ in g.trainable_variables())
+
+
+def test_imagenet_discriminator_full_width(env):
+    """gan_imagNet_resnet.py:274-334 at DIM_D = 128 (64 -> 1024 channels, label map concatenated at 16x16)."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.SNGAN import gan_imagNet_resnet as P
+    from oracle import ops as O
+    from oracle import sngan_imagenet as OI
+
+    n = 2
+    rs = np.random.RandomState(62)
+    x = rs.uniform(-1, 1, size=(n, 49152)).astype("float32")
+    labels = rs.randint(0, 1000, size=n).astype("int32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.Discriminator(xv, torch.from_numpy(labels).cuda(), update_collection="NO_OPS")[0],
+        lambda g, xt: OI.Discriminator(g, xt, torch.from_numpy(labels).long(), update_collection=O.NO_OPS)[0],
+        x, cot_np=rs.standard_normal((n,)).astype("float32"))
+    assert rel(prod["out"], refs["bf16"]["out"]) < 5e-3
+    check_band(prod, refs, tag="imagenet_d")
