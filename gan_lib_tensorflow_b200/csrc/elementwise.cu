@@ -1398,9 +1398,11 @@ extern "C" int64_t ganb_bn_stats_workspace(int n, int hw, int c, int groups) {
   return static_cast<int64_t>(groups) * 1024 * 2 * c * 4;
 }
 
+// Four blocks per SM are needed to keep HBM busy (two measured 80 % slower); small tensors get at least 128 rows per
+// chunk (the finalize kernels are latency-bound on the number of partials).
 static int stats_chunks(int rows_per_group, int groups) {
   int chunks = ceil_div(4 * sm_count(), groups);
-  const int max_chunks = ceil_div(rows_per_group, 32);
+  const int max_chunks = ceil_div(rows_per_group, 128);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks > 1024) chunks = 1024;
   if (chunks < 1) chunks = 1;
@@ -1440,6 +1442,18 @@ static int bwd_chunks(int n, int hw) {
   return chunks;
 }
 
+// The 8-channel kernels are launched as ONE wave of long-running blocks: floor(resident blocks / n) pixel chunks per
+// sample (>= 64 pixels each).  Many short blocks spent their time in the per-block prologue (constants, label lookup)
+// and epilogue (shared-memory reduction) -- the reduce kernel ran at 44 % of its HBM time.  Always <= bwd_chunks().
+static int v8_chunks(int n, int hw, int blocks_per_sm) {
+  int chunks = (sm_count() * blocks_per_sm) / (n > 0 ? n : 1);
+  const int max_chunks = hw / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int cap = bwd_chunks(n, hw);
+  return chunks < cap ? chunks : cap;
+}
+
 extern "C" int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w, int c, const float* mean, const float* rstd,
                                  int groups, const float* gamma, const float* beta, const int* labels, int act,
                                  int upsample, void* out, int out_dtype, int out_cstride, void* out_raw_bf16,
@@ -1454,9 +1468,9 @@ extern "C" int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w
   p.act = act; p.upsample = upsample;
   p.out = out; p.out_bf16 = (out_dtype == GANB_BF16); p.out_cstride = out_cstride > 0 ? out_cstride : c;
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
-  const int chunks = bwd_chunks(n, h * w);
-  const int ppc = ceil_div(h * w, chunks);
   const bool v8 = p.x_bf16 && p.out_bf16 && !p.out_raw && c % 8 == 0 && p.out_cstride % 8 == 0;
+  const int chunks = v8 ? v8_chunks(n, h * w, 3) : bwd_chunks(n, h * w);
+  const int ppc = ceil_div(h * w, chunks);
   if (v8 && upsample) launch_k(norm_act_fwd_v8_kernel<true>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
   else if (v8) launch_k(norm_act_fwd_v8_kernel<false>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
   else if (p.x_bf16) launch_k(norm_act_fwd_kernel<__nv_bfloat16>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
@@ -1516,7 +1530,7 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
   if (mean) {
     if (!workspace) return fail(GANB_E_BADARG, "norm_act_bwd: workspace required with normalisation");
     const int hw = h * w;
-    const int chunks = bwd_chunks(n, hw);
+    const int chunks = v8 ? v8_chunks(n, hw, 2) : bwd_chunks(n, hw);
     p.pix_per_chunk = ceil_div(hw, chunks);
     p.chunks = ceil_div(hw, p.pix_per_chunk);
     p.part = static_cast<float*>(workspace);
@@ -1541,7 +1555,7 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
     p.inv_count = 1.0f / (static_cast<float>(n / groups) * hw);
   }
   {
-    const int chunks2 = bwd_chunks(n, h * w);
+    const int chunks2 = v8 ? v8_chunks(n, h * w, 2) : bwd_chunks(n, h * w);
     const int ppc = ceil_div(h * w, chunks2);
     const dim3 grid(ceil_div(h * w, ppc), n);
     if (v8) {
@@ -1704,7 +1718,7 @@ static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float*
   }
   const bool narrow = (c % 4 != 0);
   int chunks = narrow ? sm_count() : 4 * sm_count();
-  const int64_t max_chunks = ceil_div64(rows, narrow ? 256 : 32);
+  const int64_t max_chunks = ceil_div64(rows, narrow ? 256 : 128);
   if (chunks > max_chunks) chunks = static_cast<int>(max_chunks);
   if (chunks > 1024) chunks = 1024;
   if (chunks < 1) chunks = 1;
