@@ -33,8 +33,8 @@ def Linear(inputs, input_dim, output_dim, name,
     store = get_store()
     inputs = F.as_var(inputs)
     with store.variable_scope(name):
-        if inputs_norm:
-            raise NotImplementedError('inputs_norm is not wired yet (PGGAN, SURVEY 8(f))')
+        in_scale = float(np.sqrt(2.0 / input_dim)) if inputs_norm else None   # linear.py:47-49
+        kw = {'in_scale': in_scale} if in_scale is not None else {}
 
         def uniform(stdev, size):
             if _weights_stdev is not None:
@@ -76,8 +76,9 @@ def Linear(inputs, input_dim, output_dim, name,
             _biases = store.get_variable(name='b', shape=[output_dim, ],
                                          initializer=lambda s: np.zeros(s, dtype='float32'))
         if len(inputs.shape) == 2:
-            return F.linear(inputs, weight, _biases, sn=sn_entry, **({'out_dtype': out_dtype} if out_dtype is not None else {}))
+            return F.linear(inputs, weight, _biases, sn=sn_entry, **kw,
+                            **({'out_dtype': out_dtype} if out_dtype is not None else {}))
         lead = inputs.shape[:-1]
         flat = F.reshape(inputs, (-1, input_dim))
-        result = F.linear(flat, weight, _biases, sn=sn_entry)
+        result = F.linear(flat, weight, _biases, sn=sn_entry, **kw)
         return F.reshape(result, tuple(lead) + (output_dim,))

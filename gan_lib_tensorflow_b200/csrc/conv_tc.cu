@@ -34,6 +34,12 @@ struct IgemmParams {
   int res_up2;   // residual is stored at half resolution [N, Ho/2, Wo/2, Cout] and read through a nearest-2x upsample
   void* out;
   int out_bf16, act;
+  // Convolution groups over ONE input (sub-pixel form of UpsampleConv, see ganb_conv2d_up2_*): `og` output groups =
+  // every pixel tile is computed og times with its own filter taps, padding and output channel offset g*Cout (output
+  // pixel stride out_cstride); `rg` reduction groups = the K loop runs over rg channel slices of the input, each with its
+  // own taps and padding.  At most one of og / rg exceeds 1.
+  int og, rg, out_cstride;
+  signed char gpad_t[4], gpad_l[4];
 };
 
 template <int NC>
@@ -67,10 +73,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // per float4 (this was the limiter of the first version of this kernel, profiles/r01_*).
 template <int NC>
 __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_t (&r)[NC], float alpha,
-                                             int64_t pix, int64_t res_pix, int co_base,
+                                             int64_t out_off, int64_t res_pix, int co_base,
                                              const float* __restrict__ bias_s) {
   const int cout = p.Cout;
-  const int64_t off = pix * cout + co_base;
+  const int64_t off = out_off + co_base;           // out_off = pixel * out_cstride + group channel offset
   const int64_t roff = res_pix * cout + co_base;
   if (cout % 4 == 0) {
     float4 v[NC / 4];
@@ -195,7 +201,7 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
       uint32_t r[NC];
       tmem_ld_cols<NC>(trow + c * NC, r);
       tmem_ld_wait();
-      if (valid) epilogue_row<NC>(p, r, alpha, pix, res_pix, tco * BN + c * NC, &bias_s[as][c * NC]);
+      if (valid) epilogue_row<NC>(p, r, alpha, pix * p.out_cstride, res_pix, tco * BN + c * NC, &bias_s[as][c * NC]);
     }
     tc_fence_before();
     mbar_arrive(&tempty[as]);
@@ -650,7 +656,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int pair_tiles = ((m_tiles + 1) >> 1) * p.tiles_co;   // work items of a cluster
+  const int pair_tiles = ((m_tiles + 1) >> 1) * p.tiles_co * p.og;   // work items of a cluster
+  const int tiles_cg = p.tiles_co * p.og;                            // (filter tile, output group) per pixel-tile pair
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -676,16 +683,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t pb = 0;
     for (int tile = pair; tile < pair_tiles; tile += num_pairs) {
       const int co0 = (tile % p.tiles_co) * BN + static_cast<int>(rank) * BH;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int tap_b = p.flip ? (p.taps - 1 - tap) : tap;
-          mbar_wait(&emptyB[sb], pb ^ 1);
-          if (elect_one()) {
-            if (rank == 0) mbar_arrive_expect_tx(&fullB[sb], 2 * B_STAGE_BYTES);
-            tma_load_3d_pair(sB + sb * B_STAGE_BYTES, &tmB, &fullB[sb], kc * BK, co0, tap_b);
+      const int go = (tile / p.tiles_co) % p.og;
+      for (int gr = 0; gr < p.rg; ++gr) {
+        const int tap_base = (go + gr) * p.taps;   // at most one of og / rg exceeds 1
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int tap_b = tap_base + (p.flip ? (p.taps - 1 - tap) : tap);
+            mbar_wait(&emptyB[sb], pb ^ 1);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(&fullB[sb], 2 * B_STAGE_BYTES);
+              tma_load_3d_pair(sB + sb * B_STAGE_BYTES, &tmB, &fullB[sb], kc * BK, co0, tap_b);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
           }
-          __syncwarp();
-          if (++sb == SB) { sb = 0; pb ^= 1; }
         }
       }
     }
@@ -694,18 +705,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int sa = 0;
     uint32_t pa = 0;
     for (int tile = pair; tile < pair_tiles; tile += num_pairs) {
-      int t = 2 * (tile / p.tiles_co) + static_cast<int>(rank);   // pixel tile of this CTA
+      int t = 2 * (tile / tiles_cg) + static_cast<int>(rank);     // pixel tile of this CTA
+      const int go = (tile / p.tiles_co) % p.og;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;                // t = image; past the batch -> TMA zero fill
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait(&emptyA[sa], pa ^ 1);
-        if (elect_one()) {
-          if (rank == 0) mbar_arrive_expect_tx(&fullA[sa], 2 * halo_bytes);
-          tma_load_4d_pair(sA + sa * a_stage_bytes, &tmA, &fullA[sa], kc * BK, tw * p.bw - p.pad_l,
-                           th * p.bh - p.pad_t, t);
+      for (int gr = 0; gr < p.rg; ++gr) {
+        const int g = go + gr;
+        const int pad_t = (p.og * p.rg > 1) ? p.gpad_t[g] : p.pad_t, pad_l = (p.og * p.rg > 1) ? p.gpad_l[g] : p.pad_l;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&emptyA[sa], pa ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&fullA[sa], 2 * halo_bytes);
+            tma_load_4d_pair(sA + sa * a_stage_bytes, &tmA, &fullA[sa], (gr * p.kchunks + kc) * BK, tw * p.bw - pad_l,
+                             th * p.bh - pad_t, t);
+          }
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pa ^= 1; }
         }
-        __syncwarp();
-        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -723,7 +739,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         uint32_t acc = 0;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int a_stages = p.rg * p.kchunks;   // one halo per (reduction group, channel chunk)
+        for (int kc = 0; kc < a_stages; ++kc) {
           mbar_wait(&fullA[sa], pa);
           uint32_t a_row = sA_addr + sa * a_stage_bytes;
           for (int r = 0; r < kh; ++r, a_row += sbo) {
@@ -766,7 +783,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t aphase = 0;
     for (int tile = pair; tile < pair_tiles; tile += num_pairs) {
       const int tco = tile % p.tiles_co;
-      int t = 2 * (tile / p.tiles_co) + static_cast<int>(rank);
+      const int go = (tile / p.tiles_co) % p.og;
+      int t = 2 * (tile / tiles_cg) + static_cast<int>(rank);
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int wo = tw * p.bw + iw, ho = th * p.bh + ih, n = t;
@@ -789,7 +807,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[NC];
         tmem_ld_cols<NC>(trow + c * NC, r);
         tmem_ld_wait();
-        if (valid) epilogue_row<NC>(p, r, alpha, pix, res_pix, tco * BN + c * NC, &bias_s[as][c * NC]);
+        if (valid)
+          epilogue_row<NC>(p, r, alpha, pix * p.out_cstride + go * p.Cout, res_pix, tco * BN + c * NC,
+                           &bias_s[as][c * NC]);
       }
       tc_fence_before();
       __syncwarp();
@@ -1136,6 +1156,8 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   p.res_up2 = (residual && residual_up2) ? 1 : 0;
   if (p.res_up2 && ((ho | wo) & 1)) return fail(GANB_E_BADARG, "conv2d_igemm: upsampled residual needs even ho, wo");
   p.out = y; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
+  p.og = 1; p.rg = 1; p.out_cstride = cout;
+  for (int i = 0; i < 4; ++i) { p.gpad_t[i] = 0; p.gpad_l[i] = 0; }
 
   // choose the N tile with a two-term cost model (cycles): tensor time = waves x k-iterations x MMA cycles of a tile,
   // operand time = bytes crossing L2->SMEM / what the chip (~6500 B/clk measured) or the active SMs (~64 B/clk

@@ -1020,13 +1020,14 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x,
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 u = ld4(x + i * 4);
-    float4 w = ld4(y + i * 4);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b != 0.f) w = ld4(y + i * 4);     // b == 0: y may be uninitialised (NaN * 0 would poison the result)
     w.x = a * u.x + b * w.x; w.y = a * u.y + b * w.y; w.z = a * u.z + b * w.z; w.w = a * u.w + b * w.w;
     st4(y + i * 4, w);
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
-    y[i] = a * x[i] + b * y[i];
+    y[i] = a * x[i] + (b != 0.f ? b * y[i] : 0.f);
   }
 }
 

@@ -275,9 +275,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ganb_pack_layer
   const int tci = local % tiles_ci; local /= tiles_ci;
   const int tap = local;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int cip = L.ci_pad > L.ci ? L.ci_pad : L.ci;   // channel count of the operand copies (zero rows beyond ci)
   const float* w = L.w + static_cast<int64_t>(tap) * L.ci * L.co;
-  __nv_bfloat16* wn = L.wn ? static_cast<__nv_bfloat16*>(L.wn) + static_cast<int64_t>(tap) * L.ci * L.co : nullptr;
-  __nv_bfloat16* wt = L.wt ? static_cast<__nv_bfloat16*>(L.wt) + static_cast<int64_t>(tap) * L.ci * L.co : nullptr;
+  __nv_bfloat16* wn = L.wn ? static_cast<__nv_bfloat16*>(L.wn) + static_cast<int64_t>(tap) * cip * L.co : nullptr;
+  __nv_bfloat16* wt = L.wt ? static_cast<__nv_bfloat16*>(L.wt) + static_cast<int64_t>(tap) * cip * L.co : nullptr;
   for (int j = ty; j < 32; j += 8) {
     const int ci = tci * 32 + j, co = tco * 32 + tx;
     float v = 0.f;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ganb_pack_layer
   if (wt) {
     for (int j = ty; j < 32; j += 8) {
       const int co = tco * 32 + j, ci = tci * 32 + tx;
-      if (ci < L.ci && co < L.co) wt[static_cast<int64_t>(co) * L.ci + ci] = __float2bfloat16_rn(tile[tx][j]);
+      if (ci < L.ci && co < L.co) wt[static_cast<int64_t>(co) * cip + ci] = __float2bfloat16_rn(tile[tx][j]);
     }
   }
 }

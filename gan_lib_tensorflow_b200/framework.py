@@ -310,8 +310,12 @@ class PackEntry:
         self.ci = shape[-2]
         self.taps = w.data.numel() // (self.ci * self.co)
         dev = w.data.device
-        self.wn = torch.empty(self.taps, self.ci, self.co, dtype=torch.bfloat16, device=dev)  # [tap][ci][co]
-        self.wt = torch.empty(self.taps, self.co, self.ci, dtype=torch.bfloat16, device=dev)  # [tap][co][ci]
+        # input channels of the operand copies: ragged counts above 8 (513 behind minibatch_std) are zero-padded to
+        # the next multiple of 8 so that every row meets the 16-byte granularity of the TMA path
+        self.ci_pad = self.ci if (self.ci < 8 or self.ci % 8 == 0) else (self.ci + 7) // 8 * 8
+        alloc = torch.zeros if self.ci_pad != self.ci else torch.empty
+        self.wn = alloc(self.taps, self.ci_pad, self.co, dtype=torch.bfloat16, device=dev)  # [tap][ci][co]
+        self.wt = alloc(self.taps, self.co, self.ci_pad, dtype=torch.bfloat16, device=dev)  # [tap][co][ci]
         # <=8-channel side: [large channel][tap*cs + c] padded to SMALL_K columns (operand of the im2col route)
         self.small = None
         self.ws = None
@@ -357,7 +361,7 @@ class PackGroup:
             items, tiles = [], 0
             for e in entries:
                 items.append(K.PackLayerStruct(e.w.data.data_ptr(), e.wn.data_ptr(), e.wt.data_ptr(), e.taps, e.ci,
-                                               e.co, tiles))
+                                               e.co, tiles, e.ci_pad, 0))
                 tiles += e.taps * (-(-e.ci // 32)) * (-(-e.co // 32))
             self.table = K.struct_array_to_device(items, entries[0].w.data.device)
             self.total_tiles = tiles
@@ -384,6 +388,7 @@ class VariableStore:
         self.u_rng = np.random.RandomState(u_seed)
         self.tape: Tape | None = None
         self.stat_groups = 1
+        self._consts: dict[float, torch.Tensor] = {}
 
     # -- scopes ---------------------------------------------------------------------------------
     @contextlib.contextmanager
@@ -467,6 +472,15 @@ class VariableStore:
         self._u_versions[root] = self._u_versions.get(root, 0) + 1
 
     # -- helpers --------------------------------------------------------------------------------
+    def const(self, value: float) -> torch.Tensor:
+        """Device-resident fp32 scalar (the `alpha` of a GEMM epilogue that is not a 1/sigma), cached by value."""
+        value = float(value)
+        t = self._consts.get(value)
+        if t is None:
+            t = torch.full((1,), value, dtype=torch.float32, device=self.device)
+            self._consts[value] = t
+        return t
+
     def sn_group(self, root) -> SNGroup:
         g = self.sn_groups.get(root)
         if g is None:

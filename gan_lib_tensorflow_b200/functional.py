@@ -89,6 +89,29 @@ def add(a: Var, b: Var) -> Var:
     return out
 
 
+def lerp(a: Var, b: Var, alpha: float) -> Var:
+    """(1 - alpha) * a + alpha * b in fp32: the fade-in of PGGAN (PGGAN/model_nvidia.py:118, :200)."""
+    alpha = float(alpha)
+    a32 = a if a.data.dtype == F32 else cast(a, F32)
+    b32 = b if b.data.dtype == F32 else cast(b, F32)
+    assert a32.shape == b32.shape
+    data = K.cast(a32.data, F32, scale=1.0 - alpha)   # scaled copy
+    K.axpby(b32.data, data, alpha, 1.0)
+    out = Var(data)
+    if _rg(a32, b32):
+        out.requires_grad = True
+
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            for v, s in ((a32, 1.0 - alpha), (b32, alpha)):
+                if v.requires_grad:
+                    v.accum(K.cast(g, v.gdtype, scale=s))
+        _tape().record(bwd)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ convolution
 def _pads(padding, h, w, kh, kw, stride):
     if padding == "SAME":
@@ -123,14 +146,20 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     stride > 1 (Pix2Pix encoders / PatchGAN): the forward and filter-gradient kernels gather every stride-th pixel
     through TMA element strides; the data gradient is the stride-1 kernel applied to the zero-dilated output
     gradient (correct for any TF padding; the structural zeros cost stride^2 more MMA work than necessary)."""
-    if in_scale is not None:
-        raise NotImplementedError("inputs_norm is not wired into the convolution epilogue yet")
     store = get_store()
     n, h, w, cin = x.shape
     cout = W.data.shape[-1]
+    if cin > 8 and cin % 8:
+        return _conv2d_ragged_cin(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale,
+                                  residual_up2, out_dtype)
     taps = kh * kw
     pt, pl, ho, wo = _pads(padding, h, w, kh, kw, stride)
-    alpha = sn.inv_sigma if sn is not None else None
+    # inputs_norm (conv2d.py:93-95): conv(c * x, W) = c * conv(x, W), so the constant rides on the epilogue's alpha
+    # (and on the filter gradient's scale) instead of costing a pass over x
+    if in_scale is not None and sn is not None:
+        raise NotImplementedError("inputs_norm together with spectral_normed (no reference call-site combines them)")
+    wscale = store.const(in_scale) if in_scale is not None else None
+    alpha = sn.inv_sigma if sn is not None else wscale
     bias = b.data if b is not None else None
     res = residual.data if residual is not None else None
     small_in, small_out = cin < 8, cout < 8   # 8 channels already satisfy the 16-byte rows of the TMA path
@@ -195,20 +224,20 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                 if route_in:
                     r = torch.empty((kp_in, cout), dtype=F32, device=gy.device)
                     K.conv_wgrad(xcol, gy16, r, n, ho, wo, kp_in, ho, wo, cout, 1, 1, 0, 0, None, 0.0)
-                    K.small_wgrad_scatter(r, dst, taps, cin, cout, False, None, beta)
+                    K.small_wgrad_scatter(r, dst, taps, cin, cout, False, wscale, beta)
                 elif route_out:
                     r = torch.empty((kp_out, cin), dtype=F32, device=gy.device)
                     K.conv_wgrad(dycol, xin.data, r, n, h, w, kp_out, h, w, cin, 1, 1, 0, 0, None, 0.0)
-                    K.small_wgrad_scatter(r, dst, taps, cout, cin, True, None, beta)
+                    K.small_wgrad_scatter(r, dst, taps, cout, cin, True, wscale, beta)
                 elif small_in:
                     K.conv_small_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, +1, False,
-                                       None, beta)
+                                       wscale, beta)
                 elif small_out:
                     gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
                     K.conv_small_wgrad(gy32, xin.data, dst, n, ho, wo, cout, h, w, cin, kh, kw, pt, pl, -1, True,
-                                       None, beta)
+                                       wscale, beta)
                 else:
-                    K.conv_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, None, beta,
+                    K.conv_wgrad(xin.data, gy16, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, wscale, beta,
                                  stride=stride)
                 if sn is not None:
                     sn.g_written = True
@@ -242,6 +271,67 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                     dx = K.conv_igemm(gyd, pack.wn, n, hd, wd, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
                                       alpha, None, None, None, gdt)
                 xin.accum(dx)
+        tape.record(bwd)
+    return out
+
+
+def _conv2d_ragged_cin(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale, residual_up2,
+                       out_dtype):
+    """Convolution whose input-channel count is above 8 and not a multiple of 8 (the 513 channels behind
+    minibatch_std, PGGAN/model_nvidia.py:223-229): x and the bf16 operand copies of the filter are zero-padded to the
+    next multiple of 8 channels; the padded rows of the filter gradient / channels of the data gradient are dropped.
+    Such layers sit at 4x4 resolution, so the two extra copies are noise."""
+    if stride != 1 or residual is not None or in_scale is not None:
+        raise NotImplementedError("ragged input-channel counts: only plain stride-1 convolutions are built")
+    store = get_store()
+    n, h, w, cin = x.shape
+    cout = W.data.shape[-1]
+    taps = kh * kw
+    pt, pl, ho, wo = _pads(padding, h, w, kh, kw, 1)
+    group = store.pack_group(W.root)
+    pack = group.entry(W)
+    group.refresh()
+    cp = pack.ci_pad
+    xp = torch.zeros((n, h, w, cp), dtype=BF16, device=x.data.device)
+    K.copy_channels(x.data, 0, xp, 0, cin)
+    alpha = sn.inv_sigma if sn is not None else None
+    y = K.conv_igemm(xp, pack.wt, n, h, w, cp, ho, wo, cout, kh, kw, pt, pl, False, alpha,
+                     b.data if b is not None else None, None, None, out_dtype)
+    out = Var(y, grad_dtype=out_grad_dtype)
+    need_w = W.needs_grad and _tape() is not None
+    need_b = b is not None and b.needs_grad and _tape() is not None
+    if _rg(x) or need_w or need_b:
+        out.requires_grad = True
+        tape = _tape()
+
+        def bwd():
+            gy = out.grad
+            if gy is None:
+                return
+            gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
+            if need_b:
+                K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
+            if need_w:
+                dwp = torch.empty((taps, cp, cout), dtype=F32, device=gy.device)
+                K.conv_wgrad(xp, gy16, dwp, n, h, w, cp, ho, wo, cout, kh, kw, pt, pl, None, 0.0)
+                dw = torch.empty((taps, cin * cout), dtype=F32, device=gy.device)
+                K.copy_channels(dwp.reshape(taps, cp * cout), 0, dw, 0, cin * cout)
+                if sn is not None:
+                    dst, beta = sn.g, (1.0 if sn.g_written else 0.0)
+                else:
+                    dst, beta = W.grad, 1.0
+                K.axpby(dw, dst, 1.0, beta)
+                if sn is not None:
+                    sn.g_written = True
+                    lst = tape.pending_sn.setdefault(W.root, [])
+                    if sn not in lst:
+                        lst.append(sn)
+            if x.requires_grad:
+                dxp = K.conv_igemm(gy16, pack.wn, n, ho, wo, cout, h, w, cp, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
+                                   alpha, None, None, None, F32)
+                dx = torch.empty((n, h, w, cin), dtype=x.gdtype, device=gy.device)
+                K.copy_channels(dxp, 0, dx, 0, cin)
+                x.accum(dx)
         tape.record(bwd)
     return out
 
@@ -301,17 +391,20 @@ def conv2d_transpose(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, 
     return out
 
 
-def linear(x: Var, W: Variable, b: Variable | None, sn=None, out_dtype=F32) -> Var:
+def linear(x: Var, W: Variable, b: Variable | None, sn=None, out_dtype=F32, in_scale: float | None = None) -> Var:
     """tf.matmul(x, W) + b (common/ops/linear.py:161-180) for 2-D x; large layers run as 1x1 convolutions on the
-    tensor cores, tiny ones (in % 8 != 0 or out < 8) on CUDA cores."""
+    tensor cores, tiny ones (in % 8 != 0 or out < 8) on CUDA cores.  in_scale = the inputs_norm constant
+    sqrt(2 / in) (linear.py:47-49), applied as the GEMM's alpha."""
     m, kin = x.shape
     kout = W.data.shape[1]
     if kin % 8 == 0 and kout % 8 == 0 and kin * kout >= 65536:
         x4 = reshape(x, (m, 1, 1, kin))
-        y4 = conv2d(x4, W, b, 1, 1, 1, "VALID", sn=sn, out_dtype=out_dtype)
+        y4 = conv2d(x4, W, b, 1, 1, 1, "VALID", sn=sn, out_dtype=out_dtype, in_scale=in_scale)
         return reshape(y4, (m, kout))
     if out_dtype != F32:
         raise NotImplementedError("bf16 output is only built for the tensor-core linear path")
+    if in_scale is not None:
+        raise NotImplementedError("inputs_norm on the CUDA-core linear path (no reference call-site: G.Input is wide)")
     xin = x if x.data.dtype == F32 else cast(x, F32)
     alpha = sn.inv_sigma if sn is not None else None
     y = torch.empty((m, kout), dtype=F32, device=x.data.device)

@@ -339,7 +339,8 @@ class SnLayerStruct(ctypes.Structure):
 
 class PackLayerStruct(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("wn", c_void_p), ("wt", c_void_p), ("taps", ctypes.c_int32), ("ci", ctypes.c_int32),
-                ("co", ctypes.c_int32), ("tile_begin", ctypes.c_int32)]
+                ("co", ctypes.c_int32), ("tile_begin", ctypes.c_int32), ("ci_pad", ctypes.c_int32),
+                ("pad_", ctypes.c_int32)]
 
 
 def struct_array_to_device(items, device) -> torch.Tensor:

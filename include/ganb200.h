@@ -148,13 +148,17 @@ int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, int total_blo
                        void* stream);
 int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int total_blocks, int max_c, void* stream);
 
-/* fp32 HWIO filters -> bf16 operands of the tensor-core kernels; wn = [tap][ci][co], wt = [tap][co][ci]
- * (either may be NULL).  tile_begin = prefix sum of taps*ceil(ci/32)*ceil(co/32) over the layers. */
+/* fp32 HWIO filters -> bf16 operands of the tensor-core kernels; wn = [tap][ci_pad][co], wt = [tap][co][ci_pad]
+ * (either may be NULL).  ci_pad >= ci (0 = ci) is the input-channel count of the operand copies: rows / columns
+ * ci..ci_pad-1 are left untouched (the caller zeroes them once), so that a filter with ci % 8 != 0 (the 513-channel
+ * convolution behind minibatch_std, PGGAN/model_nvidia.py:223-229) meets the 16-byte rows of the TMA path.
+ * tile_begin = prefix sum of taps*ceil(ci/32)*ceil(co/32) over the layers. */
 typedef struct ganb_pack_layer {
   const float* w;
   void* wn;
   void* wt;
   int32_t taps, ci, co, tile_begin;
+  int32_t ci_pad, pad_;
 } ganb_pack_layer;
 int ganb_pack_weights(const ganb_pack_layer* layers_dev, int count, int total_tiles, void* stream);
 

@@ -43,23 +43,28 @@ class _ConvRoundedOperands(torch.autograd.Function):
     dw = wgrad(r16(x), r16(dy)), dx = dgrad(r16(dy), w) -- the operand roundings of conv_tc.cu."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, padding):
+    def forward(ctx, x, w, stride, padding, scale=1.0):
+        """scale: a constant the product applies in the GEMM epilogue (inputs_norm), i.e. AFTER the rounded
+        contraction in the forward pass and after the rounded-gradient contractions in the backward pass."""
         xr = _r16(x)
         ctx.save_for_backward(xr, w)
-        ctx.cfg = (stride, padding)
-        return conv2d_nhwc(xr, w, stride, padding)
+        ctx.cfg = (stride, padding, scale)
+        y = conv2d_nhwc(xr, w, stride, padding)
+        return y if scale == 1.0 else y * scale
 
     @staticmethod
     def backward(ctx, gy):
         xr, w = ctx.saved_tensors
-        stride, padding = ctx.cfg
+        stride, padding, scale = ctx.cfg
         gyr = _r16(gy)
         with torch.enable_grad():
             x_ = xr.detach().requires_grad_(True)
             w_ = w.detach().requires_grad_(True)
             y = conv2d_nhwc(x_, w_, stride, padding)
             dx, dw = torch.autograd.grad(y, (x_, w_), gyr)
-        return dx, dw, None, None
+        if scale != 1.0:
+            dx, dw = dx * scale, dw * scale
+        return dx, dw, None, None, None
 
 # module-level switches of conv2d.py:10-28 / linear.py:12-35 / deconv2d.py:8-26
 _default_weightnorm = False
@@ -215,7 +220,12 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
             wq = _ste_r16(raw_filters)
             if spectral_normed:
                 wq = wq / sigma
-            result = _ConvRoundedOperands.apply(inputs_, wq, stride, padding)
+            if inputs_norm:
+                # the product keeps the constant outside the tensor-core contraction (the epilogue's alpha):
+                # c * conv(r16(x), r16(W)) -- same value in exact arithmetic, the rounding point moves
+                result = _ConvRoundedOperands.apply(inputs, wq, stride, padding, float(np.sqrt(2.0 / fan_in)))
+            else:
+                result = _ConvRoundedOperands.apply(inputs_, wq, stride, padding)
         else:
             result = conv2d_nhwc(inputs_, filters, stride, padding)   # conv2d.py:181-187
         if biases:                                                    # conv2d.py:212-216
@@ -304,9 +314,11 @@ def Linear(g, inputs, input_dim, output_dim, name, spectral_normed=False, update
         if (BF16_OPERANDS and inputs_.dim() == 2 and input_dim % 8 == 0 and output_dim % 8 == 0
                 and input_dim * output_dim >= 65536 and not spectral_normed):
             # the product runs this layer as a 1x1 convolution on the tensor cores
-            x4 = inputs_.reshape(-1, 1, 1, input_dim)
+            x4 = inputs.reshape(-1, 1, 1, input_dim)
             w4 = _ste_r16(weight).reshape(1, 1, input_dim, output_dim)
-            result = _ConvRoundedOperands.apply(x4, w4, 1, "VALID").reshape(-1, output_dim)
+            # inputs_norm: constant applied as the GEMM's alpha, outside the rounded contraction
+            c = float(np.sqrt(2.0 / input_dim)) if inputs_norm else 1.0
+            result = _ConvRoundedOperands.apply(x4, w4, 1, "VALID", c).reshape(-1, output_dim)
         elif inputs_.dim() == 2:                                      # linear.py:161-165
             result = inputs_ @ w_eff
         else:                                                         # linear.py:166-174

@@ -131,6 +131,37 @@ def test_variable_names_reuse_and_trainable_filter(host):
         conv2d.Conv2D(x, 32, 8, 3, 1, "bad")        # input_dim does not match the tensor
 
 
+def test_pggan_variable_manifest_matches_the_oracle(host):
+    """PGGAN/model_nvidia.py: scope-qualified variable names, shapes and NumPy-RNG initial values of G and D (incl. the
+    fade-in toRGB / fromRGB pairs and the 513-channel D.Conv) agree with the oracle restatement."""
+    store, _ = host
+    from gan_lib_tensorflow_b200.PGGAN import model_nvidia as P
+    from oracle import ops as O
+    from oracle import pggan as OP
+    from oracle import tfshim
+
+    np.random.seed(0)
+    pm = P.PGGAN(block_count=2, trans=True, inputs_norm=True)
+    fake = pm.get_generator(torch.zeros(2, 512), 0.5)
+    assert tuple(fake.shape) == (2, 16, 16, 3)
+    logits = pm.get_discriminator(fake, 0.5, update_collection="NO_OPS")
+    assert tuple(logits.shape) == (2,)
+    np.random.seed(0)
+    g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    om = OP.PGGAN(2, True, True)
+    with torch.no_grad():
+        of = om.get_generator(g, torch.zeros(2, 512), 0.5)
+        om.get_discriminator(g, of, 0.5, update_collection=O.NO_OPS)
+    assert list(store.vars) == list(g.vars)
+    for name, v in store.vars.items():
+        assert tuple(v.data.shape) == tuple(g.vars[name].shape), name
+        if "spectral_norm/u" not in name:
+            np.testing.assert_array_equal(v.data.numpy(), g.vars[name].detach().numpy(), err_msg=name)
+    assert "d_net/D.Conv/Filters" in store.vars and tuple(store.vars["d_net/D.Conv/Filters"].data.shape) == (3, 3, 513, 512)
+    assert "g_net/G.2_toRGB1/Filters" in store.vars and "d_net/D.2_fromRGB2/filters/spectral_norm/u" in store.vars
+    assert [v.key for v in store.trainable_variables("g_net")] == [n for n, _ in g.trainable_variables("g_net")]
+
+
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
     store, _ = host
     from gan_lib_tensorflow_b200.common import resnet_block
