@@ -137,7 +137,13 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
         x32 = None
     else:
         x32 = F.as_var(inputs)
-        a1, raw = _norm_act(name + '.N1', x32, labels, kind(name + '.N1'), activation_fn,
+        n1_in = x32
+        if kind(name + '.N1') in ('cbn', 'bn') and x32.data.dtype == F32:
+            # every input of a batch-statistics normalisation is stored in bf16 (DESIGN.md "Data layout"): an fp32
+            # residual stream (ACGAN's batch-normed D) is rounded once here; statistics, normalise and the shortcut
+            # operand then read 2-byte elements, the identity shortcut keeps the fp32 tensor
+            n1_in = F.cast(x32, BF16)
+        a1, raw = _norm_act(name + '.N1', n1_in, labels, kind(name + '.N1'), activation_fn,
                             upsample=(resample == 'up'), want_raw=not identity_shortcut, n_labels=n_labels)
 
     # ---- shortcut (reference order: the shortcut variables are created before Conv1's)

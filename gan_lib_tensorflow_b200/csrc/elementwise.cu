@@ -1284,24 +1284,77 @@ act_mean_hw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ do
 // mode 0: hinge D loss = mean(relu(1 - d[0:n_real])) + mean(relu(1 + d[n_real:n]))   (gan_cifar_resnet.py:376-378)
 // mode 1: G loss = -mean(d[0:n])                                                      (gan_cifar_resnet.py:492)
 // loss_out[0] (+)= scale * loss ; dlogits = scale * dloss/dd
+// mode = 2 * loss_type + side; side 0 = discriminator loss over d = [real | fake], side 1 = generator loss over the
+// fake logits; loss_type 0 HINGE, 1 WGAN / WGAN-GP, 2 LSGAN, 3 CGAN, 4 Modified_MiniMax, 5 MiniMax
+// (common/misc.py:310-394).  l = this element's contribution before the 1/count of its mean, g = dl/dv.
+__device__ __forceinline__ void gan_loss_elem(int type, int side, bool real, float v, float& l, float& g) {
+  const float sg = 1.f / (1.f + __expf(-v));                      // sigmoid(v)
+  if (side == 0) {
+    switch (type) {
+      case 0: { const float t = real ? 1.f - v : 1.f + v; l = t > 0.f ? t : 0.f; g = t > 0.f ? (real ? -1.f : 1.f) : 0.f; } break;
+      case 1: l = real ? -v : v; g = real ? -1.f : 1.f; break;
+      case 2: if (real) { l = 0.5f * (1.f - v) * (1.f - v); g = -(1.f - v); } else { l = 0.5f * v * v; g = v; } break;
+      case 3: {   // tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log1p(exp(-|x|))
+        const float sp = log1pf(__expf(-fabsf(v)));
+        if (real) { l = fmaxf(-v, 0.f) + sp; g = sg - 1.f; } else { l = fmaxf(v, 0.f) + sp; g = sg; }
+      } break;
+      default: if (real) { l = -__logf(sg); g = sg - 1.f; } else { l = -__logf(1.f - sg); g = sg; } break;
+    }
+  } else {
+    switch (type) {
+      case 0: case 1: l = -v; g = -1.f; break;
+      case 2: l = 0.5f * (1.f - v) * (1.f - v); g = -(1.f - v); break;
+      case 3: l = fmaxf(-v, 0.f) + log1pf(__expf(-fabsf(v))); g = sg - 1.f; break;
+      case 4: l = -__logf(sg); g = sg - 1.f; break;
+      default: l = __logf(1.f - sg); g = -sg; break;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gan_loss_kernel(const float* __restrict__ d, int n, int n_real, int mode, float scale, int accumulate,
                 float* __restrict__ loss_out, float* __restrict__ dlogits) {
   pdl_wait();
   __shared__ float sh[256];
   float acc = 0.f;
+  const int type = mode >> 1, side = mode & 1;
   const int n_fake = n - n_real;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = d[i];
+    const bool real = side == 0 && i < n_real;
     float l, g;
-    if (mode == 0) {
-      if (i < n_real) { const float t = 1.f - v; l = t > 0.f ? t / n_real : 0.f; g = t > 0.f ? -1.f / n_real : 0.f; }
-      else { const float t = 1.f + v; l = t > 0.f ? t / n_fake : 0.f; g = t > 0.f ? 1.f / n_fake : 0.f; }
-    } else {
-      l = -v / n; g = -1.f / n;
-    }
-    acc += l;
-    dlogits[i] = g * scale;
+    gan_loss_elem(type, side, real, d[i], l, g);
+    const float w = 1.f / (side == 1 ? n : (real ? n_real : n_fake));   // LSGAN's 1/2 is already in l
+    acc += l * w;
+    dlogits[i] = g * w * scale;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (accumulate ? loss_out[0] : 0.f) + scale * sh[0];
+}
+
+// tf.reduce_mean(tf.nn.sparse_softmax_cross_entropy_with_logits(logits, labels)) (ACGAN/train.py:110-121):
+// loss_out[0] (+)= scale * mean_i(logsumexp(z_i) - z_i[label_i]); dlogits = scale * (softmax(z_i) - onehot) / n.
+__global__ void __launch_bounds__(256)
+softmax_xent_kernel(const float* __restrict__ z, const int* __restrict__ labels, int n, int c, float scale,
+                    int accumulate, float* __restrict__ loss_out, float* __restrict__ dlogits) {
+  pdl_wait();
+  __shared__ float sh[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* row = z + static_cast<int64_t>(i) * c;
+    float m = row[0];
+    for (int j = 1; j < c; ++j) m = fmaxf(m, row[j]);
+    float se = 0.f;
+    for (int j = 0; j < c; ++j) se += expf(row[j] - m);
+    const float lse = m + logf(se);
+    const int lab = labels[i];
+    acc += (lse - row[lab]) / n;
+    for (int j = 0; j < c; ++j)
+      dlogits[static_cast<int64_t>(i) * c + j] = scale * (expf(row[j] - lse) - (j == lab ? 1.f : 0.f)) / n;
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -1823,10 +1876,19 @@ extern "C" int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, in
 extern "C" int ganb_gan_loss(const float* logits, int n, int n_real, int mode, float scale, int accumulate,
                              float* loss_out, float* dlogits, void* stream) {
   if (!logits || !loss_out || !dlogits) return fail(GANB_E_BADARG, "gan_loss: null buffer");
-  if (mode != 0 && mode != 1) return fail(GANB_E_UNSUPPORTED, "gan_loss: mode %d", mode);
-  if (mode == 0 && (n_real <= 0 || n_real >= n)) return fail(GANB_E_BADARG, "gan_loss: hinge needs 0 < n_real < n");
+  if (mode < 0 || mode > 11) return fail(GANB_E_UNSUPPORTED, "gan_loss: mode %d", mode);
+  if ((mode & 1) == 0 && (n_real <= 0 || n_real >= n)) return fail(GANB_E_BADARG, "gan_loss: the discriminator loss needs 0 < n_real < n");
   launch_k(gan_loss_kernel, 1, 256, 0, STREAM, logits, n, n_real, mode, scale, accumulate, loss_out, dlogits);
   GANB_CHECK_LAUNCH("gan_loss_kernel");
+  return 0;
+}
+
+extern "C" int ganb_softmax_xent(const float* logits, const int* labels, int n, int c, float scale, int accumulate,
+                                 float* loss_out, float* dlogits, void* stream) {
+  if (!logits || !labels || !loss_out || !dlogits) return fail(GANB_E_BADARG, "softmax_xent: null buffer");
+  if (n <= 0 || c <= 0) return fail(GANB_E_BADARG, "softmax_xent: empty input");
+  launch_k(softmax_xent_kernel, 1, 256, 0, STREAM, logits, labels, n, c, scale, accumulate, loss_out, dlogits);
+  GANB_CHECK_LAUNCH("softmax_xent_kernel");
   return 0;
 }
 

@@ -89,6 +89,39 @@ def add(a: Var, b: Var) -> Var:
     return out
 
 
+def concat_rows(a: Var, b: Var) -> Var:
+    """tf.concat([a, b], axis=0) of two fp32 logit vectors / matrices (real | fake halves of a loss)."""
+    assert a.data.dtype == F32 and b.data.dtype == F32 and a.shape[1:] == b.shape[1:]
+    na = a.shape[0]
+    data = torch.empty((na + b.shape[0],) + tuple(a.shape[1:]), dtype=F32, device=a.data.device)
+    data[:na].copy_(a.data)      # device-to-device memcpy (allocator / tensor plumbing, no arithmetic)
+    data[na:].copy_(b.data)
+    out = Var(data)
+    if _rg(a, b):
+        out.requires_grad = True
+
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            if a.requires_grad:
+                a.accum(g[:na].clone())
+            if b.requires_grad:
+                b.accum(g[na:].clone())
+        _tape().record(bwd)
+    return out
+
+
+def add_scalars(a: Var, b: Var) -> Var:
+    """Sum of two loss scalars (d_loss_gan + d_loss_acgan).  Loss Vars push their pre-computed dlogits when the tape
+    unwinds (gan_loss / softmax_xent), so the sum itself has nothing to propagate."""
+    data = K.cast(a.data, F32)
+    K.axpby(b.data, data, 1.0, 1.0)
+    out = Var(data)
+    out.requires_grad = _rg(a, b)
+    return out
+
+
 def lerp(a: Var, b: Var, alpha: float) -> Var:
     """(1 - alpha) * a + alpha * b in fp32: the fade-in of PGGAN (PGGAN/model_nvidia.py:118, :200)."""
     alpha = float(alpha)
@@ -680,10 +713,18 @@ def dropout(x: Var, keep_mask: torch.Tensor, keep_prob: float) -> Var:
     return out
 
 
-def gan_loss(logits: Var, mode: str, n_real: int = 0, scale: float = 1.0, loss_out: torch.Tensor | None = None):
-    """hinge_d: mean(relu(1-d_real)) + mean(relu(1+d_fake)) ; gen: -mean(d)  (gan_cifar_resnet.py:376-378, 492).
-    Returns the device scalar (accumulated into loss_out when given)."""
-    code = {"hinge_d": 0, "gen": 1}[mode]
+LOSS_TYPES = {"HINGE": 0, "WGAN": 1, "WGAN-GP": 1, "LSGAN": 2, "CGAN": 3, "Modified_MiniMax": 4, "MiniMax": 5}
+
+
+def gan_loss(logits: Var, mode: str, n_real: int = 0, scale: float = 1.0, loss_out: torch.Tensor | None = None,
+             loss_type: str = "HINGE"):
+    """mode 'hinge_d' / 'd': discriminator loss over logits = [disc_real (n_real) | disc_fake]; 'gen' / 'g': generator
+    loss over disc_fake -- lib.misc.get_loss (common/misc.py:310-394) for every loss_type it knows; the default is the
+    hinge pair of gan_cifar_resnet.py:376-378, 492.  Returns the device scalar (accumulated into loss_out when given)."""
+    if loss_type not in LOSS_TYPES:
+        raise ValueError(f"unknown loss_type {loss_type!r}")
+    side = {"hinge_d": 0, "d": 0, "gen": 1, "g": 1}[mode]
+    code = 2 * LOSS_TYPES[loss_type] + side
     accumulate = loss_out is not None
     if loss_out is None:
         loss_out = torch.zeros(1, dtype=F32, device=logits.data.device)
@@ -694,5 +735,22 @@ def gan_loss(logits: Var, mode: str, n_real: int = 0, scale: float = 1.0, loss_o
 
         def bwd():
             logits.accum(dlogits.reshape(logits.data.shape))
+        _tape().record(bwd)
+    return out
+
+
+def softmax_xent(logits: Var, labels: torch.Tensor, scale: float = 1.0, loss_out: torch.Tensor | None = None):
+    """scale * tf.reduce_mean(tf.nn.sparse_softmax_cross_entropy_with_logits(logits, labels)) (ACGAN/train.py:110-121)."""
+    assert logits.data.dtype == F32 and logits.data.dim() == 2
+    accumulate = loss_out is not None
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=F32, device=logits.data.device)
+    dlogits = K.softmax_xent(logits.data, labels, scale, loss_out, accumulate)
+    out = Var(loss_out)
+    if _rg(logits):
+        out.requires_grad = True
+
+        def bwd():
+            logits.accum(dlogits)
         _tape().record(bwd)
     return out

@@ -266,6 +266,14 @@ def gan_loss(logits, n_real, mode, scale, loss_out, accumulate):
     return dlogits
 
 
+def softmax_xent(logits, labels, scale, loss_out, accumulate):
+    n, c = logits.shape
+    dlogits = torch.empty_like(logits)
+    check(L().ganb_softmax_xent(ptr(logits), ptr(labels), n, c, c_float(scale), int(accumulate), ptr(loss_out),
+                                ptr(dlogits), _stream()), "ganb_softmax_xent")
+    return dlogits
+
+
 def adam(params, grads, m, v, lr_t, beta1, beta2, eps, grad_scale=1.0):
     check(L().ganb_adam(ptr(params), ptr(grads), ptr(m), ptr(v), c_int64(params.numel()), ptr(lr_t), c_float(beta1),
                         c_float(beta2), c_float(eps), c_float(grad_scale), _stream()), "ganb_adam")

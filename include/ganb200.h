@@ -230,9 +230,17 @@ int ganb_act_mean_hw_bwd(const float* x, const float* dout, int n, int hw, int c
                          void* stream);
 
 /* mode 0: hinge D loss mean(relu(1-d[:n_real])) + mean(relu(1+d[n_real:])) (gan_cifar_resnet.py:376-378)
- * mode 1: G loss -mean(d) (:492).  loss_out[0] (+)= scale*loss; dlogits = scale * dloss/dd. */
+ * mode 1: G loss -mean(d) (:492).  loss_out[0] (+)= scale*loss; dlogits = scale * dloss/dd.
+ * General form (lib.misc.get_loss, common/misc.py:310-394): mode = 2 * loss_type + side, side 0 = d_loss over
+ * logits = [disc_real (n_real) | disc_fake], side 1 = g_loss over disc_fake; loss_type 0 HINGE, 1 WGAN / WGAN-GP
+ * (without the penalty term), 2 LSGAN, 3 CGAN, 4 Modified_MiniMax, 5 MiniMax. */
 int ganb_gan_loss(const float* logits, int n, int n_real, int mode, float scale, int accumulate, float* loss_out,
                   float* dlogits, void* stream);
+
+/* tf.reduce_mean(tf.nn.sparse_softmax_cross_entropy_with_logits(logits [n, c], labels [n])) -- the auxiliary-classifier
+ * losses of ACGAN (ACGAN/train.py:110-121).  loss_out[0] (+)= scale*loss; dlogits [n, c] = scale * dloss/dlogits. */
+int ganb_softmax_xent(const float* logits, const int* labels, int n, int c, float scale, int accumulate,
+                      float* loss_out, float* dlogits, void* stream);
 
 /* tf.train.AdamOptimizer update (gan_cifar_resnet.py:521-526) over one flat parameter buffer:
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps); lr_t is a DEVICE scalar that

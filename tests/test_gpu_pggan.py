@@ -100,3 +100,128 @@ def test_pggan_discriminator(env, bc, trans):
     assert set(prod["params"]) == set(refs["fp32"]["params"])
     assert rel(prod["out"], refs["bf16"]["out"]) < 5e-3
     check_band(prod, refs, tag=f"pggan_d bc={bc}")
+
+
+# ------------------------------------------------------------------------------------------------ ACGAN (config 2)
+def test_acgan_generator(env):
+    """ACGAN/model.py:27-57: conditional-BN generator (library Normalize dispatch), batch 8."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.ACGAN import model as P
+    from oracle import acgan as OA
+
+    n = 8
+    rs = np.random.RandomState(81)
+    z = rs.standard_normal((n, 128)).astype("float32")
+    labels = rs.randint(0, 10, size=n).astype("int32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda zv: P.ACGAN().get_generator(zv, torch.from_numpy(labels).cuda()),
+        lambda g, zt: OA.ACGAN().get_generator(g, zt, torch.from_numpy(labels).long()), z)
+    assert prod["out"].shape == (n, 32, 32, 3)
+    assert set(prod["params"]) == set(refs["fp32"]["params"])
+    assert rel(prod["out"], refs["bf16"]["out"]) < 1e-2
+    check_band(prod, refs, tag="acgan_g")
+
+
+@pytest.mark.parametrize("loss_type", ["HINGE", "WGAN", "LSGAN", "CGAN", "Modified_MiniMax", "MiniMax"])
+def test_acgan_discriminator_step_losses(env, loss_type):
+    """ACGAN/model.py:59-90 + the critic / auxiliary-classifier losses of ACGAN/train.py:89-115 (without the gradient
+    penalty) for every loss_type of common/misc.py:310-394: D on 8 real + 8 fake images, gradient of
+    d_loss = d_loss_gan + d_loss_acgan; and the generator-side loss values on the same logits."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.ACGAN import model as P
+    from oracle import acgan as OA
+    from oracle import ops as O_ops
+
+    n = 8
+    rs = np.random.RandomState(82)
+    real = rs.uniform(-1, 1, size=(n, 32, 32, 3)).astype("float32")
+    fake = rs.uniform(-1, 1, size=(n, 32, 32, 3)).astype("float32")
+    rl = rs.randint(0, 10, size=n).astype("int32")
+    fl = rs.randint(0, 10, size=n).astype("int32")
+    # ---- product
+    np.random.seed(0)
+    pm = P.ACGAN()
+    rl_d, fl_d = torch.from_numpy(rl).cuda(), torch.from_numpy(fl).cuda()
+    with store.gradient_tape() as tape:
+        d_real, a_real = pm.get_discriminator(F.Var(torch.from_numpy(real).cuda()), rl_d, update_collection=None)
+        fv = F.Var(torch.from_numpy(fake).cuda(), requires_grad=True)
+        d_fake, a_fake = pm.get_discriminator(fv, fl_d, update_collection="NO_OPS", reuse=True)
+        d_loss, parts = P.discriminator_losses(d_real, a_real, rl_d, d_fake, loss_type=loss_type)
+        for v in store.vars.values():
+            if v.trainable and v.grad is None:
+                v.grad = torch.zeros_like(v.data)
+        tape.backward(d_loss)
+    g_loss, gparts = P.generator_losses(d_fake, a_fake, fl_d, loss_type=loss_type, acgan_scale_G=0.1)
+    torch.cuda.synchronize()
+    got = {k: v.grad.cpu().numpy() for k, v in store.vars.items() if v.trainable}
+    got_losses = [float(d_loss.data.item()), float(parts["d_loss_acgan"].item()), float(g_loss.data.item())]
+    with pytest.raises(NotImplementedError):
+        P.discriminator_losses(d_real, a_real, rl_d, d_fake, gradient_penalty=True)
+    # ---- oracles
+    res = {}
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        np.random.seed(0)
+        g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+        om = OA.ACGAN()
+        o_real, oa_real = om.get_discriminator(g, torch.from_numpy(real), torch.from_numpy(rl).long())
+        ft = torch.from_numpy(fake).clone().requires_grad_(True)
+        o_fake, oa_fake = om.get_discriminator(g, ft, torch.from_numpy(fl).long(), update_collection=O_ops.NO_OPS,
+                                               reuse=True)
+        dl_gan, gl_gan = OA.get_loss(o_real, o_fake, loss_type)
+        dl_ac = OA.sparse_softmax_xent_mean(oa_real, torch.from_numpy(rl))
+        gl = gl_gan + 0.1 * OA.sparse_softmax_xent_mean(oa_fake, torch.from_numpy(fl))
+        params = g.trainable_variables()
+        grads = torch.autograd.grad(dl_gan + dl_ac, [ft] + [p for _, p in params])
+        res[mode] = {"losses": [float(dl_gan + dl_ac), float(dl_ac), float(gl)], "dx": grads[0].numpy(),
+                     "params": {name: gr.numpy() for (name, _), gr in zip(params, grads[1:])}}
+    O_ops.BF16_OPERANDS = False
+    assert set(got) == set(res[False]["params"])
+    for mode in (True, False):
+        assert max(abs(a - b) / (abs(b) + 1e-3) for a, b in zip(got_losses, res[mode]["losses"])) < 1e-2
+    # four batch-normed blocks deep at batch 8: measured band (tests/test_gpu_wide.py::check_band) -- the product must
+    # be as close to the fp32 oracle as the bf16-operand oracle is, tensor by tensor
+    prod = {"out": np.asarray(got_losses), "dx": fv.grad.float().cpu().numpy(), "params": got}
+    refs = {k: {"out": np.asarray(res[m]["losses"]), "dx": res[m]["dx"], "params": res[m]["params"]}
+            for k, m in (("bf16", True), ("fp32", False))}
+    check_band(prod, refs, tag=f"acgan_d {loss_type}")
+    # the head layers sit behind the whole (compounding) forward pass but in front of no backward depth
+    for name in ("d_net/D.Output/W", "d_net/D.ACGANOutput/W", "d_net/D.NoneBlock.4.Conv2/Filters"):
+        assert rel(got[name], res[True]["params"][name]) < 5e-2, name
+
+
+@pytest.mark.parametrize("resample,cin,cout,h,act", [
+    ("down", 128, 128, 16, "lrelu"), (None, 128, 128, 8, "lrelu"), (None, 64, 128, 8, "lrelu"),
+    (None, 128, 128, 8, "relu"),
+])
+def test_batch_normed_discriminator_block(env, resample, cin, cout, h, act):
+    """ResidualBlock with spectral_normed=False under a 'D.' name: the library dispatch gives plain batch norm
+    (common/resnet_block.py:36-39) -- ACGAN's D blocks; fp32 residual stream in, leaky ReLU."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common import resnet_block as P
+    from oracle import resnet_block as ORB
+    from tests.test_gpu_ops import TOL_BLOCK_FP32, TOL_BLOCK_IMPL
+
+    x = np.random.RandomState(23).standard_normal((8, h, h, cin)).astype("float32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.ResidualBlock(xv, cin, cout, 3, "D.B", spectral_normed=False, resample=resample, activation_fn=act),
+        lambda g, xt: ORB.ResidualBlock(g, xt, cin, cout, 3, "D.B", spectral_normed=False, resample=resample,
+                                        activation_fn=act), x)
+    check(prod, refs, tol_impl=TOL_BLOCK_IMPL, tol_fp32=TOL_BLOCK_FP32, tag=f"bn block {resample} {act}")
+
+
+def test_first_block_lrelu_unnormalised(env):
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common import resnet_block as P
+    from oracle import resnet_block as ORB
+    from tests.test_gpu_ops import TOL_BLOCK_FP32, TOL_BLOCK_IMPL
+
+    x = np.random.RandomState(24).uniform(-1, 1, size=(6, 32, 32, 3)).astype("float32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.OptimizedResBlockDisc1(xv, 128, activation_fn="lrelu"),
+        lambda g, xt: ORB.OptimizedResBlockDisc1(g, xt, 128, activation_fn="lrelu"), x)
+    check(prod, refs, tol_impl=TOL_BLOCK_IMPL, tol_fp32=TOL_BLOCK_FP32, tag="first block lrelu")
