@@ -46,10 +46,16 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.ganb_last_error.restype = c_char_p
         _lib.ganb_conv2d_wgrad_workspace.restype = c_int64
+        _lib.ganb_upconv_wgrad_workspace.restype = c_int64
     return _lib
 
 
+_TRACE = os.environ.get("GANB_TRACE") == "1"   # debugging aid: print every C-ABI call as it returns
+
+
 def check(rc: int, what: str) -> None:
+    if _TRACE:
+        print(f"[ganb] {what} -> {rc}", flush=True)
     if rc != OK:
         msg = lib().ganb_last_error().decode(errors="replace")
         raise GanbError(f"{what} failed with status {rc}: {msg}")

@@ -131,6 +131,13 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
         lambda nm: _normalize_kind(nm, labels, spectral_normed))
     identity_shortcut = (output_dim == input_dim and resample is None)
 
+    # 'up' blocks: Conv1 = UpsampleConv runs in sub-pixel form (four 2x2 convolutions over the LOW-resolution
+    # activation, 4/9 of the MMA work, no upsampled operand) wherever the CTA-pair kernel tiles the shape
+    subpixel = False
+    if resample == 'up' and pre_activated is None and not spectral_normed and not inputs_norm:
+        n_, h_, w_, _c = F.as_var(inputs).shape
+        subpixel = F.upconv_eligible(n_, h_, w_, input_dim, output_dim, filter_size)
+
     # ---- N1 + nonlinearity (+ upsample), and the raw bf16 copy feeding the 1x1 shortcut
     if pre_activated is not None:
         raw, a1 = pre_activated
@@ -144,7 +151,8 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
             # operand then read 2-byte elements, the identity shortcut keeps the fp32 tensor
             n1_in = F.cast(x32, BF16)
         a1, raw = _norm_act(name + '.N1', n1_in, labels, kind(name + '.N1'), activation_fn,
-                            upsample=(resample == 'up'), want_raw=not identity_shortcut, n_labels=n_labels)
+                            upsample=(resample == 'up' and not subpixel), want_raw=not identity_shortcut,
+                            n_labels=n_labels)
 
     # ---- shortcut (reference order: the shortcut variables are created before Conv1's)
     if identity_shortcut:
@@ -161,7 +169,8 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # h1 is only consumed by N2 + nonlinearity, whose backward can emit the bf16 tensor-core operand directly
     # and which is stored in bf16: it is only read by that kernel (rounding commutes with relu / leaky relu, so
     # without a normalisation in between this is bit-identical to rounding after the activation)
-    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16, out_dtype=BF16)
+    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16, out_dtype=BF16,
+              subpixel_up2=subpixel)
 
     # ---- N2 + nonlinearity
     a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn, n_labels=n_labels)

@@ -841,6 +841,9 @@ struct WgradParams {
   int num_pb, splits, pb_per_split;
   int ci_tiles, co_tiles;
   float* partial;  // [splits][taps][Cin][Cout]
+  // sub-pixel UpsampleConv (ganb_upconv_wgrad): taps = 4 parities x (2 x 2); parity g = 2i + j reads the channel slice
+  // [g*Cout, (g+1)*Cout) of the quad-layout gradient [N, Ho, Wo, 4*Cout] and pads its 2x2 window by (1 - i, 1 - j)
+  int quad;
 };
 
 template <int BN, int STAGES>
@@ -891,10 +894,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int tci = u % p.ci_tiles; u /= p.ci_tiles;
   const int tap = u % p.taps;     u /= p.taps;
   const int split = u;
-  const int r = tap / p.kw, s = tap - r * p.kw;
+  const int ltap = p.quad ? (tap & 3) : tap;                 // tap inside its parity group
+  const int grp = p.quad ? (tap >> 2) : 0;
+  const int r = ltap / p.kw, s = ltap - r * p.kw;
+  const int pad_t = p.quad ? 1 - (grp >> 1) : p.pad_t, pad_l = p.quad ? 1 - (grp & 1) : p.pad_l;
   const int pb_begin = split * p.pb_per_split;
   const int pb_end = min(p.num_pb, pb_begin + p.pb_per_split);
   const int ci0 = tci * BM, co0 = tco * BN;
+  const int dy_c0 = grp * p.Cout + co0;                     // channel coordinate inside the dy tensor map
 
   if (warp == 0) {
     // TMA producer: warp-uniform loop, one elected lane issues.
@@ -910,11 +917,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint8_t* b = sB + stage * B_BYTES;
 #pragma unroll
         for (int j = 0; j < BM / 64; ++j)
-          tma_load_4d(a + j * BOX_BYTES, &tmX, &full[stage], ci0 + 64 * j, w0 * p.stride + s - p.pad_l,
-                      h0 * p.stride + r - p.pad_t, n0);
+          tma_load_4d(a + j * BOX_BYTES, &tmX, &full[stage], ci0 + 64 * j, w0 * p.stride + s - pad_l,
+                      h0 * p.stride + r - pad_t, n0);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(b + j * BOX_BYTES, &tmDY, &full[stage], co0 + 64 * j, w0, h0, n0);
+          tma_load_4d(b + j * BOX_BYTES, &tmDY, &full[stage], dy_c0 + 64 * j, w0, h0, n0);
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1109,7 +1116,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int pair_tiles = ((m_tiles + 1) / 2) * p.tiles_co;
+  const int pair_tiles = ((m_tiles + 1) / 2) * p.tiles_co * p.og;
   p.num_tiles = pair_tiles;
   int clusters = sm_count() / 2;
   if (clusters > pair_tiles) clusters = pair_tiles;
@@ -1306,7 +1313,7 @@ extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void*
   plan_wgrad(n, ho, wo, cin, cout, kh, kw, &plan);
   if (stride < 1 || stride > 4) return fail(GANB_E_UNSUPPORTED, "conv2d_wgrad: stride=%d (1..4 supported)", stride);
   WgradParams& p = plan.p;
-  p.pad_t = pad_t; p.pad_l = pad_l; p.stride = stride;
+  p.pad_t = pad_t; p.pad_l = pad_l; p.stride = stride; p.quad = 0;
   p.partial = static_cast<float*>(workspace);
 
   CUtensorMap tmX, tmDY;
@@ -1338,5 +1345,214 @@ extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void*
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   launch_k(splitk_reduce_kernel, blocks, 256, 0, stream, p.partial, dw, n4, p.splits, scale, beta);
   GANB_CHECK_LAUNCH("splitk_reduce_kernel");
+  return 0;
+}
+
+
+// ================================================================================================
+// Sub-pixel form of UpsampleConv (common/resnet_block.py:83-97: nearest-2x upsample, then a 3x3 SAME convolution).
+// Output pixel (2a+i, 2b+j) only sees the 2x2 low-resolution neighbourhood rows {a+i-1, a+i}, columns {b+j-1, b+j}:
+//     y[2a+i, 2b+j] = sum_{p,q in {0,1}} E_ij[p][q] . x[a+i-1+p, b+j-1+q],   E_ij[p][q] = sum_{r in R_i[p], s in R_j[q]} W[r][s]
+// with R_0 = ({0}, {1,2}), R_1 = ({0,1}, {2}).  Four 2x2 convolutions over the LOW-resolution tensor replace one 3x3
+// convolution over the 4x larger one: 16/36 = 4/9 of the MMA work, and the upsampled operand is never written.
+// The result is kept in "quad layout" [N, h, w, 4 = 2i+j, C]: a pixel permutation of NHWC [N, 2h, 2w, C] that the
+// batch-statistics normalisation behind it (the only consumer) reads directly (ganb_norm_act_* x_quad = 1).
+// ================================================================================================
+namespace ganb {
+
+// E (bf16) in both GEMM layouts: we_t [16 = 4*(2i+j) + 2p+q][co][ci] (fprop), we_n [16][ci][co] (dgrad)
+__global__ void __launch_bounds__(256) upconv_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ we_t,
+                                                          __nv_bfloat16* __restrict__ we_n, int ci_n, int co_n) {
+  pdl_wait();
+  __shared__ float tile[32][33];
+  const int tiles_co = (co_n + 31) / 32;
+  const int tco = blockIdx.x % tiles_co, tci = blockIdx.x / tiles_co;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int64_t plane = static_cast<int64_t>(ci_n) * co_n;
+  for (int t16 = 0; t16 < 16; ++t16) {
+    const int i = t16 >> 3, j = (t16 >> 2) & 1, pp = (t16 >> 1) & 1, qq = t16 & 1;
+    // rows r with (r + 1 - i) >> 1 == pp, columns s with (s + 1 - j) >> 1 == qq
+    for (int jj = ty; jj < 32; jj += 8) {
+      const int ci = tci * 32 + jj, co = tco * 32 + tx;
+      float v = 0.f;
+      if (ci < ci_n && co < co_n) {
+        for (int r = 0; r < 3; ++r) {
+          if (((r + 1 - i) >> 1) != pp) continue;
+          for (int s2 = 0; s2 < 3; ++s2) {
+            if (((s2 + 1 - j) >> 1) != qq) continue;
+            v += w[(r * 3 + s2) * plane + static_cast<int64_t>(ci) * co_n + co];
+          }
+        }
+        we_n[t16 * plane + static_cast<int64_t>(ci) * co_n + co] = __float2bfloat16_rn(v);
+      }
+      tile[jj][tx] = v;
+    }
+    __syncthreads();
+    for (int jj = ty; jj < 32; jj += 8) {
+      const int co = tco * 32 + jj, ci = tci * 32 + tx;
+      if (ci < ci_n && co < co_n) we_t[t16 * plane + static_cast<int64_t>(co) * ci_n + ci] = __float2bfloat16_rn(tile[tx][jj]);
+    }
+    __syncthreads();
+  }
+}
+
+// dW[r][s] = beta*dW[r][s] + scale * sum_splits sum_{i,j} dE_ij[p(i,r)][q(j,s)]   (transpose of the map W -> E)
+__global__ void upconv_fold_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int64_t plane4,
+                                          int splits, const float* __restrict__ scale, float beta) {
+  pdl_wait();
+  const float sc = scale ? __ldg(scale) : 1.0f;
+  const int64_t total = 9 * plane4;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int rs = static_cast<int>(idx / plane4);
+    const int64_t e = idx - rs * plane4;
+    const int r = rs / 3, s2 = rs - 3 * r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int i = g >> 1, j = g & 1;
+        const int t16 = g * 4 + ((r + 1 - i) >> 1) * 2 + ((s2 + 1 - j) >> 1);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + (static_cast<int64_t>(sp) * 16 + t16) * plane4 + e);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    float4 o = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+    if (beta != 0.f) {
+      const float4 d = reinterpret_cast<const float4*>(dw)[idx];
+      o.x += beta * d.x; o.y += beta * d.y; o.z += beta * d.z; o.w += beta * d.w;
+    }
+    reinterpret_cast<float4*>(dw)[idx] = o;
+  }
+}
+
+// shapes the CTA-pair kernel covers with 16 x 8 pixel tiles and whole 64-channel chunks on both sides
+static bool upconv_shape_ok(int n, int h, int w, int cin, int cout) {
+  return n > 0 && h >= HALO_BH && w >= HALO_BW && h % HALO_BH == 0 && w % HALO_BW == 0 && cin % 64 == 0 &&
+         cout % 64 == 0 && cin >= 128 && cout >= 128;
+}
+
+// One launch of the pair kernel over the low-resolution tile grid.  fprop: og = 4 output groups; dgrad: rg = 4
+// reduction groups over the channel slices of the quad-layout gradient.
+static int launch_upconv(bool dgrad, const void* a, const void* wp, void* out, int n, int h, int w, int ca, int cn,
+                         const float* alpha, const float* bias, int act, int out_dtype, cudaStream_t stream) {
+  IgemmParams p;
+  p.N = n; p.Ho = h; p.Wo = w; p.Cout = cn;
+  p.taps = 4; p.kw = 2; p.stride = 1; p.pad_t = 0; p.pad_l = 0;
+  p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1;
+  p.tiles_w = w / HALO_BW; p.tiles_h = h / HALO_BH; p.tiles_n = n;
+  p.kchunks = ca / BK;
+  p.flip = dgrad ? 1 : 0;
+  p.alpha = alpha; p.bias = bias; p.residual = nullptr; p.res_up2 = 0;
+  p.out = out; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
+  p.og = dgrad ? 1 : 4; p.rg = dgrad ? 4 : 1;
+  p.out_cstride = dgrad ? cn : 4 * cn;
+  for (int g = 0; g < 4; ++g) {
+    const int i = g >> 1, j = g & 1;
+    p.gpad_t[g] = static_cast<signed char>(dgrad ? i : 1 - i);
+    p.gpad_l[g] = static_cast<signed char>(dgrad ? j : 1 - j);
+  }
+  const int pair_bn = cn > 128 ? 256 : 128;
+  const int a_channels = dgrad ? 4 * ca : ca;      // the gradient tensor holds the four parity slices side by side
+  CUtensorMap tmA, tmB;
+  const int halo_w = HALO_BW + 1, halo_h = HALO_BH + 1;
+  {
+    const uint64_t dims[4] = {(uint64_t)a_channels, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)a_channels * 2, (uint64_t)w * a_channels * 2, (uint64_t)h * w * a_channels * 2};
+    const uint32_t box[4] = {BK, (uint32_t)halo_w, (uint32_t)halo_h, 1};
+    int rc = encode_tmap_bf16(&tmA, a, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)ca, (uint64_t)cn, 16};
+    const uint64_t strides[2] = {(uint64_t)ca * 2, (uint64_t)ca * cn * 2};
+    const uint32_t box[3] = {BK, (uint32_t)(pair_bn / 2), 1};
+    int rc = encode_tmap_bf16(&tmB, wp, 3, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  const int halo_bytes = halo_w * halo_h * 128;
+  const int a_stage = (halo_bytes + 1023) / 1024 * 1024;
+  if (pair_bn == 256) return launch_pair<256, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+  return launch_pair<128, 4, 12>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+}
+
+}  // namespace ganb
+
+extern "C" int ganb_upconv_supported(int n, int h, int w, int cin, int cout) {
+  return upconv_shape_ok(n, h, w, cin, cout) ? 1 : 0;
+}
+
+extern "C" int ganb_upconv_pack(const float* w_hwio, void* we_t_bf16, void* we_n_bf16, int cin, int cout, void* stream) {
+  if (!w_hwio || !we_t_bf16 || !we_n_bf16) return fail(GANB_E_BADARG, "upconv_pack: null buffer");
+  const int blocks = ceil_div(cin, 32) * ceil_div(cout, 32);
+  launch_k(upconv_pack_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), w_hwio,
+           static_cast<__nv_bfloat16*>(we_t_bf16), static_cast<__nv_bfloat16*>(we_n_bf16), cin, cout);
+  GANB_CHECK_LAUNCH("upconv_pack_kernel");
+  return 0;
+}
+
+extern "C" int ganb_upconv_fprop(const void* x_bf16, const void* we_t_bf16, void* y_quad, int n, int h, int w, int cin,
+                                 int cout, const float* alpha, const float* bias, int act, int out_dtype, void* stream) {
+  if (!x_bf16 || !we_t_bf16 || !y_quad) return fail(GANB_E_BADARG, "upconv_fprop: null buffer");
+  if (!upconv_shape_ok(n, h, w, cin, cout))
+    return fail(GANB_E_UNSUPPORTED, "upconv_fprop: n=%d h=%d w=%d cin=%d cout=%d (see ganb_upconv_supported)", n, h, w, cin, cout);
+  return launch_upconv(false, x_bf16, we_t_bf16, y_quad, n, h, w, cin, cout, alpha, bias, act, out_dtype,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ganb_upconv_dgrad(const void* dy_quad_bf16, const void* we_n_bf16, void* dx, int n, int h, int w, int cin,
+                                 int cout, const float* alpha, int out_dtype, void* stream) {
+  if (!dy_quad_bf16 || !we_n_bf16 || !dx) return fail(GANB_E_BADARG, "upconv_dgrad: null buffer");
+  if (!upconv_shape_ok(n, h, w, cin, cout))
+    return fail(GANB_E_UNSUPPORTED, "upconv_dgrad: n=%d h=%d w=%d cin=%d cout=%d (see ganb_upconv_supported)", n, h, w, cin, cout);
+  return launch_upconv(true, dy_quad_bf16, we_n_bf16, dx, n, h, w, cout, cin, alpha, nullptr, 0, out_dtype,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int64_t ganb_upconv_wgrad_workspace(int n, int h, int w, int cin, int cout) {
+  WgradPlan plan;
+  plan_wgrad(n, h, w, cin, cout, 4, 4, &plan);     // 16 (parity, tap) units
+  return static_cast<int64_t>(plan.p.splits) * 16 * cin * cout * 4;
+}
+
+extern "C" int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, float* dw_hwio, void* workspace, int n,
+                                 int h, int w, int cin, int cout, const float* scale, float beta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x_bf16 || !dy_quad_bf16 || !dw_hwio || !workspace) return fail(GANB_E_BADARG, "upconv_wgrad: null buffer");
+  if (!upconv_shape_ok(n, h, w, cin, cout))
+    return fail(GANB_E_UNSUPPORTED, "upconv_wgrad: n=%d h=%d w=%d cin=%d cout=%d (see ganb_upconv_supported)", n, h, w, cin, cout);
+  WgradPlan plan;
+  plan_wgrad(n, h, w, cin, cout, 4, 4, &plan);
+  WgradParams& p = plan.p;
+  p.kw = 2; p.pad_t = 0; p.pad_l = 0; p.stride = 1; p.quad = 1;
+  p.partial = static_cast<float*>(workspace);
+  CUtensorMap tmX, tmDY;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = encode_tmap_bf16(&tmX, x_bf16, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t c4 = 4ull * cout;
+    const uint64_t dims[4] = {c4, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {c4 * 2, (uint64_t)w * c4 * 2, (uint64_t)h * w * c4 * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = encode_tmap_bf16(&tmDY, dy_quad_bf16, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  int rc;
+  switch (plan.bn_tile) {
+    case 64: rc = launch_wgrad<64, 6>(tmX, tmDY, p, plan.grid, stream); break;
+    case 128: rc = launch_wgrad<128, 6>(tmX, tmDY, p, plan.grid, stream); break;
+    default: rc = launch_wgrad<256, 4>(tmX, tmDY, p, plan.grid, stream); break;
+  }
+  if (rc) return rc;
+  const int64_t plane4 = static_cast<int64_t>(cin) * cout / 4;
+  int blocks = static_cast<int>(ceil_div64(9 * plane4, 256));
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  launch_k(upconv_fold_reduce_kernel, blocks, 256, 0, stream, p.partial, dw_hwio, plane4, p.splits, scale, beta);
+  GANB_CHECK_LAUNCH("upconv_fold_reduce_kernel");
   return 0;
 }

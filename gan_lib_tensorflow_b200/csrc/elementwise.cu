@@ -149,6 +149,7 @@ struct NormActFwd {
   const float* mean; const float* rstd; int groups;       // mean == nullptr: no normalisation
   const float* gamma; const float* beta; const int* labels;  // tables [n_labels, c]; labels == nullptr: row 0
   int act, upsample;
+  int quad;   // x is stored in quad layout [n, h/2, w/2, 4 = 2i+j, c] (ganb_upconv_fprop); out is plain NHWC [n,h,w,c]
   void* out; int out_bf16; int out_cstride;               // channel stride of the output pixel (>= c)
   __nv_bfloat16* out_raw; int raw_cstride;                 // optional bf16 copy of x at input resolution
 };
@@ -231,6 +232,7 @@ struct NormActBwd {
   const float* mean; const float* rstd; int groups;
   const float* gamma; const float* beta; const int* labels;
   int act, upsample;
+  int quad;   // x and dx are stored in quad layout [n, h/2, w/2, 4, c]; dz is plain NHWC [n,h,w,c]
   // reduce outputs: per-sample sums
   float* part;    // [n][chunks][2][c]
   int chunks, pix_per_chunk;
@@ -564,6 +566,14 @@ bn_stats_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int rows_per_gro
   }
 }
 
+// pixel index inside one sample: quad layout [h/2][w/2][2i+j] -> NHWC row-major [h][w]
+__device__ __forceinline__ int quad_to_nhwc(int q, int w) {
+  const int g = q & 3, cell = q >> 2;
+  const int w2 = w >> 1;
+  const int a = cell / w2, b = cell - a * w2;
+  return (2 * a + (g >> 1)) * w + 2 * b + (g & 1);
+}
+
 template <bool UPS>
 __global__ void __launch_bounds__(256) norm_act_fwd_v8_kernel(const NormActFwd p, int pix_per_chunk) {
   pdl_wait();
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_v8_kernel(const NormActFwd p
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = act_f(a[j] * sc[j] + sf[j], p.act);
         const uint4 y = pack8(a);
-        const int64_t pix = static_cast<int64_t>(ni) * hw + q;
+        const int64_t pix = static_cast<int64_t>(ni) * hw + (p.quad ? quad_to_nhwc(q, p.w) : q);
         if (!UPS) {
           stg16(op + pix * p.out_cstride + c8, y);
         } else {
@@ -661,7 +671,8 @@ template <bool UPS>
 __device__ __forceinline__ void bwd_load_dz8(const NormActBwd& p, int ni, int px, int c8, uint4 (&raw)[UPS ? 4 : 1]) {
   const __nv_bfloat16* dz = static_cast<const __nv_bfloat16*>(p.dz);
   if (!UPS) {
-    raw[0] = ldg16(dz + (static_cast<int64_t>(ni) * p.h * p.w + px) * p.dz_cstride + c8);
+    const int qz = p.quad ? quad_to_nhwc(px, p.w) : px;
+    raw[0] = ldg16(dz + (static_cast<int64_t>(ni) * p.h * p.w + qz) * p.dz_cstride + c8);
   } else {
     const int hi = px / p.w, wi = px - hi * p.w;
     const int ow = 2 * p.w;
@@ -1519,10 +1530,13 @@ extern "C" int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w
   p.x = x; p.x_bf16 = (x_dtype == GANB_BF16); p.n = n; p.h = h; p.w = w; p.c = c;
   p.mean = mean; p.rstd = rstd; p.groups = groups;
   p.gamma = gamma; p.beta = beta; p.labels = labels;
-  p.act = act; p.upsample = upsample;
+  p.act = act; p.quad = (upsample == 2); p.upsample = p.quad ? 0 : upsample;
+  upsample = p.upsample;
   p.out = out; p.out_bf16 = (out_dtype == GANB_BF16); p.out_cstride = out_cstride > 0 ? out_cstride : c;
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
   const bool v8 = p.x_bf16 && p.out_bf16 && !p.out_raw && c % 8 == 0 && p.out_cstride % 8 == 0;
+  if (p.quad && (!v8 || (h & 1) || (w & 1)))
+    return fail(GANB_E_UNSUPPORTED, "norm_act_fwd: quad-layout input needs bf16 in/out, c %% 8 == 0, even h, w and no raw copy");
   const int chunks = v8 ? v8_chunks(n, h * w, 3) : bwd_chunks(n, h * w);
   const int ppc = ceil_div(h * w, chunks);
   if (v8 && upsample) launch_k(norm_act_fwd_v8_kernel<true>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
@@ -1576,11 +1590,14 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
   p.n = n; p.h = h; p.w = w; p.c = c;
   p.mean = mean; p.rstd = rstd; p.groups = groups;
   p.gamma = gamma; p.beta = beta; p.labels = labels;
-  p.act = act; p.upsample = upsample;
+  p.act = act; p.quad = (upsample == 2); p.upsample = p.quad ? 0 : upsample;
+  upsample = p.upsample;
   p.add = add; p.add_bf16 = (add_dtype == GANB_BF16); p.dx = dx; p.dx_bf16 = (dx_dtype == GANB_BF16);
   p.part = nullptr; p.s1 = nullptr; p.s2 = nullptr; p.chunks = 0; p.pix_per_chunk = 0; p.inv_count = 0.f;
   // all-bf16 fast path: 8 channels per thread
   const bool v8 = p.x_bf16 && p.dz_bf16 && p.dx_bf16 && (!add || p.add_bf16) && c % 8 == 0 && p.dz_cstride % 8 == 0;
+  if (p.quad && (!v8 || add || (h & 1) || (w & 1)))
+    return fail(GANB_E_UNSUPPORTED, "norm_act_bwd: quad-layout input needs the all-bf16 path, even h, w and no added gradient");
   if (mean) {
     if (!workspace) return fail(GANB_E_BADARG, "norm_act_bwd: workspace required with normalisation");
     const int hw = h * w;

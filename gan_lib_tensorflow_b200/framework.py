@@ -38,10 +38,11 @@ _ALIGN = 64  # floats: every variable starts on a 256-byte boundary inside the f
 class Var:
     """A value on the tape: `data` is a device tensor, `grad` is filled by Tape.backward()."""
 
-    __slots__ = ("data", "grad", "requires_grad", "grad_dtype")
+    __slots__ = ("data", "grad", "requires_grad", "grad_dtype", "quad")
 
     def __init__(self, data: torch.Tensor, requires_grad: bool = False, grad_dtype=None):
         self.data = data
+        self.quad = False   # storage is the quad layout of functional.upconv2d (value AND gradient)
         self.grad = None
         self.requires_grad = requires_grad
         self.grad_dtype = grad_dtype  # dtype producers should use for this value's gradient (None: fp32)
@@ -328,6 +329,18 @@ class PackEntry:
             self.small = "co"
             self.kpad = small_k(self.taps, self.co)
             self.ws = torch.empty(self.ci, self.kpad, dtype=torch.bfloat16, device=dev)
+        # effective 2x2 filters of the sub-pixel UpsampleConv (functional.upconv2d), allocated on first use
+        self.we_t = None   # [16][co][ci]
+        self.we_n = None   # [16][ci][co]
+
+    def enable_upconv(self) -> bool:
+        """Allocates the sub-pixel operand copies; returns True when they were just created (the group must re-pack)."""
+        if self.we_t is not None:
+            return False
+        dev = self.w.data.device
+        self.we_t = torch.empty(16, self.co, self.ci, dtype=torch.bfloat16, device=dev)
+        self.we_n = torch.empty(16, self.ci, self.co, dtype=torch.bfloat16, device=dev)
+        return True
 
 
 class PackGroup:
@@ -370,6 +383,8 @@ class PackGroup:
         for e in entries:
             if e.small is not None:
                 K.pack_small(e.w.data, e.ws, e.taps, e.ci, e.co, e.small == "ci", e.kpad)
+            if e.we_t is not None:
+                K.upconv_pack(e.w.data, e.we_t, e.we_n, e.ci, e.co)
         self.valid_for = ver
 
 

@@ -308,6 +308,57 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     return out
 
 
+SUBPIXEL_UPCONV = True   # sub-pixel form of UpsampleConv where ganb_upconv_supported() and the layer is large enough
+
+
+def upconv_eligible(n: int, h: int, w: int, cin: int, cout: int, k: int = 3) -> bool:
+    """True when UpsampleConv(k x k) over a [n, h, w, cin] input runs in its sub-pixel form: the shapes the CTA-pair
+    kernel tiles (ganb_upconv_supported) and enough pixel tiles to fill the machine in the data-gradient pass."""
+    return (SUBPIXEL_UPCONV and k == 3 and n * h * w >= 16384 and K.upconv_supported(n, h, w, cin, cout))
+
+
+def upconv2d(x: Var, W: Variable, b: Variable | None, out_grad_dtype=None, out_dtype=BF16) -> Var:
+    """UpsampleConv (common/resnet_block.py:83-97) = nearest 2x + 3x3 SAME Conv2D + bias, computed as four 2x2
+    convolutions over the LOW-resolution x (4/9 of the MMA work, the upsampled tensor is never written).
+
+    Returns a Var of logical shape [n, 2h, 2w, cout] whose storage is in QUAD LAYOUT (`quad = True`): only batch
+    statistics / norm_act (which translate the pixel order) and column sums may consume it."""
+    store = get_store()
+    n, h, w, cin = x.shape
+    cout = W.data.shape[-1]
+    group = store.pack_group(W.root)
+    pack = group.entry(W)
+    if pack.enable_upconv():
+        group.valid_for = None
+    group.refresh()
+    xin = x if x.data.dtype == BF16 else cast(x, BF16)
+    y = K.upconv_fprop(xin.data, pack.we_t, n, h, w, cin, cout, None, b.data if b is not None else None, None, out_dtype)
+    out = Var(y, grad_dtype=out_grad_dtype)
+    out.quad = True
+    need_w = W.needs_grad and _tape() is not None
+    need_b = b is not None and b.needs_grad and _tape() is not None
+    if _rg(xin) or need_w or need_b:
+        out.requires_grad = True
+        tape = _tape()
+
+        def bwd():
+            gy = out.grad          # quad layout, like the forward value
+            if gy is None:
+                return
+            gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
+            if need_b or need_w:
+                tape.keep.extend((gy, gy16))
+                with tape.offchain():
+                    if need_b:
+                        K.colsum(gy, n * 4 * h * w, cout, b.grad, 1.0)
+                    if need_w:
+                        K.upconv_wgrad(xin.data, gy16, W.grad, n, h, w, cin, cout, None, 1.0)
+            if xin.requires_grad:
+                xin.accum(K.upconv_dgrad(gy16, pack.we_n, n, h, w, cin, cout, None, xin.gdtype))
+        tape.record(bwd)
+    return out
+
+
 def _conv2d_ragged_cin(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale, residual_up2,
                        out_dtype):
     """Convolution whose input-channel count is above 8 and not a multiple of 8 (the 513 channels behind
@@ -501,7 +552,11 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
     # the raw bf16 copy (1x1-shortcut operand) is x itself when x is already stored in bf16
     share_raw = want_raw and x.data.dtype == BF16
     raw = torch.empty((n, h, w, c), dtype=BF16, device=x.data.device) if (want_raw and not share_raw) else None
-    y = K.norm_act_fwd(x.data, n, h, w, c, mean, rstd, g, gam, bet, labels, act, upsample, out_dtype, out_raw=raw)
+    quad = bool(getattr(x, "quad", False))   # x is the quad-layout output of upconv2d; the result is plain NHWC
+    if quad and (upsample or want_raw):
+        raise NotImplementedError("a quad-layout tensor can only be normalised in place (no upsample / raw copy)")
+    ups = 2 if quad else upsample
+    y = K.norm_act_fwd(x.data, n, h, w, c, mean, rstd, g, gam, bet, labels, act, ups, out_dtype, out_raw=raw)
     out = Var(y, grad_dtype=out_grad_dtype)
     raw_var = x if share_raw else (Var(raw) if want_raw else None)  # bf16 value, bf16 gradient
     need_p = gamma is not None and gamma.needs_grad and _tape() is not None
@@ -523,9 +578,10 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
                 return
             # a second gradient path into x (shortcut operand, or an identity-shortcut residual already accumulated
             # in x.grad) is added inside the same kernel instead of a separate read-modify-write pass
-            if extra is None and x.grad is not None and x.requires_grad and x.grad.shape == x.data.shape:
+            if (extra is None and x.grad is not None and x.requires_grad and x.grad.shape == x.data.shape
+                    and not quad):
                 extra, x.grad = x.grad, None
-            dx = K.norm_act_bwd(x.data, gz, 0, n, h, w, c, mean, rstd, g, gam, bet, labels, act, upsample, dgam, dbet,
+            dx = K.norm_act_bwd(x.data, gz, 0, n, h, w, c, mean, rstd, g, gam, bet, labels, act, ups, dgam, dbet,
                                 extra, x.gdtype)
             if x.requires_grad:
                 x.accum(dx)

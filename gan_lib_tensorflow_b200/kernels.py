@@ -39,7 +39,7 @@ def L():
             _L = _NullLib()
             return _L
         _L = cabi.lib()
-        for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
+        for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
                      "ganb_minibatch_std_workspace",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
@@ -110,6 +110,36 @@ def conv_wgrad(x, dy, dw, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, scal
                                 ptr(scale), c_float(beta), _stream()), "ganb_conv2d_wgrad")
 
 
+# ------------------------------------------------------------------------------------------------ sub-pixel UpsampleConv
+def upconv_supported(n, h, w, cin, cout) -> bool:
+    return bool(L().ganb_upconv_supported(n, h, w, cin, cout))
+
+
+def upconv_pack(w, we_t, we_n, cin, cout):
+    check(L().ganb_upconv_pack(ptr(w), ptr(we_t), ptr(we_n), cin, cout, _stream()), "ganb_upconv_pack")
+
+
+def upconv_fprop(x, we_t, n, h, w, cin, cout, alpha, bias, act, out_dtype):
+    """-> quad-layout tensor, allocated with the logical NHWC shape [n, 2h, 2w, cout]."""
+    y = torch.empty((n, 2 * h, 2 * w, cout), dtype=out_dtype, device=x.device)
+    check(L().ganb_upconv_fprop(ptr(x), ptr(we_t), ptr(y), n, h, w, cin, cout, ptr(alpha), ptr(bias), act_code(act),
+                                BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_upconv_fprop")
+    return y
+
+
+def upconv_dgrad(dy_quad, we_n, n, h, w, cin, cout, alpha, out_dtype):
+    dx = torch.empty((n, h, w, cin), dtype=out_dtype, device=dy_quad.device)
+    check(L().ganb_upconv_dgrad(ptr(dy_quad), ptr(we_n), ptr(dx), n, h, w, cin, cout, ptr(alpha),
+                                BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_upconv_dgrad")
+    return dx
+
+
+def upconv_wgrad(x, dy_quad, dw, n, h, w, cin, cout, scale, beta):
+    ws = _ws(L().ganb_upconv_wgrad_workspace(n, h, w, cin, cout), x.device)
+    check(L().ganb_upconv_wgrad(ptr(x), ptr(dy_quad), ptr(dw), ptr(ws), n, h, w, cin, cout, ptr(scale), c_float(beta),
+                                _stream()), "ganb_upconv_wgrad")
+
+
 # ------------------------------------------------------------------------------------------------ conv (small)
 def conv_smallcin(x, w, n, h, w_in, cs, ho, wo, cl, kh, kw, pad_t, pad_l, flip, w_clcs, alpha, bias, act, out_dtype):
     y = torch.empty((n, ho, wo, cl), dtype=out_dtype, device=x.device)
@@ -163,10 +193,10 @@ def bn_stats(x, n, hw, c, groups, eps):
 def norm_act_fwd(x, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, upsample, out_dtype, out=None,
                  out_cstride=0, out_raw=None, raw_cstride=0):
     if out is None:
-        s = 2 if upsample else 1
+        s = 2 if int(upsample) == 1 else 1     # upsample == 2: quad-layout INPUT, same resolution
         out = torch.empty((n, s * h, s * w, c), dtype=out_dtype, device=x.device)
     check(L().ganb_norm_act_fwd(ptr(x), dt(x), n, h, w, c, ptr(mean), ptr(rstd), groups, ptr(gamma), ptr(beta), ptr(labels),
-                                act_code(act), int(bool(upsample)), ptr(out), dt(out), out_cstride, ptr(out_raw),
+                                act_code(act), int(upsample), ptr(out), dt(out), out_cstride, ptr(out_raw),
                                 raw_cstride, _stream()), "ganb_norm_act_fwd")
     return out
 
@@ -179,7 +209,7 @@ def norm_act_bwd(x, dz, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta,
         ws = _ws(L().ganb_norm_act_bwd_workspace(n, h * w, c, groups), x.device)
     n_rows = int(gamma.shape[0]) if (gamma is not None and gamma.dim() == 2) else 1
     check(L().ganb_norm_act_bwd(ptr(x), dt(x), ptr(dz), dt(dz), dz_cstride, n, h, w, c, ptr(mean), ptr(rstd), groups,
-                                ptr(gamma), ptr(beta), ptr(labels), n_rows, act_code(act), int(bool(upsample)), ptr(dgamma),
+                                ptr(gamma), ptr(beta), ptr(labels), n_rows, act_code(act), int(upsample), ptr(dgamma),
                                 ptr(dbeta), ptr(add), dt(add) if add is not None else F32, ptr(dx), dt(dx), ptr(ws),
                                 _stream()), "ganb_norm_act_bwd")
     return dx

@@ -148,6 +148,31 @@ int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, int total_blo
                        void* stream);
 int ganb_sn_bwd(const ganb_sn_layer* layers_dev, int count, int total_blocks, int max_c, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Sub-pixel form of UpsampleConv (common/resnet_block.py:83-97: tf.depth_to_space(concat x4) = nearest 2x, then
+ * lib.ops.conv2d.Conv2D 3x3 SAME): replaces tf.concat + tf.depth_to_space + tf.nn.conv2d and their gradients.
+ * Output pixel (2a+i, 2b+j) only sees x[a+i-1 .. a+i, b+j-1 .. b+j], so the layer is four 2x2 convolutions over the
+ * LOW-resolution tensor with effective filters E_ij[p][q] = sum_{r in R_i[p], s in R_j[q]} W[r][s],
+ * R_0 = ({0}, {1,2}), R_1 = ({0,1}, {2}): 4/9 of the MMA work, no upsampled operand in HBM.
+ *   ganb_upconv_pack  : W fp32 [3][3][cin][cout] -> E bf16 as we_t [16 = 4*(2i+j) + 2p+q][cout][cin] (fprop operand)
+ *                       and we_n [16][cin][cout] (dgrad operand).
+ *   ganb_upconv_fprop : x bf16 [n,h,w,cin] -> y in QUAD LAYOUT [n, h, w, 4 = 2i+j, cout] (= NHWC [n,2h,2w,cout] with
+ *                       the pixels of each 2x2 cell stored together), y = act(alpha * conv + bias), f32 or bf16.
+ *   ganb_upconv_dgrad : dy quad bf16 -> dx [n,h,w,cin] = alpha * sum over the four parities (one launch).
+ *   ganb_upconv_wgrad : dW[3][3][cin][cout] = beta*dW + scale * fold(dE), dE_ij[p][q] = x (shifted)^T dy_ij.
+ * Supported shapes (ganb_upconv_supported): h % 16 == 0, w % 8 == 0, cin, cout multiples of 64 and >= 128.
+ * Quad-layout tensors are consumed by ganb_bn_stats (layout-agnostic), ganb_colsum, and by ganb_norm_act_fwd / _bwd
+ * with upsample = 2. */
+int ganb_upconv_supported(int n, int h, int w, int cin, int cout);
+int ganb_upconv_pack(const float* w_hwio, void* we_t_bf16, void* we_n_bf16, int cin, int cout, void* stream);
+int ganb_upconv_fprop(const void* x_bf16, const void* we_t_bf16, void* y_quad, int n, int h, int w, int cin, int cout,
+                      const float* alpha, const float* bias, int act, int out_dtype, void* stream);
+int ganb_upconv_dgrad(const void* dy_quad_bf16, const void* we_n_bf16, void* dx, int n, int h, int w, int cin, int cout,
+                      const float* alpha, int out_dtype, void* stream);
+int64_t ganb_upconv_wgrad_workspace(int n, int h, int w, int cin, int cout);
+int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, float* dw_hwio, void* workspace, int n, int h, int w,
+                      int cin, int cout, const float* scale, float beta, void* stream);
+
 /* fp32 HWIO filters -> bf16 operands of the tensor-core kernels; wn = [tap][ci_pad][co], wt = [tap][co][ci_pad]
  * (either may be NULL).  ci_pad >= ci (0 = ci) is the input-channel count of the operand copies: rows / columns
  * ci..ci_pad-1 are left untouched (the caller zeroes them once), so that a filter with ci % 8 != 0 (the 513-channel
@@ -173,6 +198,9 @@ int ganb_pack_weights(const ganb_pack_layer* layers_dev, int count, int total_ti
  * 2 = the reference's two per-device towers batched into one call, n = instance norm.
  * gamma/beta are tables [n_labels, c] indexed by labels[n] (labels NULL -> row 0; gamma NULL -> 1/0).
  * mean == NULL skips normalisation (pure activation + cast + resample).
+ * upsample: 0 = none, 1 = the output is written through a nearest 2x upsample (backward: dz is [n,2h,2w,c]),
+ * 2 = x (and dx) are stored in the QUAD LAYOUT of ganb_upconv_fprop, out / dz are plain NHWC at the same resolution
+ *     (all-bf16 path only).
  * ---------------------------------------------------------------------------------------------- */
 int64_t ganb_bn_stats_workspace(int n, int hw, int c, int groups);
 /* x is fp32 or bf16 (x_dtype); statistics are accumulated in fp32 per chunk and fp64 across chunks. One launch:

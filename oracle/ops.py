@@ -108,10 +108,32 @@ def conv2d_nhwc(x, filt, stride=1, padding="SAME"):
         pt, pb, _ = same_pads(x.shape[1], kh, stride)
         pl, pr, _ = same_pads(x.shape[2], kw, stride)
         xc = F.pad(xc, (pl, pr, pt, pb))
+    elif isinstance(padding, (tuple, list)):      # explicit (top, bottom, left, right) zero padding
+        pt, pb, pl, pr = padding
+        xc = F.pad(xc, (pl, pr, pt, pb))
     elif padding != "VALID":
         raise ValueError(padding)
     y = F.conv2d(xc, filt.permute(3, 2, 0, 1), stride=stride)
     return y.permute(0, 2, 3, 1)
+
+
+def subpixel_upconv_rounded(x_low, w, r16_filters=True):
+    """conv3x3_SAME(nearest2x(x_low), w) evaluated the way the B200 path does (ganb_upconv_*): four 2x2 convolutions
+    over the low-resolution tensor with effective filters E_ij[p][q] = sum_{r in R_i[p], s in R_j[q]} w[r][s],
+    R_0 = ({0}, {1,2}), R_1 = ({0,1}, {2}); identical to the reference formula in exact arithmetic -- the bf16 rounding
+    point moves from w to E (used only with BF16_OPERANDS)."""
+    n, h, wd, _ = x_low.shape
+    cout = w.shape[-1]
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = x_low.new_zeros((n, h, 2, wd, 2, cout))
+    for i in (0, 1):
+        for j in (0, 1):
+            e = torch.stack([torch.stack([sum(w[r, s] for r in rows[i][p_] for s in rows[j][q_]) for q_ in (0, 1)])
+                             for p_ in (0, 1)])                                 # [2, 2, cin, cout]
+            eq = _ste_r16(e) if r16_filters else e
+            y = _ConvRoundedOperands.apply(x_low, eq, 1, (1 - i, i, 1 - j, j))
+            out[:, :, i, :, j, :] = y
+    return out.reshape(n, 2 * h, 2 * wd, cout)
 
 
 def conv2d_transpose_nhwc(x, filt, stride=2, padding="SAME"):
@@ -184,8 +206,12 @@ def spectral_normed_weight(g, W, u=None, num_iters=1, update_collection=None, wi
 # ---------------------------------------------------------------------------------------------- conv2d.py
 def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv2D", conv_type="conv2d",
            channel_multiplier=0, padding="SAME", spectral_normed=False, update_collection=None,
-           inputs_norm=False, he_init=True, mask_type=None, weightnorm=None, biases=True, gain=1.0, reuse=None):
-    """common/ops/conv2d.py:31-218 (conv2d_.py adds the ignored `reuse` keyword)."""
+           inputs_norm=False, he_init=True, mask_type=None, weightnorm=None, biases=True, gain=1.0, reuse=None,
+           subpixel_up2=False):
+    """common/ops/conv2d.py:31-218 (conv2d_.py adds the ignored `reuse` keyword).
+    subpixel_up2 (oracle-only plumbing for UpsampleConv, resnet_block.py:83-97): `inputs` is the tensor BEFORE the
+    nearest 2x upsample; the fp32 oracle upsamples and convolves exactly like the reference, the bf16-operand oracle
+    mirrors the product's sub-pixel evaluation (subpixel_upconv_rounded)."""
     if conv_type != "conv2d":
         raise NotImplementedError("{0} is not supported by the oracle".format(conv_type))
     if mask_type is not None:
@@ -216,7 +242,15 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
             with g.variable_scope("filters"):
                 filters, sigma = spectral_normed_weight(g, filters, update_collection=update_collection,
                                                         with_sigma=True)
-        if BF16_OPERANDS:
+        if subpixel_up2:
+            assert filter_size == 3 and stride == 1 and padding == "SAME" and not spectral_normed and not inputs_norm
+            if BF16_OPERANDS:
+                result = subpixel_upconv_rounded(inputs_, raw_filters)
+            else:
+                n_, h_, w_, c_ = inputs_.shape
+                up = torch.cat([inputs_] * 4, dim=3).reshape(n_, h_, w_, 2, 2, c_).permute(0, 1, 3, 2, 4, 5)
+                result = conv2d_nhwc(up.reshape(n_, 2 * h_, 2 * w_, c_), filters, stride, padding)
+        elif BF16_OPERANDS:
             wq = _ste_r16(raw_filters)
             if spectral_normed:
                 wq = wq / sigma

@@ -68,9 +68,20 @@ def MeanPoolConv(g, inputs, output_dim, filter_size=3, stride=1, name=None, spec
                       inputs_norm=inputs_norm, he_init=he_init, biases=biases)
 
 
+# Set by tests to the product's rule (functional.upconv_eligible) so that the bf16-operand oracle rounds at the same
+# points as the product: (n, h, w, cin, cout, k) -> bool.  None: UpsampleConv is always upsample + conv.
+SUBPIXEL_RULE = None
+
+
 def UpsampleConv(g, inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False,
                  update_collection=None, inputs_norm=False, he_init=True, biases=True):
     """common/resnet_block.py:83-97"""
+    n, h, w, c = inputs.shape
+    if (SUBPIXEL_RULE is not None and not spectral_normed and not inputs_norm and stride == 1
+            and SUBPIXEL_RULE(n, h, w, c, output_dim, filter_size)):
+        return ops.Conv2D(g, inputs, c, output_dim, filter_size, stride, name, spectral_normed=False,
+                          update_collection=update_collection, inputs_norm=False, he_init=he_init, biases=biases,
+                          subpixel_up2=True)
     output = upsample2(inputs)
     return ops.Conv2D(g, output, output.shape[-1], output_dim, filter_size, stride, name,
                       spectral_normed=spectral_normed, update_collection=update_collection,
