@@ -200,7 +200,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     store = framework.reset_default_graph("cuda")
     allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
-    tr = P.Trainer(batch_size=64, seed=0, world_size=world, grad_allreduce=allreduce)
+    tr = P.Trainer(batch_size=64, seed=0, world_size=world, grad_allreduce=allreduce,
+                   bn_sync=bool(getattr(args, "bn_sync", False)))
 
     # synthetic inputs of SURVEY 8(d): int32 [64, 3072] uniform 0..255 (CHW-flattened), labels uniform 0..9;
     # every rank draws its own shard.
@@ -288,7 +289,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "images_per_s": value * 64,
             "l2": "no explicit flush: one step streams ~3 GB of activations, >> 126 MB L2",
             "step_tflops_algorithmic": PAIR_GFLOP / ms_step / 1e3 * 1.0,
-            "cuda_graphs": True, "final_d_loss": d_loss, "final_g_loss": g_loss,
+            "cuda_graphs": not tr.bn_sync, "bn_statistics": "all-reduced over ranks" if tr.bn_sync else "per rank (reference towers)",
+            "final_d_loss": d_loss, "final_g_loss": g_loss,
             "value_counts": "batch-64 D+G pairs per second summed over ranks (global images/s / 64)",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_data.numel() * 4 + host_labels.numel() * 4),
@@ -321,6 +323,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bn-sync", action="store_true",
+                    help="N > 1: also reduce G's batch-norm statistics over the ranks (eager mode; default: per-rank "
+                         "statistics = the reference's per-tower semantics, CUDA graphs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -142,8 +142,17 @@ class Trainer:
     """Builds the variables in the reference's graph-construction order and runs D / G training steps."""
 
     def __init__(self, batch_size: int = BATCH_SIZE, seed: int | None = 0, store=None, world_size: int = 1,
-                 grad_allreduce=None):
+                 grad_allreduce=None, bn_sync: bool = False):
+        """bn_sync: reduce the (conditional) batch-norm statistics of G over all ranks as well (every statistic tower
+        then spans the ranks' shares: N GPUs x batch/N reproduce one GPU at the global batch).  Default: per-rank
+        statistics, the reference's per-tower semantics.  The statistic all-reduces sit in the middle of the forward /
+        backward passes, so this mode runs eagerly (capture() is a no-op)."""
         self.store = store or get_store()
+        self.bn_sync = bool(bn_sync) and world_size > 1
+        if self.bn_sync:
+            if grad_allreduce is None:
+                raise ValueError("bn_sync needs the all-reduce callable (grad_allreduce)")
+            self.store.bn_sync = (grad_allreduce, world_size)
         self.batch = batch_size
         self.gen_batch = GEN_BS_MULTIPLE * batch_size
         self.world_size = world_size
@@ -274,6 +283,8 @@ class Trainer:
         parts = (("d_compute", self._d_compute), ("d_update", self._d_update),
                  ("g_compute", self._g_compute), ("g_update", self._g_update))
         self.graph_launches = {}
+        if self.bn_sync:
+            return   # collectives inside the passes: eager mode
         for root in ('Generator', 'Discriminator'):   # operand copies are current before any compute graph runs
             self._repack(root)
         for name, body in parts:
@@ -310,7 +321,12 @@ class Trainer:
         return self.g_loss
 
     def launches_per_pair(self) -> int:
-        """libganb200 kernels in one D-step + one G-step (valid after capture())."""
+        """libganb200 kernels in one D-step + one G-step (valid after capture(); counted live in eager mode)."""
+        if not self.graph_launches:
+            before = K.launch_count()
+            self.d_step(1)
+            self.g_step(1)
+            return K.launch_count() - before
         return sum(self.graph_launches.values())
 
     def train_iteration(self, iteration: int, batches):

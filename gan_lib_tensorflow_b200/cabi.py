@@ -10,7 +10,7 @@ import re
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libganb200.so")
+LIB_PATH = os.environ.get("GANB200_LIB") or os.path.join(HERE, "libganb200.so")   # override: kernel A/B experiments
 HEADER_PATH = os.path.join(HERE, "..", "include", "ganb200.h")
 
 OK = 0

@@ -1576,11 +1576,14 @@ static void launch_bwd_apply(const NormActBwd& p, bool norm, dim3 grid, int ppc,
 }
 }  // namespace ganb
 
-extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int dz_dtype, int dz_cstride, int n, int h,
-                                 int w, int c, const float* mean, const float* rstd, int groups, const float* gamma,
-                                 const float* beta, const int* labels, int n_rows, int act, int upsample,
-                                 float* dgamma, float* dbeta, const void* add, int add_dtype, void* dx, int dx_dtype,
-                                 void* workspace, void* stream) {
+// phase 0: everything; phase 1: per-sample / per-group sums only (reduce + finalize + dgamma/dbeta scatter), leaving
+// [s1 | s2] in the workspace at ganb_norm_act_bwd_sums_offset() for a cross-GPU all-reduce; phase 2: apply only, reading
+// the (all-reduced) sums back, with 1/count scaled by count_scale = 1/world.
+static int norm_act_bwd_impl(const void* x, int x_dtype, const void* dz, int dz_dtype, int dz_cstride, int n, int h,
+                             int w, int c, const float* mean, const float* rstd, int groups, const float* gamma,
+                             const float* beta, const int* labels, int n_rows, int act, int upsample,
+                             float* dgamma, float* dbeta, const void* add, int add_dtype, void* dx, int dx_dtype,
+                             void* workspace, int phase, float count_scale, void* stream) {
   if (!x || !dz || !dx) return fail(GANB_E_BADARG, "norm_act_bwd: null buffer");
   if (c % 4 != 0) return fail(GANB_E_UNSUPPORTED, "norm_act_bwd: c=%d must be a multiple of 4", c);
   if (groups <= 0 || n % groups != 0) return fail(GANB_E_BADARG, "norm_act_bwd: bad groups");
@@ -1605,26 +1608,30 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
     p.pix_per_chunk = ceil_div(hw, chunks);
     p.chunks = ceil_div(hw, p.pix_per_chunk);
     p.part = static_cast<float*>(workspace);
-    float* sums = p.part + static_cast<int64_t>(n) * chunks * 2 * c;
+    // fixed layout (independent of the chunk count actually used): [n][bwd_chunks][2][c] | [n][2][c] | s1 | s2
+    float* sums = p.part + static_cast<int64_t>(n) * bwd_chunks(n, hw) * 2 * c;
     float* s1 = sums + 2LL * n * c;
     float* s2 = s1 + static_cast<int64_t>(groups) * c;
-    const dim3 grid(p.chunks, n);
-    if (v8 && upsample) launch_k(norm_act_bwd_reduce_v8_kernel<true>, grid, 256, 0, STREAM, p);
-    else if (v8) launch_k(norm_act_bwd_reduce_v8_kernel<false>, grid, 256, 0, STREAM, p);
-    else if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
-    else launch_bwd_reduce<float>(p, grid, STREAM);
-    GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
-    launch_k(norm_act_bwd_finalize_kernel, dim3(ceil_div(c, 8), groups), 256, 0, STREAM, p.part, n, c, p.chunks, groups, gamma,
-                                                                                  labels, sums, s1, s2);
-    GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
-    if (gamma && dgamma && dbeta) {
-      const int rows = (labels && n_rows > 0) ? n_rows : 1;
-      launch_k(norm_act_bwd_scatter_kernel, ceil_div(rows * c, 8), 256, 0, STREAM, sums, n, c, rows, labels, dgamma, dbeta);
-      GANB_CHECK_LAUNCH("norm_act_bwd_scatter_kernel");
+    if (phase != 2) {
+      const dim3 grid(p.chunks, n);
+      if (v8 && upsample) launch_k(norm_act_bwd_reduce_v8_kernel<true>, grid, 256, 0, STREAM, p);
+      else if (v8) launch_k(norm_act_bwd_reduce_v8_kernel<false>, grid, 256, 0, STREAM, p);
+      else if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
+      else launch_bwd_reduce<float>(p, grid, STREAM);
+      GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
+      launch_k(norm_act_bwd_finalize_kernel, dim3(ceil_div(c, 8), groups), 256, 0, STREAM, p.part, n, c, p.chunks, groups, gamma,
+                                                                                    labels, sums, s1, s2);
+      GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
+      if (gamma && dgamma && dbeta) {
+        const int rows = (labels && n_rows > 0) ? n_rows : 1;
+        launch_k(norm_act_bwd_scatter_kernel, ceil_div(rows * c, 8), 256, 0, STREAM, sums, n, c, rows, labels, dgamma, dbeta);
+        GANB_CHECK_LAUNCH("norm_act_bwd_scatter_kernel");
+      }
     }
     p.s1 = s1; p.s2 = s2;
-    p.inv_count = 1.0f / (static_cast<float>(n / groups) * hw);
+    p.inv_count = count_scale / (static_cast<float>(n / groups) * hw);
   }
+  if (phase == 1) return mean ? 0 : fail(GANB_E_BADARG, "norm_act_bwd: phase 1 needs normalisation statistics");
   {
     const int chunks2 = v8 ? v8_chunks(n, h * w, 2) : bwd_chunks(n, h * w);
     const int ppc = ceil_div(h * w, chunks2);
@@ -1641,6 +1648,70 @@ extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int
     else launch_bwd_apply<float>(p, mean != nullptr, grid, ppc, STREAM);
   }
   GANB_CHECK_LAUNCH("norm_act_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int dz_dtype, int dz_cstride, int n, int h,
+                                 int w, int c, const float* mean, const float* rstd, int groups, const float* gamma,
+                                 const float* beta, const int* labels, int n_rows, int act, int upsample,
+                                 float* dgamma, float* dbeta, const void* add, int add_dtype, void* dx, int dx_dtype,
+                                 void* workspace, void* stream) {
+  return norm_act_bwd_impl(x, x_dtype, dz, dz_dtype, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta, labels, n_rows,
+                           act, upsample, dgamma, dbeta, add, add_dtype, dx, dx_dtype, workspace, 0, 1.0f, stream);
+}
+
+extern "C" int ganb_norm_act_bwd_phase(const void* x, int x_dtype, const void* dz, int dz_dtype, int dz_cstride, int n,
+                                       int h, int w, int c, const float* mean, const float* rstd, int groups,
+                                       const float* gamma, const float* beta, const int* labels, int n_rows, int act,
+                                       int upsample, float* dgamma, float* dbeta, const void* add, int add_dtype, void* dx,
+                                       int dx_dtype, void* workspace, int phase, float count_scale, void* stream) {
+  if (phase != 1 && phase != 2) return fail(GANB_E_BADARG, "norm_act_bwd_phase: phase must be 1 or 2");
+  return norm_act_bwd_impl(x, x_dtype, dz, dz_dtype, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta, labels, n_rows,
+                           act, upsample, dgamma, dbeta, add, add_dtype, dx, dx_dtype, workspace, phase, count_scale, stream);
+}
+
+extern "C" int64_t ganb_norm_act_bwd_sums_offset(int n, int hw, int c, int groups) {
+  (void)groups;
+  return (static_cast<int64_t>(n) * bwd_chunks(n, hw) * 2 * c + 2LL * n * c) * 4;
+}
+
+namespace ganb {
+// cross-GPU batch statistics: every rank contributes [mean, E[x^2]] of its (equally sized) share of a statistic group
+__global__ void __launch_bounds__(256) bn_moments_pack_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              int count, float eps, float* __restrict__ out) {
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= count) return;
+  const float m = mean[i], r = rstd[i];
+  out[i] = m;
+  out[count + i] = 1.0f / (r * r) - eps + m * m;
+}
+__global__ void __launch_bounds__(256) bn_moments_unpack_kernel(const float* __restrict__ sums, int count, float inv_world,
+                                                                float eps, float* __restrict__ mean,
+                                                                float* __restrict__ rstd) {
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= count) return;
+  const float m = sums[i] * inv_world;
+  float var = sums[count + i] * inv_world - m * m;
+  if (var < 0.f) var = 0.f;
+  mean[i] = m;
+  rstd[i] = rsqrtf(var + eps);
+}
+}  // namespace ganb
+
+extern "C" int ganb_bn_moments_pack(const float* mean, const float* rstd, int count, float eps, float* out, void* stream) {
+  if (!mean || !rstd || !out || count <= 0) return fail(GANB_E_BADARG, "bn_moments_pack: bad arguments");
+  launch_k(bn_moments_pack_kernel, ceil_div(count, 256), 256, 0, STREAM, mean, rstd, count, eps, out);
+  GANB_CHECK_LAUNCH("bn_moments_pack_kernel");
+  return 0;
+}
+
+extern "C" int ganb_bn_moments_unpack(const float* sums, int count, float inv_world, float eps, float* mean, float* rstd,
+                                      void* stream) {
+  if (!sums || !mean || !rstd || count <= 0) return fail(GANB_E_BADARG, "bn_moments_unpack: bad arguments");
+  launch_k(bn_moments_unpack_kernel, ceil_div(count, 256), 256, 0, STREAM, sums, count, inv_world, eps, mean, rstd);
+  GANB_CHECK_LAUNCH("bn_moments_unpack_kernel");
   return 0;
 }
 

@@ -404,6 +404,9 @@ class VariableStore:
         self.tape: Tape | None = None
         self.stat_groups = 1
         self._consts: dict[float, torch.Tensor] = {}
+        # cross-GPU batch statistics: (allreduce_sum(tensor) -> None, world size) or None = per-rank statistics, the
+        # reference's per-tower semantics (common/ops/normalization.py:47)
+        self.bn_sync = None
 
     # -- scopes ---------------------------------------------------------------------------------
     @contextlib.contextmanager

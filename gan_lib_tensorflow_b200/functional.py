@@ -545,8 +545,12 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
         g = n
     elif stats is not None:
         raise ValueError(stats)
+    # cross-GPU batch statistics (store.bn_sync = (allreduce_sum, world)): only for statistics over the BATCH
+    sync = store.bn_sync if stats == "batch" else None
     if stats is not None:
         mean, rstd = K.bn_stats(x.data, n, h * w, c, g, eps)
+        if sync is not None:
+            K.bn_stats_sync(mean, rstd, eps, sync)
     gam = gamma.data if gamma is not None else None
     bet = beta.data if beta is not None else None
     # the raw bf16 copy (1x1-shortcut operand) is x itself when x is already stored in bf16
@@ -582,7 +586,7 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
                     and not quad):
                 extra, x.grad = x.grad, None
             dx = K.norm_act_bwd(x.data, gz, 0, n, h, w, c, mean, rstd, g, gam, bet, labels, act, ups, dgam, dbet,
-                                extra, x.gdtype)
+                                extra, x.gdtype, sync=sync)
             if x.requires_grad:
                 x.accum(dx)
         _tape().record(bwd)

@@ -39,7 +39,8 @@ def L():
             _L = _NullLib()
             return _L
         _L = cabi.lib()
-        for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
+        for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace",
+                     "ganb_norm_act_bwd_sums_offset", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
                      "ganb_minibatch_std_workspace",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
@@ -202,17 +203,38 @@ def norm_act_fwd(x, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, up
 
 
 def norm_act_bwd(x, dz, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, upsample, dgamma, dbeta,
-                 add, dx_dtype):
+                 add, dx_dtype, sync=None):
+    """sync = (allreduce_sum(tensor) -> None, world): cross-GPU batch statistics -- the per-group sums of the local
+    share are all-reduced between the reduction and the apply kernels."""
     dx = torch.empty((n, h, w, c), dtype=dx_dtype, device=x.device)
     ws = None
     if mean is not None:
         ws = _ws(L().ganb_norm_act_bwd_workspace(n, h * w, c, groups), x.device)
     n_rows = int(gamma.shape[0]) if (gamma is not None and gamma.dim() == 2) else 1
-    check(L().ganb_norm_act_bwd(ptr(x), dt(x), ptr(dz), dt(dz), dz_cstride, n, h, w, c, ptr(mean), ptr(rstd), groups,
-                                ptr(gamma), ptr(beta), ptr(labels), n_rows, act_code(act), int(upsample), ptr(dgamma),
-                                ptr(dbeta), ptr(add), dt(add) if add is not None else F32, ptr(dx), dt(dx), ptr(ws),
-                                _stream()), "ganb_norm_act_bwd")
+    args = (ptr(x), dt(x), ptr(dz), dt(dz), dz_cstride, n, h, w, c, ptr(mean), ptr(rstd), groups,
+            ptr(gamma), ptr(beta), ptr(labels), n_rows, act_code(act), int(upsample), ptr(dgamma),
+            ptr(dbeta), ptr(add), dt(add) if add is not None else F32, ptr(dx), dt(dx), ptr(ws))
+    if sync is None or mean is None:
+        check(L().ganb_norm_act_bwd(*args, _stream()), "ganb_norm_act_bwd")
+        return dx
+    allreduce, world = sync
+    check(L().ganb_norm_act_bwd_phase(*args, 1, c_float(1.0), _stream()), "ganb_norm_act_bwd_phase")
+    off = int(L().ganb_norm_act_bwd_sums_offset(n, h * w, c, groups))
+    sums = ws[off:off + 2 * groups * c * 4].view(torch.float32)
+    allreduce(sums)
+    check(L().ganb_norm_act_bwd_phase(*args, 2, c_float(1.0 / world), _stream()), "ganb_norm_act_bwd_phase")
     return dx
+
+
+def bn_stats_sync(mean, rstd, eps, sync):
+    """Replaces the local (mean, rstd) [groups, c] by the statistics over all ranks (equal shares per rank)."""
+    allreduce, world = sync
+    count = mean.numel()
+    buf = torch.empty(2 * count, dtype=torch.float32, device=mean.device)
+    check(L().ganb_bn_moments_pack(ptr(mean), ptr(rstd), count, c_float(eps), ptr(buf), _stream()), "ganb_bn_moments_pack")
+    allreduce(buf)
+    check(L().ganb_bn_moments_unpack(ptr(buf), count, c_float(1.0 / world), c_float(eps), ptr(mean), ptr(rstd), _stream()),
+          "ganb_bn_moments_unpack")
 
 
 def meanpool2(x, add, out_dtype):

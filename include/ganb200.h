@@ -220,6 +220,22 @@ int ganb_norm_act_bwd(const void* x, int x_dtype, const void* dz, int dz_dtype, 
                       const int* labels, int n_rows, int act, int upsample, float* dgamma, float* dbeta,
                       const void* add, int add_dtype, void* dx, int dx_dtype, void* workspace, void* stream);
 
+/* Cross-GPU batch statistics (the BatchNorm statistic reduction of the multi-GPU path; the reference itself keeps
+ * statistics per tower, common/ops/normalization.py:47).  Forward: ganb_bn_stats on the local share, then
+ * ganb_bn_moments_pack -> [mean | E[x^2]] (2*count floats, count = groups*c) -> NCCL all-reduce(sum) ->
+ * ganb_bn_moments_unpack (inv_world = 1/ranks; equal shares per rank) -> global mean / rstd.
+ * Backward: ganb_norm_act_bwd_phase(phase 1) leaves [sum(dy) | sum(dy*xhat)] (2*groups*c floats) at byte offset
+ * ganb_norm_act_bwd_sums_offset() of the workspace -> all-reduce(sum) -> phase 2 applies with count_scale = 1/ranks. */
+int ganb_bn_moments_pack(const float* mean, const float* rstd, int count, float eps, float* out, void* stream);
+int ganb_bn_moments_unpack(const float* sums, int count, float inv_world, float eps, float* mean, float* rstd,
+                           void* stream);
+int64_t ganb_norm_act_bwd_sums_offset(int n, int hw, int c, int groups);
+int ganb_norm_act_bwd_phase(const void* x, int x_dtype, const void* dz, int dz_dtype, int dz_cstride, int n, int h, int w,
+                            int c, const float* mean, const float* rstd, int groups, const float* gamma, const float* beta,
+                            const int* labels, int n_rows, int act, int upsample, float* dgamma, float* dbeta,
+                            const void* add, int add_dtype, void* dx, int dx_dtype, void* workspace, int phase,
+                            float count_scale, void* stream);
+
 /* 2x2 mean-pool written as in common/resnet_block.py:62-63 (add_n of four strided slices / 4), + optional add */
 int ganb_meanpool2_fwd(const void* x, int x_dtype, const float* add, void* out, int out_dtype, int n, int h, int w,
                        int c, void* stream);

@@ -20,6 +20,18 @@ which = sys.argv[1] if len(sys.argv) > 1 else "fprop"
 for _ in range(4):
     if which == "fprop":
         K.conv_igemm(x, wp, n, h, w, cin, h, w, cout, k, k, 1, 1, False, None, bias, None, None, torch.float32)
+    elif which == "upconv":      # sub-pixel UpsampleConv 256->256 from 16x16 (G.Block.3.Conv1), fprop + dgrad + wgrad
+        xl = x[:, :16, :16, :].contiguous()
+        we = (torch.randn(16, cout, cin, device=dev) * 0.02).to(torch.bfloat16)
+        yq = K.upconv_fprop(xl, we, n, 16, 16, cin, cout, None, bias, None, torch.bfloat16)
+        K.upconv_dgrad(dy, we, n, 16, 16, cin, cout, None, torch.bfloat16)
+        K.upconv_wgrad(xl, dy, dw, n, 16, 16, cin, cout, None, 0.0)
+    elif which == "norm":        # conditional-BN forward / backward kernels at G.Block.3's size (HBM-bound)
+        xb = x
+        mean, rstd = K.bn_stats(xb, n, h * w, cin, 2, 1e-5)
+        a = K.norm_act_fwd(xb, n, h, w, cin, mean, rstd, 2, None, None, None, "relu", False, torch.bfloat16)
+        K.norm_act_bwd(xb, dy, 0, n, h, w, cin, mean, rstd, 2, None, None, None, "relu", False, None, None, None,
+                       torch.bfloat16)
     elif which == "dgrad":
         K.conv_igemm(dy, wp, n, h, w, cout, h, w, cin, k, k, 1, 1, True, None, None, None, None, torch.float32)
     else:

@@ -162,6 +162,35 @@ def test_pggan_variable_manifest_matches_the_oracle(host):
     assert [v.key for v in store.trainable_variables("g_net")] == [n for n, _ in g.trainable_variables("g_net")]
 
 
+def test_cross_gpu_batch_statistics_call_sequence(host):
+    """store.bn_sync = (allreduce, world): a batch-statistics normalisation all-reduces [mean | E[x^2]] between
+    ganb_bn_stats and the normalise kernel, and [sum(dy) | sum(dy*xhat)] between the two backward phases; instance
+    statistics and un-normalised activations are never reduced."""
+    store, rec = host
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.framework import Var
+
+    reduced = []
+    store.bn_sync = (lambda t: reduced.append((len(rec.calls), tuple(t.shape))), 4)
+    x = Var(torch.zeros(4, 8, 8, 16, dtype=torch.bfloat16), requires_grad=True)
+    with store.gradient_tape() as tape:
+        y, _ = F.norm_act(x, stats="batch", act="relu")
+        tape.backward(y, grad=torch.zeros(4, 8, 8, 16, dtype=torch.bfloat16))
+    names = rec.names()
+    assert names == ["ganb_bn_stats", "ganb_bn_moments_pack", "ganb_bn_moments_unpack", "ganb_norm_act_fwd",
+                     "ganb_norm_act_bwd_phase", "ganb_norm_act_bwd_sums_offset", "ganb_norm_act_bwd_phase"]
+    assert [r[0] for r in reduced] == [2, 6]                  # after pack, and between the two backward phases
+    assert reduced[0][1] == (2 * 16,)      # [mean | E[x^2]] of 16 channels, one statistic group
+    phases = [c[1][-3] for c in rec.calls if c[0] == "ganb_norm_act_bwd_phase"]
+    scales = [c[1][-2].value for c in rec.calls if c[0] == "ganb_norm_act_bwd_phase"]
+    assert phases == [1, 2] and scales == [1.0, 0.25]
+    n_before = len(reduced)
+    with store.gradient_tape() as tape:
+        y, _ = F.norm_act(x, stats="instance", act=None)
+        z, _ = F.norm_act(x, stats=None, act="relu")
+    assert len(reduced) == n_before
+
+
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
     store, _ = host
     from gan_lib_tensorflow_b200.common import resnet_block
