@@ -566,6 +566,87 @@ bn_stats_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int rows_per_gro
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ cp.async rings
+// The streaming reductions below are bound by HBM latency x bytes in flight, not by instruction issue: with plain
+// loads a thread holds 4 x 16 B per tensor in registers and nothing is in flight while it computes (ncu: 3.1-3.7 TB/s,
+// profiles/r01_ncu_norm_kernels.txt).  The *_v8p kernels issue the same 16-byte accesses as cp.async into a per-thread
+// shared-memory ring (STAGES iterations deep, no registers held, no block-level synchronisation: every thread reads
+// back only what it copied), which keeps 2-3x more bytes in flight per SM.
+__device__ __forceinline__ void cp_async16(uint4* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = pred ? 16 : 0;                 // src-size 0: nothing is read, the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int PIPE_U = 4;        // 16-byte accesses per tensor per iteration and thread
+constexpr int STATS_STAGES = 3;  // bn_stats: 3 x 4 x 256 x 16 B = 48 KB per block
+constexpr int BWD_STAGES = 2;    // backward kernels: up to 3 tensors x 2 x 4 x 256 x 16 B = 96 KB per block
+
+__global__ void __launch_bounds__(256)
+bn_stats_partial_v8p_kernel(const __nv_bfloat16* __restrict__ x, int rows_per_group, int c, int chunks,
+                            int rows_per_chunk, float* __restrict__ partial) {
+  pdl_wait();
+  extern __shared__ uint4 ring_raw[];
+  uint4* ring = ring_raw + threadIdx.x;        // [stage][u][256 threads]
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const int v = c >> 3;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int r0 = chunk * rows_per_chunk;
+  const int r1 = min(rows_per_group, r0 + rows_per_chunk);
+  const __nv_bfloat16* xg = x + static_cast<int64_t>(g) * rows_per_group * c;
+  __shared__ float sh[256][17];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (col < v && ry < lanes) {
+      const __nv_bfloat16* xc = xg + col * 8;
+      const int step = lanes * PIPE_U;
+      const int iters = (r1 - r0 - ry + step - 1) / step;
+      auto issue = [&](int it) {
+        uint4* dst = ring + (it % STATS_STAGES) * PIPE_U * 256;
+#pragma unroll
+        for (int u = 0; u < PIPE_U; ++u) {
+          const int r = r0 + ry + (it * PIPE_U + u) * lanes;
+          const bool ok = r < r1;
+          cp_async16(dst + u * 256, xc + static_cast<int64_t>(ok ? r : r0) * c, ok);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int it = 0; it < STATS_STAGES - 1; ++it) issue(it);
+      for (int it = 0; it < iters; ++it) {
+        issue(it + STATS_STAGES - 1);
+        cp_async_wait<STATS_STAGES - 1>();
+        const uint4* src = ring + (it % STATS_STAGES) * PIPE_U * 256;
+#pragma unroll
+        for (int u = 0; u < PIPE_U; ++u) {
+          float a[8];
+          cvt8(src[u * 256], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s[j] += a[j]; q[j] += a[j] * a[j]; }
+        }
+      }
+      cp_async_wait<0>();
+    }
+    lanes_sum16(s, q, lanes, cols_per_pass, cx, ry, sh);
+    if (ry == 0 && col < v) {
+      float* out = partial + (static_cast<int64_t>(g) * chunks + chunk) * 2 * c;
+      st4(out + col * 8, make_float4(s[0], s[1], s[2], s[3]));
+      st4(out + col * 8 + 4, make_float4(s[4], s[5], s[6], s[7]));
+      st4(out + c + col * 8, make_float4(q[0], q[1], q[2], q[3]));
+      st4(out + c + col * 8 + 4, make_float4(q[4], q[5], q[6], q[7]));
+    }
+  }
+}
+
 // pixel index inside one sample: quad layout [h/2][w/2][2i+j] -> NHWC row-major [h][w]
 __device__ __forceinline__ int quad_to_nhwc(int q, int w) {
   const int g = q & 3, cell = q >> 2;
@@ -826,6 +907,98 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8_kernel(const Nor
   }
 }
 
+
+// cp.async-ring variant of the backward apply kernel for the common case (no upsample in the forward pass).
+// element offset of the upstream gradient of pixel px (sample ni)
+__device__ __forceinline__ int64_t bwd_dz_off(const NormActBwd& p, int ni, int px, int c8) {
+  const int qz = p.quad ? quad_to_nhwc(px, p.w) : px;
+  return (static_cast<int64_t>(ni) * p.h * p.w + qz) * p.dz_cstride + c8;
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8p_kernel(const NormActBwd p, int pix_per_chunk) {
+  pdl_wait();
+  extern __shared__ uint4 ring_raw[];
+  uint4* ring_x = ring_raw + threadIdx.x;
+  uint4* ring_z = ring_x + BWD_STAGES * PIPE_U * 256;
+  uint4* ring_a = ring_z + BWD_STAGES * PIPE_U * 256;
+  const int ni = blockIdx.y;
+  const int v = p.c >> 3;
+  const int cols = min(v, 256);
+  const int lanes = 256 / cols;
+  const int cx = threadIdx.x % cols, ly = threadIdx.x / cols;
+  if (ly >= lanes) return;
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * pix_per_chunk, p1 = min(hw, p0 + pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(p.x);
+  const __nv_bfloat16* dzp = static_cast<const __nv_bfloat16*>(p.dz);
+  const __nv_bfloat16* addp = static_cast<const __nv_bfloat16*>(p.add);
+  __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(p.dx);
+  for (int cb = 0; cb < v; cb += cols) {
+    const int col = cb + cx;
+    if (col >= v) continue;
+    const int c8 = col * 8;
+    float t1[8], t2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
+    if (NORM) {
+      ldf8(p.s1 + g * p.c + c8, t1);
+      ldf8(p.s2 + g * p.c + c8, t2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { t1[j] *= p.inv_count; t2[j] *= p.inv_count; }
+    }
+    BwdConst8 k;
+    bwd_const8<NORM>(p, ni, g, c8, k);
+    const int step = lanes * PIPE_U;
+    const int iters = (p1 - p0 - ly + step - 1) / step;
+    auto issue = [&](int it) {
+      const int so = (it % BWD_STAGES) * PIPE_U * 256;
+#pragma unroll
+      for (int u = 0; u < PIPE_U; ++u) {
+        const int qx = p0 + ly + (it * PIPE_U + u) * lanes;
+        const bool ok = qx < p1;
+        const int qq = ok ? qx : p0;
+        const int64_t pix = static_cast<int64_t>(ni) * hw + qq;
+        cp_async16(ring_x + so + u * 256, xp + pix * p.c + c8, ok);
+        cp_async16(ring_z + so + u * 256, dzp + bwd_dz_off(p, ni, qq, c8), ok);
+        if (addp) cp_async16(ring_a + so + u * 256, addp + pix * p.c + c8, ok);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int it = 0; it < BWD_STAGES - 1; ++it) issue(it);
+    for (int it = 0; it < iters; ++it) {
+      issue(it + BWD_STAGES - 1);
+      cp_async_wait<BWD_STAGES - 1>();
+      const int so = (it % BWD_STAGES) * PIPE_U * 256;
+#pragma unroll
+      for (int u = 0; u < PIPE_U; ++u) {
+        const int qx = p0 + ly + (it * PIPE_U + u) * lanes;
+        if (qx >= p1) break;
+        const int64_t pix = static_cast<int64_t>(ni) * hw + qx;
+        float a[8], dz[8], dx[8];
+        cvt8(ring_x[so + u * 256], a);
+        cvt8(ring_z[so + u * 256], dz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = a[j] * k.r[j] - k.mr[j];
+          const float dy = dz[j] * dact_f(xh * k.ga[j] + k.be[j], p.act);
+          dx[j] = NORM ? k.r[j] * (k.ga[j] * dy - t1[j] - xh * t2[j]) : dy;
+        }
+        if (addp) {
+          float q[8];
+          cvt8(ring_a[so + u * 256], q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dx[j] += q[j];
+        }
+        stg16(dxp + pix * p.c + c8, pack8(dx));
+      }
+    }
+    cp_async_wait<0>();
+  }
+}
+
 __global__ void __launch_bounds__(256)
 colsum_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int c, int rows_per_chunk,
                          float* __restrict__ partial) {
@@ -858,6 +1031,64 @@ colsum_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int 
           for (int j = 0; j < 8; ++j) s[j] += a[j];
         }
       }
+    }
+    lanes_sum16(s, z, lanes, cols_per_pass, cx, ry, sh);
+    if (ry == 0 && col < v) {
+      st4(partial + static_cast<int64_t>(chunk) * c + col * 8, make_float4(s[0], s[1], s[2], s[3]));
+      st4(partial + static_cast<int64_t>(chunk) * c + col * 8 + 4, make_float4(s[4], s[5], s[6], s[7]));
+    }
+  }
+}
+
+// cp.async-ring variant (see bn_stats_partial_v8p_kernel): same access pattern, 3 iterations in flight
+__global__ void __launch_bounds__(256)
+colsum_partial_v8p_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int c, int rows_per_chunk,
+                          float* __restrict__ partial) {
+  pdl_wait();
+  extern __shared__ uint4 ring_raw[];
+  uint4* ring = ring_raw + threadIdx.x;
+  const int chunk = blockIdx.x;
+  const int v = c >> 3;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int64_t r0 = static_cast<int64_t>(chunk) * rows_per_chunk;
+  const int64_t r1 = min(rows, r0 + rows_per_chunk);
+  __shared__ float sh[256][17];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float s[8], z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; z[j] = 0.f; }
+    if (col < v && ry < lanes) {
+      const __nv_bfloat16* xc = x + col * 8;
+      const int step = lanes * PIPE_U;
+      const int iters = static_cast<int>((r1 - r0 - ry + step - 1) / step);
+      auto issue = [&](int it) {
+        uint4* dst = ring + (it % STATS_STAGES) * PIPE_U * 256;
+#pragma unroll
+        for (int u = 0; u < PIPE_U; ++u) {
+          const int64_t r = r0 + ry + static_cast<int64_t>(it * PIPE_U + u) * lanes;
+          const bool ok = r < r1;
+          cp_async16(dst + u * 256, xc + (ok ? r : r0) * c, ok);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int it = 0; it < STATS_STAGES - 1; ++it) issue(it);
+      for (int it = 0; it < iters; ++it) {
+        issue(it + STATS_STAGES - 1);
+        cp_async_wait<STATS_STAGES - 1>();
+        const uint4* src = ring + (it % STATS_STAGES) * PIPE_U * 256;
+#pragma unroll
+        for (int u = 0; u < PIPE_U; ++u) {
+          float a[8];
+          cvt8(src[u * 256], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] += a[j];
+        }
+      }
+      cp_async_wait<0>();
     }
     lanes_sum16(s, z, lanes, cols_per_pass, cx, ry, sh);
     if (ry == 0 && col < v) {
@@ -1484,9 +1715,16 @@ extern "C" int ganb_bn_stats(const void* x, int x_dtype, int n, int hw, int c, i
   const int rows_per_chunk = ceil_div(rows_per_group, chunks);
   const int used = ceil_div(rows_per_group, rows_per_chunk);
   const dim3 grid(used, groups);
-  if (x_dtype == GANB_BF16 && c % 8 == 0)
-    launch_k(bn_stats_partial_v8_kernel, grid, 256, 0, STREAM, static_cast<const __nv_bfloat16*>(x), rows_per_group, c, used,
-             rows_per_chunk, static_cast<float*>(workspace));
+  if (x_dtype == GANB_BF16 && c % 8 == 0) {
+    constexpr int smem = STATS_STAGES * PIPE_U * 256 * 16;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(bn_stats_partial_v8p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      configured = true;
+    }
+    launch_k(bn_stats_partial_v8p_kernel, grid, 256, smem, STREAM, static_cast<const __nv_bfloat16*>(x), rows_per_group, c,
+             used, rows_per_chunk, static_cast<float*>(workspace));
+  }
   else if (x_dtype == GANB_BF16)
     launch_k(bn_stats_partial_kernel<__nv_bfloat16>, grid, 256, 0, STREAM, static_cast<const __nv_bfloat16*>(x), rows_per_group, c,
                                                                       used, rows_per_chunk, static_cast<float*>(workspace));
@@ -1615,6 +1853,8 @@ static int norm_act_bwd_impl(const void* x, int x_dtype, const void* dz, int dz_
     if (phase != 2) {
       const dim3 grid(p.chunks, n);
       if (v8 && upsample) launch_k(norm_act_bwd_reduce_v8_kernel<true>, grid, 256, 0, STREAM, p);
+      // (the cp.async-ring variant of this kernel measured SLOWER than plain loads, 244 vs 211 us per step --
+      // profiles/r01_elementwise_pipe_ab.txt -- while the statistics and apply kernels gained; it is not used)
       else if (v8) launch_k(norm_act_bwd_reduce_v8_kernel<false>, grid, 256, 0, STREAM, p);
       else if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
       else launch_bwd_reduce<float>(p, grid, STREAM);
@@ -1637,11 +1877,17 @@ static int norm_act_bwd_impl(const void* x, int x_dtype, const void* dz, int dz_
     const int ppc = ceil_div(h * w, chunks2);
     const dim3 grid(ceil_div(h * w, ppc), n);
     if (v8) {
+      constexpr int smem = 3 * BWD_STAGES * PIPE_U * 256 * 16;
+      static bool configured = false;
+      if (!configured) {
+        cudaFuncSetAttribute(norm_act_bwd_apply_v8p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+      }
       const int idx = (mean ? 2 : 0) | (upsample ? 1 : 0);
       switch (idx) {
-        case 0: launch_k(norm_act_bwd_apply_v8_kernel<false, false>, grid, 256, 0, STREAM, p, ppc); break;
+        case 0: launch_k(norm_act_bwd_apply_v8_kernel<false, false>, grid, 256, 0, STREAM, p, ppc); break;   // neutral in A/B
         case 1: launch_k(norm_act_bwd_apply_v8_kernel<false, true>, grid, 256, 0, STREAM, p, ppc); break;
-        case 2: launch_k(norm_act_bwd_apply_v8_kernel<true, false>, grid, 256, 0, STREAM, p, ppc); break;
+        case 2: launch_k(norm_act_bwd_apply_v8p_kernel<true>, grid, 256, smem, STREAM, p, ppc); break;
         default: launch_k(norm_act_bwd_apply_v8_kernel<true, true>, grid, 256, 0, STREAM, p, ppc); break;
       }
     } else if (p.x_bf16) launch_bwd_apply<__nv_bfloat16>(p, mean != nullptr, grid, ppc, STREAM);
@@ -1870,9 +2116,16 @@ static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float*
     launch_k(colsum_narrow_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
     GANB_CHECK_LAUNCH("colsum_narrow_kernel");
   } else {
-    if (sizeof(TIn) == 2 && c % 8 == 0)
-      launch_k(colsum_partial_v8_kernel, used, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), rows, c, rows_per_chunk,
-               static_cast<float*>(workspace));
+    if (sizeof(TIn) == 2 && c % 8 == 0) {
+      constexpr int smem = STATS_STAGES * PIPE_U * 256 * 16;
+      static bool configured = false;
+      if (!configured) {
+        cudaFuncSetAttribute(colsum_partial_v8p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+      }
+      launch_k(colsum_partial_v8p_kernel, used, 256, smem, s, reinterpret_cast<const __nv_bfloat16*>(x), rows, c,
+               rows_per_chunk, static_cast<float*>(workspace));
+    }
     else
       launch_k(colsum_partial_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
     GANB_CHECK_LAUNCH("colsum_partial_kernel");
