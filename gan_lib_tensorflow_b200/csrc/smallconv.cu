@@ -191,19 +191,31 @@ struct SgemmParams {
   const float* alpha; const float* bias; float beta;
 };
 
+// 16 x 16 outputs per block, 64-deep k tiles: every thread has 8 independent global loads in flight per round trip
+// (the 16-deep version spent one full memory latency per 16 k: 13 us for k = 300, all of it on D's critical chain).
 __global__ void __launch_bounds__(256) sgemm_small_kernel(const SgemmParams p) {
   pdl_wait();
-  __shared__ float As[16][17], Bs[16][17];
+  constexpr int KT = 64;
+  __shared__ float As[16][KT + 1], Bs[KT][17];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
   float acc = 0.f;
-  for (int k0 = 0; k0 < p.k; k0 += 16) {
-    const int ka = k0 + tx, kb = k0 + ty;
-    As[ty][tx] = (row < p.m && ka < p.k) ? p.a[row * p.a_sm + ka * p.a_sk] : 0.f;
-    Bs[ty][tx] = (kb < p.k && col < p.n) ? p.b[kb * p.b_sk + col * p.b_sn] : 0.f;
+  for (int k0 = 0; k0 < p.k; k0 += KT) {
+    float av[KT / 16], bv[KT / 16];
+#pragma unroll
+    for (int i = 0; i < KT / 16; ++i) {
+      const int ka = k0 + tx + 16 * i, kb = k0 + ty + 16 * i;
+      av[i] = (row < p.m && ka < p.k) ? p.a[row * p.a_sm + ka * p.a_sk] : 0.f;
+      bv[i] = (kb < p.k && col < p.n) ? p.b[kb * p.b_sk + col * p.b_sn] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < KT / 16; ++i) {
+      As[ty][tx + 16 * i] = av[i];
+      Bs[ty + 16 * i][tx] = bv[i];
+    }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) acc += As[ty][kk] * Bs[kk][tx];
+    for (int kk = 0; kk < KT; ++kk) acc += As[ty][kk] * Bs[kk][tx];
     __syncthreads();
   }
   if (row < p.m && col < p.n) {
