@@ -280,11 +280,16 @@ class Trainer:
         Must be called after at least one eager D-step and G-step (all workspaces / descriptor tables exist).
         With a gradient collective the compute and update halves are captured separately and the all-reduce
         runs between them on the same stream."""
-        parts = (("d_compute", self._d_compute), ("d_update", self._d_update),
-                 ("g_compute", self._g_compute), ("g_update", self._g_update))
         self.graph_launches = {}
         if self.bn_sync:
             return   # collectives inside the passes: eager mode
+        if self.grad_allreduce is None:
+            # single GPU: nothing sits between the backward pass and the update, so each step is ONE graph (every graph
+            # boundary costs ~20-30 us of idle GPU at this step size)
+            parts = (("d_full", self._d_body), ("g_full", self._g_body))
+        else:
+            parts = (("d_compute", self._d_compute), ("d_update", self._d_update),
+                     ("g_compute", self._g_compute), ("g_update", self._g_update))
         for root in ('Generator', 'Discriminator'):   # operand copies are current before any compute graph runs
             self._repack(root)
         for name, body in parts:
@@ -299,7 +304,9 @@ class Trainer:
         self._invalidate_caches(packs=False)
 
     def _run(self, which):
-        if (which + "_compute") in self._graphs:
+        if (which + "_full") in self._graphs:
+            self._graphs[which + "_full"].replay()
+        elif (which + "_compute") in self._graphs:
             self._graphs[which + "_compute"].replay()
             if self.grad_allreduce is not None:
                 root = 'Discriminator' if which == 'd' else 'Generator'
