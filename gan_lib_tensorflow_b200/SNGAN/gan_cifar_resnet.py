@@ -139,7 +139,20 @@ class AdamState:
 
 
 class Trainer:
-    """Builds the variables in the reference's graph-construction order and runs D / G training steps."""
+    """Builds the variables in the reference's graph-construction order and runs D / G training steps.
+
+    The model-specific pieces are class attributes so that the ImageNet script (same graph structure,
+    SNGAN/gan_imagNet_resnet.py:336-500) reuses the step logic: see gan_imagNet_resnet.Trainer."""
+
+    generator = staticmethod(lambda *a, **k: Generator(*a, **k))
+    discriminator = staticmethod(lambda *a, **k: Discriminator(*a, **k))
+    output_dim = OUTPUT_DIM          # flattened image size (CHW order on the input side)
+    image_hw = 1024                  # pixels per image
+    n_classes = 10                   # fake labels are uniform in [0, n_classes)
+    n_towers = N_TOWERS
+    gen_bs_multiple = GEN_BS_MULTIPLE
+    base_lr = LR
+    lr_schedule = staticmethod(lambda it: lr_decay(it))
 
     def __init__(self, batch_size: int = BATCH_SIZE, seed: int | None = 0, store=None, world_size: int = 1,
                  grad_allreduce=None, bn_sync: bool = False):
@@ -154,7 +167,7 @@ class Trainer:
                 raise ValueError("bn_sync needs the all-reduce callable (grad_allreduce)")
             self.store.bn_sync = (grad_allreduce, world_size)
         self.batch = batch_size
-        self.gen_batch = GEN_BS_MULTIPLE * batch_size
+        self.gen_batch = self.gen_bs_multiple * batch_size
         self.world_size = world_size
         self.grad_allreduce = grad_allreduce  # callable(flat_grads) -> None, sums over ranks (NCCL)
         dev = self.store.device
@@ -164,13 +177,13 @@ class Trainer:
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         # static step inputs (also the CUDA-graph placeholders)
-        self.real_int = torch.zeros(batch_size, OUTPUT_DIM, **i32)
+        self.real_int = torch.zeros(batch_size, self.output_dim, **i32)
         self.real_labels = torch.zeros(batch_size, **i32)
-        self.deq_noise = torch.zeros(batch_size, OUTPUT_DIM, **f32)
+        self.deq_noise = torch.zeros(batch_size, self.output_dim, **f32)
         self.z_d = torch.zeros(batch_size, 128, **f32)
         self.z_g = torch.zeros(self.gen_batch, 128, **f32)
         self.fake_labels = torch.zeros(self.gen_batch, **i32)
-        self.d_in = torch.zeros(2 * batch_size, OUTPUT_DIM, **f32)
+        self.d_in = torch.zeros(2 * batch_size, self.output_dim, **f32)
         self.d_labels = torch.zeros(2 * batch_size, **i32)
         self.d_loss = torch.zeros(1, **f32)
         self.g_loss = torch.zeros(1, **f32)
@@ -187,11 +200,12 @@ class Trainer:
         z = torch.zeros(2, 128, device=dev)
         lab = torch.zeros(2, dtype=torch.int32, device=dev)
         with st.building():
-            fake = Generator(2, lab, noise=z)
-            Generator(2, lab, noise=z, reuse=True)
-            Discriminator(fake, lab, update_collection="NO_OPS")
-            for _ in range(N_TOWERS):
-                Discriminator(Generator(2, lab, noise=z, reuse=True), lab, update_collection="NO_OPS", reuse=True)
+            fake = self.generator(2, lab, noise=z)
+            self.generator(2, lab, noise=z, reuse=True)
+            self.discriminator(fake, lab, update_collection="NO_OPS")
+            for _ in range(self.n_towers):
+                self.discriminator(self.generator(2, lab, noise=z, reuse=True), lab, update_collection="NO_OPS",
+                                   reuse=True)
         st.finalize()
 
     # ------------------------------------------------------------------------------------------ inputs
@@ -205,7 +219,7 @@ class Trainer:
         self.z_d.normal_()
         self.z_g.normal_()
         self.deq_noise.uniform_(0.0, 1.0 / 128)
-        self.fake_labels.copy_((torch.rand(self.gen_batch, device=self.store.device) * 10).to(torch.int32))
+        self.fake_labels.copy_((torch.rand(self.gen_batch, device=self.store.device) * self.n_classes).to(torch.int32))
 
     # ------------------------------------------------------------------------------------------ steps
     def _d_compute(self):
@@ -213,18 +227,22 @@ class Trainer:
         st = self.store
         b = self.batch
         st.zero_grad('Discriminator')
-        with st.stat_towers(N_TOWERS):
-            fake = Generator(b, self.real_labels, noise=self.z_d, reuse=True)  # no tape: var_list = disc_params
-        real = K.preprocess_real(self.real_int, self.deq_noise, b, 1024)
+        with st.stat_towers(self.n_towers):
+            fake = self.generator(b, self.real_labels, noise=self.z_d, reuse=True)  # no tape: var_list = disc_params
+        real = self._preprocess_real(b)
         self.d_in[:b].copy_(real)
         self.d_in[b:].copy_(fake.data)
         self.d_labels[:b].copy_(self.real_labels)
         self.d_labels[b:].copy_(self.real_labels)
         with st.gradient_tape() as tape, st.frozen_scopes('Generator'):
-            disc_all, _ = Discriminator(Var(self.d_in), self.d_labels, update_collection=None, reuse=True)
+            disc_all, _ = self.discriminator(Var(self.d_in), self.d_labels, update_collection=None, reuse=True)
             loss = F.gan_loss(disc_all, 'hinge_d', n_real=b)
             tape.backward(loss)
         self.d_loss.copy_(loss.data)
+
+    def _preprocess_real(self, b):
+        """int pixels -> [-1, 1) + dequantisation noise, CHW -> NHWC (gan_cifar_resnet.py:334-337)."""
+        return K.preprocess_real(self.real_int, self.deq_noise, b, self.image_hw)
 
     def _repack(self, root):
         """bf16 operand copies of the updated network, refreshed right behind its Adam step (so the compute graphs
@@ -243,9 +261,9 @@ class Trainer:
         st = self.store
         st.zero_grad('Generator')
         with st.gradient_tape() as tape, st.frozen_scopes('Discriminator'):
-            with st.stat_towers(N_TOWERS):
-                fake = Generator(self.gen_batch, self.fake_labels, noise=self.z_g, reuse=True)
-            disc_fake, _ = Discriminator(fake, self.fake_labels, update_collection="NO_OPS", reuse=True)
+            with st.stat_towers(self.n_towers):
+                fake = self.generator(self.gen_batch, self.fake_labels, noise=self.z_g, reuse=True)
+            disc_fake, _ = self.discriminator(fake, self.fake_labels, update_collection="NO_OPS", reuse=True)
             loss = F.gan_loss(disc_fake, 'gen')
             tape.backward(loss)
         self.g_loss.copy_(loss.data)
@@ -318,12 +336,12 @@ class Trainer:
             self._g_body()
 
     def d_step(self, iteration: int):
-        self.disc_opt.set_lr(LR * lr_decay(iteration))
+        self.disc_opt.set_lr(self.base_lr * self.lr_schedule(iteration))
         self._run('d')
         return self.d_loss
 
     def g_step(self, iteration: int):
-        self.gen_opt.set_lr(LR * lr_decay(iteration))
+        self.gen_opt.set_lr(self.base_lr * self.lr_schedule(iteration))
         self._run('g')
         return self.g_loss
 

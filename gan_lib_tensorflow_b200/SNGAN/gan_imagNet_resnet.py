@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 
 from .. import functional as F
+from .. import kernels as K
 from ..common import resnet_block as rb
 from ..common.ops import conv2d as conv2d_ops
 from ..common.ops import embedding as embedding_ops
@@ -102,3 +103,31 @@ def lr_decay(iteration: int) -> float:
     if not DECAY:
         return 1.0
     return 1.0 if iteration < 400000 else max(0.0, 1.0 - iteration / 450000.0)
+
+
+def _trainer_class():
+    from . import gan_cifar_resnet as cifar
+
+    class Trainer(cifar.Trainer):
+        """D / G training steps of gan_imagNet_resnet.py:336-526: the graph structure of the CIFAR script (two towers,
+        real + fake concatenated through D, hinge losses, Adam(2e-4, 0, 0.9), N_CRITIC = 5) around this module's
+        Generator / Discriminator; BATCH_SIZE = 32 per process (:40), 1000 classes, no CHW -> NHWC transpose (:275)."""
+        generator = staticmethod(lambda *a, **k: Generator(*a, **k))
+        discriminator = staticmethod(lambda *a, **k: Discriminator(*a, **k))
+        output_dim = OUTPUT_DIM
+        image_hw = 128 * 128
+        n_classes = VOCAB_SIZE
+        gen_bs_multiple = GEN_BS_MULTIPLE
+        base_lr = LR
+        lr_schedule = staticmethod(lambda it: lr_decay(it))
+
+        def __init__(self, batch_size: int = BATCH_SIZE, **kw):
+            super().__init__(batch_size=batch_size, **kw)
+
+        def _preprocess_real(self, b):
+            # the flat vector is already NHWC: dequantise element-wise (hw = 1 makes the kernel's transpose the identity)
+            return K.preprocess_real(self.real_int, self.deq_noise, b * self.image_hw, 1).reshape(b, self.output_dim)
+    return Trainer
+
+
+Trainer = _trainer_class()

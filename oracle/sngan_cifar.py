@@ -127,6 +127,13 @@ class SNGANCifar:
     """Graph + optimisers; build() mirrors the reference's graph-construction order so that the NumPy RNG
     stream is consumed identically (Appendix A of SURVEY.md)."""
 
+    # model-specific pieces (overridden by oracle.sngan_imagenet.SNGANImageNet: same graph structure)
+    G = staticmethod(lambda *a, **k: Generator(*a, **k))
+    D = staticmethod(lambda *a, **k: Discriminator(*a, **k))
+    preprocess = staticmethod(lambda real_int, deq_noise, dtype: preprocess_real(real_int, deq_noise, dtype))
+    lr = LR
+    decay = staticmethod(lambda it: lr_decay(it))
+
     def __init__(self, dtype=torch.float32, u_seed=2):
         self.g = tfshim.Graph(dtype=dtype, u_seed=u_seed)
         self.dtype = dtype
@@ -140,12 +147,11 @@ class SNGANCifar:
         lab = torch.zeros(2, dtype=torch.int64)
         self.g.draw_on_reuse = True
         with torch.no_grad():
-            fake = Generator(self.g, 2, lab, z)
-            Generator(self.g, 2, lab, z, reuse=True)
-            Discriminator(self.g, fake, lab, update_collection=ops.NO_OPS)
+            fake = self.G(self.g, 2, lab, z)
+            self.G(self.g, 2, lab, z, reuse=True)
+            self.D(self.g, fake, lab, update_collection=ops.NO_OPS)
             for _ in range(N_TOWERS):  # G-step towers (gan_cifar_resnet.py:464-482): G and D draw-and-discard
-                Discriminator(self.g, Generator(self.g, 2, lab, z, reuse=True), lab, update_collection=ops.NO_OPS,
-                              reuse=True)
+                self.D(self.g, self.G(self.g, 2, lab, z, reuse=True), lab, update_collection=ops.NO_OPS, reuse=True)
         self.g.draw_on_reuse = False
         self.built = True
 
@@ -154,13 +160,13 @@ class SNGANCifar:
         """gan_cifar_resnet.py:322-381 with one physical device (two towers of BATCH/2)."""
         g = self.g
         labels_splits = torch.chunk(real_labels, N_TOWERS)
-        fake_splits = [Generator(g, BATCH_SIZE // N_TOWERS, labels_splits[i], noises[i], reuse=i > 0)
+        fake_splits = [self.G(g, real_int.shape[0] // N_TOWERS, labels_splits[i], noises[i], reuse=i > 0)
                        for i in range(N_TOWERS)]
-        all_real = preprocess_real(real_int, deq_noise, self.dtype)
+        all_real = self.preprocess(real_int, deq_noise, self.dtype)
         real_splits = torch.chunk(all_real, N_TOWERS)
         real_and_fake = torch.cat([real_splits[0], real_splits[1], fake_splits[0], fake_splits[1]], dim=0)
         labels = torch.cat([labels_splits[0], labels_splits[1], labels_splits[0], labels_splits[1]], dim=0)
-        disc_all, _ = Discriminator(g, real_and_fake, labels, update_collection=update_collection, reuse=True)
+        disc_all, _ = self.D(g, real_and_fake, labels, update_collection=update_collection, reuse=True)
         n_real = real_int.shape[0]
         disc_real, disc_fake = disc_all[:n_real], disc_all[n_real:]
         cost = torch.relu(1.0 - disc_real).mean() + torch.relu(1.0 + disc_fake).mean()   # :376-378
@@ -172,8 +178,8 @@ class SNGANCifar:
         costs = []
         for i in range(N_TOWERS):
             n_samples = noises[i].shape[0]
-            fake = Generator(g, n_samples, fake_labels[i], noises[i], reuse=True)
-            disc_fake, _ = Discriminator(g, fake, fake_labels[i], update_collection=ops.NO_OPS, reuse=True)
+            fake = self.G(g, n_samples, fake_labels[i], noises[i], reuse=True)
+            disc_fake, _ = self.D(g, fake, fake_labels[i], update_collection=ops.NO_OPS, reuse=True)
             costs.append(-disc_fake.mean())
         return sum(costs) / N_TOWERS
 
@@ -192,12 +198,12 @@ class SNGANCifar:
 
     def disc_train_op(self, iteration, real_int, real_labels, noises, deq_noise):
         cost, params, grads = self.disc_grads(real_int, real_labels, noises, deq_noise, update_collection=None)
-        self.disc_opt.apply(params, grads, LR * lr_decay(iteration))
+        self.disc_opt.apply(params, grads, self.lr * self.decay(iteration))
         return cost
 
     def gen_train_op(self, iteration, noises, fake_labels):
         cost, params, grads = self.gen_grads(noises, fake_labels)
-        self.gen_opt.apply(params, grads, LR * lr_decay(iteration))
+        self.gen_opt.apply(params, grads, self.lr * self.decay(iteration))
         return cost
 
 

@@ -76,3 +76,31 @@ def Discriminator(g, inputs, labels, update_collection=None, reuse=False):
         output = rb.nonlinearity(output).mean(dim=(1, 2))
         out = ops.Linear(g, output, DIM_D * 8, 1, "D.Output", spectral_normed=True, update_collection=update_collection)
         return out.reshape(-1), None
+
+
+def preprocess_real(real_int, deq_noise, dtype):
+    """gan_imagNet_resnet.py:354-356: int [B, 49152] -> float in [-1, 1) + U(0, 1/128); NO transpose -- the script
+    reshapes the flat vector straight to [-1, 128, 128, 3] (:275)."""
+    return 2 * ((real_int.to(dtype) / 256.0) - 0.5) + deq_noise
+
+
+def lr_decay(iteration):
+    """gan_imagNet_resnet.py:473-476"""
+    return 1.0 if iteration < 400000 else max(0.0, 1.0 - iteration / 450000.0)
+
+
+def _trainer_class():
+    from . import sngan_cifar
+
+    class SNGANImageNet(sngan_cifar.SNGANCifar):
+        """Losses / train ops of gan_imagNet_resnet.py:336-500: the same two-tower structure as the CIFAR script
+        (real + fake concatenated through D, hinge losses :376-380 / :497-500, Adam(2e-4, 0, 0.9) :521-526)."""
+        G = staticmethod(lambda *a, **k: Generator(*a, **k))
+        D = staticmethod(lambda *a, **k: Discriminator(*a, **k))
+        preprocess = staticmethod(preprocess_real)
+        lr = 0.0002
+        decay = staticmethod(lr_decay)
+    return SNGANImageNet
+
+
+SNGANImageNet = _trainer_class()

@@ -217,3 +217,70 @@ def test_loss_trajectory_tracks_the_oracle():
         band = 0.02 + 0.01 * s
         assert abs(p[0] - o[0]) <= band and abs(p[1] - o[1]) <= band, (s, p, o)
     assert prod[-1][0] < prod[0][0]       # the critic learns on both sides
+
+
+def test_imagenet_training_steps_match_the_oracle(monkeypatch):
+    """SNGAN ImageNet-128 (config 3): one critic step and one generator step of gan_imagNet_resnet.py:336-526 (two
+    towers, 1000-class conditional BN, label map concatenated at 16x16, hinge losses, no CHW->NHWC transpose) through
+    the shared Trainer, at width 32 and batch 4, against the oracle's restatement of the same graph."""
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200.SNGAN import gan_imagNet_resnet as P
+    from oracle import ops as O_ops
+    from oracle import sngan_imagenet as OI
+
+    batch, dim = 4, 32
+    for mod in (P, OI):
+        monkeypatch.setattr(mod, "DIM_G", dim)
+        monkeypatch.setattr(mod, "DIM_D", dim)
+    rs = np.random.RandomState(7)
+    data = rs.randint(0, 256, size=(batch, 49152)).astype("int32")
+    labels = rs.randint(0, 1000, size=batch).astype("int32")
+    z_d = rs.standard_normal((batch, 128)).astype("float32")
+    deq = rs.uniform(0, 1 / 128, size=(batch, 49152)).astype("float32")
+    z_g = rs.standard_normal((2 * batch, 128)).astype("float32")
+    fl = rs.randint(0, 1000, size=2 * batch).astype("int32")
+    # ---- product
+    store = framework.reset_default_graph("cuda", u_seed=2)
+    tr = P.Trainer(batch_size=batch, seed=0)
+    tr.set_real_batch(data, labels)
+    tr.z_d.copy_(torch.from_numpy(z_d)); tr.deq_noise.copy_(torch.from_numpy(deq))
+    tr.z_g.copy_(torch.from_numpy(z_g)); tr.fake_labels.copy_(torch.from_numpy(fl))
+    tr.disc_opt.set_lr(0.0); tr.gen_opt.set_lr(0.0)
+    tr._d_body()
+    d_loss = tr.d_loss.item()
+    d_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("Discriminator")}
+    tr._g_body()
+    g_loss = tr.g_loss.item()
+    g_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("Generator")}
+    torch.cuda.synchronize()
+    framework.set_store(None)
+    # ---- oracles
+    refs = {}
+    h = batch // 2
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        try:
+            np.random.seed(0)
+            om = OI.SNGANImageNet(dtype=torch.float32, u_seed=2)
+            om.build()
+            lab = torch.from_numpy(labels).long()
+            dc, dp, dg = om.disc_grads(torch.from_numpy(data), lab, [torch.from_numpy(z_d[:h]), torch.from_numpy(z_d[h:])],
+                                       torch.from_numpy(deq), None)
+            gc, gp, gg = om.gen_grads([torch.from_numpy(z_g[:batch]), torch.from_numpy(z_g[batch:])],
+                                      [torch.from_numpy(fl[:batch]).long(), torch.from_numpy(fl[batch:]).long()])
+            refs[mode] = dict(d=dc.item(), g=gc.item(),
+                              dg={n: t.numpy() for (n, _), t in zip(dp, dg) if t is not None},
+                              gg={n: t.numpy() for (n, _), t in zip(gp, gg) if t is not None})
+        finally:
+            O_ops.BF16_OPERANDS = False
+    assert set(d_grads) == set(refs[False]["dg"]) and set(g_grads) == set(refs[False]["gg"])
+    assert abs(d_loss - refs[True]["d"]) < 2e-3 and abs(d_loss - refs[False]["d"]) < 1e-2
+    assert abs(g_loss - refs[True]["g"]) < 2e-3 and abs(g_loss - refs[False]["g"]) < 1e-2
+    # measured band (see tests/test_gpu_wide.py::check_band): as close to fp32 as the bf16-operand oracle is
+    for got, key in ((d_grads, "dg"), (g_grads, "gg")):
+        gmax = max(np.linalg.norm(t) for t in refs[False][key].values())
+        for name, f32 in refs[False][key].items():
+            if np.linalg.norm(f32) < 5e-2 * gmax:
+                continue
+            e_prod, e_orc = rel(got[name], f32), rel(refs[True][key][name], f32)
+            assert e_prod <= 2.0 * e_orc + 5e-3, (name, e_prod, e_orc)
