@@ -1,0 +1,74 @@
+"""Training steps of PGGAN/train.py:83-136, 182-190 on the B200 layer ops: hinge losses, two Adam(1e-4, beta1 = 0,
+beta2 = 0.9) optimisers, per iteration one generator step followed by n_dis critic steps, alpha = step / max_iter.
+Real images arrive as NHWC float tensors already resized to the stage's resolution (tf.image.resize_images,
+train.py:89-93, is an input-pipeline step outside the hot path)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import functional as F
+from ..framework import Var, get_store
+from ..training import TwoPlayer
+from .model_nvidia import PGGAN
+
+LR = 0.0001      # train.py:125, 128
+N_DIS = 5        # --n_dis
+Z_DIM = 512      # --z_dim
+
+
+class Trainer:
+    def __init__(self, block_count: int, trans: bool, inputs_norm: bool = False, batch_size: int = 16,
+                 z_dim: int = Z_DIM, max_iter: int = 100000, seed: int | None = 0, world_size: int = 1,
+                 grad_allreduce=None):
+        self.store = get_store()
+        self.model = PGGAN(block_count=block_count, trans=trans, inputs_norm=inputs_norm)
+        self.batch, self.z_dim, self.max_iter = batch_size, z_dim, max_iter
+        self.size = 4 * 2 ** block_count
+        if seed is not None:
+            np.random.seed(seed)
+        dev = self.store.device
+        # graph construction order of train.py:103-107: D(real), G, D(fake, reuse)
+        with self.store.building():
+            real0 = torch.zeros(2, self.size, self.size, 3, device=dev)
+            self.model.get_discriminator(real0, 0.0, update_collection="NO_OPS")
+            fake0 = self.model.get_generator(torch.zeros(2, z_dim, device=dev), 0.0)
+            self.model.get_discriminator(fake0, 0.0, update_collection="NO_OPS", reuse=True)
+        self.players = TwoPlayer("d_net", "g_net", beta1=0.0, beta2=0.9, world_size=world_size,
+                                 grad_allreduce=grad_allreduce)
+        self.players.finalize()
+
+    def alpha(self, step: int) -> float:
+        return (step * 1.0) / self.max_iter          # train.py:184
+
+    # ------------------------------------------------------------------------------------------ losses
+    def d_loss(self, real, z, alpha):
+        """train.py:103-113: D(real) assigns u (update_collection=None), D(G(z)) runs with NO_OPS; G gets no gradient."""
+        m = self.model
+        fake = m.get_generator(z, alpha, reuse=True)                      # no tape entry survives: g_net is frozen
+        disc_real = m.get_discriminator(Var(real), alpha, update_collection=None, reuse=True)
+        disc_fake = m.get_discriminator(Var(fake.data), alpha, update_collection="NO_OPS", reuse=True)
+        return F.gan_loss(F.concat_rows(disc_real, disc_fake), 'd', n_real=real.shape[0], loss_type="HINGE")
+
+    def g_loss(self, z, alpha):
+        m = self.model
+        fake = m.get_generator(z, alpha, reuse=True)
+        disc_fake = m.get_discriminator(fake, alpha, update_collection="NO_OPS", reuse=True)
+        return F.gan_loss(disc_fake, 'g', loss_type="HINGE")
+
+    # ------------------------------------------------------------------------------------------ steps
+    def d_step(self, real, z, alpha):
+        return self.players.step("d", lambda: self.d_loss(real, z, alpha), LR)
+
+    def g_step(self, z, alpha):
+        return self.players.step("g", lambda: self.g_loss(z, alpha), LR)
+
+    def train_iteration(self, step: int, batches, n_dis: int = N_DIS):
+        """train.py:182-190.  `batches` yields NHWC float real images [batch, size, size, 3]."""
+        a = self.alpha(step)
+        dev = self.store.device
+        g = self.g_step(torch.randn(self.batch, self.z_dim, device=dev), a)
+        d = None
+        for _ in range(n_dis):
+            d = self.d_step(next(batches), torch.randn(self.batch, self.z_dim, device=dev), a)
+        return d, g

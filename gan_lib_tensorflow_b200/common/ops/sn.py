@@ -58,17 +58,14 @@ def spectral_normed_weight(W, u=None, num_iters=1, update_collection=None, with_
                                    initializer=lambda s: truncated_normal(s, store.u_rng))
         elif not isinstance(u, Variable):
             raise TypeError("u must be a framework.Variable (persistent state)")
-    group = store.sn_group(W.root)
-    entry = group.entry(W, u)
+    entry = store.sn_acquire(W, u, assign=update_collection is None)
     if update_collection is None:
         global _warned
         if not _warned:
             warnings.warn('Setting update_collection to None will make u being updated every W execution. This '
                           'maybe undesirable. Please consider using a update collection instead.', stacklevel=2)
             _warned = True
-        group.acquire(entry, assign=True)
     else:
-        group.acquire(entry, assign=False)
         if update_collection != NO_OPS:
             _collections.setdefault(update_collection, []).append((u, entry.u_out.clone().reshape(u.data.shape)))
     w_bar = SNWeight(W, entry, entry.sigma)

@@ -164,7 +164,13 @@ class Tape:
         self.join()
         self.nodes.clear()
         for root, entries in self.pending_sn.items():
-            self.store.sn_groups[root].backward(entries)
+            # one launch sequence per evaluation of the network: a weight evaluated twice on this tape (D(real) and
+            # D(fake) as separate calls) has one state per evaluation, and both add into the same dW
+            by_group = OrderedDict()
+            for e in entries:
+                by_group.setdefault(id(e.group), (e.group, []))[1].append(e)
+            for group, es in by_group.values():
+                group.backward(es)
         self.pending_sn.clear()
 
 
@@ -213,6 +219,7 @@ class SNEntry:
         self.g = torch.zeros(self.k, self.c, **f32)  # dL/d(W/sigma), written by the layer's wgrad
         self.g_written = False
         self.fresh = False
+        self.group = None   # the SNGroup that owns this evaluation state
 
     @property
     def inv_sigma(self):
@@ -233,11 +240,13 @@ class SNGroup:
         self.table_ptrs = None
         self.valid_for = None
         self.fresh_for = None
+        self.used_token = None   # tape on which the current evaluation has consumers (see VariableStore.sn_group)
 
     def entry(self, w: Variable, u: Variable) -> SNEntry:
         e = self.entries.get(w.key)
         if e is None:
             e = SNEntry(w, u)
+            e.group = self
             self.entries[w.key] = e
             self.table = None
             self.valid_for = None
@@ -267,6 +276,13 @@ class SNGroup:
             self.table, self.blocks, self.max_c = self._build_table(entries)
             self.table_ptrs = self._ptrs()
         K.sn_power_iter(self.table, len(entries), self.blocks, self.max_c, assign)
+
+    def needs_new_evaluation(self, e: SNEntry, assign: bool) -> bool:
+        """True when acquire(e, assign) would run the power iteration again (and overwrite sigma / v / u_used)."""
+        ver = self.store.version(self.root)
+        if assign:
+            return not (e.fresh and self.fresh_for == ver)
+        return self.valid_for != (ver, self.store.u_version(self.root))
 
     def acquire(self, e: SNEntry, assign: bool) -> None:
         """Makes e.scal / e.v / e.u_used current for this evaluation of the network.
@@ -398,6 +414,11 @@ class VariableStore:
         self._versions: dict[str, int] = {}
         self._u_versions: dict[str, int] = {}
         self.sn_groups: dict[str, SNGroup] = {}
+        # further evaluations of the same network on ONE tape (PGGAN / Pix2Pix call D on real and fake images
+        # separately, with different u): every evaluation keeps its own sigma / v / u' until the backward pass
+        self.sn_shadow: dict[str, list] = {}
+        self._sn_gen: dict[str, int] = {}
+        self.tape_token = 0
         self.pack_groups: dict[str, PackGroup] = {}
         self.flat: dict[str, FlatGroup] = {}
         self.u_rng = np.random.RandomState(u_seed)
@@ -499,11 +520,42 @@ class VariableStore:
             self._consts[value] = t
         return t
 
-    def sn_group(self, root) -> SNGroup:
+    def sn_group(self, root, gen: int = 0) -> SNGroup:
         g = self.sn_groups.get(root)
         if g is None:
             g = self.sn_groups[root] = SNGroup(self, root)
-        return g
+        if gen == 0:
+            return g
+        shadows = self.sn_shadow.setdefault(root, [])
+        while len(shadows) < gen:
+            sh = SNGroup(self, root)
+            for e in g.entries.values():     # same layers, separate evaluation state
+                sh.entry(e.w, e.u)
+            shadows.append(sh)
+        sh = shadows[gen - 1]
+        for e in g.entries.values():
+            if e.w.key not in sh.entries:
+                sh.entry(e.w, e.u)
+        return sh
+
+    def sn_acquire(self, w: Variable, u: Variable, assign: bool) -> SNEntry:
+        """Evaluation state of W / sigma for the layer call being built.  While a tape is recording, a network whose
+        current state already has consumers on that tape and would be re-evaluated (changed u, or another
+        update_collection=None pass) moves on to a fresh state set instead of overwriting the one in use."""
+        root = w.root
+        gen = self._sn_gen.get(root, 0) if self.tape is not None else 0
+        group = self.sn_group(root, gen)
+        entry = group.entry(w, u)
+        if (self.tape is not None and group.used_token == self.tape_token
+                and group.needs_new_evaluation(entry, assign)):
+            gen += 1
+            self._sn_gen[root] = gen
+            group = self.sn_group(root, gen)
+            entry = group.entry(w, u)
+        group.acquire(entry, assign)
+        if self.tape is not None:
+            group.used_token = self.tape_token
+        return entry
 
     def pack_group(self, root) -> PackGroup:
         g = self.pack_groups.get(root)
@@ -515,6 +567,8 @@ class VariableStore:
     def gradient_tape(self):
         prev = self.tape
         self.tape = Tape(self)
+        self.tape_token += 1
+        self._sn_gen = {}
         try:
             yield self.tape
         finally:

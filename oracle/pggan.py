@@ -126,3 +126,35 @@ class PGGAN:
             output = torch.mean(output, dim=(1, 2))                                              # :234
             logits = ops.Linear(g, output, output.shape[-1], 1, "D.Output")                      # :235
             return logits.reshape(-1)                                                            # :236
+
+
+class PGGANLosses:
+    """Losses of PGGAN/train.py:103-113 (hinge) over the model above: returns (cost, params, grads) like the SNGAN
+    oracle; D(real) runs with update_collection=None, the fake branch with NO_OPS."""
+
+    def __init__(self, g, block_count, trans, inputs_norm, size, z_dim=512):
+        self.g, self.model = g, PGGAN(block_count, trans, inputs_norm)
+        with torch.no_grad():   # graph construction order: D(real), G, D(fake, reuse)
+            g.draw_on_reuse = True
+            self.model.get_discriminator(g, torch.zeros(2, size, size, 3), 0.0, update_collection=ops.NO_OPS)
+            f = self.model.get_generator(g, torch.zeros(2, z_dim), 0.0)
+            self.model.get_discriminator(g, f, 0.0, update_collection=ops.NO_OPS, reuse=True)
+            g.draw_on_reuse = False
+
+    def d_grads(self, real, z, alpha):
+        m, g = self.model, self.g
+        with torch.no_grad():
+            fake = m.get_generator(g, z, alpha, reuse=True)
+        disc_real = m.get_discriminator(g, real, alpha, update_collection=None, reuse=True)
+        disc_fake = m.get_discriminator(g, fake, alpha, update_collection=ops.NO_OPS, reuse=True)
+        cost = torch.relu(1.0 - disc_real).mean() + torch.relu(1.0 + disc_fake).mean()      # train.py:110-112
+        params = g.trainable_variables("d_net")
+        return cost.detach(), params, torch.autograd.grad(cost, [p for _, p in params], allow_unused=True)
+
+    def g_grads(self, z, alpha):
+        m, g = self.model, self.g
+        disc_fake = m.get_discriminator(g, m.get_generator(g, z, alpha, reuse=True), alpha,
+                                        update_collection=ops.NO_OPS, reuse=True)
+        cost = -disc_fake.mean()                                                              # train.py:113
+        params = g.trainable_variables("g_net")
+        return cost.detach(), params, torch.autograd.grad(cost, [p for _, p in params], allow_unused=True)

@@ -225,3 +225,63 @@ def test_first_block_lrelu_unnormalised(env):
         lambda xv: P.OptimizedResBlockDisc1(xv, 128, activation_fn="lrelu"),
         lambda g, xt: ORB.OptimizedResBlockDisc1(g, xt, 128, activation_fn="lrelu"), x)
     check(prod, refs, tol_impl=TOL_BLOCK_IMPL, tol_fp32=TOL_BLOCK_FP32, tag="first block lrelu")
+
+
+def _band(got, ref_b16, ref_f32, factor=2.0, floor=5e-3):
+    gmax = max(np.linalg.norm(t) for t in ref_f32.values())
+    for name, f32 in ref_f32.items():
+        if np.linalg.norm(f32) < 5e-2 * gmax:
+            continue
+        e_prod, e_orc = rel(got[name], f32), rel(ref_b16[name], f32)
+        assert e_prod <= factor * e_orc + floor, (name, e_prod, e_orc)
+
+
+@pytest.mark.parametrize("bc,trans", [(1, False), (2, True)])
+def test_pggan_training_steps(env, bc, trans):
+    """PGGAN/train.py:103-136: critic and generator gradients of the hinge losses (D(real) with update_collection=None,
+    fake branch NO_OPS, alpha fade-in) through PGGAN.train.Trainer vs the oracle; then one Adam step moves both."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+    from oracle import ops as O_ops
+    from oracle import pggan as OP
+
+    n, alpha = 4, 0.4
+    size = 4 * 2 ** bc
+    rs = np.random.RandomState(91)
+    real = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    z = rs.standard_normal((n, 512)).astype("float32")
+    tr = PT.Trainer(bc, trans, inputs_norm=True, batch_size=n, seed=0)
+    real_d, z_d = torch.from_numpy(real).cuda(), torch.from_numpy(z).cuda()
+    dl = tr.players.gradients("d", lambda: tr.d_loss(real_d, z_d, alpha))
+    d_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("d_net")}
+    u_after = {k: v.data.cpu().numpy().copy() for k, v in store.vars.items() if k.endswith("/u")}
+    gl = tr.players.gradients("g", lambda: tr.g_loss(z_d, alpha))
+    g_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("g_net")}
+    d_loss, g_loss = float(dl.data.item()), float(gl.data.item())
+    refs = {}
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        try:
+            np.random.seed(0)
+            g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+            ol = OP.PGGANLosses(g, bc, trans, True, size)
+            dc, dp, dg = ol.d_grads(torch.from_numpy(real), torch.from_numpy(z), alpha)
+            u_ref = {k_: v.detach().numpy().copy() for k_, v in g.vars.items() if k_.endswith("/u")}
+            gc, gp, gg = ol.g_grads(torch.from_numpy(z), alpha)
+            refs[mode] = dict(d=dc.item(), g=gc.item(), u=u_ref,
+                              dg={nm: t.numpy() for (nm, _), t in zip(dp, dg) if t is not None},
+                              gg={nm: t.numpy() for (nm, _), t in zip(gp, gg) if t is not None})
+        finally:
+            O_ops.BF16_OPERANDS = False
+    assert set(d_grads) == set(refs[False]["dg"]) and set(g_grads) == set(refs[False]["gg"])
+    assert abs(d_loss - refs[True]["d"]) < 2e-3 and abs(g_loss - refs[True]["g"]) < 2e-3
+    for name, u in refs[False]["u"].items():          # u <- u' by the D(real) pass only
+        assert rel(u_after[name], u) < 1e-4, name
+    _band(d_grads, refs[True]["dg"], refs[False]["dg"])
+    _band(g_grads, refs[True]["gg"], refs[False]["gg"])
+    # one reference iteration (G step, then D steps) runs and moves the parameters
+    before = store.flat["g_net"].params.clone()
+    d, g_ = tr.train_iteration(1, iter([real_d] * 2), n_dis=2)
+    torch.cuda.synchronize()
+    assert np.isfinite(d.data.item()) and np.isfinite(g_.data.item())
+    assert not torch.equal(before, store.flat["g_net"].params)

@@ -191,6 +191,41 @@ def test_cross_gpu_batch_statistics_call_sequence(host):
     assert len(reduced) == n_before
 
 
+def test_two_evaluations_of_one_network_on_a_tape_keep_separate_sn_state(host):
+    """PGGAN / Pix2Pix call D on real and on fake images as separate layer calls inside one gradient computation
+    (PGGAN/train.py:103-107): D(real) assigns u, D(fake) then sees the new u, so the two calls have different sigma.
+    Each evaluation must keep its own sigma / v / u' / G buffers until the backward pass; outside a tape, and for a
+    repeated evaluation with unchanged u, the state is shared (one grouped launch per weight version)."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.common.ops import conv2d
+    from gan_lib_tensorflow_b200.common.ops.sn import spectral_normed_weight
+    from gan_lib_tensorflow_b200.framework import Var
+
+    x = Var(torch.zeros(2, 8, 8, 16), requires_grad=True)
+
+    def layer(mode, reuse):
+        with store.variable_scope("d_net", reuse=reuse):
+            return conv2d.Conv2D(x, 16, 16, 3, 1, "D.Conv", spectral_normed=True, update_collection=mode)
+
+    layer("NO_OPS", False)                                    # graph construction, no tape
+    w = store.vars["d_net/D.Conv/Filters"]
+    u = store.vars["d_net/D.Conv/filters/spectral_norm/u"]
+    base = store.sn_groups["d_net"].entries[w.key]
+    n0 = rec.names().count("ganb_sn_power_iter")
+    with store.gradient_tape() as tape:
+        with store.variable_scope("d_net", reuse=True), store.variable_scope("D.Conv"), store.variable_scope("filters"):
+            e_real = spectral_normed_weight(w, update_collection=None).entry           # assigns u
+            e_fake = spectral_normed_weight(w, update_collection="NO_OPS").entry       # re-evaluated from the new u
+            e_again = spectral_normed_weight(w, update_collection="NO_OPS").entry      # unchanged u: shared
+    assert e_real is base and e_fake is not base and e_again is e_fake
+    assert e_fake.g.data_ptr() != e_real.g.data_ptr() and e_fake.scal.data_ptr() != e_real.scal.data_ptr()
+    assert rec.names().count("ganb_sn_power_iter") == n0 + 2
+    assert e_fake.u is u and e_fake.group is store.sn_shadow["d_net"][0]
+    with store.gradient_tape():                                 # a new tape starts from the shared state again
+        with store.variable_scope("d_net", reuse=True), store.variable_scope("D.Conv"), store.variable_scope("filters"):
+            assert spectral_normed_weight(w, update_collection="NO_OPS").entry is base
+
+
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
     store, _ = host
     from gan_lib_tensorflow_b200.common import resnet_block
