@@ -1,0 +1,97 @@
+"""Training steps of Pix2Pix/train.py:447-539, 694-729 on the B200 layer ops (config 4 of BASELINE.json): U-Net
+generator, spectrally-normalised PatchGAN, lib.misc.get_loss(loss_type) for both players, gen_loss = gan_weight *
+GAN + l1_weight * L1, two Adam(beta1 = 0, beta2 = 0.9) optimisers with a linear learning-rate decay driven by the
+generator's global step; per iteration n_dis critic steps on the batch, then one generator step.
+
+Every discriminator call uses update_collection=None in the reference (train.py:459-478): u is re-assigned by D(real),
+by D(fake) and again by D(fake) of the generator step, so each call sees a different sigma (framework.sn_acquire keeps
+one spectral-norm state per evaluation).  The WGAN-GP penalty (train.py:489-507) is not built."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import functional as F
+from ..framework import Var, get_store
+from ..training import TwoPlayer
+from . import networks
+
+
+class Pix2Pix(object):
+    """Pix2Pix/model.py:15-100 for the unet_g / unet_d topology (the one config 4 names)."""
+
+    def get_generator(self, inputs, outputs_channels, ngf=64, padding='SAME', reuse=False, keep_masks=None, **_kw):
+        with get_store().variable_scope('g_net', reuse=reuse):
+            return networks.unet_g(inputs, outputs_channels, ngf, padding=padding, keep_masks=keep_masks)
+
+    def get_discriminator(self, inputs, targets, ndf=64, spectral_normed=True, update_collection=None,
+                          padding='VALID', reuse=False, **_kw):
+        with get_store().variable_scope('d_net', reuse=reuse):
+            return networks.unet_d(inputs, targets, ndf, spectral_normed, update_collection, padding=padding)
+
+
+class Trainer:
+    def __init__(self, ngf: int = 64, ndf: int = 64, size: int = 256, loss_type: str = 'HINGE',
+                 gan_weight: float = 1.0, l1_weight: float = 100.0, initial_lr: float = 0.0002, end_lr: float = 0.0001,
+                 beta1: float = 0.0, beta2: float = 0.9, max_steps: int = 23600, seed: int | None = 0,
+                 world_size: int = 1, grad_allreduce=None):
+        if loss_type == 'WGAN-GP':
+            raise NotImplementedError('the gradient penalty of Pix2Pix/train.py:489-507 is not built (SURVEY 8(f))')
+        self.store = get_store()
+        self.model = Pix2Pix()
+        self.ngf, self.ndf, self.loss_type = ngf, ndf, loss_type
+        self.gan_weight, self.l1_weight = gan_weight, l1_weight
+        self.initial_lr, self.end_lr, self.max_steps = initial_lr, end_lr, max_steps
+        self.global_step = 0
+        if seed is not None:
+            np.random.seed(seed)
+        dev = self.store.device
+        with self.store.building():                      # create_model(): G, D(real), D(fake, reuse)
+            x0 = torch.zeros(1, size, size, 3, device=dev)
+            out0 = self.model.get_generator(x0, 3, ngf=ngf)
+            self.model.get_discriminator(x0, x0, ndf=ndf, update_collection="NO_OPS")
+            self.model.get_discriminator(x0, out0, ndf=ndf, update_collection="NO_OPS", reuse=True)
+        self.players = TwoPlayer("d_net", "g_net", beta1=beta1, beta2=beta2, world_size=world_size,
+                                 grad_allreduce=grad_allreduce)
+        self.players.finalize()
+
+    def learning_rate(self) -> float:
+        """tf.train.polynomial_decay(initial_lr, global_step, max_steps, end_lr), power 1 (train.py:521-526)."""
+        t = min(self.global_step, self.max_steps) / float(self.max_steps)
+        return (self.initial_lr - self.end_lr) * (1.0 - t) + self.end_lr
+
+    # ------------------------------------------------------------------------------------------ losses
+    def d_loss(self, inputs, targets, keep_masks=None):
+        m = self.model
+        outputs = m.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=keep_masks)   # g_net is frozen
+        predict_real = m.get_discriminator(inputs, targets, ndf=self.ndf, update_collection=None, reuse=True)
+        predict_fake = m.get_discriminator(inputs, Var(outputs.data), ndf=self.ndf, update_collection=None, reuse=True)
+        pr, pf = F.reshape(predict_real, (-1,)), F.reshape(predict_fake, (-1,))
+        return F.gan_loss(F.concat_rows(pr, pf), 'd', n_real=pr.shape[0], loss_type=self.loss_type)
+
+    def g_loss(self, inputs, targets, keep_masks=None):
+        m = self.model
+        outputs = m.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=keep_masks)
+        predict_fake = m.get_discriminator(inputs, outputs, ndf=self.ndf, update_collection=None, reuse=True)
+        gen_loss_gan = F.gan_loss(F.reshape(predict_fake, (-1,)), 'g', scale=self.gan_weight, loss_type=self.loss_type)
+        gen_loss_l1 = F.l1_loss(targets, outputs, scale=self.l1_weight)
+        self.last = {'gen_loss_GAN_weighted': gen_loss_gan.data, 'gen_loss_L1_weighted': gen_loss_l1.data}
+        return F.add_scalars(gen_loss_gan, gen_loss_l1)
+
+    # ------------------------------------------------------------------------------------------ steps
+    def d_step(self, inputs, targets, keep_masks=None):
+        return self.players.step("d", lambda: self.d_loss(inputs, targets, keep_masks), self.learning_rate())
+
+    def g_step(self, inputs, targets, keep_masks=None):
+        loss = self.players.step("g", lambda: self.g_loss(inputs, targets, keep_masks), self.learning_rate())
+        self.global_step += 1                             # gen_optim.apply_gradients(..., global_step=global_step)
+        return loss
+
+    def train_iteration(self, inputs, targets, n_dis: int = 5, mask_fn=None):
+        """train.py:703-729: n_dis critic steps on the batch, then the generator step.  mask_fn() -> three dropout
+        keep masks (fresh ones for every session.run in the reference)."""
+        d = None
+        for _ in range(n_dis):
+            d = self.d_step(inputs, targets, mask_fn() if mask_fn else None)
+        g = self.g_step(inputs, targets, mask_fn() if mask_fn else None)
+        return d, g

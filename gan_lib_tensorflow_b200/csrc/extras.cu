@@ -340,3 +340,63 @@ extern "C" int ganb_copy_channels(const void* src, int src_dtype, int src_cstrid
   GANB_CHECK_LAUNCH("copy_channels_kernel");
   return 0;
 }
+
+namespace ganb {
+// L1 reconstruction loss of Pix2Pix (Pix2Pix/train.py:511: tf.reduce_mean(tf.abs(targets - outputs))):
+// stage 1 writes d(loss)/d(outputs) = scale * sign(outputs - targets) / count and one partial sum per block,
+// stage 2 adds the partials in block order (deterministic).
+__global__ void __launch_bounds__(256)
+l1_loss_partial_kernel(const float* __restrict__ targets, const float* __restrict__ outputs, int64_t count, float gscale,
+                       float* __restrict__ dout, float* __restrict__ partial) {
+  pdl_wait();
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < count; i += gridDim.x * 256LL) {
+    const float d = outputs[i] - targets[i];
+    acc += fabsf(d);
+    dout[i] = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f);
+  }
+  __shared__ float sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256)
+l1_loss_finish_kernel(const float* __restrict__ partial, int blocks, float scale_over_count, int accumulate,
+                      float* __restrict__ loss_out) {
+  pdl_wait();
+  __shared__ float sh[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < blocks; i += 256) acc += partial[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (accumulate ? loss_out[0] : 0.f) + sh[0] * scale_over_count;
+}
+}  // namespace ganb
+
+extern "C" int64_t ganb_l1_loss_workspace(int64_t count) {
+  (void)count;
+  return 1024 * 4;
+}
+
+extern "C" int ganb_l1_loss(const float* targets, const float* outputs, int64_t count, float scale, int accumulate,
+                            float* loss_out, float* doutputs, void* workspace, void* stream) {
+  if (!targets || !outputs || !loss_out || !doutputs || !workspace || count <= 0)
+    return fail(GANB_E_BADARG, "l1_loss: bad arguments");
+  int blocks = egrid(count, 256);
+  if (blocks > 1024) blocks = 1024;
+  launch_k(l1_loss_partial_kernel, blocks, 256, 0, STREAM, targets, outputs, count, scale / static_cast<float>(count),
+           doutputs, static_cast<float*>(workspace));
+  GANB_CHECK_LAUNCH("l1_loss_partial_kernel");
+  launch_k(l1_loss_finish_kernel, 1, 256, 0, STREAM, static_cast<const float*>(workspace), blocks,
+           scale / static_cast<float>(count), accumulate, loss_out);
+  GANB_CHECK_LAUNCH("l1_loss_finish_kernel");
+  return 0;
+}

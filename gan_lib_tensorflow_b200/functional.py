@@ -814,3 +814,20 @@ def softmax_xent(logits: Var, labels: torch.Tensor, scale: float = 1.0, loss_out
             logits.accum(dlogits)
         _tape().record(bwd)
     return out
+
+
+def l1_loss(targets: torch.Tensor, outputs: Var, scale: float = 1.0, loss_out: torch.Tensor | None = None):
+    """scale * tf.reduce_mean(tf.abs(targets - outputs)) (Pix2Pix/train.py:511); `targets` is a constant."""
+    assert outputs.data.dtype == F32
+    accumulate = loss_out is not None
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=F32, device=outputs.data.device)
+    d = K.l1_loss(targets, outputs.data, scale, loss_out, accumulate)
+    out = Var(loss_out)
+    if _rg(outputs):
+        out.requires_grad = True
+
+        def bwd():
+            outputs.accum(d)
+        _tape().record(bwd)
+    return out

@@ -40,7 +40,7 @@ def L():
             return _L
         _L = cabi.lib()
         for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace",
-                     "ganb_norm_act_bwd_sums_offset", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
+                     "ganb_norm_act_bwd_sums_offset", "ganb_l1_loss_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
                      "ganb_minibatch_std_workspace",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
@@ -316,6 +316,15 @@ def gan_loss(logits, n_real, mode, scale, loss_out, accumulate):
     check(L().ganb_gan_loss(ptr(logits), n, n_real, mode, c_float(scale), int(accumulate), ptr(loss_out),
                             ptr(dlogits), _stream()), "ganb_gan_loss")
     return dlogits
+
+
+def l1_loss(targets, outputs, scale, loss_out, accumulate):
+    assert targets.dtype == torch.float32 and outputs.dtype == torch.float32 and targets.numel() == outputs.numel()
+    d = torch.empty_like(outputs)
+    ws = _ws(L().ganb_l1_loss_workspace(c_int64(outputs.numel())), outputs.device)
+    check(L().ganb_l1_loss(ptr(targets), ptr(outputs), c_int64(outputs.numel()), c_float(scale), int(accumulate),
+                           ptr(loss_out), ptr(d), ptr(ws), _stream()), "ganb_l1_loss")
+    return d
 
 
 def softmax_xent(logits, labels, scale, loss_out, accumulate):

@@ -318,6 +318,12 @@ int ganb_minibatch_std_bwd(const float* x, const float* dout, int b, int h, int 
 int ganb_copy_channels(const void* src, int src_dtype, int src_cstride, int src_off, void* dst, int dst_dtype,
                        int dst_cstride, int dst_off, int64_t pixels, int c, const float* mask, float scale, void* stream);
 
+/* scale * tf.reduce_mean(tf.abs(targets - outputs)) (Pix2Pix/train.py:511) and its gradient w.r.t. outputs
+ * (scale * sign(outputs - targets) / count, 0 at equality like tf.abs); loss_out[0] (+)= the value. */
+int64_t ganb_l1_loss_workspace(int64_t count);
+int ganb_l1_loss(const float* targets, const float* outputs, int64_t count, float scale, int accumulate, float* loss_out,
+                 float* doutputs, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,46 @@ def unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_coll
     with g.variable_scope("layer_%d" % (len(layers) + 1)):                                       # :340-352
         layers.append(_conv(g, pad(layers[-1]), 1, 1, padding, spectral_normed, update_collection))
     return layers[-1]
+
+
+class Pix2PixLosses:
+    """create_model() of Pix2Pix/train.py:447-539 for the unet_g / unet_d topology: returns (cost, params, grads)."""
+
+    def __init__(self, g, ngf, ndf, size, loss_type="HINGE", gan_weight=1.0, l1_weight=100.0):
+        self.g, self.ngf, self.ndf, self.loss_type = g, ngf, ndf, loss_type
+        self.gan_weight, self.l1_weight = gan_weight, l1_weight
+        with torch.no_grad():
+            g.draw_on_reuse = True
+            x0 = torch.zeros(1, size, size, 3)
+            out0 = self.G(x0)
+            self.D(x0, x0, ops.NO_OPS)
+            self.D(x0, out0, ops.NO_OPS)
+            g.draw_on_reuse = False
+
+    def G(self, inputs, keep_masks=None):
+        with self.g.variable_scope("g_net"):
+            return unet_g(self.g, inputs, 3, self.ngf, keep_masks=keep_masks)
+
+    def D(self, inputs, targets, update_collection):
+        with self.g.variable_scope("d_net"):
+            return unet_d(self.g, inputs, targets, self.ndf, True, update_collection)
+
+    def d_grads(self, inputs, targets, keep_masks=None):
+        from .acgan import get_loss
+        with torch.no_grad():
+            outputs = self.G(inputs, keep_masks)
+        predict_real = self.D(inputs, targets, None)           # train.py:459-467, update_collection=None
+        predict_fake = self.D(inputs, outputs, None)           # :470-478
+        cost, _ = get_loss(predict_real, predict_fake, self.loss_type)                           # :486
+        params = self.g.trainable_variables("d_net")
+        return cost.detach(), params, torch.autograd.grad(cost, [p for _, p in params], allow_unused=True)
+
+    def g_grads(self, inputs, targets, keep_masks=None):
+        from .acgan import get_loss
+        outputs = self.G(inputs, keep_masks)
+        predict_fake = self.D(inputs, outputs, None)
+        _, gen_loss_gan = get_loss(predict_fake, predict_fake, self.loss_type)                   # :510 (real unused)
+        gen_loss_l1 = torch.mean(torch.abs(targets - outputs))                                   # :511
+        cost = gen_loss_gan * self.gan_weight + gen_loss_l1 * self.l1_weight                     # :512
+        params = self.g.trainable_variables("g_net")
+        return cost.detach(), params, torch.autograd.grad(cost, [p for _, p in params], allow_unused=True)

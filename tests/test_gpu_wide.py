@@ -270,3 +270,63 @@ def test_imagenet_discriminator_full_width(env):
         x, cot_np=rs.standard_normal((n,)).astype("float32"))
     assert rel(prod["out"], refs["bf16"]["out"]) < 5e-3
     check_band(prod, refs, tag="imagenet_d")
+
+
+# ------------------------------------------------------------------------------------------------ Pix2Pix training
+@pytest.mark.parametrize("loss_type", ["HINGE", "LSGAN"])
+def test_pix2pix_training_steps(env, loss_type):
+    """Pix2Pix/train.py:447-539: critic gradients of get_loss(loss_type) with D(real) and D(fake) both assigning u
+    (update_collection=None: two different sigma in one gradient computation) and generator gradients of
+    gan_weight * GAN + l1_weight * L1 through the U-Net with dropout, vs the oracle; then one Adam iteration."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.Pix2Pix import train as PT
+    from oracle import ops as O_ops
+    from oracle import pix2pix as OP
+
+    n, ngf, size = 1, 8, 512
+    rs = np.random.RandomState(95)
+    x = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    tgt = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    masks = [(rs.uniform(size=(n, s, s, ngf * 8)) < 0.5).astype("float32") for s in (4, 8, 16)]
+    tr = PT.Trainer(ngf=ngf, ndf=ngf, size=size, loss_type=loss_type, seed=0, max_steps=100)
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(tgt).cuda()
+    md = [torch.from_numpy(m).cuda() for m in masks]
+    dl = tr.players.gradients("d", lambda: tr.d_loss(xd, td, md))
+    d_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("d_net")}
+    u_after_d = {k: v.data.cpu().numpy().copy() for k, v in store.vars.items() if k.endswith("/u")}
+    gl = tr.players.gradients("g", lambda: tr.g_loss(xd, td, md))
+    g_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("g_net")}
+    d_loss, g_loss = float(dl.data.item()), float(gl.data.item())
+    refs = {}
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        try:
+            np.random.seed(0)
+            g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+            ol = OP.Pix2PixLosses(g, ngf, ngf, size, loss_type)
+            mt = [torch.from_numpy(m) for m in masks]
+            dc, dp, dg = ol.d_grads(torch.from_numpy(x), torch.from_numpy(tgt), mt)
+            u_ref = {k_: v.detach().numpy().copy() for k_, v in g.vars.items() if k_.endswith("/u")}
+            gc, gp, gg = ol.g_grads(torch.from_numpy(x), torch.from_numpy(tgt), mt)
+            refs[mode] = dict(d=dc.item(), g=gc.item(), u=u_ref,
+                              dg={nm: t.numpy() for (nm, _), t in zip(dp, dg) if t is not None},
+                              gg={nm: t.numpy() for (nm, _), t in zip(gp, gg) if t is not None})
+        finally:
+            O_ops.BF16_OPERANDS = False
+    assert set(d_grads) == set(refs[False]["dg"]) and set(g_grads) == set(refs[False]["gg"])
+    assert abs(d_loss - refs[True]["d"]) < 5e-3 * max(1.0, abs(refs[True]["d"]))
+    assert abs(g_loss - refs[True]["g"]) < 5e-3 * max(1.0, abs(refs[True]["g"]))
+    for name, u in refs[False]["u"].items():          # two assignments during the critic pass (real, then fake)
+        assert rel(u_after_d[name], u) < 1e-3, name
+    for got, key in ((d_grads, "dg"), (g_grads, "gg")):
+        gmax = max(np.linalg.norm(t) for t in refs[False][key].values())
+        for name, f32 in refs[False][key].items():
+            if np.linalg.norm(f32) < 5e-2 * gmax:
+                continue
+            e_prod, e_orc = rel(got[name], f32), rel(refs[True][key][name], f32)
+            assert e_prod <= 2.0 * e_orc + 5e-3, (key, name, e_prod, e_orc)
+    lr0 = tr.learning_rate()
+    d, g_ = tr.train_iteration(xd, td, n_dis=2, mask_fn=lambda: md)
+    torch.cuda.synchronize()
+    assert np.isfinite(d.data.item()) and np.isfinite(g_.data.item())
+    assert tr.global_step == 1 and tr.learning_rate() < lr0 == 0.0002
