@@ -1,0 +1,94 @@
+"""Training steps of ACGAN/train.py:78-146, 191-203 on the B200 layer ops (config 2 of BASELINE.json): critic loss
+get_loss(loss_type) + auxiliary-classifier cross-entropy on the real batch, generator loss get_loss + acgan_scale_G *
+cross-entropy on the fake batch, two Adam(beta1 = 0, beta2 = 0.9) optimisers on
+tf.train.polynomial_decay(4e-4 -> 2e-4 over max_iter / 2 generator steps); per iteration one generator step (skipped
+at step 0) and n_dis critic steps.
+
+NOT reference-complete: the script always adds the WGAN-GP gradient penalty (train.py:97-105), a second backward pass
+through D's batch norms that is not built; the Trainer therefore has to be asked for explicitly with
+gradient_penalty=False."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import functional as F
+from .. import kernels as K
+from ..framework import Var, get_store
+from ..training import TwoPlayer
+from . import model as M
+
+
+class Trainer:
+    def __init__(self, batch_size: int = 64, z_dim: int = 128, loss_type: str = 'HINGE', acgan_scale_G: float = 0.1,
+                 max_iter: int = 100000, gradient_penalty: bool = True, seed: int | None = 0, world_size: int = 1,
+                 grad_allreduce=None):
+        if gradient_penalty:
+            raise NotImplementedError("ACGAN/train.py:97-105 (WGAN-GP term: a second backward pass through D's batch "
+                                      "norms) is not built; pass gradient_penalty=False for the remaining losses")
+        self.store = get_store()
+        self.model = M.ACGAN()
+        self.batch, self.z_dim, self.loss_type, self.scale_g = batch_size, z_dim, loss_type, acgan_scale_G
+        self.max_iter, self.global_step = max_iter, 0
+        if seed is not None:
+            np.random.seed(seed)
+        dev = self.store.device
+        lab = torch.zeros(2, dtype=torch.int32, device=dev)
+        with self.store.building():          # train.py:89-94: D(real), G, D(fake, reuse)
+            self.model.get_discriminator(torch.zeros(2, 32, 32, 3, device=dev), lab, update_collection=None)
+            fake = self.model.get_generator(torch.zeros(2, z_dim, device=dev), lab)
+            self.model.get_discriminator(fake, lab, update_collection='NO_OPS', reuse=True)
+        self.players = TwoPlayer("d_net", "g_net", beta1=0.0, beta2=0.9, world_size=world_size,
+                                 grad_allreduce=grad_allreduce)
+        self.players.finalize()
+
+    def learning_rate(self) -> float:
+        """tf.train.polynomial_decay(0.0004, global_step, max_iter // 2, 0.0002) (train.py:141)"""
+        steps = self.max_iter // 2
+        t = min(self.global_step, steps) / float(steps)
+        return (0.0004 - 0.0002) * (1.0 - t) + 0.0002
+
+    def preprocess(self, real_int, deq_noise):
+        """int [B, 3072] CHW -> NHWC float in [-1, 1) + U(0, 1/128) (train.py:78-81)"""
+        b = real_int.shape[0]
+        return K.preprocess_real(real_int, deq_noise, b, 1024).reshape(b, 32, 32, 3)
+
+    def d_loss(self, real, real_labels, z, fake_labels):
+        m = self.model
+        fake = m.get_generator(z, fake_labels, reuse=True)                                   # g_net frozen
+        disc_real, disc_real_acgan = m.get_discriminator(Var(real), real_labels, update_collection=None, reuse=True)
+        disc_fake, _ = m.get_discriminator(Var(fake.data), fake_labels, update_collection='NO_OPS', reuse=True)
+        loss, self.last_d = M.discriminator_losses(disc_real, disc_real_acgan, real_labels, disc_fake, self.loss_type)
+        return loss
+
+    def g_loss(self, z, fake_labels):
+        m = self.model
+        fake = m.get_generator(z, fake_labels, reuse=True)
+        disc_fake, disc_fake_acgan = m.get_discriminator(fake, fake_labels, update_collection='NO_OPS', reuse=True)
+        loss, self.last_g = M.generator_losses(disc_fake, disc_fake_acgan, fake_labels, self.loss_type, self.scale_g)
+        return loss
+
+    def d_step(self, real, real_labels, z, fake_labels):
+        return self.players.step("d", lambda: self.d_loss(real, real_labels, z, fake_labels), self.learning_rate())
+
+    def g_step(self, z, fake_labels):
+        loss = self.players.step("g", lambda: self.g_loss(z, fake_labels), self.learning_rate())
+        self.global_step += 1                # g_opt.minimize(..., global_step=global_step)
+        return loss
+
+    def _noise(self):
+        dev = self.store.device
+        z = torch.randn(self.batch, self.z_dim, device=dev)
+        labels = (torch.rand(self.batch, device=dev) * 10).to(torch.int32)
+        return z, labels
+
+    def train_iteration(self, step: int, batches, n_dis: int = 5):
+        """train.py:191-203.  `batches` yields (NHWC float real images, int32 labels) on the device."""
+        g = None
+        if step > 0:
+            g = self.g_step(*self._noise())
+        d = None
+        for _ in range(n_dis):
+            real, labels = next(batches)
+            d = self.d_step(real, labels, *self._noise())
+        return d, g

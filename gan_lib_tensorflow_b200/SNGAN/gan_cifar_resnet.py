@@ -21,6 +21,7 @@ from ..common import resnet_block as rb
 from ..common.ops import conv2d as conv2d_ops
 from ..common.ops import embedding as embedding_ops
 from ..common.ops import linear as linear_ops
+from ..training import AdamState  # noqa: F401  (tf.train.AdamOptimizer over a network's flat buffers)
 from ..framework import Var, get_store
 
 BATCH_SIZE = 64  # Critic batch size
@@ -115,27 +116,6 @@ def lr_decay(iteration: int) -> float:
     if not DECAY:
         return 1.0
     return max(0.0, 1.0 - iteration / 100000.0) if iteration < 50000 else 0.5
-
-
-class AdamState:
-    """tf.train.AdamOptimizer(lr, beta1=0., beta2=0.9) over one network's flat buffers."""
-
-    def __init__(self, flat, beta1=0.0, beta2=0.9, eps=1e-8):
-        self.flat, self.beta1, self.beta2, self.eps = flat, beta1, beta2, eps
-        self.t = 0
-        self.lr_t = torch.zeros(1, dtype=torch.float32, device=flat.params.device)
-
-    def set_lr(self, lr: float) -> None:
-        """Advances the step count and uploads lr_t = lr * sqrt(1-b2^t) / (1-b1^t)."""
-        self.t += 1
-        val = lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
-        # the value travels as a kernel argument: no host buffer that a run-ahead CPU could overwrite before
-        # the stream consumes it (the training ops themselves are CUDA-graph replays)
-        self.lr_t.fill_(val)
-
-    def apply(self, grad_scale: float = 1.0) -> None:
-        K.adam(self.flat.params, self.flat.grads, self.flat.m, self.flat.v, self.lr_t, self.beta1, self.beta2,
-               self.eps, grad_scale)
 
 
 class Trainer:

@@ -285,3 +285,29 @@ def test_pggan_training_steps(env, bc, trans):
     torch.cuda.synchronize()
     assert np.isfinite(d.data.item()) and np.isfinite(g_.data.item())
     assert not torch.equal(before, store.flat["g_net"].params)
+
+
+def test_acgan_trainer_runs_the_reference_iteration_without_the_penalty(env):
+    """ACGAN/train.py:191-203 loop structure (G step skipped at step 0, n_dis critic steps, LR decay on the generator's
+    global step); the gradient penalty must be declined explicitly."""
+    store, _ = env
+    from gan_lib_tensorflow_b200.ACGAN import train as AT
+
+    with pytest.raises(NotImplementedError):
+        AT.Trainer(batch_size=8)
+    tr = AT.Trainer(batch_size=8, gradient_penalty=False, seed=0, max_iter=10)
+    rs = np.random.RandomState(3)
+    data = torch.from_numpy(rs.randint(0, 256, size=(8, 3072)).astype("int32")).cuda()
+    labels = torch.from_numpy(rs.randint(0, 10, size=8).astype("int32")).cuda()
+    real = tr.preprocess(data, None)
+    assert real.shape == (8, 32, 32, 3) and float(real.min()) >= -1.0 and float(real.max()) < 1.0
+    batches = iter([(real, labels)] * 8)
+    d0, g0 = tr.train_iteration(0, batches, n_dis=2)
+    assert g0 is None and tr.global_step == 0 and abs(tr.learning_rate() - 0.0004) < 1e-12
+    before = store.flat["g_net"].params.clone()
+    d1, g1 = tr.train_iteration(1, batches, n_dis=2)
+    torch.cuda.synchronize()
+    assert np.isfinite(d1.data.item()) and np.isfinite(g1.data.item())
+    assert tr.global_step == 1 and tr.learning_rate() < 0.0004
+    assert not torch.equal(before, store.flat["g_net"].params)
+    assert set(tr.last_d) == {"d_loss_gan", "d_loss_acgan"}
