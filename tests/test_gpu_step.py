@@ -169,7 +169,7 @@ def test_loss_trajectory_tracks_the_oracle():
     """D / G loss TRAJECTORIES (north star: 'loss trajectories within a stated band'): 12 D+G training pairs at batch
     16 with identical data, noise and labels on both sides, Adam updates included, against the fp32 oracle.  Training
     is chaotic, so the band widens with the step: |loss_product - loss_oracle| <= 0.02 + 0.01 * step for both losses
-    (measured: 1e-4 at step 0, <= 2e-2 through step 11 -- profiles/r01_parity_report_acgan_pggan.txt)."""
+    (measured: 1e-4 at step 0, <= 2e-2 through step 11 -- profiles/r01_parity_report_full_suite.txt)."""
     from oracle import ops as O_ops
     from oracle import sngan_cifar as O
     from tests.test_gpu_ops import _report
