@@ -523,53 +523,6 @@ __device__ __forceinline__ void lanes_sum16(float (&a)[8], float (&b)[8], int la
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
-bn_stats_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int rows_per_group, int c, int chunks,
-                           int rows_per_chunk, float* __restrict__ partial) {
-  pdl_wait();
-  const int g = blockIdx.y, chunk = blockIdx.x;
-  const int v = c >> 3;
-  const int lanes = max(1, 256 / min(v, 256));
-  const int cols_per_pass = 256 / lanes;
-  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
-  const int r0 = chunk * rows_per_chunk;
-  const int r1 = min(rows_per_group, r0 + rows_per_chunk);
-  const __nv_bfloat16* xg = x + static_cast<int64_t>(g) * rows_per_group * c;
-  __shared__ float sh[256][17];
-  for (int cb = 0; cb < v; cb += cols_per_pass) {
-    const int col = cb + cx;
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-    if (col < v && ry < lanes) {
-      constexpr int U = 4;
-      for (int r = r0 + ry; r < r1; r += lanes * U) {
-        uint4 raw[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          raw[u] = (r + u * lanes < r1) ? ldg16(xg + static_cast<int64_t>(r + u * lanes) * c + col * 8)
-                                        : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          float a[8];
-          cvt8(raw[u], a);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { s[j] += a[j]; q[j] += a[j] * a[j]; }
-        }
-      }
-    }
-    lanes_sum16(s, q, lanes, cols_per_pass, cx, ry, sh);
-    if (ry == 0 && col < v) {
-      float* out = partial + (static_cast<int64_t>(g) * chunks + chunk) * 2 * c;
-      st4(out + col * 8, make_float4(s[0], s[1], s[2], s[3]));
-      st4(out + col * 8 + 4, make_float4(s[4], s[5], s[6], s[7]));
-      st4(out + c + col * 8, make_float4(q[0], q[1], q[2], q[3]));
-      st4(out + c + col * 8 + 4, make_float4(q[4], q[5], q[6], q[7]));
-    }
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------ cp.async rings
 // The streaming reductions below are bound by HBM latency x bytes in flight, not by instruction issue: with plain
 // loads a thread holds 4 x 16 B per tensor in registers and nothing is in flight while it computes (ncu: 3.1-3.7 TB/s,
@@ -999,47 +952,6 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8p_kernel(const No
       }
     }
     cp_async_wait<0>();
-  }
-}
-
-__global__ void __launch_bounds__(256)
-colsum_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int c, int rows_per_chunk,
-                         float* __restrict__ partial) {
-  pdl_wait();
-  const int chunk = blockIdx.x;
-  const int v = c >> 3;
-  const int lanes = max(1, 256 / min(v, 256));
-  const int cols_per_pass = 256 / lanes;
-  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
-  const int64_t r0 = static_cast<int64_t>(chunk) * rows_per_chunk;
-  const int64_t r1 = min(rows, r0 + rows_per_chunk);
-  __shared__ float sh[256][17];
-  for (int cb = 0; cb < v; cb += cols_per_pass) {
-    const int col = cb + cx;
-    float s[8], z[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] = 0.f; z[j] = 0.f; }
-    if (col < v && ry < lanes) {
-      constexpr int U = 4;
-      for (int64_t r = r0 + ry; r < r1; r += lanes * U) {
-        uint4 raw[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          raw[u] = (r + u * lanes < r1) ? ldg16(x + (r + u * lanes) * c + col * 8) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          float a[8];
-          cvt8(raw[u], a);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s[j] += a[j];
-        }
-      }
-    }
-    lanes_sum16(s, z, lanes, cols_per_pass, cx, ry, sh);
-    if (ry == 0 && col < v) {
-      st4(partial + static_cast<int64_t>(chunk) * c + col * 8, make_float4(s[0], s[1], s[2], s[3]));
-      st4(partial + static_cast<int64_t>(chunk) * c + col * 8 + 4, make_float4(s[4], s[5], s[6], s[7]));
-    }
   }
 }
 
