@@ -36,28 +36,28 @@ def Linear(inputs, input_dim, output_dim, name,
         in_scale = float(np.sqrt(2.0 / input_dim)) if inputs_norm else None   # linear.py:47-49
         kw = {'in_scale': in_scale} if in_scale is not None else {}
 
-        def uniform(stdev, size):
-            if _weights_stdev is not None:
-                stdev = _weights_stdev
-            return np.random.uniform(low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3), size=size).astype('float32')
+        shape = (input_dim, output_dim)
+        # stdev of the uniform(+-stdev*sqrt(3)) draw per scheme (linear.py:63-136); None / 'glorot' / 'xavier' share
+        # the Glorot value, which also makes the reference's "orthogonal if square" clause unreachable (:112-113)
+        stdevs = {
+            'lecun': np.sqrt(1. / input_dim),
+            None: np.sqrt(2. / (input_dim + output_dim)),
+            'glorot': np.sqrt(2. / (input_dim + output_dim)),
+            'xavier': np.sqrt(2. / (input_dim + output_dim)),
+            'he': np.sqrt(2. / input_dim),
+            'glorot_he': np.sqrt(4. / (input_dim + output_dim)),
+        }
 
         def draw():
-            if initialization == 'lecun':
-                wv = uniform(np.sqrt(1. / input_dim), (input_dim, output_dim))
-            elif initialization == 'glorot' or initialization == 'xavier' or (initialization is None):
-                wv = uniform(np.sqrt(2. / (input_dim + output_dim)), (input_dim, output_dim))
-            elif initialization == 'he':
-                wv = uniform(np.sqrt(2. / input_dim), (input_dim, output_dim))
-            elif initialization == 'glorot_he':
-                wv = uniform(np.sqrt(4. / (input_dim + output_dim)), (input_dim, output_dim))
+            if isinstance(initialization, (tuple, list)) and initialization[0] == 'uniform':
+                bound = initialization[1]
+                wv = np.random.uniform(low=-bound, high=bound, size=shape).astype('float32')
             elif initialization == 'orthogonal':
-                a = np.random.normal(0.0, 1.0, (input_dim, output_dim))
-                u, _, v = np.linalg.svd(a, full_matrices=False)
-                q = u if u.shape == (input_dim, output_dim) else v
-                wv = q.reshape((input_dim, output_dim)).astype('float32')
-            elif initialization[0] == 'uniform':
-                wv = np.random.uniform(low=-initialization[1], high=initialization[1],
-                                       size=(input_dim, output_dim)).astype('float32')
+                u, _, v = np.linalg.svd(np.random.normal(0.0, 1.0, shape), full_matrices=False)
+                wv = (u if u.shape == shape else v).reshape(shape).astype('float32')
+            elif initialization in stdevs:
+                stdev = _weights_stdev if _weights_stdev is not None else stdevs[initialization]
+                wv = np.random.uniform(low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3), size=shape).astype('float32')
             else:
                 raise Exception('Invalid initialization!')
             return wv * np.float32(gain)

@@ -1369,7 +1369,8 @@ __global__ void __launch_bounds__(256) upconv_pack_kernel(const float* __restric
   const int tco = blockIdx.x % tiles_co, tci = blockIdx.x / tiles_co;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const int64_t plane = static_cast<int64_t>(ci_n) * co_n;
-  for (int t16 = 0; t16 < 16; ++t16) {
+  {
+    const int t16 = blockIdx.y;                              // one (parity, tap) per block row
     const int i = t16 >> 3, j = (t16 >> 2) & 1, pp = (t16 >> 1) & 1, qq = t16 & 1;
     // rows r with (r + 1 - i) >> 1 == pp, columns s with (s + 1 - j) >> 1 == qq
     for (int jj = ty; jj < 32; jj += 8) {
@@ -1392,7 +1393,6 @@ __global__ void __launch_bounds__(256) upconv_pack_kernel(const float* __restric
       const int co = tco * 32 + jj, ci = tci * 32 + tx;
       if (ci < ci_n && co < co_n) we_t[t16 * plane + static_cast<int64_t>(co) * ci_n + ci] = __float2bfloat16_rn(tile[tx][jj]);
     }
-    __syncthreads();
   }
 }
 
@@ -1485,7 +1485,7 @@ extern "C" int ganb_upconv_supported(int n, int h, int w, int cin, int cout) {
 extern "C" int ganb_upconv_pack(const float* w_hwio, void* we_t_bf16, void* we_n_bf16, int cin, int cout, void* stream) {
   if (!w_hwio || !we_t_bf16 || !we_n_bf16) return fail(GANB_E_BADARG, "upconv_pack: null buffer");
   const int blocks = ceil_div(cin, 32) * ceil_div(cout, 32);
-  launch_k(upconv_pack_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), w_hwio,
+  launch_k(upconv_pack_kernel, dim3(blocks, 16), 256, 0, static_cast<cudaStream_t>(stream), w_hwio,
            static_cast<__nv_bfloat16*>(we_t_bf16), static_cast<__nv_bfloat16*>(we_n_bf16), cin, cout);
   GANB_CHECK_LAUNCH("upconv_pack_kernel");
   return 0;

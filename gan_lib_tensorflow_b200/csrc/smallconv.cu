@@ -233,28 +233,40 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const SgemmParams p) {
 __global__ void __launch_bounds__(256)
 im2col_small_kernel(const float* __restrict__ xs, __nv_bfloat16* __restrict__ out, int n, int hs, int ws, int cs,
                     int ho, int wo, int kh, int kw, int stride, int pad_t, int pad_l, int sign, int kpad) {
+  // per-column offsets (dh, dw, channel) once per block instead of two integer divisions per element
+  __shared__ int lut[128];
+  const int kvalid = kh * kw * cs;
+  for (int j = threadIdx.x; j < kpad; j += blockDim.x) {
+    int packed = -1;
+    if (j < kvalid) {
+      const int tap = j / cs, c = j - tap * cs;
+      const int r = tap / kw, sx = tap - r * kw;
+      packed = ((sign * (r - pad_t) + 64) << 16) | ((sign * (sx - pad_l) + 64) << 8) | c;
+    }
+    lut[j] = packed;
+  }
   pdl_wait();
+  __syncthreads();
   const int groups = kpad >> 3;  // 8 bf16 = 16 bytes per thread
   const int64_t total = static_cast<int64_t>(n) * ho * wo * groups;
-  const int kvalid = kh * kw * cs;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int gq = static_cast<int>(i % groups);
     const int64_t pix = i / groups;
-    const int w0 = static_cast<int>(pix % wo);
-    const int h0 = static_cast<int>((pix / wo) % ho);
-    const int ni = static_cast<int>(pix / (static_cast<int64_t>(wo) * ho));
+    const int pq = static_cast<int>(pix);          // pixel counts fit 32 bits (checked by the launcher)
+    const int w0 = pq % wo;
+    const int t2 = pq / wo;
+    const int h0 = t2 % ho;
+    const int ni = t2 / ho;
+    const float* xn = xs + static_cast<int64_t>(ni) * hs * ws * cs;
     __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int j = gq * 8 + e;
+      const int packed = lut[gq * 8 + e];
       float val = 0.f;
-      if (j < kvalid) {
-        const int tap = j / cs, c = j - tap * cs;
-        const int r = tap / kw, sx = tap - r * kw;
-        const int hx = h0 * stride + sign * (r - pad_t), wx = w0 * stride + sign * (sx - pad_l);
-        if (hx >= 0 && hx < hs && wx >= 0 && wx < ws)
-          val = __ldg(xs + ((static_cast<int64_t>(ni) * hs + hx) * ws + wx) * cs + c);
+      if (packed >= 0) {
+        const int hx = h0 * stride + (packed >> 16) - 64, wx = w0 * stride + ((packed >> 8) & 0xff) - 64;
+        if (hx >= 0 && hx < hs && wx >= 0 && wx < ws) val = __ldg(xn + (hx * ws + wx) * cs + (packed & 0xff));
       }
       v[e] = __float2bfloat16_rn(val);
     }
@@ -386,6 +398,8 @@ extern "C" int ganb_im2col_small(const float* xs, void* out_bf16, int n, int hs,
   if (!xs || !out_bf16) return fail(GANB_E_BADARG, "im2col_small: null buffer");
   if (kpad % 8 != 0 || kh * kw * cs > kpad) return fail(GANB_E_BADARG, "im2col_small: kh*kw*cs=%d does not fit kpad=%d", kh * kw * cs, kpad);
   if (sign != 1 && sign != -1) return fail(GANB_E_BADARG, "im2col_small: sign must be +-1");
+  if (kpad > 128 || kh > 32 || kw > 32 || static_cast<int64_t>(n) * ho * wo >= (1LL << 31))
+    return fail(GANB_E_UNSUPPORTED, "im2col_small: kpad=%d (<= 128), kernel %dx%d (<= 32) or pixel count out of range", kpad, kh, kw);
   const int64_t items = static_cast<int64_t>(n) * ho * wo * (kpad / 8);
   int64_t blocks = ceil_div64(items, 256);
   if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();

@@ -18,7 +18,7 @@ namespace ganb {
 
 constexpr float SN_EPS = 1e-12f;  // sn.py:11
 constexpr int SN_THREADS = 256;
-constexpr int SN_ROWS = 64;       // rows of W per CTA
+constexpr int SN_ROWS = GANB_SN_ROWS;   // rows of W per CTA (2 per warp: the per-row dot -> axpy chain is latency-bound)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -111,22 +111,36 @@ __global__ void __launch_bounds__(SN_THREADS) sn_fwd_rows_kernel(const ganb_sn_l
 }
 
 // Forward, stage 2 (one CTA per weight): reduce the partials, normalise, emit u', sigma.
-__global__ void __launch_bounds__(SN_THREADS) sn_fwd_finish_kernel(const ganb_sn_layer* __restrict__ layers, int assign) {
+constexpr int SN_FINISH_THREADS = 1024;
+__global__ void __launch_bounds__(SN_FINISH_THREADS) sn_fwd_finish_kernel(const ganb_sn_layer* __restrict__ layers, int assign) {
   pdl_wait();
   const ganb_sn_layer L = layers[blockIdx.x];
   const int K = L.k, C = L.c;
   const int nblk = (K + SN_ROWS - 1) / SN_ROWS;
   extern __shared__ float sm[];
-  float* b_s = sm;  // [C]
+  float* b_s = sm;          // [C]
+  float* part_s = sm + C;   // [slices][C]: the per-CTA partials are summed by `slices` thread groups side by side
   __shared__ float red[32];
   float sa = 0.f;
   for (int i = threadIdx.x; i < nblk; i += blockDim.x) sa += L.work[static_cast<int64_t>(i) * (C + 4) + C];
   const float na = sqrtf(block_sum(sa, red));
   const float inv_a = 1.f / (na + SN_EPS);
+  const int cols = min(C, static_cast<int>(blockDim.x));
+  const int slices = blockDim.x / cols;
+  const int cg = threadIdx.x % cols, sl = threadIdx.x / cols;
+  if (sl < slices) {
+    for (int c = cg; c < C; c += cols) {
+      float t = 0.f;
+#pragma unroll 4
+      for (int i = sl; i < nblk; i += slices) t += __ldg(L.work + static_cast<int64_t>(i) * (C + 4) + c);
+      part_s[sl * C + c] = t;
+    }
+  }
+  __syncthreads();
   float part = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float t = 0.f;
-    for (int i = 0; i < nblk; ++i) t += L.work[static_cast<int64_t>(i) * (C + 4) + c];
+    for (int g = 0; g < slices; ++g) t += part_s[g * C + c];   // fixed order: deterministic
     t *= inv_a;  // b = W^T v
     b_s[c] = t;
     part += t * t;
@@ -313,7 +327,9 @@ extern "C" int ganb_sn_power_iter(const ganb_sn_layer* layers_dev, int count, in
   }
   launch_k(sn_fwd_rows_kernel, total_blocks, SN_THREADS, smem1, STREAM, layers_dev, count);
   GANB_CHECK_LAUNCH("sn_fwd_rows_kernel");
-  launch_k(sn_fwd_finish_kernel, count, SN_THREADS, max_c * 4, STREAM, layers_dev, assign);
+  // b_s [C] + part_s [slices][C], slices * C <= max(C, threads)
+  const int smem2 = (max_c + (max_c > SN_FINISH_THREADS ? max_c : SN_FINISH_THREADS)) * 4;
+  launch_k(sn_fwd_finish_kernel, count, SN_FINISH_THREADS, smem2, STREAM, layers_dev, assign);
   GANB_CHECK_LAUNCH("sn_fwd_finish_kernel");
   return 0;
 }

@@ -213,7 +213,7 @@ class SNEntry:
         self.v = torch.zeros(self.k, **f32)
         self.b = torch.zeros(self.c, **f32)
         self.scal = torch.zeros(8, **f32)            # sigma, 1/sigma, |Wu|, |b|, bwd scratch
-        self.nblk = -(-self.k // 64)
+        self.nblk = -(-self.k // K.SN_ROWS)
         self.t = torch.zeros(self.k, **f32)
         self.work = torch.zeros(self.nblk * (self.c + 4), **f32)
         self.g = torch.zeros(self.k, self.c, **f32)  # dL/d(W/sigma), written by the layer's wgrad

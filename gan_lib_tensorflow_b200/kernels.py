@@ -399,6 +399,9 @@ def copy_channels(src, src_off, dst, dst_off, c, mask=None, scale=1.0):
 
 
 # ------------------------------------------------------------------------------------------------ grouped SN / pack
+SN_ROWS = 16   # GANB_SN_ROWS of include/ganb200.h (checked by tests/test_host_logic.py)
+
+
 class SnLayerStruct(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("u", c_void_p), ("u_out", c_void_p), ("u_used", c_void_p), ("v", c_void_p),
                 ("b", c_void_p), ("scal", c_void_p), ("g", c_void_p), ("dw", c_void_p), ("t", c_void_p),

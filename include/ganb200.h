@@ -126,6 +126,7 @@ int ganb_sgemm_small(const float* a, const float* b, float* c, int m, int n, int
  *   fwd : v = l2n(W u), b = W^T v, u_out = l2n(b), scal = {sigma, 1/sigma, |W u|, |b|}     (W is [k, c])
  *   bwd : dw += g/sigma + v (x) bbar + abar (x) u_used with g = dL/d(W/sigma)
  * ---------------------------------------------------------------------------------------------- */
+#define GANB_SN_ROWS 16   /* rows of the [k, c] weight matrix handled by one CTA of the grouped launches */
 typedef struct ganb_sn_layer {
   const float* w;   /* [k, c] fp32 weight (HWIO filter flattened to [kh*kw*cin, cout], or linear [in,out]) */
   float* u;         /* [c]  persistent power-iteration vector (sn.py:32); overwritten with u_out when assign=1 */
@@ -137,9 +138,9 @@ typedef struct ganb_sn_layer {
   const float* g;   /* bwd only: [k, c] gradient w.r.t. W/sigma */
   float* dw;        /* bwd only: [k, c] accumulated gradient w.r.t. W */
   float* t;         /* [k]  bwd scratch (W b) */
-  float* work;      /* [ceil(k/64) * (c + 4)] per-CTA partials */
+  float* work;      /* [ceil(k/GANB_SN_ROWS) * (c + 4)] per-CTA partials */
   int32_t k, c;
-  int32_t blk_begin; /* prefix sum of ceil(k/64) over the preceding layers */
+  int32_t blk_begin; /* prefix sum of ceil(k/GANB_SN_ROWS) over the preceding layers */
   int32_t pad_;
 } ganb_sn_layer;
 /* assign=1 reproduces update_collection=None (u.assign(u_final) on every evaluation, sn.py:48-56);

@@ -67,9 +67,9 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_mirrors_match_the_c_layout():
     from gan_lib_tensorflow_b200 import kernels as K
 
-    src = '#include "ganb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+    src = '#include "ganb200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %d\\n",' \
           'sizeof(ganb_sn_layer), offsetof(ganb_sn_layer, k), offsetof(ganb_sn_layer, blk_begin),' \
-          'sizeof(ganb_pack_layer), offsetof(ganb_pack_layer, tile_begin));}'
+          'sizeof(ganb_pack_layer), offsetof(ganb_pack_layer, tile_begin), GANB_SN_ROWS);}'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
         with open(c, "w") as fh:
@@ -78,7 +78,7 @@ def test_struct_mirrors_match_the_c_layout():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         out = subprocess.check_output([exe]).decode().split()
     got = [ctypes.sizeof(K.SnLayerStruct), K.SnLayerStruct.k.offset, K.SnLayerStruct.blk_begin.offset,
-           ctypes.sizeof(K.PackLayerStruct), K.PackLayerStruct.tile_begin.offset]
+           ctypes.sizeof(K.PackLayerStruct), K.PackLayerStruct.tile_begin.offset, K.SN_ROWS]
     assert [int(v) for v in out] == got
 
 
