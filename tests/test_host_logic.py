@@ -226,6 +226,34 @@ def test_two_evaluations_of_one_network_on_a_tape_keep_separate_sn_state(host):
             assert spectral_normed_weight(w, update_collection="NO_OPS").entry is base
 
 
+def test_two_player_trainers_call_sequence(host):
+    """training.TwoPlayer through the PGGAN trainer (PGGAN/train.py:103-136, 182-190), kernels recorded on CPU: the
+    critic step evaluates D twice (power iteration with assignment for D(real), a second state for D(fake)), leaves G's
+    parameters without gradient work, ends in one Adam launch + operand repack of d_net; the generator step runs the
+    power iteration once (NO_OPS) and updates g_net only."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+
+    tr = PT.Trainer(block_count=1, trans=True, inputs_norm=True, batch_size=2, seed=0)
+    assert set(store.flat) == {"d_net", "g_net"}
+    real, z = torch.zeros(2, 8, 8, 3), torch.zeros(2, 512)
+    n0 = len(rec.calls)
+    tr.d_step(real, z, 0.25)
+    d_calls = rec.names()[n0:]
+    assert d_calls.count("ganb_sn_power_iter") == 2 and d_calls.count("ganb_sn_bwd") == 2
+    assert d_calls.count("ganb_adam") == 1 and d_calls[-1] in ("ganb_pack_weights", "ganb_pack_small")
+    assert "ganb_minibatch_std_fwd" in d_calls and "ganb_minibatch_std_bwd" in d_calls
+    d_params = {v.key for v in store.trainable_variables("d_net")}
+    assert all(v.grad is not None for v in store.trainable_variables("d_net")) and len(d_params) > 10
+    n1 = len(rec.calls)
+    tr.g_step(z, 0.25)
+    g_calls = rec.names()[n1:]
+    assert g_calls.count("ganb_sn_power_iter") == 1 and g_calls.count("ganb_sn_bwd") == 0     # d_net is frozen
+    assert g_calls.count("ganb_adam") == 1 and "ganb_pixel_norm_bwd" in g_calls
+    assert tr.players.opt["d"].t == 1 and tr.players.opt["g"].t == 1
+    assert abs(tr.alpha(50000) - 0.5) < 1e-12
+
+
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
     store, _ = host
     from gan_lib_tensorflow_b200.common import resnet_block
