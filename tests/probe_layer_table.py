@@ -42,9 +42,16 @@ def hook(name, flops_fn):
 
 def main():
     framework.reset_default_graph("cuda")
-    tr = P.Trainer(batch_size=64, seed=0)
     rs = np.random.RandomState(0)
-    tr.set_real_batch(rs.randint(0, 256, size=(64, 3072)).astype("int32"), rs.randint(0, 10, size=64).astype("int32"))
+    if len(sys.argv) > 1 and sys.argv[1] == "imagenet":      # config 3: SNGAN ImageNet-128, batch 32 per GPU
+        from gan_lib_tensorflow_b200.SNGAN import gan_imagNet_resnet as PI
+        tr = PI.Trainer(batch_size=32, seed=0)
+        tr.set_real_batch(rs.randint(0, 256, size=(32, 49152)).astype("int32"),
+                          rs.randint(0, 1000, size=32).astype("int32"))
+    else:
+        tr = P.Trainer(batch_size=64, seed=0)
+        tr.set_real_batch(rs.randint(0, 256, size=(64, 3072)).astype("int32"),
+                          rs.randint(0, 10, size=64).astype("int32"))
     tr.sample_noise()
     tr.d_step(1)
     tr.g_step(1)
@@ -93,6 +100,8 @@ def main():
     print(f"{'call':13s} {'n,h,w,cin,ho,wo,cout,kh,kw':42s} {'x':>2s} {'us':>8s} {'TF/s':>7s} {'total':>8s} {'lost':>8s}")
     for r in rows:
         print(f"{r['name']:13s} {str(r['dims']):42s} {r['count']:2d} {r['us']:8.1f} {r['tflops']:7.0f} {r['total_us']:8.0f} {r['lost_us']:8.0f}")
+    for r in rows:
+        r.pop("fn", None)
     json.dump(rows, open("gpurun_out/layer_table.json", "w"))
 
 
