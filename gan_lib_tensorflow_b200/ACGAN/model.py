@@ -6,8 +6,8 @@ common/resnet_block.py:32-50) -> batch norm -> relu -> 3x3 conv -> tanh.  D = Op
 two plain residual blocks, NOT spectrally normalised, so the library dispatch gives every D block plain batch norm;
 leaky-ReLU throughout; spatial mean; two Linear heads (critic logit, 10-way auxiliary classifier).
 
-Not built: the gradient penalty of ACGAN/train.py:97-105 (a second backward pass through D's batch norms, SURVEY
-8(f)); `discriminator_losses(gradient_penalty=True)` raises."""
+The gradient penalty of ACGAN/train.py:97-105 lives in ACGAN/gp.py (it needs the interpolated images, not only the
+logits); `discriminator_losses(gradient_penalty=True)` points there."""
 from __future__ import annotations
 
 import torch
@@ -65,8 +65,8 @@ def discriminator_losses(disc_real, disc_real_acgan, real_labels, disc_fake, los
     """d_loss = d_loss_gan (+ gradient penalty) + d_loss_acgan (ACGAN/train.py:94-115).
     Returns (d_loss Var, device scalars {d_loss_gan, d_loss_acgan})."""
     if gradient_penalty:
-        raise NotImplementedError("the WGAN-GP term of ACGAN/train.py:97-105 needs a second backward pass through "
-                                  "D's batch norms (SURVEY 8(f)); not built")
+        raise NotImplementedError("the WGAN-GP term is a function of the images: add ACGAN.gp.gradient_penalty(real, "
+                                  "fake, alpha) to this loss (ACGAN.train.Trainer does)")
     logits = F.concat_rows(disc_real, disc_fake)
     n_real = disc_real.shape[0]
     d_loss_gan = F.gan_loss(logits, 'd', n_real=n_real, loss_type=loss_type)

@@ -4,9 +4,9 @@ cross-entropy on the fake batch, two Adam(beta1 = 0, beta2 = 0.9) optimisers on
 tf.train.polynomial_decay(4e-4 -> 2e-4 over max_iter / 2 generator steps); per iteration one generator step (skipped
 at step 0) and n_dis critic steps.
 
-NOT reference-complete: the script always adds the WGAN-GP gradient penalty (train.py:97-105), a second backward pass
-through D's batch norms that is not built; the Trainer therefore has to be asked for explicitly with
-gradient_penalty=False."""
+The WGAN-GP gradient penalty the script always adds (train.py:97-105) is ACGAN/gp.py: a third pass of D over the
+interpolates whose input gradient is built from differentiable backward ops, so the penalty reaches D's parameters
+through the backward pass (grad-grad of the batch norms included).  gradient_penalty=False drops the term."""
 from __future__ import annotations
 
 import numpy as np
@@ -16,6 +16,7 @@ from .. import functional as F
 from .. import kernels as K
 from ..framework import Var, get_store
 from ..training import TwoPlayer
+from . import gp as GP
 from . import model as M
 
 
@@ -23,9 +24,7 @@ class Trainer:
     def __init__(self, batch_size: int = 64, z_dim: int = 128, loss_type: str = 'HINGE', acgan_scale_G: float = 0.1,
                  max_iter: int = 100000, gradient_penalty: bool = True, seed: int | None = 0, world_size: int = 1,
                  grad_allreduce=None):
-        if gradient_penalty:
-            raise NotImplementedError("ACGAN/train.py:97-105 (WGAN-GP term: a second backward pass through D's batch "
-                                      "norms) is not built; pass gradient_penalty=False for the remaining losses")
+        self.gradient_penalty = bool(gradient_penalty)
         self.store = get_store()
         self.model = M.ACGAN()
         self.batch, self.z_dim, self.loss_type, self.scale_g = batch_size, z_dim, loss_type, acgan_scale_G
@@ -53,12 +52,21 @@ class Trainer:
         b = real_int.shape[0]
         return K.preprocess_real(real_int, deq_noise, b, 1024).reshape(b, 32, 32, 3)
 
-    def d_loss(self, real, real_labels, z, fake_labels):
+    def d_loss(self, real, real_labels, z, fake_labels, alpha=None):
+        """alpha: fp32 [batch] interpolation coefficients of the penalty (tf.random_uniform, train.py:98); drawn here
+        when not given."""
         m = self.model
         fake = m.get_generator(z, fake_labels, reuse=True)                                   # g_net frozen
         disc_real, disc_real_acgan = m.get_discriminator(Var(real), real_labels, update_collection=None, reuse=True)
         disc_fake, _ = m.get_discriminator(Var(fake.data), fake_labels, update_collection='NO_OPS', reuse=True)
         loss, self.last_d = M.discriminator_losses(disc_real, disc_real_acgan, real_labels, disc_fake, self.loss_type)
+        if self.gradient_penalty:
+            if alpha is None:
+                alpha = torch.rand(real.shape[0], device=real.device)
+            fake32 = fake.data if fake.data.dtype == torch.float32 else K.cast(fake.data, torch.float32)
+            gp = GP.gradient_penalty(real, fake32, alpha)
+            self.last_d['gradient_penalty'] = gp.data
+            loss = F.add_scalars(loss, gp)
         return loss
 
     def g_loss(self, z, fake_labels):
@@ -68,8 +76,9 @@ class Trainer:
         loss, self.last_g = M.generator_losses(disc_fake, disc_fake_acgan, fake_labels, self.loss_type, self.scale_g)
         return loss
 
-    def d_step(self, real, real_labels, z, fake_labels):
-        return self.players.step("d", lambda: self.d_loss(real, real_labels, z, fake_labels), self.learning_rate())
+    def d_step(self, real, real_labels, z, fake_labels, alpha=None):
+        return self.players.step("d", lambda: self.d_loss(real, real_labels, z, fake_labels, alpha),
+                                 self.learning_rate())
 
     def g_step(self, z, fake_labels):
         loss = self.players.step("g", lambda: self.g_loss(z, fake_labels), self.learning_rate())

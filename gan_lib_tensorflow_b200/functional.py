@@ -831,3 +831,171 @@ def l1_loss(targets: torch.Tensor, outputs: Var, scale: float = 1.0, loss_out: t
             outputs.accum(d)
         _tape().record(bwd)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ second order
+# The WGAN-GP penalty (ACGAN/train.py:97-105) is a function of g = d sum(D(x_hat)) / d x_hat and is differentiated
+# w.r.t. D's parameters, i.e. through the backward pass of D.  The ops below are the steps of that backward pass written
+# as differentiable forward ops ("*_input_grad"): each computes the input gradient of one layer with the same kernels
+# the tape uses, and records the vector-Jacobian product of THAT computation.  Convolution and pooling backward are
+# linear (their VJPs are the layers' own forward / filter-gradient kernels), activation masks are piecewise constant;
+# only the backward of a training-mode batch norm depends on the forward activations (ganb_bn_bwd_vjp).
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == F32 else K.cast(t, F32)
+
+
+def conv2d_input_grad(gy: Var, W: Variable, x_shape, kh: int, kw: int, padding: str = "SAME") -> Var:
+    """gx = d<gy, conv2d(x, W)>/dx for a stride-1 convolution without spectral norm (tf.nn.conv2d's
+    Conv2DBackpropInput), differentiable w.r.t. gy and W."""
+    store = get_store()
+    n, h, w, cin = x_shape
+    cout = W.data.shape[-1]
+    taps = kh * kw
+    pt, pl, ho, wo = _pads(padding, h, w, kh, kw, 1)
+    if cout % 8 or (cin % 8 and not (cin < 8 and small_k(taps, cin) is not None)):
+        raise NotImplementedError(f"conv2d_input_grad: cin={cin}, cout={cout}")
+    small_in = cin < 8
+    kp_in = small_k(taps, cin) if small_in else None
+    group = store.pack_group(W.root)
+    pack = group.entry(W)
+    group.refresh()
+    gy16 = gy.data if gy.data.dtype == BF16 else K.cast(gy.data, BF16)
+    gx = K.conv_igemm(gy16, pack.wn, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True, None, None,
+                      None, None, F32)
+    out = Var(gx, grad_dtype=F32)
+    need_w = W.needs_grad and _tape() is not None
+    if _rg(gy) or need_w:
+        out.requires_grad = True
+
+        def bwd():
+            c = out.grad
+            if c is None:
+                return
+            c32 = _f32(c)
+            if small_in:
+                ccol = K.im2col_small(c32, n, h, w, cin, ho, wo, kh, kw, pt, pl, +1, kp_in)
+                if gy.requires_grad:   # forward convolution of the cotangent
+                    gy.accum(K.conv_igemm(ccol, pack.ws, n, ho, wo, kp_in, ho, wo, cout, 1, 1, 0, 0, False, None, None,
+                                          None, None, gy.gdtype))
+                if need_w:
+                    r = torch.empty((kp_in, cout), dtype=F32, device=c.device)
+                    K.conv_wgrad(ccol, gy16, r, n, ho, wo, kp_in, ho, wo, cout, 1, 1, 0, 0, None, 0.0)
+                    K.small_wgrad_scatter(r, W.grad, taps, cin, cout, False, None, 1.0)
+            else:
+                c16 = K.cast(c32, BF16)
+                if gy.requires_grad:
+                    gy.accum(K.conv_igemm(c16, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, None, None,
+                                          None, None, gy.gdtype))
+                if need_w:             # gx is linear in W: dW = wgrad with the cotangent in the activation's place
+                    K.conv_wgrad(c16, gy16, W.grad, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, None, 1.0)
+        _tape().record(bwd)
+    return out
+
+
+def act_input_grad(x: Var, gy: Var, act) -> Var:
+    """gx = gy * act'(x) (backward of a stand-alone relu / leaky relu on fp32 x); the mask is piecewise constant."""
+    n, h, w, c = x.shape
+    gx = K.norm_act_bwd(_f32(x.data), _f32(gy.data), 0, n, h, w, c, None, None, 1, None, None, None, act, False, None,
+                        None, None, F32)
+    out = Var(gx, grad_dtype=F32)
+    if _rg(gy):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                gy.accum(K.norm_act_bwd(_f32(x.data), _f32(out.grad), 0, n, h, w, c, None, None, 1, None, None, None, act,
+                                        False, None, None, None, gy.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def bn_act_input_grad(x: Var, gy: Var, gamma: Variable, beta: Variable, mean: torch.Tensor, rstd: torch.Tensor, act,
+                      eps: float = 1e-5) -> Var:
+    """gx = d<gy, act(batch_norm(x))>/dx in training mode (one statistic group) for fp32 x; differentiable w.r.t. x
+    (the statistics and x_hat), gy and gamma -- the grad-grad of fused batch norm (ganb_bn_bwd_vjp)."""
+    n, h, w, c = x.shape
+    assert x.data.dtype == F32
+    gy32 = _f32(gy.data)
+    gx = K.norm_act_bwd(x.data, gy32, 0, n, h, w, c, mean, rstd, 1, gamma.data, beta.data, None, act, False, None, None,
+                        None, F32)
+    out = Var(gx, grad_dtype=F32)
+    need_p = gamma.needs_grad and _tape() is not None
+    if _rg(x, gy) or need_p:
+        out.requires_grad = True
+
+        def bwd():
+            c_ = out.grad
+            if c_ is None:
+                return
+            dx, dgy = K.bn_bwd_vjp(x.data, gy32, _f32(c_), mean.reshape(-1), rstd.reshape(-1), gamma.data, beta.data, act,
+                                   gamma.grad if need_p else None)
+            if x.requires_grad:
+                x.accum(dx if x.gdtype == F32 else K.cast(dx, x.gdtype))
+            if gy.requires_grad:
+                gy.accum(dgy if gy.gdtype == F32 else K.cast(dgy, gy.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def meanpool2_input_grad(gy: Var) -> Var:
+    """gx[n, 2h, 2w, c] = gy / 4 replicated 2x2 (backward of the 2x2 mean pool)."""
+    out = Var(K.expand2(_f32(gy.data), 0.25, F32), grad_dtype=F32)
+    if _rg(gy):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                gy.accum(K.sum2x2(_f32(out.grad), 0.25, gy.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def act_mean_hw_input_grad(x: Var, gout: Var, act) -> Var:
+    """gx = act'(x) * gout[n, None, None, :] / (h w) (backward of mean over (h, w) of act(x)), fp32 x."""
+    n, h, w, c = x.shape
+    out = Var(K.act_mean_hw_bwd(_f32(x.data), _f32(gout.data), act, F32), grad_dtype=F32)
+    if _rg(gout):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is None:
+                return
+            masked = K.norm_act_bwd(_f32(x.data), _f32(out.grad), 0, n, h, w, c, None, None, 1, None, None, None, act,
+                                    False, None, None, None, F32)
+            gout.accum(K.act_mean_hw_fwd(masked, None))
+        _tape().record(bwd)
+    return out
+
+
+def linear_input_grad(gout: torch.Tensor, W: Variable) -> Var:
+    """g[m, in] = gout[m, out] @ W^T for a constant upstream gradient (the ones of tf.gradients), differentiable w.r.t. W."""
+    m, kout = gout.shape
+    kin = W.data.shape[0]
+    g = torch.empty((m, kin), dtype=F32, device=gout.device)
+    K.sgemm_small(gout, W.data, g, m, kin, kout, False, True, None, None, 0.0)
+    out = Var(g, grad_dtype=F32)
+    if W.needs_grad and _tape() is not None:
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:      # dW[in, out] += c^T @ gout
+                K.sgemm_small(_f32(out.grad), gout, W.grad, kin, kout, m, True, False, None, None, 1.0)
+        _tape().record(bwd)
+    return out
+
+
+def gradient_penalty_loss(g: Var, scale: float = 10.0, loss_out: torch.Tensor | None = None) -> Var:
+    """scale * mean_n (sqrt(sum_{hwc} g^2 + 1e-10) - 1)^2 (ACGAN/train.py:102-104)."""
+    accumulate = loss_out is not None
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=F32, device=g.data.device)
+    n = g.shape[0]
+    dg = K.gp_loss(_f32(g.data).reshape(n, -1), scale, loss_out, accumulate)
+    out = Var(loss_out)
+    if _rg(g):
+        out.requires_grad = True
+
+        def bwd():
+            g.accum(dg.reshape(g.data.shape))
+        _tape().record(bwd)
+    return out

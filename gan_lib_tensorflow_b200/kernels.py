@@ -40,7 +40,7 @@ def L():
             return _L
         _L = cabi.lib()
         for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace",
-                     "ganb_norm_act_bwd_sums_offset", "ganb_l1_loss_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
+                     "ganb_norm_act_bwd_sums_offset", "ganb_l1_loss_workspace", "ganb_bn_bwd_vjp_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
                      "ganb_minibatch_std_workspace",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
@@ -325,6 +325,35 @@ def l1_loss(targets, outputs, scale, loss_out, accumulate):
     check(L().ganb_l1_loss(ptr(targets), ptr(outputs), c_int64(outputs.numel()), c_float(scale), int(accumulate),
                            ptr(loss_out), ptr(d), ptr(ws), _stream()), "ganb_l1_loss")
     return d
+
+
+# ------------------------------------------------------------------------------------------------ gradient penalty
+def interpolate(real, fake, alpha):
+    n = real.shape[0]
+    out = torch.empty_like(real)
+    check(L().ganb_interpolate(ptr(real), ptr(fake), ptr(alpha), n, c_int64(real.numel() // n), ptr(out), _stream()),
+          "ganb_interpolate")
+    return out
+
+
+def gp_loss(g, scale, loss_out, accumulate):
+    n = g.shape[0]
+    dg = torch.empty_like(g)
+    ws = torch.empty(n, dtype=torch.float32, device=g.device)
+    check(L().ganb_gp_loss(ptr(g), n, c_int64(g.numel() // n), c_float(scale), int(accumulate), ptr(loss_out), ptr(dg),
+                           ptr(ws), _stream()), "ganb_gp_loss")
+    return dg
+
+
+def bn_bwd_vjp(x, gy, cot, mean, rstd, gamma, beta, act, dgamma):
+    """-> (d/dx, d/dgy) of sum(cot * BNbwd(x, gy)); d/dgamma accumulated into `dgamma` (may be None)."""
+    c = x.shape[-1]
+    pixels = x.numel() // c
+    dx, dgy = torch.empty_like(x), torch.empty_like(gy)
+    ws = _ws(L().ganb_bn_bwd_vjp_workspace(c_int64(pixels), c), x.device)
+    check(L().ganb_bn_bwd_vjp(ptr(x), ptr(gy), ptr(cot), ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), c_int64(pixels), c,
+                              act_code(act), ptr(dx), ptr(dgy), ptr(dgamma), ptr(ws), _stream()), "ganb_bn_bwd_vjp")
+    return dx, dgy
 
 
 def softmax_xent(logits, labels, scale, loss_out, accumulate):

@@ -325,6 +325,23 @@ int64_t ganb_l1_loss_workspace(int64_t count);
 int ganb_l1_loss(const float* targets, const float* outputs, int64_t count, float scale, int accumulate, float* loss_out,
                  float* doutputs, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * WGAN-GP gradient penalty (ACGAN/train.py:97-105; tf.random_uniform interpolation, tf.gradients of D w.r.t. the
+ * interpolates, 10 * mean((slopes - 1)^2)), differentiated w.r.t. D's parameters through the backward pass.
+ *   ganb_interpolate : out[n, :] = real[n, :] + alpha[n] * (fake[n, :] - real[n, :])
+ *   ganb_gp_loss     : loss_out[0] (+)= scale * mean_n (sqrt(sum g[n,:]^2 + 1e-10) - 1)^2, dg = d/dg; workspace n floats
+ *   ganb_bn_bwd_vjp  : vector-Jacobian product of the BACKWARD of act(batch_norm(x)) (training mode, one statistic
+ *                      group): for gx = BNbwd(x, gy) and a cotangent `cot` of gx it returns d/dx, d/dgy and accumulates
+ *                      d/dgamma (the "grad-grad" of fused batch norm that tf.gradients builds for the penalty). */
+int ganb_interpolate(const float* real, const float* fake, const float* alpha, int n, int64_t per_sample, float* out,
+                     void* stream);
+int ganb_gp_loss(const float* g, int n, int64_t per_sample, float scale, int accumulate, float* loss_out, float* dg,
+                 float* workspace_n, void* stream);
+int64_t ganb_bn_bwd_vjp_workspace(int64_t pixels, int c);
+int ganb_bn_bwd_vjp(const float* x, const float* gy, const float* cot, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, int64_t pixels, int c, int act, float* dx, float* dgy,
+                    float* dgamma, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,3 +72,12 @@ def get_loss(disc_real, disc_fake, loss_type="HINGE"):
 def sparse_softmax_xent_mean(logits, labels):
     """tf.reduce_mean(tf.nn.sparse_softmax_cross_entropy_with_logits(...)) (ACGAN/train.py:110-121)"""
     return torch.nn.functional.cross_entropy(logits, labels.long(), reduction="mean")
+
+
+def gradient_penalty(g, model, real, fake, alpha, labels):
+    """ACGAN/train.py:97-104 (torch double backward stands in for tf.gradients of tf.gradients)"""
+    interpolates = (real + alpha.reshape(-1, 1, 1, 1) * (fake - real)).detach().requires_grad_(True)
+    d = model.get_discriminator(g, interpolates, labels, update_collection=ops.NO_OPS, reuse=True)[0]
+    gradients = torch.autograd.grad(d.sum(), interpolates, create_graph=True)[0]
+    slopes = torch.sqrt(torch.sum(gradients ** 2, dim=(1, 2, 3)) + 1e-10)
+    return 10 * torch.mean((slopes - 1.0) ** 2)

@@ -54,17 +54,34 @@ class _ConvRoundedOperands(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
+        """Written with differentiable ops (no once_differentiable): the WGAN-GP oracle differentiates THROUGH this
+        backward pass (torch.autograd.grad(..., create_graph=True))."""
         xr, w = ctx.saved_tensors
         stride, padding, scale = ctx.cfg
-        gyr = _r16(gy)
-        with torch.enable_grad():
-            x_ = xr.detach().requires_grad_(True)
-            w_ = w.detach().requires_grad_(True)
-            y = conv2d_nhwc(x_, w_, stride, padding)
-            dx, dw = torch.autograd.grad(y, (x_, w_), gyr)
+        gyr = _ste_r16(gy)
+        dx, dw = _conv_grads_nhwc(xr, w, gyr, stride, padding)
         if scale != 1.0:
             dx, dw = dx * scale, dw * scale
         return dx, dw, None, None, None
+
+
+def _conv_grads_nhwc(x, w, gy, stride, padding):
+    """(d/dx, d/dw) of sum(gy * conv2d_nhwc(x, w)) as differentiable expressions (TF padding handled explicitly)."""
+    kh, kw = w.shape[0], w.shape[1]
+    if padding == "SAME":
+        pt, pb, _ = same_pads(x.shape[1], kh, stride)
+        pl, pr, _ = same_pads(x.shape[2], kw, stride)
+    elif isinstance(padding, (tuple, list)):
+        pt, pb, pl, pr = padding
+    else:
+        pt = pb = pl = pr = 0
+    xc = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    wc = w.permute(3, 2, 0, 1)
+    gc = gy.permute(0, 3, 1, 2)
+    dxp = torch.nn.grad.conv2d_input(xc.shape, wc, gc, stride=stride)
+    dwc = torch.nn.grad.conv2d_weight(xc, wc.shape, gc, stride=stride)
+    dx = dxp[:, :, pt:dxp.shape[2] - pb, pl:dxp.shape[3] - pr].permute(0, 2, 3, 1)
+    return dx, dwc.permute(2, 3, 1, 0)
 
 # module-level switches of conv2d.py:10-28 / linear.py:12-35 / deconv2d.py:8-26
 _default_weightnorm = False

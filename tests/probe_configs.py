@@ -1,5 +1,5 @@
 """Full-size timing of the other BASELINE.json configs on one B200 (synthetic data, eager steps, CUDA events):
-  2  ACGAN CIFAR-10 (batch 64, without the gradient penalty)      3  SNGAN ImageNet-128 (batch 32 per GPU, CUDA graphs)
+  2  ACGAN CIFAR-10 (batch 64, with the gradient penalty)         3  SNGAN ImageNet-128 (batch 32 per GPU, CUDA graphs)
   4  Pix2Pix U-Net + PatchGAN at 256x256 (batch 32)                5  PGGAN 256x256 (block_count 6, fade-in, batch 16)
 Prints ms per critic step / generator step and the implied reference iterations per second.  Not a pytest file."""
 import json
@@ -49,13 +49,13 @@ def imagenet():
 def acgan():
     from gan_lib_tensorflow_b200.ACGAN import train as AT
     framework.reset_default_graph("cuda")
-    tr = AT.Trainer(batch_size=64, gradient_penalty=False, seed=0)
+    tr = AT.Trainer(batch_size=64, gradient_penalty=True, seed=0)
     rs = np.random.RandomState(0)
     real = tr.preprocess(torch.from_numpy(rs.randint(0, 256, size=(64, 3072)).astype("int32")).cuda(), None)
     labels = torch.from_numpy(rs.randint(0, 10, size=64).astype("int32")).cuda()
     d = timed(lambda: tr.d_step(real, labels, *tr._noise()))
     g = timed(lambda: tr.g_step(*tr._noise()))
-    return dict(config="2 ACGAN CIFAR-10, batch 64, no gradient penalty, eager", d_ms=d, g_ms=g, n_critic=5)
+    return dict(config="2 ACGAN CIFAR-10, batch 64, with the WGAN-GP gradient penalty, eager", d_ms=d, g_ms=g, n_critic=5)
 
 
 def pix2pix():

@@ -289,12 +289,10 @@ def test_pggan_training_steps(env, bc, trans):
 
 def test_acgan_trainer_runs_the_reference_iteration_without_the_penalty(env):
     """ACGAN/train.py:191-203 loop structure (G step skipped at step 0, n_dis critic steps, LR decay on the generator's
-    global step); the gradient penalty must be declined explicitly."""
+    global step), here without the penalty term (its parity is test_acgan_gradient_penalty)."""
     store, _ = env
     from gan_lib_tensorflow_b200.ACGAN import train as AT
 
-    with pytest.raises(NotImplementedError):
-        AT.Trainer(batch_size=8)
     tr = AT.Trainer(batch_size=8, gradient_penalty=False, seed=0, max_iter=10)
     rs = np.random.RandomState(3)
     data = torch.from_numpy(rs.randint(0, 256, size=(8, 3072)).astype("int32")).cuda()
@@ -311,3 +309,152 @@ def test_acgan_trainer_runs_the_reference_iteration_without_the_penalty(env):
     assert tr.global_step == 1 and tr.learning_rate() < 0.0004
     assert not torch.equal(before, store.flat["g_net"].params)
     assert set(tr.last_d) == {"d_loss_gan", "d_loss_acgan"}
+
+
+def test_acgan_gradient_penalty(env):
+    """ACGAN/train.py:97-105: WGAN-GP on the interpolates, differentiated w.r.t. D's parameters THROUGH the backward
+    pass (grad-grad of six batch norms, ganb_bn_bwd_vjp).  Value and every parameter gradient of the penalty alone vs
+    the fp32 oracle (torch double backward); the product runs its convolutions on bf16 operands in both passes."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.ACGAN import gp as GP
+    from gan_lib_tensorflow_b200.ACGAN import train as AT
+    from oracle import acgan as OA
+    from oracle import ops as O_ops
+    from tests.test_gpu_ops import _report
+
+    n = 8
+    rs = np.random.RandomState(97)
+    real = rs.uniform(-1, 1, size=(n, 32, 32, 3)).astype("float32")
+    fake = rs.uniform(-1, 1, size=(n, 32, 32, 3)).astype("float32")
+    alpha = rs.uniform(0, 1, size=n).astype("float32")
+    labels = rs.randint(0, 10, size=n).astype("int32")
+    tr = AT.Trainer(batch_size=n, gradient_penalty=True, seed=0)
+    # perturb gamma / beta so that the batch-norm parameters matter
+    prs = np.random.RandomState(5)
+    pert = {}
+    for k, v in store.vars.items():
+        if "BatchNorm" in k:
+            pert[k] = (v.data.cpu().numpy() + 0.2 * prs.standard_normal(tuple(v.data.shape))).astype("float32")
+            v.data.copy_(torch.from_numpy(pert[k]))
+    store.zero_grad("d_net")
+    with store.gradient_tape() as tape, store.frozen_scopes("g_net"):
+        gp = GP.gradient_penalty(torch.from_numpy(real).cuda(), torch.from_numpy(fake).cuda(),
+                                 torch.from_numpy(alpha).cuda())
+        tape.backward(gp)
+    torch.cuda.synchronize()
+    got = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("d_net")}
+    gp_val = float(gp.data.item())
+    # ---- oracles: fp32 (the reference formula) and bf16-operand (rounded convolutions, differentiated twice)
+    refs = {}
+    lab = torch.from_numpy(labels).long()
+    for mode in (False, True):
+        O_ops.BF16_OPERANDS = mode
+        try:
+            np.random.seed(0)
+            g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+            om = OA.ACGAN()
+            with torch.no_grad():
+                om.get_discriminator(g, torch.zeros(2, 32, 32, 3), lab[:2])
+                om.get_generator(g, torch.zeros(2, 128), lab[:2])
+            for k, arr in pert.items():
+                g.assign(k, torch.from_numpy(arr))
+            ref = OA.gradient_penalty(g, om, torch.from_numpy(real), torch.from_numpy(fake), torch.from_numpy(alpha), lab)
+            params = g.trainable_variables("d_net")
+            grads = torch.autograd.grad(ref, [p for _, p in params], allow_unused=True)
+            refs[mode] = (float(ref.detach()), {nm: (t.numpy() if t is not None else None)
+                                                for (nm, _), t in zip(params, grads)})
+        finally:
+            O_ops.BF16_OPERANDS = False
+    f32_val, f32 = refs[False]
+    b16_val, b16 = refs[True]
+    gmax = max(np.linalg.norm(t) for t in f32.values() if t is not None)
+    errs = {}
+    for nm, t in f32.items():
+        if t is None or np.linalg.norm(t) < 5e-2 * gmax:
+            continue
+        errs[nm] = (rel(got[nm], t), rel(b16[nm], t))
+    _report(f"acgan gradient penalty: value {gp_val:.5f} vs fp32 oracle {f32_val:.5f} / bf16 oracle {b16_val:.5f}; "
+            "prod-vs-fp32/bf16oracle-vs-fp32: " +
+            " ".join(f"{k.split('/', 1)[1]}={v[0]:.2e}/{v[1]:.2e}" for k, v in sorted(errs.items(), key=lambda kv: -kv[1][0])[:10]))
+    assert abs(gp_val - f32_val) < 1e-2 * abs(f32_val) + 1e-4
+    # batch-8 batch norms differentiated twice: the bf16 band is wide (the two ORACLES differ by 15-20 %); the product
+    # must be as close to fp32 as the bf16-operand oracle is.  The pieces are held tightly by the unit tests below.
+    assert len(errs) >= 8
+    for nm, (e_prod, e_orc) in errs.items():
+        assert e_prod <= 1.5 * e_orc + 1e-2, (nm, e_prod, e_orc)
+    # heads that take no part in the critic logit's input gradient get no penalty gradient
+    assert np.abs(got["d_net/D.ACGANOutput/W"]).max() == 0.0
+    # and the full critic loss of the trainer includes the term
+    d = tr.d_loss(torch.from_numpy(real).cuda(), torch.from_numpy(labels).cuda(), torch.randn(n, 128, device="cuda"),
+                  torch.from_numpy(labels).cuda(), torch.from_numpy(alpha).cuda())
+    assert "gradient_penalty" in tr.last_d and np.isfinite(d.data.item())
+
+
+def test_second_order_ops_match_torch_double_backward(env):
+    """The differentiable backward ops of functional.py ("second order") one by one, fp32-exact where the op is fp32:
+    bn_act_input_grad (ganb_bn_bwd_vjp: grad-grad of a training-mode batch norm + leaky relu) against torch's double
+    backward; conv2d_input_grad's two VJPs with bf16-representable operands."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200 import kernels as K
+    from gan_lib_tensorflow_b200.common.ops import conv2d as C
+    from tests.test_gpu_ops import _bf16_repr
+
+    rs = np.random.RandomState(11)
+    # ---------------- batch norm + lrelu: gx = d<gy, lrelu(BN(x))>/dx ; L2 = <cot, gx>
+    n, h, c = 6, 8, 32
+    x = (rs.standard_normal((n, h, h, c)) * 1.5 + 0.3).astype("float32")
+    gy = rs.standard_normal((n, h, h, c)).astype("float32")
+    cot = rs.standard_normal((n, h, h, c)).astype("float32")
+    gam = (1 + 0.3 * rs.standard_normal(c)).astype("float32")
+    bet = (0.2 * rs.standard_normal(c)).astype("float32")
+    with store.variable_scope("t"):
+        gv = store.get_variable("gamma", initializer=gam)
+        bv = store.get_variable("beta", initializer=bet)
+    gv.grad, bv.grad = torch.zeros_like(gv.data), torch.zeros_like(bv.data)
+    xv = F.Var(torch.from_numpy(x).cuda(), requires_grad=True)
+    gyv = F.Var(torch.from_numpy(gy).cuda(), requires_grad=True)
+    mean, rstd = K.bn_stats(xv.data, n, h * h, c, 1, 1e-5)
+    with store.gradient_tape() as tape:
+        gx = F.bn_act_input_grad(xv, gyv, gv, bv, mean, rstd, 'lrelu')
+        tape.backward(gx, grad=torch.from_numpy(cot).cuda())
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    gyt = torch.from_numpy(gy).double().requires_grad_(True)
+    gt = torch.from_numpy(gam).double().requires_grad_(True)
+    bt = torch.from_numpy(bet).double()
+    mu = xt.mean(dim=(0, 1, 2)); var = xt.var(dim=(0, 1, 2), unbiased=False)
+    z = (xt - mu) * torch.rsqrt(var + 1e-5) * gt + bt
+    y = torch.where(z >= 0, z, 0.2 * z)
+    gx_ref, = torch.autograd.grad(y, xt, gyt, create_graph=True)
+    d_x, d_gy, d_g = torch.autograd.grad(gx_ref, (xt, gyt, gt), torch.from_numpy(cot).double())
+    assert rel(gx.data.cpu().numpy(), gx_ref.detach().numpy()) < 2e-5
+    assert rel(xv.grad.cpu().numpy(), d_x.numpy()) < 1e-4
+    assert rel(gyv.grad.cpu().numpy(), d_gy.numpy()) < 2e-5
+    assert rel(gv.grad.cpu().numpy(), d_g.numpy()) < 1e-4
+    # ---------------- convolution: gx = d<gy, conv(x, W)>/dx ; VJPs w.r.t. gy (forward conv) and W (filter gradient)
+    for cin, cout, k in ((64, 128, 3), (3, 64, 3), (64, 64, 1)):
+        name = f"c{cin}_{cout}_{k}"
+        np.random.seed(3)
+        x0 = F.Var(torch.zeros(4, 16, 16, cin, device="cuda"))
+        C.Conv2D(x0, cin, cout, k, 1, name, biases=False)               # creates the filter variable
+        W = store.vars[name + "/Filters"]
+        W.data.copy_(W.data.to(torch.bfloat16).float())                  # bf16-representable filter
+        store.bump(W.root)
+        W.grad = torch.zeros_like(W.data)
+        gy2 = _bf16_repr(rs.standard_normal((4, 16, 16, cout)).astype("float32"))
+        cot2 = _bf16_repr(rs.standard_normal((4, 16, 16, cin)).astype("float32"))
+        gyv2 = F.Var(torch.from_numpy(gy2).cuda(), requires_grad=True)
+        with store.gradient_tape() as tape:
+            gx2 = F.conv2d_input_grad(gyv2, W, (4, 16, 16, cin), k, k)
+            tape.backward(gx2, grad=torch.from_numpy(cot2).cuda())
+        torch.cuda.synchronize()
+        wt = W.data.cpu().double().requires_grad_(True)
+        gt2 = torch.from_numpy(gy2).double().requires_grad_(True)
+        xz = torch.zeros(4, 16, 16, cin, dtype=torch.double, requires_grad=True)
+        from oracle import ops as O
+        yy = O.conv2d_nhwc(xz, wt, 1, "SAME")
+        gx_r, = torch.autograd.grad(yy, xz, gt2, create_graph=True)
+        d_gy2, d_w = torch.autograd.grad(gx_r, (gt2, wt), torch.from_numpy(cot2).double())
+        assert rel(gx2.data.cpu().numpy(), gx_r.detach().numpy()) < 1e-5, name
+        assert rel(gyv2.grad.float().cpu().numpy(), d_gy2.numpy()) < 1e-5, name
+        assert rel(W.grad.cpu().numpy(), d_w.numpy()) < 1e-4, name
