@@ -326,12 +326,9 @@ class Trainer:
         return self.g_loss
 
     def launches_per_pair(self) -> int:
-        """libganb200 kernels in one D-step + one G-step (valid after capture(); counted live in eager mode)."""
-        if not self.graph_launches:
-            before = K.launch_count()
-            self.d_step(1)
-            self.g_step(1)
-            return K.launch_count() - before
+        """libganb200 kernels in one D-step + one G-step (valid after capture(); 0 in eager mode, where the caller
+        counts ganb_launch_count() around its own steps -- running extra steps here would issue collectives on one
+        rank only)."""
         return sum(self.graph_launches.values())
 
     def train_iteration(self, iteration: int, batches):
