@@ -77,13 +77,47 @@ class Trainer:
         return loss
 
     def d_step(self, real, real_labels, z, fake_labels, alpha=None):
+        if self.players.captured("d"):
+            s = self.static
+            s['real'].copy_(real, non_blocking=True)
+            s['real_labels'].copy_(real_labels, non_blocking=True)
+            s['z_d'].copy_(z, non_blocking=True)
+            s['fake_labels_d'].copy_(fake_labels, non_blocking=True)
+            if alpha is None:
+                s['alpha'].uniform_(0.0, 1.0)
+            else:
+                s['alpha'].copy_(alpha, non_blocking=True)
+            return self.players.replay("d", self.learning_rate())
         return self.players.step("d", lambda: self.d_loss(real, real_labels, z, fake_labels, alpha),
                                  self.learning_rate())
 
     def g_step(self, z, fake_labels):
-        loss = self.players.step("g", lambda: self.g_loss(z, fake_labels), self.learning_rate())
+        if self.players.captured("g"):
+            self.static['z_g'].copy_(z, non_blocking=True)
+            self.static['fake_labels_g'].copy_(fake_labels, non_blocking=True)
+            loss = self.players.replay("g", self.learning_rate())
+        else:
+            loss = self.players.step("g", lambda: self.g_loss(z, fake_labels), self.learning_rate())
         self.global_step += 1                # g_opt.minimize(..., global_step=global_step)
         return loss
+
+    def capture(self):
+        """Both training ops as CUDA graphs over static input buffers (the step is launch-bound at CIFAR size: ~500
+        kernels of a few microseconds each).  Call after at least one eager d_step and g_step (every workspace,
+        descriptor table and operand copy exists); afterwards d_step / g_step copy their arguments into the static
+        buffers and replay."""
+        dev, b = self.store.device, self.batch
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        s = self.static = {
+            'real': torch.zeros(b, 32, 32, 3, **f32), 'real_labels': torch.zeros(b, **i32),
+            'z_d': torch.zeros(b, self.z_dim, **f32), 'fake_labels_d': torch.zeros(b, **i32),
+            'alpha': torch.zeros(b, **f32), 'z_g': torch.zeros(b, self.z_dim, **f32),
+            'fake_labels_g': torch.zeros(b, **i32),
+        }
+        d_fn = lambda: self.d_loss(s['real'], s['real_labels'], s['z_d'], s['fake_labels_d'], s['alpha'])  # noqa: E731
+        g_fn = lambda: self.g_loss(s['z_g'], s['fake_labels_g'])                                             # noqa: E731
+        self.players.capture("d", d_fn)
+        self.players.capture("g", g_fn)
 
     def _noise(self):
         dev = self.store.device

@@ -79,13 +79,39 @@ class Trainer:
         return F.add_scalars(gen_loss_gan, gen_loss_l1)
 
     # ------------------------------------------------------------------------------------------ steps
+    def _stage(self, inputs, targets, keep_masks):
+        s = self.static
+        s['inputs'].copy_(inputs, non_blocking=True)
+        s['targets'].copy_(targets, non_blocking=True)
+        if (keep_masks is None) != (s['masks'] is None):
+            raise ValueError("captured with%s dropout masks: pass keep_masks accordingly" % ("out" if s['masks'] is None else ""))
+        if keep_masks is not None:
+            for dst, src in zip(s['masks'], keep_masks):
+                dst.copy_(src, non_blocking=True)
+
     def d_step(self, inputs, targets, keep_masks=None):
+        if self.players.captured("d"):
+            self._stage(inputs, targets, keep_masks)
+            return self.players.replay("d", self.learning_rate())
         return self.players.step("d", lambda: self.d_loss(inputs, targets, keep_masks), self.learning_rate())
 
     def g_step(self, inputs, targets, keep_masks=None):
-        loss = self.players.step("g", lambda: self.g_loss(inputs, targets, keep_masks), self.learning_rate())
+        if self.players.captured("g"):
+            self._stage(inputs, targets, keep_masks)
+            loss = self.players.replay("g", self.learning_rate())
+        else:
+            loss = self.players.step("g", lambda: self.g_loss(inputs, targets, keep_masks), self.learning_rate())
         self.global_step += 1                             # gen_optim.apply_gradients(..., global_step=global_step)
         return loss
+
+    def capture(self, inputs, targets, keep_masks=None):
+        """Both training ops as CUDA graphs over static buffers shaped like the given batch (call after one eager
+        d_step and g_step with the same shapes); later d_step / g_step calls copy their arguments in and replay."""
+        self.static = {'inputs': torch.empty_like(inputs), 'targets': torch.empty_like(targets),
+                       'masks': None if keep_masks is None else [torch.empty_like(m) for m in keep_masks]}
+        s = self.static
+        self.players.capture("d", lambda: self.d_loss(s['inputs'], s['targets'], s['masks']))
+        self.players.capture("g", lambda: self.g_loss(s['inputs'], s['targets'], s['masks']))
 
     def train_iteration(self, inputs, targets, n_dis: int = 5, mask_fn=None):
         """train.py:703-729: n_dis critic steps on the batch, then the generator step.  mask_fn() -> three dropout

@@ -40,6 +40,7 @@ class TwoPlayer:
         self.world_size, self.grad_allreduce = world_size, grad_allreduce
         self.betas = (beta1, beta2, eps)
         self.opt = {}
+        self._graphs, self.graph_launches, self.graph_loss = {}, {}, {}
 
     def finalize(self) -> None:
         """Call once every variable exists: flat parameter / gradient / Adam-slot buffers per network."""
@@ -64,9 +65,75 @@ class TwoPlayer:
         if self.grad_allreduce is not None:
             self.grad_allreduce(self.store.flat[root].grads)
         self.opt[which].set_lr(lr)
+        self._update(which)          # Adam, then the bf16 operand copies follow the update
+        return loss
+
+    # ------------------------------------------------------------------------------------------ CUDA graphs
+    def _update(self, which: str) -> None:
+        root = self.roots[which]
         self.opt[which].apply(1.0 / self.world_size)
         self.store.bump(root)
         group = self.store.pack_groups.get(root)
         if group is not None and group.entries:
-            group.refresh()          # bf16 operand copies follow the update
-        return loss
+            group.refresh()
+
+    def _invalidate_sn(self) -> None:
+        """Every captured compute graph re-evaluates the spectral-norm state it uses (the host-side version cache
+        does not run at replay)."""
+        st = self.store
+        groups = list(st.sn_groups.values()) + [g for shadows in st.sn_shadow.values() for g in shadows]
+        for g in groups:
+            g.valid_for = None
+            g.fresh_for = None
+
+    def capture(self, which: str, loss_fn) -> None:
+        """Captures step(which, loss_fn, lr) into CUDA graphs.  loss_fn must read its inputs from tensors that keep
+        their addresses (the trainer's static buffers), and at least one eager step of this kind must have run
+        (workspaces, descriptor tables and operand copies exist).  With a gradient collective the compute and update
+        halves are captured separately and the all-reduce runs between them at replay; the learning rate stays a
+        device scalar written by AdamState.set_lr before each replay."""
+        st = self.store
+        for root in self.roots.values():          # operand copies are current before any compute graph runs
+            group = st.pack_groups.get(root)
+            if group is not None and group.entries:
+                group.refresh()
+        loss_out = torch.zeros(1, dtype=torch.float32, device=st.device)
+
+        def compute():
+            loss = self.gradients(which, loss_fn)
+            loss_out.copy_(loss.data.reshape(-1)[:1])
+
+        def full():
+            compute()
+            self._update(which)
+
+        parts = (("full", full),) if self.grad_allreduce is None else (("compute", compute),
+                                                                        ("update", lambda: self._update(which)))
+        torch.cuda.synchronize()
+        for name, body in parts:
+            self._invalidate_sn()
+            before = K.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[(which, name)] = g
+            self.graph_launches[(which, name)] = K.launch_count() - before
+        self._invalidate_sn()
+        self.graph_loss[which] = loss_out
+
+    def captured(self, which: str) -> bool:
+        return which in self.graph_loss
+
+    def replay(self, which: str, lr: float) -> torch.Tensor:
+        """One captured step of network `which`; returns the (static) loss scalar."""
+        self.opt[which].set_lr(lr)
+        if (which, "full") in self._graphs:
+            self._graphs[(which, "full")].replay()
+        else:
+            self._graphs[(which, "compute")].replay()
+            self.grad_allreduce(self.store.flat[self.roots[which]].grads)
+            self._graphs[(which, "update")].replay()
+        return self.graph_loss[which]
+
+    def launches(self, which: str) -> int:
+        return sum(n for (w, _), n in self.graph_launches.items() if w == which)

@@ -55,7 +55,12 @@ def acgan():
     labels = torch.from_numpy(rs.randint(0, 10, size=64).astype("int32")).cuda()
     d = timed(lambda: tr.d_step(real, labels, *tr._noise()))
     g = timed(lambda: tr.g_step(*tr._noise()))
-    return dict(config="2 ACGAN CIFAR-10, batch 64, with the WGAN-GP gradient penalty, eager", d_ms=d, g_ms=g, n_critic=5)
+    tr.capture()
+    dg = timed(lambda: tr.d_step(real, labels, *tr._noise()), warm=3, reps=20)
+    gg = timed(lambda: tr.g_step(*tr._noise()), warm=3, reps=20)
+    return dict(config="2 ACGAN CIFAR-10, batch 64, with the WGAN-GP gradient penalty, CUDA graphs", d_ms=dg, g_ms=gg,
+                n_critic=5, eager_d_ms=d, eager_g_ms=g, launches_d=tr.players.launches("d"),
+                launches_g=tr.players.launches("g"), gflop_pair=650.0 + 764.0)
 
 
 def pix2pix():
@@ -67,7 +72,12 @@ def pix2pix():
     masks = lambda: [(torch.rand(32, s, s, 512, device="cuda") < 0.5).float() for s in (2, 4, 8)]  # noqa: E731
     d = timed(lambda: tr.d_step(x, t, masks()))
     g = timed(lambda: tr.g_step(x, t, masks()))
-    return dict(config="4 Pix2Pix unet_g + unet_d 256x256, batch 32, ngf = ndf = 64, eager", d_ms=d, g_ms=g, n_critic=5,
+    tr.capture(x, t, masks())
+    dg = timed(lambda: tr.d_step(x, t, masks()), warm=3, reps=10)
+    gg = timed(lambda: tr.g_step(x, t, masks()), warm=3, reps=10)
+    return dict(config="4 Pix2Pix unet_g + unet_d 256x256, batch 32, ngf = ndf = 64, CUDA graphs", d_ms=dg, g_ms=gg,
+                n_critic=5, eager_d_ms=d, eager_g_ms=g, launches_d=tr.players.launches("d"),
+                launches_g=tr.players.launches("g"),
                 note="encoder_8's instance norm sees one pixel at 256x256 (reference quirk, DESIGN.md section 2)")
 
 
