@@ -10,8 +10,8 @@ minibatch-stddev channel, 3x3 conv over C+1 channels, lrelu, spatial mean, Linea
 Scheduling: pixel-norm + lrelu is ONE bandwidth-bound kernel that emits the bf16 tensor-core operand of the next
 convolution; `inputs_norm` (x * sqrt(2 / fan_in), conv2d.py:93-95) never touches x -- it is the alpha of the GEMM
 epilogue; the (C+1)-channel convolution behind minibatch_std runs on zero-padded operands (functional._conv2d_ragged_cin).
-`alpha` is a Python float (a placeholder fed per step in the reference, PGGAN/train.py:83); a CUDA graph captured with
-one alpha must be re-captured when it changes."""
+`alpha` (a placeholder fed per step in the reference, PGGAN/train.py:83) is a Python float or a 1-element fp32 device
+tensor; the blend kernel reads it from device memory, so a captured CUDA graph follows the tensor's value."""
 from __future__ import annotations
 
 import torch

@@ -58,10 +58,32 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------ steps
     def d_step(self, real, z, alpha):
+        if self.players.captured("d"):
+            s = self.static
+            s['real'].copy_(real, non_blocking=True)
+            s['z_d'].copy_(z, non_blocking=True)
+            s['alpha'].fill_(float(alpha))
+            return self.players.replay("d", LR)
         return self.players.step("d", lambda: self.d_loss(real, z, alpha), LR)
 
     def g_step(self, z, alpha):
+        if self.players.captured("g"):
+            self.static['z_g'].copy_(z, non_blocking=True)
+            self.static['alpha'].fill_(float(alpha))
+            return self.players.replay("g", LR)
         return self.players.step("g", lambda: self.g_loss(z, alpha), LR)
+
+    def capture(self):
+        """Both training ops as CUDA graphs over static buffers (call after one eager d_step and g_step).  alpha lives
+        in a device scalar that functional.lerp reads at run time (the placeholder of train.py:83), so the graphs
+        follow alpha = step / max_iter without being re-captured."""
+        dev = self.store.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        s = self.static = {'real': torch.zeros(self.batch, self.size, self.size, 3, **f32),
+                           'z_d': torch.zeros(self.batch, self.z_dim, **f32),
+                           'z_g': torch.zeros(self.batch, self.z_dim, **f32), 'alpha': torch.zeros(1, **f32)}
+        self.players.capture("d", lambda: self.d_loss(s['real'], s['z_d'], s['alpha']))
+        self.players.capture("g", lambda: self.g_loss(s['z_g'], s['alpha']))
 
     def train_iteration(self, step: int, batches, n_dis: int = N_DIS):
         """train.py:182-190.  `batches` yields NHWC float real images [batch, size, size, 3]."""

@@ -43,7 +43,7 @@ def _normalize_kind(name, labels):
     if CONDITIONAL and ACGAN and ('D.' in name):
         labels = None
     if ('D.' in name) and NORMALIZATION_D:
-        raise NotImplementedError('layer_norm in D (NORMALIZATION_D=True) is not built')
+        return 'ln'
     elif ('G.' in name) and NORMALIZATION_G:
         return 'cbn' if labels is not None else 'bn'
     return None

@@ -43,6 +43,20 @@ def _memo(fn):
     return get
 
 
+def pixelcnn_mask(mask_type, filter_size, input_dim, output_dim):
+    """The constant filter mask of common/ops/conv2d.py:63-81: mask_type = ('a' | 'b', n_channels)."""
+    kind, mask_n_channels = mask_type
+    mask = np.ones((filter_size, filter_size, input_dim, output_dim), dtype='float32')
+    center = filter_size // 2
+    mask[center + 1:, :, :, :] = 0.          # future rows
+    mask[center, center + 1:, :, :] = 0.     # future columns of the centre row
+    for i in range(mask_n_channels):         # future channels at the centre tap
+        for j in range(mask_n_channels):
+            if (kind == 'a' and i >= j) or (kind == 'b' and i > j):
+                mask[center, center, i::mask_n_channels, j::mask_n_channels] = 0.
+    return mask
+
+
 def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D',
            conv_type='conv2d', channel_multiplier=0, padding='SAME',
            spectral_normed=False, update_collection=None, inputs_norm=False, he_init=True,
@@ -63,8 +77,6 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
     with store.variable_scope(name):
         if conv_type != 'conv2d':
             raise NotImplementedError('{0} is not supported!'.format(conv_type))
-        if mask_type is not None:
-            raise NotImplementedError('PixelCNN masks are not built (SURVEY 8(f) rank 4)')
         if input_dim != inputs.shape[-1]:
             raise ValueError('input_dim={} but inputs have {} channels'.format(input_dim, inputs.shape[-1]))
 
@@ -73,6 +85,10 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
 
         fan_in = input_dim * filter_size ** 2
         fan_out = output_dim * filter_size ** 2 / (stride ** 2)
+        in_scale = float(np.sqrt(2.0 / fan_in)) if inputs_norm else None   # conv2d.py:93-95, before the halving below
+        if mask_type is not None:  # "only approximately correct" (conv2d.py:99-101)
+            fan_in /= 2.
+            fan_out /= 2.
         if he_init:
             filters_stdev = np.sqrt(4. / (fan_in + fan_out))
         else:  # Normalized init (Glorot & Bengio)
@@ -84,15 +100,21 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
 
         if weightnorm is None:
             weightnorm = _default_weightnorm
-        if weightnorm:
-            raise NotImplementedError('weight-norm is not built (SURVEY 8(f) rank 4)')
+        target_norms = None
+        if weightnorm:   # conv2d.py:153-163: g initialised to the norms of the INITIAL values, filters * (g / norms)
+            target_norms = store.get_variable(
+                name='g', initializer=lambda _s: np.sqrt(np.sum(np.square(filter_values()), axis=(0, 1, 2))))
+        mask_fn = None
+        if mask_type is not None:   # conv2d.py:165-167
+            mask_fn = lambda: pixelcnn_mask(mask_type, filter_size, input_dim, output_dim)  # noqa: E731
+        filters = store.effective_weight(filters, target_norms, mask_fn,
+                                         (filter_size * filter_size * input_dim, output_dim, 1))
 
         sn_entry = None
         if spectral_normed:
             with store.variable_scope('filters'):
                 sn_entry = spectral_normed_weight(filters, update_collection=update_collection).entry
 
-        in_scale = float(np.sqrt(2.0 / fan_in)) if inputs_norm else None
         _biases = None
         if biases:
             _biases = store.get_variable(name='Biases', shape=[output_dim, ],

@@ -42,13 +42,23 @@ def Deconv2D(inputs, in_channels, output_channels, filter_size, stride=2, paddin
         stdev = np.sqrt((4. if he_init else 2.) / (fan_in + fan_out))
         if _weights_stdev is not None:
             stdev = _weights_stdev
-        filters = store.get_variable(name='Filters', initializer=lambda _s: np.random.uniform(
-            low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3),
-            size=(filter_size, filter_size, output_channels, in_channels)).astype('float32') * np.float32(gain))
+        box = []
+
+        def filter_values():
+            if not box:
+                box.append(np.random.uniform(
+                    low=-stdev * np.sqrt(3), high=stdev * np.sqrt(3),
+                    size=(filter_size, filter_size, output_channels, in_channels)).astype('float32') * np.float32(gain))
+            return box[0]
+
+        filters = store.get_variable(name='Filters', initializer=lambda _s: filter_values())
         if weight_norm is None:
             weight_norm = _default_weightnorm
-        if weight_norm:
-            raise NotImplementedError('weight-norm is not built (SURVEY 8(f) rank 4)')
+        if weight_norm:   # deconv2d.py:87-96: one norm per OUTPUT channel (axis 2 of [k, k, Cout, Cin])
+            target_norms = store.get_variable(
+                name='g', initializer=lambda _s: np.sqrt(np.sum(np.square(filter_values()), axis=(0, 1, 3))))
+            filters = store.effective_weight(filters, target_norms, None,
+                                             (filter_size * filter_size, output_channels, in_channels))
         _biases = None
         if biases:
             _biases = store.get_variable(name='Biases', shape=[output_channels, ],

@@ -66,8 +66,10 @@ def Linear(inputs, input_dim, output_dim, name,
         weight = store.get_variable(name='W', initializer=lambda _s: weight_values())
         if weightnorm is None:
             weightnorm = _default_weightnorm
-        if weightnorm:
-            raise NotImplementedError('weight-norm is not built (SURVEY 8(f) rank 4)')
+        if weightnorm:   # linear.py:143-155: norms over axis 0
+            target_norms = store.get_variable(
+                name='g', initializer=lambda _s: np.sqrt(np.sum(np.square(weight_values()), axis=0)))
+            weight = store.effective_weight(weight, target_norms, None, (input_dim, output_dim, 1))
         sn_entry = None
         if spectral_normed:
             sn_entry = spectral_normed_weight(weight, update_collection=update_collection).entry

@@ -52,9 +52,18 @@ def cond_batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update
         return (out, raw) if want_raw else out
 
 
-def layer_norm(name, norm_axes, inputs):
-    """common/ops/normalization.py:62-82 -- only reachable with NORMALIZATION_D=True in the SNGAN scripts."""
-    raise NotImplementedError('layer_norm is not built (SURVEY 8(f) rank 4: unreachable with the shipped flags)')
+def layer_norm(name, norm_axes, inputs, act=None, out_dtype=torch.float32):
+    """common/ops/normalization.py:62-82: tf.contrib.layers.layer_norm(begin_norm_axis=1, begin_params_axis=-1,
+    scope=name) -- moments over (h, w, c) per sample, `beta` then `gamma` of shape [c] under the scope `name`
+    (reached with NORMALIZATION_D=True in the SNGAN scripts).  norm_axes is ignored by the reference as well.
+    `act` fuses the nonlinearity that follows it in the residual blocks."""
+    store = get_store()
+    inputs = F.as_var(inputs)
+    with store.variable_scope(name):
+        c = inputs.shape[-1]
+        beta = store.get_variable('beta', shape=[c], initializer=lambda s: np.zeros(s, dtype='float32'))
+        gamma = store.get_variable('gamma', shape=[c], initializer=lambda s: np.ones(s, dtype='float32'))
+        return F.layer_norm(inputs, gamma, beta, eps=1e-12, act=act, out_dtype=out_dtype)
 
 
 def instance_norm(inputs, epsilon=1e-06, act=None, upsample=False, out_dtype=torch.float32):

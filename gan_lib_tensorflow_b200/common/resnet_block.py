@@ -60,6 +60,16 @@ def _norm_act(name, inputs, labels, kind, act, upsample=False, want_raw=False, o
         elif kind == 'bn':
             res = _norm.batch_norm(inputs, fused=True, act=act, upsample=upsample, out_dtype=out_dtype,
                                    want_raw=want_raw)
+        elif kind == 'ln':
+            # layer norm of the critic (the SNGAN scripts' NORMALIZATION_D switch); D blocks never upsample
+            if upsample:
+                raise NotImplementedError('layer_norm in front of an upsample (no reference call-site)')
+            inputs = F.as_var(inputs)
+            out = _norm.layer_norm(name, [1, 2, 3], inputs, act=act, out_dtype=out_dtype)
+            raw = None
+            if want_raw:
+                raw = inputs if inputs.data.dtype == BF16 else F.cast(inputs, BF16)
+            return out, raw
         else:
             return F.norm_act(inputs, stats=None, act=act, upsample=upsample, out_dtype=out_dtype, want_raw=want_raw)
     return res if want_raw else (res, None)

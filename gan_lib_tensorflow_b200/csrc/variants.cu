@@ -1,0 +1,589 @@
+// Secondary layer variants of the hot path -- all bandwidth-bound, fp32 arithmetic:
+//
+//   * effective filters: weight-norm  W * (g / ||W||)  over every axis but the output-channel one, followed by the
+//     constant PixelCNN mask (common/ops/conv2d.py:63-81, 153-167; linear.py:143-155; deconv2d.py:87-96), and the
+//     backward map from dL/dW_eff to dL/dW and dL/dg;
+//   * layer norm of the critic (tf.contrib.layers.layer_norm, begin_norm_axis=1, begin_params_axis=-1,
+//     common/ops/normalization.py:62-82; reached with NORMALIZATION_D, SNGAN/gan_cifar_resnet.py:99-100) with the
+//     activation that follows it fused, forward and backward;
+//   * the fade-in blend of PGGAN (PGGAN/model_nvidia.py:118, :200) with alpha read from device memory, so a captured
+//     CUDA graph follows alpha = step / max_iter without being re-captured.
+#include "host_common.h"
+
+#include <cuda_bf16.h>
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+namespace ganb {
+
+struct alignas(8) bf16x4v {
+  __nv_bfloat162 lo, hi;
+};
+__device__ __forceinline__ float4 vld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 vld4(const __nv_bfloat16* p) {
+  const bf16x4v v = *reinterpret_cast<const bf16x4v*>(p);
+  const float2 a = __bfloat1622float2(v.lo), b = __bfloat1622float2(v.hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void vst4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void vst4(__nv_bfloat16* p, float4 v) {
+  bf16x4v o;
+  o.lo = __floats2bfloat162_rn(v.x, v.y);
+  o.hi = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<bf16x4v*>(p) = o;
+}
+__device__ __forceinline__ float vact(float v, int act) {
+  if (act == GANB_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == GANB_ACT_LRELU) return v >= 0.f ? v : 0.2f * v;
+  return v;
+}
+__device__ __forceinline__ float vdact(float z, int act) {
+  if (act == GANB_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == GANB_ACT_LRELU) return z >= 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+__device__ __forceinline__ float vwarp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Sum over the 256 threads of a block, returned to every thread.  `red` holds >= 8 floats.
+__device__ __forceinline__ float vblock_sum(float v, float* red) {
+  v = vwarp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  return s;
+}
+
+// ================================================================================================ effective filters
+// Geometry [A][C][B] (element (a, c, b) at (a*C + c)*B + b), the norm runs over a and b for every c:
+//   Conv2D Filters [k, k, Cin, Cout]  -> A = k*k*Cin, C = Cout, B = 1     (conv2d.py:154, axis (0, 1, 2))
+//   Linear W [in, out]                -> A = in,      C = out,  B = 1     (linear.py:146, axis 0)
+//   Deconv2D Filters [k, k, Cout, Cin]-> A = k*k,     C = Cout, B = Cin   (deconv2d.py:90, axes (0, 1, 3))
+// B == 1: a block owns 32 neighbouring channels x WT_ROWS rows (128-byte row segments); B > 1: a block owns one
+// channel x WT_ROWS slabs of B contiguous floats.  Two launches per direction: per-chunk partial sums, then the apply
+// kernel folds the partials of its channels (deterministic order) and streams the tile.
+constexpr int WT_ROWS = 64;
+
+template <bool kDot>
+__global__ void __launch_bounds__(256)
+wt_partial_kernel(const float* __restrict__ W, const float* __restrict__ dWe, const float* __restrict__ mask,
+                  float* __restrict__ partial, int A, int C, int B) {
+  pdl_wait();
+  __shared__ float red[256];
+  const int chunk = blockIdx.y;
+  const int a0 = chunk * WT_ROWS;
+  const int a1 = min(A, a0 + WT_ROWS);
+  float acc = 0.f;
+  if (B == 1) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (c < C) {
+      for (int a = a0 + (threadIdx.x >> 5); a < a1; a += 8) {
+        const int64_t i = static_cast<int64_t>(a) * C + c;
+        const float w = W[i];
+        if (kDot) {
+          float d = dWe[i];
+          if (mask) d *= mask[i];
+          acc += d * w;
+        } else {
+          acc += w * w;
+        }
+      }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32 && c < C) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s += red[r * 32 + threadIdx.x];
+      partial[static_cast<int64_t>(chunk) * C + c] = s;
+    }
+  } else {
+    const int c = blockIdx.x;
+    const int64_t items = static_cast<int64_t>(a1 - a0) * B;
+    for (int64_t j = threadIdx.x; j < items; j += 256) {
+      const int a = a0 + static_cast<int>(j / B), b = static_cast<int>(j % B);
+      const int64_t i = (static_cast<int64_t>(a) * C + c) * B + b;
+      const float w = W[i];
+      if (kDot) {
+        float d = dWe[i];
+        if (mask) d *= mask[i];
+        acc += d * w;
+      } else {
+        acc += w * w;
+      }
+    }
+    const float s = vblock_sum(acc, red);
+    if (threadIdx.x == 0) partial[static_cast<int64_t>(chunk) * C + c] = s;
+  }
+}
+
+// kBwd = false: We = W * (g / ||W||) * mask, norms out.      kBwd = true: dW += s*(dV - W*dot/||W||^2), dg += dot/||W||
+// with dV = dWe * mask, s = g / ||W||, dot = sum dV*W (the partials).  g == nullptr: mask only (scale 1, no norm term).
+template <bool kBwd>
+__global__ void __launch_bounds__(256)
+wt_apply_kernel(const float* __restrict__ W, const float* __restrict__ src, const float* __restrict__ g,
+                const float* __restrict__ mask, const float* __restrict__ partial, int chunks,
+                float* __restrict__ norms, float* __restrict__ dst, float* __restrict__ dg, int A, int C, int B) {
+  pdl_wait();
+  __shared__ float s_scale[32], s_coef[32];
+  const int chunk = blockIdx.y;
+  const int a0 = chunk * WT_ROWS;
+  const int a1 = min(A, a0 + WT_ROWS);
+  const int width = (B == 1) ? 32 : 1;
+  if (threadIdx.x < width) {
+    const int c = (B == 1) ? blockIdx.x * 32 + threadIdx.x : blockIdx.x;
+    float scale = 1.f, coef = 0.f;
+    if (c < C && g != nullptr) {
+      float tot = 0.f;
+      for (int k = 0; k < chunks; ++k) tot += partial[static_cast<int64_t>(k) * C + c];
+      if (!kBwd) {
+        const float nrm = sqrtf(tot);
+        scale = g[c] / nrm;
+        if (chunk == 0) norms[c] = nrm;
+      } else {
+        const float nrm = norms[c];
+        scale = g[c] / nrm;
+        coef = tot / (nrm * nrm);
+        if (chunk == 0 && dg != nullptr) dg[c] += tot / nrm;
+      }
+    }
+    s_scale[threadIdx.x] = scale;
+    s_coef[threadIdx.x] = coef;
+  }
+  __syncthreads();
+  if (B == 1) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 32 + lane;
+    if (c >= C) return;
+    const float scale = s_scale[lane], coef = s_coef[lane];
+    for (int a = a0 + (threadIdx.x >> 5); a < a1; a += 8) {
+      const int64_t i = static_cast<int64_t>(a) * C + c;
+      const float m = mask ? mask[i] : 1.f;
+      if (!kBwd) {
+        dst[i] = W[i] * scale * m;
+      } else {
+        dst[i] += scale * (src[i] * m - W[i] * coef);
+      }
+    }
+  } else {
+    const int c = blockIdx.x;
+    const float scale = s_scale[0], coef = s_coef[0];
+    const int64_t items = static_cast<int64_t>(a1 - a0) * B;
+    for (int64_t j = threadIdx.x; j < items; j += 256) {
+      const int a = a0 + static_cast<int>(j / B), b = static_cast<int>(j % B);
+      const int64_t i = (static_cast<int64_t>(a) * C + c) * B + b;
+      const float m = mask ? mask[i] : 1.f;
+      if (!kBwd) {
+        dst[i] = W[i] * scale * m;
+      } else {
+        dst[i] += scale * (src[i] * m - W[i] * coef);
+      }
+    }
+  }
+}
+
+static inline dim3 wt_grid(int A, int C, int B) {
+  return dim3(B == 1 ? ceil_div(C, 32) : C, ceil_div(A, WT_ROWS));
+}
+
+// ================================================================================================ layer norm
+// One sample = per_sample = H*W*C contiguous elements; a block owns LN_CHUNK of them (16 float4 per thread, held in
+// registers so that the chunk mean and the squared deviations around it come from ONE pass over memory).  The apply
+// kernels fold the per-chunk (count, mean, M2) triples with Chan's formula -- the two-pass accuracy of tf.nn.moments
+// without the second read.
+constexpr int LN_VEC = 16;
+constexpr int LN_CHUNK = 256 * 4 * LN_VEC;   // 16384 elements
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_stats_partial_kernel(const T* __restrict__ x, float* __restrict__ partial /*[n][splits][2]: mean, M2*/,
+                        int64_t per_sample, int splits) {
+  pdl_wait();
+  __shared__ float red[8];
+  const int s = blockIdx.x, n = blockIdx.y;
+  const int64_t begin = static_cast<int64_t>(s) * LN_CHUNK;
+  const int64_t len = min(static_cast<int64_t>(LN_CHUNK), per_sample - begin);
+  const T* xp = x + n * per_sample + begin;
+  float4 v[LN_VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_VEC; ++i) {
+    const int64_t e = (static_cast<int64_t>(i) * 256 + threadIdx.x) * 4;
+    if (e < len) {
+      v[i] = vld4(xp + e);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = vblock_sum(sum, red) / static_cast<float>(len);
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_VEC; ++i) {
+    const int64_t e = (static_cast<int64_t>(i) * 256 + threadIdx.x) * 4;
+    if (e < len) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      m2 += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  m2 = vblock_sum(m2, red);
+  if (threadIdx.x == 0) {
+    float* p = partial + (static_cast<int64_t>(n) * splits + s) * 2;
+    p[0] = mean;
+    p[1] = m2;
+  }
+}
+
+// Folds the chunk statistics of sample n: returns (mean, rstd).  Every thread of the block computes the same value
+// (splits <= a few dozen, the partials sit in L2).
+__device__ __forceinline__ float2 ln_fold(const float* __restrict__ partial, int n, int splits, int64_t per_sample,
+                                          float eps) {
+  const float* p = partial + static_cast<int64_t>(n) * splits * 2;
+  double tot = 0.0;
+  for (int k = 0; k < splits; ++k) {
+    const double cnt = static_cast<double>(min(static_cast<int64_t>(LN_CHUNK), per_sample - static_cast<int64_t>(k) * LN_CHUNK));
+    tot += cnt * p[2 * k];
+  }
+  const double mean = tot / static_cast<double>(per_sample);
+  double m2 = 0.0;
+  for (int k = 0; k < splits; ++k) {
+    const double cnt = static_cast<double>(min(static_cast<int64_t>(LN_CHUNK), per_sample - static_cast<int64_t>(k) * LN_CHUNK));
+    const double d = p[2 * k] - mean;
+    m2 += p[2 * k + 1] + cnt * d * d;
+  }
+  const float var = static_cast<float>(m2 / static_cast<double>(per_sample));
+  return make_float2(static_cast<float>(mean), rsqrtf(var + eps));
+}
+
+// y = act(x*inv + (beta - mean*inv)), inv = rstd*gamma  (tf.nn.batch_normalization's arithmetic)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+ln_fwd_apply_kernel(const TIn* __restrict__ x, const float* __restrict__ partial, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, TOut* __restrict__ y, float* __restrict__ mean_rstd /*[n][2]*/,
+                    int64_t per_sample, int splits, int c, float eps, int act) {
+  pdl_wait();
+  const int s = blockIdx.x, n = blockIdx.y;
+  const float2 mr = ln_fold(partial, n, splits, per_sample, eps);
+  if (s == 0 && threadIdx.x == 0) {
+    mean_rstd[2 * n] = mr.x;
+    mean_rstd[2 * n + 1] = mr.y;
+  }
+  const int64_t begin = static_cast<int64_t>(s) * LN_CHUNK;
+  const int64_t len = min(static_cast<int64_t>(LN_CHUNK), per_sample - begin);
+  const TIn* xp = x + n * per_sample + begin;
+  TOut* yp = y + n * per_sample + begin;
+#pragma unroll 4
+  for (int i = 0; i < LN_VEC; ++i) {
+    const int64_t e = (static_cast<int64_t>(i) * 256 + threadIdx.x) * 4;
+    if (e >= len) break;
+    const int ch = static_cast<int>((begin + e) % c);
+    const float4 xv = vld4(xp + e), gv = vld4(gamma + ch), bv = vld4(beta + ch);
+    float4 o;
+    float inv = mr.y * gv.x; o.x = vact(xv.x * inv + (bv.x - mr.x * inv), act);
+    inv = mr.y * gv.y;       o.y = vact(xv.y * inv + (bv.y - mr.x * inv), act);
+    inv = mr.y * gv.z;       o.z = vact(xv.z * inv + (bv.z - mr.x * inv), act);
+    inv = mr.y * gv.w;       o.w = vact(xv.w * inv + (bv.w - mr.x * inv), act);
+    vst4(yp + e, o);
+  }
+}
+
+// Backward, pass 1.  With xh = (x - mean)*rstd, z = xh*gamma + beta, dz = dy*act'(z), dyh = dz*gamma:
+//   per sample:  s1 = sum dyh, s2 = sum dyh*xh           -> sums[n][splits][2]
+//   per channel: dgamma += dz*xh, dbeta += dz            -> chan[2][n*splits][c]  (rows folded by ganb_colsum)
+// 1024 % c == 0, so a thread meets the same four channels in every one of its LN_VEC float4s.
+template <typename TX, typename TDY>
+__global__ void __launch_bounds__(256)
+ln_bwd_partial_kernel(const TX* __restrict__ x, const TDY* __restrict__ dy, const float* __restrict__ mean_rstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums,
+                      float* __restrict__ chan, int64_t per_sample, int splits, int c, int act, int64_t rows) {
+  pdl_wait();
+  __shared__ float red[8];
+  __shared__ float4 sg[256], sb[256];
+  const int s = blockIdx.x, n = blockIdx.y;
+  const float mean = mean_rstd[2 * n], rstd = mean_rstd[2 * n + 1];
+  const int64_t begin = static_cast<int64_t>(s) * LN_CHUNK;
+  const int64_t len = min(static_cast<int64_t>(LN_CHUNK), per_sample - begin);
+  const TX* xp = x + n * per_sample + begin;
+  const TDY* dp = dy + n * per_sample + begin;
+  const int ch = static_cast<int>((begin + threadIdx.x * 4) % c);
+  const float4 gv = vld4(gamma + ch), bv = vld4(beta + ch);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < LN_VEC; ++i) {
+    const int64_t e = (static_cast<int64_t>(i) * 256 + threadIdx.x) * 4;
+    if (e >= len) break;
+    const float4 xv = vld4(xp + e), dv = vld4(dp + e);
+    float xh, dz, dyh;
+    xh = (xv.x - mean) * rstd; dz = dv.x * vdact(xh * gv.x + bv.x, act); dyh = dz * gv.x;
+    ag.x += dz * xh; ab.x += dz; s1 += dyh; s2 += dyh * xh;
+    xh = (xv.y - mean) * rstd; dz = dv.y * vdact(xh * gv.y + bv.y, act); dyh = dz * gv.y;
+    ag.y += dz * xh; ab.y += dz; s1 += dyh; s2 += dyh * xh;
+    xh = (xv.z - mean) * rstd; dz = dv.z * vdact(xh * gv.z + bv.z, act); dyh = dz * gv.z;
+    ag.z += dz * xh; ab.z += dz; s1 += dyh; s2 += dyh * xh;
+    xh = (xv.w - mean) * rstd; dz = dv.w * vdact(xh * gv.w + bv.w, act); dyh = dz * gv.w;
+    ag.w += dz * xh; ab.w += dz; s1 += dyh; s2 += dyh * xh;
+  }
+  s1 = vblock_sum(s1, red);
+  s2 = vblock_sum(s2, red);
+  sg[threadIdx.x] = ag;
+  sb[threadIdx.x] = ab;
+  __syncthreads();
+  const int64_t row = static_cast<int64_t>(n) * splits + s;
+  if (threadIdx.x == 0) {
+    sums[row * 2] = s1;
+    sums[row * 2 + 1] = s2;
+  }
+  // channel group j (4 channels) is met by the threads t with (g0 + t) % q == j, q = c / 4, g0 = (begin / 4) % q
+  const int q = c >> 2;
+  if (threadIdx.x < q) {
+    const int j = threadIdx.x;
+    const int g0 = static_cast<int>((begin >> 2) % q);
+    const int first = ((j - g0) % q + q) % q;
+    float4 tg = make_float4(0.f, 0.f, 0.f, 0.f), tb = tg;
+    for (int t = first; t < 256; t += q) {
+      const float4 a = sg[t], b = sb[t];
+      tg.x += a.x; tg.y += a.y; tg.z += a.z; tg.w += a.w;
+      tb.x += b.x; tb.y += b.y; tb.z += b.z; tb.w += b.w;
+    }
+    vst4(chan + row * c + j * 4, tg);
+    vst4(chan + (rows + row) * c + j * 4, tb);
+  }
+}
+
+// Backward, pass 2: dx = rstd * (dyh - mean(dyh) - xh * mean(dyh*xh))
+template <typename TX, typename TDY, typename TDX>
+__global__ void __launch_bounds__(256)
+ln_bwd_apply_kernel(const TX* __restrict__ x, const TDY* __restrict__ dy, const float* __restrict__ mean_rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums,
+                    TDX* __restrict__ dx, int64_t per_sample, int splits, int c, int act) {
+  pdl_wait();
+  const int s = blockIdx.x, n = blockIdx.y;
+  const float mean = mean_rstd[2 * n], rstd = mean_rstd[2 * n + 1];
+  double t1 = 0.0, t2 = 0.0;
+  for (int k = 0; k < splits; ++k) {
+    t1 += sums[(static_cast<int64_t>(n) * splits + k) * 2];
+    t2 += sums[(static_cast<int64_t>(n) * splits + k) * 2 + 1];
+  }
+  const float m1 = static_cast<float>(t1 / static_cast<double>(per_sample));
+  const float m2 = static_cast<float>(t2 / static_cast<double>(per_sample));
+  const int64_t begin = static_cast<int64_t>(s) * LN_CHUNK;
+  const int64_t len = min(static_cast<int64_t>(LN_CHUNK), per_sample - begin);
+  const TX* xp = x + n * per_sample + begin;
+  const TDY* dp = dy + n * per_sample + begin;
+  TDX* op = dx + n * per_sample + begin;
+  const int ch = static_cast<int>((begin + threadIdx.x * 4) % c);
+  const float4 gv = vld4(gamma + ch), bv = vld4(beta + ch);
+#pragma unroll 4
+  for (int i = 0; i < LN_VEC; ++i) {
+    const int64_t e = (static_cast<int64_t>(i) * 256 + threadIdx.x) * 4;
+    if (e >= len) break;
+    const float4 xv = vld4(xp + e), dv = vld4(dp + e);
+    float4 o;
+    float xh;
+    xh = (xv.x - mean) * rstd; o.x = rstd * (dv.x * vdact(xh * gv.x + bv.x, act) * gv.x - m1 - xh * m2);
+    xh = (xv.y - mean) * rstd; o.y = rstd * (dv.y * vdact(xh * gv.y + bv.y, act) * gv.y - m1 - xh * m2);
+    xh = (xv.z - mean) * rstd; o.z = rstd * (dv.z * vdact(xh * gv.z + bv.z, act) * gv.z - m1 - xh * m2);
+    xh = (xv.w - mean) * rstd; o.w = rstd * (dv.w * vdact(xh * gv.w + bv.w, act) * gv.w - m1 - xh * m2);
+    vst4(op + e, o);
+  }
+}
+
+static inline int ln_splits(int64_t per_sample) { return static_cast<int>(ceil_div64(per_sample, LN_CHUNK)); }
+static inline bool ln_shape_ok(int64_t per_sample, int c) {
+  return c >= 4 && c <= 1024 && (1024 % c) == 0 && per_sample % c == 0;
+}
+
+// ================================================================================================ fade-in blend
+__global__ void __launch_bounds__(256)
+lerp_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n,
+                const float* __restrict__ alpha) {
+  pdl_wait();
+  const float t = *alpha, u = 1.f - t;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    const float4 p = vld4(a + i * 4), q = vld4(b + i * 4);
+    vst4(y + i * 4, make_float4(u * p.x + t * q.x, u * p.y + t * q.y, u * p.z + t * q.z, u * p.w + t * q.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    y[i] = u * a[i] + t * b[i];
+  }
+}
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+lerp_bwd_kernel(const float* __restrict__ dy, TA* __restrict__ da, TB* __restrict__ db, int64_t n,
+                const float* __restrict__ alpha) {
+  pdl_wait();
+  const float t = *alpha, u = 1.f - t;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    const float4 g = vld4(dy + i * 4);
+    if (da) vst4(da + i * 4, make_float4(u * g.x, u * g.y, u * g.z, u * g.w));
+    if (db) vst4(db + i * 4, make_float4(t * g.x, t * g.y, t * g.z, t * g.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    if (da) da[i] = static_cast<TA>(u * dy[i]);
+    if (db) db[i] = static_cast<TB>(t * dy[i]);
+  }
+}
+
+static inline int flat_grid(int64_t items) {
+  int64_t b = ceil_div64(items, 256);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (b > cap) b = cap;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+
+}  // namespace ganb
+
+using namespace ganb;
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int64_t ganb_weight_transform_workspace(int a, int c) {
+  return static_cast<int64_t>(ceil_div(a, WT_ROWS)) * c * 4;
+}
+
+extern "C" int ganb_weight_transform_fwd(const float* w, const float* g, const float* mask, float* w_eff, float* norms,
+                                         void* workspace, int a, int c, int b, void* stream) {
+  if (!w || !w_eff) return fail(GANB_E_BADARG, "weight_transform_fwd: null buffer");
+  if (a < 1 || c < 1 || b < 1) return fail(GANB_E_BADARG, "weight_transform_fwd: bad geometry %d x %d x %d", a, c, b);
+  if (g && (!norms || !workspace)) return fail(GANB_E_BADARG, "weight_transform_fwd: weight-norm needs norms + workspace");
+  const dim3 grid = wt_grid(a, c, b);
+  float* partial = static_cast<float*>(workspace);
+  if (g) {
+    launch_k(wt_partial_kernel<false>, grid, 256, 0, STREAM, w, static_cast<const float*>(nullptr), mask, partial, a, c, b);
+    GANB_CHECK_LAUNCH("wt_partial_kernel<fwd>");
+  }
+  launch_k(wt_apply_kernel<false>, grid, 256, 0, STREAM, w, static_cast<const float*>(nullptr), g, mask,
+           static_cast<const float*>(partial), static_cast<int>(grid.y), norms, w_eff, static_cast<float*>(nullptr), a, c, b);
+  GANB_CHECK_LAUNCH("wt_apply_kernel<fwd>");
+  return 0;
+}
+
+extern "C" int ganb_weight_transform_bwd(const float* w, const float* dw_eff, const float* g, const float* mask,
+                                         const float* norms, float* dw, float* dg, void* workspace, int a, int c, int b,
+                                         void* stream) {
+  if (!w || !dw_eff || !dw) return fail(GANB_E_BADARG, "weight_transform_bwd: null buffer");
+  if (a < 1 || c < 1 || b < 1) return fail(GANB_E_BADARG, "weight_transform_bwd: bad geometry %d x %d x %d", a, c, b);
+  if (g && (!norms || !workspace)) return fail(GANB_E_BADARG, "weight_transform_bwd: weight-norm needs norms + workspace");
+  const dim3 grid = wt_grid(a, c, b);
+  float* partial = static_cast<float*>(workspace);
+  if (g) {
+    launch_k(wt_partial_kernel<true>, grid, 256, 0, STREAM, w, dw_eff, mask, partial, a, c, b);
+    GANB_CHECK_LAUNCH("wt_partial_kernel<bwd>");
+  }
+  launch_k(wt_apply_kernel<true>, grid, 256, 0, STREAM, w, dw_eff, g, mask, static_cast<const float*>(partial),
+           static_cast<int>(grid.y), const_cast<float*>(norms), dw, dg, a, c, b);
+  GANB_CHECK_LAUNCH("wt_apply_kernel<bwd>");
+  return 0;
+}
+
+extern "C" int64_t ganb_layer_norm_workspace(int n, int64_t per_sample, int c) {
+  // forward: [n][splits][2] chunk statistics; backward: [n][splits][2] sums + [2][n*splits][c] channel partials
+  const int64_t rows = static_cast<int64_t>(n) * ln_splits(per_sample);
+  return rows * 2 * 4 + 2 * rows * c * 4 + 64;
+}
+
+extern "C" int64_t ganb_layer_norm_rows(int n, int64_t per_sample) {
+  return static_cast<int64_t>(n) * ln_splits(per_sample);
+}
+
+extern "C" int ganb_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                                   float* mean_rstd, void* workspace, int n, int64_t per_sample, int c, float eps, int act,
+                                   void* stream) {
+  if (!x || !gamma || !beta || !y || !mean_rstd || !workspace) return fail(GANB_E_BADARG, "layer_norm_fwd: null buffer");
+  if (n < 1 || !ln_shape_ok(per_sample, c))
+    return fail(GANB_E_UNSUPPORTED, "layer_norm_fwd: channels must divide 1024 (got c=%d, %lld per sample)", c,
+                static_cast<long long>(per_sample));
+  const int splits = ln_splits(per_sample);
+  const dim3 grid(splits, n);
+  float* partial = static_cast<float*>(workspace);
+#define LN_FWD(TI, TO)                                                                                                 \
+  do {                                                                                                                 \
+    launch_k(ln_stats_partial_kernel<TI>, grid, 256, 0, STREAM, static_cast<const TI*>(x), partial, per_sample, splits); \
+    GANB_CHECK_LAUNCH("ln_stats_partial_kernel");                                                                      \
+    launch_k(ln_fwd_apply_kernel<TI, TO>, grid, 256, 0, STREAM, static_cast<const TI*>(x),                            \
+             static_cast<const float*>(partial), gamma, beta, static_cast<TO*>(y), mean_rstd, per_sample, splits, c,  \
+             eps, act);                                                                                                \
+    GANB_CHECK_LAUNCH("ln_fwd_apply_kernel");                                                                          \
+    return 0;                                                                                                          \
+  } while (0)
+  if (x_dtype == GANB_F32 && y_dtype == GANB_F32) LN_FWD(float, float);
+  if (x_dtype == GANB_F32 && y_dtype == GANB_BF16) LN_FWD(float, __nv_bfloat16);
+  if (x_dtype == GANB_BF16 && y_dtype == GANB_F32) LN_FWD(__nv_bfloat16, float);
+  LN_FWD(__nv_bfloat16, __nv_bfloat16);
+#undef LN_FWD
+}
+
+namespace ganb {
+template <typename TX, typename TDY>
+static int ln_bwd_launch(const void* x, const void* dy, const float* mean_rstd, const float* gamma, const float* beta,
+                         void* dx, int dx_dtype, float* sums, float* chan, int n, int64_t per_sample, int c, int act,
+                         cudaStream_t s) {
+  const int splits = ln_splits(per_sample);
+  const dim3 grid(splits, n);
+  const int64_t rows = static_cast<int64_t>(n) * splits;
+  launch_k(ln_bwd_partial_kernel<TX, TDY>, grid, 256, 0, s, static_cast<const TX*>(x), static_cast<const TDY*>(dy),
+           mean_rstd, gamma, beta, sums, chan, per_sample, splits, c, act, rows);
+  GANB_CHECK_LAUNCH("ln_bwd_partial_kernel");
+  if (dx == nullptr) return 0;
+  if (dx_dtype == GANB_F32) {
+    launch_k(ln_bwd_apply_kernel<TX, TDY, float>, grid, 256, 0, s, static_cast<const TX*>(x),
+             static_cast<const TDY*>(dy), mean_rstd, gamma, beta, static_cast<const float*>(sums),
+             static_cast<float*>(dx), per_sample, splits, c, act);
+  } else {
+    launch_k(ln_bwd_apply_kernel<TX, TDY, __nv_bfloat16>, grid, 256, 0, s, static_cast<const TX*>(x),
+             static_cast<const TDY*>(dy), mean_rstd, gamma, beta, static_cast<const float*>(sums),
+             static_cast<__nv_bfloat16*>(dx), per_sample, splits, c, act);
+  }
+  GANB_CHECK_LAUNCH("ln_bwd_apply_kernel");
+  return 0;
+}
+}  // namespace ganb
+
+extern "C" int ganb_layer_norm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* mean_rstd,
+                                   const float* gamma, const float* beta, void* dx, int dx_dtype, float* chan_partials,
+                                   void* workspace, int n, int64_t per_sample, int c, int act, void* stream) {
+  if (!x || !dy || !mean_rstd || !gamma || !beta || !chan_partials || !workspace)
+    return fail(GANB_E_BADARG, "layer_norm_bwd: null buffer");
+  if (n < 1 || !ln_shape_ok(per_sample, c))
+    return fail(GANB_E_UNSUPPORTED, "layer_norm_bwd: channels must divide 1024 (got c=%d)", c);
+  float* sums = static_cast<float*>(workspace);
+  if (x_dtype == GANB_F32 && dy_dtype == GANB_F32)
+    return ln_bwd_launch<float, float>(x, dy, mean_rstd, gamma, beta, dx, dx_dtype, sums, chan_partials, n, per_sample, c, act, STREAM);
+  if (x_dtype == GANB_F32 && dy_dtype == GANB_BF16)
+    return ln_bwd_launch<float, __nv_bfloat16>(x, dy, mean_rstd, gamma, beta, dx, dx_dtype, sums, chan_partials, n, per_sample, c, act, STREAM);
+  if (x_dtype == GANB_BF16 && dy_dtype == GANB_F32)
+    return ln_bwd_launch<__nv_bfloat16, float>(x, dy, mean_rstd, gamma, beta, dx, dx_dtype, sums, chan_partials, n, per_sample, c, act, STREAM);
+  return ln_bwd_launch<__nv_bfloat16, __nv_bfloat16>(x, dy, mean_rstd, gamma, beta, dx, dx_dtype, sums, chan_partials, n, per_sample, c, act, STREAM);
+}
+
+extern "C" int ganb_lerp_fwd(const float* a, const float* b, float* y, int64_t count, const float* alpha, void* stream) {
+  if (!a || !b || !y || !alpha) return fail(GANB_E_BADARG, "lerp_fwd: null buffer");
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return fail(GANB_E_BADARG, "lerp_fwd: buffers must be 16-byte aligned");
+  launch_k(lerp_fwd_kernel, flat_grid(count / 4 + 1), 256, 0, STREAM, a, b, y, count, alpha);
+  GANB_CHECK_LAUNCH("lerp_fwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_lerp_bwd(const float* dy, void* da, int da_dtype, void* db, int db_dtype, int64_t count,
+                             const float* alpha, void* stream) {
+  if (!dy || !alpha || (!da && !db)) return fail(GANB_E_BADARG, "lerp_bwd: null buffer");
+  const int grid = flat_grid(count / 4 + 1);
+#define LERP_BWD(TA, TB)                                                                                             \
+  launch_k(lerp_bwd_kernel<TA, TB>, grid, 256, 0, STREAM, dy, static_cast<TA*>(da), static_cast<TB*>(db), count, alpha)
+  if (da_dtype == GANB_F32 && db_dtype == GANB_F32) LERP_BWD(float, float);
+  else if (da_dtype == GANB_F32) LERP_BWD(float, __nv_bfloat16);
+  else if (db_dtype == GANB_F32) LERP_BWD(__nv_bfloat16, float);
+  else LERP_BWD(__nv_bfloat16, __nv_bfloat16);
+#undef LERP_BWD
+  GANB_CHECK_LAUNCH("lerp_bwd_kernel");
+  return 0;
+}

@@ -107,6 +107,53 @@ class Variable(Var):
         writer(self.grad, 1.0)
 
 
+class DerivedWeight(Variable):
+    """Filters after weight-norm and / or a constant mask: W_eff = W * (g / ||W||) * mask (common/ops/conv2d.py:153-167,
+    linear.py:143-155, deconv2d.py:87-96).  Layers (and the spectral-norm / operand-pack groups) see it as the weight;
+    `data` is recomputed when the network's version moves, `grad` collects dL/dW_eff during a backward pass and
+    Tape.backward maps it onto W.grad / g.grad at the end (after the spectral-norm backward, which also adds into
+    `grad`).  geom = (a, c, b) of include/ganb200.h."""
+
+    __slots__ = ("src", "gvar", "mask", "geom", "norms", "valid_for", "tape_token")
+
+    def __init__(self, src: Variable, gvar, mask, geom):
+        super().__init__(src.key + ":effective", torch.empty_like(src.data), False, src.store)
+        self.root = src.root
+        self.src, self.gvar, self.mask, self.geom = src, gvar, mask, geom
+        self.norms = torch.empty(geom[1], dtype=torch.float32, device=src.data.device) if gvar is not None else None
+        self.grad = torch.zeros_like(self.data)
+        self.valid_for = None
+        self.tape_token = None
+
+    @property
+    def needs_grad(self):
+        return self.src.needs_grad
+
+    def refresh(self) -> None:
+        ver = self.store.version(self.root)
+        if self.valid_for == ver:
+            return
+        K.weight_transform_fwd(self.src.data, None if self.gvar is None else self.gvar.data, self.mask, self.data,
+                               self.norms, *self.geom)
+        self.valid_for = ver
+
+    def attach(self) -> None:
+        """Called by the layer on every use: on a recording tape the first use clears `grad` and books the backward map."""
+        st = self.store
+        if st.tape is None or not self.needs_grad or self.tape_token == st.tape_token:
+            return
+        self.tape_token = st.tape_token
+        self.grad.zero_()
+        st.tape.pending_derived.append(self)
+
+    def backward(self) -> None:
+        for v in (self.src, self.gvar):
+            if v is not None and v.grad is None:
+                v.grad = torch.zeros_like(v.data)
+        K.weight_transform_bwd(self.src.data, self.grad, None if self.gvar is None else self.gvar.data, self.mask,
+                               self.norms, self.src.grad, None if self.gvar is None else self.gvar.grad, *self.geom)
+
+
 SIDE_STREAM = os.environ.get("GANB_SIDE_STREAM", "1") != "0"
 _side_streams = {}
 
@@ -130,6 +177,7 @@ class Tape:
         self.nodes = []
         self.store = store
         self.pending_sn = OrderedDict()  # root -> list of SN entries whose G buffer has been written
+        self.pending_derived = []        # DerivedWeight instances used on this tape (weight-norm / masks)
         self.keep = []       # temporaries read by side-stream launches: kept alive until the join
         self._forked = False
 
@@ -172,6 +220,10 @@ class Tape:
             for group, es in by_group.values():
                 group.backward(es)
         self.pending_sn.clear()
+        for d in self.pending_derived:   # dL/dW_eff (incl. the spectral-norm part) -> dL/dW, dL/dg
+            d.backward()
+            d.tape_token = None
+        self.pending_derived.clear()
 
 
 class FlatGroup:
@@ -386,6 +438,9 @@ class PackGroup:
         if self.valid_for == ver:
             return
         entries = list(self.entries.values())
+        for e in entries:
+            if isinstance(e.w, DerivedWeight):
+                e.w.refresh()        # the operand copies are taken from the effective filters
         if self.table is None or self.table_ptrs != self._ptrs():
             items, tiles = [], 0
             for e in entries:
@@ -420,6 +475,7 @@ class VariableStore:
         self._sn_gen: dict[str, int] = {}
         self.tape_token = 0
         self.pack_groups: dict[str, PackGroup] = {}
+        self.derived: dict[str, DerivedWeight] = {}
         self.flat: dict[str, FlatGroup] = {}
         self.u_rng = np.random.RandomState(u_seed)
         self.tape: Tape | None = None
@@ -556,6 +612,22 @@ class VariableStore:
         if self.tape is not None:
             group.used_token = self.tape_token
         return entry
+
+    def effective_weight(self, w: Variable, gvar=None, mask=None, geom=None) -> Variable:
+        """The weight a layer multiplies with: `w` itself, or its DerivedWeight when weight-norm (gvar) and / or a
+        constant mask apply.  Current on return; registered with the recording tape."""
+        if gvar is None and mask is None:
+            return w
+        d = self.derived.get(w.key)
+        if d is None:
+            if callable(mask):
+                mask = mask()
+            if mask is not None and not torch.is_tensor(mask):
+                mask = torch.from_numpy(np.ascontiguousarray(mask, dtype=np.float32)).to(self.device)
+            d = self.derived[w.key] = DerivedWeight(w, gvar, mask, geom)
+        d.refresh()
+        d.attach()
+        return d
 
     def pack_group(self, root) -> PackGroup:
         g = self.pack_groups.get(root)

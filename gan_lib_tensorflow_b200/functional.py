@@ -122,15 +122,16 @@ def add_scalars(a: Var, b: Var) -> Var:
     return out
 
 
-def lerp(a: Var, b: Var, alpha: float) -> Var:
-    """(1 - alpha) * a + alpha * b in fp32: the fade-in of PGGAN (PGGAN/model_nvidia.py:118, :200)."""
-    alpha = float(alpha)
+def lerp(a: Var, b: Var, alpha) -> Var:
+    """(1 - alpha) * a + alpha * b in fp32: the fade-in of PGGAN (PGGAN/model_nvidia.py:118, :200).  alpha: a Python
+    float, or a 1-element fp32 device tensor (the placeholder of PGGAN/train.py:83 -- a captured CUDA graph then
+    follows the value written into it)."""
+    if not torch.is_tensor(alpha):
+        alpha = torch.full((1,), float(alpha), dtype=F32, device=a.data.device)
     a32 = a if a.data.dtype == F32 else cast(a, F32)
     b32 = b if b.data.dtype == F32 else cast(b, F32)
     assert a32.shape == b32.shape
-    data = K.cast(a32.data, F32, scale=1.0 - alpha)   # scaled copy
-    K.axpby(b32.data, data, alpha, 1.0)
-    out = Var(data)
+    out = Var(K.lerp_fwd(a32.data, b32.data, alpha))
     if _rg(a32, b32):
         out.requires_grad = True
 
@@ -138,9 +139,13 @@ def lerp(a: Var, b: Var, alpha: float) -> Var:
             g = out.grad
             if g is None:
                 return
-            for v, s in ((a32, 1.0 - alpha), (b32, alpha)):
-                if v.requires_grad:
-                    v.accum(K.cast(g, v.gdtype, scale=s))
+            g = g if g.dtype == F32 else K.cast(g, F32)
+            da, db = K.lerp_bwd(g, alpha, a32.gdtype if a32.requires_grad else None,
+                                b32.gdtype if b32.requires_grad else None)
+            if da is not None:
+                a32.accum(da)
+            if db is not None:
+                b32.accum(db)
         _tape().record(bwd)
     return out
 
@@ -526,6 +531,28 @@ def linear(x: Var, W: Variable, b: Variable | None, sn=None, out_dtype=F32, in_s
 
 
 # ------------------------------------------------------------------------------------------------ norm + act
+def layer_norm(x: Var, gamma: Variable, beta: Variable, eps: float = 1e-12, act=None, out_dtype=BF16,
+               out_grad_dtype=None) -> Var:
+    """act(tf.contrib.layers.layer_norm(x, begin_norm_axis=1, begin_params_axis=-1)): per-sample moments over (h, w, c),
+    per-channel gamma / beta (common/ops/normalization.py:62-82; variance_epsilon 1e-12 is contrib's constant)."""
+    y, mr = K.layer_norm_fwd(x.data, gamma.data, beta.data, eps, act, out_dtype)
+    out = Var(y, grad_dtype=out_grad_dtype)
+    need_p = gamma.needs_grad and _tape() is not None
+    if _rg(x) or need_p:
+        out.requires_grad = True
+
+        def bwd():
+            gz = out.grad
+            if gz is None or not (x.requires_grad or need_p):
+                return
+            dx = K.layer_norm_bwd(x.data, gz, mr, gamma.data, beta.data, act, x.gdtype if x.requires_grad else None,
+                                  gamma.grad if need_p else None, beta.grad if need_p else None)
+            if dx is not None:
+                x.accum(dx)
+        _tape().record(bwd)
+    return out
+
+
 def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | None = None,
              beta: Variable | None = None, labels: torch.Tensor | None = None, act=None, upsample: bool = False,
              out_dtype=BF16, want_raw: bool = False, groups: int | None = None, out_grad_dtype=None):

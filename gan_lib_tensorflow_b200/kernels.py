@@ -41,7 +41,8 @@ def L():
         _L = cabi.lib()
         for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace",
                      "ganb_norm_act_bwd_sums_offset", "ganb_l1_loss_workspace", "ganb_bn_bwd_vjp_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
-                     "ganb_minibatch_std_workspace",
+                     "ganb_minibatch_std_workspace", "ganb_weight_transform_workspace", "ganb_layer_norm_workspace",
+                     "ganb_layer_norm_rows",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
     return _L
@@ -462,3 +463,68 @@ def sn_bwd(table_dev, count, total_blocks, max_c):
 
 def pack_weights(table_dev, count, total_tiles):
     check(L().ganb_pack_weights(ptr(table_dev), count, total_tiles, _stream()), "ganb_pack_weights")
+
+
+# ------------------------------------------------------------------------------------------------ secondary variants
+def weight_transform_fwd(w, g, mask, w_eff, norms, a, c, b):
+    """w_eff = w * (g / ||w||) * mask over geometry [a][c][b] (include/ganb200.h); g / mask may be None."""
+    ws = _ws(L().ganb_weight_transform_workspace(a, c), w.device) if g is not None else None
+    check(L().ganb_weight_transform_fwd(ptr(w), ptr(g), ptr(mask), ptr(w_eff), ptr(norms), ptr(ws), a, c, b, _stream()),
+          "ganb_weight_transform_fwd")
+
+
+def weight_transform_bwd(w, dw_eff, g, mask, norms, dw, dg, a, c, b):
+    """Adds the gradients of weight_transform_fwd into dw (and dg)."""
+    ws = _ws(L().ganb_weight_transform_workspace(a, c), w.device) if g is not None else None
+    check(L().ganb_weight_transform_bwd(ptr(w), ptr(dw_eff), ptr(g), ptr(mask), ptr(norms), ptr(dw), ptr(dg), ptr(ws),
+                                        a, c, b, _stream()), "ganb_weight_transform_bwd")
+
+
+def layer_norm_fwd(x, gamma, beta, eps, act, out_dtype):
+    """Per-sample moments over (h, w, c), y = act(batch_normalization(x, mean, var, beta, gamma, eps)).
+    Returns (y, mean_rstd [n, 2])."""
+    n, c = x.shape[0], x.shape[-1]
+    per = x.numel() // n
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    mr = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+    ws = _ws(L().ganb_layer_norm_workspace(n, c_int64(per), c), x.device)
+    check(L().ganb_layer_norm_fwd(ptr(x), dt(x), ptr(gamma), ptr(beta), ptr(y), dt(y), ptr(mr), ptr(ws), n, c_int64(per),
+                                  c, c_float(eps), act_code(act), _stream()), "ganb_layer_norm_fwd")
+    return y, mr
+
+
+def layer_norm_bwd(x, dy, mean_rstd, gamma, beta, act, dx_dtype, dgamma, dbeta):
+    """Returns dx (None when dx_dtype is None); adds into dgamma / dbeta (either may be None)."""
+    n, c = x.shape[0], x.shape[-1]
+    per = x.numel() // n
+    rows = int(L().ganb_layer_norm_rows(n, c_int64(per)))
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device) if dx_dtype is not None else None
+    chan = torch.empty((2, rows, c), dtype=torch.float32, device=x.device)
+    ws = _ws(L().ganb_layer_norm_workspace(n, c_int64(per), c), x.device)
+    check(L().ganb_layer_norm_bwd(ptr(x), dt(x), ptr(dy), dt(dy), ptr(mean_rstd), ptr(gamma), ptr(beta), ptr(dx),
+                                  dt(dx) if dx is not None else F32, ptr(chan), ptr(ws), n, c_int64(per), c,
+                                  act_code(act), _stream()), "ganb_layer_norm_bwd")
+    if dgamma is not None:
+        colsum(chan[0], rows, c, dgamma, 1.0)
+    if dbeta is not None:
+        colsum(chan[1], rows, c, dbeta, 1.0)
+    return dx
+
+
+def lerp_fwd(a, b, alpha_dev):
+    """(1 - alpha) * a + alpha * b, fp32, alpha a device scalar."""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape
+    y = torch.empty_like(a)
+    check(L().ganb_lerp_fwd(ptr(a), ptr(b), ptr(y), c_int64(a.numel()), ptr(alpha_dev), _stream()), "ganb_lerp_fwd")
+    return y
+
+
+def lerp_bwd(dy, alpha_dev, da_dtype, db_dtype):
+    """((1 - alpha) * dy, alpha * dy); a dtype of None skips that output."""
+    assert dy.dtype == torch.float32
+    da = torch.empty(dy.shape, dtype=da_dtype, device=dy.device) if da_dtype is not None else None
+    db = torch.empty(dy.shape, dtype=db_dtype, device=dy.device) if db_dtype is not None else None
+    check(L().ganb_lerp_bwd(ptr(dy), ptr(da), dt(da) if da is not None else F32, ptr(db),
+                            dt(db) if db is not None else F32, c_int64(dy.numel()), ptr(alpha_dev), _stream()),
+          "ganb_lerp_bwd")
+    return da, db

@@ -342,6 +342,44 @@ int ganb_bn_bwd_vjp(const float* x, const float* gy, const float* cot, const flo
                     const float* gamma, const float* beta, int64_t pixels, int c, int act, float* dx, float* dgy,
                     float* dgamma, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Secondary layer variants, all bandwidth-bound fp32 arithmetic.
+ *
+ * Effective filters: W_eff = W * (g / ||W||) * mask with the norm over every axis but the output-channel one
+ *   (weight-norm: common/ops/conv2d.py:153-163, linear.py:143-155, deconv2d.py:87-96; PixelCNN mask: conv2d.py:63-81,
+ *   165-167).  Geometry [a][c][b], element (i, ch, j) at (i*c + ch)*b + j, the norm runs over i and j:
+ *   Conv2D Filters [k,k,Cin,Cout] -> (k*k*Cin, Cout, 1); Linear W [in,out] -> (in, out, 1);
+ *   Deconv2D Filters [k,k,Cout,Cin] -> (k*k, Cout, Cin).  g == NULL: mask only; mask == NULL: weight-norm only.
+ *   fwd writes w_eff and norms[c]; bwd ADDS into dw and dg:  dV = dw_eff*mask, dot = sum dV*W,
+ *   dw += (g/||W||) * (dV - W*dot/||W||^2), dg += dot/||W||.  workspace: ganb_weight_transform_workspace(a, c) bytes.
+ *
+ * Layer norm of the critic: tf.contrib.layers.layer_norm(begin_norm_axis=1, begin_params_axis=-1), i.e. moments over
+ *   (h, w, c) per sample with tf.nn.moments, then tf.nn.batch_normalization(x, mean, var, beta[c], gamma[c], 1e-12)
+ *   (common/ops/normalization.py:62-82, reached through SNGAN/gan_cifar_resnet.py:99-100), followed by `act`
+ *   (common/resnet_block.py:24-29) in the same pass.  per_sample = h*w*c, 1024 % c == 0.  fwd writes y and
+ *   mean_rstd[n][2]; bwd writes dx (may be NULL) and chan_partials[2][rows][c] (rows = ganb_layer_norm_rows), whose
+ *   column sums (ganb_colsum) are dgamma and dbeta.  workspace: ganb_layer_norm_workspace bytes for either direction.
+ *
+ * Fade-in blend of PGGAN ((1 - alpha)*a + alpha*b, PGGAN/model_nvidia.py:118, :200) with alpha in DEVICE memory (the
+ *   reference feeds it per step, PGGAN/train.py:83, 184), so that captured CUDA graphs follow it.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ganb_weight_transform_workspace(int a, int c);
+int ganb_weight_transform_fwd(const float* w, const float* g, const float* mask, float* w_eff, float* norms,
+                              void* workspace, int a, int c, int b, void* stream);
+int ganb_weight_transform_bwd(const float* w, const float* dw_eff, const float* g, const float* mask, const float* norms,
+                              float* dw, float* dg, void* workspace, int a, int c, int b, void* stream);
+int64_t ganb_layer_norm_workspace(int n, int64_t per_sample, int c);
+int64_t ganb_layer_norm_rows(int n, int64_t per_sample);
+int ganb_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                        float* mean_rstd, void* workspace, int n, int64_t per_sample, int c, float eps, int act,
+                        void* stream);
+int ganb_layer_norm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* mean_rstd,
+                        const float* gamma, const float* beta, void* dx, int dx_dtype, float* chan_partials,
+                        void* workspace, int n, int64_t per_sample, int c, int act, void* stream);
+int ganb_lerp_fwd(const float* a, const float* b, float* y, int64_t count, const float* alpha, void* stream);
+int ganb_lerp_bwd(const float* dy, void* da, int da_dtype, void* db, int db_dtype, int64_t count, const float* alpha,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -231,15 +231,28 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
     mirrors the product's sub-pixel evaluation (subpixel_upconv_rounded)."""
     if conv_type != "conv2d":
         raise NotImplementedError("{0} is not supported by the oracle".format(conv_type))
-    if mask_type is not None:
-        raise NotImplementedError("PixelCNN masks are out of scope (SURVEY 8(f) rank 4)")
     with g.variable_scope(name):
+        mask = None
+        if mask_type is not None:                                     # conv2d.py:63-81
+            kind, mask_n_channels = mask_type
+            mask = np.ones((filter_size, filter_size, input_dim, output_dim), dtype="float32")
+            center = filter_size // 2
+            mask[center + 1:, :, :, :] = 0.0
+            mask[center, center + 1:, :, :] = 0.0
+            for i in range(mask_n_channels):
+                for j in range(mask_n_channels):
+                    if (kind == "a" and i >= j) or (kind == "b" and i > j):
+                        mask[center, center, i::mask_n_channels, j::mask_n_channels] = 0.0
         fan_in = input_dim * filter_size ** 2                         # conv2d.py:90
         fan_out = output_dim * filter_size ** 2 / (stride ** 2)       # conv2d.py:91
+        inv_c = float(np.sqrt(2.0 / fan_in))
         if inputs_norm:                                               # conv2d.py:93-97
-            inputs_ = inputs * float(np.sqrt(2.0 / fan_in))
+            inputs_ = inputs * inv_c
         else:
             inputs_ = inputs
+        if mask_type is not None:                                     # conv2d.py:99-101
+            fan_in /= 2.0
+            fan_out /= 2.0
         if he_init:                                                   # conv2d.py:103-106
             filters_stdev = np.sqrt(4.0 / (fan_in + fan_out))
         else:
@@ -254,6 +267,8 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
             target_norms = g.get_variable("g", initializer=norm_values)
             norms = torch.sqrt(torch.sum(filters ** 2, dim=(0, 1, 2)))
             filters = filters * (target_norms / norms)
+        if mask is not None:                                          # conv2d.py:165-167
+            filters = filters * torch.as_tensor(mask, dtype=filters.dtype)
         raw_filters = filters
         if spectral_normed:                                           # conv2d.py:169-171
             with g.variable_scope("filters"):
@@ -274,7 +289,7 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
             if inputs_norm:
                 # the product keeps the constant outside the tensor-core contraction (the epilogue's alpha):
                 # c * conv(r16(x), r16(W)) -- same value in exact arithmetic, the rounding point moves
-                result = _ConvRoundedOperands.apply(inputs, wq, stride, padding, float(np.sqrt(2.0 / fan_in)))
+                result = _ConvRoundedOperands.apply(inputs, wq, stride, padding, inv_c)
             else:
                 result = _ConvRoundedOperands.apply(inputs_, wq, stride, padding)
         else:
@@ -432,6 +447,8 @@ def layer_norm(g, name, norm_axes, inputs):
         c = inputs.shape[-1]
         beta = g.get_variable("beta", initializer=tfshim.constant_initializer(0.0), shape=[c])
         gamma = g.get_variable("gamma", initializer=tfshim.constant_initializer(1.0), shape=[c])
+        if BF16_OPERANDS:
+            inputs = _ste_r16(inputs)   # the B200 path keeps Conv1's output (the input of N2) in bf16
         red = tuple(range(1, inputs.dim()))
         mean = inputs.mean(dim=red, keepdim=True)
         var = inputs.var(dim=red, unbiased=False, keepdim=True)

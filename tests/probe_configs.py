@@ -89,8 +89,12 @@ def pggan():
     z = lambda: torch.randn(16, 512, device="cuda")  # noqa: E731
     d = timed(lambda: tr.d_step(real, z(), 0.5))
     g = timed(lambda: tr.g_step(z(), 0.5))
-    return dict(config="5 PGGAN nvidia 256x256, block_count 6, trans, inputs_norm, batch 16, alpha 0.5, eager",
-                d_ms=d, g_ms=g, n_critic=5)
+    tr.capture()
+    dg = timed(lambda: tr.d_step(real, z(), 0.5), warm=3, reps=10)
+    gg = timed(lambda: tr.g_step(z(), 0.5), warm=3, reps=10)
+    return dict(config="5 PGGAN nvidia 256x256, block_count 6, trans, inputs_norm, batch 16, alpha 0.5, CUDA graphs "
+                       "(alpha in a device scalar)", d_ms=dg, g_ms=gg, n_critic=5, eager_d_ms=d, eager_g_ms=g,
+                launches_d=tr.players.launches("d"), launches_g=tr.players.launches("g"))
 
 
 def main():

@@ -1,0 +1,305 @@
+"""GPU parity tests for the secondary layer variants: weight-norm of Conv2D / conv2d_.Conv2D /
+Linear / Deconv2D (common/ops/conv2d.py:153-163, linear.py:143-155, deconv2d.py:87-96), PixelCNN masks
+(conv2d.py:63-81, 165-167), layer norm of the critic (normalization.py:62-82, NORMALIZATION_D), the PGGAN fade-in
+with alpha in device memory and the CUDA-graph capture of the PGGAN training ops that it enables.  Same protocol as
+test_gpu_ops.py: CUDA path through the C ABI against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from tests.test_gpu_graphs import Snapshot, _compare, _state
+from tests.test_gpu_ops import TOL_F32, _bf16_repr, check, env, rel, run_pair  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _g_values(cout, seed):
+    """Target norms away from their initial value (= the norms of the initial filters), so that g / ||W|| != 1."""
+    return (0.5 + np.random.RandomState(seed).uniform(size=cout)).astype("float32")
+
+
+# ------------------------------------------------------------------------------------------------ weight-norm
+@pytest.mark.parametrize("n,h,cin,cout,k,sn,module", [
+    (4, 16, 64, 64, 3, False, "conv2d"),
+    (3, 8, 72, 40, 3, True, "conv2d"),       # ragged channels; spectral norm of the weight-normed filters
+    (5, 16, 3, 128, 3, False, "conv2d"),     # RGB side (im2col route takes its operand from the effective filters)
+    (2, 16, 128, 256, 1, False, "conv2d_"),
+])
+def test_weightnorm_conv2d(env, n, h, cin, cout, k, sn, module):
+    store, tfshim = env
+    import importlib
+
+    P = importlib.import_module("gan_lib_tensorflow_b200.common.ops." + module)
+    from oracle import ops as O
+
+    x = np.random.RandomState(1).standard_normal((n, h, h, cin)).astype("float32")
+    gv = _g_values(cout, 2)
+
+    def prod_fn(xv):
+        with store.variable_scope("L"):
+            store.get_variable("g", initializer=gv)
+        return P.Conv2D(xv, cin, cout, k, name="L", weightnorm=True, spectral_normed=sn, update_collection="NO_OPS")
+
+    def orc_fn(g, xt):
+        with g.variable_scope("L"):
+            g.get_variable("g", initializer=gv)
+        return O.Conv2D(g, xt, cin, cout, k, name="L", weightnorm=True, spectral_normed=sn,
+                        update_collection="NO_OPS")
+
+    prod, refs = run_pair(store, tfshim, prod_fn, orc_fn, x)
+    assert "L/g" in refs["fp32"]["params"] and "L/Filters" in refs["fp32"]["params"]
+    check(prod, refs, tag=f"weightnorm {module} {cin}->{cout} k{k} sn={sn}")
+
+
+def test_weightnorm_initial_g_is_the_initial_norm(env):
+    """conv2d.py:154-158: g starts at the norms of the initial filter values, so the first forward pass is the plain
+    convolution."""
+    store, _ = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+
+    x = torch.from_numpy(np.random.RandomState(3).standard_normal((2, 8, 8, 64)).astype("float32")).cuda()
+    np.random.seed(0)
+    a = P.Conv2D(F.Var(x), 64, 64, 3, name="A", weightnorm=True)
+    np.random.seed(0)
+    b = P.Conv2D(F.Var(x), 64, 64, 3, name="B", weightnorm=False)
+    torch.cuda.synchronize()
+    w = store.vars["A/Filters"].data
+    assert rel(store.vars["A/g"].data.cpu().numpy(), w.pow(2).sum(dim=(0, 1, 2)).sqrt().cpu().numpy()) < 1e-6
+    assert rel(a.data.float().cpu().numpy(), b.data.float().cpu().numpy()) < 5e-3   # W*(g/|W|) rounds differently
+
+
+def test_weightnorm_linear(env):
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import linear as PL
+    from oracle import ops as O
+
+    # Linear: norms over axis 0 (linear.py:146)
+    x = np.random.RandomState(4).standard_normal((32, 300)).astype("float32")
+    gv = _g_values(128, 5)
+
+    def prod_fn(xv):
+        with store.variable_scope("Lin"):
+            store.get_variable("g", initializer=gv)
+        return PL.Linear(xv, 300, 128, "Lin", weightnorm=True)
+
+    def orc_fn(g, xt):
+        with g.variable_scope("Lin"):
+            g.get_variable("g", initializer=gv)
+        return O.Linear(g, xt, 300, 128, "Lin", weightnorm=True)
+
+    prod, refs = run_pair(store, tfshim, prod_fn, orc_fn, x)
+    check(prod, refs, tag="weightnorm linear")
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k", [(4, 8, 128, 64, 4), (3, 5, 72, 40, 4)])
+def test_weightnorm_deconv2d(env, n, h, cin, cout, k):
+    """deconv2d.py:87-96: one norm per OUTPUT channel = axis 2 of [k, k, Cout, Cin] (geometry with an inner axis)."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import deconv2d as P
+    from oracle import ops as O
+
+    x = _bf16_repr(np.random.RandomState(43).standard_normal((n, h, h, cin)).astype("float32"))
+    cot = _bf16_repr(np.random.RandomState(44).standard_normal((n, 2 * h, 2 * h, cout)).astype("float32"))
+    gv = _g_values(cout, 6)
+
+    def prod_fn(xv):
+        with store.variable_scope("L"):
+            store.get_variable("g", initializer=gv)
+        return P.Deconv2D(xv, cin, cout, k, name="L", weight_norm=True)
+
+    def orc_fn(g, xt):
+        with g.variable_scope("L"):
+            g.get_variable("g", initializer=gv)
+        return O.Deconv2D(g, xt, cin, cout, k, name="L", weight_norm=True)
+
+    prod, refs = run_pair(store, tfshim, prod_fn, orc_fn, x, cot_np=cot, bf16=False)
+    check(prod, refs, tag=f"weightnorm deconv {cin}->{cout}")   # effective filters are not bf16-representable: 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ PixelCNN masks
+@pytest.mark.parametrize("mask_type,cin,cout,k,weightnorm", [
+    (("a", 1), 64, 64, 3, False),
+    (("b", 1), 64, 128, 5, False),
+    (("a", 3), 72, 48, 3, False),      # three colour channels interleaved over the channel axis
+    (("b", 3), 72, 72, 3, True),       # mask applied after weight-norm (conv2d.py:153-167)
+])
+def test_masked_conv2d(env, mask_type, cin, cout, k, weightnorm):
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+    from oracle import ops as O
+
+    x = np.random.RandomState(7).standard_normal((3, 8, 8, cin)).astype("float32")
+
+    def prod_fn(xv):
+        return P.Conv2D(xv, cin, cout, k, name="L", mask_type=mask_type, weightnorm=weightnorm)
+
+    def orc_fn(g, xt):
+        return O.Conv2D(g, xt, cin, cout, k, name="L", mask_type=mask_type, weightnorm=weightnorm)
+
+    prod, refs = run_pair(store, tfshim, prod_fn, orc_fn, x)
+    check(prod, refs, tag=f"mask {mask_type} {cin}->{cout} k{k} wn={weightnorm}")
+    # causality: masked taps receive no gradient and the output at (0, 0) of a type-'a' mask sees nothing but the bias
+    m = P.pixelcnn_mask(mask_type, k, cin, cout)
+    dW = prod["params"]["L/Filters"]
+    assert np.all(dW[m == 0] == 0.0)
+    # same initial values as the oracle (the halved fans of conv2d.py:99-101)
+    np.random.seed(0)
+    g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    O.Conv2D(g, torch.from_numpy(x), cin, cout, k, name="L", mask_type=mask_type, weightnorm=weightnorm)
+    w_o = dict(g.trainable_variables())["L/Filters"].detach().numpy()
+    assert np.array_equal(store.vars["L/Filters"].data.cpu().numpy(), w_o)
+
+
+# ------------------------------------------------------------------------------------------------ layer norm
+@pytest.mark.parametrize("shape,act,xdtype", [
+    ((8, 16, 16, 128), "relu", torch.float32),
+    ((5, 8, 8, 128), None, torch.float32),
+    ((3, 32, 32, 64), "lrelu", torch.bfloat16),
+    ((2, 4, 4, 256), "relu", torch.float32),
+    ((64, 8, 8, 128), "relu", torch.bfloat16),
+])
+def test_layer_norm_act(env, shape, act, xdtype):
+    """tf.contrib.layers.layer_norm(begin_norm_axis=1, begin_params_axis=-1) + the activation behind it, forward and
+    backward (dx, dgamma, dbeta) against the float64 oracle."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.common.ops import normalization as P
+    from oracle import ops as O
+
+    rs = np.random.RandomState(8)
+    c = shape[-1]
+    x = (rs.standard_normal(shape) * 1.7 + 0.3).astype("float32")
+    if xdtype == torch.bfloat16:
+        x = _bf16_repr(x)
+    cot = rs.standard_normal(shape).astype("float32")
+    gam = (1.0 + 0.3 * rs.standard_normal(c)).astype("float32")
+    bet = (0.2 * rs.standard_normal(c)).astype("float32")
+
+    with store.variable_scope("LN"):
+        store.get_variable("beta", initializer=bet)
+        store.get_variable("gamma", initializer=gam)
+    xv = F.Var(torch.from_numpy(x).cuda().to(xdtype), requires_grad=True, grad_dtype=torch.float32)
+    with store.gradient_tape() as tape:
+        out = P.layer_norm("LN", [1, 2, 3], xv, act=act, out_dtype=torch.float32)
+        for v in store.vars.values():
+            if v.trainable and v.grad is None:
+                v.grad = torch.zeros_like(v.data)
+        tape.backward(out, grad=torch.from_numpy(cot).cuda())
+    torch.cuda.synchronize()
+
+    g = tfshim.Graph(dtype=torch.float64, u_seed=2)
+    with g.variable_scope("LN"):
+        g.get_variable("beta", initializer=bet.astype("float64"))
+        g.get_variable("gamma", initializer=gam.astype("float64"))
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    yo = O.layer_norm(g, "LN", [1, 2, 3], xt)
+    if act == "relu":
+        yo = torch.relu(yo)
+    elif act == "lrelu":
+        yo = torch.maximum(yo, 0.2 * yo)
+    params = dict(g.trainable_variables())
+    dx, dgam, dbet = torch.autograd.grad(yo, [xt, params["LN/gamma"], params["LN/beta"]],
+                                         torch.from_numpy(cot).double())
+    errs = dict(out=rel(out.data.cpu().numpy(), yo.detach().numpy()), dx=rel(xv.grad.float().cpu().numpy(), dx.numpy()),
+                dgamma=rel(store.vars["LN/gamma"].grad.cpu().numpy(), dgam.numpy()),
+                dbeta=rel(store.vars["LN/beta"].grad.cpu().numpy(), dbet.numpy()))
+    print("layer_norm", shape, act, errs)
+    for k, v in errs.items():
+        assert v < 5e-5, (k, v)
+
+
+def test_layer_normed_critic_block(env):
+    """A 'down' residual block of the critic with NORMALIZATION_D (gan_cifar_resnet.py:99-100, 259-270)."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as PS
+    from oracle import sngan_cifar as OS
+    from tests.test_gpu_ops import TOL_BLOCK_FP32, TOL_BLOCK_IMPL
+
+    x = _bf16_repr(np.random.RandomState(9).standard_normal((4, 16, 16, 128)).astype("float32"))
+    old_p, old_o = PS.NORMALIZATION_D, OS.NORMALIZATION_D
+    PS.NORMALIZATION_D = OS.NORMALIZATION_D = True
+    try:
+        def prod_fn(xv):
+            return PS._block(xv, 128, 128, 3, "D.Block.2", resample="down", spectral_normed=True,
+                             update_collection="NO_OPS")
+
+        def orc_fn(g, xt):
+            return OS._block(g, xt, 128, 128, 3, "D.Block.2", resample="down", spectral_normed=True,
+                             update_collection="NO_OPS")
+
+        prod, refs = run_pair(store, tfshim, prod_fn, orc_fn, x)
+    finally:
+        PS.NORMALIZATION_D, OS.NORMALIZATION_D = old_p, old_o
+    assert any(k.endswith("N1/gamma") for k in refs["fp32"]["params"]), list(refs["fp32"]["params"])
+    check(prod, refs, tol_impl=TOL_BLOCK_IMPL, tol_fp32=TOL_BLOCK_FP32, tag="layer-normed D block")
+
+
+# ------------------------------------------------------------------------------------------------ fade-in
+def test_lerp_device_alpha(env):
+    store, _ = env
+    from gan_lib_tensorflow_b200 import functional as F
+
+    rs = np.random.RandomState(10)
+    a = rs.standard_normal((3, 8, 8, 40)).astype("float32")
+    b = rs.standard_normal((3, 8, 8, 40)).astype("float32")
+    cot = rs.standard_normal(a.shape).astype("float32")
+    alpha = torch.zeros(1, device="cuda")
+    for val in (0.0, 0.3, 1.0):
+        alpha.fill_(val)
+        av = F.Var(torch.from_numpy(a).cuda(), requires_grad=True)
+        bv = F.Var(torch.from_numpy(b).cuda().bfloat16(), requires_grad=True)
+        with store.gradient_tape() as tape:
+            out = F.lerp(av, bv, alpha)
+            tape.backward(out, grad=torch.from_numpy(cot).cuda())
+        torch.cuda.synchronize()
+        b16 = _bf16_repr(b)
+        assert rel(out.data.cpu().numpy(), (1 - val) * a + val * b16) < 1e-6
+        assert rel(av.grad.float().cpu().numpy(), (1 - val) * cot) < (1e-6 if av.grad.dtype == torch.float32 else 4e-3) \
+            or val == 1.0
+        assert rel(bv.grad.float().cpu().numpy(), val * cot) < 4e-3 or val == 0.0
+        if val == 1.0:
+            assert float(av.grad.float().abs().max()) == 0.0
+        if val == 0.0:
+            assert float(bv.grad.float().abs().max()) == 0.0
+    # a Python float is the same op
+    out2 = F.lerp(F.Var(torch.from_numpy(a).cuda()), F.Var(torch.from_numpy(b).cuda()), 0.25)
+    assert rel(out2.data.cpu().numpy(), 0.75 * a + 0.25 * b) < 1e-6
+
+
+def test_pggan_captured_steps_follow_alpha(env):
+    """PGGAN training ops as CUDA graphs (PGGAN/train.py:83, 184: alpha is fed per step): a replay with a NEW alpha
+    must reproduce the eager step at that alpha from the same state."""
+    store, _ = env
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+
+    b = 4
+    tr = PT.Trainer(block_count=2, trans=True, inputs_norm=True, batch_size=b, seed=0)
+    rs = np.random.RandomState(11)
+    real = torch.from_numpy(rs.uniform(-1, 1, size=(b, tr.size, tr.size, 3)).astype("float32")).cuda()
+    z = torch.from_numpy(rs.standard_normal((b, tr.z_dim)).astype("float32")).cuda()
+    tr.d_step(real, z, 0.1)
+    tr.g_step(z, 0.1)
+    snap = Snapshot(store, tr.players, tr)
+
+    ld = float(tr.d_step(real, z, 0.7).data.reshape(-1)[0])
+    d_eager = _state(store, "d_net")
+    lg = float(tr.g_step(z, 0.7).data.reshape(-1)[0])
+    g_eager = _state(store, "g_net")
+
+    snap.restore()
+    tr.capture()                      # captured while alpha holds 0.0
+    snap.restore()
+    assert tr.players.captured("d") and tr.players.captured("g")
+    ld_g = float(tr.d_step(real, z, 0.7).reshape(-1)[0])
+    d_graph = _state(store, "d_net")
+    lg_g = float(tr.g_step(z, 0.7).reshape(-1)[0])
+    g_graph = _state(store, "g_net")
+    print(f"pggan losses eager {ld:.6f} {lg:.6f} graph {ld_g:.6f} {lg_g:.6f}")
+    assert abs(ld - ld_g) < 1e-4 * max(1.0, abs(ld)) and abs(lg - lg_g) < 1e-4 * max(1.0, abs(lg))
+    _compare("pggan d_step", d_eager, d_graph)
+    _compare("pggan g_step", g_eager, g_graph)
+    # and a different alpha gives a different loss from the same state
+    snap.restore()
+    ld_other = float(tr.d_step(real, z, 0.2).reshape(-1)[0])
+    assert abs(ld_other - ld_g) > 1e-6
