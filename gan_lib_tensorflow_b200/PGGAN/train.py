@@ -20,9 +20,15 @@ Z_DIM = 512      # --z_dim
 class Trainer:
     def __init__(self, block_count: int, trans: bool, inputs_norm: bool = False, batch_size: int = 16,
                  z_dim: int = Z_DIM, max_iter: int = 100000, seed: int | None = 0, world_size: int = 1,
-                 grad_allreduce=None):
+                 grad_allreduce=None, model: str = "nvidia"):
         self.store = get_store()
-        self.model = PGGAN(block_count=block_count, trans=trans, inputs_norm=inputs_norm)
+        if model == "nvidia":                    # train.py:61-66 (--model)
+            self.model = PGGAN(block_count=block_count, trans=trans, inputs_norm=inputs_norm)
+        elif model == "resnet":
+            from .model_resnet import PGGAN as PGGANResNet
+            self.model = PGGANResNet(block_count=block_count, trans=trans, inputs_norm=inputs_norm)
+        else:
+            raise NotImplementedError('Not supported model!')
         self.batch, self.z_dim, self.max_iter = batch_size, z_dim, max_iter
         self.size = 4 * 2 ** block_count
         if seed is not None:

@@ -1,5 +1,6 @@
 """Pix2Pix U-Net generator and PatchGAN discriminator on the B200 layer ops, with the reference's function names,
-arguments and variable scopes (Pix2Pix/networks.py:25-43, 174-354).
+arguments and variable scopes (Pix2Pix/networks.py:25-43, 174-354; the 512x512 pair unet_generator /
+unet_discriminator of :359-536 is the same graph one level deeper).
 
 Graph kept from the reference:
   * unet_g: encoder_1 = 4x4 s2 SAME conv; encoder_2..8 = lrelu -> 4x4 s2 conv -> instance norm; decoder_8..2 =
@@ -47,8 +48,23 @@ def _conv(inputs, out_channels, stride, padding, spectral_normed=False, update_c
 
 def unet_g(generator_inputs, generator_outputs_channels, ngf, conv_type='conv2d', channel_multiplier=0, padding='SAME',
            upsampe_method='depth_to_space', keep_masks=None):
-    """Pix2Pix/networks.py:174-284.  keep_masks: three fp32 {0,1} tensors for the dropout of decoder_8/7/6 (None
-    disables dropout, i.e. keep_prob = 1)."""
+    """Pix2Pix/networks.py:174-284 (8 encoders: 256x256 -> 1x1).  keep_masks: three fp32 {0,1} tensors for the dropout
+    of decoder_8/7/6 (None disables dropout, i.e. keep_prob = 1)."""
+    return _unet(generator_inputs, generator_outputs_channels, ngf, conv_type, channel_multiplier, padding,
+                 upsampe_method, keep_masks, deep=4)
+
+
+def unet_generator(generator_inputs, generator_outputs_channels, ngf, conv_type='conv2d', channel_multiplier=0,
+                   padding='SAME', upsampe_method='depth_to_space', keep_masks=None):
+    """Pix2Pix/networks.py:359-472: the 512x512 U-Net -- one more ngf*8 encoder (encoder_9: 2x2 -> 1x1) and decoder
+    (decoder_9 .. decoder_7 carry the dropout) than unet_g, otherwise the same graph."""
+    return _unet(generator_inputs, generator_outputs_channels, ngf, conv_type, channel_multiplier, padding,
+                 upsampe_method, keep_masks, deep=5)
+
+
+def _unet(generator_inputs, generator_outputs_channels, ngf, conv_type, channel_multiplier, padding, upsampe_method,
+          keep_masks, deep):
+    """`deep` = number of ngf*8 encoders after encoder_4 (4: unet_g, 5: unet_generator)."""
     if upsampe_method not in ('depth_to_space', 'resize'):
         raise NotImplementedError('upsampe_method [%s] is not recognized' % upsampe_method)  # both are nearest 2x
     store = get_store()
@@ -56,14 +72,13 @@ def unet_g(generator_inputs, generator_outputs_channels, ngf, conv_type='conv2d'
     with store.variable_scope("encoder_1"):
         layers.append(_conv(F.as_var(generator_inputs), ngf, 2, padding, conv_type=conv_type,
                             channel_multiplier=channel_multiplier))
-    for out_channels in (ngf * 2, ngf * 4, ngf * 8, ngf * 8, ngf * 8, ngf * 8, ngf * 8):
+    for out_channels in (ngf * 2, ngf * 4, ngf * 8) + (ngf * 8,) * deep:
         with store.variable_scope("encoder_%d" % (len(layers) + 1)):
             rectified = _act(layers[-1], 'lrelu')
             convolved = _conv(rectified, out_channels, 2, padding, conv_type=conv_type,
                               channel_multiplier=channel_multiplier)
             layers.append(norm_layer(convolved, decay=0.9, epsilon=1e-5, is_training=True, norm_type="IN"))
-    layer_specs = [(ngf * 8, 0.5), (ngf * 8, 0.5), (ngf * 8, 0.5), (ngf * 8, 0.0), (ngf * 4, 0.0), (ngf * 2, 0.0),
-                   (ngf, 0.0)]
+    layer_specs = [(ngf * 8, 0.5)] * 3 + [(ngf * 8, 0.0)] * (deep - 3) + [(ngf * 4, 0.0), (ngf * 2, 0.0), (ngf, 0.0)]
     num_encoder_layers = len(layers)
     for decoder_layer, (out_channels, dropout) in enumerate(layer_specs):
         skip_layer = num_encoder_layers - decoder_layer - 1
@@ -89,10 +104,22 @@ def unet_g(generator_inputs, generator_outputs_channels, ngf, conv_type='conv2d'
 def unet_d(discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, conv_type='conv2d',
            channel_multiplier=0, padding='VALID'):
     """Pix2Pix/networks.py:287-354: 70x70 PatchGAN; every convolution is tf.pad(1) + 4x4 `padding` conv."""
+    return _patchgan(discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, conv_type,
+                     channel_multiplier, padding, n_layers=3)
+
+
+def unet_discriminator(discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, conv_type='conv2d',
+                       channel_multiplier=0, padding='VALID'):
+    """Pix2Pix/networks.py:475-536: the 512x512 PatchGAN -- n_layers = 4 (one more stride-2 layer, ndf*8 twice)."""
+    return _patchgan(discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, conv_type,
+                     channel_multiplier, padding, n_layers=4)
+
+
+def _patchgan(discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, conv_type, channel_multiplier,
+              padding, n_layers):
     if padding != 'VALID':
-        raise NotImplementedError("unet_d is built for padding='VALID' (Pix2Pix/train.py:466, 476, 499)")
+        raise NotImplementedError("the PatchGAN is built for padding='VALID' (Pix2Pix/train.py:466, 476, 499)")
     store = get_store()
-    n_layers = 3
     a, b = F.as_var(discrim_inputs), F.as_var(discrim_targets)
     inputs = F.concat_channels(a, b)
     pad1 = (1, 1, 1, 1)   # tf.pad [[0,0],[1,1],[1,1],[0,0]] folded into the convolution's zero fill

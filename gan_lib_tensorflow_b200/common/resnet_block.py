@@ -18,6 +18,7 @@ from .. import functional as F
 from ..framework import Var, get_store
 from . import ops as _ops  # noqa: F401  (keeps `lib.ops.<module>` attribute access working)
 from .ops import conv2d as _conv2d
+from .ops import linear as _linear
 from .ops import normalization as _norm
 
 NORMALIZATION_G = True
@@ -160,9 +161,14 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
             # residual stream (ACGAN's batch-normed D) is rounded once here; statistics, normalise and the shortcut
             # operand then read 2-byte elements, the identity shortcut keeps the fp32 tensor
             n1_in = F.cast(x32, BF16)
-        a1, raw = _norm_act(name + '.N1', n1_in, labels, kind(name + '.N1'), activation_fn,
-                            upsample=(resample == 'up' and not subpixel), want_raw=not identity_shortcut,
-                            n_labels=n_labels)
+        if kind(name + '.N1') is None and input_dim % 4 and resample != 'up':
+            # an RGB-sided block (D.*_fromRGB of the ResNet PGGAN critic, resnet_block.py:283-311): the activation
+            # runs on the flat fp32 tensor and both small-channel convolutions read fp32
+            a1, raw = F.activation(x32 if x32.data.dtype == F32 else F.cast(x32, F32), activation_fn), x32
+        else:
+            a1, raw = _norm_act(name + '.N1', n1_in, labels, kind(name + '.N1'), activation_fn,
+                                upsample=(resample == 'up' and not subpixel), want_raw=not identity_shortcut,
+                                n_labels=n_labels)
 
     # ---- shortcut (reference order: the shortcut variables are created before Conv1's)
     if identity_shortcut:
@@ -222,3 +228,73 @@ def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
 def get_dim(stage):
     """common/resnet_block.py:188-189 (returns a float under Python 3 in the reference; int here)."""
     return int(min(2048 / (2 ** stage), 512))
+
+
+def Generator_PGGAN(noise, bc, trans=False, alpha=0.01, inputs_norm=False, labels=None, training=True):
+    """common/resnet_block.py:192-263 -- the ResNet PGGAN generator (PGGAN/model_resnet.py:24-39): Linear to
+    [n, 4, 4, 1024], batch norm + relu, 3x3 conv, bc 'up' residual blocks of get_dim(i) channels, a toRGB residual
+    block, batch norm + relu, 3x3 conv to RGB, tanh.  With `trans` the last 'up' block + toRGB1 block is blended
+    with toRGB2 = a residual block over the nearest-2x upsample of the previous stage (fade-in over FEATURE maps, :237).
+    alpha: Python float or 1-element device tensor (functional.lerp)."""
+    noise = F.as_var(noise)
+    output = _linear.Linear(noise, noise.shape[-1], 4 * 4 * 1024, 'G.Input', inputs_norm=inputs_norm, biases=True,
+                            initialization=None, out_dtype=BF16)
+    output = F.reshape(output, (-1, 4, 4, 1024))
+    output, _ = _norm_act('G.N0', output, labels, _normalize_kind('G.N0', labels, True), 'relu')
+    output = _conv2d.Conv2D(output, output.shape[-1], 1024, 3, 1, 'G.Conv', he_init=True, biases=True)
+
+    def block(x, out_dim, name, resample):
+        return ResidualBlock(x, x.shape[-1], out_dim, 3, name, inputs_norm=inputs_norm, resample=resample, labels=labels)
+
+    for i in range(bc - 1):
+        output = block(output, get_dim(i), 'G.UpBlock.{}'.format(i + 1), 'up')
+    if trans:
+        toRGB1 = block(output, get_dim(bc - 1), 'G.UpBlock.{}'.format(bc), 'up')
+        toRGB1 = block(toRGB1, get_dim(bc - 1), 'G.{}_toRGB1'.format(bc), None)
+        # tf.image.resize_nearest_neighbor to toRGB1's size = nearest 2x
+        toRGB2 = F.upsample2(F.as_var(output))
+        toRGB2 = block(toRGB2, get_dim(bc - 1), 'G.{}_toRGB2'.format(bc), None)
+        toRGB = F.lerp(toRGB2, toRGB1, alpha)       # fade in
+    else:
+        toRGB = block(output, get_dim(bc - 1), 'G.UpBlock.{}'.format(bc), 'up') if bc > 0 else output
+        toRGB = block(toRGB, get_dim(bc - 1), 'G.{}_toRGB'.format(bc), None)
+    toRGB = F.as_var(toRGB)
+    if toRGB.data.dtype == F32:
+        toRGB = F.cast(toRGB, BF16)       # input of a batch-statistics normalisation (DESIGN.md "Data layout")
+    output, _ = _norm_act('G.Output_Normalize', toRGB, labels, _normalize_kind('G.Output_Normalize', labels, True),
+                          'relu')
+    output = _conv2d.Conv2D(output, output.shape[-1], 3, 3, 1, 'G.Output', he_init=False)
+    return F.activation(output, 'tanh')
+
+
+def Discriminator_PGGAN(x_var, c_var, bc, trans=False, alpha=0.01, inputs_norm=False, labels=None,
+                        update_collection=None, reuse=False):
+    """common/resnet_block.py:266-349 -- the ResNet PGGAN critic: a fromRGB residual block (3 -> get_dim(bc-1), no
+    resampling), bc 'down' blocks, D.NoneBlock, relu, spatial mean, spectrally-normalised Linear.  With `trans` the
+    skip path runs a second fromRGB block over the image resized (nearest) to half its size and the two FEATURE maps
+    are blended (:294).  Every layer is spectrally normalised, so Normalize is the identity (:34-36).  c_var is unused
+    by the reference as well."""
+    del c_var, labels
+    kw = dict(spectral_normed=True, update_collection=update_collection, inputs_norm=inputs_norm, biases=True)
+    x_var = F.as_var(x_var)
+    if trans:
+        fromRGB1 = ResidualBlock(x_var, 3, get_dim(bc - 1), 3, 'D.{}_fromRGB1'.format(bc), resample=None, **kw)
+        fromRGB1 = ResidualBlock(fromRGB1, get_dim(bc - 1), get_dim(bc - 1), 3, 'D.DownBlock.{}'.format(bc),
+                                 resample='down', **kw)
+        fromRGB2 = F.subsample2(x_var)         # tf.image.resize_nearest_neighbor to fromRGB1's size: x[:, ::2, ::2]
+        fromRGB2 = ResidualBlock(fromRGB2, 3, get_dim(bc - 1), 3, 'D.{}_fromRGB2'.format(bc), resample=None, **kw)
+        x_code = F.lerp(fromRGB2, fromRGB1, alpha)
+    else:
+        x_code = ResidualBlock(x_var, 3, get_dim(bc - 1), 3, 'D.{}_fromRGB'.format(bc), resample=None, **kw)
+        if bc > 0:
+            x_code = ResidualBlock(x_code, get_dim(bc - 1), get_dim(bc - 1), 3, 'D.DownBlock.{}'.format(bc),
+                                   resample='down', **kw)
+    for i in range(1, bc):
+        x_code = ResidualBlock(x_code, x_code.shape[-1], get_dim(bc - 1 - i), 3, 'D.DownBlock.{}'.format(bc - i),
+                               resample='down', **kw)
+    output = ResidualBlock(x_code, x_code.shape[-1], get_dim(0), 3, 'D.NoneBlock', resample=None, **kw)
+    output = F.act_mean_hw(output, 'relu')      # nonlinearity + tf.reduce_mean(axis=[1, 2])
+    logits = _linear.Linear(output, output.shape[-1], 1, 'D.Output', spectral_normed=True,
+                            update_collection=update_collection, inputs_norm=inputs_norm, biases=True,
+                            initialization=None)
+    return F.reshape(logits, (-1,))

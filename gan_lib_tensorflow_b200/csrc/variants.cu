@@ -7,7 +7,10 @@
 //     common/ops/normalization.py:62-82; reached with NORMALIZATION_D, SNGAN/gan_cifar_resnet.py:99-100) with the
 //     activation that follows it fused, forward and backward;
 //   * the fade-in blend of PGGAN (PGGAN/model_nvidia.py:118, :200) with alpha read from device memory, so a captured
-//     CUDA graph follows alpha = step / max_iter without being re-captured.
+//     CUDA graph follows alpha = step / max_iter without being re-captured;
+//   * tf.image.resize_nearest_neighbor to HALF the size (the skip path of the ResNet PGGAN critic,
+//     common/resnet_block.py:286-287): y[i, j] = x[2i, 2j], and its gradient (zeros off the sampled grid), for any
+//     channel count (the critic's input is RGB).
 #include "host_common.h"
 
 #include <cuda_bf16.h>
@@ -433,6 +436,33 @@ lerp_bwd_kernel(const float* __restrict__ dy, TA* __restrict__ da, TB* __restric
   }
 }
 
+// ================================================================================================ nearest 1/2 resize
+// Forward (kScatter = false): y[n, i, j, :] = x[n, i*s, j*s, :], y is [n, oh, ow, c], x is [n, h, w, c].
+// Backward (kScatter = true): y[n, I, J, :] = (I % s == 0 && J % s == 0) ? x[n, I/s, J/s, :] : 0, y is [n, oh, ow, c].
+// One thread per output element (gather on both sides, coalesced writes); tensors on this path are RGB-sized.
+template <typename TIn, typename TOut, bool kScatter>
+__global__ void __launch_bounds__(256)
+subsample2d_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int h, int w, int c, int oh, int ow, int stride,
+                   int64_t total) {
+  pdl_wait();
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int ch = static_cast<int>(i % c);
+    int64_t p = i / c;
+    const int oj = static_cast<int>(p % ow);
+    p /= ow;
+    const int oi = static_cast<int>(p % oh);
+    const int64_t img = p / oh;
+    float v = 0.f;
+    if (kScatter) {
+      if (oi % stride == 0 && oj % stride == 0)
+        v = static_cast<float>(x[((img * h + oi / stride) * w + oj / stride) * c + ch]);
+    } else {
+      v = static_cast<float>(x[((img * h + static_cast<int64_t>(oi) * stride) * w + static_cast<int64_t>(oj) * stride) * c + ch]);
+    }
+    y[i] = static_cast<TOut>(v);
+  }
+}
+
 static inline int flat_grid(int64_t items) {
   int64_t b = ceil_div64(items, 256);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -585,5 +615,31 @@ extern "C" int ganb_lerp_bwd(const float* dy, void* da, int da_dtype, void* db, 
   else LERP_BWD(__nv_bfloat16, __nv_bfloat16);
 #undef LERP_BWD
   GANB_CHECK_LAUNCH("lerp_bwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_subsample2d(const void* x, int x_dtype, void* y, int y_dtype, int n, int h, int w, int c, int stride,
+                                int scatter, void* stream) {
+  if (!x || !y) return fail(GANB_E_BADARG, "subsample2d: null buffer");
+  if (n < 1 || h < 1 || w < 1 || c < 1 || stride < 1) return fail(GANB_E_BADARG, "subsample2d: bad shape");
+  // forward: x [n,h,w,c] -> y [n,ceil(h/s),ceil(w/s),c]; scatter: x [n,ceil(h/s),ceil(w/s),c] -> y [n,h,w,c]
+  const int sh = (h + stride - 1) / stride, sw = (w + stride - 1) / stride;
+  const int64_t total = static_cast<int64_t>(n) * (scatter ? h : sh) * (scatter ? w : sw) * c;
+  const int grid = flat_grid(total);
+#define SUBS(TI, TO)                                                                                                  \
+  do {                                                                                                                \
+    if (scatter)                                                                                                      \
+      launch_k(subsample2d_kernel<TI, TO, true>, grid, 256, 0, STREAM, static_cast<const TI*>(x), static_cast<TO*>(y), \
+               sh, sw, c, h, w, stride, total);                                                                       \
+    else                                                                                                              \
+      launch_k(subsample2d_kernel<TI, TO, false>, grid, 256, 0, STREAM, static_cast<const TI*>(x), static_cast<TO*>(y), \
+               h, w, c, sh, sw, stride, total);                                                                       \
+  } while (0)
+  if (x_dtype == GANB_F32 && y_dtype == GANB_F32) SUBS(float, float);
+  else if (x_dtype == GANB_F32) SUBS(float, __nv_bfloat16);
+  else if (y_dtype == GANB_F32) SUBS(__nv_bfloat16, float);
+  else SUBS(__nv_bfloat16, __nv_bfloat16);
+#undef SUBS
+  GANB_CHECK_LAUNCH("subsample2d_kernel");
   return 0;
 }

@@ -194,10 +194,13 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     pt, pl, ho, wo = _pads(padding, h, w, kh, kw, stride)
     # inputs_norm (conv2d.py:93-95): conv(c * x, W) = c * conv(x, W), so the constant rides on the epilogue's alpha
     # (and on the filter gradient's scale) instead of costing a pass over x
-    if in_scale is not None and sn is not None:
-        raise NotImplementedError("inputs_norm together with spectral_normed (no reference call-site combines them)")
     wscale = store.const(in_scale) if in_scale is not None else None
-    alpha = sn.inv_sigma if sn is not None else wscale
+    if in_scale is not None and sn is not None:
+        # the ResNet PGGAN critic (common/resnet_block.py:276-337): y = (c / sigma) * conv(x, W); the filter gradient
+        # wrt W / sigma carries c (wscale below), the data gradient c / sigma of THIS evaluation
+        alpha = K.cast(sn.inv_sigma, F32, scale=in_scale)
+    else:
+        alpha = sn.inv_sigma if sn is not None else wscale
     bias = b.data if b is not None else None
     res = residual.data if residual is not None else None
     small_in, small_out = cin < 8, cout < 8   # 8 channels already satisfy the 16-byte rows of the TMA path
@@ -492,10 +495,12 @@ def linear(x: Var, W: Variable, b: Variable | None, sn=None, out_dtype=F32, in_s
         return reshape(y4, (m, kout))
     if out_dtype != F32:
         raise NotImplementedError("bf16 output is only built for the tensor-core linear path")
-    if in_scale is not None:
-        raise NotImplementedError("inputs_norm on the CUDA-core linear path (no reference call-site: G.Input is wide)")
     xin = x if x.data.dtype == F32 else cast(x, F32)
-    alpha = sn.inv_sigma if sn is not None else None
+    wscale = get_store().const(in_scale) if in_scale is not None else None     # D.Output of the ResNet PGGAN critic
+    if in_scale is not None and sn is not None:
+        alpha = K.cast(sn.inv_sigma, F32, scale=in_scale)
+    else:
+        alpha = sn.inv_sigma if sn is not None else wscale
     y = torch.empty((m, kout), dtype=F32, device=x.data.device)
     K.sgemm_small(xin.data, W.data, y, m, kout, kin, False, False, alpha, b.data if b is not None else None, 0.0)
     out = Var(y)
@@ -514,14 +519,14 @@ def linear(x: Var, W: Variable, b: Variable | None, sn=None, out_dtype=F32, in_s
                 K.colsum(gy, m, kout, b.grad, 1.0)
             if need_w:
                 if sn is not None:
-                    K.sgemm_small(xin.data, gy, sn.g, kin, kout, m, True, False, None, None,
+                    K.sgemm_small(xin.data, gy, sn.g, kin, kout, m, True, False, wscale, None,
                                   1.0 if sn.g_written else 0.0)
                     sn.g_written = True
                     lst = tape.pending_sn.setdefault(W.root, [])
                     if sn not in lst:
                         lst.append(sn)
                 else:
-                    K.sgemm_small(xin.data, gy, W.grad, kin, kout, m, True, False, None, None, 1.0)
+                    K.sgemm_small(xin.data, gy, W.grad, kin, kout, m, True, False, wscale, None, 1.0)
             if xin.requires_grad:
                 dx = torch.empty((m, kin), dtype=F32, device=gy.device)
                 K.sgemm_small(gy, W.data, dx, m, kin, kout, False, True, alpha, None, 0.0)
@@ -662,6 +667,22 @@ def upsample2(x: Var, out_dtype=None) -> Var:
         def bwd():
             if out.grad is not None:
                 x.accum(K.sum2x2(out.grad, 1.0, x.gdtype))
+        _tape().record(bwd)
+    return out
+
+
+def subsample2(x: Var, out_dtype=None) -> Var:
+    """tf.image.resize_nearest_neighbor to half the size: x[:, ::2, ::2, :] (common/resnet_block.py:286-287)."""
+    n, h, w, c = x.shape
+    if h % 2 or w % 2:   # TF picks floor(i * h / out_h): only for even sizes is that every second pixel
+        raise NotImplementedError("subsample2: odd sizes (no reference call-site; PGGAN stages are powers of two)")
+    out = Var(K.subsample2d(x.data, 2, out_dtype or x.data.dtype))
+    if _rg(x):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                x.accum(K.subsample2d_bwd(out.grad, 2, h, w, x.gdtype))
         _tape().record(bwd)
     return out
 

@@ -528,3 +528,19 @@ def lerp_bwd(dy, alpha_dev, da_dtype, db_dtype):
                             dt(db) if db is not None else F32, c_int64(dy.numel()), ptr(alpha_dev), _stream()),
           "ganb_lerp_bwd")
     return da, db
+
+
+def subsample2d(x, stride, out_dtype=None):
+    """y[n, i, j, c] = x[n, i*stride, j*stride, c] (tf.image.resize_nearest_neighbor to 1/stride of the size)."""
+    n, h, w, c = x.shape
+    y = torch.empty((n, -(-h // stride), -(-w // stride), c), dtype=out_dtype or x.dtype, device=x.device)
+    check(L().ganb_subsample2d(ptr(x), dt(x), ptr(y), dt(y), n, h, w, c, stride, 0, _stream()), "ganb_subsample2d")
+    return y
+
+
+def subsample2d_bwd(dy, stride, h, w, out_dtype=None):
+    """Gradient of subsample2d: [n, h, w, c] with dy on the sampled grid and zeros elsewhere."""
+    n, _, _, c = dy.shape
+    dx = torch.empty((n, h, w, c), dtype=out_dtype or dy.dtype, device=dy.device)
+    check(L().ganb_subsample2d(ptr(dy), dt(dy), ptr(dx), dt(dx), n, h, w, c, stride, 1, _stream()), "ganb_subsample2d")
+    return dx

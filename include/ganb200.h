@@ -379,6 +379,12 @@ int ganb_layer_norm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype
 int ganb_lerp_fwd(const float* a, const float* b, float* y, int64_t count, const float* alpha, void* stream);
 int ganb_lerp_bwd(const float* dy, void* da, int da_dtype, void* db, int db_dtype, int64_t count, const float* alpha,
                   void* stream);
+/* tf.image.resize_nearest_neighbor to 1/stride of the size (align_corners=False: source index = i*stride), the skip path
+ * of the ResNet PGGAN critic (common/resnet_block.py:286-287).  (h, w) is always the LARGE size.
+ *   scatter = 0: x [n,h,w,c] -> y [n,ceil(h/s),ceil(w/s),c], y[i,j] = x[i*s, j*s];
+ *   scatter = 1 (its gradient): x [n,ceil(h/s),ceil(w/s),c] -> y [n,h,w,c], zero off the sampled grid.  Any c. */
+int ganb_subsample2d(const void* x, int x_dtype, void* y, int y_dtype, int n, int h, int w, int c, int stride,
+                     int scatter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -128,12 +128,30 @@ class PGGAN:
             return logits.reshape(-1)                                                            # :236
 
 
+class PGGANResNet:
+    """PGGAN/model_resnet.py:14-70: the ResNet variant (common/resnet_block.py:192-349) behind the same two methods."""
+
+    def __init__(self, block_count, trans, inputs_norm):
+        self.bc, self.trans, self.inputs_norm = block_count, trans, inputs_norm
+
+    def get_generator(self, g, z_var, alpha, training=True, reuse=False):
+        with g.variable_scope("g_net", reuse=reuse):                                                 # :33-38
+            z_var_ = z_var.reshape(z_var.shape[0], -1)
+            return rb.Generator_PGGAN(g, z_var_, self.bc, self.trans, alpha, self.inputs_norm, training=training)
+
+    def get_discriminator(self, g, x_var, alpha, labels=None, update_collection=None, reuse=False):
+        with g.variable_scope("d_net", reuse=reuse):                                                 # :50-69
+            return rb.Discriminator_PGGAN(g, x_var, labels, self.bc, self.trans, alpha, self.inputs_norm,
+                                          update_collection=update_collection, reuse=reuse)
+
+
 class PGGANLosses:
     """Losses of PGGAN/train.py:103-113 (hinge) over the model above: returns (cost, params, grads) like the SNGAN
     oracle; D(real) runs with update_collection=None, the fake branch with NO_OPS."""
 
-    def __init__(self, g, block_count, trans, inputs_norm, size, z_dim=512):
-        self.g, self.model = g, PGGAN(block_count, trans, inputs_norm)
+    def __init__(self, g, block_count, trans, inputs_norm, size, z_dim=512, model="nvidia"):
+        cls = PGGAN if model == "nvidia" else PGGANResNet                                     # train.py:61-66
+        self.g, self.model = g, cls(block_count, trans, inputs_norm)
         with torch.no_grad():   # graph construction order: D(real), G, D(fake, reuse)
             g.draw_on_reuse = True
             self.model.get_discriminator(g, torch.zeros(2, size, size, 3), 0.0, update_collection=ops.NO_OPS)

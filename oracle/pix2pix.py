@@ -25,18 +25,28 @@ def _conv(g, x, out_channels, stride, padding, sn=False, uc=None):
                       update_collection=uc, inputs_norm=False, he_init=True, biases=True)
 
 
-def unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME", keep_masks=None):
-    """Pix2Pix/networks.py:174-284"""
+def unet_generator(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME", keep_masks=None):
+    """Pix2Pix/networks.py:359-472: unet_g with a ninth encoder / decoder level (512x512 -> 1x1)."""
+    return unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding, keep_masks, deep=5)
+
+
+def unet_discriminator(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding="VALID"):
+    """Pix2Pix/networks.py:475-536: unet_d with n_layers = 4."""
+    return unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding, n_layers=4)
+
+
+def unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME", keep_masks=None, deep=4):
+    """Pix2Pix/networks.py:174-284 (deep = 4); deep = 5 gives the layer lists of unet_generator, :373-383 / :406-415"""
     layers = []
     with g.variable_scope("encoder_1"):
         layers.append(_conv(g, generator_inputs, ngf, 2, padding))                               # :178-185
-    for out_channels in (ngf * 2, ngf * 4, ngf * 8, ngf * 8, ngf * 8, ngf * 8, ngf * 8):         # :187-195
+    for out_channels in (ngf * 2, ngf * 4, ngf * 8) + (ngf * 8,) * deep:                         # :187-195
         with g.variable_scope("encoder_%d" % (len(layers) + 1)):
             rectified = rb.nonlinearity(layers[-1], "lrelu", 0.2)                                 # :199
             convolved = _conv(g, rectified, out_channels, 2, padding)                            # :201-206
             layers.append(norm_layer(g, convolved, epsilon=1e-5, norm_type="IN"))                # :207
-    layer_specs = [(ngf * 8, 0.5), (ngf * 8, 0.5), (ngf * 8, 0.5), (ngf * 8, 0.0), (ngf * 4, 0.0), (ngf * 2, 0.0),
-                   (ngf, 0.0)]                                                                   # :214-222
+    layer_specs = ([(ngf * 8, 0.5)] * 3 + [(ngf * 8, 0.0)] * (deep - 3)
+                   + [(ngf * 4, 0.0), (ngf * 2, 0.0), (ngf, 0.0)])                               # :214-222
     num_encoder_layers = len(layers)
     for decoder_layer, (out_channels, dropout) in enumerate(layer_specs):
         skip_layer = num_encoder_layers - decoder_layer - 1
@@ -61,9 +71,8 @@ def unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME",
     return layers[-1]
 
 
-def unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding="VALID"):
-    """Pix2Pix/networks.py:287-354"""
-    n_layers = 3
+def unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding="VALID", n_layers=3):
+    """Pix2Pix/networks.py:287-354 (n_layers = 3)"""
     pad = lambda t: torch.nn.functional.pad(t, (0, 0, 1, 1, 1, 1))  # noqa: E731  tf.pad [[0,0],[1,1],[1,1],[0,0]]
     inputs = torch.cat([discrim_inputs, discrim_targets], dim=3)                                  # :293
     with g.variable_scope("layer_1"):                                                            # :296-307

@@ -142,3 +142,75 @@ def OptimizedResBlockDisc1(g, inputs, DIM_D=128, activation_fn="relu", spectral_
     output = conv_2(inputs=output, filter_size=3, name=prefix + ".Conv2", spectral_normed=spectral_normed,
                     update_collection=update_collection, inputs_norm=inputs_norm, he_init=True, biases=biases)
     return shortcut + output
+
+
+# ---------------------------------------------------------------------------------------------- ResNet PGGAN
+def get_dim(stage):
+    """common/resnet_block.py:188-189 (a float under Python 3 in the reference; used as a channel count)."""
+    return int(min(2048 / (2 ** stage), 512))
+
+
+def resize_nearest(x, out_h, out_w):
+    """tf.image.resize_nearest_neighbor(align_corners=False): source index = floor(i * in / out)."""
+    n, h, w, c = x.shape
+    ii = torch.div(torch.arange(out_h) * h, out_h, rounding_mode="floor")
+    jj = torch.div(torch.arange(out_w) * w, out_w, rounding_mode="floor")
+    return x[:, ii][:, :, jj]
+
+
+def Generator_PGGAN(g, noise, bc, trans=False, alpha=0.01, inputs_norm=False, labels=None, training=True):
+    """common/resnet_block.py:192-263"""
+    output = ops.Linear(g, noise, noise.shape[-1], 4 * 4 * 1024, "G.Input", inputs_norm=inputs_norm, biases=True,
+                        initialization=None)                                                        # :206-207
+    output = output.reshape(-1, 4, 4, 1024)                                                         # :208
+    output = Normalize(g, "G.N0", output, labels=labels, spectral_normed=True)                      # :211
+    output = nonlinearity(output, activation_fn="relu")                                             # :212
+    output = ops.Conv2D(g, output, output.shape[-1], 1024, 3, 1, "G.Conv", he_init=True, biases=True)   # :215-216
+
+    def block(x, out_dim, name, resample):
+        return ResidualBlock(g, x, x.shape[-1], out_dim, 3, name, inputs_norm=inputs_norm, resample=resample,
+                             labels=labels)
+
+    for i in range(bc - 1):                                                                         # :222-225
+        output = block(output, get_dim(i), "G.UpBlock.{}".format(i + 1), "up")
+    if trans:                                                                                       # :227-241
+        toRGB1 = block(output, get_dim(bc - 1), "G.UpBlock.{}".format(bc), "up")
+        toRGB1 = block(toRGB1, get_dim(bc - 1), "G.{}_toRGB1".format(bc), None)
+        toRGB2 = resize_nearest(output, toRGB1.shape[1], toRGB1.shape[2])
+        toRGB2 = block(toRGB2, get_dim(bc - 1), "G.{}_toRGB2".format(bc), None)
+        toRGB = (1.0 - alpha) * toRGB2 + alpha * toRGB1
+    else:                                                                                           # :242-250
+        toRGB = block(output, get_dim(bc - 1), "G.UpBlock.{}".format(bc), "up") if bc > 0 else output
+        toRGB = block(toRGB, get_dim(bc - 1), "G.{}_toRGB".format(bc), None)
+    output = Normalize(g, "G.Output_Normalize", toRGB, labels=labels, spectral_normed=True)         # :253
+    output = nonlinearity(output, activation_fn="relu")
+    output = ops.Conv2D(g, output, output.shape[-1], 3, 3, 1, "G.Output", he_init=False)            # :255
+    return torch.tanh(output)                                                                       # :259
+
+
+def Discriminator_PGGAN(g, x_var, c_var, bc, trans=False, alpha=0.01, inputs_norm=False, labels=None,
+                        update_collection=None, reuse=False):
+    """common/resnet_block.py:266-349"""
+    kw = dict(spectral_normed=True, update_collection=update_collection, inputs_norm=inputs_norm, biases=True)
+    if trans:                                                                                       # :282-296
+        fromRGB1 = ResidualBlock(g, x_var, 3, get_dim(bc - 1), 3, "D.{}_fromRGB1".format(bc), resample=None, **kw)
+        fromRGB1 = ResidualBlock(g, fromRGB1, get_dim(bc - 1), get_dim(bc - 1), 3, "D.DownBlock.{}".format(bc),
+                                 resample="down", **kw)
+        fromRGB2 = resize_nearest(x_var, fromRGB1.shape[1], fromRGB1.shape[2])
+        fromRGB2 = ResidualBlock(g, fromRGB2, 3, get_dim(bc - 1), 3, "D.{}_fromRGB2".format(bc), resample=None, **kw)
+        x_code = (1.0 - alpha) * fromRGB2 + alpha * fromRGB1
+    else:                                                                                           # :297-311
+        x_code = ResidualBlock(g, x_var, 3, get_dim(bc - 1), 3, "D.{}_fromRGB".format(bc), resample=None, **kw)
+        if bc > 0:
+            x_code = ResidualBlock(g, x_code, get_dim(bc - 1), get_dim(bc - 1), 3, "D.DownBlock.{}".format(bc),
+                                   resample="down", **kw)
+    for i in range(1, bc):                                                                          # :313-320
+        x_code = ResidualBlock(g, x_code, x_code.shape[-1], get_dim(bc - 1 - i), 3, "D.DownBlock.{}".format(bc - i),
+                               resample="down", **kw)
+    output = ResidualBlock(g, x_code, x_code.shape[-1], get_dim(0), 3, "D.NoneBlock", resample=None, **kw)  # :322-328
+    output = nonlinearity(output, activation_fn="relu")
+    output = output.mean(dim=(1, 2))                                                                # :332
+    logits = ops.Linear(g, output, output.shape[-1], 1, "D.Output", spectral_normed=True,
+                        update_collection=update_collection, inputs_norm=inputs_norm, biases=True,
+                        initialization=None)                                                        # :333-337
+    return logits.reshape(-1)

@@ -236,8 +236,9 @@ def _band(got, ref_b16, ref_f32, factor=2.0, floor=5e-3):
         assert e_prod <= factor * e_orc + floor, (name, e_prod, e_orc)
 
 
-@pytest.mark.parametrize("bc,trans", [(1, False), (2, True)])
-def test_pggan_training_steps(env, bc, trans):
+@pytest.mark.parametrize("bc,trans,model", [(1, False, "nvidia"), (2, True, "nvidia"), (1, False, "resnet"),
+                                            (2, True, "resnet")])
+def test_pggan_training_steps(env, bc, trans, model):
     """PGGAN/train.py:103-136: critic and generator gradients of the hinge losses (D(real) with update_collection=None,
     fake branch NO_OPS, alpha fade-in) through PGGAN.train.Trainer vs the oracle; then one Adam step moves both."""
     store, tfshim = env
@@ -250,7 +251,7 @@ def test_pggan_training_steps(env, bc, trans):
     rs = np.random.RandomState(91)
     real = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
     z = rs.standard_normal((n, 512)).astype("float32")
-    tr = PT.Trainer(bc, trans, inputs_norm=True, batch_size=n, seed=0)
+    tr = PT.Trainer(bc, trans, inputs_norm=True, batch_size=n, seed=0, model=model)
     real_d, z_d = torch.from_numpy(real).cuda(), torch.from_numpy(z).cuda()
     dl = tr.players.gradients("d", lambda: tr.d_loss(real_d, z_d, alpha))
     d_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("d_net")}
@@ -264,7 +265,7 @@ def test_pggan_training_steps(env, bc, trans):
         try:
             np.random.seed(0)
             g = tfshim.Graph(dtype=torch.float32, u_seed=2)
-            ol = OP.PGGANLosses(g, bc, trans, True, size)
+            ol = OP.PGGANLosses(g, bc, trans, True, size, model=model)
             dc, dp, dg = ol.d_grads(torch.from_numpy(real), torch.from_numpy(z), alpha)
             u_ref = {k_: v.detach().numpy().copy() for k_, v in g.vars.items() if k_.endswith("/u")}
             gc, gp, gg = ol.g_grads(torch.from_numpy(z), alpha)

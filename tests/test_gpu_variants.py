@@ -303,3 +303,122 @@ def test_pggan_captured_steps_follow_alpha(env):
     snap.restore()
     ld_other = float(tr.d_step(real, z, 0.2).reshape(-1)[0])
     assert abs(ld_other - ld_g) > 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ ResNet PGGAN pieces
+@pytest.mark.parametrize("shape,dtype", [((3, 8, 8, 3), torch.float32), ((2, 16, 12, 3), torch.float32),
+                                         ((2, 6, 4, 16), torch.bfloat16)])
+def test_subsample2_nearest_half_resize(env, shape, dtype):
+    """tf.image.resize_nearest_neighbor to half the size (common/resnet_block.py:286-287) and its gradient."""
+    store, _ = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from oracle import resnet_block as ORB
+
+    rs = np.random.RandomState(12)
+    x = _bf16_repr(rs.standard_normal(shape).astype("float32"))
+    n, h, w, c = shape
+    oh, ow = -(-h // 2), -(-w // 2)
+    cot = _bf16_repr(rs.standard_normal((n, oh, ow, c)).astype("float32"))
+    xv = F.Var(torch.from_numpy(x).cuda().to(dtype), requires_grad=True)
+    with store.gradient_tape() as tape:
+        out = F.subsample2(xv)
+        tape.backward(out, grad=torch.from_numpy(cot).cuda().to(out.gdtype))
+    torch.cuda.synchronize()
+    xt = torch.from_numpy(x).requires_grad_(True)
+    yo = ORB.resize_nearest(xt, oh, ow)
+    (dx,) = torch.autograd.grad(yo, xt, torch.from_numpy(cot))
+    assert np.array_equal(out.data.float().cpu().numpy(), yo.detach().numpy())
+    assert np.array_equal(out.data.float().cpu().numpy(), x[:, ::2, ::2, :])
+    assert np.array_equal(xv.grad.float().cpu().numpy(), dx.numpy())
+
+
+@pytest.mark.parametrize("cin,cout,k", [(3, 128, 3), (3, 64, 1), (128, 128, 3)])
+def test_inputs_norm_with_spectral_norm_conv(env, cin, cout, k):
+    """The ResNet PGGAN critic combines inputs_norm and spectral_normed on every layer (common/resnet_block.py:276-337):
+    y = (sqrt(2 / fan_in) / sigma) * conv(x, W) + b."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+    from oracle import ops as O
+
+    x = np.random.RandomState(13).standard_normal((4, 8, 8, cin)).astype("float32")
+    kw = dict(inputs_norm=True, spectral_normed=True, update_collection="NO_OPS")
+    prod, refs = run_pair(store, tfshim, lambda xv: P.Conv2D(xv, cin, cout, k, name="L", **kw),
+                          lambda g, xt: O.Conv2D(g, xt, cin, cout, k, name="L", **kw), x)
+    check(prod, refs, tag=f"inputs_norm+sn {cin}->{cout} k{k}")
+
+
+def test_inputs_norm_with_spectral_norm_linear(env):
+    """D.Output of the ResNet PGGAN critic: Linear 512 -> 1 with inputs_norm and spectral norm (:333-337)."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import linear as P
+    from oracle import ops as O
+
+    x = np.random.RandomState(14).standard_normal((6, 512)).astype("float32")
+    kw = dict(inputs_norm=True, spectral_normed=True, update_collection="NO_OPS")
+    prod, refs = run_pair(store, tfshim, lambda xv: P.Linear(xv, 512, 1, "L", **kw),
+                          lambda g, xt: O.Linear(g, xt, 512, 1, "L", **kw), x)
+    check(prod, refs, tag="inputs_norm+sn linear 512->1")
+
+
+@pytest.mark.parametrize("bc,trans", [(1, True), (2, False)])
+def test_resnet_pggan_forward_backward(env, bc, trans):
+    """PGGAN/model_resnet.py: generator forward and critic forward + backward (all parameter gradients and the gradient
+    wrt the image, which runs through the nearest half-resize of the skip path) against both oracles."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.PGGAN import model_resnet as P
+    from oracle import ops as O_ops
+    from oracle import pggan as OP
+
+    n, alpha = 4, 0.3
+    size = 4 * 2 ** bc
+    rs = np.random.RandomState(15)
+    z = rs.standard_normal((n, 512)).astype("float32")
+    img = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    cot = rs.standard_normal(n).astype("float32")
+    np.random.seed(0)
+    pm = P.PGGAN(block_count=bc, trans=trans, inputs_norm=True)
+    fake = pm.get_generator(torch.from_numpy(z).cuda(), alpha)
+    xv = F.Var(torch.from_numpy(img).cuda(), requires_grad=True)
+    with store.gradient_tape() as tape:
+        logits = pm.get_discriminator(xv, alpha, update_collection="NO_OPS")
+        for v in store.trainable_variables("d_net"):
+            if v.grad is None:
+                v.grad = torch.zeros_like(v.data)
+        tape.backward(logits, grad=torch.from_numpy(cot).cuda())
+    torch.cuda.synchronize()
+    assert tuple(fake.shape) == (n, size, size, 3)
+    got = dict(fake=fake.data.float().cpu().numpy(), logits=logits.data.float().cpu().numpy(),
+               dx=xv.grad.float().cpu().numpy())
+    got.update({v.key: v.grad.cpu().numpy() for v in store.trainable_variables("d_net")})
+    refs = {}
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        try:
+            np.random.seed(0)
+            g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+            om = OP.PGGANResNet(bc, trans, True)
+            with torch.no_grad():
+                of = om.get_generator(g, torch.from_numpy(z), alpha)
+            xt = torch.from_numpy(img).clone().requires_grad_(True)
+            lo = om.get_discriminator(g, xt, alpha, update_collection=O_ops.NO_OPS)
+            params = g.trainable_variables("d_net")
+            grads = torch.autograd.grad(lo, [xt] + [p_ for _, p_ in params], torch.from_numpy(cot))
+            r = dict(fake=of.numpy(), logits=lo.detach().numpy(), dx=grads[0].numpy())
+            r.update({nm: gr.numpy() for (nm, _), gr in zip(params, grads[1:])})
+            refs[mode] = r
+        finally:
+            O_ops.BF16_OPERANDS = False
+    assert set(got) == set(refs[False])
+    worst = {}
+    for name in got:
+        e_impl = rel(got[name], refs[True][name])
+        e_prod = rel(got[name], refs[False][name])
+        e_orc = rel(refs[True][name], refs[False][name])
+        worst[name] = (e_impl, e_prod, e_orc)
+        # the implementation follows the bf16-operand oracle, and sits no further from fp32 than that oracle does
+        assert e_impl < 2e-2 and e_prod <= 1.5 * e_orc + 1e-2, (name, e_impl, e_prod, e_orc)
+    top = sorted(worst.items(), key=lambda kv: -kv[1][0])[:3]
+    print(f"resnet pggan bc={bc} trans={trans}: worst vs bf16-oracle", [(k, f"{v[0]:.1e}") for k, v in top],
+          "fake", f"{worst['fake'][0]:.1e}", "logits", f"{worst['logits'][0]:.1e}")
+    assert worst["logits"][0] < 4e-3 and worst["fake"][0] < 2e-2

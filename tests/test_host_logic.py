@@ -162,6 +162,46 @@ def test_pggan_variable_manifest_matches_the_oracle(host):
     assert [v.key for v in store.trainable_variables("g_net")] == [n for n, _ in g.trainable_variables("g_net")]
 
 
+def test_resnet_pggan_variable_manifest_matches_the_oracle(host):
+    """PGGAN/model_resnet.py over common/resnet_block.py:192-349: names, shapes and initial values of the ResNet
+    variant (feature-map fade-in blocks G.2_toRGB1 / G.2_toRGB2, RGB-input residual blocks D.2_fromRGB1 / 2) agree with
+    the oracle restatement; the manifest carries the double scope of Normalize + BatchNorm."""
+    store, _ = host
+    from gan_lib_tensorflow_b200.PGGAN import model_resnet as P
+    from oracle import ops as O
+    from oracle import pggan as OP
+    from oracle import tfshim
+
+    np.random.seed(0)
+    pm = P.PGGAN(block_count=2, trans=True, inputs_norm=True)
+    fake = pm.get_generator(torch.zeros(2, 512), 0.5)
+    assert tuple(fake.shape) == (2, 16, 16, 3)
+    logits = pm.get_discriminator(fake, 0.5, update_collection="NO_OPS")
+    assert tuple(logits.shape) == (2,)
+    np.random.seed(0)
+    g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    om = OP.PGGANResNet(2, True, True)
+    with torch.no_grad():
+        of = om.get_generator(g, torch.zeros(2, 512), 0.5)
+        assert tuple(of.shape) == (2, 16, 16, 3)
+        om.get_discriminator(g, of, 0.5, update_collection=O.NO_OPS)
+    # BatchNorm moving averages are write-only state in the reference and are not kept by the product (DESIGN.md 7)
+    # (the product creates N1's constant-initialised beta / gamma before the shortcut's filters: same NumPy stream)
+    assert sorted(store.vars) == sorted(k for k in g.vars if "/moving_" not in k)
+    norm = lambda ks: [k for k in ks if "/BatchNorm/" not in k]  # noqa: E731
+    assert norm(store.vars) == norm(g.vars)
+    for name, v in store.vars.items():
+        assert tuple(v.data.shape) == tuple(g.vars[name].shape), name
+        if "spectral_norm/u" not in name:
+            np.testing.assert_array_equal(v.data.numpy(), g.vars[name].detach().numpy(), err_msg=name)
+    for name in ("g_net/G.N0/BatchNorm/beta", "g_net/G.UpBlock.1.Shortcut/Filters", "g_net/G.2_toRGB2.Conv1/Filters",
+                 "g_net/G.Output_Normalize/BatchNorm/gamma", "d_net/D.2_fromRGB1.Shortcut/filters/spectral_norm/u",
+                 "d_net/D.DownBlock.1.Conv2/Filters", "d_net/D.NoneBlock.Conv1/Biases", "d_net/D.Output/W"):
+        assert name in store.vars, name
+    assert tuple(store.vars["g_net/G.Conv/Filters"].data.shape) == (3, 3, 1024, 1024)
+    assert tuple(store.vars["d_net/D.2_fromRGB2.Conv1/Filters"].data.shape) == (3, 3, 3, 512)
+
+
 def test_cross_gpu_batch_statistics_call_sequence(host):
     """store.bn_sync = (allreduce, world): a batch-statistics normalisation all-reduces [mean | E[x^2]] between
     ganb_bn_stats and the normalise kernel, and [sum(dy) | sum(dy*xhat)] between the two backward phases; instance
@@ -252,6 +292,32 @@ def test_two_player_trainers_call_sequence(host):
     assert g_calls.count("ganb_adam") == 1 and "ganb_pixel_norm_bwd" in g_calls
     assert tr.players.opt["d"].t == 1 and tr.players.opt["g"].t == 1
     assert abs(tr.alpha(50000) - 0.5) < 1e-12
+
+
+def test_resnet_pggan_trainer_call_sequence(host):
+    """PGGAN/train.py with --model resnet (train.py:61-66): the same two training ops over model_resnet.PGGAN.  The
+    critic's skip path resizes the image with ganb_subsample2d, whose gradient (scatter = 1) only runs in the generator
+    step (the critic step needs no image gradient); the fade-in blends feature maps with ganb_lerp_*."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+
+    tr = PT.Trainer(block_count=1, trans=True, inputs_norm=True, batch_size=2, seed=0, model="resnet")
+    real, z = torch.zeros(2, 8, 8, 3), torch.zeros(2, 512)
+    n0 = len(rec.calls)
+    tr.d_step(real, z, 0.25)
+    d_calls = rec.names()[n0:]
+    assert d_calls.count("ganb_sn_power_iter") == 2 and d_calls.count("ganb_sn_bwd") == 2
+    assert d_calls.count("ganb_subsample2d") == 2          # D(real) and D(fake), forward only
+    assert d_calls.count("ganb_lerp_fwd") == 3 and d_calls.count("ganb_lerp_bwd") == 2   # G (no tape), D twice
+    assert d_calls.count("ganb_adam") == 1
+    n1 = len(rec.calls)
+    tr.g_step(z, 0.25)
+    g_calls = rec.names()[n1:]
+    assert g_calls.count("ganb_subsample2d") == 2          # forward + the scatter of the image gradient
+    assert g_calls.count("ganb_lerp_fwd") == 2 and g_calls.count("ganb_lerp_bwd") == 2
+    assert g_calls.count("ganb_sn_power_iter") == 1 and g_calls.count("ganb_sn_bwd") == 0
+    with pytest.raises(NotImplementedError):
+        PT.Trainer(block_count=1, trans=False, model="vgg")
 
 
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
