@@ -463,6 +463,33 @@ subsample2d_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int h, int w
   }
 }
 
+// ================================================================================================ sample grid
+// generate_image + save_images (SNGAN/gan_cifar_resnet.py:536-539, common/misc.py:215-244): samples in (-1, 1) ->
+// ((s + 1) * 127.5) truncated like astype('int32') -> image k at tile (k / nw, k % nw) of an [nh*h, nw*w, c] uint8 grid.
+// One thread per grid byte (coalesced 1-byte stores, the reads of a tile row are contiguous h*w*c floats per image).
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+sample_grid_kernel(const TIn* __restrict__ x, unsigned char* __restrict__ grid, int n, int h, int w, int c, int nw,
+                   int64_t total) {
+  pdl_wait();
+  const int64_t row_elems = static_cast<int64_t>(nw) * w * c;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int64_t gy = i / row_elems;
+    const int64_t r = i - gy * row_elems;
+    const int gx = static_cast<int>(r / c), ch = static_cast<int>(r - static_cast<int64_t>(gx) * c);
+    const int tj = static_cast<int>(gy / h), y = static_cast<int>(gy - static_cast<int64_t>(tj) * h);
+    const int ti = gx / w, xx = gx - ti * w;
+    const int img = tj * nw + ti;
+    int v = 0;
+    if (img < n) {
+      const float s = static_cast<float>(x[((static_cast<int64_t>(img) * h + y) * w + xx) * c + ch]);
+      v = static_cast<int>((s + 1.f) * 127.5f);   // float -> int truncates toward zero, as NumPy's astype does
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    }
+    grid[i] = static_cast<unsigned char>(v);
+  }
+}
+
 static inline int flat_grid(int64_t items) {
   int64_t b = ceil_div64(items, 256);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -641,5 +668,21 @@ extern "C" int ganb_subsample2d(const void* x, int x_dtype, void* y, int y_dtype
   else SUBS(__nv_bfloat16, __nv_bfloat16);
 #undef SUBS
   GANB_CHECK_LAUNCH("subsample2d_kernel");
+  return 0;
+}
+
+extern "C" int ganb_sample_grid(const void* samples, int dtype, int n, int h, int w, int c, int nw, unsigned char* grid,
+                                void* stream) {
+  if (!samples || !grid) return fail(GANB_E_BADARG, "sample_grid: null buffer");
+  if (n < 1 || h < 1 || w < 1 || c < 1 || nw < 1) return fail(GANB_E_BADARG, "sample_grid: bad shape");
+  const int nh = (n + nw - 1) / nw;
+  const int64_t total = static_cast<int64_t>(nh) * h * nw * w * c;
+  if (dtype == GANB_F32)
+    launch_k(sample_grid_kernel<float>, flat_grid(total), 256, 0, STREAM, static_cast<const float*>(samples), grid, n, h,
+             w, c, nw, total);
+  else
+    launch_k(sample_grid_kernel<__nv_bfloat16>, flat_grid(total), 256, 0, STREAM,
+             static_cast<const __nv_bfloat16*>(samples), grid, n, h, w, c, nw, total);
+  GANB_CHECK_LAUNCH("sample_grid_kernel");
   return 0;
 }

@@ -544,3 +544,11 @@ def subsample2d_bwd(dy, stride, h, w, out_dtype=None):
     dx = torch.empty((n, h, w, c), dtype=out_dtype or dy.dtype, device=dy.device)
     check(L().ganb_subsample2d(ptr(dy), dt(dy), ptr(dx), dt(dx), n, h, w, c, stride, 1, _stream()), "ganb_subsample2d")
     return dx
+
+
+def sample_grid(samples, nw):
+    """[n, h, w, c] samples in (-1, 1) -> uint8 grid [ceil(n / nw) * h, nw * w, c] (common/misc.py:215-244)."""
+    n, h, w, c = samples.shape
+    grid = torch.empty((-(-n // nw) * h, nw * w, c), dtype=torch.uint8, device=samples.device)
+    check(L().ganb_sample_grid(ptr(samples), dt(samples), n, h, w, c, nw, ptr(grid), _stream()), "ganb_sample_grid")
+    return grid

@@ -386,6 +386,12 @@ int ganb_lerp_bwd(const float* dy, void* da, int da_dtype, void* db, int db_dtyp
 int ganb_subsample2d(const void* x, int x_dtype, void* y, int y_dtype, int n, int h, int w, int c, int stride,
                      int scatter, void* stream);
 
+/* Sample grid of generate_image / save_images (SNGAN/gan_cifar_resnet.py:536-539, common/misc.py:215-244): samples
+ * [n,h,w,c] in (-1, 1) -> ((s + 1) * 127.5) truncated toward zero (astype('int32')), clamped to [0, 255], image k
+ * written to tile (k / nw, k % nw) of the uint8 grid [ceil(n/nw)*h, nw*w, c]; unused tiles are zero. */
+int ganb_sample_grid(const void* samples, int dtype, int n, int h, int w, int c, int nw, unsigned char* grid,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,204 @@
+"""The step either side of the hot path: common.misc (sample grid, get_z, get_loss,
+optimistic_restore, TF-1 checkpoint names incl. the Adam slots) and common.plot.  CPU tests use the host-logic mode
+(kernels recorded, not run); the GPU tests check the sample-grid kernel against a NumPy restatement of
+generate_image + save_images (SNGAN/gan_cifar_resnet.py:536-539, common/misc.py:215-244)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_host_logic import host  # noqa: F401
+
+
+def _reference_grid(samples_pm1):
+    """NumPy restatement of generate_image + save_images up to the imsave call: returns the float grid it passes on."""
+    X = ((samples_pm1 + 1.) * (255. / 2)).astype('int32')                   # gan_cifar_resnet.py:538
+    n_samples = X.shape[0]
+    rows = int(np.sqrt(n_samples))                                         # misc.py:221-226
+    while n_samples % rows != 0:
+        rows -= 1
+    nh, nw = rows, int(n_samples / rows)
+    h, w = X[0].shape[:2]
+    img = np.zeros((h * nh, w * nw, 3))                                    # misc.py:232-235
+    for n, x in enumerate(X):                                              # misc.py:239-242
+        j, i = int(n / nw), int(n % nw)
+        img[j * h:j * h + h, i * w:i * w + w] = x
+    return img
+
+
+def _imsave_bytes(img):
+    """scipy.misc.imsave -> toimage -> bytescale(cmin=None, cmax=None) of a non-uint8 array (scipy 1.0 source)."""
+    cmin, cmax = img.min(), img.max()
+    cscale = (cmax - cmin) or 1
+    bytedata = (img - cmin) * (255.0 / cscale)
+    return (bytedata.clip(0, 255) + 0.5).astype(np.uint8)
+
+
+def test_grid_shape_and_bytescale():
+    from gan_lib_tensorflow_b200.common import misc
+
+    assert misc.grid_shape(100) == (10, 10) and misc.grid_shape(64) == (8, 8)
+    assert misc.grid_shape(50) == (5, 10) and misc.grid_shape(7) == (1, 7) and misc.grid_shape(12) == (3, 4)
+    rs = np.random.RandomState(0)
+    img = rs.randint(3, 250, size=(8, 8, 3)).astype("float64")
+    np.testing.assert_array_equal(misc._bytescale(img), _imsave_bytes(img))
+    assert misc._bytescale(np.full((2, 2), 7.0)).max() == 0      # constant image: cscale falls back to 1
+
+
+def test_save_images_host_path_matches_the_reference_loop(tmp_path):
+    from PIL import Image
+
+    from gan_lib_tensorflow_b200.common import misc
+
+    rs = np.random.RandomState(1)
+    samples = rs.uniform(-1, 1, size=(12, 8, 8, 3)).astype("float32")
+    X = ((samples + 1.) * (255. / 2)).astype('int32')
+    out = misc.save_images(X, tmp_path / "s.png")
+    np.testing.assert_array_equal(out, _imsave_bytes(_reference_grid(samples)))
+    np.testing.assert_array_equal(np.asarray(Image.open(tmp_path / "s.png")), out)
+    # floats in [0, 1] are scaled by 255.99 (misc.py:217-218)
+    f = rs.uniform(size=(4, 6, 6, 3))
+    out_f = misc.save_images(f, tmp_path / "f.png", stretch=False)
+    assert out_f.shape == (12, 12, 3) and out_f[0, 0, 0] == int(255.99 * f[0, 0, 0, 0])
+
+
+def test_plot_tick_flush_log(tmp_path, capsys):
+    from gan_lib_tensorflow_b200.common import plot
+
+    plot.reset()
+    plot.set_output_dir(str(tmp_path))
+    for it in range(3):
+        plot.plot('d_cost', 1.0 + it)
+        plot.plot('g_cost', torch.tensor([0.5 * it]))       # device scalars are read back at flush time only
+        plot.tick()
+    plot.flush()
+    printed = capsys.readouterr().out
+    assert "iter 3" in printed and "d_cost: 2.0" in printed and "g_cost: 0.5" in printed
+    with open(tmp_path / "log.pkl", "rb") as fh:
+        log = pickle.load(fh)
+    assert log["d_cost"] == {0: 1.0, 1: 2.0, 2: 3.0} and log["g_cost"][2] == 1.0
+    plot.plot('d_cost', 10.0)
+    plot.flush()
+    with open(tmp_path / "log.pkl", "rb") as fh:
+        assert pickle.load(fh)["d_cost"][3] == 10.0
+    plot.reset()
+    plot.set_output_dir('.')
+
+
+def test_checkpoint_names_and_round_trip(host, tmp_path):  # noqa: F811
+    """TF-1 names of a Saver checkpoint: variables, `<var>/Adam`, `<var>/Adam_1`, beta powers per optimiser
+    (gen_opt first, SNGAN/gan_cifar_resnet.py:520-526); restore follows optimistic_restore's name + shape rule."""
+    store, _ = host
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+    from gan_lib_tensorflow_b200.common import misc
+
+    tr = PT.Trainer(block_count=1, trans=False, batch_size=2, seed=0)
+    og, od = tr.players.opt["g"], tr.players.opt["d"]
+    og.t, od.t = 3, 15
+    og.flat.m.uniform_(-1, 1); og.flat.v.uniform_(0, 1); od.flat.m.uniform_(-1, 1); od.flat.v.uniform_(0, 1)
+    names = misc.save_checkpoint(tmp_path / "model.ckpt-7", optimizers=(og, od))
+    assert "g_net/G.Input/W" in names and "g_net/G.Input/W/Adam" in names and "g_net/G.Input/W/Adam_1" in names
+    assert "d_net/D.Conv/filters/spectral_norm/u" in names and "d_net/D.Conv/filters/spectral_norm/u/Adam" not in names
+    assert {"beta1_power", "beta2_power", "beta1_power_1", "beta2_power_1"} <= set(names)
+    state = misc.checkpoint_state((og, od))
+    assert abs(float(state["beta2_power"]) - 0.9 ** 4) < 1e-7 and abs(float(state["beta2_power_1"]) - 0.9 ** 16) < 1e-7
+    assert float(state["beta1_power"]) == 0.0
+    w = store.vars["g_net/G.Input/W"]
+    off = og.flat.offsets[og.flat.variables.index(w)]
+    np.testing.assert_array_equal(state["g_net/G.Input/W/Adam"].reshape(-1),
+                                  og.flat.m[off:off + w.data.numel()].numpy())
+    saved = {k: v.copy() for k, v in state.items()}
+    # perturb everything, then restore
+    for f in (og.flat, od.flat):
+        f.params.add_(1.0); f.m.zero_(); f.v.zero_()
+    og.t = od.t = 0
+    restored = misc.restore_checkpoint(tmp_path / "model.ckpt-7", optimizers=(og, od))
+    assert og.t == 3 and od.t == 15 and "g_net/G.Input/W/Adam_1" in restored
+    now = misc.checkpoint_state((og, od))
+    for k, v in saved.items():
+        np.testing.assert_array_equal(now[k], v, err_msg=k)
+    # optimistic rule: a shape mismatch and an unknown name are skipped silently
+    bad = {"g_net/G.Input/W": np.zeros((3, 3), "float32"), "nope/W": np.zeros(2, "float32"),
+           "g_net/G.Input/b": saved["g_net/G.Input/b"] + 1}
+    got = misc.optimistic_restore(None, bad)
+    assert got == ["g_net/G.Input/b"]
+
+
+def test_get_loss_needs_a_player_inside_a_tape(host):  # noqa: F811
+    store, rec = host
+    from gan_lib_tensorflow_b200.common import misc
+
+    real, fake = torch.zeros(4), torch.zeros(4)
+    d, g = misc.get_loss(real, fake, 'LSGAN')
+    assert d is not None and g is not None and rec.names().count("ganb_gan_loss") == 2
+    with store.gradient_tape():
+        with pytest.raises(ValueError):
+            misc.get_loss(real, fake, 'HINGE')
+        d, g = misc.get_loss(real, fake, 'HINGE', player='d')
+        assert d is not None and g is None
+    z = misc.get_z(5, 7)
+    assert z.shape == (5, 7) and z.dtype == np.float32
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,h,w,dtype", [(100, 32, 32, torch.float32), (12, 8, 16, torch.float32),
+                                         (7, 4, 4, torch.bfloat16), (64, 128, 128, torch.float32)])
+def test_sample_grid_kernel_matches_generate_image(n, h, w, dtype, tmp_path):
+    from PIL import Image
+
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200.common import misc
+
+    framework.reset_default_graph("cuda")
+    try:
+        rs = np.random.RandomState(2)
+        s = np.tanh(rs.standard_normal((n, h, w, 3)) * 2).astype("float32")
+        s[0, 0, 0, :] = [-1.0, 1.0, 0.0]
+        t = torch.from_numpy(s).cuda().to(dtype)
+        s = t.float().cpu().numpy()
+        ref = _reference_grid(s)
+        got = misc.sample_grid(t, stretch=False)
+        assert got.dtype == np.uint8 and got.shape == ref.shape
+        np.testing.assert_array_equal(got, ref.astype(np.uint8))            # bit-exact integer work
+        out = misc.save_images(t, tmp_path / "g.png")
+        np.testing.assert_array_equal(out, _imsave_bytes(ref))
+        np.testing.assert_array_equal(np.asarray(Image.open(tmp_path / "g.png")), out)
+        if h == w:   # the [n, h*w*3] layout the Generator returns
+            np.testing.assert_array_equal(misc.sample_grid(t.reshape(n, -1), stretch=False), got)
+    finally:
+        framework.set_store(None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("loss_type", ["HINGE", "WGAN", "WGAN-GP", "LSGAN", "CGAN", "Modified_MiniMax", "MiniMax"])
+def test_get_loss_pair_matches_the_oracle(loss_type):
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.common import misc
+    from oracle import acgan as OA
+
+    store = framework.reset_default_graph("cuda")
+    try:
+        rs = np.random.RandomState(3)
+        real = rs.standard_normal(24).astype("float32")
+        fake = rs.standard_normal(24).astype("float32")
+        d, g = misc.get_loss(torch.from_numpy(real).cuda(), torch.from_numpy(fake).cuda(), loss_type)
+        rt = torch.from_numpy(real).double().requires_grad_(True)
+        ft = torch.from_numpy(fake).double().requires_grad_(True)
+        od, og = OA.get_loss(rt, ft, loss_type)
+        assert abs(float(d.data.item()) - od.item()) < 1e-5 and abs(float(g.data.item()) - og.item()) < 1e-5
+        for player, loss in (("d", od), ("g", og)):
+            rv = F.Var(torch.from_numpy(real).cuda(), requires_grad=True)
+            fv = F.Var(torch.from_numpy(fake).cuda(), requires_grad=True)
+            with store.gradient_tape() as tape:
+                pair = misc.get_loss(rv, fv, loss_type, player=player)
+                tape.backward(pair[0] if player == "d" else pair[1])
+            gr, gf = torch.autograd.grad(loss, [rt, ft], allow_unused=True, retain_graph=True)
+            if gr is not None and player == "d":
+                np.testing.assert_allclose(rv.grad.cpu().numpy(), gr.numpy(), atol=1e-6)
+            np.testing.assert_allclose(fv.grad.cpu().numpy(), gf.numpy(), atol=1e-6)
+    finally:
+        framework.set_store(None)

@@ -221,6 +221,58 @@ def test_pix2pix_patchgan_discriminator(env):
     check(prod, refs, tol_impl=6e-3, tol_fp32=1e-1, tag="unet_d")   # 5 layers of lrelu-mask sensitivity vs fp32
 
 
+def test_pix2pix_512_unet_generator_and_discriminator(env):
+    """Pix2Pix/networks.py:359-536: unet_generator (nine encoder / decoder levels) and unet_discriminator (n_layers = 4).
+    The generator runs at 1024x1024 with ngf = 8 so that encoder_9's instance norm still sees 2x2 pixels (see
+    test_pix2pix_unet_generator); forward only for G (its backward is the same ops as unet_g's), forward + backward for D."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.Pix2Pix import networks as P
+    from oracle import ops as O
+    from oracle import ops as O_ops
+    from oracle import pix2pix as OP
+
+    n, ngf, size = 1, 8, 1024
+    rs = np.random.RandomState(53)
+    x = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    masks = [(rs.uniform(size=(n, s, s, ngf * 8)) < 0.5).astype("float32") for s in (4, 8, 16)]
+    np.random.seed(0)
+    with store.variable_scope("G"):
+        out = P.unet_generator(torch.from_numpy(x).cuda(), 3, ngf,
+                               keep_masks=[torch.from_numpy(m).cuda() for m in masks])
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (n, size, size, 3)
+    assert "G/encoder_9/Conv2D/Filters" in store.vars and "G/decoder_9/InstanceNorm/gamma" in store.vars
+    errs = {}
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        try:
+            np.random.seed(0)
+            g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+            with torch.no_grad(), g.variable_scope("G"):
+                ref = OP.unet_generator(g, torch.from_numpy(x), 3, ngf, keep_masks=[torch.from_numpy(m) for m in masks])
+            errs[mode] = rel(out.data.float().cpu().numpy(), ref.numpy())
+            if mode:
+                ref16 = ref.numpy()
+            else:
+                e_orc = rel(ref16, ref.numpy())
+        finally:
+            O_ops.BF16_OPERANDS = False
+    print(f"unet_generator 1024: vs bf16-oracle {errs[True]:.2e}, vs fp32 {errs[False]:.2e} (bf16-oracle vs fp32 {e_orc:.2e})")
+    assert sorted(k for k in store.vars) == sorted(k for k in g.vars if "/moving_" not in k)
+    assert errs[True] < 1e-2 and errs[False] <= 1.5 * e_orc + 1e-2
+
+    ndf = 16
+    xd = rs.uniform(-1, 1, size=(2, 128, 128, 3)).astype("float32")
+    tgt = rs.uniform(-1, 1, size=(2, 128, 128, 3)).astype("float32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.unet_discriminator(xv, F.Var(torch.from_numpy(tgt).cuda()), ndf, True, "NO_OPS"),
+        lambda g_, xt: OP.unet_discriminator(g_, xt, torch.from_numpy(tgt), ndf, True, O.NO_OPS), xd)
+    assert prod["out"].shape == (2, 6, 6, 1)
+    check(prod, refs, tol_impl=1.2e-2, tol_fp32=1.2e-1, tag="unet_discriminator")   # 6 layers of lrelu-mask flips (5: 6e-3)
+
+
 # ------------------------------------------------------------------------------------------------ SNGAN ImageNet-128
 def test_imagenet_generator_forward_full_width(env):
     """gan_imagNet_resnet.py:241-271 at the real widths (DIM_G = 128: 1024 -> 64 channels, 4x4 -> 128x128), 1000-class
