@@ -6,6 +6,7 @@ Glorot stdev, conv2d.py:83-140), and are drawn on every call during graph constr
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 from ... import functional as F
 from ...framework import Var, get_store
@@ -57,6 +58,41 @@ def pixelcnn_mask(mask_type, filter_size, input_dim, output_dim):
     return mask
 
 
+def _depthwise_types(store, inputs, conv_type, depthwise_filters, pointwise_filters, input_dim, output_dim,
+                     channel_multiplier, stride, padding, spectral_normed, inputs_norm, mask_type, weightnorm, biases,
+                     residual, subpixel_up2, out_grad_dtype, out_dtype):
+    """conv_type 'depthwise_conv2d' / 'separable_conv2d' (common/ops/conv2d.py:188-208).  The reference applies
+    weight-norm, masks and spectral norm to `Filters` only, which these two types never read: they have no effect on the
+    result (spectral_normed still creates the `u` variable, which then keeps its initial value)."""
+    if depthwise_filters is None:
+        raise ValueError('{0} needs channel_multiplier > 0 (the reference fails with a NameError)'.format(conv_type))
+    if inputs_norm or residual is not None or subpixel_up2:
+        raise NotImplementedError('{0} with inputs_norm / a fused residual (no reference call-site)'.format(conv_type))
+    if weightnorm is None:
+        weightnorm = _default_weightnorm
+    if weightnorm or mask_type is not None:
+        raise NotImplementedError('weight-norm / masks act on the unused `Filters` of {0}'.format(conv_type))
+    if spectral_normed:
+        from ...framework import truncated_normal
+        with store.variable_scope('filters'), store.variable_scope('spectral_norm'):
+            store.get_variable('u', shape=[1, output_dim], trainable=False,
+                               initializer=lambda s: truncated_normal(s, store.u_rng))
+    _biases = None
+    if biases:
+        _biases = store.get_variable(name='Biases', shape=[output_dim, ],
+                                     initializer=lambda s: np.zeros(s, dtype='float32'))
+    if conv_type == 'depthwise_conv2d':
+        if biases and output_dim != input_dim * channel_multiplier:
+            raise ValueError('depthwise_conv2d yields input_dim * channel_multiplier = {} channels but Biases has '
+                             'output_dim = {} (tf.nn.bias_add fails in the reference)'.format(
+                                 input_dim * channel_multiplier, output_dim))
+        return F.depthwise_conv2d(inputs, depthwise_filters, _biases, stride, padding,
+                                  out_dtype=out_dtype or torch.float32, out_grad_dtype=out_grad_dtype)
+    mid = F.depthwise_conv2d(inputs, depthwise_filters, None, stride, padding)
+    return F.conv2d(mid, pointwise_filters, _biases, 1, 1, 1, 'VALID', out_grad_dtype=out_grad_dtype,
+                    **({'out_dtype': out_dtype} if out_dtype is not None else {}))
+
+
 def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D',
            conv_type='conv2d', channel_multiplier=0, padding='SAME',
            spectral_normed=False, update_collection=None, inputs_norm=False, he_init=True,
@@ -75,8 +111,8 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
     store = get_store()
     inputs = F.as_var(inputs)
     with store.variable_scope(name):
-        if conv_type != 'conv2d':
-            raise NotImplementedError('{0} is not supported!'.format(conv_type))
+        if conv_type not in ('conv2d', 'depthwise_conv2d', 'separable_conv2d'):
+            raise NotImplementedError('{0} is not supported!'.format(conv_type))      # conv2d.py:209-210
         if input_dim != inputs.shape[-1]:
             raise ValueError('input_dim={} but inputs have {} channels'.format(input_dim, inputs.shape[-1]))
 
@@ -97,6 +133,16 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
         filter_values = _memo(
             lambda: uniform(stdev, (filter_size, filter_size, input_dim, output_dim)) * np.float32(gain))
         filters = store.get_variable(name='Filters', initializer=lambda _s: filter_values())
+        depthwise_filters = pointwise_filters = None
+        if channel_multiplier > 0:   # conv2d.py:117-126, 145-150: drawn after the filter values, never scaled by gain
+            depthwise_filters = store.get_variable(name='depthwise_filters', initializer=lambda _s: uniform(
+                stdev, (filter_size, filter_size, input_dim, channel_multiplier)))
+            pointwise_filters = store.get_variable(name='pointwise_filters', initializer=lambda _s: uniform(
+                stdev, (1, 1, input_dim * channel_multiplier, output_dim)))
+        if conv_type != 'conv2d':
+            return _depthwise_types(store, inputs, conv_type, depthwise_filters, pointwise_filters, input_dim,
+                                    output_dim, channel_multiplier, stride, padding, spectral_normed, inputs_norm,
+                                    mask_type, weightnorm, biases, residual, subpixel_up2, out_grad_dtype, out_dtype)
 
         if weightnorm is None:
             weightnorm = _default_weightnorm

@@ -490,6 +490,105 @@ sample_grid_kernel(const TIn* __restrict__ x, unsigned char* __restrict__ grid, 
   }
 }
 
+// ================================================================================================ depthwise conv
+// tf.nn.depthwise_conv2d / the first half of tf.nn.separable_conv2d (common/ops/conv2d.py:188-208, Pix2Pix --conv_type):
+//   y[n, ho, wo, ci*cm + m] = sum_{r,s} x[n, ho*stride + r - pad_t, wo*stride + s - pad_l, ci] * f[r, s, ci, m]
+// No reuse across output channels: bandwidth-bound, one thread per output element with the channel fastest (coalesced
+// stores; for cm = 1 the k*k tap reads are coalesced too and hit L1/L2 k*k/stride^2 times each).  fp32 arithmetic.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+depthwise_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ f, const float* __restrict__ bias,
+                     TOut* __restrict__ y, int h, int w, int c, int cm, int ho, int wo, int kh, int kw, int stride,
+                     int pad_t, int pad_l, int64_t total) {
+  pdl_wait();
+  const int oc_n = c * cm;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int oc = static_cast<int>(i % oc_n);
+    int64_t p = i / oc_n;
+    const int ow = static_cast<int>(p % wo);
+    p /= wo;
+    const int oh = static_cast<int>(p % ho);
+    const int64_t img = p / ho;
+    const int ci = oc / cm, m = oc - ci * cm;
+    float acc = bias ? bias[oc] : 0.f;
+    for (int r = 0; r < kh; ++r) {
+      const int hi = oh * stride + r - pad_t;
+      if (hi < 0 || hi >= h) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int wi = ow * stride + q - pad_l;
+        if (wi < 0 || wi >= w) continue;
+        acc += static_cast<float>(x[((img * h + hi) * w + wi) * c + ci]) * f[((r * kw + q) * c + ci) * cm + m];
+      }
+    }
+    y[i] = static_cast<TOut>(acc);
+  }
+}
+
+// dx[n, hi, wi, ci] = sum_{r,s,m} dy[n, (hi + pad_t - r)/stride, (wi + pad_l - s)/stride, ci*cm + m] * f[r, s, ci, m]
+template <typename TDy, typename TOut>
+__global__ void __launch_bounds__(256)
+depthwise_bwd_input_kernel(const TDy* __restrict__ dy, const float* __restrict__ f, TOut* __restrict__ dx, int h, int w,
+                           int c, int cm, int ho, int wo, int kh, int kw, int stride, int pad_t, int pad_l,
+                           int64_t total) {
+  pdl_wait();
+  const int oc_n = c * cm;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int ci = static_cast<int>(i % c);
+    int64_t p = i / c;
+    const int wi = static_cast<int>(p % w);
+    p /= w;
+    const int hi = static_cast<int>(p % h);
+    const int64_t img = p / h;
+    float acc = 0.f;
+    for (int r = 0; r < kh; ++r) {
+      const int th = hi + pad_t - r;
+      if (th < 0 || th % stride) continue;
+      const int oh = th / stride;
+      if (oh >= ho) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int tw = wi + pad_l - q;
+        if (tw < 0 || tw % stride) continue;
+        const int ow = tw / stride;
+        if (ow >= wo) continue;
+        const TDy* g = dy + ((img * ho + oh) * wo + ow) * oc_n + ci * cm;
+        const float* ff = f + ((r * kw + q) * c + ci) * cm;
+        for (int m = 0; m < cm; ++m) acc += static_cast<float>(g[m]) * ff[m];
+      }
+    }
+    dx[i] = static_cast<TOut>(acc);
+  }
+}
+
+// Filter gradient, deterministic two-level reduction: block (chunk, tap) sums its pixel chunk for every output channel
+// (threads stride over ci*cm + m: coalesced dy reads) into partial[chunk][tap][c*cm]; the chunks are folded by
+// ganb_colsum (rows = chunks, columns = taps*c*cm).
+constexpr int DW_CHUNKS_MAX = 512;
+template <typename TIn, typename TDy>
+__global__ void __launch_bounds__(256)
+depthwise_bwd_filter_kernel(const TIn* __restrict__ x, const TDy* __restrict__ dy, float* __restrict__ partial, int h,
+                            int w, int c, int cm, int ho, int wo, int kw, int stride, int pad_t, int pad_l,
+                            int64_t pixels, int64_t per_chunk) {
+  pdl_wait();
+  const int oc_n = c * cm;
+  const int tap = blockIdx.y, r = tap / kw, q = tap - r * kw;
+  const int64_t p0 = blockIdx.x * per_chunk;
+  const int64_t p1 = p0 + per_chunk < pixels ? p0 + per_chunk : pixels;
+  for (int oc = threadIdx.x; oc < oc_n; oc += 256) {
+    const int ci = oc / cm;
+    float acc = 0.f;
+    for (int64_t p = p0; p < p1; ++p) {
+      const int ow = static_cast<int>(p % wo);
+      const int64_t t = p / wo;
+      const int oh = static_cast<int>(t % ho);
+      const int64_t img = t / ho;
+      const int hi = oh * stride + r - pad_t, wi = ow * stride + q - pad_l;
+      if (hi < 0 || hi >= h || wi < 0 || wi >= w) continue;
+      acc += static_cast<float>(x[((img * h + hi) * w + wi) * c + ci]) * static_cast<float>(dy[p * oc_n + oc]);
+    }
+    partial[(static_cast<int64_t>(blockIdx.x) * gridDim.y + tap) * oc_n + oc] = acc;
+  }
+}
+
 static inline int flat_grid(int64_t items) {
   int64_t b = ceil_div64(items, 256);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -684,5 +783,79 @@ extern "C" int ganb_sample_grid(const void* samples, int dtype, int n, int h, in
     launch_k(sample_grid_kernel<__nv_bfloat16>, flat_grid(total), 256, 0, STREAM,
              static_cast<const __nv_bfloat16*>(samples), grid, n, h, w, c, nw, total);
   GANB_CHECK_LAUNCH("sample_grid_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- depthwise conv entries
+static bool dw_args_ok(int n, int h, int w, int c, int cm, int ho, int wo, int kh, int kw, int stride) {
+  return n >= 1 && h >= 1 && w >= 1 && c >= 1 && cm >= 1 && ho >= 1 && wo >= 1 && kh >= 1 && kw >= 1 && stride >= 1;
+}
+
+extern "C" int ganb_depthwise_conv2d_fwd(const void* x, int x_dtype, const float* filter, const float* bias, void* y,
+                                         int y_dtype, int n, int h, int w, int c, int cm, int ho, int wo, int kh, int kw,
+                                         int stride, int pad_t, int pad_l, void* stream) {
+  if (!x || !filter || !y) return fail(GANB_E_BADARG, "depthwise_conv2d_fwd: null buffer");
+  if (!dw_args_ok(n, h, w, c, cm, ho, wo, kh, kw, stride)) return fail(GANB_E_BADARG, "depthwise_conv2d_fwd: bad shape");
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * c * cm;
+#define DW_FWD(TI, TO)                                                                                                \
+  launch_k(depthwise_fwd_kernel<TI, TO>, flat_grid(total), 256, 0, STREAM, static_cast<const TI*>(x), filter, bias,   \
+           static_cast<TO*>(y), h, w, c, cm, ho, wo, kh, kw, stride, pad_t, pad_l, total)
+  if (x_dtype == GANB_F32 && y_dtype == GANB_F32) DW_FWD(float, float);
+  else if (x_dtype == GANB_F32) DW_FWD(float, __nv_bfloat16);
+  else if (y_dtype == GANB_F32) DW_FWD(__nv_bfloat16, float);
+  else DW_FWD(__nv_bfloat16, __nv_bfloat16);
+#undef DW_FWD
+  GANB_CHECK_LAUNCH("depthwise_fwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_depthwise_conv2d_bwd_input(const void* dy, int dy_dtype, const float* filter, void* dx, int dx_dtype,
+                                               int n, int h, int w, int c, int cm, int ho, int wo, int kh, int kw,
+                                               int stride, int pad_t, int pad_l, void* stream) {
+  if (!dy || !filter || !dx) return fail(GANB_E_BADARG, "depthwise_conv2d_bwd_input: null buffer");
+  if (!dw_args_ok(n, h, w, c, cm, ho, wo, kh, kw, stride))
+    return fail(GANB_E_BADARG, "depthwise_conv2d_bwd_input: bad shape");
+  const int64_t total = static_cast<int64_t>(n) * h * w * c;
+#define DW_BI(TD, TO)                                                                                                 \
+  launch_k(depthwise_bwd_input_kernel<TD, TO>, flat_grid(total), 256, 0, STREAM, static_cast<const TD*>(dy), filter,  \
+           static_cast<TO*>(dx), h, w, c, cm, ho, wo, kh, kw, stride, pad_t, pad_l, total)
+  if (dy_dtype == GANB_F32 && dx_dtype == GANB_F32) DW_BI(float, float);
+  else if (dy_dtype == GANB_F32) DW_BI(float, __nv_bfloat16);
+  else if (dx_dtype == GANB_F32) DW_BI(__nv_bfloat16, float);
+  else DW_BI(__nv_bfloat16, __nv_bfloat16);
+#undef DW_BI
+  GANB_CHECK_LAUNCH("depthwise_bwd_input_kernel");
+  return 0;
+}
+
+static int dw_chunks(int64_t pixels) {
+  int64_t ch = ceil_div64(pixels, 256);      // >= 256 pixels per block
+  if (ch > DW_CHUNKS_MAX) ch = DW_CHUNKS_MAX;
+  return static_cast<int>(ch < 1 ? 1 : ch);
+}
+
+extern "C" int64_t ganb_depthwise_conv2d_chunks(int n, int ho, int wo) {
+  return dw_chunks(static_cast<int64_t>(n) * ho * wo);
+}
+
+extern "C" int ganb_depthwise_conv2d_bwd_filter(const void* x, int x_dtype, const void* dy, int dy_dtype,
+                                                float* partials, int n, int h, int w, int c, int cm, int ho, int wo,
+                                                int kh, int kw, int stride, int pad_t, int pad_l, void* stream) {
+  if (!x || !dy || !partials) return fail(GANB_E_BADARG, "depthwise_conv2d_bwd_filter: null buffer");
+  if (!dw_args_ok(n, h, w, c, cm, ho, wo, kh, kw, stride))
+    return fail(GANB_E_BADARG, "depthwise_conv2d_bwd_filter: bad shape");
+  const int64_t pixels = static_cast<int64_t>(n) * ho * wo;
+  const int chunks = dw_chunks(pixels);
+  const int64_t per_chunk = ceil_div64(pixels, chunks);
+  const dim3 grid(chunks, kh * kw);
+#define DW_BF(TI, TD)                                                                                                 \
+  launch_k(depthwise_bwd_filter_kernel<TI, TD>, grid, 256, 0, STREAM, static_cast<const TI*>(x),                      \
+           static_cast<const TD*>(dy), partials, h, w, c, cm, ho, wo, kw, stride, pad_t, pad_l, pixels, per_chunk)
+  if (x_dtype == GANB_F32 && dy_dtype == GANB_F32) DW_BF(float, float);
+  else if (x_dtype == GANB_F32) DW_BF(float, __nv_bfloat16);
+  else if (dy_dtype == GANB_F32) DW_BF(__nv_bfloat16, float);
+  else DW_BF(__nv_bfloat16, __nv_bfloat16);
+#undef DW_BF
+  GANB_CHECK_LAUNCH("depthwise_bwd_filter_kernel");
   return 0;
 }

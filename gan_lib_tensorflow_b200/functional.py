@@ -316,6 +316,38 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     return out
 
 
+def depthwise_conv2d(x: Var, Wd: Variable, b: Variable | None, stride: int = 1, padding="SAME", out_dtype=BF16,
+                     out_grad_dtype=F32) -> Var:
+    """tf.nn.depthwise_conv2d(x, Wd [kh, kw, c, cm]) (+ bias): the `depthwise_conv2d` conv_type and the first half of
+    `separable_conv2d` (common/ops/conv2d.py:188-208).  Bandwidth-bound CUDA-core kernels in fp32 arithmetic; the input
+    is read in bf16 (like every convolution operand of this library) and the output is the bf16 operand of the pointwise
+    1x1 convolution that follows, with an fp32 gradient."""
+    n, h, w, c = x.shape
+    kh, kw, c2, cm = Wd.data.shape
+    assert c2 == c, (c2, c)
+    pt, pl, ho, wo = _pads(padding, h, w, kh, kw, stride)
+    xin = x if x.data.dtype == BF16 else cast(x, BF16)
+    y = K.depthwise_fwd(xin.data, Wd.data, b.data if b is not None else None, ho, wo, stride, pt, pl, out_dtype)
+    out = Var(y, grad_dtype=out_grad_dtype)
+    need_w = Wd.needs_grad and _tape() is not None
+    need_b = b is not None and b.needs_grad and _tape() is not None
+    if _rg(xin) or need_w or need_b:
+        out.requires_grad = True
+
+        def bwd():
+            gy = out.grad
+            if gy is None:
+                return
+            if need_b:
+                K.colsum(gy, n * ho * wo, c * cm, b.grad, 1.0)
+            if need_w:
+                K.depthwise_bwd_filter(xin.data, gy, Wd.grad, kh, kw, cm, stride, pt, pl)
+            if xin.requires_grad:
+                xin.accum(K.depthwise_bwd_input(gy, Wd.data, h, w, stride, pt, pl, xin.gdtype))
+        _tape().record(bwd)
+    return out
+
+
 SUBPIXEL_UPCONV = True   # sub-pixel form of UpsampleConv where ganb_upconv_supported() and the layer is large enough
 
 

@@ -42,7 +42,7 @@ def L():
         for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace",
                      "ganb_norm_act_bwd_sums_offset", "ganb_l1_loss_workspace", "ganb_bn_bwd_vjp_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
                      "ganb_minibatch_std_workspace", "ganb_weight_transform_workspace", "ganb_layer_norm_workspace",
-                     "ganb_layer_norm_rows",
+                     "ganb_layer_norm_rows", "ganb_depthwise_conv2d_chunks",
                      "ganb_norm_act_bwd_workspace", "ganb_colsum_workspace"):
             getattr(_L, name).restype = c_int64
     return _L
@@ -552,3 +552,34 @@ def sample_grid(samples, nw):
     grid = torch.empty((-(-n // nw) * h, nw * w, c), dtype=torch.uint8, device=samples.device)
     check(L().ganb_sample_grid(ptr(samples), dt(samples), n, h, w, c, nw, ptr(grid), _stream()), "ganb_sample_grid")
     return grid
+
+
+def depthwise_fwd(x, filt, bias, ho, wo, stride, pad_t, pad_l, out_dtype):
+    """tf.nn.depthwise_conv2d (+ bias): x [n,h,w,c], filt [kh,kw,c,cm] fp32 -> [n,ho,wo,c*cm]."""
+    n, h, w, c = x.shape
+    kh, kw, _, cm = filt.shape
+    y = torch.empty((n, ho, wo, c * cm), dtype=out_dtype, device=x.device)
+    check(L().ganb_depthwise_conv2d_fwd(ptr(x), dt(x), ptr(filt), ptr(bias), ptr(y), dt(y), n, h, w, c, cm, ho, wo, kh,
+                                        kw, stride, pad_t, pad_l, _stream()), "ganb_depthwise_conv2d_fwd")
+    return y
+
+
+def depthwise_bwd_input(dy, filt, h, w, stride, pad_t, pad_l, out_dtype):
+    n, ho, wo, _ = dy.shape
+    kh, kw, c, cm = filt.shape
+    dx = torch.empty((n, h, w, c), dtype=out_dtype, device=dy.device)
+    check(L().ganb_depthwise_conv2d_bwd_input(ptr(dy), dt(dy), ptr(filt), ptr(dx), dt(dx), n, h, w, c, cm, ho, wo, kh, kw,
+                                              stride, pad_t, pad_l, _stream()), "ganb_depthwise_conv2d_bwd_input")
+    return dx
+
+
+def depthwise_bwd_filter(x, dy, dfilt, kh, kw, cm, stride, pad_t, pad_l):
+    """Adds the filter gradient into dfilt [kh,kw,c,cm]."""
+    n, h, w, c = x.shape
+    _, ho, wo, _ = dy.shape
+    chunks = int(L().ganb_depthwise_conv2d_chunks(n, ho, wo))
+    cols = kh * kw * c * cm
+    partials = torch.empty((chunks, cols), dtype=torch.float32, device=x.device)
+    check(L().ganb_depthwise_conv2d_bwd_filter(ptr(x), dt(x), ptr(dy), dt(dy), ptr(partials), n, h, w, c, cm, ho, wo, kh,
+                                               kw, stride, pad_t, pad_l, _stream()), "ganb_depthwise_conv2d_bwd_filter")
+    colsum(partials, chunks, cols, dfilt, 1.0)

@@ -392,6 +392,23 @@ int ganb_subsample2d(const void* x, int x_dtype, void* y, int y_dtype, int n, in
 int ganb_sample_grid(const void* samples, int dtype, int n, int h, int w, int c, int nw, unsigned char* grid,
                      void* stream);
 
+/* tf.nn.depthwise_conv2d, and the depthwise half of tf.nn.separable_conv2d (common/ops/conv2d.py:188-208; the
+ * pointwise half is ganb_conv2d_igemm with a 1x1 filter):
+ *   y[n,ho,wo,ci*cm+m] = sum_{r,s} x[n, ho*stride+r-pad_t, wo*stride+s-pad_l, ci] * filter[r,s,ci,m],
+ * filter = `depthwise_filters` [kh,kw,c,cm] fp32 (conv2d.py:146-148), + bias[c*cm] when not NULL.  bwd_input writes dx [n,h,w,c]; bwd_filter writes
+ * partials[chunks][kh*kw][c*cm] (chunks = ganb_depthwise_conv2d_chunks(n, ho, wo)) whose column sums over the chunk
+ * axis (ganb_colsum, rows = chunks, c = kh*kw*c*cm) are the filter gradient in filter layout.  Any channel count. */
+int ganb_depthwise_conv2d_fwd(const void* x, int x_dtype, const float* filter, const float* bias, void* y, int y_dtype,
+                              int n, int h, int w, int c, int cm, int ho, int wo, int kh, int kw, int stride, int pad_t,
+                              int pad_l, void* stream);
+int ganb_depthwise_conv2d_bwd_input(const void* dy, int dy_dtype, const float* filter, void* dx, int dx_dtype, int n,
+                                    int h, int w, int c, int cm, int ho, int wo, int kh, int kw, int stride, int pad_t,
+                                    int pad_l, void* stream);
+int64_t ganb_depthwise_conv2d_chunks(int n, int ho, int wo);
+int ganb_depthwise_conv2d_bwd_filter(const void* x, int x_dtype, const void* dy, int dy_dtype, float* partials, int n,
+                                     int h, int w, int c, int cm, int ho, int wo, int kh, int kw, int stride, int pad_t,
+                                     int pad_l, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,25 @@ def conv2d_nhwc(x, filt, stride=1, padding="SAME"):
     return y.permute(0, 2, 3, 1)
 
 
+def depthwise_conv2d_nhwc(x, filt, stride=1, padding="SAME"):
+    """tf.nn.depthwise_conv2d(NHWC, [kh, kw, c, cm]): output channel ci*cm + m = the grouped convolution with one group
+    per input channel (conv2d.py:188-197)."""
+    kh, kw, c, cm = filt.shape
+    xc = x.permute(0, 3, 1, 2)
+    if padding == "SAME":
+        pt, pb, _ = same_pads(x.shape[1], kh, stride)
+        pl, pr, _ = same_pads(x.shape[2], kw, stride)
+        xc = F.pad(xc, (pl, pr, pt, pb))
+    elif isinstance(padding, (tuple, list)):
+        pt, pb, pl, pr = padding
+        xc = F.pad(xc, (pl, pr, pt, pb))
+    elif padding != "VALID":
+        raise ValueError(padding)
+    wg = filt.permute(2, 3, 0, 1).reshape(c * cm, 1, kh, kw)          # torch grouped layout [c*cm, 1, kh, kw]
+    y = F.conv2d(xc, wg, stride=stride, groups=c)
+    return y.permute(0, 2, 3, 1)
+
+
 def subpixel_upconv_rounded(x_low, w, r16_filters=True):
     """conv3x3_SAME(nearest2x(x_low), w) evaluated the way the B200 path does (ganb_upconv_*): four 2x2 convolutions
     over the low-resolution tensor with effective filters E_ij[p][q] = sum_{r in R_i[p], s in R_j[q]} w[r][s],
@@ -229,8 +248,8 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
     subpixel_up2 (oracle-only plumbing for UpsampleConv, resnet_block.py:83-97): `inputs` is the tensor BEFORE the
     nearest 2x upsample; the fp32 oracle upsamples and convolves exactly like the reference, the bf16-operand oracle
     mirrors the product's sub-pixel evaluation (subpixel_upconv_rounded)."""
-    if conv_type != "conv2d":
-        raise NotImplementedError("{0} is not supported by the oracle".format(conv_type))
+    if conv_type not in ("conv2d", "depthwise_conv2d", "separable_conv2d"):
+        raise NotImplementedError("{0} is not supported!".format(conv_type))   # conv2d.py:209-210
     with g.variable_scope(name):
         mask = None
         if mask_type is not None:                                     # conv2d.py:63-81
@@ -260,6 +279,28 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
         stdev = _weights_stdev if _weights_stdev is not None else filters_stdev
         fv = _memo(lambda: _uniform(stdev, (filter_size, filter_size, input_dim, output_dim)) * np.float32(gain))
         filters = g.get_variable("Filters", initializer=lambda _s: fv())   # conv2d.py:124-144
+        if channel_multiplier > 0:                                    # conv2d.py:117-126, 145-150 (no gain)
+            depthwise_filters = g.get_variable("depthwise_filters", initializer=lambda _s: _uniform(
+                stdev, (filter_size, filter_size, input_dim, channel_multiplier)))
+            pointwise_filters = g.get_variable("pointwise_filters", initializer=lambda _s: _uniform(
+                stdev, (1, 1, input_dim * channel_multiplier, output_dim)))
+        if conv_type != "conv2d":
+            # weight-norm / mask / spectral norm act on `Filters`, which these types never read (conv2d.py:153-171):
+            # only the `u` variable of the spectral norm is created
+            if spectral_normed:
+                with g.variable_scope("filters"):
+                    spectral_normed_weight(g, filters, update_collection=NO_OPS)
+            x_ = _ste_r16(inputs_) if BF16_OPERANDS else inputs_      # the B200 path reads conv operands in bf16
+            result = depthwise_conv2d_nhwc(x_, depthwise_filters, stride, padding)        # conv2d.py:188-197
+            if conv_type == "separable_conv2d":                       # conv2d.py:198-208: then the 1x1 pointwise conv
+                if BF16_OPERANDS:
+                    result = _ConvRoundedOperands.apply(result, _ste_r16(pointwise_filters), 1, "VALID")
+                else:
+                    result = conv2d_nhwc(result, pointwise_filters, 1, "VALID")
+            if biases:
+                b = g.get_variable("Biases", initializer=tfshim.constant_initializer(0.0), shape=[output_dim])
+                result = result + b                                   # fails in TF too unless the channels agree
+            return result
         if weightnorm is None:
             weightnorm = _default_weightnorm
         if weightnorm:                                                # conv2d.py:153-163

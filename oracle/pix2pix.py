@@ -20,8 +20,12 @@ def norm_layer(g, inputs, decay=0.9, epsilon=1e-5, is_training=True, norm_type="
     raise NotImplementedError("Normalization [%s] is not implemented!" % norm_type)
 
 
+_CONV_TYPE = ["conv2d", 0]   # (--conv_type, --channel_multiplier) of Pix2Pix/train.py:31-33, set per network call
+
+
 def _conv(g, x, out_channels, stride, padding, sn=False, uc=None):
-    return ops.Conv2D(g, x, x.shape[-1], out_channels, 4, stride, "Conv2D", padding=padding, spectral_normed=sn,
+    return ops.Conv2D(g, x, x.shape[-1], out_channels, 4, stride, "Conv2D", conv_type=_CONV_TYPE[0],
+                      channel_multiplier=_CONV_TYPE[1], padding=padding, spectral_normed=sn,
                       update_collection=uc, inputs_norm=False, he_init=True, biases=True)
 
 
@@ -35,8 +39,10 @@ def unet_discriminator(g, discrim_inputs, discrim_targets, ndf, spectral_normed,
     return unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding, n_layers=4)
 
 
-def unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME", keep_masks=None, deep=4):
+def unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME", keep_masks=None, deep=4,
+           conv_type="conv2d", channel_multiplier=0):
     """Pix2Pix/networks.py:174-284 (deep = 4); deep = 5 gives the layer lists of unet_generator, :373-383 / :406-415"""
+    _CONV_TYPE[:] = [conv_type, channel_multiplier]
     layers = []
     with g.variable_scope("encoder_1"):
         layers.append(_conv(g, generator_inputs, ngf, 2, padding))                               # :178-185
@@ -71,8 +77,10 @@ def unet_g(g, generator_inputs, generator_outputs_channels, ngf, padding="SAME",
     return layers[-1]
 
 
-def unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding="VALID", n_layers=3):
+def unet_d(g, discrim_inputs, discrim_targets, ndf, spectral_normed, update_collection, padding="VALID", n_layers=3,
+           conv_type="conv2d", channel_multiplier=0):
     """Pix2Pix/networks.py:287-354 (n_layers = 3)"""
+    _CONV_TYPE[:] = [conv_type, channel_multiplier]
     pad = lambda t: torch.nn.functional.pad(t, (0, 0, 1, 1, 1, 1))  # noqa: E731  tf.pad [[0,0],[1,1],[1,1],[0,0]]
     inputs = torch.cat([discrim_inputs, discrim_targets], dim=3)                                  # :293
     with g.variable_scope("layer_1"):                                                            # :296-307

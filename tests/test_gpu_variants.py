@@ -422,3 +422,72 @@ def test_resnet_pggan_forward_backward(env, bc, trans):
     print(f"resnet pggan bc={bc} trans={trans}: worst vs bf16-oracle", [(k, f"{v[0]:.1e}") for k, v in top],
           "fake", f"{worst['fake'][0]:.1e}", "logits", f"{worst['logits'][0]:.1e}")
     assert worst["logits"][0] < 4e-3 and worst["fake"][0] < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ depthwise / separable
+@pytest.mark.parametrize("n,h,cin,cm,k,stride,padding", [
+    (3, 16, 64, 2, 3, 1, "SAME"),
+    (2, 16, 72, 1, 4, 2, "SAME"),       # Pix2Pix encoder geometry (4x4 s2), ragged channels
+    (2, 9, 8, 3, 3, 2, "VALID"),
+    (2, 16, 3, 4, 4, 2, (1, 1, 1, 1)),  # RGB input, explicit pads (PatchGAN layer_1 geometry)
+])
+def test_depthwise_conv2d(env, n, h, cin, cm, k, stride, padding):
+    """conv_type='depthwise_conv2d' (common/ops/conv2d.py:188-197): forward, dx, d(depthwise_filters), dBiases.  Input
+    and cotangent are bf16-representable, so the fp32 oracle is the exact reference of the fp32-arithmetic kernels."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+    from oracle import ops as O
+
+    x = _bf16_repr(np.random.RandomState(20).standard_normal((n, h, h, cin)).astype("float32"))
+    kw = dict(conv_type="depthwise_conv2d", channel_multiplier=cm, padding=padding)
+    prod, refs = run_pair(store, tfshim, lambda xv: P.Conv2D(xv, cin, cin * cm, k, stride, "L", **kw),
+                          lambda g, xt: O.Conv2D(g, xt, cin, cin * cm, k, stride, "L", **kw), x, bf16=False)
+    assert "L/depthwise_filters" in refs["fp32"]["params"] and "L/Filters" not in refs["fp32"]["params"]
+    check(prod, refs, tol_fp32=2e-3, tag=f"depthwise {cin}x{cm} k{k} s{stride} {padding}")   # dx is stored in bf16
+    with pytest.raises(ValueError):     # tf.nn.bias_add fails unless output_dim == input_dim * channel_multiplier
+        P.Conv2D(torch.zeros(1, 8, 8, cin).cuda(), cin, cin * cm + 8, k, stride, "Bad", **kw)
+
+
+@pytest.mark.parametrize("n,h,cin,cout,cm,k,stride,sn", [
+    (3, 16, 64, 128, 1, 4, 2, False),
+    (2, 16, 64, 64, 2, 4, 1, True),      # spectral_normed: creates u, leaves the result alone (acts on `Filters`)
+    (2, 32, 3, 64, 4, 4, 2, False),      # RGB input: 12 depthwise channels into the pointwise conv
+    (2, 8, 128, 8, 1, 3, 1, False),
+])
+def test_separable_conv2d(env, n, h, cin, cout, cm, k, stride, sn):
+    """conv_type='separable_conv2d' (conv2d.py:198-208): depthwise kernel + 1x1 pointwise conv on the tensor cores."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+    from oracle import ops as O
+
+    x = np.random.RandomState(21).standard_normal((n, h, h, cin)).astype("float32")
+    kw = dict(conv_type="separable_conv2d", channel_multiplier=cm, spectral_normed=sn, update_collection="NO_OPS")
+    prod, refs = run_pair(store, tfshim, lambda xv: P.Conv2D(xv, cin, cout, k, stride, "L", **kw),
+                          lambda g, xt: O.Conv2D(g, xt, cin, cout, k, stride, "L", **kw), x)
+    assert {"L/depthwise_filters", "L/pointwise_filters", "L/Biases"} <= set(refs["fp32"]["params"])
+    assert float(np.abs(prod["params"]["L/Filters"]).max()) == 0.0        # `Filters` exists but is never read
+    if sn:
+        assert "L/filters/spectral_norm/u" in store.vars
+    check(prod, refs, tol_impl=3e-3, tag=f"separable {cin}->{cout} cm{cm} k{k} s{stride}")
+
+
+def test_pix2pix_patchgan_with_separable_convs(env):
+    """Pix2Pix --conv_type separable_conv2d --channel_multiplier 1 through unet_d (Pix2Pix/train.py:31-33, 464-465)."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200 import functional as F
+    from gan_lib_tensorflow_b200.Pix2Pix import networks as P
+    from oracle import ops as O
+    from oracle import pix2pix as OP
+
+    n, ndf = 2, 16
+    rs = np.random.RandomState(22)
+    x = rs.uniform(-1, 1, size=(n, 64, 64, 3)).astype("float32")
+    tgt = rs.uniform(-1, 1, size=(n, 64, 64, 3)).astype("float32")
+    prod, refs = run_pair(
+        store, tfshim,
+        lambda xv: P.unet_d(xv, F.Var(torch.from_numpy(tgt).cuda()), ndf, True, "NO_OPS",
+                            conv_type="separable_conv2d", channel_multiplier=1),
+        lambda g, xt: OP.unet_d(g, xt, torch.from_numpy(tgt), ndf, True, O.NO_OPS, conv_type="separable_conv2d",
+                                channel_multiplier=1), x)
+    assert prod["out"].shape == (n, 6, 6, 1)
+    check(prod, refs, tol_impl=1.2e-2, tol_fp32=1.2e-1, tag="unet_d separable")

@@ -270,7 +270,9 @@ def test_pix2pix_512_unet_generator_and_discriminator(env):
         lambda xv: P.unet_discriminator(xv, F.Var(torch.from_numpy(tgt).cuda()), ndf, True, "NO_OPS"),
         lambda g_, xt: OP.unet_discriminator(g_, xt, torch.from_numpy(tgt), ndf, True, O.NO_OPS), xd)
     assert prod["out"].shape == (2, 6, 6, 1)
-    check(prod, refs, tol_impl=1.2e-2, tol_fp32=1.2e-1, tag="unet_discriminator")   # 6 layers of lrelu-mask flips (5: 6e-3)
+    # six layers of leaky-ReLU mask flips (unet_d's five sit at 6e-3 against the bf16-operand oracle): measured band
+    assert rel(prod["out"], refs["bf16"]["out"]) < 4e-3
+    check_band(prod, refs, tag="unet_discriminator")
 
 
 # ------------------------------------------------------------------------------------------------ SNGAN ImageNet-128

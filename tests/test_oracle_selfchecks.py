@@ -198,3 +198,39 @@ def test_golden_vectors():
     now = make_golden.compute()
     for key, val in gold.items():
         np.testing.assert_allclose(np.asarray(now[key]), np.asarray(val), rtol=2e-5, atol=1e-7, err_msg=key)
+
+
+def test_depthwise_conv_matches_an_explicit_loop():
+    """oracle.ops.depthwise_conv2d_nhwc (tf.nn.depthwise_conv2d: output channel ci*cm + m, TF SAME padding) against a
+    NumPy loop written from the definition; separable_conv2d = that followed by the 1x1 pointwise convolution."""
+    import numpy as np
+    import torch
+
+    from oracle import ops as O
+    from oracle import tfshim
+
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((2, 7, 6, 3)).astype("float32")
+    f = rs.standard_normal((3, 4, 3, 2)).astype("float32")
+    for stride in (1, 2):
+        y = O.depthwise_conv2d_nhwc(torch.from_numpy(x), torch.from_numpy(f), stride, "SAME").numpy()
+        pt, _, ho = O.same_pads(7, 3, stride)
+        pl, _, wo = O.same_pads(6, 4, stride)
+        ref = np.zeros((2, ho, wo, 6), "float64")
+        for a in range(ho):
+            for b in range(wo):
+                for r in range(3):
+                    for q in range(4):
+                        hi, wi = a * stride + r - pt, b * stride + q - pl
+                        if 0 <= hi < 7 and 0 <= wi < 6:
+                            ref[:, a, b, :] += (x[:, hi, wi, :, None] * f[r, q][None]).reshape(2, 6)
+        assert y.shape == ref.shape and np.abs(y - ref).max() < 1e-5
+    np.random.seed(0)
+    g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    out = O.Conv2D(g, torch.from_numpy(x), 3, 16, 4, 2, "L", conv_type="separable_conv2d", channel_multiplier=4,
+                   spectral_normed=True, update_collection=O.NO_OPS)
+    assert list(g.vars) == ["L/Filters", "L/depthwise_filters", "L/pointwise_filters", "L/filters/spectral_norm/u",
+                            "L/Biases"]
+    dw = O.depthwise_conv2d_nhwc(torch.from_numpy(x), g.vars["L/depthwise_filters"], 2, "SAME")
+    pw = torch.einsum("nhwc,co->nhwo", dw, g.vars["L/pointwise_filters"][0, 0])
+    assert torch.allclose(out, pw, atol=1e-5)
