@@ -14,32 +14,24 @@ import torch
 from .. import functional as F
 from ..framework import Var, get_store
 from ..training import TwoPlayer
-from . import networks
-
-
-class Pix2Pix(object):
-    """Pix2Pix/model.py:15-100 for the unet_g / unet_d topology (the one config 4 names)."""
-
-    def get_generator(self, inputs, outputs_channels, ngf=64, padding='SAME', reuse=False, keep_masks=None, **_kw):
-        with get_store().variable_scope('g_net', reuse=reuse):
-            return networks.unet_g(inputs, outputs_channels, ngf, padding=padding, keep_masks=keep_masks)
-
-    def get_discriminator(self, inputs, targets, ndf=64, spectral_normed=True, update_collection=None,
-                          padding='VALID', reuse=False, **_kw):
-        with get_store().variable_scope('d_net', reuse=reuse):
-            return networks.unet_d(inputs, targets, ndf, spectral_normed, update_collection, padding=padding)
+from . import networks  # noqa: F401
+from .model import Pix2Pix
 
 
 class Trainer:
     def __init__(self, ngf: int = 64, ndf: int = 64, size: int = 256, loss_type: str = 'HINGE',
                  gan_weight: float = 1.0, l1_weight: float = 100.0, initial_lr: float = 0.0002, end_lr: float = 0.0001,
                  beta1: float = 0.0, beta2: float = 0.9, max_steps: int = 23600, seed: int | None = 0,
-                 world_size: int = 1, grad_allreduce=None):
+                 world_size: int = 1, grad_allreduce=None, net_type: str = 'UNet_Attention', conv_type: str = 'conv2d',
+                 channel_multiplier: int = 0):
+        """net_type / conv_type / channel_multiplier: the flags of Pix2Pix/train.py:31-36 ('UNet_Attention' = unet_g /
+        unet_d, the 256x256 topology of config 4; 'UNet' = the 512x512 pair)."""
         if loss_type == 'WGAN-GP':
             raise NotImplementedError('the gradient penalty of Pix2Pix/train.py:489-507 is not built (SURVEY 8(f))')
         self.store = get_store()
         self.model = Pix2Pix()
         self.ngf, self.ndf, self.loss_type = ngf, ndf, loss_type
+        self.net = dict(net_type=net_type, conv_type=conv_type, channel_multiplier=channel_multiplier)
         self.gan_weight, self.l1_weight = gan_weight, l1_weight
         self.initial_lr, self.end_lr, self.max_steps = initial_lr, end_lr, max_steps
         self.global_step = 0
@@ -48,9 +40,9 @@ class Trainer:
         dev = self.store.device
         with self.store.building():                      # create_model(): G, D(real), D(fake, reuse)
             x0 = torch.zeros(1, size, size, 3, device=dev)
-            out0 = self.model.get_generator(x0, 3, ngf=ngf)
-            self.model.get_discriminator(x0, x0, ndf=ndf, update_collection="NO_OPS")
-            self.model.get_discriminator(x0, out0, ndf=ndf, update_collection="NO_OPS", reuse=True)
+            out0 = self.model.get_generator(x0, 3, ngf=ngf, **self.net)
+            self.model.get_discriminator(x0, x0, ndf=ndf, update_collection="NO_OPS", **self.net)
+            self.model.get_discriminator(x0, out0, ndf=ndf, update_collection="NO_OPS", reuse=True, **self.net)
         self.players = TwoPlayer("d_net", "g_net", beta1=beta1, beta2=beta2, world_size=world_size,
                                  grad_allreduce=grad_allreduce)
         self.players.finalize()
@@ -63,16 +55,17 @@ class Trainer:
     # ------------------------------------------------------------------------------------------ losses
     def d_loss(self, inputs, targets, keep_masks=None):
         m = self.model
-        outputs = m.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=keep_masks)   # g_net is frozen
-        predict_real = m.get_discriminator(inputs, targets, ndf=self.ndf, update_collection=None, reuse=True)
-        predict_fake = m.get_discriminator(inputs, Var(outputs.data), ndf=self.ndf, update_collection=None, reuse=True)
+        outputs = m.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=keep_masks, **self.net)  # g_net frozen
+        predict_real = m.get_discriminator(inputs, targets, ndf=self.ndf, update_collection=None, reuse=True, **self.net)
+        predict_fake = m.get_discriminator(inputs, Var(outputs.data), ndf=self.ndf, update_collection=None, reuse=True,
+                                           **self.net)
         pr, pf = F.reshape(predict_real, (-1,)), F.reshape(predict_fake, (-1,))
         return F.gan_loss(F.concat_rows(pr, pf), 'd', n_real=pr.shape[0], loss_type=self.loss_type)
 
     def g_loss(self, inputs, targets, keep_masks=None):
         m = self.model
-        outputs = m.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=keep_masks)
-        predict_fake = m.get_discriminator(inputs, outputs, ndf=self.ndf, update_collection=None, reuse=True)
+        outputs = m.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=keep_masks, **self.net)
+        predict_fake = m.get_discriminator(inputs, outputs, ndf=self.ndf, update_collection=None, reuse=True, **self.net)
         gen_loss_gan = F.gan_loss(F.reshape(predict_fake, (-1,)), 'g', scale=self.gan_weight, loss_type=self.loss_type)
         gen_loss_l1 = F.l1_loss(targets, outputs, scale=self.l1_weight)
         self.last = {'gen_loss_GAN_weighted': gen_loss_gan.data, 'gen_loss_L1_weighted': gen_loss_l1.data}

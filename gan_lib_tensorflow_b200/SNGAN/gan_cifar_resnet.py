@@ -331,6 +331,44 @@ class Trainer:
         rank only)."""
         return sum(self.graph_launches.values())
 
+    # ------------------------------------------------------------------------------------------ evaluation fetches
+    def disc_cost_eval(self, data_int, labels):
+        """session.run([disc_cost], feed_dict={all_real_data_int, all_real_labels}) -- the dev-set cost of
+        gan_cifar_resnet.py:640-647: fresh noise, G forward, D forward on real + fake, no gradients.  The D call of this
+        graph has update_collection=None, so -- like the reference -- every evaluation also assigns u."""
+        st = self.store
+        b = self.batch
+        self._invalidate_caches(packs=False)    # graph replays move the weights behind the Python-side version counters
+        self.set_real_batch(data_int, labels)
+        self.sample_noise()
+        with st.stat_towers(self.n_towers):
+            fake = self.generator(b, self.real_labels, noise=self.z_d, reuse=True)
+        real = self._preprocess_real(b)
+        d_in = torch.cat([real.reshape(b, -1), fake.data.reshape(b, -1)], dim=0)      # tensor plumbing (no arithmetic)
+        d_labels = torch.cat([self.real_labels, self.real_labels], dim=0)
+        disc_all, _ = self.discriminator(Var(d_in), d_labels, update_collection=None, reuse=True)
+        loss = F.gan_loss(disc_all, 'hinge_d', n_real=b).data
+        self._invalidate_caches(packs=False)
+        return loss
+
+    def gen_cost_eval(self):
+        """The `gen_cost` fetch that the reference adds to every critic step's session.run (:611-615): a forward pass of
+        the generator-step graph on fresh noise / labels (D with NO_OPS), nothing updated."""
+        st = self.store
+        self._invalidate_caches(packs=False)
+        self.sample_noise()
+        with st.stat_towers(self.n_towers):
+            fake = self.generator(self.gen_batch, self.fake_labels, noise=self.z_g, reuse=True)
+        disc_fake, _ = self.discriminator(fake, self.fake_labels, update_collection="NO_OPS", reuse=True)
+        loss = F.gan_loss(disc_fake, 'gen').data
+        self._invalidate_caches(packs=False)
+        return loss
+
+    def fixed_samples(self, fixed_noise, fixed_labels):
+        """fixed_noise_samples of :530-533: Generator(100, fixed_labels, noise=fixed_noise, reuse=True) as ONE tower."""
+        out = self.generator(fixed_noise.shape[0], fixed_labels, noise=fixed_noise, reuse=True)
+        return out.data
+
     def train_iteration(self, iteration: int, batches):
         """One reference iteration (gan_cifar_resnet.py:599-620): G-step if iteration > 0, then N_CRITIC D-steps.
         `batches` yields (data_int, labels)."""
@@ -343,3 +381,91 @@ class Trainer:
             self.sample_noise()
             self.d_step(iteration)
         return self.d_loss, self.g_loss
+
+
+def synthetic_batches(batch_size: int = BATCH_SIZE, seed: int = 0, n_batches: int = 8, output_dim: int = OUTPUT_DIM,
+                      n_classes: int = 10):
+    """Stand-in for common.data.cifar10.load (:557): an epoch generator factory over CHW-flattened int pixels in
+    [0, 255] and int labels, shaped like the loader's batches (there is no dataset in this environment)."""
+    rs = np.random.RandomState(seed)
+    data = rs.randint(0, 256, size=(n_batches, batch_size, output_dim)).astype('int32')
+    labels = rs.randint(0, n_classes, size=(n_batches, batch_size)).astype('int32')
+
+    def get_epoch():
+        for i in range(n_batches):
+            yield data[i], labels[i]
+    return get_epoch
+
+
+def train(iters: int = ITERS, train_gen=None, dev_gen=None, out_dir: str = '.', checkpoint_dir: str | None = None,
+          batch_size: int = BATCH_SIZE, seed: int | None = 0, capture: bool = True, fetch_gen_cost: bool = False,
+          restore: bool = False, sample_every: int = 100, flush_until: int = 500, flush_every: int = 1000,
+          trainer: "Trainer | None" = None):
+    """The training loop of the reference script (gan_cifar_resnet.py:528-660) on the B200 ops: per iteration one
+    generator step (skipped at iteration 0) and N_CRITIC critic steps, `lib.plot` scalars d_cost / g_cost, every
+    `sample_every` iterations the dev-set cost and a 10 x 10 sample grid from fixed noise (labels 0..9 repeated), flush +
+    checkpoint while iteration < flush_until and every flush_every-th iteration.
+
+    train_gen / dev_gen: epoch generator factories as returned by common.data.cifar10.load (default: synthetic).
+    fetch_gen_cost: evaluate gen_cost inside every critic step like the reference's session.run does (:611-615; a
+    redundant generator-step forward pass) instead of reporting the loss of the last generator step.
+    The Inception score hook (:634-637) needs the external Inception graph and is not run.  Returns the Trainer."""
+    import os
+
+    from ..common import misc as lib_misc
+    from ..common import plot as lib_plot
+
+    tr = trainer or Trainer(batch_size=batch_size, seed=seed)
+    st = tr.store
+    # :530-533 -- drawn from the global NumPy stream right after graph construction
+    fixed_noise = torch.from_numpy(np.random.normal(size=(100, 128)).astype('float32')).to(st.device)
+    fixed_labels = torch.from_numpy(np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype='int32')).to(st.device)
+    train_gen = train_gen or synthetic_batches(batch_size, seed=0)
+    dev_gen = dev_gen or synthetic_batches(batch_size, seed=1, n_batches=2)
+    checkpoint_dir = checkpoint_dir or os.path.join(out_dir, 'checkpoint')
+    lib_plot.set_output_dir(out_dir)
+    if restore:                                                           # :590-594
+        ckpts = sorted(f for f in os.listdir(checkpoint_dir) if f.startswith('model.ckpt-')) \
+            if os.path.isdir(checkpoint_dir) else []
+        if ckpts:
+            latest = max(ckpts, key=lambda f: int(f.split('-')[1].split('.')[0]))
+            print('restore model from: {}...'.format(latest))
+            lib_misc.restore_checkpoint(os.path.join(checkpoint_dir, latest), (tr.gen_opt, tr.disc_opt))
+
+    def inf_train_gen():                                                  # :560-566
+        while True:
+            for images_, labels_ in train_gen():
+                yield images_, labels_
+
+    gen = inf_train_gen()
+    captured = False
+    for iteration in range(iters):
+        if 0 < iteration:                                                 # :602-603
+            tr.sample_noise()
+            tr.g_step(iteration)
+        gen_cost = tr.g_loss
+        for _ in range(N_CRITIC):                                         # :605-620
+            _data, _labels = next(gen)
+            tr.set_real_batch(_data, _labels)
+            tr.sample_noise()
+            tr.d_step(iteration)
+            if fetch_gen_cost:
+                gen_cost = tr.gen_cost_eval()
+        if capture and not captured and iteration >= 1:                   # one eager G-step and D-step have run
+            tr.capture()
+            captured = True
+        lib_plot.plot('d_cost', tr.d_loss)                                # :625-626
+        lib_plot.plot('g_cost', gen_cost)
+        if iteration % sample_every == sample_every - 1:                  # :639-649
+            dev_disc_costs = [tr.disc_cost_eval(images, _labels).clone() for images, _labels in dev_gen()]
+            lib_plot.plot('dev_cost', torch.stack(dev_disc_costs).mean())
+            samples = tr.fixed_samples(fixed_noise, fixed_labels)         # generate_image, :536-539
+            lib_misc.save_images(samples.reshape(100, 32, 32, 3), os.path.join(out_dir, 'samples_{}.png'.format(iteration)))
+        if (iteration < flush_until) or (iteration % flush_every == flush_every - 1):   # :651-656
+            lib_plot.flush()
+            if not os.path.exists(checkpoint_dir):
+                os.mkdir(checkpoint_dir)
+            lib_misc.save_checkpoint(os.path.join(checkpoint_dir, 'model.ckpt-{}'.format(iteration)),
+                                     (tr.gen_opt, tr.disc_opt))
+        lib_plot.tick()
+    return tr

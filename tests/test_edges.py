@@ -142,6 +142,35 @@ def test_get_loss_needs_a_player_inside_a_tape(host):  # noqa: F811
     assert z.shape == (5, 7) and z.dtype == np.float32
 
 
+def test_reference_train_loop_call_sequence(host, tmp_path, capsys):  # noqa: F811
+    """SNGAN.gan_cifar_resnet.train (the loop of gan_cifar_resnet.py:599-658) in host-logic mode: G-step skipped at
+    iteration 0, N_CRITIC critic steps per iteration, the gen_cost fetch, dev cost + sample grid every `sample_every`,
+    flush + checkpoint, tick."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+    from gan_lib_tensorflow_b200.common import plot
+
+    plot.reset()
+    tr = P.train(iters=3, out_dir=str(tmp_path), batch_size=4, capture=False, fetch_gen_cost=True, sample_every=2)
+    names = rec.names()
+    assert names.count("ganb_adam") == 2 + 3 * P.N_CRITIC          # G-steps at iterations 1, 2; 5 D-steps each
+    assert tr.gen_opt.t == 2 and tr.disc_opt.t == 15
+    assert names.count("ganb_sample_grid") == 1                     # iteration 1 only (1 % 2 == 1)
+    # gan_loss launches: 15 D-steps + 2 G-steps + 15 gen_cost fetches + 2 dev batches
+    assert names.count("ganb_gan_loss") == 15 + 2 + 15 + 2
+    assert os.path.exists(tmp_path / "samples_1.png") and os.path.exists(tmp_path / "log.pkl")
+    assert sorted(os.listdir(tmp_path / "checkpoint")) == ["model.ckpt-0.npz", "model.ckpt-1.npz", "model.ckpt-2.npz"]
+    with open(tmp_path / "log.pkl", "rb") as fh:
+        log = pickle.load(fh)
+    assert set(log) == {"d_cost", "g_cost", "dev_cost"} and sorted(log["d_cost"]) == [0, 1, 2] and list(log["dev_cost"]) == [1]
+    assert "iter 2" in capsys.readouterr().out
+    with np.load(tmp_path / "checkpoint" / "model.ckpt-2.npz") as z:
+        assert "Generator/G.Input/W/Adam_1" in z.files and "beta2_power_1" in z.files
+        assert abs(float(z["beta2_power"]) - 0.9 ** 3) < 1e-6 and abs(float(z["beta2_power_1"]) - 0.9 ** 16) < 1e-6
+    plot.reset()
+    plot.set_output_dir('.')
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,h,w,dtype", [(100, 32, 32, torch.float32), (12, 8, 16, torch.float32),
@@ -201,4 +230,47 @@ def test_get_loss_pair_matches_the_oracle(loss_type):
                 np.testing.assert_allclose(rv.grad.cpu().numpy(), gr.numpy(), atol=1e-6)
             np.testing.assert_allclose(fv.grad.cpu().numpy(), gf.numpy(), atol=1e-6)
     finally:
+        framework.set_store(None)
+
+
+@pytest.mark.gpu
+def test_reference_train_loop_runs_and_resumes(tmp_path):
+    """gan_cifar_resnet.train for a few iterations on synthetic batches with CUDA-graph capture: finite losses, a
+    sample grid, log.pkl and TF-1-named checkpoints; a second call with restore=True resumes from the last checkpoint
+    (parameters, Adam slots and step counts)."""
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+    from gan_lib_tensorflow_b200.common import misc, plot
+
+    plot.reset()
+    framework.reset_default_graph("cuda", u_seed=2)
+    try:
+        tr = P.train(iters=4, out_dir=str(tmp_path), batch_size=16, capture=True, sample_every=2)
+        torch.cuda.synchronize()
+        assert tr._graphs and np.isfinite(float(tr.d_loss.item())) and np.isfinite(float(tr.g_loss.item()))
+        with open(tmp_path / "log.pkl", "rb") as fh:
+            log = pickle.load(fh)
+        assert sorted(log["d_cost"]) == [0, 1, 2, 3] and sorted(log["dev_cost"]) == [1, 3]
+        assert all(np.isfinite(v) for v in log["d_cost"].values()) and 0.0 <= log["dev_cost"][3] < 10.0
+        from PIL import Image
+        img = np.asarray(Image.open(tmp_path / "samples_3.png"))
+        assert img.shape == (320, 320, 3) and img.std() > 1.0
+        state = misc.checkpoint_state((tr.gen_opt, tr.disc_opt))
+        with np.load(tmp_path / "checkpoint" / "model.ckpt-3.npz") as z:
+            for k in ("Generator/G.Block.1.Conv1/Filters", "Discriminator/D.Block.2.Conv1/filters/spectral_norm/u",
+                      "Discriminator/D.Output/W/Adam_1"):
+                np.testing.assert_array_equal(z[k], state[k], err_msg=k)
+        # resume in a fresh graph
+        plot.reset()
+        framework.reset_default_graph("cuda", u_seed=3)
+        tr2 = P.Trainer(batch_size=16, seed=1)
+        before = tr2.store.vars["Generator/G.Input/W"].data.clone()
+        P.train(iters=0, out_dir=str(tmp_path), batch_size=16, restore=True, trainer=tr2)
+        assert tr2.gen_opt.t == 3 and tr2.disc_opt.t == 20
+        assert not torch.equal(before, tr2.store.vars["Generator/G.Input/W"].data)
+        np.testing.assert_array_equal(tr2.store.vars["Generator/G.Input/W"].data.cpu().numpy(),
+                                      state["Generator/G.Input/W"])
+    finally:
+        plot.reset()
+        plot.set_output_dir('.')
         framework.set_store(None)

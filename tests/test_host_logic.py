@@ -320,6 +320,35 @@ def test_resnet_pggan_trainer_call_sequence(host):
         PT.Trainer(block_count=1, trans=False, model="vgg")
 
 
+def test_pix2pix_model_net_type_dispatch(host):
+    """Pix2Pix/model.py:15-100: 'UNet' -> the nine-level unet_generator / unet_discriminator, 'UNet_Attention' -> unet_g /
+    unet_d; conv_type / channel_multiplier reach every Conv2D; the unrunnable families raise."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.Pix2Pix.model import Pix2Pix
+    from gan_lib_tensorflow_b200.Pix2Pix.train import Trainer
+
+    m = Pix2Pix()
+    x = torch.zeros(1, 512, 512, 3)
+    out = m.get_generator(x, 3, ngf=8, net_type='UNet')
+    assert tuple(out.shape) == (1, 512, 512, 3) and "g_net/encoder_9/Conv2D/Filters" in store.vars
+    d = m.get_discriminator(x, out, ndf=8, update_collection="NO_OPS", net_type='UNet')
+    assert tuple(d.shape) == (1, 30, 30, 1) and "d_net/layer_6/Conv2D/filters/spectral_norm/u" in store.vars
+    for net_type in ('ResNet', 'VGG', 'nope'):
+        with pytest.raises(NotImplementedError):
+            m.get_generator(x, 3, net_type=net_type, reuse=True)
+        with pytest.raises(NotImplementedError):
+            m.get_discriminator(x, x, net_type=net_type, reuse=True)
+    from gan_lib_tensorflow_b200 import framework
+    store2 = framework.reset_default_graph("cpu", u_seed=2)
+    tr = Trainer(ngf=8, ndf=8, size=256, conv_type='separable_conv2d', channel_multiplier=1)
+    assert "g_net/encoder_9/Conv2D/Filters" not in store2.vars          # default net_type: unet_g / unet_d
+    assert "g_net/encoder_8/Conv2D/pointwise_filters" in store2.vars and "d_net/layer_5/Conv2D/depthwise_filters" in store2.vars
+    n0 = len(rec.calls)
+    tr.d_step(torch.zeros(1, 256, 256, 3), torch.zeros(1, 256, 256, 3))
+    calls = rec.names()[n0:]
+    assert calls.count("ganb_depthwise_conv2d_fwd") == 16 + 2 * 5 and calls.count("ganb_depthwise_conv2d_bwd_filter") == 2 * 5
+
+
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
     store, _ = host
     from gan_lib_tensorflow_b200.common import resnet_block
