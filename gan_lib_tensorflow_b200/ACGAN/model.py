@@ -22,6 +22,9 @@ BF16 = torch.bfloat16
 
 
 class ACGAN(object):
+    G_INPUT_DIM = 1024    # channels of the 4x4 seed (ACGAN/model.py:34-35)
+    G_DIM = 256           # channels of the three 'up' blocks (:37-42); ACGAN/model_.py uses 128 / 128
+
     def __init__(self):
         pass
 
@@ -31,10 +34,10 @@ class ACGAN(object):
         with store.variable_scope('g_net', reuse=reuse):
             z_var_ = F.as_var(z_var)
             z_var_ = F.reshape(z_var_, (z_var_.shape[0], -1))
-            output = linear_ops.Linear(z_var_, z_var_.shape[-1], 4 * 4 * 1024, 'G.Input', out_dtype=BF16)
-            output = F.reshape(output, (-1, 4, 4, 1024))
+            output = linear_ops.Linear(z_var_, z_var_.shape[-1], 4 * 4 * self.G_INPUT_DIM, 'G.Input', out_dtype=BF16)
+            output = F.reshape(output, (-1, 4, 4, self.G_INPUT_DIM))
             for i in (1, 2, 3):
-                output = rb.ResidualBlock(output, output.shape[-1], 256, 3, 'G.%d' % i, resample='up', labels=labels,
+                output = rb.ResidualBlock(output, output.shape[-1], self.G_DIM, 3, 'G.%d' % i, resample='up', labels=labels,
                                           activation_fn='relu', out_dtype=BF16)
             # Normalize('G.OutputN', output) has no labels -> plain batch norm; fused with the relu behind it
             output, _ = rb._norm_act('G.OutputN', output, None, rb._normalize_kind('G.OutputN', None, False), 'relu')

@@ -349,6 +349,18 @@ def test_pix2pix_model_net_type_dispatch(host):
     assert calls.count("ganb_depthwise_conv2d_fwd") == 16 + 2 * 5 and calls.count("ganb_depthwise_conv2d_bwd_filter") == 2 * 5
 
 
+def test_acgan_narrow_generator_variant(host):
+    """ACGAN/model_.py: 4x4x128 seed, 128-channel blocks, same names."""
+    store, _ = host
+    from gan_lib_tensorflow_b200.ACGAN.model_ import ACGAN
+
+    out = ACGAN().get_generator(torch.zeros(2, 128), labels=torch.zeros(2, dtype=torch.int32))
+    assert tuple(out.shape) == (2, 32, 32, 3)
+    assert tuple(store.vars["g_net/G.Input/W"].data.shape) == (128, 2048)
+    assert tuple(store.vars["g_net/G.3.Conv2/Filters"].data.shape) == (3, 3, 128, 128)
+    assert "g_net/G.1.Shortcut/Filters" in store.vars      # 'up' blocks always have a conv shortcut
+
+
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
     store, _ = host
     from gan_lib_tensorflow_b200.common import resnet_block
