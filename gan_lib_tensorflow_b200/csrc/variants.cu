@@ -463,6 +463,168 @@ subsample2d_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int h, int w
   }
 }
 
+// ---- 8-channel fast paths (channel_multiplier 1, c % 8 == 0, bf16 activations): one 16-byte load per tap and thread
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+depthwise_fwd_v8_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ f, const float* __restrict__ bias,
+                        TOut* __restrict__ y, int h, int w, int c, int ho, int wo, int kh, int kw, int stride, int pad_t,
+                        int pad_l, int64_t total8) {
+  pdl_wait();
+  const int cg = c >> 3;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total8; i += gridDim.x * 256LL) {
+    const int c8 = static_cast<int>(i % cg) * 8;
+    int64_t p = i / cg;
+    const int ow = static_cast<int>(p % wo);
+    p /= wo;
+    const int oh = static_cast<int>(p % ho);
+    const int64_t img = p / ho;
+    float acc[8];
+    if (bias) ld8(bias + c8, acc);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    }
+    for (int r = 0; r < kh; ++r) {
+      const int hi = oh * stride + r - pad_t;
+      if (hi < 0 || hi >= h) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int wi = ow * stride + q - pad_l;
+        if (wi < 0 || wi >= w) continue;
+        float a[8], ff[8];
+        ld8(x + ((img * h + hi) * w + wi) * c + c8, a);
+        ld8(f + (r * kw + q) * c + c8, ff);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += a[j] * ff[j];
+      }
+    }
+    st8(y + i * 8, acc);
+  }
+}
+
+template <typename TDy, typename TOut>
+__global__ void __launch_bounds__(256)
+depthwise_bwd_input_v8_kernel(const TDy* __restrict__ dy, const float* __restrict__ f, TOut* __restrict__ dx, int h, int w,
+                              int c, int ho, int wo, int kh, int kw, int stride, int pad_t, int pad_l, int64_t total8) {
+  pdl_wait();
+  const int cg = c >> 3;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < total8; i += gridDim.x * 256LL) {
+    const int c8 = static_cast<int>(i % cg) * 8;
+    int64_t p = i / cg;
+    const int wi = static_cast<int>(p % w);
+    p /= w;
+    const int hi = static_cast<int>(p % h);
+    const int64_t img = p / h;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < kh; ++r) {
+      const int th = hi + pad_t - r;
+      if (th < 0 || th % stride) continue;
+      const int oh = th / stride;
+      if (oh >= ho) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int tw = wi + pad_l - q;
+        if (tw < 0 || tw % stride) continue;
+        const int ow = tw / stride;
+        if (ow >= wo) continue;
+        float g[8], ff[8];
+        ld8(dy + ((img * ho + oh) * wo + ow) * c + c8, g);
+        ld8(f + (r * kw + q) * c + c8, ff);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += g[j] * ff[j];
+      }
+    }
+    st8(dx + i * 8, acc);
+  }
+}
+
+// Filter gradient, fast path: one block per pixel chunk handles ALL KS*KS taps (dy is read once per pixel); thread =
+// (pixel lane, 8-channel group) with KS*KS*8 accumulators, lanes folded through shared memory tap by tap.
+template <int KS, typename TDy>
+__global__ void __launch_bounds__(256)
+depthwise_bwd_filter_v8_kernel(const __nv_bfloat16* __restrict__ x, const TDy* __restrict__ dy,
+                               float* __restrict__ partial, int h, int w, int c, int ho, int wo, int stride, int pad_t,
+                               int pad_l, int64_t pixels, int64_t per_chunk) {
+  pdl_wait();
+  __shared__ float sm[2048];
+  const int cg = c >> 3;
+  const int lanes = 256 / cg;
+  const int cgi = threadIdx.x % cg, lane = threadIdx.x / cg;
+  const bool active = lane < lanes;
+  const int c8 = cgi * 8;
+  float acc[KS * KS][8];
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const int64_t p0 = blockIdx.x * per_chunk;
+  const int64_t p1 = p0 + per_chunk < pixels ? p0 + per_chunk : pixels;
+  if (active) {
+    for (int64_t p = p0 + lane; p < p1; p += lanes) {
+      const int ow = static_cast<int>(p % wo);
+      const int64_t t2 = p / wo;
+      const int oh = static_cast<int>(t2 % ho);
+      const int64_t img = t2 / ho;
+      float g[8];
+      ld8(dy + p * c + c8, g);
+#pragma unroll
+      for (int r = 0; r < KS; ++r) {
+        const int hi = oh * stride + r - pad_t;
+        if (hi < 0 || hi >= h) continue;
+#pragma unroll
+        for (int q = 0; q < KS; ++q) {
+          const int wi = ow * stride + q - pad_l;
+          if (wi < 0 || wi >= w) continue;
+          float a[8];
+          ld8(x + ((img * h + hi) * w + wi) * c + c8, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r * KS + q][j] += a[j] * g[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t) {
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sm[lane * c + c8 + j] = acc[t][j];
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += 256) {
+      float s2 = 0.f;
+      for (int l = 0; l < lanes; ++l) s2 += sm[l * c + ch];
+      partial[(static_cast<int64_t>(blockIdx.x) * (KS * KS) + t) * c + ch] = s2;
+    }
+  }
+}
+
 // ================================================================================================ sample grid
 // generate_image + save_images (SNGAN/gan_cifar_resnet.py:536-539, common/misc.py:215-244): samples in (-1, 1) ->
 // ((s + 1) * 127.5) truncated like astype('int32') -> image k at tile (k / nw, k % nw) of an [nh*h, nw*w, c] uint8 grid.
@@ -797,6 +959,18 @@ extern "C" int ganb_depthwise_conv2d_fwd(const void* x, int x_dtype, const float
   if (!x || !filter || !y) return fail(GANB_E_BADARG, "depthwise_conv2d_fwd: null buffer");
   if (!dw_args_ok(n, h, w, c, cm, ho, wo, kh, kw, stride)) return fail(GANB_E_BADARG, "depthwise_conv2d_fwd: bad shape");
   const int64_t total = static_cast<int64_t>(n) * ho * wo * c * cm;
+  if (cm == 1 && c % 8 == 0 && x_dtype == GANB_BF16) {   // 8 channels per thread
+    const int64_t total8 = total / 8;
+    if (y_dtype == GANB_F32)
+      launch_k(depthwise_fwd_v8_kernel<float>, flat_grid(total8), 256, 0, STREAM, static_cast<const __nv_bfloat16*>(x),
+               filter, bias, static_cast<float*>(y), h, w, c, ho, wo, kh, kw, stride, pad_t, pad_l, total8);
+    else
+      launch_k(depthwise_fwd_v8_kernel<__nv_bfloat16>, flat_grid(total8), 256, 0, STREAM,
+               static_cast<const __nv_bfloat16*>(x), filter, bias, static_cast<__nv_bfloat16*>(y), h, w, c, ho, wo, kh,
+               kw, stride, pad_t, pad_l, total8);
+    GANB_CHECK_LAUNCH("depthwise_fwd_v8_kernel");
+    return 0;
+  }
 #define DW_FWD(TI, TO)                                                                                                \
   launch_k(depthwise_fwd_kernel<TI, TO>, flat_grid(total), 256, 0, STREAM, static_cast<const TI*>(x), filter, bias,   \
            static_cast<TO*>(y), h, w, c, cm, ho, wo, kh, kw, stride, pad_t, pad_l, total)
@@ -816,6 +990,19 @@ extern "C" int ganb_depthwise_conv2d_bwd_input(const void* dy, int dy_dtype, con
   if (!dw_args_ok(n, h, w, c, cm, ho, wo, kh, kw, stride))
     return fail(GANB_E_BADARG, "depthwise_conv2d_bwd_input: bad shape");
   const int64_t total = static_cast<int64_t>(n) * h * w * c;
+  if (cm == 1 && c % 8 == 0) {
+    const int64_t total8 = total / 8;
+#define DW_BI8(TD, TO)                                                                                                \
+  launch_k(depthwise_bwd_input_v8_kernel<TD, TO>, flat_grid(total8), 256, 0, STREAM, static_cast<const TD*>(dy), filter, \
+           static_cast<TO*>(dx), h, w, c, ho, wo, kh, kw, stride, pad_t, pad_l, total8)
+    if (dy_dtype == GANB_F32 && dx_dtype == GANB_F32) DW_BI8(float, float);
+    else if (dy_dtype == GANB_F32) DW_BI8(float, __nv_bfloat16);
+    else if (dx_dtype == GANB_F32) DW_BI8(__nv_bfloat16, float);
+    else DW_BI8(__nv_bfloat16, __nv_bfloat16);
+#undef DW_BI8
+    GANB_CHECK_LAUNCH("depthwise_bwd_input_v8_kernel");
+    return 0;
+  }
 #define DW_BI(TD, TO)                                                                                                 \
   launch_k(depthwise_bwd_input_kernel<TD, TO>, flat_grid(total), 256, 0, STREAM, static_cast<const TD*>(dy), filter,  \
            static_cast<TO*>(dx), h, w, c, cm, ho, wo, kh, kw, stride, pad_t, pad_l, total)
@@ -829,7 +1016,7 @@ extern "C" int ganb_depthwise_conv2d_bwd_input(const void* dy, int dy_dtype, con
 }
 
 static int dw_chunks(int64_t pixels) {
-  int64_t ch = ceil_div64(pixels, 256);      // >= 256 pixels per block
+  int64_t ch = ceil_div64(pixels, 64);       // >= 64 pixels per block
   if (ch > DW_CHUNKS_MAX) ch = DW_CHUNKS_MAX;
   return static_cast<int>(ch < 1 ? 1 : ch);
 }
@@ -847,6 +1034,18 @@ extern "C" int ganb_depthwise_conv2d_bwd_filter(const void* x, int x_dtype, cons
   const int64_t pixels = static_cast<int64_t>(n) * ho * wo;
   const int chunks = dw_chunks(pixels);
   const int64_t per_chunk = ceil_div64(pixels, chunks);
+  if (cm == 1 && c % 8 == 0 && c <= 2048 && x_dtype == GANB_BF16 && kh == kw && (kh == 3 || kh == 4)) {
+#define DW_BF8(KS, TD)                                                                                                \
+  launch_k(depthwise_bwd_filter_v8_kernel<KS, TD>, chunks, 256, 0, STREAM, static_cast<const __nv_bfloat16*>(x),      \
+           static_cast<const TD*>(dy), partials, h, w, c, ho, wo, stride, pad_t, pad_l, pixels, per_chunk)
+    if (kh == 3 && dy_dtype == GANB_F32) DW_BF8(3, float);
+    else if (kh == 3) DW_BF8(3, __nv_bfloat16);
+    else if (dy_dtype == GANB_F32) DW_BF8(4, float);
+    else DW_BF8(4, __nv_bfloat16);
+#undef DW_BF8
+    GANB_CHECK_LAUNCH("depthwise_bwd_filter_v8_kernel");
+    return 0;
+  }
   const dim3 grid(chunks, kh * kw);
 #define DW_BF(TI, TD)                                                                                                 \
   launch_k(depthwise_bwd_filter_kernel<TI, TD>, grid, 256, 0, STREAM, static_cast<const TI*>(x),                      \
