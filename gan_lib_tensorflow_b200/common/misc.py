@@ -124,7 +124,8 @@ def optimistic_restore(session, save_file):
             with np.load(path) as z:
                 state = {k: z[k] for k in z.files}
         else:
-            state = torch.load(path, map_location='cpu')
+            state = torch.load(path, map_location='cpu', weights_only=False)   # the caller's own state dict
+            state = {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in state.items()}
     else:
         state = save_file
     restored = store.load_state_dict(state, strict=False)
