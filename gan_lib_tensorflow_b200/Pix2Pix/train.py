@@ -5,7 +5,7 @@ generator's global step; per iteration n_dis critic steps on the batch, then one
 
 Every discriminator call uses update_collection=None in the reference (train.py:459-478): u is re-assigned by D(real),
 by D(fake) and again by D(fake) of the generator step, so each call sees a different sigma (framework.sn_acquire keeps
-one spectral-norm state per evaluation).  The WGAN-GP penalty (train.py:489-507) is not built."""
+one spectral-norm state per evaluation).  The WGAN-GP penalty (train.py:489-503) is Pix2Pix/gp.py: a third such pass."""
 from __future__ import annotations
 
 import numpy as np
@@ -26,8 +26,8 @@ class Trainer:
                  channel_multiplier: int = 0):
         """net_type / conv_type / channel_multiplier: the flags of Pix2Pix/train.py:31-36 ('UNet_Attention' = unet_g /
         unet_d, the 256x256 topology of config 4; 'UNet' = the 512x512 pair)."""
-        if loss_type == 'WGAN-GP':
-            raise NotImplementedError('the gradient penalty of Pix2Pix/train.py:489-507 is not built (SURVEY 8(f))')
+        if loss_type == 'WGAN-GP' and conv_type != 'conv2d':
+            raise NotImplementedError('the gradient penalty (Pix2Pix/gp.py) is built for conv_type conv2d')
         self.store = get_store()
         self.model = Pix2Pix()
         self.ngf, self.ndf, self.loss_type = ngf, ndf, loss_type
@@ -53,14 +53,27 @@ class Trainer:
         return (self.initial_lr - self.end_lr) * (1.0 - t) + self.end_lr
 
     # ------------------------------------------------------------------------------------------ losses
-    def d_loss(self, inputs, targets, keep_masks=None):
+    def d_loss(self, inputs, targets, keep_masks=None, gp_alpha=None):
+        """discrim_loss of train.py:459-503.  gp_alpha: the tf.random_uniform([batch]) draw of the WGAN-GP term (drawn
+        here when None)."""
         m = self.model
         outputs = m.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=keep_masks, **self.net)  # g_net frozen
         predict_real = m.get_discriminator(inputs, targets, ndf=self.ndf, update_collection=None, reuse=True, **self.net)
         predict_fake = m.get_discriminator(inputs, Var(outputs.data), ndf=self.ndf, update_collection=None, reuse=True,
                                            **self.net)
         pr, pf = F.reshape(predict_real, (-1,)), F.reshape(predict_fake, (-1,))
-        return F.gan_loss(F.concat_rows(pr, pf), 'd', n_real=pr.shape[0], loss_type=self.loss_type)
+        loss = F.gan_loss(F.concat_rows(pr, pf), 'd', n_real=pr.shape[0], loss_type=self.loss_type)
+        if self.loss_type == 'WGAN-GP':                    # train.py:489-503, a third update_collection=None pass of D
+            from . import gp
+            x = inputs.data if isinstance(inputs, Var) else inputs
+            t = targets.data if isinstance(targets, Var) else targets
+            if gp_alpha is None:
+                gp_alpha = torch.rand(x.shape[0], device=x.device)
+            penalty = gp.gradient_penalty(x, t, outputs.data, gp_alpha,
+                                          n_layers=4 if self.net['net_type'] == 'UNet' else 3)
+            self.last_penalty = penalty.data
+            loss = F.add_scalars(loss, penalty)
+        return loss
 
     def g_loss(self, inputs, targets, keep_masks=None):
         m = self.model
@@ -82,11 +95,16 @@ class Trainer:
             for dst, src in zip(s['masks'], keep_masks):
                 dst.copy_(src, non_blocking=True)
 
-    def d_step(self, inputs, targets, keep_masks=None):
+    def d_step(self, inputs, targets, keep_masks=None, gp_alpha=None):
         if self.players.captured("d"):
             self._stage(inputs, targets, keep_masks)
+            if self.loss_type == 'WGAN-GP':
+                if gp_alpha is None:
+                    self.static['alpha'].uniform_()
+                else:
+                    self.static['alpha'].copy_(gp_alpha, non_blocking=True)
             return self.players.replay("d", self.learning_rate())
-        return self.players.step("d", lambda: self.d_loss(inputs, targets, keep_masks), self.learning_rate())
+        return self.players.step("d", lambda: self.d_loss(inputs, targets, keep_masks, gp_alpha), self.learning_rate())
 
     def g_step(self, inputs, targets, keep_masks=None):
         if self.players.captured("g"):
@@ -101,9 +119,10 @@ class Trainer:
         """Both training ops as CUDA graphs over static buffers shaped like the given batch (call after one eager
         d_step and g_step with the same shapes); later d_step / g_step calls copy their arguments in and replay."""
         self.static = {'inputs': torch.empty_like(inputs), 'targets': torch.empty_like(targets),
-                       'masks': None if keep_masks is None else [torch.empty_like(m) for m in keep_masks]}
+                       'masks': None if keep_masks is None else [torch.empty_like(m) for m in keep_masks],
+                       'alpha': torch.rand(inputs.shape[0], device=inputs.device)}
         s = self.static
-        self.players.capture("d", lambda: self.d_loss(s['inputs'], s['targets'], s['masks']))
+        self.players.capture("d", lambda: self.d_loss(s['inputs'], s['targets'], s['masks'], s['alpha']))
         self.players.capture("g", lambda: self.g_loss(s['inputs'], s['targets'], s['masks']))
 
     def train_iteration(self, inputs, targets, n_dis: int = 5, mask_fn=None):

@@ -119,13 +119,22 @@ class Pix2PixLosses:
         with self.g.variable_scope("d_net"):
             return unet_d(self.g, inputs, targets, self.ndf, True, update_collection)
 
-    def d_grads(self, inputs, targets, keep_masks=None):
+    def d_grads(self, inputs, targets, keep_masks=None, gp_alpha=None):
         from .acgan import get_loss
         with torch.no_grad():
             outputs = self.G(inputs, keep_masks)
         predict_real = self.D(inputs, targets, None)           # train.py:459-467, update_collection=None
         predict_fake = self.D(inputs, outputs, None)           # :470-478
         cost, _ = get_loss(predict_real, predict_fake, self.loss_type)                           # :486
+        if self.loss_type == "WGAN-GP":                                                          # :489-503
+            alpha = gp_alpha.reshape(-1, 1, 1, 1)              # tf.random_uniform([batch_size, 1, 1, 1])
+            differences = outputs - targets
+            interpolates = (targets + alpha * differences).detach().requires_grad_(True)
+            d_hat = self.D(inputs, interpolates, None)
+            gradients = torch.autograd.grad(d_hat.sum(), interpolates, create_graph=True)[0]
+            slopes = torch.sqrt(torch.sum(gradients ** 2, dim=(1, 2, 3)) + 1e-10)
+            self.last_penalty = 10 * torch.mean((slopes - 1.0) ** 2)
+            cost = cost + self.last_penalty
         params = self.g.trainable_variables("d_net")
         return cost.detach(), params, torch.autograd.grad(cost, [p for _, p in params], allow_unused=True)
 

@@ -384,3 +384,67 @@ def test_pix2pix_training_steps(env, loss_type):
     torch.cuda.synchronize()
     assert np.isfinite(d.data.item()) and np.isfinite(g_.data.item())
     assert tr.global_step == 1 and tr.learning_rate() < lr0 == 0.0002
+
+
+def test_pix2pix_gradient_penalty(env):
+    """Pix2Pix --loss_type WGAN-GP (train.py:489-503): the penalty of the spectrally-normalised PatchGAN on the
+    interpolates, a THIRD update_collection=None evaluation of D inside the critic step, differentiated through D's
+    backward pass (Pix2Pix/gp.py) -- value, total critic loss, u after three assignments and every critic gradient
+    against the oracle's torch double backward."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.Pix2Pix import train as PT
+    from oracle import ops as O_ops
+    from oracle import pix2pix as OP
+    from tests.test_gpu_ops import _report
+
+    n, ngf, size = 2, 8, 512
+    rs = np.random.RandomState(96)
+    x = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    tgt = rs.uniform(-1, 1, size=(n, size, size, 3)).astype("float32")
+    alpha = np.array([0.37, 0.81], dtype="float32")
+    tr = PT.Trainer(ngf=ngf, ndf=ngf, size=size, loss_type="WGAN-GP", seed=0, max_steps=100)
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(tgt).cuda()
+    dl = tr.players.gradients("d", lambda: tr.d_loss(xd, td, None, gp_alpha=torch.from_numpy(alpha).cuda()))
+    torch.cuda.synchronize()
+    d_grads = {v.key: v.grad.cpu().numpy().copy() for v in store.trainable_variables("d_net")}
+    u_after = {k: v.data.cpu().numpy().copy() for k, v in store.vars.items() if k.endswith("/u")}
+    d_loss, pen = float(dl.data.item()), float(tr.last_penalty.item())
+    refs = {}
+    for mode in (True, False):
+        O_ops.BF16_OPERANDS = mode
+        try:
+            np.random.seed(0)
+            g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+            ol = OP.Pix2PixLosses(g, ngf, ngf, size, "WGAN-GP")
+            dc, dp, dg = ol.d_grads(torch.from_numpy(x), torch.from_numpy(tgt), None, gp_alpha=torch.from_numpy(alpha))
+            refs[mode] = dict(d=dc.item(), pen=float(ol.last_penalty.item()),
+                              u={k_: v.detach().numpy().copy() for k_, v in g.vars.items() if k_.endswith("/u")},
+                              dg={nm: t.numpy() for (nm, _), t in zip(dp, dg) if t is not None})
+        finally:
+            O_ops.BF16_OPERANDS = False
+    _report(f"pix2pix WGAN-GP: penalty product {pen:.5f} bf16-oracle {refs[True]['pen']:.5f} fp32-oracle {refs[False]['pen']:.5f}; "
+            f"d_loss {d_loss:.5f} / {refs[True]['d']:.5f} / {refs[False]['d']:.5f}")
+    assert set(d_grads) == set(refs[False]["dg"])
+    assert refs[False]["pen"] > 1e-3                                            # the term is active in this test
+    assert abs(pen - refs[True]["pen"]) <= 1e-2 * refs[True]["pen"] + 1e-4
+    assert abs(pen - refs[False]["pen"]) <= 3e-2 * refs[False]["pen"] + 1e-4
+    assert abs(d_loss - refs[True]["d"]) < 5e-3 * max(1.0, abs(refs[True]["d"]))
+    for name, u in refs[False]["u"].items():          # three assignments: D(real), D(fake), D(interpolates)
+        assert rel(u_after[name], u) < 1e-3, name
+    gmax = max(np.linalg.norm(t) for t in refs[False]["dg"].values())
+    lines = []
+    for name, f32 in refs[False]["dg"].items():
+        if np.linalg.norm(f32) < 5e-2 * gmax:
+            continue
+        e_impl = rel(d_grads[name], refs[True]["dg"][name])
+        e_prod, e_orc = rel(d_grads[name], f32), rel(refs[True]["dg"][name], f32)
+        lines.append(f"{name}={e_impl:.1e}/{e_prod:.1e}/{e_orc:.1e}")
+        assert e_prod <= 2.0 * e_orc + 1e-2, (name, e_impl, e_prod, e_orc)
+    _report("pix2pix WGAN-GP gradients (vs bf16-oracle / vs fp32 / bf16-oracle vs fp32): " + " ".join(lines))
+    # the step runs through the optimiser, eagerly and as a captured graph
+    d1 = tr.d_step(xd, td)
+    tr.g_step(xd, td)
+    tr.capture(xd, td)
+    d2 = tr.d_step(xd, td)
+    torch.cuda.synchronize()
+    assert np.isfinite(float(d1.data.reshape(-1)[0])) and np.isfinite(float(d2.reshape(-1)[0]))

@@ -361,6 +361,29 @@ def test_acgan_narrow_generator_variant(host):
     assert "g_net/G.1.Shortcut/Filters" in store.vars      # 'up' blocks always have a conv shortcut
 
 
+def test_pix2pix_gradient_penalty_call_sequence(host):
+    """Pix2Pix --loss_type WGAN-GP (train.py:489-503, Pix2Pix/gp.py): the critic step evaluates D three times with
+    update_collection=None (three power iterations, three spectral-norm backward passes over three state generations),
+    interpolates once, evaluates the penalty kernel once, and every one of the 5 convolutions emits 3 filter gradients
+    (real / fake passes + the penalty's wgrad(c_l, gy_l))."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.Pix2Pix import train as PT
+
+    tr = PT.Trainer(ngf=8, ndf=8, size=256, loss_type='WGAN-GP')
+    x, t = torch.zeros(2, 256, 256, 3), torch.zeros(2, 256, 256, 3)
+    n0 = len(rec.calls)
+    token = store.tape_token
+    loss = tr.players.gradients("d", lambda: tr.d_loss(x, t, None, gp_alpha=torch.tensor([0.3, 0.6])))
+    names = rec.names()[n0:]
+    assert tuple(loss.shape) == (1,)
+    assert names.count("ganb_sn_power_iter") == 3 and names.count("ganb_sn_bwd") == 3
+    assert names.count("ganb_interpolate") == 1 and names.count("ganb_gp_loss") == 1
+    assert names.count("ganb_conv2d_wgrad") == 15
+    assert store.tape_token == token + 1 and store.tape is None       # the inner tapes leave the outer bookkeeping alone
+    with pytest.raises(NotImplementedError):
+        PT.Trainer(ngf=8, ndf=8, size=256, loss_type='WGAN-GP', conv_type='separable_conv2d', channel_multiplier=1)
+
+
 def test_legacy_conv2d_signature_and_pixelnorm_alias(host):
     store, _ = host
     from gan_lib_tensorflow_b200.common import resnet_block
