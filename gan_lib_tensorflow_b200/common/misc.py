@@ -114,11 +114,20 @@ def get_loss(disc_real, disc_fake, loss_type='HINGE', player=None):
 
 def optimistic_restore(session, save_file):
     """common/misc.py:275-307: restore every variable whose NAME and SHAPE match the checkpoint, skip the rest.
-    `session` is ignored (the variable store is global state like TF's default graph); save_file is a state dict
-    {name: array} or the path of one written with torch.save(store.state_dict()) / numpy.savez.  Returns the list of
-    restored names (the reference prints them)."""
+    `session` is ignored (the variable store is global state like TF's default graph); save_file is the prefix of a
+    TensorFlow-1 checkpoint (`<prefix>.index` + `<prefix>.data-*`, read by common/tf_checkpoint.py), a state dict
+    {name: array}, or the path of one written with numpy.savez / torch.save.  Returns the list of restored names (the
+    reference prints them)."""
     store = get_store()
-    if isinstance(save_file, (str, os.PathLike)):
+    if isinstance(save_file, (str, os.PathLike)) and os.path.exists(os.fspath(save_file) + '.index'):
+        # a TensorFlow-1 tensor-bundle checkpoint (what saver.save wrote): read without TensorFlow, only the
+        # variables whose names exist here (tf_checkpoint.CheckpointReader = tf.train.NewCheckpointReader)
+        from .tf_checkpoint import CheckpointReader
+        reader = CheckpointReader(os.fspath(save_file))
+        shapes = reader.get_variable_to_shape_map()
+        state = reader.state_dict([k for k in shapes if k in store.vars
+                                   and list(store.vars[k].data.shape) == shapes[k]])
+    elif isinstance(save_file, (str, os.PathLike)):
         path = os.fspath(save_file)
         if path.endswith('.npz'):
             with np.load(path) as z:
@@ -156,10 +165,16 @@ def checkpoint_state(optimizers=()):
     return state
 
 
-def save_checkpoint(save_file, optimizers=()):
-    """saver.save(): one .npz of checkpoint_state() (TF's tensor-bundle container itself is not written)."""
+def save_checkpoint(save_file, optimizers=(), tf_bundle: bool = False):
+    """saver.save(): one .npz of checkpoint_state(); tf_bundle=True writes TensorFlow's tensor-bundle container instead
+    (`<save_file>.index` + `.data-00000-of-00001` + the `checkpoint` state file, common/tf_checkpoint.py -- pure-Python
+    checksums, slow for large models)."""
     state = checkpoint_state(optimizers)
     path = os.fspath(save_file)
+    if tf_bundle:
+        from .tf_checkpoint import write_checkpoint
+        write_checkpoint(path, {k: np.asarray(v, dtype=np.float32) for k, v in state.items()})
+        return sorted(state)
     np.savez(path if path.endswith('.npz') else path + '.npz', **{k: np.asarray(v) for k, v in state.items()})
     return sorted(state)
 
@@ -167,7 +182,10 @@ def save_checkpoint(save_file, optimizers=()):
 def restore_checkpoint(save_file, optimizers=()):
     """saver.restore() with optimistic_restore's name + shape rule, including the Adam slots and step counts of
     `optimizers` (same order as at save time).  Returns the restored names."""
-    if isinstance(save_file, (str, os.PathLike)):
+    if isinstance(save_file, (str, os.PathLike)) and os.path.exists(os.fspath(save_file) + '.index'):
+        from .tf_checkpoint import CheckpointReader
+        state = CheckpointReader(os.fspath(save_file)).state_dict()      # a TensorFlow-1 tensor bundle
+    elif isinstance(save_file, (str, os.PathLike)):
         path = os.fspath(save_file)
         with np.load(path if path.endswith('.npz') else path + '.npz') as z:
             state = {k: z[k] for k in z.files}

@@ -126,6 +126,78 @@ def test_checkpoint_names_and_round_trip(host, tmp_path):  # noqa: F811
     assert got == ["g_net/G.Input/b"]
 
 
+def test_tf1_tensor_bundle_reader(host, tmp_path):  # noqa: F811
+    """common/tf_checkpoint.py: the TensorFlow-1 checkpoint container (LevelDB-style table index + raw data shard) read
+    without TensorFlow.  Known answers for the checksum, a hand-assembled table block, a multi-block round trip through
+    the independent writer, corruption detection, and optimistic_restore / restore_checkpoint straight from a bundle."""
+    import struct
+
+    store, _ = host
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+    from gan_lib_tensorflow_b200.common import misc
+    from gan_lib_tensorflow_b200.common import tf_checkpoint as T
+
+    assert T.crc32c(b"123456789") == 0xE3069283                      # CRC-32C (Castagnoli) check value
+    assert T.crc32c(b"") == 0 and T.masked_crc32c(b"") == 0xa282ead8
+    assert T.crc32c(bytes(32)) == 0x8A9136AA and T.crc32c(b"\xff" * 32) == 0x62A8AB43   # RFC 3720 B.4 test vectors
+    assert T.crc32c(bytes(range(32))) == 0x46DD794E
+    # a block written by hand: keys "ab" -> "1", "abc" -> "22" (shares 2 bytes), one restart at 0
+    blk = bytes([0, 2, 1]) + b"ab" + b"1" + bytes([2, 1, 2]) + b"c" + b"22" + struct.pack("<II", 0, 1)
+    assert list(T._block_entries(blk)) == [(b"ab", b"1"), (b"abc", b"22")]
+    assert T._put_varint(300) == bytes([0xAC, 0x02]) and T._varint(bytes([0xAC, 0x02]), 0) == (300, 2)
+    e = T._parse_entry(T._msg([(1, 0, 1), (2, 2, T._msg([(2, 2, T._msg([(1, 0, 3)])), (2, 2, T._msg([(1, 0, 5)]))])),
+                               (4, 0, 64), (5, 0, 60), (6, 5, 7)]))
+    assert e["dtype"] == 1 and e["shape"] == [3, 5] and e["offset"] == 64 and e["size"] == 60 and e["crc32c"] == 7
+
+    rs = np.random.RandomState(0)
+    tensors = {"net/layer_%03d/W" % i: rs.standard_normal((3, i % 5 + 1)).astype("float32") for i in range(150)}
+    tensors["global_step"] = np.array(1234, dtype=np.int64)
+    tensors["beta1_power"] = np.float32(0.0).reshape(())
+    prefix = str(tmp_path / "model.ckpt-1234")
+    T.write_checkpoint(prefix, tensors, block_entries=16)            # 10 data blocks
+    with open(prefix + ".index", "rb") as fh:
+        assert struct.unpack("<Q", fh.read()[-8:])[0] == T.TABLE_MAGIC
+    r = T.CheckpointReader(prefix, verify=True)
+    assert r.get_variable_to_shape_map()["net/layer_007/W"] == [3, 3] and r.get_variable_to_shape_map()["global_step"] == []
+    assert sorted(r.entries) == sorted(tensors) and r.has_tensor("beta1_power") and not r.has_tensor("nope")
+    for k, v in tensors.items():
+        got = r.get_tensor(k)
+        assert got.dtype == v.dtype and got.shape == v.shape
+        np.testing.assert_array_equal(got, v)
+    assert T.latest_checkpoint(str(tmp_path)) == prefix
+    with open(prefix + ".data-00000-of-00001", "r+b") as fh:          # flip one byte: the entry checksum catches it
+        fh.seek(5)
+        b = fh.read(1)
+        fh.seek(5)
+        fh.write(bytes([b[0] ^ 0xFF]))
+    with pytest.raises(ValueError):
+        T.CheckpointReader(prefix, verify=True).get_tensor("global_step")        # bytes 4..11 of the shard
+    with pytest.raises(ValueError):
+        T.read_index(prefix + ".data-00000-of-00001")
+
+    # a trainer's state through the TF container and back (names incl. Adam slots, optimistic rule on the way in)
+    tr = PT.Trainer(block_count=1, trans=False, batch_size=2, seed=0)
+    og, od = tr.players.opt["g"], tr.players.opt["d"]
+    og.t, od.t = 4, 9
+    og.flat.m.uniform_(-1, 1)
+    saved = misc.checkpoint_state((og, od))
+    p2 = str(tmp_path / "pggan.ckpt-9")
+    names = misc.save_checkpoint(p2, (og, od), tf_bundle=True)
+    assert os.path.exists(p2 + ".index") and "g_net/G.Input/W/Adam" in names
+    og.flat.params.add_(1.0)
+    og.flat.m.zero_()
+    og.t = od.t = 0
+    restored = misc.restore_checkpoint(p2, (og, od))
+    assert og.t == 4 and od.t == 9 and "g_net/G.Input/W/Adam" in restored
+    now = misc.checkpoint_state((og, od))
+    for k in ("g_net/G.Input/W", "g_net/G.Input/W/Adam", "d_net/D.Conv/Filters"):
+        np.testing.assert_array_equal(now[k], saved[k], err_msg=k)
+    og.flat.params.add_(1.0)
+    got = misc.optimistic_restore(None, p2)
+    assert "g_net/G.Input/W" in got and "g_net/G.Input/W/Adam" not in got      # variables of the store only
+    np.testing.assert_array_equal(store.vars["g_net/G.Input/W"].data.numpy(), saved["g_net/G.Input/W"])
+
+
 def test_get_loss_needs_a_player_inside_a_tape(host):  # noqa: F811
     store, rec = host
     from gan_lib_tensorflow_b200.common import misc
