@@ -135,3 +135,48 @@ class Trainer:
             real, labels = next(batches)
             d = self.d_step(real, labels, *self._noise())
         return d, g
+
+    # ------------------------------------------------------------------------------------------ the script's loop
+    def train(self, max_iter: int, train_gen, dev_gen=None, n_dis: int = 5, **kw):
+        """ACGAN/train.py:148-233.  train_gen / dev_gen: epoch generator factories yielding (int pixels [B, 3072] CHW,
+        int labels [B]) like common.data.cifar10.load; the G step is skipped at step 0 (:192), then n_dis critic steps;
+        fixed-noise samples use labels 0..9 repeated (:150-152).  Remaining keywords: training.reference_loop."""
+        from ..common import misc as lib_misc
+        from ..training import reference_loop
+
+        dev = self.store.device
+        fixed_z = torch.from_numpy(lib_misc.get_z(100, n_hidden=self.z_dim)).to(dev)                # :148
+        fixed_labels = torch.from_numpy(np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype='int32')).to(dev)
+
+        def inf_train_gen():
+            while True:
+                for images_, labels_ in train_gen():
+                    yield images_, labels_
+
+        gen = inf_train_gen()
+
+        def feed(images, labels):
+            real_int = torch.as_tensor(images, dtype=torch.int32).to(dev)
+            deq = torch.rand(real_int.shape[0], real_int.shape[1], device=dev) / 128.0              # :80-81
+            return self.preprocess(real_int, deq), torch.as_tensor(labels, dtype=torch.int32).to(dev)
+
+        def step_fn(step):
+            self.train_iteration(step, (feed(*next(gen)) for _ in iter(int, 1)), n_dis=n_dis)
+
+        def scalars():
+            out = {}
+            if getattr(self, 'last_g', None):      # the kernel folds acgan_scale_G into the term; the script logs it unscaled
+                out.update({'g_loss_gan': self.last_g['g_loss_gan'],
+                            'g_loss_acgan': self.last_g['g_loss_acgan_scaled'] / self.scale_g})
+            out.update({'d_loss_gan': self.last_d['d_loss_gan'], 'd_loss_acgan': self.last_d['d_loss_acgan']})
+            return out
+
+        def dev_costs(_step):
+            if dev_gen is None:
+                return []
+            return [self.d_loss(*feed(images, labels), *self._noise()).data.clone() for images, labels in dev_gen()]
+
+        def samples(_step):
+            return self.model.get_generator(fixed_z, fixed_labels, reuse=True).data
+
+        return reference_loop(self, max_iter, step_fn, scalars, dev_costs, samples, capture_fn=self.capture, **kw)

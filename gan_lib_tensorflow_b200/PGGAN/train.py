@@ -100,3 +100,53 @@ class Trainer:
         for _ in range(n_dis):
             d = self.d_step(next(batches), torch.randn(self.batch, self.z_dim, device=dev), a)
         return d, g
+
+    # ------------------------------------------------------------------------------------------ the script's loop
+    def train(self, train_gen, dev_gen=None, max_iter: int | None = None, n_dis: int = N_DIS, **kw):
+        """PGGAN/train.py:138-226.  train_gen / dev_gen: epoch generator factories yielding NHWC float images
+        [batch, size, size, 3] already resized to this stage (train.py:89-93 is an input-pipeline step) -- labels, if a
+        tuple is yielded, are ignored like in the reference; every step runs the G step first (:183), then n_dis critic
+        steps, all with alpha = step / max_iter.  Remaining keywords: training.reference_loop."""
+        from ..common import misc as lib_misc
+        from ..training import reference_loop
+
+        if max_iter is not None:
+            self.max_iter = max_iter                 # alpha = step / args.max_iter (:184)
+        max_iter = self.max_iter
+        dev = self.store.device
+        fixed_z = torch.from_numpy(lib_misc.get_z(100, n_hidden=self.z_dim)).to(dev)                # :138
+
+        def images_of(item):
+            x = item[0] if isinstance(item, (tuple, list)) else item
+            return torch.as_tensor(x, dtype=torch.float32).to(dev)
+
+        def inf_train_gen():
+            while True:
+                for item in train_gen():
+                    yield images_of(item)
+
+        gen = inf_train_gen()
+        last = {}
+
+        def step_fn(step):
+            d, g = self.train_iteration(step, gen, n_dis=n_dis)
+            last['d_loss'], last['g_loss'] = d.data if hasattr(d, 'data') else d, g.data if hasattr(g, 'data') else g
+
+        def z():
+            return torch.randn(self.batch, self.z_dim, device=dev)
+
+        def dev_costs(step):
+            if dev_gen is None:
+                return []
+            # eager evaluations between graph replays: the replays move the weights behind the host-side spectral-norm
+            # cache, so it is dropped before and after (D(real) assigns u here too, like the reference's dev loop)
+            self.players._invalidate_sn()
+            costs = [self.d_loss(images_of(item), z(), self.alpha(step)).data.clone() for item in dev_gen()]
+            self.players._invalidate_sn()
+            return costs
+
+        def samples(step):
+            return self.model.get_generator(fixed_z, self.alpha(step), reuse=True).data
+
+        return reference_loop(self, max_iter, step_fn, lambda: dict(g_loss=last['g_loss'], d_loss=last['d_loss']),
+                              dev_costs, samples, capture_fn=self.capture, **kw)

@@ -137,3 +137,50 @@ class TwoPlayer:
 
     def launches(self, which: str) -> int:
         return sum(n for (w, _), n in self.graph_launches.items() if w == which)
+
+
+def reference_loop(trainer, max_iter: int, step_fn, scalars_fn, dev_cost_fn, samples_fn, *, out_dir: str = '.',
+                   checkpoint_dir: str | None = None, display_interval: int = 100, out_image_interval: int = 1000,
+                   restore: bool = False, capture_after: int | None = 1, capture_fn=None, log=print):
+    """The body shared by ACGAN/train.py:176-233 and PGGAN/train.py:168-226: optional restore of the latest checkpoint
+    (optimistic_restore), then per step `step_fn(step)` (the script's G step / n_dis D steps), a progress line every
+    display_interval steps, and every out_image_interval steps the dev-set critic loss (`lib.plot.plot('dev_cost')`),
+    the fixed-noise sample grid (`samples_<step>.png`) and `saver.save(... 'model.ckpt', global_step=step)`;
+    `lib.plot.tick()` closes every step.  The Inception-score hook (evaluation_interval) needs the external Inception
+    graph and is not run.  capture_after: the step after which capture_fn() turns the training ops into CUDA graphs."""
+    import os
+
+    from .common import misc as lib_misc
+    from .common import plot as lib_plot
+
+    checkpoint_dir = checkpoint_dir or os.path.join(out_dir, 'checkpoint')
+    lib_plot.set_output_dir(out_dir)
+    opts = (trainer.players.opt['g'], trainer.players.opt['d'])          # g_opt is created first in both scripts
+    if restore:
+        ckpts = [f for f in os.listdir(checkpoint_dir) if f.startswith('model.ckpt-')] if os.path.isdir(checkpoint_dir) else []
+        if ckpts:
+            latest = max(ckpts, key=lambda f: int(f.split('-')[1].split('.')[0]))
+            log('Restore model from: {}...'.format(latest))
+            lib_misc.restore_checkpoint(os.path.join(checkpoint_dir, latest.split('.npz')[0].split('.index')[0]), opts)
+        else:
+            log('No checkpoint found in: {}'.format(checkpoint_dir))
+    captured = False
+    for step in range(max_iter):
+        step_fn(step)
+        if capture_fn is not None and capture_after is not None and not captured and step >= capture_after:
+            capture_fn()
+            captured = True
+        if step % display_interval == display_interval - 1:
+            log('step: {}, '.format(step) + ', '.join('{}: {}'.format(k, float(v.reshape(-1)[0]))
+                                                      for k, v in scalars_fn().items()))
+        if step % out_image_interval == out_image_interval - 1:
+            costs = dev_cost_fn(step)
+            if costs:
+                lib_plot.plot('dev_cost', torch.stack([c.reshape(-1)[0] for c in costs]).mean())
+                lib_plot.flush()
+            lib_misc.save_images(samples_fn(step), os.path.join(out_dir, 'samples_{}.png'.format(step)))
+            if not os.path.exists(checkpoint_dir):
+                os.mkdir(checkpoint_dir)
+            lib_misc.save_checkpoint(os.path.join(checkpoint_dir, 'model.ckpt-{}'.format(step)), opts)
+        lib_plot.tick()
+    return trainer

@@ -243,6 +243,61 @@ def test_reference_train_loop_call_sequence(host, tmp_path, capsys):  # noqa: F8
     plot.set_output_dir('.')
 
 
+def test_acgan_and_pggan_train_loops_call_sequence(host, tmp_path, capsys):  # noqa: F811
+    """ACGAN/train.py:176-233 and PGGAN/train.py:168-226 through Trainer.train (training.reference_loop), host-logic
+    mode: G step skipped at step 0 for ACGAN but not for PGGAN, n_dis critic steps, progress line, dev cost + sample
+    grid + checkpoint every out_image_interval, resume."""
+    store, rec = host
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200.ACGAN import train as AT
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+    from gan_lib_tensorflow_b200.common import plot
+
+    plot.reset()
+    rs = np.random.RandomState(0)
+
+    def cifar(n_batches, b=4):
+        data = rs.randint(0, 256, size=(n_batches, b, 3072)).astype("int32")
+        labels = rs.randint(0, 10, size=(n_batches, b)).astype("int32")
+        return lambda: ((data[i], labels[i]) for i in range(n_batches))
+
+    out_a = tmp_path / "acgan"
+    os.makedirs(out_a)
+    tr = AT.Trainer(batch_size=4, gradient_penalty=False, seed=0, max_iter=10)
+    n0 = len(rec.calls)
+    tr.train(3, cifar(5), cifar(2), n_dis=2, out_dir=str(out_a), display_interval=1, out_image_interval=2,
+             capture_after=None)
+    names = rec.names()[n0:]
+    assert tr.players.opt["g"].t == 2 and tr.players.opt["d"].t == 6        # G skipped at step 0; 2 D-steps per step
+    assert names.count("ganb_adam") == 8 and names.count("ganb_sample_grid") == 1
+    assert sorted(os.listdir(out_a / "checkpoint")) == ["model.ckpt-1.npz"] and os.path.exists(out_a / "samples_1.png")
+    printed = capsys.readouterr().out
+    assert "step: 0, d_loss_gan:" in printed and "step: 2, g_loss_gan:" in printed and "dev_cost" in printed
+    with open(out_a / "log.pkl", "rb") as fh:
+        assert list(pickle.load(fh)["dev_cost"]) == [1]
+    # resume: a fresh trainer picks up parameters and optimiser step counts
+    framework.reset_default_graph("cpu", u_seed=2)
+    tr2 = AT.Trainer(batch_size=4, gradient_penalty=False, seed=1, max_iter=10)
+    tr2.train(0, cifar(1), None, out_dir=str(out_a), restore=True)
+    assert tr2.players.opt["g"].t == 1 and tr2.players.opt["d"].t == 4       # state of the checkpoint written at step 1
+    assert "Restore model from: model.ckpt-1" in capsys.readouterr().out
+
+    framework.reset_default_graph("cpu", u_seed=2)
+    plot.reset()
+    out_p = tmp_path / "pggan"
+    os.makedirs(out_p)
+    imgs = rs.uniform(-1, 1, size=(3, 2, 8, 8, 3)).astype("float32")
+    trp = PT.Trainer(block_count=1, trans=True, batch_size=2, seed=0, model="resnet")
+    trp.train(lambda: (imgs[i] for i in range(3)), lambda: ((imgs[i], None) for i in range(2)), max_iter=2, n_dis=2,
+              out_dir=str(out_p), display_interval=1, out_image_interval=2, capture_after=None)
+    assert trp.players.opt["g"].t == 2 and trp.players.opt["d"].t == 4      # PGGAN runs the G step at step 0 as well
+    assert abs(trp.alpha(1) - 0.5) < 1e-12
+    assert os.path.exists(out_p / "samples_1.png") and os.path.exists(out_p / "checkpoint" / "model.ckpt-1.npz")
+    assert "step: 1, g_loss:" in capsys.readouterr().out
+    plot.reset()
+    plot.set_output_dir('.')
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,h,w,dtype", [(100, 32, 32, torch.float32), (12, 8, 16, torch.float32),
@@ -342,6 +397,56 @@ def test_reference_train_loop_runs_and_resumes(tmp_path):
         assert not torch.equal(before, tr2.store.vars["Generator/G.Input/W"].data)
         np.testing.assert_array_equal(tr2.store.vars["Generator/G.Input/W"].data.cpu().numpy(),
                                       state["Generator/G.Input/W"])
+    finally:
+        plot.reset()
+        plot.set_output_dir('.')
+        framework.set_store(None)
+
+
+@pytest.mark.gpu
+def test_acgan_and_pggan_train_loops_run_with_graphs(tmp_path):
+    """Trainer.train of ACGAN (with the gradient penalty) and PGGAN (ResNet variant, fade-in) for a few steps on the GPU:
+    CUDA graphs captured after step 1, eager dev-cost evaluations and fixed-noise samples between replays."""
+    from PIL import Image
+
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200.ACGAN import train as AT
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+    from gan_lib_tensorflow_b200.common import plot
+
+    rs = np.random.RandomState(0)
+    data = rs.randint(0, 256, size=(4, 8, 3072)).astype("int32")
+    labels = rs.randint(0, 10, size=(4, 8)).astype("int32")
+    cifar = lambda: ((data[i], labels[i]) for i in range(4))  # noqa: E731
+    try:
+        plot.reset()
+        framework.reset_default_graph("cuda", u_seed=2)
+        out_a = tmp_path / "acgan"
+        os.makedirs(out_a)
+        tr = AT.Trainer(batch_size=8, gradient_penalty=True, seed=0, max_iter=10)
+        tr.train(4, cifar, cifar, n_dis=2, out_dir=str(out_a), display_interval=2, out_image_interval=2)
+        torch.cuda.synchronize()
+        assert tr.players.captured("d") and tr.players.captured("g")
+        assert tr.players.opt["g"].t == 3 and tr.players.opt["d"].t == 8
+        with open(out_a / "log.pkl", "rb") as fh:
+            dev = pickle.load(fh)["dev_cost"]
+        assert sorted(dev) == [1, 3] and all(np.isfinite(v) for v in dev.values())
+        assert np.asarray(Image.open(out_a / "samples_3.png")).shape == (320, 320, 3)
+
+        plot.reset()
+        framework.reset_default_graph("cuda", u_seed=2)
+        out_p = tmp_path / "pggan"
+        os.makedirs(out_p)
+        imgs = rs.uniform(-1, 1, size=(4, 4, 8, 8, 3)).astype("float32")
+        trp = PT.Trainer(block_count=1, trans=True, inputs_norm=True, batch_size=4, seed=0, model="resnet")
+        trp.train(lambda: (imgs[i] for i in range(4)), lambda: (imgs[i] for i in range(2)), max_iter=4, n_dis=2,
+                  out_dir=str(out_p), display_interval=2, out_image_interval=2)
+        torch.cuda.synchronize()
+        assert trp.players.captured("d") and trp.players.opt["g"].t == 4 and trp.players.opt["d"].t == 8
+        with open(out_p / "log.pkl", "rb") as fh:
+            dev = pickle.load(fh)["dev_cost"]
+        assert sorted(dev) == [1, 3] and all(np.isfinite(v) for v in dev.values())
+        assert np.asarray(Image.open(out_p / "samples_3.png")).shape == (80, 80, 3)
     finally:
         plot.reset()
         plot.set_output_dir('.')
