@@ -133,3 +133,53 @@ class Trainer:
             d = self.d_step(inputs, targets, mask_fn() if mask_fn else None)
         g = self.g_step(inputs, targets, mask_fn() if mask_fn else None)
         return d, g
+
+    # ------------------------------------------------------------------------------------------ the script's loop
+    def train(self, batches, max_steps: int | None = None, n_dis: int = 5, progress_freq: int = 50,
+              display_freq: int = 0, save_freq: int = 4000, val_batches=(), out_dir: str = '.', mask_fn=None,
+              capture_after: int | None = 0, log=print):
+        """Pix2Pix/train.py:694-772.  `batches`: a sequence of (inputs, targets) device tensor pairs in [-1, 1]
+        (train_data[idx] after the script's preprocessing; indexed step % len like :695); per step n_dis critic
+        steps on the batch, then the generator step; every progress_freq steps the three losses (:746-749, GAN and L1
+        unweighted like the `gen_loss_GAN` / `gen_loss_L1` fetches); every display_freq steps the
+        inputs | targets | outputs grid of the batch; every save_freq steps the validation pass (:751-766: the script
+        saves images there, not a model) over val_batches.  should(freq) also fires on the last step (:701-702)."""
+        import os
+        import time
+
+        from ..common import misc as lib_misc
+
+        max_steps = self.max_steps if max_steps is None else max_steps
+        start = time.time()
+        captured = False
+
+        def should(freq, step):
+            return freq > 0 and ((step + 1) % freq == 0 or step == max_steps - 1)
+
+        def triple(inputs, targets):
+            out = self.model.get_generator(inputs, 3, ngf=self.ngf, reuse=True, keep_masks=None, **self.net).data
+            return torch.cat([inputs, targets, out.to(inputs.dtype)], dim=0)       # plumbing: the display fetches
+
+        for step in range(max_steps):
+            inputs, targets = batches[step % len(batches)]
+            masks = (lambda: mask_fn()) if mask_fn else (lambda: None)
+            d = None
+            for _ in range(n_dis):
+                d = self.d_step(inputs, targets, masks())
+            self.g_step(inputs, targets, masks())
+            if capture_after is not None and not captured and step >= capture_after:
+                self.capture(inputs, targets, masks())
+                captured = True
+            if should(progress_freq, step):
+                rate = (step + 1) * inputs.shape[0] / (time.time() - start)
+                log("progress  step %d  image/sec %0.1f" % (self.global_step, rate))
+                log("discrim_loss", float(d.reshape(-1)[0] if torch.is_tensor(d) else d.data.reshape(-1)[0]))
+                log("gen_loss_GAN", float(self.last['gen_loss_GAN_weighted'].reshape(-1)[0]) / self.gan_weight)
+                log("gen_loss_L1", float(self.last['gen_loss_L1_weighted'].reshape(-1)[0]) / self.l1_weight)
+            if should(display_freq, step):
+                lib_misc.save_images(triple(inputs, targets), os.path.join(out_dir, 'train_%08d.png' % self.global_step))
+            if should(save_freq, step):
+                for i, (vi, vt) in enumerate(val_batches):
+                    lib_misc.save_images(triple(vi, vt), os.path.join(out_dir, 'val_%04d.png' % i))
+                    log("evaluated image", 'val_%04d.png' % i)
+        return self

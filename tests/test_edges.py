@@ -298,6 +298,27 @@ def test_acgan_and_pggan_train_loops_call_sequence(host, tmp_path, capsys):  # n
     plot.set_output_dir('.')
 
 
+def test_pix2pix_train_loop_call_sequence(host, tmp_path):  # noqa: F811
+    """Pix2Pix/train.py:694-772 through Trainer.train, host-logic mode: n_dis critic steps then the generator step per
+    batch, should(freq) firing on multiples and on the last step, display grid and validation images."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.Pix2Pix import train as PT
+
+    tr = PT.Trainer(ngf=8, ndf=8, size=256, max_steps=3)
+    batches = [(torch.zeros(1, 256, 256, 3), torch.zeros(1, 256, 256, 3)) for _ in range(2)]
+    lines = []
+    n0 = len(rec.calls)
+    tr.train(batches, n_dis=2, progress_freq=2, display_freq=2, save_freq=3, val_batches=batches[:1],
+             out_dir=str(tmp_path), capture_after=None, log=lambda *a: lines.append(" ".join(str(x) for x in a)))
+    names = rec.names()[n0:]
+    assert tr.players.opt["d"].t == 6 and tr.players.opt["g"].t == 3 and tr.global_step == 3
+    assert names.count("ganb_adam") == 9
+    assert [l.split()[0] for l in lines].count("progress") == 2          # steps 1 (multiple of 2) and 2 (last)
+    assert any(l.startswith("gen_loss_L1") for l in lines) and "evaluated image val_0000.png" in lines
+    assert sorted(f for f in os.listdir(tmp_path)) == ["train_00000002.png", "train_00000003.png", "val_0000.png"]
+    assert names.count("ganb_sample_grid") == 3
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,h,w,dtype", [(100, 32, 32, torch.float32), (12, 8, 16, torch.float32),
@@ -450,4 +471,32 @@ def test_acgan_and_pggan_train_loops_run_with_graphs(tmp_path):
     finally:
         plot.reset()
         plot.set_output_dir('.')
+        framework.set_store(None)
+
+
+@pytest.mark.gpu
+def test_pix2pix_train_loop_runs_with_graphs(tmp_path):
+    """Pix2Pix Trainer.train on the GPU: graphs captured after the first step, display / validation grids written from
+    eager generator passes between replays."""
+    from PIL import Image
+
+    from gan_lib_tensorflow_b200 import framework
+    from gan_lib_tensorflow_b200.Pix2Pix import train as PT
+
+    framework.reset_default_graph("cuda", u_seed=2)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        batches = [(torch.rand(1, 256, 256, 3, device="cuda", generator=g) * 2 - 1,
+                    torch.rand(1, 256, 256, 3, device="cuda", generator=g) * 2 - 1) for _ in range(2)]
+        tr = PT.Trainer(ngf=8, ndf=8, size=256, max_steps=3, seed=0)
+        lines = []
+        tr.train(batches, n_dis=2, progress_freq=1, display_freq=3, save_freq=3, val_batches=batches[:1],
+                 out_dir=str(tmp_path), log=lambda *a: lines.append(" ".join(str(x) for x in a)))
+        torch.cuda.synchronize()
+        assert tr.players.captured("d") and tr.players.captured("g") and tr.global_step == 3
+        vals = [float(l.split()[1]) for l in lines if l.startswith(("discrim_loss", "gen_loss_GAN", "gen_loss_L1"))]
+        assert len(vals) == 9 and all(np.isfinite(v) for v in vals)
+        assert np.asarray(Image.open(tmp_path / "train_00000003.png")).shape == (256, 768, 3)
+        assert os.path.exists(tmp_path / "val_0000.png")
+    finally:
         framework.set_store(None)
