@@ -400,7 +400,7 @@ def synthetic_batches(batch_size: int = BATCH_SIZE, seed: int = 0, n_batches: in
 def train(iters: int = ITERS, train_gen=None, dev_gen=None, out_dir: str = '.', checkpoint_dir: str | None = None,
           batch_size: int = BATCH_SIZE, seed: int | None = 0, capture: bool = True, fetch_gen_cost: bool = False,
           restore: bool = False, sample_every: int = 100, flush_until: int = 500, flush_every: int = 1000,
-          trainer: "Trainer | None" = None):
+          trainer: "Trainer | None" = None, n_fixed: int = 100, fixed_labels_fn=None):
     """The training loop of the reference script (gan_cifar_resnet.py:528-660) on the B200 ops: per iteration one
     generator step (skipped at iteration 0) and N_CRITIC critic steps, `lib.plot` scalars d_cost / g_cost, every
     `sample_every` iterations the dev-set cost and a 10 x 10 sample grid from fixed noise (labels 0..9 repeated), flush +
@@ -409,6 +409,9 @@ def train(iters: int = ITERS, train_gen=None, dev_gen=None, out_dir: str = '.', 
     train_gen / dev_gen: epoch generator factories as returned by common.data.cifar10.load (default: synthetic).
     fetch_gen_cost: evaluate gen_cost inside every critic step like the reference's session.run does (:611-615; a
     redundant generator-step forward pass) instead of reporting the loss of the last generator step.
+    n_fixed / fixed_labels_fn() -> (int32 labels [n_fixed], file-name tag): the fixed-noise sample batch (default: 100
+    samples, labels 0..9 repeated; the ImageNet script uses 25 samples of one randomly chosen class, see
+    gan_imagNet_resnet.train).  dev_gen=False skips the dev cost (commented out in the ImageNet script).
     The Inception score hook (:634-637) needs the external Inception graph and is not run.  Returns the Trainer."""
     import os
 
@@ -418,10 +421,13 @@ def train(iters: int = ITERS, train_gen=None, dev_gen=None, out_dir: str = '.', 
     tr = trainer or Trainer(batch_size=batch_size, seed=seed)
     st = tr.store
     # :530-533 -- drawn from the global NumPy stream right after graph construction
-    fixed_noise = torch.from_numpy(np.random.normal(size=(100, 128)).astype('float32')).to(st.device)
-    fixed_labels = torch.from_numpy(np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype='int32')).to(st.device)
-    train_gen = train_gen or synthetic_batches(batch_size, seed=0)
-    dev_gen = dev_gen or synthetic_batches(batch_size, seed=1, n_batches=2)
+    fixed_noise = torch.from_numpy(np.random.normal(size=(n_fixed, 128)).astype('float32')).to(st.device)
+    if fixed_labels_fn is None:
+        fixed_labels_fn = lambda: (np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype='int32'), None)  # noqa: E731
+    side = int(round((tr.output_dim // 3) ** 0.5))
+    train_gen = train_gen or synthetic_batches(batch_size, seed=0, output_dim=tr.output_dim, n_classes=tr.n_classes)
+    if dev_gen is None:
+        dev_gen = synthetic_batches(batch_size, seed=1, n_batches=2, output_dim=tr.output_dim, n_classes=tr.n_classes)
     checkpoint_dir = checkpoint_dir or os.path.join(out_dir, 'checkpoint')
     lib_plot.set_output_dir(out_dir)
     if restore:                                                           # :590-594
@@ -457,10 +463,14 @@ def train(iters: int = ITERS, train_gen=None, dev_gen=None, out_dir: str = '.', 
         lib_plot.plot('d_cost', tr.d_loss)                                # :625-626
         lib_plot.plot('g_cost', gen_cost)
         if iteration % sample_every == sample_every - 1:                  # :639-649
-            dev_disc_costs = [tr.disc_cost_eval(images, _labels).clone() for images, _labels in dev_gen()]
-            lib_plot.plot('dev_cost', torch.stack(dev_disc_costs).mean())
+            if dev_gen:
+                dev_disc_costs = [tr.disc_cost_eval(images, _labels).clone() for images, _labels in dev_gen()]
+                lib_plot.plot('dev_cost', torch.stack(dev_disc_costs).mean())
+            labels_np, tag = fixed_labels_fn()
+            fixed_labels = torch.from_numpy(np.asarray(labels_np, dtype='int32')).to(st.device)
             samples = tr.fixed_samples(fixed_noise, fixed_labels)         # generate_image, :536-539
-            lib_misc.save_images(samples.reshape(100, 32, 32, 3), os.path.join(out_dir, 'samples_{}.png'.format(iteration)))
+            name = 'samples_{}.png'.format(iteration) if tag is None else 'samples_{}_{}.png'.format(iteration, tag)
+            lib_misc.save_images(samples.reshape(n_fixed, side, side, 3), os.path.join(out_dir, name))
         if (iteration < flush_until) or (iteration % flush_every == flush_every - 1):   # :651-656
             lib_plot.flush()
             if not os.path.exists(checkpoint_dir):

@@ -131,3 +131,26 @@ def _trainer_class():
 
 
 Trainer = _trainer_class()
+
+
+SAMPLE_LABELS = [3, 547, 671, 833, 147, 218, 283, 292, 493, 555, 668, 698, 780, 985, 977, 963]   # :549-555
+
+
+def train(iters: int = ITERS, **kw):
+    """The training loop of gan_imagNet_resnet.py:546-705 -- the CIFAR script's loop (gan_cifar_resnet.train) around
+    this module's Trainer, with the ImageNet script's sample function: 25 fixed-noise samples of ONE class drawn
+    uniformly from SAMPLE_LABELS at every call (tf.multinomial over equal logits, :557-563), written as
+    samples_<iteration>_<label>.png (:573); the dev-set cost is commented out in this script (:688-694)."""
+    import numpy as np
+
+    from . import gan_cifar_resnet as cifar
+
+    def fixed_labels_fn():
+        label = int(SAMPLE_LABELS[np.random.randint(len(SAMPLE_LABELS))])
+        return np.full(25, label, dtype='int32'), label
+
+    kw.setdefault('batch_size', BATCH_SIZE)
+    if kw.get('trainer') is None:
+        kw['trainer'] = Trainer(batch_size=kw['batch_size'], seed=kw.get('seed', 0))
+    kw.setdefault('dev_gen', False)
+    return cifar.train(iters, n_fixed=25, fixed_labels_fn=fixed_labels_fn, **kw)

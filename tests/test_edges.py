@@ -298,6 +298,33 @@ def test_acgan_and_pggan_train_loops_call_sequence(host, tmp_path, capsys):  # n
     plot.set_output_dir('.')
 
 
+def test_imagenet_train_loop_call_sequence(host, tmp_path, monkeypatch):  # noqa: F811
+    """gan_imagNet_resnet.train (gan_imagNet_resnet.py:546-705): the CIFAR loop around the ImageNet Trainer, 25 fixed
+    samples of one class from SAMPLE_LABELS per grid (file name carries the label), no dev cost."""
+    store, rec = host
+    from gan_lib_tensorflow_b200.SNGAN import gan_imagNet_resnet as P
+    from gan_lib_tensorflow_b200.common import plot
+
+    monkeypatch.setattr(P, "DIM_G", 16)
+    monkeypatch.setattr(P, "DIM_D", 16)
+    plot.reset()
+    np.random.seed(0)
+    tr = P.train(iters=2, out_dir=str(tmp_path), batch_size=2, capture=False, sample_every=2, flush_until=0,
+                 flush_every=2)
+    names = rec.names()
+    assert tr.output_dim == 49152 and tr.gen_opt.t == 1 and tr.disc_opt.t == 2 * 5
+    assert names.count("ganb_sample_grid") == 1
+    pngs = [f for f in os.listdir(tmp_path) if f.endswith(".png")]
+    assert len(pngs) == 1 and pngs[0].startswith("samples_1_") and int(pngs[0][:-4].split("_")[2]) in P.SAMPLE_LABELS
+    from PIL import Image
+    assert np.asarray(Image.open(tmp_path / pngs[0])).shape == (5 * 128, 5 * 128, 3)
+    with open(tmp_path / "log.pkl", "rb") as fh:
+        assert set(pickle.load(fh)) == {"d_cost", "g_cost"}           # the dev cost is commented out in this script
+    assert os.path.exists(tmp_path / "checkpoint" / "model.ckpt-1.npz")
+    plot.reset()
+    plot.set_output_dir('.')
+
+
 def test_pix2pix_train_loop_call_sequence(host, tmp_path):  # noqa: F811
     """Pix2Pix/train.py:694-772 through Trainer.train, host-logic mode: n_dis critic steps then the generator step per
     batch, should(freq) firing on multiples and on the last step, display grid and validation images."""
