@@ -436,7 +436,8 @@ def train(iters: int = ITERS, train_gen=None, dev_gen=None, out_dir: str = '.', 
         if ckpts:
             latest = max(ckpts, key=lambda f: int(f.split('-')[1].split('.')[0]))
             print('restore model from: {}...'.format(latest))
-            lib_misc.restore_checkpoint(os.path.join(checkpoint_dir, latest), (tr.gen_opt, tr.disc_opt))
+            prefix = latest.split('.npz')[0].split('.index')[0].split('.data-')[0]     # .npz or a TF tensor bundle
+            lib_misc.restore_checkpoint(os.path.join(checkpoint_dir, prefix), (tr.gen_opt, tr.disc_opt))
 
     def inf_train_gen():                                                  # :560-566
         while True:

@@ -161,7 +161,8 @@ def reference_loop(trainer, max_iter: int, step_fn, scalars_fn, dev_cost_fn, sam
         if ckpts:
             latest = max(ckpts, key=lambda f: int(f.split('-')[1].split('.')[0]))
             log('Restore model from: {}...'.format(latest))
-            lib_misc.restore_checkpoint(os.path.join(checkpoint_dir, latest.split('.npz')[0].split('.index')[0]), opts)
+            prefix = latest.split('.npz')[0].split('.index')[0].split('.data-')[0]     # .npz or a TF tensor bundle
+            lib_misc.restore_checkpoint(os.path.join(checkpoint_dir, prefix), opts)
         else:
             log('No checkpoint found in: {}'.format(checkpoint_dir))
     captured = False
