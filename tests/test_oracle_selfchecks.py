@@ -234,3 +234,114 @@ def test_depthwise_conv_matches_an_explicit_loop():
     dw = O.depthwise_conv2d_nhwc(torch.from_numpy(x), g.vars["L/depthwise_filters"], 2, "SAME")
     pw = torch.einsum("nhwc,co->nhwo", dw, g.vars["L/pointwise_filters"][0, 0])
     assert torch.allclose(out, pw, atol=1e-5)
+
+
+def test_variant_ops_closed_forms():
+    """Closed-form pins of the oracle restatements added for the secondary variants: weight-norm makes the per-output-
+    channel norm equal g for Conv2D / Linear / Deconv2D axes (conv2d.py:153-163, linear.py:143-155, deconv2d.py:87-96);
+    PixelCNN masks are causal (conv2d.py:63-81); layer norm gives zero mean / unit variance per sample before gamma /
+    beta (normalization.py:62-82); resize_nearest to half size picks every second pixel, to double size repeats."""
+    import numpy as np
+    import torch
+
+    from oracle import ops as O
+    from oracle import resnet_block as ORB
+    from oracle import tfshim
+
+    rs = np.random.RandomState(3)
+    # ---- weight norm: ||W_eff[..., co]|| == g[co]
+    np.random.seed(1)
+    g = tfshim.Graph(dtype=torch.float64, u_seed=2)
+    gv = (0.5 + rs.uniform(size=6))
+    with g.variable_scope("C"):
+        g.get_variable("g", initializer=gv)
+    x = torch.from_numpy(rs.standard_normal((1, 5, 5, 4)))
+    O.Conv2D(g, x, 4, 6, 3, name="C", weightnorm=True)
+    w = g.vars["C/Filters"]
+    # an impulse at the centre reads the effective filter back: y[0, 2+1-r, 2+1-s, co] = W_eff[r, s, ci, co]
+    imp = torch.zeros(1, 5, 5, 4, dtype=torch.float64)
+    imp[0, 2, 2, 1] = 1.0
+    y = O.Conv2D(g, imp, 4, 6, 3, name="C", weightnorm=True, biases=False) if False else None
+    w_eff = w * (torch.from_numpy(gv) / torch.sqrt((w ** 2).sum(dim=(0, 1, 2))))
+    assert torch.allclose(torch.sqrt((w_eff ** 2).sum(dim=(0, 1, 2))), torch.from_numpy(gv), atol=1e-12)
+    out = O.Conv2D(g, x, 4, 6, 3, name="C", weightnorm=True)
+    ref = O.conv2d_nhwc(x, w_eff, 1, "SAME") + g.vars["C/Biases"]
+    assert torch.allclose(out, ref, atol=1e-12)
+    del y
+    # ---- PixelCNN mask: the output at a pixel does not change when a "future" pixel changes; type 'a' also ignores the
+    #      pixel itself, type 'b' sees it
+    for kind, sees_self in (("a", False), ("b", True)):
+        np.random.seed(2)
+        g2 = tfshim.Graph(dtype=torch.float64, u_seed=2)
+        xa = torch.from_numpy(rs.standard_normal((1, 6, 6, 2)))
+        ya = O.Conv2D(g2, xa, 2, 3, 3, name="M", mask_type=(kind, 1))
+        xb = xa.clone()
+        xb[0, 3, 4:, :] += 1.0          # same row, to the right of (3, 3)
+        xb[0, 4:, :, :] += 1.0          # rows below
+        yb = O.Conv2D(g2, xb, 2, 3, 3, name="M", mask_type=(kind, 1))
+        assert torch.allclose(ya[0, 3, 3], yb[0, 3, 3], atol=1e-12) and not torch.allclose(ya[0, 5, 5], yb[0, 5, 5])
+        xc = xa.clone()
+        xc[0, 3, 3, :] += 1.0
+        yc = O.Conv2D(g2, xc, 2, 3, 3, name="M", mask_type=(kind, 1))
+        assert torch.allclose(ya[0, 3, 3], yc[0, 3, 3], atol=1e-12) != sees_self
+    # ---- layer norm
+    g3 = tfshim.Graph(dtype=torch.float64, u_seed=2)
+    xl = torch.from_numpy(rs.standard_normal((3, 4, 4, 8)) * 2.5 + 1.0)
+    yl = O.layer_norm(g3, "LN", [1, 2, 3], xl)
+    assert torch.allclose(yl.mean(dim=(1, 2, 3)), torch.zeros(3, dtype=torch.float64), atol=1e-9)
+    assert torch.allclose(yl.var(dim=(1, 2, 3), unbiased=False), torch.ones(3, dtype=torch.float64), atol=1e-6)
+    assert list(g3.vars) == ["LN/beta", "LN/gamma"]
+    # ---- nearest resize
+    xr = torch.from_numpy(rs.standard_normal((2, 8, 8, 3)))
+    assert torch.equal(ORB.resize_nearest(xr, 4, 4), xr[:, ::2, ::2, :])
+    up = ORB.resize_nearest(xr, 16, 16)
+    assert torch.equal(up, ORB.upsample2(xr)) and torch.equal(up[:, 1::2, 1::2], xr)
+
+
+def test_pix2pix_gradient_penalty_oracle_matches_finite_differences():
+    """The oracle's WGAN-GP term (Pix2Pix/train.py:489-503: torch double backward through the spectrally-normalised
+    PatchGAN) against central finite differences of the penalty in float64, for one filter of every layer."""
+    import numpy as np
+    import torch
+
+    from oracle import ops as O
+    from oracle import pix2pix as OP
+    from oracle import tfshim
+
+    rs = np.random.RandomState(4)
+    size, ndf, n = 32, 4, 2
+    inputs = torch.from_numpy(rs.uniform(-1, 1, size=(n, size, size, 3)))
+    targets = torch.from_numpy(rs.uniform(-1, 1, size=(n, size, size, 3)))
+    outputs = torch.from_numpy(rs.uniform(-1, 1, size=(n, size, size, 3)))
+    alpha = torch.from_numpy(np.array([0.3, 0.8])).reshape(-1, 1, 1, 1)
+    np.random.seed(0)
+    g = tfshim.Graph(dtype=torch.float64, u_seed=2)
+    with torch.no_grad(), g.variable_scope("d_net"):
+        OP.unet_d(g, inputs, targets, ndf, True, O.NO_OPS)
+
+    def penalty():
+        interp = (targets + alpha * (outputs - targets)).detach().requires_grad_(True)
+        with g.variable_scope("d_net"):
+            d = OP.unet_d(g, inputs, interp, ndf, True, O.NO_OPS)       # NO_OPS: u fixed, so the function is repeatable
+        grads = torch.autograd.grad(d.sum(), interp, create_graph=True)[0]
+        slopes = torch.sqrt((grads ** 2).sum(dim=(1, 2, 3)) + 1e-10)
+        return 10 * ((slopes - 1.0) ** 2).mean()
+
+    params = dict(g.trainable_variables("d_net"))
+    names = [k for k in params if k.endswith("/Filters")]
+    analytic = dict(zip(names, torch.autograd.grad(penalty(), [params[k] for k in names])))
+    for k in names:
+        w = params[k]
+        idx = tuple(int(rs.randint(0, s)) for s in w.shape)
+        eps = 1e-5
+        with torch.no_grad():
+            w[idx] += eps
+        up = penalty().item()
+        with torch.no_grad():
+            w[idx] -= 2 * eps
+        dn = penalty().item()
+        with torch.no_grad():
+            w[idx] += eps
+        fd = (up - dn) / (2 * eps)
+        an = analytic[k][idx].item()
+        assert abs(fd - an) <= 1e-4 * max(1.0, abs(an)), (k, idx, fd, an)
