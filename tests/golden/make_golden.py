@@ -84,6 +84,46 @@ def compute():
         out["sngan_ggrad_G.Output"] = _sig(gg["Generator/G.Output/Filters"])
     finally:
         S.BATCH_SIZE = 64
+
+    # ---- secondary variants and the other model families (appended: the entries above keep their RNG streams)
+    from oracle import pggan as PG
+    from oracle import pix2pix as P2
+
+    rs = np.random.RandomState(7)
+    x = torch.from_numpy(rs.standard_normal((2, 8, 8, 16)).astype("float32"))
+    np.random.seed(3)
+    g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    out["conv_weightnorm_sn"] = _sig(O.Conv2D(g, x, 16, 8, 3, 1, "wn", weightnorm=True, spectral_normed=True,
+                                              update_collection=O.NO_OPS))
+    out["conv_mask_b3"] = _sig(O.Conv2D(g, x[..., :12].contiguous(), 12, 9, 3, 1, "mk", mask_type=("b", 3)))
+    out["conv_separable_s2"] = _sig(O.Conv2D(g, x, 16, 8, 4, 2, "sep", conv_type="separable_conv2d",
+                                             channel_multiplier=2))
+    out["conv_depthwise_valid"] = _sig(O.Conv2D(g, x, 16, 32, 3, 1, "dw", conv_type="depthwise_conv2d",
+                                                channel_multiplier=2, padding="VALID"))
+    out["deconv_weightnorm"] = _sig(O.Deconv2D(g, x, 16, 8, 4, name="dc", weight_norm=True))
+    out["linear_weightnorm_inputs_norm"] = _sig(O.Linear(g, x.reshape(2, -1), 1024, 6, "lw", weightnorm=True,
+                                                         inputs_norm=True))
+    out["layer_norm"] = _sig(O.layer_norm(g, "ln", [1, 2, 3], x))
+    out["resize_nearest_half"] = _sig(RB.resize_nearest(x, 4, 4))
+
+    np.random.seed(4)
+    g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    z = torch.from_numpy(rs.standard_normal((2, 64)).astype("float32"))
+    for cls, tag in ((PG.PGGAN, "nvidia"), (PG.PGGANResNet, "resnet")):
+        m = cls(1, True, True)
+        with torch.no_grad(), g.variable_scope(tag):
+            fake = m.get_generator(g, z, 0.3)
+            out["pggan_%s_fake" % tag] = _sig(fake)
+            out["pggan_%s_logits" % tag] = _sig(m.get_discriminator(g, fake, 0.3, update_collection=O.NO_OPS))
+
+    np.random.seed(5)
+    g = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    a = torch.from_numpy(rs.uniform(-1, 1, size=(1, 64, 64, 3)).astype("float32"))
+    b = torch.from_numpy(rs.uniform(-1, 1, size=(1, 64, 64, 3)).astype("float32"))
+    with torch.no_grad(), g.variable_scope("d_net"):
+        out["pix2pix_patchgan"] = _sig(P2.unet_d(g, a, b, 8, True, O.NO_OPS))
+    with torch.no_grad(), g.variable_scope("d512"):
+        out["pix2pix_patchgan_n_layers4"] = _sig(P2.unet_discriminator(g, a, b, 8, True, O.NO_OPS))
     return out
 
 
