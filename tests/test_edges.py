@@ -198,6 +198,31 @@ def test_tf1_tensor_bundle_reader(host, tmp_path):  # noqa: F811
     np.testing.assert_array_equal(store.vars["g_net/G.Input/W"].data.numpy(), saved["g_net/G.Input/W"])
 
 
+def test_cifar10_loader_interface(tmp_path, capsys):
+    """common/data/cifar10.py: load() -> (train, dev) epoch factories over the pickled batches; partial batches are
+    dropped; images and labels stay paired through the per-epoch reshuffle (shared RNG state)."""
+    import gan_lib_tensorflow_b200.common as lib
+    from gan_lib_tensorflow_b200.common.data import cifar10
+
+    rs = np.random.RandomState(0)
+    for name, n in [("data_batch_%d" % i, 10) for i in range(1, 6)] + [("test_batch", 7)]:
+        labels = rs.randint(0, 10, size=n)
+        data = np.tile(labels[:, None].astype("uint8"), (1, 3072))       # every pixel carries the label: pairing check
+        with open(tmp_path / name, "wb") as fh:
+            pickle.dump({b"data": data, b"labels": labels.tolist()}, fh)
+    train_gen, dev_gen = cifar10.load(8, str(tmp_path))
+    np.random.seed(1)
+    epoch1 = [(i.copy(), l.copy()) for i, l in train_gen()]     # the batches are views of the arrays shuffled in place
+    epoch2 = [(i.copy(), l.copy()) for i, l in train_gen()]
+    assert len(epoch1) == 6 and len(list(dev_gen())) == 0 and epoch1[0][0].shape == (8, 3072)     # 50 // 8, 7 // 8
+    for images, labels in epoch1 + epoch2:
+        assert np.array_equal(images[:, 0], np.asarray(labels).astype("uint8"))
+    assert not np.array_equal(epoch1[0][1], epoch2[0][1])                # reshuffled per epoch
+    lib.print_model_settings({"BATCH_SIZE": 64, "lower": 1, "T": 2})
+    out = capsys.readouterr().out
+    assert "BATCH_SIZE: 64" in out and "lower" not in out
+
+
 def test_get_loss_needs_a_player_inside_a_tape(host):  # noqa: F811
     store, rec = host
     from gan_lib_tensorflow_b200.common import misc
