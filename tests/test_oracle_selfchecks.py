@@ -345,3 +345,46 @@ def test_pix2pix_gradient_penalty_oracle_matches_finite_differences():
         fd = (up - dn) / (2 * eps)
         an = analytic[k][idx].item()
         assert abs(fd - an) <= 1e-4 * max(1.0, abs(an)), (k, idx, fd, an)
+
+
+def test_losses_schedules_and_pggan_statistics_closed_forms():
+    """lib.misc.get_loss (common/misc.py:310-394) against the formulas written out in NumPy for all seven loss types;
+    the SNGAN learning-rate decay (gan_cifar_resnet.py:454-457) at its break points; minibatch_std
+    (PGGAN/model_nvidia.py:20-28) and pixel_norm (normalization.py:125-140) on hand-sized tensors."""
+    import numpy as np
+    import torch
+
+    from oracle import acgan as OA
+    from oracle import ops as O
+    from oracle import pggan as OP
+    from oracle import sngan_cifar as OS
+
+    rs = np.random.RandomState(6)
+    r, f = rs.standard_normal(11), rs.standard_normal(11)
+    sig = lambda t: 1.0 / (1.0 + np.exp(-t))            # noqa: E731
+    xent = lambda logit, label: np.maximum(logit, 0) - logit * label + np.log1p(np.exp(-np.abs(logit)))   # noqa: E731  TF's stable form
+    want = {
+        "HINGE": (np.maximum(0, 1 - r).mean() + np.maximum(0, 1 + f).mean(), -f.mean()),
+        "WGAN": (-r.mean() + f.mean(), -f.mean()),
+        "WGAN-GP": (-r.mean() + f.mean(), -f.mean()),
+        "LSGAN": (((1 - r) ** 2).mean() / 2 + (f ** 2).mean() / 2, ((1 - f) ** 2).mean() / 2),
+        "CGAN": (xent(r, 1.0).mean() + xent(f, 0.0).mean(), xent(f, 1.0).mean()),
+        "Modified_MiniMax": (-np.log(sig(r)).mean() - np.log(1 - sig(f)).mean(), -np.log(sig(f)).mean()),
+        "MiniMax": (-np.log(sig(r)).mean() - np.log(1 - sig(f)).mean(), np.log(1 - sig(f)).mean()),
+    }
+    for loss_type, (d_want, g_want) in want.items():
+        d, g = OA.get_loss(torch.from_numpy(r), torch.from_numpy(f), loss_type)
+        assert abs(d.item() - d_want) < 1e-12 and abs(g.item() - g_want) < 1e-12, loss_type
+    assert OS.lr_decay(0) == 1.0 and abs(OS.lr_decay(25000) - 0.75) < 1e-12
+    assert abs(OS.lr_decay(49999) - 0.50001) < 1e-9 and OS.lr_decay(50000) == 0.5 and OS.lr_decay(99999) == 0.5
+    # minibatch_std: per-position std over the batch (+1e-8 inside the sqrt), averaged to ONE scalar channel
+    x = np.zeros((2, 1, 2, 1))
+    x[0, 0, 0, 0], x[1, 0, 0, 0] = 1.0, 3.0          # std 1 at position (0, 0), 0 at (0, 1)
+    y = OP.minibatch_std(torch.from_numpy(x))
+    assert tuple(y.shape) == (2, 1, 2, 2)
+    expect = (np.sqrt(1.0 + 1e-8) + np.sqrt(1e-8)) / 2
+    assert torch.allclose(y[..., 1], torch.full((2, 1, 2), expect, dtype=torch.float64), atol=1e-12)
+    assert torch.equal(y[..., 0], torch.from_numpy(x)[..., 0])
+    # pixel_norm: unit mean square over the channels of every pixel
+    p = O.pixel_norm(torch.from_numpy(rs.standard_normal((2, 3, 3, 16)) * 4))
+    assert torch.allclose((p ** 2).mean(dim=3), torch.ones(2, 3, 3, dtype=torch.float64), atol=1e-6)
