@@ -157,7 +157,7 @@ class Trainer:
 
         def feed(images, labels):
             real_int = torch.as_tensor(images, dtype=torch.int32).to(dev)
-            deq = torch.rand(real_int.shape[0], real_int.shape[1], device=dev) / 128.0              # :80-81
+            deq = torch.empty(real_int.shape[0], real_int.shape[1], device=dev).uniform_(0.0, 1.0 / 128)   # :80-81
             return self.preprocess(real_int, deq), torch.as_tensor(labels, dtype=torch.int32).to(dev)
 
         def step_fn(step):
