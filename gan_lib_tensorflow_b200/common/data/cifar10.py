@@ -1,8 +1,14 @@
-"""CIFAR-10 (Python version) batch reader with the reference's interface (common/data/cifar10.py:9-45):
-`load(batch_size, data_dir)` returns (train epoch generator factory, dev epoch generator factory); an epoch yields
-(uint8 pixels [batch, 3072] CHW-flattened, labels [batch]) and drops the last partial batch; images and labels are
-reshuffled at the start of every epoch with ONE shared NumPy RNG state (get_state / set_state around the two shuffles,
-:30-33).  Host code: the hot path starts at the uint8 -> float dequantisation kernel (ganb_preprocess_real)."""
+"""CIFAR-10 (Python version) batches behind the call the reference scripts make:
+`train_gen, dev_gen = lib.data.cifar10.load(batch_size, data_dir)`; calling either object starts an epoch that yields
+(uint8 pixels [batch, 3072] CHW-flattened, int labels [batch]) and drops the trailing partial batch
+(reference: common/data/cifar10.py:9-45).
+
+Design: each split is ONE contiguous uint8 matrix read once, plus a persistent ORDER vector.  An epoch draws one
+permutation from NumPy's global RNG and composes it onto the order -- the same sequence of batches, and the same RNG
+consumption, as the reference's pair of in-place shuffles under a saved / restored RNG state (a shuffle of the rows is
+the row-gather by `permutation(n)` of the same stream) -- and every batch is a fresh gather, so a consumer may keep it
+across epochs (the reference hands out views of the array it reshuffles).  Host code; the hot path starts at the
+dequantisation kernel (ganb_preprocess_real)."""
 from __future__ import annotations
 
 import os
@@ -10,36 +16,35 @@ import pickle
 
 import numpy as np
 
-
-def unpickle(file):
-    with open(file, 'rb') as fo:
-        d = pickle.load(fo, encoding='bytes')
-    return d[b'data'], d[b'labels']
+TRAIN_FILES = tuple('data_batch_%d' % i for i in range(1, 6))
+TEST_FILES = ('test_batch',)
 
 
-def cifar_generator(filenames, batch_size, data_dir):
-    all_data, all_labels = [], []
-    for filename in filenames:
-        data, labels = unpickle(os.path.join(data_dir, filename))
-        all_data.append(data)
-        all_labels.append(labels)
-    images = np.concatenate(all_data, axis=0)
-    labels = np.concatenate(all_labels, axis=0)
+class CifarSplit:
+    def __init__(self, files, batch_size: int, data_dir: str):
+        pixels, labels = [], []
+        for name in files:
+            with open(os.path.join(data_dir, name), 'rb') as fh:
+                record = pickle.load(fh, encoding='bytes')
+            pixels.append(np.asarray(record[b'data'], dtype=np.uint8))
+            labels.append(np.asarray(record[b'labels'], dtype=np.int64))
+        self.pixels = np.ascontiguousarray(np.concatenate(pixels, axis=0))
+        self.labels = np.concatenate(labels, axis=0)
+        self.batch_size = int(batch_size)
+        self.order = np.arange(len(self.labels))
 
-    def get_epoch():
-        rng_state = np.random.get_state()
-        np.random.shuffle(images)
-        np.random.set_state(rng_state)
-        np.random.shuffle(labels)
-        for i in range(int(len(images) / batch_size)):
-            yield (images[i * batch_size:(i + 1) * batch_size], labels[i * batch_size:(i + 1) * batch_size])
+    def __len__(self):
+        return len(self.labels) // self.batch_size          # full batches per epoch
 
-    return get_epoch
+    def __call__(self):
+        """One epoch.  The permutation is drawn when the epoch starts to be consumed (generator semantics, like the
+        reference's get_epoch)."""
+        self.order = self.order[np.random.permutation(len(self.order))]
+        b = self.batch_size
+        for k in range(len(self)):
+            rows = self.order[k * b:(k + 1) * b]
+            yield self.pixels[rows], self.labels[rows]
 
 
 def load(batch_size, data_dir):
-    return (
-        cifar_generator(['data_batch_1', 'data_batch_2', 'data_batch_3', 'data_batch_4', 'data_batch_5'], batch_size,
-                        data_dir),
-        cifar_generator(['test_batch'], batch_size, data_dir),
-    )
+    return CifarSplit(TRAIN_FILES, batch_size, data_dir), CifarSplit(TEST_FILES, batch_size, data_dir)

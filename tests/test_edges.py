@@ -212,12 +212,22 @@ def test_cifar10_loader_interface(tmp_path, capsys):
             pickle.dump({b"data": data, b"labels": labels.tolist()}, fh)
     train_gen, dev_gen = cifar10.load(8, str(tmp_path))
     np.random.seed(1)
-    epoch1 = [(i.copy(), l.copy()) for i, l in train_gen()]     # the batches are views of the arrays shuffled in place
-    epoch2 = [(i.copy(), l.copy()) for i, l in train_gen()]
+    epoch1 = list(train_gen())                                   # fresh gathers: safe to keep across epochs
+    epoch2 = list(train_gen())
     assert len(epoch1) == 6 and len(list(dev_gen())) == 0 and epoch1[0][0].shape == (8, 3072)     # 50 // 8, 7 // 8
     for images, labels in epoch1 + epoch2:
         assert np.array_equal(images[:, 0], np.asarray(labels).astype("uint8"))
     assert not np.array_equal(epoch1[0][1], epoch2[0][1])                # reshuffled per epoch
+    # same batch sequence and RNG consumption as two in-place shuffles under a saved / restored RNG state
+    # (common/data/cifar10.py:30-33), epoch after epoch
+    ref_labels = np.concatenate([np.asarray(pickle.load(open(tmp_path / ("data_batch_%d" % i), "rb"))[b"labels"])
+                                 for i in range(1, 6)])
+    np.random.seed(1)
+    for epoch in (epoch1, epoch2):
+        np.random.shuffle(ref_labels)
+        assert np.array_equal(np.concatenate([l for _, l in epoch]), ref_labels[:48])
+    assert np.random.randint(1 << 30) == (np.random.seed(1), [np.random.permutation(50) for _ in range(2)],
+                                          np.random.randint(1 << 30))[2]
     lib.print_model_settings({"BATCH_SIZE": 64, "lower": 1, "T": 2})
     out = capsys.readouterr().out
     assert "BATCH_SIZE: 64" in out and "lower" not in out
