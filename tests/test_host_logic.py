@@ -563,3 +563,60 @@ def test_two_rank_gradient_allreduce_gloo():
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out.decode()[-2000:]
+
+
+_WORKER_LOOP = r'''
+import os, sys, tempfile
+sys.path.insert(0, {root!r})
+os.environ["GANB_HOST_LOGIC_ONLY"] = "1"
+import numpy as np, torch, torch.distributed as dist
+from gan_lib_tensorflow_b200 import framework
+from gan_lib_tensorflow_b200.ACGAN import train as AT
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+store = framework.reset_default_graph("cpu")
+calls = []
+def allreduce(g):
+    calls.append(g.numel())
+    g.fill_(rank + 1.0)                      # stand-in for the rank's local gradient
+    dist.all_reduce(g)
+    assert torch.all(g == 3.0)
+tr = AT.Trainer(batch_size=4, gradient_penalty=False, seed=0, world_size=2, grad_allreduce=allreduce)
+rs = np.random.RandomState(10 + rank)        # every rank reads its own shard
+data = rs.randint(0, 256, size=(3, 4, 3072)).astype("int32")
+labels = rs.randint(0, 10, size=(3, 4)).astype("int32")
+out = tempfile.mkdtemp()
+tr.train(2, lambda: ((data[i], labels[i]) for i in range(3)), None, n_dis=2, out_dir=out, display_interval=10,
+         out_image_interval=10, capture_after=None, log=lambda *a: None)
+# 4 critic steps + 1 generator step, one collective each, over the whole flat gradient buffer of that network
+sizes = [store.flat["d_net"].grads.numel()] * 2 + [store.flat["g_net"].grads.numel()] + [store.flat["d_net"].grads.numel()] * 2
+assert calls == sizes, (calls, sizes)
+assert tr.players.opt["d"].t == 4 and tr.players.opt["g"].t == 1 and tr.players.world_size == 2
+w = store.vars["d_net/D.Output/W"].data.clone()
+ws = [torch.zeros_like(w) for _ in range(2)]
+dist.all_gather(ws, w)
+assert torch.equal(ws[0], ws[1])             # replicated parameters stay identical (same initial values, summed gradients)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_training_loop_gloo():
+    """ACGAN Trainer.train (training.reference_loop over TwoPlayer) on two gloo ranks in host-logic mode: one gradient
+    collective per optimiser step over that network's flat buffer, in step order (D, D, G, D, D), replicated
+    parameters identical afterwards."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    code = _WORKER_LOOP.format(root=ROOT, port=port)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out.decode()[-2000:]
