@@ -211,10 +211,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     host_losses = torch.zeros(2, dtype=torch.float32).pin_memory()
     tr.set_real_batch(host_data, host_labels)
 
+    use_pair = not getattr(args, "no_pair_schedule", False) and not tr.bn_sync
+
     def pair(it):
         tr.sample_noise()
-        tr.d_step(it)
-        tr.g_step(it)
+        if use_pair and tr._graphs:      # one critic step + one generator step as one schedule (Trainer.pair_step)
+            tr.pair_step(it)
+        else:
+            tr.d_step(it)
+            tr.g_step(it)
 
     for it in range(2):  # eager warm-up: creates descriptor tables / workspaces
         pair(it + 1)
@@ -325,6 +330,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-pair-schedule", action="store_true",
+                    help="replay the critic step and the generator step as separate graphs (round-1 schedule) instead "
+                         "of Trainer.pair_step, which runs the generator step's G forward next to the critic step")
     ap.add_argument("--bn-sync", action="store_true",
                     help="N > 1: also reduce G's batch-norm statistics over the ranks (eager mode; default: per-rank "
                          "statistics = the reference's per-tower semantics, CUDA graphs)")

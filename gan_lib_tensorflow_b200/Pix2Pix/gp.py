@@ -61,7 +61,7 @@ def gradient_penalty(inputs: torch.Tensor, targets: torch.Tensor, outputs: torch
             entries.append(spectral_normed_weight(w, update_collection=None).entry)
         ws.append(w)
         bs.append(st.vars[key + "Biases"])
-    token, gens = st.tape_token, dict(st._sn_gen)
+    token, gens = st.tape_token, st._sn_gen
     try:
         # ---- 1. D(x_hat) and its input gradient on an inner tape (parameters frozen: data gradients only)
         xv = Var(x_hat, requires_grad=True, grad_dtype=F32)

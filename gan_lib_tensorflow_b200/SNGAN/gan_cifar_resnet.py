@@ -23,6 +23,7 @@ from ..common.ops import embedding as embedding_ops
 from ..common.ops import linear as linear_ops
 from ..training import AdamState  # noqa: F401  (tf.train.AdamOptimizer over a network's flat buffers)
 from ..framework import Var, get_store
+from ..framework import aux_stream as framework_aux_stream
 
 BATCH_SIZE = 64  # Critic batch size
 GEN_BS_MULTIPLE = 2  # Generator batch size, as a multiple of BATCH_SIZE
@@ -170,6 +171,7 @@ class Trainer:
         self.gen_opt = AdamState(self.store.flat['Generator'])
         self.disc_opt = AdamState(self.store.flat['Discriminator'])
         self._graphs = {}
+        self._pair_state = None
 
     # ------------------------------------------------------------------------------------------ build
     def _build(self):
@@ -236,17 +238,29 @@ class Trainer:
         self.store.bump('Discriminator')
         self._repack('Discriminator')
 
-    def _g_compute(self):
-        """Forward + backward of the generator step (gan_cifar_resnet.py:462-498, 523): gradients of gen_cost."""
+    def _g_forward(self, tape):
+        """First half of the generator step: G's forward pass on `tape`.  It reads G's parameters only, so it does not
+        depend on the critic step in front of it (see _pair_body)."""
         st = self.store
-        st.zero_grad('Generator')
-        with st.gradient_tape() as tape, st.frozen_scopes('Discriminator'):
-            with st.stat_towers(self.n_towers):
-                fake = self.generator(self.gen_batch, self.fake_labels, noise=self.z_g, reuse=True)
+        with st.resume_tape(tape), st.frozen_scopes('Discriminator'), st.stat_towers(self.n_towers):
+            return self.generator(self.gen_batch, self.fake_labels, noise=self.z_g, reuse=True)
+
+    def _g_rest(self, tape, fake):
+        """Second half: D on the fake batch, gen_cost and the backward pass through D and G."""
+        st = self.store
+        with st.resume_tape(tape), st.frozen_scopes('Discriminator'):
             disc_fake, _ = self.discriminator(fake, self.fake_labels, update_collection="NO_OPS", reuse=True)
             loss = F.gan_loss(disc_fake, 'gen')
             tape.backward(loss)
         self.g_loss.copy_(loss.data)
+
+    def _g_compute(self):
+        """Forward + backward of the generator step (gan_cifar_resnet.py:462-498, 523): gradients of gen_cost."""
+        st = self.store
+        st.zero_grad('Generator')
+        with st.gradient_tape() as tape:
+            pass
+        self._g_rest(tape, self._g_forward(tape))
 
     def _g_update(self):
         self.gen_opt.apply(1.0 / self.world_size)
@@ -265,6 +279,66 @@ class Trainer:
             self.grad_allreduce(self.store.flat['Generator'].grads)
         self._g_update()
 
+    # ------------------------------------------------------------------------------------------ D+G pair
+    # One critic step followed by one generator step.  The generator step starts with G's forward pass on fresh noise,
+    # which reads nothing the critic step writes: it is issued on a third stream next to the critic step, so the
+    # tensor-core kernels of one pass run while the other pass is in its bandwidth-bound normalisation kernels
+    # (the same idea as the filter-gradient side stream of framework.Tape, one level up).  Results are identical to
+    # d_step(); g_step(): only the launch order of independent work changes.
+    def _pair_fork(self):
+        """[aux stream] G forward of the generator step  ||  [main stream] critic forward + backward."""
+        st = self.store
+        with st.gradient_tape() as tape:
+            pass
+        if K.host_logic_only():          # CPU call-sequence tests: no streams
+            st.zero_grad('Generator')
+            self._pair_state = (tape, self._g_forward(tape), None)
+            self._d_compute()
+            return
+        main = torch.cuda.current_stream()
+        aux = framework_aux_stream(main.device)
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            st.zero_grad('Generator')
+            fake = self._g_forward(tape)
+        self._pair_state = (tape, fake, aux)
+        self._d_compute()
+
+    def _pair_join(self):
+        """Critic update, then the rest of the generator step behind the join with the aux stream."""
+        tape, fake, aux = self._pair_state
+        self._pair_state = None
+        self._d_update()
+        if aux is not None:
+            torch.cuda.current_stream().wait_stream(aux)
+        self._g_rest(tape, fake)
+
+    def _pair_body(self):
+        self._pair_fork()
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(self.store.flat['Discriminator'].grads)
+        self._pair_join()
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(self.store.flat['Generator'].grads)
+        self._g_update()
+
+    def pair_step(self, iteration: int):
+        """d_step(iteration) followed by g_step(iteration) as one schedule (one CUDA graph on a single GPU)."""
+        self.disc_opt.set_lr(self.base_lr * self.lr_schedule(iteration))
+        self.gen_opt.set_lr(self.base_lr * self.lr_schedule(iteration))
+        gs = self._graphs
+        if "pair_full" in gs:
+            gs["pair_full"].replay()
+        elif "pair_fork" in gs:
+            gs["pair_fork"].replay()
+            self.grad_allreduce(self.store.flat['Discriminator'].grads)
+            gs["pair_join"].replay()
+            self.grad_allreduce(self.store.flat['Generator'].grads)
+            gs["g_update"].replay()
+        else:
+            self._pair_body()
+        return self.d_loss, self.g_loss
+
     def _invalidate_caches(self, packs=True):
         for g in self.store.sn_groups.values():
             g.valid_for = None
@@ -273,7 +347,7 @@ class Trainer:
             for g in self.store.pack_groups.values():
                 g.valid_for = None
 
-    def capture(self):
+    def capture(self, pair: bool = True):
         """Captures the training ops into CUDA graphs (static shapes; launch latency is first-order at batch 64).
         Must be called after at least one eager D-step and G-step (all workspaces / descriptor tables exist).
         With a gradient collective the compute and update halves are captured separately and the all-reduce
@@ -299,6 +373,23 @@ class Trainer:
                 body()
             self._graphs[name] = g
             self.graph_launches[name] = K.launch_count() - before
+        if pair:
+            # the D+G pair schedule (pair_step): one graph on a single GPU; with a gradient collective the graphs
+            # fork / join share one memory pool, because G's saved activations live across the all-reduce between them
+            pool = torch.cuda.graph_pool_handle()
+            pparts = (("pair_full", self._pair_body),) if self.grad_allreduce is None else (
+                ("pair_fork", self._pair_fork), ("pair_join", self._pair_join))
+            self.pair_launches = 0
+            for name, body in pparts:
+                self._invalidate_caches(packs=False)
+                before = K.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    body()
+                self._graphs[name] = g
+                self.pair_launches += K.launch_count() - before
+            if self.grad_allreduce is not None:
+                self.pair_launches += self.graph_launches["g_update"]
         self._invalidate_caches(packs=False)
 
     def _run(self, which):
@@ -329,6 +420,8 @@ class Trainer:
         """libganb200 kernels in one D-step + one G-step (valid after capture(); 0 in eager mode, where the caller
         counts ganb_launch_count() around its own steps -- running extra steps here would issue collectives on one
         rank only)."""
+        if getattr(self, "pair_launches", 0):
+            return self.pair_launches        # the pair schedule launches the same kernels as d_full + g_full
         return sum(self.graph_launches.values())
 
     # ------------------------------------------------------------------------------------------ evaluation fetches

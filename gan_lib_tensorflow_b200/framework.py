@@ -165,6 +165,18 @@ def _side_stream(device) -> "torch.cuda.Stream":
     return _side_streams[key]
 
 
+_aux_streams = {}
+
+
+def aux_stream(device) -> "torch.cuda.Stream":
+    """Third stream: a whole independent pass (the generator forward of the G-step, which does not depend on the critic
+    update) runs here next to the critic step of the main stream; see SNGAN.gan_cifar_resnet.Trainer._pair_body."""
+    key = torch.device(device).index or 0
+    if key not in _aux_streams:
+        _aux_streams[key] = torch.cuda.Stream(device=device)
+    return _aux_streams[key]
+
+
 class Tape:
     """Records backward closures in execution order; backward() replays them in reverse.
 
@@ -180,6 +192,8 @@ class Tape:
         self.pending_derived = []        # DerivedWeight instances used on this tape (weight-norm / masks)
         self.keep = []       # temporaries read by side-stream launches: kept alive until the join
         self._forked = False
+        self.token = 0       # identity of this tape for the spectral-norm evaluation bookkeeping (VariableStore)
+        self.sn_gen = {}     # root -> index of the spectral-norm state set in use on this tape
 
     def record(self, fn) -> None:
         self.nodes.append(fn)
@@ -474,6 +488,7 @@ class VariableStore:
         self.sn_shadow: dict[str, list] = {}
         self._sn_gen: dict[str, int] = {}
         self.tape_token = 0
+        self._token_seq = 0
         self.pack_groups: dict[str, PackGroup] = {}
         self.derived: dict[str, DerivedWeight] = {}
         self.flat: dict[str, FlatGroup] = {}
@@ -637,14 +652,22 @@ class VariableStore:
 
     @contextlib.contextmanager
     def gradient_tape(self):
-        prev = self.tape
-        self.tape = Tape(self)
-        self.tape_token += 1
-        self._sn_gen = {}
+        self._token_seq += 1
+        tape = Tape(self)
+        tape.token = self._token_seq
+        with self.resume_tape(tape):
+            yield tape
+
+    @contextlib.contextmanager
+    def resume_tape(self, tape: Tape):
+        """Makes `tape` the recording tape again: a forward pass may be recorded in pieces with other tapes (another
+        network's whole step) in between -- the generator forward of the G-step is issued next to the critic step."""
+        prev = (self.tape, self.tape_token, self._sn_gen)
+        self.tape, self.tape_token, self._sn_gen = tape, tape.token, tape.sn_gen
         try:
-            yield self.tape
+            yield tape
         finally:
-            self.tape = prev
+            self.tape, self.tape_token, self._sn_gen = prev
 
     @contextlib.contextmanager
     def frozen_scopes(self, *roots):

@@ -14,6 +14,14 @@ from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P  # noqa: E402
 
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.json"
+    pair = "--steps" not in sys.argv      # default: the D+G pair schedule (Trainer.pair_step); --steps: d_step + g_step
+
+    def run_pair():
+        if pair:
+            tr.pair_step(1)
+        else:
+            tr.d_step(1)
+            tr.g_step(1)
     framework.reset_default_graph("cuda")
     tr = P.Trainer(batch_size=64, seed=0)
     rs = np.random.RandomState(0)
@@ -28,14 +36,12 @@ def main():
         tr.capture()
     torch.cuda.current_stream().wait_stream(s)
     for it in range(5):
-        tr.d_step(1)
-        tr.g_step(1)
+        run_pair()
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for it in range(3):
-            tr.d_step(1)
-            tr.g_step(1)
+            run_pair()
         torch.cuda.synchronize()
     ev = []
     for e in prof.events():

@@ -109,6 +109,41 @@ def test_d_step_and_g_step_gradients_match_the_oracle(batch):
         assert rel(store.vars[name].data.cpu().numpy(), u) < 1e-5, name
 
 
+def test_pair_schedule_equals_d_step_then_g_step():
+    """Trainer.pair_step issues the generator step's G forward next to the critic step (third stream).  Only the launch
+    order of independent work changes: parameters after 3 pairs are bit-identical to d_step(); g_step(), eagerly and
+    as one captured graph."""
+    from gan_lib_tensorflow_b200 import framework
+
+    inp = _inputs(64)
+    results = []
+    for mode in ("steps", "pair_eager", "pair_graph"):
+        store, tr = _trainer(64, inp)
+        for it in range(2):
+            tr.d_step(1)
+            tr.g_step(1)
+        if mode == "pair_graph":
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                tr.capture()
+            torch.cuda.current_stream().wait_stream(s)
+            assert "pair_full" in tr._graphs
+        for it in range(3):
+            if mode == "steps":
+                tr.d_step(1)
+                tr.g_step(1)
+            else:
+                tr.pair_step(1)
+        torch.cuda.synchronize()
+        results.append((store.flat["Generator"].params.clone(), store.flat["Discriminator"].params.clone(),
+                        tr.d_loss.item(), tr.g_loss.item()))
+        framework.set_store(None)
+    for other in results[1:]:
+        assert torch.equal(results[0][0], other[0]) and torch.equal(results[0][1], other[1])
+        assert results[0][2] == other[2] and results[0][3] == other[3]
+
+
 def test_graph_replay_equals_eager_and_training_moves_the_losses():
     """CUDA-graph capture is a pure scheduling change: same inputs, same noise -> identical parameters."""
     from gan_lib_tensorflow_b200 import framework

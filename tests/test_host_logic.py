@@ -379,7 +379,9 @@ def test_pix2pix_gradient_penalty_call_sequence(host):
     assert names.count("ganb_sn_power_iter") == 3 and names.count("ganb_sn_bwd") == 3
     assert names.count("ganb_interpolate") == 1 and names.count("ganb_gp_loss") == 1
     assert names.count("ganb_conv2d_wgrad") == 15
-    assert store.tape_token == token + 1 and store.tape is None       # the inner tapes leave the outer bookkeeping alone
+    # the inner tapes leave the outer bookkeeping alone: every tape has its own token, the outer one is current again
+    # after each inner tape and nothing is recording once the step is over
+    assert store.tape_token == token and store.tape is None and store._token_seq == token + 3
     with pytest.raises(NotImplementedError):
         PT.Trainer(ngf=8, ndf=8, size=256, loss_type='WGAN-GP', conv_type='separable_conv2d', channel_multiplier=1)
 
@@ -487,6 +489,32 @@ def test_training_step_call_sequence_and_freezing(host):
     assert len(stats) == 7 and all(c[1][5] == 2 for c in stats)   # two statistic towers of 64 (reference towers)
     assert tr.disc_opt.t == 1 and tr.gen_opt.t == 1
     assert P.lr_decay(0) == 1.0 and P.lr_decay(60000) == 0.5
+
+
+def test_pair_schedule_issues_the_same_calls_as_the_two_steps(host):
+    """Trainer.pair_step = d_step + g_step with the generator step's G forward issued first (next to the critic step on
+    the GPU): the same multiset of kernel calls, one Adam per optimiser, G's statistics in two towers of 64."""
+    store, rec = host
+    from collections import Counter
+
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+
+    tr = P.Trainer(batch_size=64, seed=0, store=store)
+    tr.d_step(1)
+    tr.g_step(1)
+    rec.calls.clear()
+    tr.d_step(2)
+    tr.g_step(2)
+    two_steps = Counter(rec.names())
+    rec.calls.clear()
+    tr.pair_step(3)
+    pair = rec.names()
+    assert Counter(pair) == two_steps
+    # the generator forward of the G-step (two towers of 64: groups == 2 at n == 128) comes before the critic's wgrads
+    first_wgrad = pair.index("ganb_conv2d_wgrad")
+    g_stats = [i for i, c in enumerate(rec.calls) if c[0] == "ganb_bn_stats" and c[1][2] == 128]
+    assert len(g_stats) == 7 and max(g_stats) < first_wgrad
+    assert tr.disc_opt.t == 3 and tr.gen_opt.t == 3 and store.tape is None
 
 
 def test_optimistic_restore_matches_name_and_shape_only(host):
