@@ -58,12 +58,17 @@ def pixelcnn_mask(mask_type, filter_size, input_dim, output_dim):
     return mask
 
 
-def _depthwise_types(store, inputs, conv_type, depthwise_filters, pointwise_filters, input_dim, output_dim,
-                     channel_multiplier, stride, padding, spectral_normed, inputs_norm, mask_type, weightnorm, biases,
-                     residual, subpixel_up2, out_grad_dtype, out_dtype):
-    """conv_type 'depthwise_conv2d' / 'separable_conv2d' (common/ops/conv2d.py:188-208).  The reference applies
-    weight-norm, masks and spectral norm to `Filters` only, which these two types never read: they have no effect on the
-    result (spectral_normed still creates the `u` variable, which then keeps its initial value)."""
+def _depthwise_types(store, inputs, conv_type, filters, depthwise_filters, pointwise_filters, input_dim, output_dim,
+                     channel_multiplier, stride, padding, spectral_normed, update_collection, inputs_norm, mask_type,
+                     weightnorm, biases, residual, subpixel_up2, out_grad_dtype, out_dtype):
+    """conv_type 'depthwise_conv2d' / 'separable_conv2d' (common/ops/conv2d.py:188-208).
+
+    Weight-norm and the PixelCNN mask act on `Filters` only (conv2d.py:153-167), which these two types never read.
+    Spectral norm wraps ALL THREE filters (conv2d.py:169-178), each under its own scope -- `filters/spectral_norm/u`,
+    `depthwise_filters/spectral_norm/u`, `pointwise_filters/spectral_norm/u` -- and the normalised depthwise / pointwise
+    filters are what the op consumes.  A normalised filter that no op reads (`Filters` always; `pointwise_filters` of a
+    plain depthwise layer) never runs its control-dependent u.assign in TensorFlow: its `u` variable is created and
+    keeps its initial value, no power iteration is evaluated for it."""
     if depthwise_filters is None:
         raise ValueError('{0} needs channel_multiplier > 0 (the reference fails with a NameError)'.format(conv_type))
     if inputs_norm or residual is not None or subpixel_up2:
@@ -72,11 +77,23 @@ def _depthwise_types(store, inputs, conv_type, depthwise_filters, pointwise_filt
         weightnorm = _default_weightnorm
     if weightnorm or mask_type is not None:
         raise NotImplementedError('weight-norm / masks act on the unused `Filters` of {0}'.format(conv_type))
+    sn_dw = sn_pw = None
     if spectral_normed:
         from ...framework import truncated_normal
-        with store.variable_scope('filters'), store.variable_scope('spectral_norm'):
-            store.get_variable('u', shape=[1, output_dim], trainable=False,
-                               initializer=lambda s: truncated_normal(s, store.u_rng))
+
+        def dead_u(scope, c):
+            with store.variable_scope(scope), store.variable_scope('spectral_norm'):
+                store.get_variable('u', shape=[1, c], trainable=False,
+                                   initializer=lambda s: truncated_normal(s, store.u_rng))
+
+        dead_u('filters', output_dim)                                            # conv2d.py:170-171
+        with store.variable_scope('depthwise_filters'):                          # conv2d.py:173-175
+            sn_dw = spectral_normed_weight(depthwise_filters, update_collection=update_collection).entry
+        if conv_type == 'separable_conv2d':                                      # conv2d.py:176-178
+            with store.variable_scope('pointwise_filters'):
+                sn_pw = spectral_normed_weight(pointwise_filters, update_collection=update_collection).entry
+        else:
+            dead_u('pointwise_filters', output_dim)
     _biases = None
     if biases:
         _biases = store.get_variable(name='Biases', shape=[output_dim, ],
@@ -87,9 +104,9 @@ def _depthwise_types(store, inputs, conv_type, depthwise_filters, pointwise_filt
                              'output_dim = {} (tf.nn.bias_add fails in the reference)'.format(
                                  input_dim * channel_multiplier, output_dim))
         return F.depthwise_conv2d(inputs, depthwise_filters, _biases, stride, padding,
-                                  out_dtype=out_dtype or torch.float32, out_grad_dtype=out_grad_dtype)
-    mid = F.depthwise_conv2d(inputs, depthwise_filters, None, stride, padding)
-    return F.conv2d(mid, pointwise_filters, _biases, 1, 1, 1, 'VALID', out_grad_dtype=out_grad_dtype,
+                                  out_dtype=out_dtype or torch.float32, out_grad_dtype=out_grad_dtype, sn=sn_dw)
+    mid = F.depthwise_conv2d(inputs, depthwise_filters, None, stride, padding, sn=sn_dw)
+    return F.conv2d(mid, pointwise_filters, _biases, 1, 1, 1, 'VALID', sn=sn_pw, out_grad_dtype=out_grad_dtype,
                     **({'out_dtype': out_dtype} if out_dtype is not None else {}))
 
 
@@ -140,9 +157,10 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
             pointwise_filters = store.get_variable(name='pointwise_filters', initializer=lambda _s: uniform(
                 stdev, (1, 1, input_dim * channel_multiplier, output_dim)))
         if conv_type != 'conv2d':
-            return _depthwise_types(store, inputs, conv_type, depthwise_filters, pointwise_filters, input_dim,
-                                    output_dim, channel_multiplier, stride, padding, spectral_normed, inputs_norm,
-                                    mask_type, weightnorm, biases, residual, subpixel_up2, out_grad_dtype, out_dtype)
+            return _depthwise_types(store, inputs, conv_type, filters, depthwise_filters, pointwise_filters, input_dim,
+                                    output_dim, channel_multiplier, stride, padding, spectral_normed,
+                                    update_collection, inputs_norm, mask_type, weightnorm, biases, residual,
+                                    subpixel_up2, out_grad_dtype, out_dtype)
 
         if weightnorm is None:
             weightnorm = _default_weightnorm

@@ -40,6 +40,12 @@ struct IgemmParams {
   // own taps and padding.  At most one of og / rg exceeds 1.
   int og, rg, out_cstride;
   signed char gpad_t[4], gpad_l[4];
+  // Batch statistics of the STORED output (after alpha / bias / residual / activation and the rounding to the output
+  // dtype), produced by the epilogue for the batch norm that follows the layer: stats[(pixel_tile * og + g) * 2 + {0, 1}]
+  // [Cout] = per-tile column sums of y and y^2 (rows outside the tensor contribute 0).  Pixel tiles are image-major,
+  // so the rows of one statistic tower are contiguous and bn_stats_finalize_kernel folds them in a fixed order
+  // (deterministic).  nullptr: off.
+  float* stats;
 };
 
 template <int NC>
@@ -67,14 +73,69 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Column sums over the 32 pixels of a warp: every lane holds 32 per-pixel values r[0..32); lane L returns
+// sum over lanes of r[L].  Halving butterfly (16 + 8 + 4 + 2 + 1 = 31 shuffles), fixed order.
+__device__ __forceinline__ float warp_transpose_sum32(float (&r)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = upper ? r[j] : r[j + off];
+      const float keep = upper ? r[j + off] : r[j];
+      r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return r[0];
+}
+
+// Fused batch statistics: the 4 epilogue warps of a CTA leave their 32-pixel column sums in shared memory
+// ([warp][{sum, sumsq}][BN]); epilogue_stats_flush folds them and writes the tile's row of IgemmParams::stats.
+template <int BN>
+struct EpiStats {
+  float s[4][2][BN];
+};
+
+template <int NC, int BN>
+__device__ __forceinline__ void epilogue_stats_chunk(EpiStats<BN>& st, const float (&val)[NC], bool valid, int q,
+                                                     int lane, int c0) {
+  static_assert(NC == 32, "fused statistics need 32-column chunks");
+  float a[32], b[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    a[j] = valid ? val[j] : 0.f;
+    b[j] = a[j] * a[j];
+  }
+  const float ts = warp_transpose_sum32(a, lane);
+  const float tq = warp_transpose_sum32(b, lane);
+  st.s[q][0][c0 + lane] = ts;
+  st.s[q][1][c0 + lane] = tq;
+}
+
+// called by all EPI_THREADS epilogue threads after the chunk loop of a tile (contains a named barrier)
+template <int BN>
+__device__ __forceinline__ void epilogue_stats_flush(const IgemmParams& p, const EpiStats<BN>& st, int64_t row,
+                                                     bool row_ok, int co_tile, int et) {
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+  if (row_ok) {
+    float* out = p.stats + row * 2 * p.Cout;
+    for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+      const int k = i / BN, c = i - k * BN;
+      const int co = co_tile + c;
+      if (co < p.Cout) out[k * p.Cout + co] = (st.s[0][k][c] + st.s[1][k][c]) + (st.s[2][k][c] + st.s[3][k][c]);
+    }
+  }
+}
+
 // One thread owns one output pixel (TMEM lane) and NC consecutive channels held in registers.
 // All loads (bias from shared memory, residual from global) are issued BEFORE the first store: the output pointer
 // may alias the inputs as far as the compiler knows, so interleaving them would serialise one memory round trip
 // per float4 (this was the limiter of the first version of this kernel, profiles/r01_*).
+// `val` (optional): receives the values as stored (rounded to the output dtype), for the fused statistics.
 template <int NC>
 __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_t (&r)[NC], float alpha,
                                              int64_t out_off, int64_t res_pix, int co_base,
-                                             const float* __restrict__ bias_s) {
+                                             const float* __restrict__ bias_s, float* __restrict__ val = nullptr) {
   const int cout = p.Cout;
   const int64_t off = out_off + co_base;           // out_off = pixel * out_cstride + group channel offset
   const int64_t roff = res_pix * cout + co_base;
@@ -105,6 +166,17 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
       for (int j = 0; j < NC / 4; ++j) {
         v[j].x = apply_act(v[j].x, p.act); v[j].y = apply_act(v[j].y, p.act);
         v[j].z = apply_act(v[j].z, p.act); v[j].w = apply_act(v[j].w, p.act);
+      }
+    }
+    if (val) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        float4 t = v[j / 4];
+        if (p.out_bf16) {
+          t.x = __bfloat162float(__float2bfloat16_rn(t.x)); t.y = __bfloat162float(__float2bfloat16_rn(t.y));
+          t.z = __bfloat162float(__float2bfloat16_rn(t.z)); t.w = __bfloat162float(__float2bfloat16_rn(t.w));
+        }
+        val[j] = t.x; val[j + 1] = t.y; val[j + 2] = t.z; val[j + 3] = t.w;
       }
     }
     if (p.out_bf16 && (cout % 8 == 0) && (NC % 8 == 0)) {

@@ -417,6 +417,15 @@ lerp_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
   }
 }
 
+// y = alpha * x with alpha read from device memory: the spectrally-normalised depthwise filter W_d / sigma (the
+// depthwise kernels have no GEMM epilogue to carry 1/sigma; the filter is k*k*c*cm floats, i.e. tiny)
+__global__ void __launch_bounds__(256)
+scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ alpha, float* __restrict__ y, int64_t n) {
+  pdl_wait();
+  const float t = *alpha;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) y[i] = t * x[i];
+}
+
 template <typename TA, typename TB>
 __global__ void __launch_bounds__(256)
 lerp_bwd_kernel(const float* __restrict__ dy, TA* __restrict__ da, TB* __restrict__ db, int64_t n,
@@ -888,6 +897,13 @@ extern "C" int ganb_lerp_fwd(const float* a, const float* b, float* y, int64_t c
     return fail(GANB_E_BADARG, "lerp_fwd: buffers must be 16-byte aligned");
   launch_k(lerp_fwd_kernel, flat_grid(count / 4 + 1), 256, 0, STREAM, a, b, y, count, alpha);
   GANB_CHECK_LAUNCH("lerp_fwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_scale_dev(const float* x, const float* alpha, float* y, int64_t count, void* stream) {
+  if (!x || !alpha || !y) return fail(GANB_E_BADARG, "scale_dev: null buffer");
+  launch_k(scale_dev_kernel, flat_grid(count), 256, 0, STREAM, x, alpha, y, count);
+  GANB_CHECK_LAUNCH("scale_dev_kernel");
   return 0;
 }
 

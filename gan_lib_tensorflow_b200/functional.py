@@ -317,22 +317,28 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
 
 
 def depthwise_conv2d(x: Var, Wd: Variable, b: Variable | None, stride: int = 1, padding="SAME", out_dtype=BF16,
-                     out_grad_dtype=F32) -> Var:
+                     out_grad_dtype=F32, sn=None) -> Var:
     """tf.nn.depthwise_conv2d(x, Wd [kh, kw, c, cm]) (+ bias): the `depthwise_conv2d` conv_type and the first half of
     `separable_conv2d` (common/ops/conv2d.py:188-208).  Bandwidth-bound CUDA-core kernels in fp32 arithmetic; the input
     is read in bf16 (like every convolution operand of this library) and the output is the bf16 operand of the pointwise
-    1x1 convolution that follows, with an fp32 gradient."""
+    1x1 convolution that follows, with an fp32 gradient.
+
+    `sn`: the framework.SNEntry of `depthwise_filters` (conv2d.py:173-175).  These kernels have no GEMM epilogue to carry
+    1/sigma, and the filter is tiny, so W_d / sigma is formed explicitly; the filter gradient is dL/d(W_d / sigma),
+    handed to the spectral-norm backward of the network through sn.g like every other normalised weight."""
     n, h, w, c = x.shape
     kh, kw, c2, cm = Wd.data.shape
     assert c2 == c, (c2, c)
     pt, pl, ho, wo = _pads(padding, h, w, kh, kw, stride)
     xin = x if x.data.dtype == BF16 else cast(x, BF16)
-    y = K.depthwise_fwd(xin.data, Wd.data, b.data if b is not None else None, ho, wo, stride, pt, pl, out_dtype)
+    w_eff = Wd.data if sn is None else K.scale_dev(Wd.data, sn.inv_sigma)
+    y = K.depthwise_fwd(xin.data, w_eff, b.data if b is not None else None, ho, wo, stride, pt, pl, out_dtype)
     out = Var(y, grad_dtype=out_grad_dtype)
     need_w = Wd.needs_grad and _tape() is not None
     need_b = b is not None and b.needs_grad and _tape() is not None
     if _rg(xin) or need_w or need_b:
         out.requires_grad = True
+        tape = _tape()
 
         def bwd():
             gy = out.grad
@@ -340,11 +346,19 @@ def depthwise_conv2d(x: Var, Wd: Variable, b: Variable | None, stride: int = 1, 
                 return
             if need_b:
                 K.colsum(gy, n * ho * wo, c * cm, b.grad, 1.0)
-            if need_w:
+            if need_w and sn is None:
                 K.depthwise_bwd_filter(xin.data, gy, Wd.grad, kh, kw, cm, stride, pt, pl)
+            elif need_w:
+                if not sn.g_written:
+                    sn.g.zero_()                    # depthwise_bwd_filter adds into its destination
+                K.depthwise_bwd_filter(xin.data, gy, sn.g.view(Wd.data.shape), kh, kw, cm, stride, pt, pl)
+                sn.g_written = True
+                lst = tape.pending_sn.setdefault(Wd.root, [])
+                if sn not in lst:
+                    lst.append(sn)
             if xin.requires_grad:
-                xin.accum(K.depthwise_bwd_input(gy, Wd.data, h, w, stride, pt, pl, xin.gdtype))
-        _tape().record(bwd)
+                xin.accum(K.depthwise_bwd_input(gy, w_eff, h, w, stride, pt, pl, xin.gdtype))
+        tape.record(bwd)
     return out
 
 

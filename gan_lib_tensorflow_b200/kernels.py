@@ -511,6 +511,14 @@ def layer_norm_bwd(x, dy, mean_rstd, gamma, beta, act, dx_dtype, dgamma, dbeta):
     return dx
 
 
+def scale_dev(x, alpha_dev):
+    """alpha * x (fp32) with alpha a 1-element device tensor."""
+    assert x.dtype == torch.float32
+    y = torch.empty_like(x)
+    check(L().ganb_scale_dev(ptr(x), ptr(alpha_dev), ptr(y), c_int64(x.numel()), _stream()), "ganb_scale_dev")
+    return y
+
+
 def lerp_fwd(a, b, alpha_dev):
     """(1 - alpha) * a + alpha * b, fp32, alpha a device scalar."""
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape

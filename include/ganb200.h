@@ -376,6 +376,9 @@ int ganb_layer_norm_fwd(const void* x, int x_dtype, const float* gamma, const fl
 int ganb_layer_norm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* mean_rstd,
                         const float* gamma, const float* beta, void* dx, int dx_dtype, float* chan_partials,
                         void* workspace, int n, int64_t per_sample, int c, int act, void* stream);
+/* y = alpha * x, alpha a device scalar: W / sigma for the `depthwise_filters` of a spectrally-normalised
+ * depthwise / separable convolution (common/ops/conv2d.py:173-175); the other layers carry 1/sigma in the GEMM epilogue. */
+int ganb_scale_dev(const float* x, const float* alpha, float* y, int64_t count, void* stream);
 int ganb_lerp_fwd(const float* a, const float* b, float* y, int64_t count, const float* alpha, void* stream);
 int ganb_lerp_bwd(const float* dy, void* da, int da_dtype, void* db, int db_dtype, int64_t count, const float* alpha,
                   void* stream);

@@ -285,16 +285,29 @@ def Conv2D(g, inputs, input_dim, output_dim, filter_size=3, stride=1, name="Conv
             pointwise_filters = g.get_variable("pointwise_filters", initializer=lambda _s: _uniform(
                 stdev, (1, 1, input_dim * channel_multiplier, output_dim)))
         if conv_type != "conv2d":
-            # weight-norm / mask / spectral norm act on `Filters`, which these types never read (conv2d.py:153-171):
-            # only the `u` variable of the spectral norm is created
+            # weight-norm and the mask act on `Filters` only, which these types never read (conv2d.py:153-167).
+            # Spectral norm wraps ALL THREE filters (conv2d.py:169-178), each under its own scope: `filters` (W_bar
+            # unused, so in TF its u.assign never runs: the variable exists and keeps its initial value),
+            # `depthwise_filters` and `pointwise_filters` -- and the normalised ones are what the op consumes.  A
+            # W_bar that no op reads never runs its control-dependent u.assign in TF: evaluated with NO_OPS here.
+            pw_raw, pw_sigma = pointwise_filters, None
             if spectral_normed:
                 with g.variable_scope("filters"):
                     spectral_normed_weight(g, filters, update_collection=NO_OPS)
+                with g.variable_scope("depthwise_filters"):           # conv2d.py:173-175
+                    depthwise_filters = spectral_normed_weight(g, depthwise_filters, update_collection=update_collection)
+                with g.variable_scope("pointwise_filters"):           # conv2d.py:176-178
+                    uc = update_collection if conv_type == "separable_conv2d" else NO_OPS
+                    pointwise_filters, pw_sigma = spectral_normed_weight(g, pointwise_filters, update_collection=uc,
+                                                                         with_sigma=True)
             x_ = _ste_r16(inputs_) if BF16_OPERANDS else inputs_      # the B200 path reads conv operands in bf16
             result = depthwise_conv2d_nhwc(x_, depthwise_filters, stride, padding)        # conv2d.py:188-197
             if conv_type == "separable_conv2d":                       # conv2d.py:198-208: then the 1x1 pointwise conv
                 if BF16_OPERANDS:
-                    result = _ConvRoundedOperands.apply(result, _ste_r16(pointwise_filters), 1, "VALID")
+                    wq = _ste_r16(pw_raw)                             # bf16 operand copy of W, 1/sigma in the epilogue
+                    if pw_sigma is not None:
+                        wq = wq / pw_sigma
+                    result = _ConvRoundedOperands.apply(result, wq, 1, "VALID")
                 else:
                     result = conv2d_nhwc(result, pointwise_filters, 1, "VALID")
             if biases:

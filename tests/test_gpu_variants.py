@@ -450,7 +450,8 @@ def test_depthwise_conv2d(env, n, h, cin, cm, k, stride, padding):
 
 @pytest.mark.parametrize("n,h,cin,cout,cm,k,stride,sn", [
     (3, 16, 64, 128, 1, 4, 2, False),
-    (2, 16, 64, 64, 2, 4, 1, True),      # spectral_normed: creates u, leaves the result alone (acts on `Filters`)
+    (2, 16, 64, 64, 2, 4, 1, True),      # spectral_normed: depthwise AND pointwise filters are normalised (conv2d.py:169-178)
+    (3, 16, 64, 128, 1, 4, 2, True),     # PatchGAN layer shape of Pix2Pix with --conv_type separable_conv2d
     (2, 32, 3, 64, 4, 4, 2, False),      # RGB input: 12 depthwise channels into the pointwise conv
     (2, 8, 128, 8, 1, 3, 1, False),
 ])
@@ -467,8 +468,38 @@ def test_separable_conv2d(env, n, h, cin, cout, cm, k, stride, sn):
     assert {"L/depthwise_filters", "L/pointwise_filters", "L/Biases"} <= set(refs["fp32"]["params"])
     assert float(np.abs(prod["params"]["L/Filters"]).max()) == 0.0        # `Filters` exists but is never read
     if sn:
-        assert "L/filters/spectral_norm/u" in store.vars
-    check(prod, refs, tol_impl=3e-3, tag=f"separable {cin}->{cout} cm{cm} k{k} s{stride}")
+        for scope in ("filters", "depthwise_filters", "pointwise_filters"):
+            assert "L/%s/spectral_norm/u" % scope in store.vars
+        # sigma really is applied: the un-normalised layer gives a different result
+        from gan_lib_tensorflow_b200 import functional as F
+        np.random.seed(0)
+        plain = P.Conv2D(F.Var(torch.from_numpy(x).cuda()), cin, cout, k, stride, "L", conv_type="separable_conv2d",
+                         channel_multiplier=cm, spectral_normed=False).data.float().cpu().numpy()
+        assert rel(plain, refs["fp32"]["out"]) > 0.03
+    check(prod, refs, tol_impl=3e-3, tag=f"separable {cin}->{cout} cm{cm} k{k} s{stride} sn={sn}")
+
+
+def test_spectral_normed_depthwise_conv2d(env):
+    """conv_type='depthwise_conv2d' with spectral_normed (conv2d.py:173-175, 188-197): W_d / sigma_d is what the op
+    reads; u of the depthwise filter follows update_collection, the u of `Filters` / `pointwise_filters` (whose
+    normalised values no op reads) keep their initial values."""
+    store, tfshim = env
+    from gan_lib_tensorflow_b200.common.ops import conv2d as P
+    from oracle import ops as O
+
+    n, h, cin, cm, k, stride = 2, 16, 64, 2, 3, 1
+    x = _bf16_repr(np.random.RandomState(23).standard_normal((n, h, h, cin)).astype("float32"))
+    kw = dict(conv_type="depthwise_conv2d", channel_multiplier=cm, spectral_normed=True, update_collection=None)
+    prod, refs = run_pair(store, tfshim, lambda xv: P.Conv2D(xv, cin, cin * cm, k, stride, "L", **kw),
+                          lambda g, xt: O.Conv2D(g, xt, cin, cin * cm, k, stride, "L", **kw), x, bf16=False)
+    check(prod, refs, tol_fp32=2e-3, tag="depthwise spectral_normed")
+    u_rng = np.random.RandomState(2)          # the store's u stream (u_seed=2): filters, depthwise, pointwise
+    from gan_lib_tensorflow_b200.framework import truncated_normal
+    u_f, u_d, u_p = (truncated_normal([1, c], u_rng) for c in (cin * cm, cm, cin * cm))
+    got = {s: store.vars["L/%s/spectral_norm/u" % s].data.cpu().numpy() for s in
+           ("filters", "depthwise_filters", "pointwise_filters")}
+    assert np.array_equal(got["filters"], u_f) and np.array_equal(got["pointwise_filters"], u_p)
+    assert not np.allclose(got["depthwise_filters"], u_d)          # u <- u' (update_collection=None)
 
 
 def test_pix2pix_patchgan_with_separable_convs(env):

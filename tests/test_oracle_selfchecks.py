@@ -229,11 +229,44 @@ def test_depthwise_conv_matches_an_explicit_loop():
     g = tfshim.Graph(dtype=torch.float32, u_seed=2)
     out = O.Conv2D(g, torch.from_numpy(x), 3, 16, 4, 2, "L", conv_type="separable_conv2d", channel_multiplier=4,
                    spectral_normed=True, update_collection=O.NO_OPS)
+    # conv2d.py:169-178: spectral norm wraps Filters AND depthwise_filters AND pointwise_filters (three u variables,
+    # created in that order), and the normalised depthwise / pointwise filters are what separable_conv2d consumes
     assert list(g.vars) == ["L/Filters", "L/depthwise_filters", "L/pointwise_filters", "L/filters/spectral_norm/u",
-                            "L/Biases"]
-    dw = O.depthwise_conv2d_nhwc(torch.from_numpy(x), g.vars["L/depthwise_filters"], 2, "SAME")
-    pw = torch.einsum("nhwc,co->nhwo", dw, g.vars["L/pointwise_filters"][0, 0])
-    assert torch.allclose(out, pw, atol=1e-5)
+                            "L/depthwise_filters/spectral_norm/u", "L/pointwise_filters/spectral_norm/u", "L/Biases"]
+    assert tuple(g.vars["L/depthwise_filters/spectral_norm/u"].shape) == (1, 4)
+    assert tuple(g.vars["L/pointwise_filters/spectral_norm/u"].shape) == (1, 16)
+
+    def sigma_np(w, u):
+        """One power iteration from u written from sn.py:34-58 in float64 NumPy."""
+        w2 = np.asarray(w, "float64").reshape(-1, w.shape[-1])
+        v = np.asarray(u, "float64") @ w2.T
+        v /= np.sqrt((v ** 2).sum()) + 1e-12
+        u1 = v @ w2
+        u1 /= np.sqrt((u1 ** 2).sum()) + 1e-12
+        return float((v @ w2 @ u1.T)[0, 0])
+
+    wd, wp = g.vars["L/depthwise_filters"].detach(), g.vars["L/pointwise_filters"].detach()
+    sd = sigma_np(wd.numpy(), g.vars["L/depthwise_filters/spectral_norm/u"].numpy())
+    sp = sigma_np(wp.numpy(), g.vars["L/pointwise_filters/spectral_norm/u"].numpy())
+    dw = O.depthwise_conv2d_nhwc(torch.from_numpy(x), wd / sd, 2, "SAME")
+    pw = torch.einsum("nhwc,co->nhwo", dw, (wp / sp)[0, 0])
+    assert torch.allclose(out, pw.float(), atol=1e-5)
+    plain = torch.einsum("nhwc,co->nhwo", O.depthwise_conv2d_nhwc(torch.from_numpy(x), wd, 2, "SAME"), wp[0, 0])
+    assert not torch.allclose(out, plain, atol=1e-3)            # sigma of both filters really is applied
+    # update_collection=None assigns u of the two filters the op reads; the unused `Filters` never runs its assign in TF
+    np.random.seed(0)
+    g2 = tfshim.Graph(dtype=torch.float32, u_seed=2)
+    u0 = {}
+    O.Conv2D(g2, torch.from_numpy(x), 3, 12, 4, 2, "D", conv_type="depthwise_conv2d", channel_multiplier=4,
+             spectral_normed=True, update_collection=O.NO_OPS)
+    for k in list(g2.vars):
+        if k.endswith("/u"):
+            u0[k] = g2.vars[k].clone()
+    O.Conv2D(g2, torch.from_numpy(x), 3, 12, 4, 2, "D", conv_type="depthwise_conv2d", channel_multiplier=4,
+             spectral_normed=True, update_collection=None)       # existing variables are reused by name
+    assert not torch.equal(g2.vars["D/depthwise_filters/spectral_norm/u"], u0["D/depthwise_filters/spectral_norm/u"])
+    assert torch.equal(g2.vars["D/filters/spectral_norm/u"], u0["D/filters/spectral_norm/u"])
+    assert torch.equal(g2.vars["D/pointwise_filters/spectral_norm/u"], u0["D/pointwise_filters/spectral_norm/u"])
 
 
 def test_variant_ops_closed_forms():
