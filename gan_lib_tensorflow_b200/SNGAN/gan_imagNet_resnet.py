@@ -66,7 +66,7 @@ def Generator(n_samples_, labels, noise=None, reuse=False):
                 (DIM_G, DIM_G // 2)]
         for i, (din, dout) in enumerate(dims):
             output = _block(output, din, dout, 3, 'G.Block.%d' % (i + 1), resample='up', labels=labels, biases=True,
-                            out_dtype=BF16)
+                            out_dtype=BF16, out_bn_stats=True)
         output, _ = rb._norm_act('G.OutputNorm', output, labels, _normalize_kind('G.OutputNorm', labels), 'relu',
                                  n_labels=VOCAB_SIZE)
         output = conv2d_ops.Conv2D(output, DIM_G // 2, 3, 3, 1, 'G.Output', he_init=False)

@@ -114,13 +114,15 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
            conv_type='conv2d', channel_multiplier=0, padding='SAME',
            spectral_normed=False, update_collection=None, inputs_norm=False, he_init=True,
            mask_type=None, weightnorm=None, biases=True, gain=1., reuse=None,
-           residual=None, out_grad_dtype=None, residual_up2=False, out_dtype=None, subpixel_up2=False):
+           residual=None, out_grad_dtype=None, residual_up2=False, out_dtype=None, subpixel_up2=False,
+           bn_stats=False):
     """
     Args mirror common/ops/conv2d.py:31-55 (`reuse` is the extra keyword of conv2d_.py:33, accepted and ignored).
     `residual` (fp32 Var added in the GEMM epilogue; `residual_up2`: given at half resolution) and `out_grad_dtype`
     are extensions used by resnet_block.  `subpixel_up2`: the layer is UpsampleConv (nearest 2x in front of this 3x3
     convolution, common/resnet_block.py:83-97) and `inputs` is the LOW-resolution tensor: evaluated in sub-pixel
-    form, output in quad layout (functional.upconv2d).
+    form, output in quad layout (functional.upconv2d).  `bn_stats`: the output feeds a batch-statistics normalisation
+    (the convolution epilogue then also produces its per-channel sums, functional.conv2d).
 
     Returns:
       Var of shape (batch_size, out_height, out_width, output_dim), fp32
@@ -187,8 +189,9 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
             if (filter_size != 3 or stride != 1 or padding != 'SAME' or sn_entry is not None or in_scale is not None
                     or residual is not None):
                 raise NotImplementedError('sub-pixel UpsampleConv: plain 3x3 stride-1 SAME layers only')
-            return F.upconv2d(inputs, filters, _biases, out_grad_dtype=out_grad_dtype,
+            return F.upconv2d(inputs, filters, _biases, out_grad_dtype=out_grad_dtype, bn_stats=bn_stats,
                               **({'out_dtype': out_dtype} if out_dtype is not None else {}))
         return F.conv2d(inputs, filters, _biases, filter_size, filter_size, stride, padding, sn=sn_entry,
                         residual=residual, out_grad_dtype=out_grad_dtype, in_scale=in_scale,
-                        residual_up2=residual_up2, **({'out_dtype': out_dtype} if out_dtype is not None else {}))
+                        residual_up2=residual_up2, bn_stats=bn_stats,
+                        **({'out_dtype': out_dtype} if out_dtype is not None else {}))

@@ -123,7 +123,7 @@ def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None,
 def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
                   spectral_normed=False, update_collection=None, inputs_norm=False,
                   resample=None, labels=None, biases=True, activation_fn='relu',
-                  normalize_kind=None, pre_activated=None, out_dtype=None, n_labels=10):
+                  normalize_kind=None, pre_activated=None, out_dtype=None, n_labels=10, out_bn_stats=False):
     """resample: None, 'down', or 'up' -- common/resnet_block.py:100-156.
 
     out_dtype=torch.bfloat16 stores the block output (the input of the next block's normalisation) in bf16; the sum
@@ -131,7 +131,9 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
 
     normalize_kind overrides the name-based Normalize dispatch (used by the SNGAN scripts' own Normalize).
     pre_activated = (raw_bf16, act_bf16) lets a producer that already emitted both operands (the label-map
-    concat of D) skip the block's first activation pass."""
+    concat of D) skip the block's first activation pass.
+    out_bn_stats: the block output feeds a batch-statistics normalisation (the next block's N1 / the output norm of a
+    generator): Conv2's epilogue then leaves the per-channel sums next to the output (functional.conv2d)."""
     if resample not in (None, 'down', 'up'):
         raise Exception('invalid resample value')
     if activation_fn not in ('relu', 'lrelu'):
@@ -186,7 +188,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # and which is stored in bf16: it is only read by that kernel (rounding commutes with relu / leaky relu, so
     # without a normalisation in between this is bit-identical to rounding after the activation)
     h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16, out_dtype=BF16,
-              subpixel_up2=subpixel)
+              subpixel_up2=subpixel, bn_stats=kind(name + '.N2') in ('cbn', 'bn'))
 
     # ---- N2 + nonlinearity
     a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn, n_labels=n_labels)
@@ -201,6 +203,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # convolutions only: its gradient is a tensor-core operand, so it is produced in bf16 directly
     return conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut,
                 residual_up2=(resample == 'up' and not identity_shortcut), out_grad_dtype=BF16,
+                bn_stats=bool(out_bn_stats) and out_dtype == BF16,
                 **({'out_dtype': out_dtype} if out_dtype is not None else {}))
 
 

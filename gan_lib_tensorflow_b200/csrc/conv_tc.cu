@@ -3,7 +3,7 @@
 //
 //   conv_igemm_kernel : fprop / dgrad / 1x1 / linear.  A = activation box (K-major, 128B swizzle),
 //                       B = packed filter [tap][cout][cin] (K-major).  Persistent, warp-specialised:
-//                       warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+//                       warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue.
 //   conv_wgrad_kernel : filter gradient.  Both operands are MN-major (channels contiguous, pixels = K),
 //                       split over pixel ranges; partials reduced by splitk_reduce_kernel.
 //
@@ -18,8 +18,19 @@ namespace ganb {
 constexpr int BM = 128;                      // UMMA M: output pixels (igemm) / input channels (wgrad)
 constexpr int BK = 64;                       // bf16 elements per 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+// Warp roles of the fprop / dgrad kernels: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2.. epilogue.
+// A warp may only read the TMEM lane quadrant (warp & 3), so the 128 accumulator rows need four warps.
+// GANB_EPI_SPLIT = 2 drains tiles of >= 64 channels with EIGHT warps (two per quadrant, half of the columns each).
+// Measured and NOT used: the kernel time of the K = 2304 layers is unchanged (they are MMA-paced), while 352 threads x
+// ~165 registers take 88 % of the SM's register file and evict the bandwidth-bound kernels of the other streams that
+// otherwise run next to the convolution: +0.15 ms per D+G pair (profiles/r02_fused_stats_ab.txt).
+#ifndef GANB_EPI_SPLIT
+#define GANB_EPI_SPLIT 1
+#endif
+constexpr int NUM_THREADS = 64 + 128 * GANB_EPI_SPLIT;
+constexpr int WG_THREADS = 192;              // filter-gradient kernel: warps 2..5 drain its single accumulator
+__host__ __device__ constexpr int epi_split(int bn) { return (GANB_EPI_SPLIT == 2 && bn >= 64) ? 2 : 1; }
+__host__ __device__ constexpr int epi_threads(int bn) { return 128 * epi_split(bn); }
 
 struct IgemmParams {
   int N, Ho, Wo, Cout;
@@ -73,53 +84,56 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// Column sums over the 32 pixels of a warp: every lane holds 32 per-pixel values r[0..32); lane L returns
-// sum over lanes of r[L].  Halving butterfly (16 + 8 + 4 + 2 + 1 = 31 shuffles), fixed order.
-__device__ __forceinline__ float warp_transpose_sum32(float (&r)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int j = 0; j < off; ++j) {
-      const float send = upper ? r[j] : r[j + off];
-      const float keep = upper ? r[j + off] : r[j];
-      r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return r[0];
-}
-
 // Fused batch statistics: the 4 epilogue warps of a CTA leave their 32-pixel column sums in shared memory
 // ([warp][{sum, sumsq}][BN]); epilogue_stats_flush folds them and writes the tile's row of IgemmParams::stats.
+// The sums over the 32 pixels of a warp go through a padded shared-memory transpose (t): 32 conflict-free stores and
+// 32 conflict-free loads per 32-channel chunk, all independent.  (A shuffle butterfly costs the same instruction
+// count but its five dependent levels stall the single epilogue warp of each scheduler: +35 % on the 256-channel
+// CTA-pair kernel, profiles/r02_fused_stats_ab.txt.)
 template <int BN>
 struct EpiStats {
   float s[4][2][BN];
+  float t[8][8][33];
 };
 
+// `ew`: index of the epilogue warp (0..7), q its TMEM lane quadrant, c0 the first of its 32 channels inside the tile
 template <int NC, int BN>
-__device__ __forceinline__ void epilogue_stats_chunk(EpiStats<BN>& st, const float (&val)[NC], bool valid, int q,
+__device__ __forceinline__ void epilogue_stats_chunk(EpiStats<BN>& st, const float (&val)[NC], bool valid, int ew, int q,
                                                      int lane, int c0) {
   static_assert(NC == 32, "fused statistics need 32-column chunks");
-  float a[32], b[32];
+  const int ch = lane & 7, k0 = (lane >> 3) * 8;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    a[j] = valid ? val[j] : 0.f;
-    b[j] = a[j] * a[j];
+  for (int part = 0; part < 4; ++part) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st.t[ew][j][lane] = valid ? val[part * 8 + j] : 0.f;
+    __syncwarp();
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {          // fixed order: deterministic
+      const float v = st.t[ew][ch][k0 + k];
+      sum += v;
+      sq += v * v;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+    if (lane < 8) {
+      st.s[q][0][c0 + part * 8 + ch] = sum;
+      st.s[q][1][c0 + part * 8 + ch] = sq;
+    }
+    __syncwarp();
   }
-  const float ts = warp_transpose_sum32(a, lane);
-  const float tq = warp_transpose_sum32(b, lane);
-  st.s[q][0][c0 + lane] = ts;
-  st.s[q][1][c0 + lane] = tq;
 }
 
-// called by all EPI_THREADS epilogue threads after the chunk loop of a tile (contains a named barrier)
+// called by all epilogue threads of the CTA after the chunk loop of a tile (contains a named barrier)
 template <int BN>
 __device__ __forceinline__ void epilogue_stats_flush(const IgemmParams& p, const EpiStats<BN>& st, int64_t row,
                                                      bool row_ok, int co_tile, int et) {
-  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(epi_threads(BN)) : "memory");
   if (row_ok) {
     float* out = p.stats + row * 2 * p.Cout;
-    for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+    for (int i = et; i < 2 * BN; i += epi_threads(BN)) {
       const int k = i / BN, c = i - k * BN;
       const int co = co_tile + c;
       if (co < p.Cout) out[k * p.Cout + co] = (st.s[0][k][c] + st.s[1][k][c]) + (st.s[2][k][c] + st.s[3][k][c]);
@@ -231,16 +245,28 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
   }
 }
 
-// Epilogue warps: TMEM -> registers -> (alpha, bias, residual, activation) -> global, one output pixel per thread.
-template <int BN>
+// Epilogue warps: TMEM -> registers -> (alpha, bias, residual, activation) -> global, one output pixel per thread and
+// (for BN >= 64) one half of the tile's channels per warp.
+// `stat_mem`: 16-byte aligned dynamic shared memory behind the barriers; holds an EpiStats<BN> when p.stats is set (the
+// host adds its size to the launch only then: resident bandwidth-bound blocks of other streams need the space otherwise)
+// STATS is a template parameter: the statistics code needs ~65 more registers per thread, and the register footprint of
+// a convolution CTA decides how many bandwidth-bound blocks of the other streams run next to it.
+template <int BN, bool STATS>
 __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tmem_base, uint64_t* tfull,
-                                              uint64_t* tempty, int warp, int lane) {
+                                              uint64_t* tempty, int warp, int lane, void* stat_mem) {
   constexpr int ACC_STAGES = 2;
-  constexpr int NC = BN < 32 ? BN : 32;  // columns per tcgen05.ld
+  constexpr int SPLIT = epi_split(BN);
+  constexpr int EPI_T = epi_threads(BN);
+  constexpr int CB = BN / SPLIT;          // channels drained by one warp
+  constexpr int NC = CB < 32 ? CB : 32;   // columns per tcgen05.ld
   __shared__ __align__(16) float bias_s[ACC_STAGES][BN];
+  EpiStats<(STATS ? BN : 1)>& stat_s = *static_cast<EpiStats<(STATS ? BN : 1)>*>(stat_mem);
+  const int ew = warp - 2;                // epilogue warp 0..7
+  const int half = ew >> 2;
+  if (half >= SPLIT) return;              // narrow tiles: warps 6..9 have nothing to drain
   const int q = warp & 3;  // TMEM lane quadrant this warp may access
   const int m = q * 32 + lane;
-  const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);  // 0..127 among the epilogue threads
+  const int et = threadIdx.x - 64;        // 0..EPI_T-1 among the epilogue threads
   const int iw = m % p.bw;
   const int ih = (m / p.bw) % p.bh;
   const int in_ = m / (p.bw * p.bh);
@@ -259,29 +285,39 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
     const int64_t res_pix =
         p.res_up2 ? (static_cast<int64_t>(n) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1) : pix;
     if (p.bias) {  // stage this tile's bias slice; the two buffers alternate with the accumulator stage
-      for (int c = et; c < BN; c += EPI_THREADS) {
+      for (int c = et; c < BN; c += EPI_T) {
         const int co = tco * BN + c;
         bias_s[as][c] = co < p.Cout ? __ldg(p.bias + co) : 0.f;
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
     mbar_wait(&tfull[as], aphase);
     tc_fence_after();
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * CB;
 #pragma unroll 1
-    for (int c = 0; c < BN / NC; ++c) {
+    for (int c = 0; c < CB / NC; ++c) {
+      const int col = half * CB + c * NC;   // first channel of this chunk inside the tile
       uint32_t r[NC];
       tmem_ld_cols<NC>(trow + c * NC, r);
       tmem_ld_wait();
-      if (valid) epilogue_row<NC>(p, r, alpha, pix * p.out_cstride, res_pix, tco * BN + c * NC, &bias_s[as][c * NC]);
+      if constexpr (STATS) {
+        float val[NC];
+        if (valid)
+          epilogue_row<NC>(p, r, alpha, pix * p.out_cstride, res_pix, tco * BN + col, &bias_s[as][col], val);
+        epilogue_stats_chunk<NC, BN>(stat_s, val, valid, ew, q, lane, col);
+      } else {
+        if (valid) epilogue_row<NC>(p, r, alpha, pix * p.out_cstride, res_pix, tco * BN + col, &bias_s[as][col]);
+      }
     }
     tc_fence_before();
     mbar_arrive(&tempty[as]);
+    // one statistics row per pixel tile: tile / tiles_co is the image-major pixel-tile index
+    if constexpr (STATS) epilogue_stats_flush<BN>(p, stat_s, tile / p.tiles_co, true, tco * BN, et);
     if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const IgemmParams p) {
@@ -314,7 +350,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], EPI_THREADS);
+      mbar_init(&tempty[i], epi_threads(BN));
     }
     fence_mbar_init();
   }
@@ -398,8 +434,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane);
+    // ===================== epilogue (warps 2..9) =====================
+    epilogue_loop<BN, STATS>(p, tmem_base, tfull, tempty, warp, lane, tmem_slot + 4);
   }
 
   tc_fence_before();
@@ -423,7 +459,7 @@ constexpr int HALO_BW = 8, HALO_BH = 16;
 constexpr int HALO_A_WARP = NUM_THREADS / 32;     // extra warp after the epilogue warps
 constexpr int HALO_THREADS = NUM_THREADS + 32;
 
-template <int BN, int SA, int SB>
+template <int BN, int SA, int SB, bool STATS>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const IgemmParams p, int a_stage_bytes, int halo_w, int halo_bytes) {
@@ -453,7 +489,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_threads(BN)); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -547,7 +583,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else {
-    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane);
+    epilogue_loop<BN, STATS>(p, tmem_base, tfull, tempty, warp, lane, tmem_slot + 4);
   }
 
   tc_fence_before();
@@ -594,7 +630,7 @@ conv_halo_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     mbar_init(fullB, 1);
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_threads(BN)); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -679,7 +715,7 @@ conv_halo_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else {
-    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane);
+    epilogue_loop<BN, false>(p, tmem_base, tfull, tempty, warp, lane, tmem_slot + 4);
   }
 
   tc_fence_before();
@@ -698,7 +734,7 @@ conv_halo_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 // utilisation (10 TB/s of TMA traffic = the chip's L2 throughput, profiles/r01_halo_ncu_summary.txt).
 // Barriers: fullA / fullB live in the leader and count both CTAs' bytes; emptyA / emptyB / tfull are signalled in both
 // CTAs by a multicast commit; tempty lives in the leader and collects one arrival per epilogue warp of both CTAs.
-template <int BN, int SA, int SB>
+template <int BN, int SA, int SB, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const IgemmParams p, int a_stage_bytes, int halo_w, int halo_bytes) {
@@ -736,7 +772,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * (EPI_THREADS / 32)); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * (epi_threads(BN) / 32)); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -842,11 +878,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 of both CTAs): own 128 pixels x BN channels =====================
+    // ===================== epilogue (warps 2..9 of both CTAs): own 128 pixels x BN channels =====================
+    constexpr int EPI_T = epi_threads(BN);
+    constexpr int CB = BN / epi_split(BN);  // channels drained by one warp
     __shared__ __align__(16) float bias_s[ACC_STAGES][BN];
+    EpiStats<BN>& stat_s = *reinterpret_cast<EpiStats<BN>*>(tmem_slot + 4);   // dynamic, present when p.stats is set
+    const int ew = warp - 2;
+    const int half = ew >> 2;
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);
+    const int et = threadIdx.x - 64;
     const int iw = m % p.bw;
     const int ih = (m / p.bw) % p.bh;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
@@ -857,6 +898,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int tco = tile % p.tiles_co;
       const int go = (tile / p.tiles_co) % p.og;
       int t = 2 * (tile / tiles_cg) + static_cast<int>(rank);
+      const int pix_tile = t;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int wo = tw * p.bw + iw, ho = th * p.bh + ih, n = t;
@@ -865,27 +907,37 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int64_t res_pix =
           p.res_up2 ? (static_cast<int64_t>(n) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1) : pix;
       if (p.bias) {
-        for (int c = et; c < BN; c += EPI_THREADS) {
+        for (int c = et; c < BN; c += EPI_T) {
           const int co = tco * BN + c;
           bias_s[as][c] = co < p.Cout ? __ldg(p.bias + co) : 0.f;
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * CB;
 #pragma unroll 1
-      for (int c = 0; c < BN / NC; ++c) {
+      for (int c = 0; c < CB / NC; ++c) {
+        const int col = half * CB + c * NC;
         uint32_t r[NC];
         tmem_ld_cols<NC>(trow + c * NC, r);
         tmem_ld_wait();
-        if (valid)
-          epilogue_row<NC>(p, r, alpha, pix * p.out_cstride + go * p.Cout, res_pix, tco * BN + c * NC,
-                           &bias_s[as][c * NC]);
+        if constexpr (STATS) {
+          float val[NC];
+          if (valid)
+            epilogue_row<NC>(p, r, alpha, pix * p.out_cstride + go * p.Cout, res_pix, tco * BN + col,
+                             &bias_s[as][col], val);
+          epilogue_stats_chunk<NC, BN>(stat_s, val, valid, ew, q, lane, col);
+        } else {
+          if (valid)
+            epilogue_row<NC>(p, r, alpha, pix * p.out_cstride + go * p.Cout, res_pix, tco * BN + col, &bias_s[as][col]);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + as * 8);
+      if constexpr (STATS)   // the odd tile of the last pair lies past the batch (n >= N): it has no statistics row
+        epilogue_stats_flush<BN>(p, stat_s, static_cast<int64_t>(pix_tile) * p.og + go, n < p.N, tco * BN, et);
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   }
@@ -919,7 +971,7 @@ struct WgradParams {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const WgradParams p) {
   constexpr int A_BYTES = PB * BM * 2;  // two 64-channel boxes of PB pixel rows
@@ -1107,15 +1159,25 @@ static void pick_box(int total, int H, int W, int* bw, int* bh, int* bn) {
   *bn = total / (w * h);
 }
 
+// dynamic shared memory of the fused-statistics buffers (only when the launch produces them)
+template <int BN>
+static int stats_smem(const IgemmParams& p) {
+  return (p.stats && BN >= 64) ? static_cast<int>(sizeof(EpiStats<BN>)) + 16 : 0;
+}
+
 template <int BN, int STAGES>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
-  static bool configured = false;
-  auto kern = conv_igemm_kernel<BN, STAGES>;
-  if (!configured) {
+  const int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + stats_smem<BN>(p);
+  auto kern = conv_igemm_kernel<BN, STAGES, false>;
+  bool with_stats = false;
+  if constexpr (BN >= 64) {
+    if (p.stats) { kern = conv_igemm_kernel<BN, STAGES, true>; with_stats = true; }
+  }
+  static int configured[2] = {0, 0};
+  if (configured[with_stats] < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "igemm smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    configured[with_stats] = smem;
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
@@ -1128,14 +1190,18 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPar
 template <int BN, int SA, int SB>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, int a_stage_bytes, int halo_w,
                        int halo_bytes, cudaStream_t stream) {
-  const int smem = SA * a_stage_bytes + SB * BN * BK * 2 + 1024 + 512;
-  if (smem > 232448) return fail(GANB_E_UNSUPPORTED, "conv halo kernel: %d bytes of shared memory needed", smem);
-  auto kern = conv_halo_kernel<BN, SA, SB>;
-  static int configured = 0;
-  if (configured < smem) {
+  const int smem = SA * a_stage_bytes + SB * BN * BK * 2 + 1024 + 512 + stats_smem<BN>(p);
+  if (smem + 8 * BN + 64 > 232448) return fail(GANB_E_UNSUPPORTED, "conv halo kernel: %d bytes of shared memory needed", smem);
+  auto kern = conv_halo_kernel<BN, SA, SB, false>;
+  bool with_stats = false;
+  if constexpr (BN >= 64) {
+    if (p.stats) { kern = conv_halo_kernel<BN, SA, SB, true>; with_stats = true; }
+  }
+  static int configured[2] = {0, 0};
+  if (configured[with_stats] < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "halo smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
+    configured[with_stats] = smem;
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
@@ -1177,14 +1243,15 @@ static bool pair_mode() {
 template <int BN, int SA, int SB>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, int a_stage_bytes, int halo_w,
                        int halo_bytes, cudaStream_t stream) {
-  const int smem = SA * a_stage_bytes + SB * (BN / 2) * BK * 2 + 1024 + 512;
-  if (smem > 232448) return fail(GANB_E_UNSUPPORTED, "conv pair kernel: %d bytes of shared memory needed", smem);
-  auto kern = conv_pair_kernel<BN, SA, SB>;
-  static int configured = 0;
-  if (configured < smem) {
+  const int smem = SA * a_stage_bytes + SB * (BN / 2) * BK * 2 + 1024 + 512 + stats_smem<BN>(p);
+  if (smem + 8 * BN + 64 > 232448) return fail(GANB_E_UNSUPPORTED, "conv pair kernel: %d bytes of shared memory needed", smem);
+  auto kern = p.stats ? conv_pair_kernel<BN, SA, SB, true> : conv_pair_kernel<BN, SA, SB, false>;
+  const bool with_stats = p.stats != nullptr;
+  static int configured[2] = {0, 0};
+  if (configured[with_stats] < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "pair smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
+    configured[with_stats] = smem;
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -1201,10 +1268,57 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
 
 using namespace ganb;
 
+namespace ganb {
+// pixel tiling of ganb_conv2d_igemm: halo tiles (16 x 8 pixels of one image) or a 128-pixel box over (n, h, w)
+static bool igemm_tiling(int ho, int wo, int kh, int kw, int stride, int* bw, int* bh, int* bn) {
+  const bool halo = (kh * kw > 1) && stride == 1 && ho >= HALO_BH && wo >= HALO_BW && (kh + HALO_BH - 1) <= 256;
+  if (halo) {
+    *bw = HALO_BW; *bh = HALO_BH; *bn = 1;
+  } else {
+    pick_box(BM, ho, wo, bw, bh, bn);
+  }
+  return halo;
+}
+}  // namespace ganb
+
+static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho, int wo,
+                             int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
+                             const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
+                             int out_dtype, float* stats, void* stream_);
+
 extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho,
                                  int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
                                  int flip_taps, const float* alpha, const float* bias, const float* residual,
                                  int residual_up2, int act, int out_dtype, void* stream_) {
+  return conv2d_igemm_impl(x, wp, y, n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l, flip_taps, alpha, bias,
+                           residual, residual_up2, act, out_dtype, nullptr, stream_);
+}
+
+extern "C" int ganb_conv2d_stats_rows(int n, int ho, int wo, int cout, int kh, int kw, int stride, int groups) {
+  if (n <= 0 || ho <= 0 || wo <= 0 || groups <= 0 || cout < 64 || cout % 32 != 0 || n % groups != 0) return 0;
+  int bw, bh, bn;
+  igemm_tiling(ho, wo, kh, kw, stride, &bw, &bh, &bn);
+  if ((n / groups) % bn != 0) return 0;          // a pixel tile would straddle two statistic towers
+  return ceil_div(wo, bw) * ceil_div(ho, bh) * ((n / groups) / bn);
+}
+
+extern "C" int ganb_conv2d_igemm_stats(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho,
+                                       int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
+                                       int flip_taps, const float* alpha, const float* bias, const float* residual,
+                                       int residual_up2, int act, int out_dtype, float* stats, int groups,
+                                       void* stream_) {
+  if (!stats) return fail(GANB_E_BADARG, "conv2d_igemm_stats: null statistics buffer");
+  if (!ganb_conv2d_stats_rows(n, ho, wo, cout, kh, kw, stride, groups))
+    return fail(GANB_E_UNSUPPORTED, "conv2d_igemm_stats: n=%d ho=%d wo=%d cout=%d groups=%d (see ganb_conv2d_stats_rows)",
+                n, ho, wo, cout, groups);
+  return conv2d_igemm_impl(x, wp, y, n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l, flip_taps, alpha, bias,
+                           residual, residual_up2, act, out_dtype, stats, stream_);
+}
+
+static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho, int wo,
+                             int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
+                             const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
+                             int out_dtype, float* stats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !wp || !y) return fail(GANB_E_BADARG, "conv2d_igemm: null buffer");
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || ho <= 0 || wo <= 0 || cout <= 0 || kh <= 0 || kw <= 0)
@@ -1220,12 +1334,8 @@ extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, 
   p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
   // halo path: every tap reads one shared-memory halo tile (needs 8-pixel row groups: 16 x 8 tiles per image)
   // strided convolutions gather every stride-th pixel through the TMA element strides of the per-tap box
-  const bool halo = (kh * kw > 1) && stride == 1 && ho >= HALO_BH && wo >= HALO_BW && (kh + HALO_BH - 1) <= 256;
-  if (halo) {
-    p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1;
-  } else {
-    pick_box(BM, ho, wo, &p.bw, &p.bh, &p.bn);
-  }
+  const bool halo = igemm_tiling(ho, wo, kh, kw, stride, &p.bw, &p.bh, &p.bn);
+  p.stats = stats;
   p.tiles_w = ceil_div(wo, p.bw);
   p.tiles_h = ceil_div(ho, p.bh);
   p.tiles_n = ceil_div(n, p.bn);
@@ -1359,7 +1469,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
     if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "wgrad smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  launch_k(kern, grid, NUM_THREADS, smem, stream, tmX, tmDY, p);
+  launch_k(kern, grid, WG_THREADS, smem, stream, tmX, tmDY, p);
   GANB_CHECK_LAUNCH("conv_wgrad_kernel");
   return 0;
 }
@@ -1507,8 +1617,10 @@ static bool upconv_shape_ok(int n, int h, int w, int cin, int cout) {
 // One launch of the pair kernel over the low-resolution tile grid.  fprop: og = 4 output groups; dgrad: rg = 4
 // reduction groups over the channel slices of the quad-layout gradient.
 static int launch_upconv(bool dgrad, const void* a, const void* wp, void* out, int n, int h, int w, int ca, int cn,
-                         const float* alpha, const float* bias, int act, int out_dtype, cudaStream_t stream) {
+                         const float* alpha, const float* bias, int act, int out_dtype, cudaStream_t stream,
+                         float* stats = nullptr) {
   IgemmParams p;
+  p.stats = stats;
   p.N = n; p.Ho = h; p.Wo = w; p.Cout = cn;
   p.taps = 4; p.kw = 2; p.stride = 1; p.pad_t = 0; p.pad_l = 0;
   p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1;
@@ -1570,6 +1682,21 @@ extern "C" int ganb_upconv_fprop(const void* x_bf16, const void* we_t_bf16, void
     return fail(GANB_E_UNSUPPORTED, "upconv_fprop: n=%d h=%d w=%d cin=%d cout=%d (see ganb_upconv_supported)", n, h, w, cin, cout);
   return launch_upconv(false, x_bf16, we_t_bf16, y_quad, n, h, w, cin, cout, alpha, bias, act, out_dtype,
                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ganb_upconv_stats_rows(int n, int h, int w, int cin, int cout, int groups) {
+  if (!upconv_shape_ok(n, h, w, cin, cout) || groups <= 0 || n % groups != 0 || cout % 32 != 0) return 0;
+  return (w / HALO_BW) * (h / HALO_BH) * (n / groups) * 4;      // four output parities per low-resolution pixel tile
+}
+
+extern "C" int ganb_upconv_fprop_stats(const void* x_bf16, const void* we_t_bf16, void* y_quad, int n, int h, int w,
+                                       int cin, int cout, const float* alpha, const float* bias, int act, int out_dtype,
+                                       float* stats, int groups, void* stream) {
+  if (!x_bf16 || !we_t_bf16 || !y_quad || !stats) return fail(GANB_E_BADARG, "upconv_fprop_stats: null buffer");
+  if (!ganb_upconv_stats_rows(n, h, w, cin, cout, groups))
+    return fail(GANB_E_UNSUPPORTED, "upconv_fprop_stats: n=%d h=%d w=%d cin=%d cout=%d groups=%d", n, h, w, cin, cout, groups);
+  return launch_upconv(false, x_bf16, we_t_bf16, y_quad, n, h, w, cin, cout, alpha, bias, act, out_dtype,
+                       static_cast<cudaStream_t>(stream), stats);
 }
 
 extern "C" int ganb_upconv_dgrad(const void* dy_quad_bf16, const void* we_n_bf16, void* dx, int n, int h, int w, int cin,

@@ -1655,6 +1655,18 @@ extern "C" int ganb_bn_stats(const void* x, int x_dtype, int n, int hw, int c, i
   return 0;
 }
 
+// mean / rstd from per-tile column sums produced by a convolution epilogue (ganb_conv2d_igemm_stats,
+// ganb_upconv_fprop_stats): partial [groups][chunks][{sum, sumsq}][c], count = elements per channel and tower.
+extern "C" int ganb_bn_stats_finalize(const float* partial, int c, int groups, int chunks, int64_t count, float eps,
+                                      float* mean, float* rstd, void* stream) {
+  if (!partial || !mean || !rstd) return fail(GANB_E_BADARG, "bn_stats_finalize: null buffer");
+  if (c <= 0 || groups <= 0 || chunks <= 0 || count <= 0) return fail(GANB_E_BADARG, "bn_stats_finalize: bad shape");
+  launch_k(bn_stats_finalize_kernel, ceil_div(groups * c, 8), 256, 0, STREAM, partial, c, groups, chunks,
+           1.0f / static_cast<float>(count), eps, mean, rstd);
+  GANB_CHECK_LAUNCH("bn_stats_finalize_kernel");
+  return 0;
+}
+
 static int bwd_chunks(int n, int hw) {
   int chunks = ceil_div(8 * sm_count(), n);
   const int max_chunks = ceil_div(hw, 16);

@@ -38,11 +38,12 @@ _ALIGN = 64  # floats: every variable starts on a 256-byte boundary inside the f
 class Var:
     """A value on the tape: `data` is a device tensor, `grad` is filled by Tape.backward()."""
 
-    __slots__ = ("data", "grad", "requires_grad", "grad_dtype", "quad")
+    __slots__ = ("data", "grad", "requires_grad", "grad_dtype", "quad", "stats")
 
     def __init__(self, data: torch.Tensor, requires_grad: bool = False, grad_dtype=None):
         self.data = data
         self.quad = False   # storage is the quad layout of functional.upconv2d (value AND gradient)
+        self.stats = None   # kernels.FusedStats left by the producing convolution's epilogue (functional.conv2d)
         self.grad = None
         self.requires_grad = requires_grad
         self.grad_dtype = grad_dtype  # dtype producers should use for this value's gradient (None: fp32)

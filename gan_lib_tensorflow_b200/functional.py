@@ -169,9 +169,23 @@ def _pads(padding, h, w, kh, kw, stride):
     return pt, pl, ho, wo
 
 
+# Batch statistics of a layer output accumulated in the convolution epilogue (ganb_conv2d_igemm_stats).  Built, tested
+# (tests/test_gpu_fused.py) and measured: alone, conv + fused statistics beats conv + ganb_bn_stats (108.7 vs 97.2 + 26.9
+# us on the dominant layer), but inside the D+G pair schedule the separate statistics kernel runs for free next to the
+# other stream's tensor-core kernel while the longer epilogue holds the tensor pipe: 3.30 vs 3.20 ms per pair, same box
+# (profiles/r02_fused_stats_ab.txt).  Default therefore OFF; GANB_FUSED_STATS=1 turns it on.
+FUSED_BN_STATS = __import__("os").environ.get("GANB_FUSED_STATS", "0") == "1"
+
+
+def _stat_groups(n: int, groups: int | None = None) -> int:
+    """Statistic towers of a batch of n (the rule of norm_act)."""
+    g = groups if groups is not None else get_store().stat_groups
+    return g if n % g == 0 else 1
+
+
 def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: int = 1, padding: str = "SAME",
            sn=None, residual: Var | None = None, out_grad_dtype=None, in_scale: float | None = None,
-           residual_up2: bool = False, out_dtype=F32) -> Var:
+           residual_up2: bool = False, out_dtype=F32, bn_stats: bool = False) -> Var:
     """NHWC x HWIO cross-correlation (tf.nn.conv2d, common/ops/conv2d.py:181-187) + bias (+ residual), fp32 out.
 
     `sn` is a framework.SNEntry whose 1/sigma multiplies the accumulator (W/sigma is never materialised).
@@ -183,7 +197,10 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
 
     stride > 1 (Pix2Pix encoders / PatchGAN): the forward and filter-gradient kernels gather every stride-th pixel
     through TMA element strides; the data gradient is the stride-1 kernel applied to the zero-dilated output
-    gradient (correct for any TF padding; the structural zeros cost stride^2 more MMA work than necessary)."""
+    gradient (correct for any TF padding; the structural zeros cost stride^2 more MMA work than necessary).
+
+    `bn_stats`: the output feeds a batch-statistics normalisation; where the kernel supports it the epilogue also leaves
+    the per-tile column sums of y and y^2 (out.stats, consumed by norm_act instead of a separate pass over y)."""
     store = get_store()
     n, h, w, cin = x.shape
     cout = W.data.shape[-1]
@@ -213,6 +230,7 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     pack = group.entry(W)
     group.refresh()
     xcol = None
+    fused = None
     if small_in:
         xin = x if x.data.dtype == F32 else cast(x, F32)
         if route_in:
@@ -228,9 +246,15 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
         if cin % 8:
             raise NotImplementedError(f"cin={cin}: tensor-core path needs cin % 8 == 0")
         xin = x if x.data.dtype == BF16 else cast(x, BF16)
-        y = K.conv_igemm(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res,
-                         None, out_dtype, residual_up2=residual_up2, stride=stride)
+        g_stats = _stat_groups(n) if (bn_stats and FUSED_BN_STATS) else 0
+        if g_stats and K.conv_stats_rows(n, ho, wo, cout, kh, kw, stride, g_stats):
+            y, fused = K.conv_igemm_stats(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha,
+                                          bias, res, None, out_dtype, g_stats, residual_up2=residual_up2, stride=stride)
+        else:
+            y = K.conv_igemm(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res,
+                             None, out_dtype, residual_up2=residual_up2, stride=stride)
     out = Var(y, grad_dtype=out_grad_dtype)
+    out.stats = fused
     need_w = W.needs_grad and _tape() is not None
     need_b = b is not None and b.needs_grad and _tape() is not None
     if _rg(xin, residual) or need_w or need_b:
@@ -371,7 +395,8 @@ def upconv_eligible(n: int, h: int, w: int, cin: int, cout: int, k: int = 3) -> 
     return (SUBPIXEL_UPCONV and k == 3 and n * h * w >= 16384 and K.upconv_supported(n, h, w, cin, cout))
 
 
-def upconv2d(x: Var, W: Variable, b: Variable | None, out_grad_dtype=None, out_dtype=BF16) -> Var:
+def upconv2d(x: Var, W: Variable, b: Variable | None, out_grad_dtype=None, out_dtype=BF16,
+             bn_stats: bool = False) -> Var:
     """UpsampleConv (common/resnet_block.py:83-97) = nearest 2x + 3x3 SAME Conv2D + bias, computed as four 2x2
     convolutions over the LOW-resolution x (4/9 of the MMA work, the upsampled tensor is never written).
 
@@ -386,8 +411,16 @@ def upconv2d(x: Var, W: Variable, b: Variable | None, out_grad_dtype=None, out_d
         group.valid_for = None
     group.refresh()
     xin = x if x.data.dtype == BF16 else cast(x, BF16)
-    y = K.upconv_fprop(xin.data, pack.we_t, n, h, w, cin, cout, None, b.data if b is not None else None, None, out_dtype)
+    g_stats = _stat_groups(n) if (bn_stats and FUSED_BN_STATS) else 0
+    fused = None
+    if g_stats and K.upconv_stats_rows(n, h, w, cin, cout, g_stats):
+        y, fused = K.upconv_fprop_stats(xin.data, pack.we_t, n, h, w, cin, cout, None,
+                                        b.data if b is not None else None, None, out_dtype, g_stats)
+    else:
+        y = K.upconv_fprop(xin.data, pack.we_t, n, h, w, cin, cout, None, b.data if b is not None else None, None,
+                           out_dtype)
     out = Var(y, grad_dtype=out_grad_dtype)
+    out.stats = fused
     out.quad = True
     need_w = W.needs_grad and _tape() is not None
     need_b = b is not None and b.needs_grad and _tape() is not None
@@ -626,7 +659,11 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
     # cross-GPU batch statistics (store.bn_sync = (allreduce_sum, world)): only for statistics over the BATCH
     sync = store.bn_sync if stats == "batch" else None
     if stats is not None:
-        mean, rstd = K.bn_stats(x.data, n, h * w, c, g, eps)
+        fused = x.stats if stats == "batch" else None
+        if fused is not None and fused.groups == g and fused.c == c:
+            mean, rstd = fused.finalize((n // g) * h * w, eps)     # sums left by the producing conv's epilogue
+        else:
+            mean, rstd = K.bn_stats(x.data, n, h * w, c, g, eps)
         if sync is not None:
             K.bn_stats_sync(mean, rstd, eps, sync)
     gam = gamma.data if gamma is not None else None

@@ -16,28 +16,27 @@ from .cabi import BF16, F32, act_code, check, ptr
 _L = None
 
 
-class _NullLib:
-    """Host-logic test double (GANB_HOST_LOGIC_ONLY=1): every entry point is a no-op that reports success, so
-    variable naming / RNG order / tape wiring can be exercised on a machine without a GPU.  NO arithmetic is
-    performed and outputs stay uninitialised -- this is not a fallback and is never selected implicitly."""
+_TEST_DOUBLE = False
 
-    def __getattr__(self, name):
-        if name.endswith("_workspace"):
-            return lambda *a: 16
-        return lambda *a: 0
+
+def install_test_double(lib) -> None:
+    """Test hook (tests/hostlogic.py): replaces the C-ABI library by an object that records / ignores calls, so that
+    variable naming, RNG order and tape wiring can be exercised on a machine without a GPU.  The double itself lives in
+    tests/; nothing in the product selects it -- without this call every entry point goes to libganb200.so and
+    cabi.lib() raises when the library is missing.  install_test_double(None) restores the real library."""
+    global _L, _TEST_DOUBLE
+    _L = lib
+    _TEST_DOUBLE = lib is not None
 
 
 def host_logic_only() -> bool:
-    import os
-    return os.environ.get("GANB_HOST_LOGIC_ONLY") == "1"
+    """True while a test double is installed (no device, no streams)."""
+    return _TEST_DOUBLE
 
 
 def L():
     global _L
     if _L is None:
-        if host_logic_only():
-            _L = _NullLib()
-            return _L
         _L = cabi.lib()
         for name in ("ganb_launch_count", "ganb_conv2d_wgrad_workspace", "ganb_upconv_wgrad_workspace",
                      "ganb_norm_act_bwd_sums_offset", "ganb_l1_loss_workspace", "ganb_bn_bwd_vjp_workspace", "ganb_conv2d_small_wgrad_workspace", "ganb_bn_stats_workspace",
@@ -105,6 +104,41 @@ def conv_igemm(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, al
     return y
 
 
+class FusedStats:
+    """Per-tile column sums (y, y^2) left by a convolution epilogue for the batch norm behind the layer."""
+
+    __slots__ = ("partial", "rows", "groups", "c")
+
+    def __init__(self, partial, rows, groups, c):
+        self.partial, self.rows, self.groups, self.c = partial, rows, groups, c
+
+    def finalize(self, count_per_group: int, eps: float):
+        """-> (mean, rstd) [groups, c], the values ganb_bn_stats would return."""
+        dev = self.partial.device
+        mean = torch.empty((self.groups, self.c), dtype=torch.float32, device=dev)
+        rstd = torch.empty((self.groups, self.c), dtype=torch.float32, device=dev)
+        check(L().ganb_bn_stats_finalize(ptr(self.partial), self.c, self.groups, self.rows, c_int64(count_per_group),
+                                         c_float(eps), ptr(mean), ptr(rstd), _stream()), "ganb_bn_stats_finalize")
+        return mean, rstd
+
+
+def conv_stats_rows(n, ho, wo, cout, kh, kw, stride, groups) -> int:
+    return int(L().ganb_conv2d_stats_rows(n, ho, wo, cout, kh, kw, stride, groups))
+
+
+def conv_igemm_stats(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, alpha, bias, residual, act,
+                     out_dtype, groups, residual_up2=False, stride=1):
+    """conv_igemm that also returns the FusedStats of its (stored) output for `groups` statistic towers."""
+    rows = conv_stats_rows(n, ho, wo, cout, kh, kw, stride, groups)
+    y = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
+    partial = torch.empty((groups, rows, 2, cout), dtype=torch.float32, device=x.device)
+    check(L().ganb_conv2d_igemm_stats(ptr(x), ptr(wp), ptr(y), n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l,
+                                      int(flip), ptr(alpha), ptr(bias), ptr(residual), int(bool(residual_up2)),
+                                      act_code(act), BF16 if out_dtype == torch.bfloat16 else F32, ptr(partial), groups,
+                                      _stream()), "ganb_conv2d_igemm_stats")
+    return y, FusedStats(partial, rows, groups, cout)
+
+
 def conv_wgrad(x, dy, dw, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, scale, beta, stride=1):
     nbytes = L().ganb_conv2d_wgrad_workspace(n, h, w, cin, ho, wo, cout, kh, kw)
     ws = _ws(nbytes, x.device)
@@ -127,6 +161,20 @@ def upconv_fprop(x, we_t, n, h, w, cin, cout, alpha, bias, act, out_dtype):
     check(L().ganb_upconv_fprop(ptr(x), ptr(we_t), ptr(y), n, h, w, cin, cout, ptr(alpha), ptr(bias), act_code(act),
                                 BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_upconv_fprop")
     return y
+
+
+def upconv_stats_rows(n, h, w, cin, cout, groups) -> int:
+    return int(L().ganb_upconv_stats_rows(n, h, w, cin, cout, groups))
+
+
+def upconv_fprop_stats(x, we_t, n, h, w, cin, cout, alpha, bias, act, out_dtype, groups):
+    rows = upconv_stats_rows(n, h, w, cin, cout, groups)
+    y = torch.empty((n, 2 * h, 2 * w, cout), dtype=out_dtype, device=x.device)
+    partial = torch.empty((groups, rows, 2, cout), dtype=torch.float32, device=x.device)
+    check(L().ganb_upconv_fprop_stats(ptr(x), ptr(we_t), ptr(y), n, h, w, cin, cout, ptr(alpha), ptr(bias),
+                                      act_code(act), BF16 if out_dtype == torch.bfloat16 else F32, ptr(partial), groups,
+                                      _stream()), "ganb_upconv_fprop_stats")
+    return y, FusedStats(partial, rows, groups, cout)
 
 
 def upconv_dgrad(dy_quad, we_n, n, h, w, cin, cout, alpha, out_dtype):

@@ -72,6 +72,21 @@ int ganb_conv2d_igemm(const void* x_bf16, const void* wp_bf16, void* y, int n, i
                       int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
                       const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
                       int out_dtype, void* stream);
+/* Batch statistics fused into the convolution epilogue (the reference computes them with a separate tf.nn.moments over
+ * the layer output, common/ops/normalization.py:29,47): the epilogue leaves, per 128-pixel output tile, the column sums
+ * of the STORED output y and of y^2 (after alpha / bias / residual / activation and the rounding to out_dtype) in
+ *   stats [groups][rows][2][cout]   (fp32; rows = ganb_conv2d_stats_rows(...), tiles are image-major, so the tiles of
+ *                                    one statistic tower are contiguous)
+ * and ganb_bn_stats_finalize folds the rows in a fixed order (deterministic) into mean / rstd [groups][cout] -- the same
+ * quantities ganb_bn_stats returns, without re-reading y.  ganb_conv2d_stats_rows returns 0 when the layer cannot do it
+ * (cout % 32 != 0, or a pixel tile would straddle two towers): callers then use ganb_bn_stats. */
+int ganb_conv2d_stats_rows(int n, int ho, int wo, int cout, int kh, int kw, int stride, int groups);
+int ganb_conv2d_igemm_stats(const void* x_bf16, const void* wp_bf16, void* y, int n, int h, int w, int cin, int ho,
+                            int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
+                            const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
+                            int out_dtype, float* stats, int groups, void* stream);
+int ganb_bn_stats_finalize(const float* partial, int c, int groups, int chunks, int64_t count, float eps, float* mean,
+                           float* rstd, void* stream);
 
 /* Filter gradient: partial[split][t][ci][co] = sum over the split's pixels of
  *     x[n, ho*stride + r - pad_t, wo*stride + s - pad_l, ci] * dy[n, ho, wo, co]
@@ -168,6 +183,12 @@ int ganb_upconv_supported(int n, int h, int w, int cin, int cout);
 int ganb_upconv_pack(const float* w_hwio, void* we_t_bf16, void* we_n_bf16, int cin, int cout, void* stream);
 int ganb_upconv_fprop(const void* x_bf16, const void* we_t_bf16, void* y_quad, int n, int h, int w, int cin, int cout,
                       const float* alpha, const float* bias, int act, int out_dtype, void* stream);
+/* ganb_upconv_fprop with the fused statistics of ganb_conv2d_igemm_stats: one row per (low-resolution pixel tile,
+ * output parity), rows = ganb_upconv_stats_rows(...) per tower (0: unsupported). */
+int ganb_upconv_stats_rows(int n, int h, int w, int cin, int cout, int groups);
+int ganb_upconv_fprop_stats(const void* x_bf16, const void* we_t_bf16, void* y_quad, int n, int h, int w, int cin,
+                            int cout, const float* alpha, const float* bias, int act, int out_dtype, float* stats,
+                            int groups, void* stream);
 int ganb_upconv_dgrad(const void* dy_quad_bf16, const void* we_n_bf16, void* dx, int n, int h, int w, int cin, int cout,
                       const float* alpha, int out_dtype, void* stream);
 int64_t ganb_upconv_wgrad_workspace(int n, int h, int w, int cin, int cout);

@@ -1,7 +1,7 @@
 """CPU tier: the C-ABI library loads and exports everything include/ganb200.h declares (no compute calls), the
 ctypes mirrors of its structs match the C layout, and the host-side mirror of the reference interface (variable
 scopes, reuse, NumPy-RNG order, spectral-norm update_collection bookkeeping, optimistic restore) behaves like the
-reference.  Layer functions run with GANB_HOST_LOGIC_ONLY=1: every kernel call is a recorded no-op, so nothing
+reference.  Layer functions run against a recording test double (tests/hostlogic.py): every kernel call is a no-op, so nothing
 here computes -- arithmetic is only ever checked on the GPU tier against the oracle."""
 import ctypes
 import os
@@ -16,39 +16,19 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class RecordingLib:
-    """Stands in for libganb200 on a machine without a GPU: records (name, args) and reports success."""
-
-    def __init__(self):
-        self.calls = []
-
-    def __getattr__(self, name):
-        if name.endswith("_workspace"):
-            return lambda *a: 16
-        if name == "ganb_launch_count":
-            return lambda *a: len(self.calls)
-
-        def fn(*a):
-            self.calls.append((name, a))
-            return 0
-        return fn
-
-    def names(self):
-        return [c[0] for c in self.calls]
+from tests.hostlogic import RecordingLib  # noqa: E402
 
 
 @pytest.fixture()
-def host(monkeypatch):
-    monkeypatch.setenv("GANB_HOST_LOGIC_ONLY", "1")
+def host():
     from gan_lib_tensorflow_b200 import framework
-    from gan_lib_tensorflow_b200 import kernels as K
+    from tests import hostlogic
 
-    rec = RecordingLib()
-    monkeypatch.setattr(K, "_L", rec)
+    rec = hostlogic.install(RecordingLib())
     store = framework.reset_default_graph("cpu", u_seed=2)
     yield store, rec
     framework.set_store(None)
-    monkeypatch.setattr(K, "_L", None)
+    hostlogic.uninstall()
 
 
 # ------------------------------------------------------------------------------------------------ C ABI
@@ -85,7 +65,9 @@ def test_struct_mirrors_match_the_c_layout():
 def test_no_cpu_fallback_when_library_or_gpu_is_missing(monkeypatch):
     from gan_lib_tensorflow_b200 import cabi, framework
 
-    monkeypatch.delenv("GANB_HOST_LOGIC_ONLY", raising=False)
+    from gan_lib_tensorflow_b200 import kernels as K
+    assert not K.host_logic_only()          # no test double installed: the product has no other way to run without a GPU
+    monkeypatch.setenv("GANB_HOST_LOGIC_ONLY", "1")      # the round-1 switch is gone: the variable changes nothing
     monkeypatch.setattr(cabi, "_lib", None)
     monkeypatch.setattr(cabi, "LIB_PATH", "/nonexistent/libganb200.so")
     with pytest.raises(cabi.GanbError):
@@ -544,7 +526,8 @@ def test_same_padding_helper():
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, {root!r})
-os.environ["GANB_HOST_LOGIC_ONLY"] = "1"
+from tests import hostlogic
+hostlogic.install()
 import torch, torch.distributed as dist
 from gan_lib_tensorflow_b200 import framework
 from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
@@ -596,7 +579,8 @@ def test_two_rank_gradient_allreduce_gloo():
 _WORKER_LOOP = r'''
 import os, sys, tempfile
 sys.path.insert(0, {root!r})
-os.environ["GANB_HOST_LOGIC_ONLY"] = "1"
+from tests import hostlogic
+hostlogic.install()
 import numpy as np, torch, torch.distributed as dist
 from gan_lib_tensorflow_b200 import framework
 from gan_lib_tensorflow_b200.ACGAN import train as AT
