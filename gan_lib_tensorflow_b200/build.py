@@ -45,13 +45,16 @@ def _stamp() -> str:
                 h.update(f.encode())
                 with open(p, "rb") as fh:
                     h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS).encode())
     return h.hexdigest()
+
+
+EXTRA_FLAGS = os.environ.get("GANB_NVCC_EXTRA", "").split()   # e.g. -DGANB_LEAN_SMEM for A/B builds (tests/ab/)
 
 
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

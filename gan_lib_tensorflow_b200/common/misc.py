@@ -162,20 +162,74 @@ def checkpoint_state(optimizers=()):
         suffix = '' if i == 0 else '_%d' % i
         state['beta1_power' + suffix] = np.float32(opt.beta1 ** (opt.t + 1))
         state['beta2_power' + suffix] = np.float32(opt.beta2 ** (opt.t + 1))
+        # beta2^(t+1) underflows in fp32 after ~1000 steps, so the step count is also stored as an integer (not a TF name)
+        state['ganb200/adam_step' + suffix] = np.int64(opt.t)
     return state
 
 
-def save_checkpoint(save_file, optimizers=(), tf_bundle: bool = False):
+MAX_TO_KEEP = 5   # tf.train.Saver(max_to_keep=5), the default of the reference's savers
+
+
+def _checkpoint_files(prefix: str):
+    """Files that make up the checkpoint `prefix` (.npz, or a tensor bundle's .index / .data-* shards)."""
+    d, base = os.path.split(prefix)
+    out = []
+    for f in os.listdir(d or '.'):
+        if f == base + '.npz' or f == base + '.index' or f.startswith(base + '.data-'):
+            out.append(os.path.join(d, f))
+    return out
+
+
+def _kept_checkpoints(directory: str):
+    """all_model_checkpoint_paths of the directory's `checkpoint` state file, oldest first."""
+    kept = []
+    state_file = os.path.join(directory, 'checkpoint')
+    if os.path.exists(state_file):
+        with open(state_file) as fh:
+            for line in fh:
+                if line.startswith('all_model_checkpoint_paths:'):
+                    kept.append(line.split(':', 1)[1].strip().strip('"'))
+    return kept
+
+
+def _rotate_checkpoints(path: str, max_to_keep: int, kept) -> None:
+    """What tf.train.Saver does next to every save: the `checkpoint` state file of the directory
+    (model_checkpoint_path + all_model_checkpoint_paths, oldest first) and deletion of everything but the last
+    `max_to_keep` checkpoints.  kept: the list before this save (_kept_checkpoints)."""
+    d = os.path.dirname(path) or '.'
+    base = os.path.basename(path[:-4] if path.endswith('.npz') else path)
+    kept = [k for k in kept if k != base] + [base]
+    if max_to_keep and max_to_keep > 0:
+        for old in kept[:-max_to_keep]:
+            for f in _checkpoint_files(os.path.join(d, old)):
+                try:
+                    os.remove(f)
+                except OSError:
+                    pass
+        kept = kept[-max_to_keep:]
+    with open(os.path.join(d, 'checkpoint'), 'w') as fh:
+        fh.write('model_checkpoint_path: "%s"\n' % base)
+        for k in kept:
+            fh.write('all_model_checkpoint_paths: "%s"\n' % k)
+
+
+def save_checkpoint(save_file, optimizers=(), tf_bundle: bool = False, max_to_keep: int = MAX_TO_KEEP, extra=None):
     """saver.save(): one .npz of checkpoint_state(); tf_bundle=True writes TensorFlow's tensor-bundle container instead
-    (`<save_file>.index` + `.data-00000-of-00001` + the `checkpoint` state file, common/tf_checkpoint.py -- pure-Python
-    checksums, slow for large models)."""
+    (`<save_file>.index` + `.data-00000-of-00001`, common/tf_checkpoint.py -- pure-Python checksums, slow for large
+    models).  Like tf.train.Saver(max_to_keep=5) the directory keeps a `checkpoint` state file and only the last
+    `max_to_keep` checkpoints (0 / None: keep everything).  extra: further entries, e.g. {'Variable': global_step}, the
+    name TF gives the trainers' un-named global_step counter (ACGAN/train.py:124, Pix2Pix/train.py:520)."""
     state = checkpoint_state(optimizers)
+    if extra:
+        state.update({k: np.asarray(v) for k, v in extra.items()})
     path = os.fspath(save_file)
+    kept = _kept_checkpoints(os.path.dirname(path) or '.')
     if tf_bundle:
         from .tf_checkpoint import write_checkpoint
         write_checkpoint(path, {k: np.asarray(v, dtype=np.float32) for k, v in state.items()})
-        return sorted(state)
-    np.savez(path if path.endswith('.npz') else path + '.npz', **{k: np.asarray(v) for k, v in state.items()})
+    else:
+        np.savez(path if path.endswith('.npz') else path + '.npz', **{k: np.asarray(v) for k, v in state.items()})
+    _rotate_checkpoints(path, max_to_keep, kept)
     return sorted(state)
 
 
@@ -204,7 +258,16 @@ def restore_checkpoint(save_file, optimizers=()):
                     restored.append(v.key + slot)
         suffix = '' if i == 0 else '_%d' % i
         b2p = state.get('beta2_power' + suffix)
-        if b2p is not None and 0.0 < float(b2p) < 1.0 and 0.0 < opt.beta2 < 1.0:
-            opt.t = max(int(round(np.log(float(b2p)) / np.log(opt.beta2))) - 1, 0)
+        step = state.get('ganb200/adam_step' + suffix)
+        if step is not None:
+            opt.t = int(step)
+            restored.append('ganb200/adam_step' + suffix)
+        elif b2p is not None and 0.0 < opt.beta2 < 1.0:
+            if 0.0 < float(b2p) < 1.0:
+                opt.t = max(int(round(np.log(float(b2p)) / np.log(opt.beta2))) - 1, 0)
+            else:
+                # a TensorFlow checkpoint whose beta2_power has underflowed to 0 in fp32: the optimiser is fully warmed
+                # up (sqrt(1 - beta2^t) = 1 to fp32 precision); any large t reproduces TF's learning-rate factor
+                opt.t = 1 << 20
             restored.append('beta2_power' + suffix)
     return restored

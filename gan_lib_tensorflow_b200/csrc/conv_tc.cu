@@ -15,6 +15,17 @@
 
 namespace ganb {
 
+// Pipeline depths (shared-memory stages).  Every kernel below is one CTA per SM; what it leaves of the 227 KB decides
+// which bandwidth-bound blocks of the other streams can run next to it (the cp.async-ring kernels of elementwise.cu
+// need 48-96 KB).  GANB_LEAN_SMEM builds the shallower set for A/B runs (profiles/r02_smem_stages_ab.txt).
+#ifdef GANB_LEAN_SMEM
+constexpr int ST_PAIR256_SB = 6, ST_PAIR128_SB = 8, ST_HALO64_SB = 6, ST_HALO128_SB = 6, ST_HALO256_SB = 4;
+constexpr int ST_IG64 = 6, ST_IG128 = 5, ST_IG256 = 3, ST_WG64 = 4, ST_WG128 = 4, ST_WG256 = 3;
+#else
+constexpr int ST_PAIR256_SB = 8, ST_PAIR128_SB = 12, ST_HALO64_SB = 9, ST_HALO128_SB = 8, ST_HALO256_SB = 5;
+constexpr int ST_IG64 = 8, ST_IG128 = 6, ST_IG256 = 4, ST_WG64 = 6, ST_WG128 = 6, ST_WG256 = 4;
+#endif
+
 constexpr int BM = 128;                      // UMMA M: output pixels (igemm) / input channels (wgrad)
 constexpr int BK = 64;                       // bf16 elements per 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
@@ -1402,8 +1413,8 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
     const int halo_bytes = halo_w * halo_h * 128;
     const int a_stage = (halo_bytes + 1023) / 1024 * 1024;
     if (pair) {
-      if (pair_bn == 256) return launch_pair<256, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
-      return launch_pair<128, 4, 12>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      if (pair_bn == 256) return launch_pair<256, 3, ST_PAIR256_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      return launch_pair<128, 4, ST_PAIR128_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
     }
     // narrow outputs: resident filter when it fits next to four halo stages
     if (bn_tile == 16 && cout <= 16 && 4 * a_stage + p.taps * p.kchunks * 16 * BK * 2 + 2048 <= 232448)
@@ -1411,17 +1422,17 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
     switch (bn_tile) {
       case 16: return launch_halo<16, 7, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
       case 32: return launch_halo<32, 6, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
-      case 64: return launch_halo<64, 5, 9>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
-      case 128: return launch_halo<128, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
-      default: return launch_halo<256, 2, 5>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 64: return launch_halo<64, 5, ST_HALO64_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      case 128: return launch_halo<128, 3, ST_HALO128_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+      default: return launch_halo<256, 2, ST_HALO256_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
     }
   }
   switch (bn_tile) {
     case 16: return launch_igemm<16, 8>(tmA, tmB, p, stream);
     case 32: return launch_igemm<32, 8>(tmA, tmB, p, stream);
-    case 64: return launch_igemm<64, 8>(tmA, tmB, p, stream);
-    case 128: return launch_igemm<128, 6>(tmA, tmB, p, stream);
-    default: return launch_igemm<256, 4>(tmA, tmB, p, stream);
+    case 64: return launch_igemm<64, ST_IG64>(tmA, tmB, p, stream);
+    case 128: return launch_igemm<128, ST_IG128>(tmA, tmB, p, stream);
+    default: return launch_igemm<256, ST_IG256>(tmA, tmB, p, stream);
   }
 }
 
@@ -1516,9 +1527,9 @@ extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void*
   }
   int rc;
   switch (plan.bn_tile) {
-    case 64: rc = launch_wgrad<64, 6>(tmX, tmDY, p, plan.grid, stream); break;
-    case 128: rc = launch_wgrad<128, 6>(tmX, tmDY, p, plan.grid, stream); break;
-    default: rc = launch_wgrad<256, 4>(tmX, tmDY, p, plan.grid, stream); break;
+    case 64: rc = launch_wgrad<64, ST_WG64>(tmX, tmDY, p, plan.grid, stream); break;
+    case 128: rc = launch_wgrad<128, ST_WG128>(tmX, tmDY, p, plan.grid, stream); break;
+    default: rc = launch_wgrad<256, ST_WG256>(tmX, tmDY, p, plan.grid, stream); break;
   }
   if (rc) return rc;
   const int64_t total = static_cast<int64_t>(kh) * kw * cin * cout;
@@ -1656,8 +1667,8 @@ static int launch_upconv(bool dgrad, const void* a, const void* wp, void* out, i
   }
   const int halo_bytes = halo_w * halo_h * 128;
   const int a_stage = (halo_bytes + 1023) / 1024 * 1024;
-  if (pair_bn == 256) return launch_pair<256, 3, 8>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
-  return launch_pair<128, 4, 12>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+  if (pair_bn == 256) return launch_pair<256, 3, ST_PAIR256_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
+  return launch_pair<128, 4, ST_PAIR128_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
 }
 
 }  // namespace ganb
@@ -1743,9 +1754,9 @@ extern "C" int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, f
   }
   int rc;
   switch (plan.bn_tile) {
-    case 64: rc = launch_wgrad<64, 6>(tmX, tmDY, p, plan.grid, stream); break;
-    case 128: rc = launch_wgrad<128, 6>(tmX, tmDY, p, plan.grid, stream); break;
-    default: rc = launch_wgrad<256, 4>(tmX, tmDY, p, plan.grid, stream); break;
+    case 64: rc = launch_wgrad<64, ST_WG64>(tmX, tmDY, p, plan.grid, stream); break;
+    case 128: rc = launch_wgrad<128, ST_WG128>(tmX, tmDY, p, plan.grid, stream); break;
+    default: rc = launch_wgrad<256, ST_WG256>(tmX, tmDY, p, plan.grid, stream); break;
   }
   if (rc) return rc;
   const int64_t plane4 = static_cast<int64_t>(cin) * cout / 4;

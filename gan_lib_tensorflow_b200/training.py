@@ -162,7 +162,14 @@ def reference_loop(trainer, max_iter: int, step_fn, scalars_fn, dev_cost_fn, sam
             latest = max(ckpts, key=lambda f: int(f.split('-')[1].split('.')[0]))
             log('Restore model from: {}...'.format(latest))
             prefix = latest.split('.npz')[0].split('.index')[0].split('.data-')[0]     # .npz or a TF tensor bundle
-            lib_misc.restore_checkpoint(os.path.join(checkpoint_dir, prefix), opts)
+            restored_path = os.path.join(checkpoint_dir, prefix)
+            lib_misc.restore_checkpoint(restored_path, opts)
+            # the trainers' global_step (TF name `Variable`) drives the polynomial learning-rate decay of ACGAN / Pix2Pix
+            if hasattr(trainer, 'global_step') and os.path.exists(restored_path + '.npz'):
+                import numpy as np
+                with np.load(restored_path + '.npz') as z:
+                    if 'Variable' in z.files:
+                        trainer.global_step = int(z['Variable'])
         else:
             log('No checkpoint found in: {}'.format(checkpoint_dir))
     captured = False
@@ -182,6 +189,7 @@ def reference_loop(trainer, max_iter: int, step_fn, scalars_fn, dev_cost_fn, sam
             lib_misc.save_images(samples_fn(step), os.path.join(out_dir, 'samples_{}.png'.format(step)))
             if not os.path.exists(checkpoint_dir):
                 os.mkdir(checkpoint_dir)
-            lib_misc.save_checkpoint(os.path.join(checkpoint_dir, 'model.ckpt-{}'.format(step)), opts)
+            extra = {'Variable': int(trainer.global_step)} if hasattr(trainer, 'global_step') else None
+            lib_misc.save_checkpoint(os.path.join(checkpoint_dir, 'model.ckpt-{}'.format(step)), opts, extra=extra)
         lib_plot.tick()
     return trainer

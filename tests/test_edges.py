@@ -126,6 +126,41 @@ def test_checkpoint_names_and_round_trip(host, tmp_path):  # noqa: F811
     assert got == ["g_net/G.Input/b"]
 
 
+def test_checkpoint_rotation_and_step_counts(host, tmp_path):  # noqa: F811
+    """tf.train.Saver(max_to_keep=5) behaviour of the savers in the reference scripts: the directory keeps the last five
+    checkpoints and a `checkpoint` state file; the Adam step count survives a save / restore after beta2^(t+1) has
+    underflowed in fp32, and a TensorFlow checkpoint with an underflowed beta2_power restores as a warmed-up optimiser."""
+    store, _ = host
+    from gan_lib_tensorflow_b200.PGGAN import train as PT
+    from gan_lib_tensorflow_b200.common import misc, tf_checkpoint
+
+    tr = PT.Trainer(block_count=0, trans=False, batch_size=2, seed=0)
+    og, od = tr.players.opt["g"], tr.players.opt["d"]
+    for step in range(8):
+        og.t, od.t = 1000 * step, 5000 * step
+        misc.save_checkpoint(tmp_path / ("model.ckpt-%d" % step), (og, od), extra={"Variable": np.int64(step)})
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("model.ckpt-"))
+    assert files == ["model.ckpt-%d.npz" % i for i in range(3, 8)]
+    lines = open(tmp_path / "checkpoint").read().splitlines()
+    assert lines[0] == 'model_checkpoint_path: "model.ckpt-7"'
+    assert lines[1:] == ['all_model_checkpoint_paths: "model.ckpt-%d"' % i for i in range(3, 8)]
+    assert tf_checkpoint.latest_checkpoint(str(tmp_path)).endswith("model.ckpt-7")
+    with np.load(tmp_path / "model.ckpt-7.npz") as z:
+        assert int(z["Variable"]) == 7 and float(z["beta2_power_1"]) == 0.0          # 0.9^35001 underflows in fp32
+    og.t = od.t = 0
+    misc.restore_checkpoint(tmp_path / "model.ckpt-7", (og, od))
+    assert og.t == 7000 and od.t == 35000
+    # a TensorFlow-written state has no integer step: beta2_power == 0 means "fully warmed up"
+    state = misc.checkpoint_state((og, od))
+    state = {k: v for k, v in state.items() if not k.startswith("ganb200/")}
+    og.t = od.t = 0
+    misc.restore_checkpoint(state, (og, od))
+    assert od.t >= 1 << 20 and og.t >= 1 << 20
+    # max_to_keep=0 keeps everything
+    misc.save_checkpoint(tmp_path / "model.ckpt-8", (og, od), max_to_keep=0)
+    assert len([f for f in os.listdir(tmp_path) if f.startswith("model.ckpt-")]) == 6
+
+
 def test_tf1_tensor_bundle_reader(host, tmp_path):  # noqa: F811
     """common/tf_checkpoint.py: the TensorFlow-1 checkpoint container (LevelDB-style table index + raw data shard) read
     without TensorFlow.  Known answers for the checksum, a hand-assembled table block, a multi-block round trip through
@@ -266,7 +301,9 @@ def test_reference_train_loop_call_sequence(host, tmp_path, capsys):  # noqa: F8
     # gan_loss launches: 15 D-steps + 2 G-steps + 15 gen_cost fetches + 2 dev batches
     assert names.count("ganb_gan_loss") == 15 + 2 + 15 + 2
     assert os.path.exists(tmp_path / "samples_1.png") and os.path.exists(tmp_path / "log.pkl")
-    assert sorted(os.listdir(tmp_path / "checkpoint")) == ["model.ckpt-0.npz", "model.ckpt-1.npz", "model.ckpt-2.npz"]
+    # three checkpoints and the Saver's `checkpoint` state file (max_to_keep = 5 not reached)
+    assert sorted(os.listdir(tmp_path / "checkpoint")) == ["checkpoint", "model.ckpt-0.npz", "model.ckpt-1.npz",
+                                                           "model.ckpt-2.npz"]
     with open(tmp_path / "log.pkl", "rb") as fh:
         log = pickle.load(fh)
     assert set(log) == {"d_cost", "g_cost", "dev_cost"} and sorted(log["d_cost"]) == [0, 1, 2] and list(log["dev_cost"]) == [1]
@@ -305,7 +342,7 @@ def test_acgan_and_pggan_train_loops_call_sequence(host, tmp_path, capsys):  # n
     names = rec.names()[n0:]
     assert tr.players.opt["g"].t == 2 and tr.players.opt["d"].t == 6        # G skipped at step 0; 2 D-steps per step
     assert names.count("ganb_adam") == 8 and names.count("ganb_sample_grid") == 1
-    assert sorted(os.listdir(out_a / "checkpoint")) == ["model.ckpt-1.npz"] and os.path.exists(out_a / "samples_1.png")
+    assert sorted(os.listdir(out_a / "checkpoint")) == ["checkpoint", "model.ckpt-1.npz"] and os.path.exists(out_a / "samples_1.png")
     printed = capsys.readouterr().out
     assert "step: 0, d_loss_gan:" in printed and "step: 2, g_loss_gan:" in printed and "dev_cost" in printed
     with open(out_a / "log.pkl", "rb") as fh:
