@@ -255,8 +255,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     store = framework.reset_default_graph("cuda")
     allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    peer, peer_note = None, None
+    if world > 1 and getattr(args, "bn_sync", False):
+        try:   # statistic exchanges as peer-memory kernels inside the graphs (gan_lib_tensorflow_b200/peer.py)
+            from gan_lib_tensorflow_b200.peer import PeerComm
+            peer = PeerComm()
+            peer_note = "peer-memory kernels (csrc/peer.cu) inside the CUDA graphs"
+        except Exception as e:  # noqa: BLE001
+            peer_note = f"NCCL all-reduce, eager (symmetric memory unavailable: {type(e).__name__}: {str(e)[:60]})"
     tr = P.Trainer(batch_size=64, seed=0, world_size=world, grad_allreduce=allreduce,
-                   bn_sync=bool(getattr(args, "bn_sync", False)))
+                   bn_sync=bool(getattr(args, "bn_sync", False)), peer=peer)
 
     # synthetic inputs of SURVEY 8(d): int32 [64, 3072] uniform 0..255 (CHW-flattened), labels uniform 0..9;
     # every rank draws its own shard.
@@ -266,7 +274,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     host_losses = torch.zeros(2, dtype=torch.float32).pin_memory()
     tr.set_real_batch(host_data, host_labels)
 
-    use_pair = not getattr(args, "no_pair_schedule", False) and not tr.bn_sync
+    use_pair = not getattr(args, "no_pair_schedule", False) and (not tr.bn_sync or tr.bn_sync_in_graph)
 
     def pair(it):
         tr.sample_noise()
@@ -354,8 +362,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "l2": "no explicit flush: one step streams ~3 GB of activations, >> 126 MB L2",
             "schedule": "D+G pair as one CUDA graph, generator-step G forward next to the critic step (Trainer.pair_step)"
                         if use_pair else "critic step and generator step as separate CUDA graphs",
-            "cuda_graphs": not tr.bn_sync,
-            "bn_statistics": "all-reduced over ranks" if tr.bn_sync else "per rank (reference towers)",
+            "cuda_graphs": (not tr.bn_sync) or tr.bn_sync_in_graph,
+            "bn_statistics": ("all-reduced over ranks: " + str(peer_note)) if tr.bn_sync else "per rank (reference towers)",
             "final_d_loss": d_loss, "final_g_loss": g_loss,
             "value_counts": "batch-64 D+G pairs per second summed over ranks (global images/s / 64)",
         },

@@ -136,17 +136,23 @@ class Trainer:
     lr_schedule = staticmethod(lambda it: lr_decay(it))
 
     def __init__(self, batch_size: int = BATCH_SIZE, seed: int | None = 0, store=None, world_size: int = 1,
-                 grad_allreduce=None, bn_sync: bool = False):
+                 grad_allreduce=None, bn_sync: bool = False, peer=None):
         """bn_sync: reduce the (conditional) batch-norm statistics of G over all ranks as well (every statistic tower
         then spans the ranks' shares: N GPUs x batch/N reproduce one GPU at the global batch).  Default: per-rank
-        statistics, the reference's per-tower semantics.  The statistic all-reduces sit in the middle of the forward /
-        backward passes, so this mode runs eagerly (capture() is a no-op)."""
+        statistics, the reference's per-tower semantics.
+        peer: a peer.PeerComm -- the statistic exchanges then are single peer-memory kernels inside the captured graphs
+        (csrc/peer.cu).  Without it they go through the all-reduce callable in the middle of the passes, and the mode
+        runs eagerly (capture() is a no-op)."""
         self.store = store or get_store()
         self.bn_sync = bool(bn_sync) and world_size > 1
+        self.bn_sync_in_graph = self.bn_sync and peer is not None
         if self.bn_sync:
-            if grad_allreduce is None:
-                raise ValueError("bn_sync needs the all-reduce callable (grad_allreduce)")
-            self.store.bn_sync = (grad_allreduce, world_size)
+            if peer is not None:
+                self.store.bn_sync = peer
+            elif grad_allreduce is None:
+                raise ValueError("bn_sync needs a peer.PeerComm or the all-reduce callable (grad_allreduce)")
+            else:
+                self.store.bn_sync = (grad_allreduce, world_size)
         self.batch = batch_size
         self.gen_batch = self.gen_bs_multiple * batch_size
         self.world_size = world_size
@@ -285,7 +291,7 @@ class Trainer:
     # tensor-core kernels of one pass run while the other pass is in its bandwidth-bound normalisation kernels
     # (the same idea as the filter-gradient side stream of framework.Tape, one level up).  Results are identical to
     # d_step(); g_step(): only the launch order of independent work changes.
-    def _pair_fork(self):
+    def _pair_fork(self, join: bool = False):
         """[aux stream] G forward of the generator step  ||  [main stream] critic forward + backward."""
         st = self.store
         with st.gradient_tape() as tape:
@@ -301,8 +307,11 @@ class Trainer:
         with torch.cuda.stream(aux):
             st.zero_grad('Generator')
             fake = self._g_forward(tape)
-        self._pair_state = (tape, fake, aux)
         self._d_compute()
+        if join:          # this half is a CUDA graph of its own (a collective follows): its streams meet at its end
+            main.wait_stream(aux)
+            aux = None
+        self._pair_state = (tape, fake, aux)
 
     def _pair_join(self):
         """Critic update, then the rest of the generator step behind the join with the aux stream."""
@@ -314,7 +323,7 @@ class Trainer:
         self._g_rest(tape, fake)
 
     def _pair_body(self):
-        self._pair_fork()
+        self._pair_fork(join=self.grad_allreduce is not None)
         if self.grad_allreduce is not None:
             self.grad_allreduce(self.store.flat['Discriminator'].grads)
         self._pair_join()
@@ -353,8 +362,8 @@ class Trainer:
         With a gradient collective the compute and update halves are captured separately and the all-reduce
         runs between them on the same stream."""
         self.graph_launches = {}
-        if self.bn_sync:
-            return   # collectives inside the passes: eager mode
+        if self.bn_sync and not self.bn_sync_in_graph:
+            return   # library collectives inside the passes: eager mode
         if self.grad_allreduce is None:
             # single GPU: nothing sits between the backward pass and the update, so each step is ONE graph (every graph
             # boundary costs ~20-30 us of idle GPU at this step size)
@@ -378,7 +387,7 @@ class Trainer:
             # fork / join share one memory pool, because G's saved activations live across the all-reduce between them
             pool = torch.cuda.graph_pool_handle()
             pparts = (("pair_full", self._pair_body),) if self.grad_allreduce is None else (
-                ("pair_fork", self._pair_fork), ("pair_join", self._pair_join))
+                ("pair_fork", lambda: self._pair_fork(join=True)), ("pair_join", self._pair_join))
             self.pair_launches = 0
             for name, body in pparts:
                 self._invalidate_caches(packs=False)

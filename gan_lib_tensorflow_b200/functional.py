@@ -647,6 +647,7 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
     store = get_store()
     n, h, w, c = x.shape
     mean = rstd = None
+    sync_key = None
     g = 1
     if stats == "batch":
         g = groups if groups is not None else store.stat_groups
@@ -665,7 +666,10 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
         else:
             mean, rstd = K.bn_stats(x.data, n, h * w, c, g, eps)
         if sync is not None:
-            K.bn_stats_sync(mean, rstd, eps, sync)
+            # one exchange site per (layer, batch size): the generator forward of the critic step and of the generator
+            # step may be in flight at the same time on two streams (Trainer.pair_step)
+            sync_key = f"{store.scope_name()}/n{n}x{h}x{w}x{c}"
+            K.bn_stats_sync(mean, rstd, eps, sync, sync_key)
     gam = gamma.data if gamma is not None else None
     bet = beta.data if beta is not None else None
     # the raw bf16 copy (1x1-shortcut operand) is x itself when x is already stored in bf16
@@ -701,7 +705,7 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
                     and not quad):
                 extra, x.grad = x.grad, None
             dx = K.norm_act_bwd(x.data, gz, 0, n, h, w, c, mean, rstd, g, gam, bet, labels, act, ups, dgam, dbet,
-                                extra, x.gdtype, sync=sync)
+                                extra, x.gdtype, sync=sync, sync_key=sync_key)
             if x.requires_grad:
                 x.accum(dx)
         _tape().record(bwd)

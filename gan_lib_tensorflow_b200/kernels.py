@@ -251,10 +251,16 @@ def norm_act_fwd(x, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, up
     return out
 
 
+def _is_peer(sync) -> bool:
+    """sync is a peer.PeerComm-like object (key-addressed exchanges) rather than the (allreduce_sum, world) pair."""
+    return sync is not None and hasattr(sync, "bn_moments")
+
+
 def norm_act_bwd(x, dz, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta, labels, act, upsample, dgamma, dbeta,
-                 add, dx_dtype, sync=None):
-    """sync = (allreduce_sum(tensor) -> None, world): cross-GPU batch statistics -- the per-group sums of the local
-    share are all-reduced between the reduction and the apply kernels."""
+                 add, dx_dtype, sync=None, sync_key=None):
+    """sync: cross-GPU batch statistics -- the per-group sums of the local share are all-reduced between the reduction
+    and the apply kernels.  Either (allreduce_sum(tensor) -> None, world) (library collective, eager mode) or a
+    peer.PeerComm (one peer-memory kernel, capturable; sync_key names the call site)."""
     dx = torch.empty((n, h, w, c), dtype=dx_dtype, device=x.device)
     ws = None
     if mean is not None:
@@ -266,17 +272,24 @@ def norm_act_bwd(x, dz, dz_cstride, n, h, w, c, mean, rstd, groups, gamma, beta,
     if sync is None or mean is None:
         check(L().ganb_norm_act_bwd(*args, _stream()), "ganb_norm_act_bwd")
         return dx
-    allreduce, world = sync
     check(L().ganb_norm_act_bwd_phase(*args, 1, c_float(1.0), _stream()), "ganb_norm_act_bwd_phase")
     off = int(L().ganb_norm_act_bwd_sums_offset(n, h * w, c, groups))
     sums = ws[off:off + 2 * groups * c * 4].view(torch.float32)
-    allreduce(sums)
+    if _is_peer(sync):
+        sync.allreduce(sync_key + "/bwd", sums)
+        world = sync.world
+    else:
+        allreduce, world = sync
+        allreduce(sums)
     check(L().ganb_norm_act_bwd_phase(*args, 2, c_float(1.0 / world), _stream()), "ganb_norm_act_bwd_phase")
     return dx
 
 
-def bn_stats_sync(mean, rstd, eps, sync):
+def bn_stats_sync(mean, rstd, eps, sync, sync_key=None):
     """Replaces the local (mean, rstd) [groups, c] by the statistics over all ranks (equal shares per rank)."""
+    if _is_peer(sync):
+        sync.bn_moments(sync_key + "/fwd", mean, rstd, eps)     # pack + exchange + unpack in one peer-memory kernel
+        return
     allreduce, world = sync
     count = mean.numel()
     buf = torch.empty(2 * count, dtype=torch.float32, device=mean.device)

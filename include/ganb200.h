@@ -433,6 +433,25 @@ int ganb_depthwise_conv2d_bwd_filter(const void* x, int x_dtype, const void* dy,
                                      int h, int w, int c, int cm, int ho, int wo, int kh, int kw, int stride, int pad_t,
                                      int pad_l, void* stream);
 
+/* Small all-reduces over NVLink / NVSwitch peer memory (csrc/peer.cu) for the statistic exchanges of the data-parallel
+ * path: cross-GPU BatchNorm moments (reference coupling point common/ops/normalization.py:47) and the
+ * [sum dy | sum dy*xhat] pair of its backward pass.  peer_bufs: HOST array of `world` device pointers = this process'
+ * mappings of every rank's symmetric buffer (same size and layout on every rank, zero-initialised, all ranks past a
+ * barrier before the first call); site_offset: byte offset of the call site's region (ganb_peer_site_bytes(count) bytes,
+ * 128-byte aligned) -- one region per call site, the same offsets on every rank.  One single-CTA kernel per call: the
+ * contribution is written into our region, a system-scope release store raises our flag in every peer's region, the peers'
+ * flags are awaited (bounded spin), and the contributions are summed in rank order (bit-identical result on every
+ * rank).  The call epoch lives in device memory, so the kernels can be captured in CUDA graphs.
+ *   ganb_peer_allreduce : out[i] = scale * sum_ranks in[i], count <= ganb_peer_max_count() (out may alias in)
+ *   ganb_peer_bn_moments: (mean, rstd)[count] of the local share -> statistics over all ranks (equal shares), in place:
+ *                         pack [mean | E x^2], exchange, unpack -- one launch */
+int64_t ganb_peer_site_bytes(int count);
+int ganb_peer_max_count(void);
+int ganb_peer_allreduce(const float* in, float* out, int count, float scale, void* const* peer_bufs, int rank, int world,
+                        int64_t site_offset, void* stream);
+int ganb_peer_bn_moments(float* mean, float* rstd, int count, float eps, void* const* peer_bufs, int rank, int world,
+                         int64_t site_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
