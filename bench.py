@@ -265,6 +265,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             peer_note = f"NCCL all-reduce, eager (symmetric memory unavailable: {type(e).__name__}: {str(e)[:60]})"
     tr = P.Trainer(batch_size=64, seed=0, world_size=world, grad_allreduce=allreduce,
                    bn_sync=bool(getattr(args, "bn_sync", False)), peer=peer)
+    tr.capture_collectives = bool(getattr(args, "captured_nccl", False)) and world > 1
 
     # synthetic inputs of SURVEY 8(d): int32 [64, 3072] uniform 0..255 (CHW-flattened), labels uniform 0..9;
     # every rank draws its own shard.
@@ -339,9 +340,18 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     sampler.join(timeout=2)
     d_loss, g_loss = float(host_losses[0]), float(host_losses[1])
 
-    if rank != 0:
+    def shutdown():
+        # captured graphs hold references into the communicator's streams: release them first
+        tr._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return 0
 
     peaks = _peaks()
@@ -351,7 +361,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     value = world * args.steps / (ms_total * 1e-3)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
     share = kernel_time_shares(torch, pair) if world == 1 else None
-    step_tflops = PAIR_GFLOP / ms_step / 1e3
+    step_tflops = PAIR_GFLOP / ms_step          # GFLOP per ms = TFLOP/s
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -394,8 +404,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                 "tensorflow_probe": probe_tensorflow()}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
     return 0
 
 
@@ -408,6 +417,9 @@ def main():
     ap.add_argument("--no-pair-schedule", action="store_true",
                     help="replay the critic step and the generator step as separate graphs (round-1 schedule) instead "
                          "of Trainer.pair_step, which runs the generator step's G forward next to the critic step")
+    ap.add_argument("--captured-nccl", action="store_true",
+                    help="N > 1: capture the gradient all-reduces (NCCL) inside the D+G pair graph instead of issuing them "
+                         "between three graph replays")
     ap.add_argument("--bn-sync", action="store_true",
                     help="N > 1: also reduce G's batch-norm statistics over the ranks (eager mode; default: per-rank "
                          "statistics = the reference's per-tower semantics, CUDA graphs)")

@@ -41,6 +41,11 @@ ACGAN = False
 VOCAB_SIZE = 10
 EMBEDDING_DIM = 300
 N_TOWERS = 2  # len(DEVICES) is always 2 in the reference (:73-75)
+# Generator step: the frozen critic's pass over the fake batch as two half-batch chains on two streams (Trainer._g_rest,
+# framework.Tape.branch).  Correct (tests pass, gradients bit-identical) but measured SLOWER: 3.30 vs 3.15 ms per pair on
+# one box -- the half-batch kernels lose the CTA-pair route at 16x16 and the tensor-core kernels of the two chains
+# serialise anyway.  Opt-in (GANB_SPLIT_CRITIC=1) for further experiments.
+SPLIT_CRITIC_PASS = __import__("os").environ.get("GANB_SPLIT_CRITIC", "0") == "1"
 
 BF16 = torch.bfloat16
 
@@ -255,8 +260,26 @@ class Trainer:
         """Second half: D on the fake batch, gen_cost and the backward pass through D and G."""
         st = self.store
         with st.resume_tape(tape), st.frozen_scopes('Discriminator'):
-            disc_fake, _ = self.discriminator(fake, self.fake_labels, update_collection="NO_OPS", reuse=True)
-            loss = F.gan_loss(disc_fake, 'gen')
+            if SPLIT_CRITIC_PASS and self.gen_batch % 2 == 0 and not K.host_logic_only():
+                # The critic is frozen here and has no batch statistics: its pass over the fake batch is two independent
+                # half-batch chains.  They run on two streams (forward and backward), so the small, latency-bound
+                # kernels of D's 16x16 / 8x8 layers overlap instead of queueing behind each other; gen_cost =
+                # -mean(D(fake)) = the two half means averaged, gradients are bit-identical to the unsplit pass.
+                h = self.gen_batch // 2
+                halves = F.split_rows(fake, [h, h])     # recorded in front of the marker: its backward joins the branches
+                marker = tape.fork()
+                losses = []
+                for k, blk in enumerate(halves):
+                    stream = None if k == 0 else framework_aux_stream(st.device)
+                    with tape.branch(marker, stream):
+                        logits, _ = self.discriminator(blk, self.fake_labels[k * h:(k + 1) * h],
+                                                       update_collection="NO_OPS", reuse=True)
+                        losses.append(F.gan_loss(logits, 'gen', scale=0.5))
+                tape.join_forward(marker)
+                loss = F.add_scalars(losses[0], losses[1])
+            else:
+                disc_fake, _ = self.discriminator(fake, self.fake_labels, update_collection="NO_OPS", reuse=True)
+                loss = F.gan_loss(disc_fake, 'gen')
             tape.backward(loss)
         self.g_loss.copy_(loss.data)
 
@@ -323,7 +346,8 @@ class Trainer:
         self._g_rest(tape, fake)
 
     def _pair_body(self):
-        self._pair_fork(join=self.grad_allreduce is not None)
+        # a collective issued between the halves needs the streams joined, unless it is captured with them
+        self._pair_fork(join=self.grad_allreduce is not None and not getattr(self, "capture_collectives", False))
         if self.grad_allreduce is not None:
             self.grad_allreduce(self.store.flat['Discriminator'].grads)
         self._pair_join()
@@ -386,7 +410,8 @@ class Trainer:
             # the D+G pair schedule (pair_step): one graph on a single GPU; with a gradient collective the graphs
             # fork / join share one memory pool, because G's saved activations live across the all-reduce between them
             pool = torch.cuda.graph_pool_handle()
-            pparts = (("pair_full", self._pair_body),) if self.grad_allreduce is None else (
+            one_graph = self.grad_allreduce is None or getattr(self, "capture_collectives", False)
+            pparts = (("pair_full", self._pair_body),) if one_graph else (
                 ("pair_fork", lambda: self._pair_fork(join=True)), ("pair_join", self._pair_join))
             self.pair_launches = 0
             for name, body in pparts:
@@ -397,7 +422,7 @@ class Trainer:
                     body()
                 self._graphs[name] = g
                 self.pair_launches += K.launch_count() - before
-            if self.grad_allreduce is not None:
+            if not one_graph:
                 self.pair_launches += self.graph_launches["g_update"]
         self._invalidate_caches(packs=False)
 

@@ -195,9 +195,45 @@ class Tape:
         self._forked = False
         self.token = 0       # identity of this tape for the spectral-norm evaluation bookkeeping (VariableStore)
         self.sn_gen = {}     # root -> index of the spectral-norm state set in use on this tape
+        self.node_stream = {}   # node index -> stream of the branch it was recorded in
+        self.branches = []      # (fork marker, stream)
+        self._branch = None
 
     def record(self, fn) -> None:
         self.nodes.append(fn)
+        if self._branch is not None:
+            self.node_stream[len(self.nodes) - 1] = self._branch
+
+    # ---- branches: independent sub-graphs of ONE pass issued on their own streams (forward and backward)
+    def fork(self) -> int:
+        """Marks the point where branches start; returns the marker that branch() / join_forward() take."""
+        return len(self.nodes)
+
+    @contextlib.contextmanager
+    def branch(self, marker: int, stream: "torch.cuda.Stream | None"):
+        """Ops recorded inside run on `stream` (None: the current stream, i.e. a branch that stays on the main chain), in
+        the forward pass and -- their backward closures -- in the backward pass.  The branch must only consume values
+        produced before fork() and must not share gradient accumulators with other branches; Tape.backward makes the
+        stream wait for the upstream gradients and makes the nodes in front of the marker wait for the branch."""
+        if stream is None or K.host_logic_only():
+            yield
+            return
+        main = torch.cuda.current_stream()
+        stream.wait_stream(main)
+        self._branch = stream
+        self.branches.append((marker, stream))
+        try:
+            with torch.cuda.stream(stream):
+                yield
+        finally:
+            self._branch = None
+
+    def join_forward(self, marker: int) -> None:
+        """The current stream waits for the forward work of every branch forked at `marker`."""
+        main = torch.cuda.current_stream()
+        for m, s in self.branches:
+            if m == marker:
+                main.wait_stream(s)
 
     @contextlib.contextmanager
     def offchain(self):
@@ -222,8 +258,32 @@ class Tape:
     def backward(self, loss: Var, grad: torch.Tensor | None = None) -> None:
         if grad is not None:
             loss.accum(grad)
-        for fn in reversed(self.nodes):
-            fn()
+        if not self.node_stream:
+            for fn in reversed(self.nodes):
+                fn()
+        else:
+            main = torch.cuda.current_stream()
+            entered, pending = set(), []          # branch streams already running backward work / not yet joined
+            for i in range(len(self.nodes) - 1, -1, -1):
+                s = self.node_stream.get(i)
+                if pending:                       # nodes in front of a fork marker consume what its branches produced
+                    for m, bs in list(pending):
+                        if i < m:
+                            main.wait_stream(bs)
+                            pending.remove((m, bs))
+                if s is None:
+                    self.nodes[i]()
+                    continue
+                if s not in entered:              # the branch needs the gradients the main chain has produced so far
+                    s.wait_stream(main)
+                    entered.add(s)
+                    pending.extend((m, bs) for m, bs in self.branches if bs is s)
+                with torch.cuda.stream(s):
+                    self.nodes[i]()
+            for _m, bs in pending:
+                main.wait_stream(bs)
+            self.node_stream.clear()
+            self.branches.clear()
         self.join()
         self.nodes.clear()
         for root, entries in self.pending_sn.items():

@@ -89,6 +89,30 @@ def add(a: Var, b: Var) -> Var:
     return out
 
 
+def split_rows(x: Var, sizes) -> list:
+    """Row blocks of a 2-D (or n-D, first axis) value as separate Vars (views, no copy): x[0:s0], x[s0:s0+s1], ...
+    Each block may then go through its own branch of the tape (framework.Tape.branch); the gradient of x is the
+    concatenation of the blocks' gradients, formed when the backward pass reaches this node."""
+    assert sum(sizes) == x.shape[0]
+    outs, start = [], 0
+    for n in sizes:
+        outs.append(Var(x.data[start:start + n], grad_dtype=x.grad_dtype))
+        start += n
+    if _rg(x):
+        for o in outs:
+            o.requires_grad = True
+
+        def bwd():
+            gs = [o.grad for o in outs]
+            if any(g is None for g in gs):
+                if all(g is None for g in gs):
+                    return
+                raise RuntimeError("split_rows: some blocks received no gradient")
+            x.accum(torch.cat([g.reshape((g.shape[0],) + tuple(x.data.shape[1:])) for g in gs], dim=0))   # tensor plumbing
+        _tape().record(bwd)
+    return outs
+
+
 def concat_rows(a: Var, b: Var) -> Var:
     """tf.concat([a, b], axis=0) of two fp32 logit vectors / matrices (real | fake halves of a loss)."""
     assert a.data.dtype == F32 and b.data.dtype == F32 and a.shape[1:] == b.shape[1:]
