@@ -76,14 +76,14 @@ def Generator(n_samples_, labels, noise=None, reuse=False):
             noise = torch.randn(n_samples_, 128, device=store.device)
         noise = F.as_var(noise)
         # every input of a (conditional) batch norm is stored in bf16 (DESIGN.md "Data layout"): G's residual stream
-        output = linear_ops.Linear(noise, 128, 4 * 4 * DIM_G * 8, 'G.Input', out_dtype=BF16)
+        output = linear_ops.Linear(noise, 128, 4 * 4 * DIM_G * 8, 'G.Input', out_dtype=rb._adt())
         output = F.reshape(output, (-1, 4, 4, DIM_G * 8))
         output = _block(output, DIM_G * 8, DIM_G * 2, 3, 'G.Block.1', resample='up', labels=labels, biases=True,
-                        out_dtype=BF16, out_bn_stats=NORMALIZATION_G)
+                        out_dtype=rb._adt(), out_bn_stats=NORMALIZATION_G)
         output = _block(output, DIM_G * 2, DIM_G * 2, 3, 'G.Block.2', resample='up', labels=labels, biases=True,
-                        out_dtype=BF16, out_bn_stats=NORMALIZATION_G)
+                        out_dtype=rb._adt(), out_bn_stats=NORMALIZATION_G)
         output = _block(output, DIM_G * 2, DIM_G * 2, 3, 'G.Block.3', resample='up', labels=labels, biases=True,
-                        out_dtype=BF16, out_bn_stats=NORMALIZATION_G)
+                        out_dtype=rb._adt(), out_bn_stats=NORMALIZATION_G)
         output, _ = rb._norm_act('G.OutputNorm', output, labels, _normalize_kind('G.OutputNorm', labels), 'relu')
         output = conv2d_ops.Conv2D(output, DIM_G * 2, 3, 3, 1, 'G.Output', he_init=False)
         output = F.activation(output, 'tanh')

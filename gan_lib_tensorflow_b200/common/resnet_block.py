@@ -28,6 +28,12 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+def _adt():
+    """Storage dtype of the activations between the layers of the network being built: bf16 (tensor-core operands of the
+    default mode) or fp32 when the network runs in TF32 operand mode (VariableStore.set_precision)."""
+    return F32 if get_store().is_tf32() else BF16
+
+
 def nonlinearity(x, activation_fn='relu', leakiness=0.2):
     """common/resnet_block.py:24-29 (the reference silently returns None for unknown names; this raises)."""
     if activation_fn == 'relu':
@@ -49,11 +55,13 @@ def _normalize_kind(name, labels, spectral_normed):
     return None
 
 
-def _norm_act(name, inputs, labels, kind, act, upsample=False, want_raw=False, out_dtype=BF16, n_labels=10):
+def _norm_act(name, inputs, labels, kind, act, upsample=False, want_raw=False, out_dtype=None, n_labels=10):
     """Normalize(name, inputs) followed by nonlinearity(), fused. Returns (out, raw_bf16_or_None).
     n_labels: 10 is hard-wired in the library's Normalize (resnet_block.py:43) and the CIFAR script; the ImageNet
     script's copy uses 1000 (gan_imagNet_resnet.py:104)."""
     store = get_store()
+    if out_dtype is None:
+        out_dtype = _adt()
     with store.variable_scope(name):
         if kind == 'cbn':
             res = _norm.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=n_labels, act=act,
@@ -94,7 +102,7 @@ def ConvMeanPool(inputs, output_dim, filter_size=3, stride=1, name=None,
     inputs = F.as_var(inputs)
     output = _conv2d.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name,
                             spectral_normed=spectral_normed, update_collection=update_collection,
-                            inputs_norm=inputs_norm, he_init=he_init, biases=biases, out_grad_dtype=BF16)
+                            inputs_norm=inputs_norm, he_init=he_init, biases=biases, out_grad_dtype=_adt())
     return F.meanpool2(output)
 
 
@@ -106,7 +114,7 @@ def MeanPoolConv(inputs, output_dim, filter_size=3, stride=1, name=None,
     output = F.meanpool2(inputs if inputs.dtype == F32 else F.cast(inputs, F32))
     return _conv2d.Conv2D(output, output.shape[-1], output_dim, filter_size, stride, name,
                           spectral_normed=spectral_normed, update_collection=update_collection,
-                          inputs_norm=inputs_norm, he_init=he_init, biases=biases, out_grad_dtype=BF16)
+                          inputs_norm=inputs_norm, he_init=he_init, biases=biases, out_grad_dtype=_adt())
 
 
 def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None,
@@ -147,7 +155,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # 'up' blocks: Conv1 = UpsampleConv runs in sub-pixel form (four 2x2 convolutions over the LOW-resolution
     # activation, 4/9 of the MMA work, no upsampled operand) wherever the CTA-pair kernel tiles the shape
     subpixel = False
-    if resample == 'up' and pre_activated is None and not spectral_normed and not inputs_norm:
+    if resample == 'up' and pre_activated is None and not spectral_normed and not inputs_norm and _adt() == BF16:
         n_, h_, w_, _c = F.as_var(inputs).shape
         subpixel = F.upconv_eligible(n_, h_, w_, input_dim, output_dim, filter_size)
 
@@ -158,7 +166,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     else:
         x32 = F.as_var(inputs)
         n1_in = x32
-        if kind(name + '.N1') in ('cbn', 'bn') and x32.data.dtype == F32:
+        if kind(name + '.N1') in ('cbn', 'bn') and x32.data.dtype == F32 and _adt() == BF16:
             # every input of a batch-statistics normalisation is stored in bf16 (DESIGN.md "Data layout"): an fp32
             # residual stream (ACGAN's batch-normed D) is rounded once here; statistics, normalise and the shortcut
             # operand then read 2-byte elements, the identity shortcut keeps the fp32 tensor
@@ -179,7 +187,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
         # ConvMeanPool / UpsampleConv / Conv2D with a 1x1 filter, he_init=False (resnet_block.py:123-127)
         shortcut = _conv2d.Conv2D(raw, input_dim, output_dim, 1, 1, name + '.Shortcut',
                                   spectral_normed=spectral_normed, update_collection=update_collection,
-                                  inputs_norm=inputs_norm, he_init=False, biases=biases, out_grad_dtype=BF16)
+                                  inputs_norm=inputs_norm, he_init=False, biases=biases, out_grad_dtype=_adt())
         # 'up': conv1x1(upsample(x)) == upsample(conv1x1(x)); the upsample itself happens inside Conv2's epilogue
 
     # ---- Conv1
@@ -187,7 +195,7 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # h1 is only consumed by N2 + nonlinearity, whose backward can emit the bf16 tensor-core operand directly
     # and which is stored in bf16: it is only read by that kernel (rounding commutes with relu / leaky relu, so
     # without a normalisation in between this is bit-identical to rounding after the activation)
-    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=BF16, out_dtype=BF16,
+    h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=_adt(), out_dtype=_adt(),
               subpixel_up2=subpixel, bn_stats=kind(name + '.N2') in ('cbn', 'bn'))
 
     # ---- N2 + nonlinearity
@@ -196,13 +204,13 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # ---- Conv2 (+ residual in the epilogue) [+ mean-pool of the sum]
     if resample == 'down':
         t = conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut,
-                 out_grad_dtype=BF16)
+                 out_grad_dtype=_adt())
         # meanpool(conv2) + meanpool(shortcut) == meanpool(conv2 + shortcut)
-        return F.meanpool2(t, out_grad_dtype=BF16)
+        return F.meanpool2(t, out_grad_dtype=_adt())
     # the block output feeds the next block's normalise/activation kernel and (through 1x1 / identity shortcuts)
     # convolutions only: its gradient is a tensor-core operand, so it is produced in bf16 directly
     return conv(a2, mid_dim, output_dim, name=name + '.Conv2', he_init=True, residual=shortcut,
-                residual_up2=(resample == 'up' and not identity_shortcut), out_grad_dtype=BF16,
+                residual_up2=(resample == 'up' and not identity_shortcut), out_grad_dtype=_adt(),
                 bn_stats=bool(out_bn_stats) and out_dtype == BF16,
                 **({'out_dtype': out_dtype} if out_dtype is not None else {}))
 
@@ -219,12 +227,12 @@ def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
                             inputs_norm=inputs_norm, he_init=False, biases=biases)
     output = _conv2d.Conv2D(inputs, cin, DIM_D, 3, 1, name_prefix + '.Conv1', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
-                            biases=biases, out_grad_dtype=BF16, out_dtype=BF16)
-    output, _ = F.norm_act(output, stats=None, act=activation_fn, out_dtype=BF16)
+                            biases=biases, out_grad_dtype=_adt(), out_dtype=_adt())
+    output, _ = F.norm_act(output, stats=None, act=activation_fn, out_dtype=_adt())
     output = _conv2d.Conv2D(output, DIM_D, DIM_D, 3, 1, name_prefix + '.Conv2', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
-                            biases=biases, out_grad_dtype=BF16)
-    return F.meanpool2(output, addend=shortcut, out_grad_dtype=BF16)
+                            biases=biases, out_grad_dtype=_adt())
+    return F.meanpool2(output, addend=shortcut, out_grad_dtype=_adt())
 
 
 # ######## ######## PGGAN ######## ######## #

@@ -328,7 +328,10 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
   }
 }
 
-template <int BN, int STAGES, bool STATS>
+// TF32 = true: fp32 operands read by kind::tf32 MMAs (north star: "BF16 or TF32 inputs").  A 128-byte swizzle row then
+// holds 32 channels instead of 64; a stage is still 128 rows x 128 bytes and four K-steps of 32 bytes, so only the
+// channel coordinates of the TMA boxes, the instruction descriptor and the MMA kind differ.
+template <int BN, int STAGES, bool STATS, bool TF32 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const IgemmParams p) {
@@ -336,7 +339,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int ACC_STAGES = 2;
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN) < 32 ? 32 : (ACC_STAGES * BN);
   constexpr int NC = BN < 32 ? BN : 32;  // columns per tcgen05.ld
-  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+  constexpr uint32_t IDESC = TF32 ? umma_idesc_tf32(BM, BN, 0, 0) : umma_idesc_bf16(BM, BN, 0, 0);
+  constexpr int BKE = TF32 ? 32 : BK;    // channels per 128-byte row
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -400,8 +404,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&empty[stage], phase ^ 1);
             if (elect_one()) {
               mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-              tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * BK, w0 + s2, h0 + r, n0);
-              tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kc * BK, co0, tap_b);
+              tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kc * BKE, w0 + s2, h0 + r, n0);
+              tma_load_3d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kc * BKE, co0, tap_b);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -430,10 +434,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one()) {
           const uint64_t adesc = umma_desc_at(desc_base, sA_addr + stage * A_STAGE_BYTES);
           const uint64_t bdesc = umma_desc_at(desc_base, sB_addr + stage * B_STAGE_BYTES);
-          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_d, adesc, bdesc, IDESC, acc);
+          // advance 16 bf16 (8 tf32) = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+          if constexpr (TF32) {
+            umma_tf32(tmem_d, adesc, bdesc, IDESC, acc);
 #pragma unroll
-          for (int k = 1; k < BK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+            for (int k = 1; k < 4; ++k) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+          } else {
+            umma_bf16(tmem_d, adesc, bdesc, IDESC, acc);
+#pragma unroll
+            for (int k = 1; k < BK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, 1u);
+          }
           umma_commit(&empty[stage]);
         }
         __syncwarp();
@@ -966,6 +976,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // operands are MN-major.  One CTA = (tap, ci tile of 128, co tile of BN, pixel split).
 // ------------------------------------------------------------------------------------------------
 constexpr int PB = 64;  // pixels per pipeline stage (4 UMMA K-steps of 16)
+#ifndef GANB_TF32_SBO
+#define GANB_TF32_SBO 512
+#endif
 
 struct WgradParams {
   int N, Ho, Wo;  // dy spatial extent
@@ -981,15 +994,19 @@ struct WgradParams {
   int quad;
 };
 
-template <int BN, int STAGES>
+// TF32 = true: fp32 operands (32 channels per 128-byte row: BM / 32 boxes per operand tile), K-steps of 8 pixels.
+template <int BN, int STAGES, bool TF32 = false>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const WgradParams p) {
-  constexpr int A_BYTES = PB * BM * 2;  // two 64-channel boxes of PB pixel rows
-  constexpr int B_BYTES = PB * BN * 2;
-  constexpr int BOX_BYTES = PB * 128;   // one 64-channel box
+  constexpr int ESZ = TF32 ? 4 : 2;
+  constexpr int BOXC = 128 / ESZ;       // channels of one 128-byte-wide box
+  constexpr int A_BYTES = PB * BM * ESZ;  // BM / BOXC boxes of PB pixel rows
+  constexpr int B_BYTES = PB * BN * ESZ;
+  constexpr int BOX_BYTES = PB * 128;   // one box
+  constexpr int KSTEP = TF32 ? 8 : 16;  // pixels per MMA
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 1, 1);
+  constexpr uint32_t IDESC = TF32 ? umma_idesc_tf32(BM, BN, 1, 1) : umma_idesc_bf16(BM, BN, 1, 1);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -1051,12 +1068,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint8_t* a = sA + stage * A_BYTES;
         uint8_t* b = sB + stage * B_BYTES;
 #pragma unroll
-        for (int j = 0; j < BM / 64; ++j)
-          tma_load_4d(a + j * BOX_BYTES, &tmX, &full[stage], ci0 + 64 * j, w0 * p.stride + s - pad_l,
+        for (int j = 0; j < BM / BOXC; ++j)
+          tma_load_4d(a + j * BOX_BYTES, &tmX, &full[stage], ci0 + BOXC * j, w0 * p.stride + s - pad_l,
                       h0 * p.stride + r - pad_t, n0);
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(b + j * BOX_BYTES, &tmDY, &full[stage], dy_c0 + 64 * j, w0, h0, n0);
+        for (int j = 0; j < BN / BOXC; ++j)
+          tma_load_4d(b + j * BOX_BYTES, &tmDY, &full[stage], dy_c0 + BOXC * j, w0, h0, n0);
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1069,7 +1086,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint32_t acc = 0;
     // MN-major, 128B swizzle: 64 channels per row, 8-pixel groups 1024 B apart (SBO),
     // next 64-channel box BOX_BYTES away (LBO).
-    const uint64_t desc_base = umma_desc_base_sw128(BOX_BYTES, 1024);
+    // TF32: MN-major fp32 operands exist only in the "128-byte swizzle on a 32-byte base" layout (4-row pattern: SBO = 512)
+    const uint64_t desc_base = TF32 ? umma_desc_base_sw128_base32(BOX_BYTES, GANB_TF32_SBO) : umma_desc_base_sw128(BOX_BYTES, 1024);
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     for (int pb = pb_begin; pb < pb_end; ++pb) {
       mbar_wait(&full[stage], phase);
@@ -1077,10 +1095,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (elect_one()) {
         const uint64_t adesc = umma_desc_at(desc_base, sA_addr + stage * A_BYTES);
         const uint64_t bdesc = umma_desc_at(desc_base, sB_addr + stage * B_BYTES);
-        // 16 pixels = 16 rows of 128 B = 2048 B -> +128 in 16-byte units
-        umma_bf16(tmem_base, adesc, bdesc, IDESC, acc);
+        // 16 (tf32: 8) pixels = rows of 128 B: +128 (+64) in 16-byte units per K-step
+        if constexpr (TF32) {
+          umma_tf32(tmem_base, adesc, bdesc, IDESC, acc);
 #pragma unroll
-        for (int k = 1; k < PB / 16; ++k) umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, 1u);
+          for (int k = 1; k < PB / KSTEP; ++k) umma_tf32(tmem_base, adesc + 64 * k, bdesc + 64 * k, IDESC, 1u);
+        } else {
+          umma_bf16(tmem_base, adesc, bdesc, IDESC, acc);
+#pragma unroll
+          for (int k = 1; k < PB / KSTEP; ++k) umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, IDESC, 1u);
+        }
         umma_commit(&empty[stage]);
       }
       __syncwarp();
@@ -1176,8 +1200,13 @@ static int stats_smem(const IgemmParams& p) {
   return (p.stats && BN >= 64) ? static_cast<int>(sizeof(EpiStats<BN>)) + 16 : 0;
 }
 
+// `ctas_per_sm`: shallow-K launches (<= 4 k-iterations per tile: K = 32 im2col routes, 1x1 shortcuts) are bound by the
+// epilogue -- one warp per scheduler, ~10 cycles per issued instruction (profiles/r02_ncu_igemm_k32.txt) -- not by the
+// tensor pipe.  A 2-stage instance needs 64 KB of shared memory and 2 x BN <= 256 TMEM columns, so TWO CTAs fit on an
+// SM and their epilogues run side by side.
 template <int BN, int STAGES>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, cudaStream_t stream) {
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, cudaStream_t stream,
+                        int ctas_per_sm = 1) {
   const int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + stats_smem<BN>(p);
   auto kern = conv_igemm_kernel<BN, STAGES, false>;
   bool with_stats = false;
@@ -1192,7 +1221,8 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPar
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
-  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const int slots = sm_count() * ctas_per_sm;
+  int grid = p.num_tiles < slots ? p.num_tiles : slots;
   launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
   GANB_CHECK_LAUNCH("conv_igemm_kernel");
   return 0;
@@ -1389,6 +1419,12 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
                     ((m_tiles + 1) / 2) * ceil_div(cout, pair_bn) >= sm_count() / 2;
   if (pair) bn_tile = pair_bn;
 
+  // shallow-K launches (see launch_igemm): two CTAs per SM; BN = 256 would take all 512 TMEM columns, so the channels
+  // are split over 128-wide tiles.  GANB_SHALLOW=0 disables the route (A/B).
+  static const bool shallow_ok = !(getenv("GANB_SHALLOW") && getenv("GANB_SHALLOW")[0] == '0');
+  const bool shallow = shallow_ok && !halo && !stats && p.taps * p.kchunks <= 4 && bn_tile >= 64;
+  if (shallow && bn_tile == 256) bn_tile = 128;
+
   CUtensorMap tmA, tmB;
   const int halo_w = p.bw + kw - 1, halo_h = p.bh + kh - 1;
   {
@@ -1427,6 +1463,10 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
       default: return launch_halo<256, 2, ST_HALO256_SB>(tmA, tmB, p, a_stage, halo_w, halo_bytes, stream);
     }
   }
+  if (shallow) {
+    if (bn_tile == 64) return launch_igemm<64, 2>(tmA, tmB, p, stream, 2);
+    return launch_igemm<128, 2>(tmA, tmB, p, stream, 2);
+  }
   switch (bn_tile) {
     case 16: return launch_igemm<16, 8>(tmA, tmB, p, stream);
     case 32: return launch_igemm<32, 8>(tmA, tmB, p, stream);
@@ -1444,7 +1484,7 @@ struct WgradPlan {
   int grid;
 };
 
-static void plan_wgrad(int n, int ho, int wo, int cin, int cout, int kh, int kw, WgradPlan* plan) {
+static void plan_wgrad(int n, int ho, int wo, int cin, int cout, int kh, int kw, WgradPlan* plan, int max_bn = 256) {
   WgradParams& p = plan->p;
   p.N = n; p.Ho = ho; p.Wo = wo; p.Cin = cin; p.Cout = cout;
   p.kw = kw; p.taps = kh * kw;
@@ -1454,6 +1494,7 @@ static void plan_wgrad(int n, int ho, int wo, int cin, int cout, int kh, int kw,
   p.pb_n = ceil_div(n, p.bn);
   p.num_pb = p.pb_w * p.pb_h * p.pb_n;
   plan->bn_tile = cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
+  if (plan->bn_tile > max_bn) plan->bn_tile = max_bn;
   p.ci_tiles = ceil_div(cin, BM);
   p.co_tiles = ceil_div(cout, plan->bn_tile);
   const int units = p.taps * p.ci_tiles * p.co_tiles;
@@ -1764,5 +1805,152 @@ extern "C" int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, f
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   launch_k(upconv_fold_reduce_kernel, blocks, 256, 0, stream, p.partial, dw_hwio, plane4, p.splits, scale, beta);
   GANB_CHECK_LAUNCH("upconv_fold_reduce_kernel");
+  return 0;
+}
+
+
+// ================================================================================================
+// TF32 operand mode (north star: "BF16 or TF32 inputs and FP32 accumulation"): the same implicit-GEMM kernels with fp32
+// operands read by kind::tf32 MMAs -- per-layer results within 1e-3 of fp32 (tests/test_gpu_tf32.py).  Every shape takes
+// the per-tap TMA-box route (conv_igemm_kernel<..., TF32 = true>) and the pixel-split filter-gradient kernel
+// (conv_wgrad_kernel<..., TF32 = true>); operands should be rounded to TF32 beforehand (ganb_round_tf32 /
+// ganb_transpose_tf32: round-to-nearest) because the MMA itself truncates the 13 low mantissa bits.
+// ================================================================================================
+namespace ganb {
+
+template <int BN, int STAGES>
+static int launch_igemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, cudaStream_t stream) {
+  const int smem = STAGES * (A_STAGE_BYTES + BN * 128) + 1024 + 256;
+  auto kern = conv_igemm_kernel<BN, STAGES, false, true>;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "igemm tf32 smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  p.tiles_co = ceil_div(p.Cout, BN);
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
+  GANB_CHECK_LAUNCH("conv_igemm_kernel<tf32>");
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad_tf32(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, int grid,
+                             cudaStream_t stream) {
+  constexpr int smem = STAGES * (PB * BM * 4 + PB * BN * 4) + 1024 + 256;
+  auto kern = conv_wgrad_kernel<BN, STAGES, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "wgrad tf32 smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  launch_k(kern, grid, WG_THREADS, smem, stream, tmX, tmDY, p);
+  GANB_CHECK_LAUNCH("conv_wgrad_kernel<tf32>");
+  return 0;
+}
+
+}  // namespace ganb
+
+extern "C" int ganb_conv2d_igemm_tf32(const float* x, const float* wp, void* y, int n, int h, int w, int cin, int ho,
+                                      int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
+                                      const float* alpha, const float* bias, const float* residual, int residual_up2,
+                                      int act, int out_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !wp || !y) return fail(GANB_E_BADARG, "conv2d_igemm_tf32: null buffer");
+  if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || ho <= 0 || wo <= 0 || cout <= 0 || kh <= 0 || kw <= 0)
+    return fail(GANB_E_BADARG, "conv2d_igemm_tf32: non-positive dimension");
+  if (cin % 4 != 0) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm_tf32: cin=%d must be a multiple of 4", cin);
+  if (stride < 1 || stride > 4) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm_tf32: stride=%d (1..4 supported)", stride);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp)) & 15)
+    return fail(GANB_E_BADARG, "conv2d_igemm_tf32: x / wp must be 16-byte aligned");
+  IgemmParams p;
+  p.N = n; p.Ho = ho; p.Wo = wo; p.Cout = cout;
+  p.taps = kh * kw; p.kw = kw;
+  p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+  pick_box(BM, ho, wo, &p.bw, &p.bh, &p.bn);
+  p.stats = nullptr;
+  p.tiles_w = ceil_div(wo, p.bw);
+  p.tiles_h = ceil_div(ho, p.bh);
+  p.tiles_n = ceil_div(n, p.bn);
+  p.kchunks = ceil_div(cin, 32);
+  p.flip = flip_taps;
+  p.alpha = alpha; p.bias = bias; p.residual = residual;
+  p.res_up2 = (residual && residual_up2) ? 1 : 0;
+  if (p.res_up2 && ((ho | wo) & 1)) return fail(GANB_E_BADARG, "conv2d_igemm_tf32: upsampled residual needs even ho, wo");
+  p.out = y; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
+  p.og = 1; p.rg = 1; p.out_cstride = cout;
+  for (int i = 0; i < 4; ++i) { p.gpad_t[i] = 0; p.gpad_l[i] = 0; }
+  const int bn_tile = cout <= 16 ? 16 : cout <= 64 ? 64 : 128;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cin * 4, (uint64_t)w * cin * 4, (uint64_t)h * w * cin * 4};
+    const uint32_t box[4] = {32, (uint32_t)((p.bw - 1) * stride + 1), (uint32_t)((p.bh - 1) * stride + 1), (uint32_t)p.bn};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (box[1] > 256 || box[2] > 256) return fail(GANB_E_UNSUPPORTED, "conv2d_igemm_tf32: tile extent exceeds the TMA box limit");
+    int rc = encode_tmap_f32(&tmA, x, 4, dims, strides, box, stride > 1 ? estr : nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)(kh * kw)};
+    const uint64_t strides[2] = {(uint64_t)cin * 4, (uint64_t)cin * cout * 4};
+    const uint32_t box[3] = {32, (uint32_t)bn_tile, 1};
+    int rc = encode_tmap_f32(&tmB, wp, 3, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  switch (bn_tile) {
+    case 16: return launch_igemm_tf32<16, 8>(tmA, tmB, p, stream);
+    case 64: return launch_igemm_tf32<64, 8>(tmA, tmB, p, stream);
+    default: return launch_igemm_tf32<128, 6>(tmA, tmB, p, stream);
+  }
+}
+
+extern "C" int64_t ganb_conv2d_wgrad_tf32_workspace(int n, int ho, int wo, int cin, int cout, int kh, int kw) {
+  WgradPlan plan;
+  plan_wgrad(n, ho, wo, cin, cout, kh, kw, &plan, 128);
+  return static_cast<int64_t>(plan.p.splits) * kh * kw * cin * cout * 4;
+}
+
+extern "C" int ganb_conv2d_wgrad_tf32(const float* x, const float* dy, float* dw, void* workspace, int n, int h, int w,
+                                      int cin, int ho, int wo, int cout, int kh, int kw, int stride, int pad_t,
+                                      int pad_l, const float* scale, float beta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !dy || !dw || !workspace) return fail(GANB_E_BADARG, "conv2d_wgrad_tf32: null buffer");
+  if (cin % 4 != 0 || cout % 4 != 0)
+    return fail(GANB_E_UNSUPPORTED, "conv2d_wgrad_tf32: cin=%d and cout=%d must be multiples of 4", cin, cout);
+  if (stride < 1 || stride > 4) return fail(GANB_E_UNSUPPORTED, "conv2d_wgrad_tf32: stride=%d (1..4 supported)", stride);
+  WgradPlan plan;
+  plan_wgrad(n, ho, wo, cin, cout, kh, kw, &plan, 128);
+  WgradParams& p = plan.p;
+  p.pad_t = pad_t; p.pad_l = pad_l; p.stride = stride; p.quad = 0;
+  p.partial = static_cast<float*>(workspace);
+  CUtensorMap tmX, tmDY;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cin * 4, (uint64_t)w * cin * 4, (uint64_t)h * w * cin * 4};
+    const uint32_t box[4] = {32, (uint32_t)((p.bw - 1) * stride + 1), (uint32_t)((p.bh - 1) * stride + 1), (uint32_t)p.bn};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = encode_tmap_f32_base32(&tmX, x, 4, dims, strides, box, stride > 1 ? estr : nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)wo, (uint64_t)ho, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cout * 4, (uint64_t)wo * cout * 4, (uint64_t)ho * wo * cout * 4};
+    const uint32_t box[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int rc = encode_tmap_f32_base32(&tmDY, dy, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  int rc;
+  if (plan.bn_tile == 64) rc = launch_wgrad_tf32<64, 4>(tmX, tmDY, p, plan.grid, stream);
+  else rc = launch_wgrad_tf32<128, 3>(tmX, tmDY, p, plan.grid, stream);
+  if (rc) return rc;
+  const int64_t n4 = static_cast<int64_t>(kh) * kw * cin * cout / 4;
+  int blocks = static_cast<int>(ceil_div64(n4, 256));
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  launch_k(splitk_reduce_kernel, blocks, 256, 0, stream, p.partial, dw, n4, p.splits, scale, beta);
+  GANB_CHECK_LAUNCH("splitk_reduce_kernel");
   return 0;
 }

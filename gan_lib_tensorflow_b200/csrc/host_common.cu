@@ -60,8 +60,29 @@ static void load_encode() {
     g_encode = reinterpret_cast<encode_tiled_fn>(fn);
 }
 
+static int encode_tmap(CUtensorMapDataType dtype, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                       CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
+
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return encode_tmap(CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, base, rank, dims, strides_bytes, box, elem_strides);
+}
+
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return encode_tmap(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, base, rank, dims, strides_bytes, box, elem_strides);
+}
+
+int encode_tmap_f32_base32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return encode_tmap(CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, base, rank, dims, strides_bytes, box, elem_strides,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+static int encode_tmap(CUtensorMapDataType dtype, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                       CUtensorMapSwizzle swizzle) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return fail(GANB_E_ARCH, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -74,9 +95,9 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
     estr[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+  CUresult r = g_encode(out, dtype, static_cast<cuuint32_t>(rank),
                         const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(GANB_E_BADARG, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu %llu %llu %llu)",

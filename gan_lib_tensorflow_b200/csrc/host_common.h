@@ -19,6 +19,13 @@ int sm_count();
 // for dims 1..rank-1. Returns 0 or a negative GANB_E_* code.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+// The same over an fp32 tensor (operands of the kind::tf32 tensor-core kernels).
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+// fp32 with the 128-byte swizzle on a 32-byte base (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the only shared-memory layout
+// tcgen05 accepts for MN-major (channels-contiguous) TF32 operands -- the filter-gradient kernel.
+int encode_tmap_f32_base32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 
 // Counts every kernel launch issued by the library (exported as ganb_launch_count()).
 void count_launch();

@@ -117,6 +117,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: fp32 words in shared memory read as TF32 (10-bit mantissa; the low 13 bits are ignored), K = 8 per
+// instruction (32 bytes of a 128-byte swizzle row, like 16 bf16), fp32 accumulation.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all MMAs previously issued by this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -230,6 +241,13 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
 __device__ __forceinline__ uint64_t umma_desc_base_sw128(uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return umma_smem_desc_sw128(0, lbo_bytes, sbo_bytes);
 }
+// 128-byte swizzle on a 32-byte base (layout type 1): MN-major TF32 operands; the swizzle pattern repeats every 4 rows
+__device__ __forceinline__ uint64_t umma_desc_base_sw128_base32(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = umma_smem_desc_sw128(0, lbo_bytes, sbo_bytes);
+  d &= ~(static_cast<uint64_t>(7) << 61);
+  d |= static_cast<uint64_t>(1) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_at(uint64_t base, uint32_t smem_addr) {
   return base | static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
 }
@@ -239,6 +257,13 @@ __device__ __forceinline__ uint64_t umma_desc_at(uint64_t base, uint32_t smem_ad
 //   bit 15 A major (0 = K, 1 = MN)  bit 16 B major  [17,23) N >> 3  [24,29) M >> 4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::tf32 (A / B format 2 = TF32), FP32 accumulation; other fields as above.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

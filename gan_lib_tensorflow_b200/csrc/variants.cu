@@ -417,6 +417,39 @@ lerp_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
   }
 }
 
+// round-to-nearest (ties away) of fp32 values to TF32 (10-bit mantissa), kept in fp32 storage: operands of the kind::tf32
+// tensor-core kernels (the MMA itself would truncate)
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_wait();
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) y[i] = round_tf32(x[i]);
+}
+// [taps][ci][co] (HWIO) -> [taps][co][ci], rounded to TF32: the fprop operand copy of a filter
+__global__ void __launch_bounds__(256) transpose_tf32_kernel(const float* __restrict__ w, float* __restrict__ wt, int ci_n,
+                                                             int co_n) {
+  pdl_wait();
+  __shared__ float tile[32][33];
+  const int tiles_co = (co_n + 31) / 32;
+  const int tco = blockIdx.x % tiles_co, tci = blockIdx.x / tiles_co;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t plane = static_cast<int64_t>(ci_n) * co_n;
+  const float* src = w + blockIdx.y * plane;
+  float* dst = wt + blockIdx.y * plane;
+  for (int j = ty; j < 32; j += 8) {
+    const int ci = tci * 32 + j, co = tco * 32 + tx;
+    tile[j][tx] = (ci < ci_n && co < co_n) ? src[static_cast<int64_t>(ci) * co_n + co] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int co = tco * 32 + j, ci = tci * 32 + tx;
+    if (ci < ci_n && co < co_n) dst[static_cast<int64_t>(co) * ci_n + ci] = round_tf32(tile[tx][j]);
+  }
+}
+
 // y = alpha * x with alpha read from device memory: the spectrally-normalised depthwise filter W_d / sigma (the
 // depthwise kernels have no GEMM epilogue to carry 1/sigma; the filter is k*k*c*cm floats, i.e. tiny)
 __global__ void __launch_bounds__(256)
@@ -897,6 +930,20 @@ extern "C" int ganb_lerp_fwd(const float* a, const float* b, float* y, int64_t c
     return fail(GANB_E_BADARG, "lerp_fwd: buffers must be 16-byte aligned");
   launch_k(lerp_fwd_kernel, flat_grid(count / 4 + 1), 256, 0, STREAM, a, b, y, count, alpha);
   GANB_CHECK_LAUNCH("lerp_fwd_kernel");
+  return 0;
+}
+
+extern "C" int ganb_round_tf32(const float* x, float* y, int64_t count, void* stream) {
+  if (!x || !y) return fail(GANB_E_BADARG, "round_tf32: null buffer");
+  launch_k(round_tf32_kernel, flat_grid(count), 256, 0, STREAM, x, y, count);
+  GANB_CHECK_LAUNCH("round_tf32_kernel");
+  return 0;
+}
+
+extern "C" int ganb_transpose_tf32(const float* w_hwio, float* wt, int taps, int cin, int cout, void* stream) {
+  if (!w_hwio || !wt || taps <= 0 || cin <= 0 || cout <= 0) return fail(GANB_E_BADARG, "transpose_tf32: bad arguments");
+  launch_k(transpose_tf32_kernel, dim3(((cin + 31) / 32) * ((cout + 31) / 32), taps), 256, 0, STREAM, w_hwio, wt, cin, cout);
+  GANB_CHECK_LAUNCH("transpose_tf32_kernel");
   return 0;
 }
 

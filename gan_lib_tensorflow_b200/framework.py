@@ -560,6 +560,10 @@ class VariableStore:
         # cross-GPU batch statistics: (allreduce_sum(tensor) -> None, world size) or None = per-rank statistics, the
         # reference's per-tower semantics (common/ops/normalization.py:47)
         self.bn_sync = None
+        # operand precision of the tensor-core layers per network (root scope): 'bf16' (default) or 'tf32' -- fp32
+        # activations and filters read by kind::tf32 MMAs (north star: "BF16 or TF32 inputs"; <= 1e-3 per layer)
+        self.precision: dict[str, str] = {}
+        self._tf32_packs: dict[str, tuple] = {}
 
     # -- scopes ---------------------------------------------------------------------------------
     @contextlib.contextmanager
@@ -641,6 +645,32 @@ class VariableStore:
 
     def bump_u(self, root):
         self._u_versions[root] = self._u_versions.get(root, 0) + 1
+
+    # -- operand precision ----------------------------------------------------------------------
+    def set_precision(self, root: str, precision: str) -> None:
+        if precision not in ("bf16", "tf32"):
+            raise ValueError("precision must be 'bf16' or 'tf32'")
+        self.precision[root] = precision
+
+    def is_tf32(self, root: str | None = None) -> bool:
+        return self.precision.get(self.root() if root is None else root, "bf16") == "tf32"
+
+    def tf32_operands(self, w: "Variable"):
+        """(fprop copy [taps, cout, cin], dgrad copy = the HWIO filter [taps, cin, cout]) of `w`, rounded to TF32;
+        refreshed when the network's version moves."""
+        if isinstance(w, DerivedWeight):
+            w.refresh()
+        ver = self.version(w.root)
+        hit = self._tf32_packs.get(w.key)
+        if hit is not None and hit[0] == ver and hit[3] == w.data.data_ptr():
+            return hit[1], hit[2]
+        co, ci = w.data.shape[-1], w.data.shape[-2]
+        taps = w.data.numel() // (ci * co)
+        flat = w.data.reshape(taps, ci, co)
+        wt = K.transpose_tf32(flat, taps, ci, co)
+        wr = K.round_tf32(flat)
+        self._tf32_packs[w.key] = (ver, wt, wr, w.data.data_ptr())
+        return wt, wr
 
     # -- helpers --------------------------------------------------------------------------------
     def const(self, value: float) -> torch.Tensor:

@@ -228,6 +228,9 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     store = get_store()
     n, h, w, cin = x.shape
     cout = W.data.shape[-1]
+    if store.is_tf32(W.root):
+        return _conv2d_tf32(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale, residual_up2,
+                            out_dtype)
     if cin > 8 and cin % 8:
         return _conv2d_ragged_cin(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale,
                                   residual_up2, out_dtype)
@@ -360,6 +363,108 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                     dx = K.conv_igemm(gyd, pack.wn, n, hd, wd, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
                                       alpha, None, None, None, gdt)
                 xin.accum(dx)
+        tape.record(bwd)
+    return out
+
+
+def _conv2d_tf32(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale, residual_up2, out_dtype):
+    """conv2d of a network in TF32 operand mode (VariableStore.set_precision(root, 'tf32')): fp32 activations and filters,
+    rounded to TF32 (round-to-nearest) and contracted by the kind::tf32 tensor-core kernels with fp32 accumulation;
+    gradients the same way (fp32 storage).  Sides with fewer than 8 channels (RGB) take the fp32 CUDA-core kernels of
+    smallconv.cu, which are exact.  Per-layer error vs fp32: ~3e-4 (tests/test_gpu_tf32.py; tolerance 1e-3)."""
+    store = get_store()
+    n, h, w, cin = x.shape
+    cout = W.data.shape[-1]
+    taps = kh * kw
+    pt, pl, ho, wo = _pads(padding, h, w, kh, kw, stride)
+    wscale = store.const(in_scale) if in_scale is not None else None
+    if in_scale is not None and sn is not None:
+        alpha = K.cast(sn.inv_sigma, F32, scale=in_scale)
+    else:
+        alpha = sn.inv_sigma if sn is not None else wscale
+    bias = b.data if b is not None else None
+    xin = x if x.data.dtype == F32 else cast(x, F32)
+    res = residual.data if residual is not None else None
+    if res is not None and res.dtype != F32:
+        res = K.cast(res, F32)
+    small_in = cin < 8
+    small_out = (not small_in) and cout < 8
+    small = small_in or small_out
+    if small and (stride != 1 or res is not None):
+        raise NotImplementedError("TF32 mode: small-channel layers are plain stride-1 convolutions (RGB sides)")
+    if not small_in and (cin % 4 or (cout % 4 and not small_out)):
+        raise NotImplementedError(f"TF32 mode: cin={cin}, cout={cout} must be multiples of 4")
+    wr = None
+    if small_in:
+        y = K.conv_smallcin(xin.data, W.data, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, False, alpha, bias,
+                            None, F32)
+        xr = xin.data
+    else:
+        wt, wr = store.tf32_operands(W)
+        xr = K.round_tf32(xin.data)
+        y = K.conv_igemm_tf32(xr, wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res, None,
+                              out_dtype, residual_up2=residual_up2, stride=stride)
+    out = Var(y, grad_dtype=out_grad_dtype if out_grad_dtype in (None, F32) else F32)
+    need_w = W.needs_grad and _tape() is not None
+    need_b = b is not None and b.needs_grad and _tape() is not None
+    if _rg(xin, residual) or need_w or need_b:
+        out.requires_grad = True
+        tape = _tape()
+
+        def bwd():
+            gy = out.grad
+            if gy is None:
+                return
+            gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
+            if residual is not None and residual.requires_grad:
+                if residual_up2:
+                    residual.accum(K.sum2x2(gy32, 1.0, residual.gdtype))
+                else:
+                    residual.accum(gy32 if residual.gdtype == F32 else K.cast(gy32, residual.gdtype))
+            need_x = xin.requires_grad
+            if not (need_w or need_x or need_b):
+                return
+            if sn is not None:
+                dst, beta = sn.g, (1.0 if sn.g_written else 0.0)
+            else:
+                dst, beta = W.grad, 1.0
+            if need_b:
+                K.colsum(gy32, n * ho * wo, cout, b.grad, 1.0)
+            if small:
+                if small_in:
+                    if need_w:
+                        K.conv_small_wgrad(xin.data, gy32, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, +1, False,
+                                           wscale, beta)
+                    if need_x:   # narrow output (3 channels): the tensor-core data-gradient kernel with a 16-wide tile
+                        _, wr_in = store.tf32_operands(W)
+                        xin.accum(K.conv_igemm_tf32(K.round_tf32(gy32), wr_in, n, ho, wo, cout, h, w, cin, kh, kw,
+                                                    kh - 1 - pt, kw - 1 - pl, True, alpha, None, None, None, F32))
+                else:
+                    if need_w:
+                        K.conv_small_wgrad(gy32, xin.data, dst, n, ho, wo, cout, h, w, cin, kh, kw, pt, pl, -1, True,
+                                           wscale, beta)
+                    if need_x:
+                        xin.accum(K.conv_smallcin(gy32, W.data, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt,
+                                                  kw - 1 - pl, True, True, alpha, None, None, F32))
+            else:
+                gyr = K.round_tf32(gy32)
+                if need_w:
+                    K.conv_wgrad_tf32(xr, gyr, dst, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, wscale, beta, stride=stride)
+                if need_x:
+                    if stride == 1:
+                        dx = K.conv_igemm_tf32(gyr, wr, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
+                                               alpha, None, None, None, F32)
+                    else:
+                        hd, wd = (ho - 1) * stride + 1, (wo - 1) * stride + 1
+                        gyd = K.dilate2d(gyr, stride, hd, wd)
+                        dx = K.conv_igemm_tf32(gyd, wr, n, hd, wd, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
+                                               alpha, None, None, None, F32)
+                    xin.accum(dx)
+            if need_w and sn is not None:
+                sn.g_written = True
+                lst = tape.pending_sn.setdefault(W.root, [])
+                if sn not in lst:
+                    lst.append(sn)
         tape.record(bwd)
     return out
 
@@ -697,7 +802,8 @@ def norm_act(x: Var, *, stats: str | None, eps: float = 1e-5, gamma: Variable | 
     gam = gamma.data if gamma is not None else None
     bet = beta.data if beta is not None else None
     # the raw bf16 copy (1x1-shortcut operand) is x itself when x is already stored in bf16
-    share_raw = want_raw and x.data.dtype == BF16
+    # (in TF32 operand mode the activations are fp32 and the shortcut convolution reads x itself)
+    share_raw = want_raw and (x.data.dtype == BF16 or (out_dtype == F32 and x.data.dtype == F32))
     raw = torch.empty((n, h, w, c), dtype=BF16, device=x.data.device) if (want_raw and not share_raw) else None
     quad = bool(getattr(x, "quad", False))   # x is the quad-layout output of upconv2d; the result is plain NHWC
     if quad and (upsample or want_raw):
@@ -827,6 +933,21 @@ def embedding(table: Variable, labels: torch.Tensor) -> Var:
     return out
 
 
+def tile_hw(e: Var, h: int, w: int) -> Var:
+    """tf.tile(e[:, None, None, :], [1, h, w, 1]) for fp32 e [n, c]; the gradient is the sum over (h, w)."""
+    n, c = e.shape
+    out = Var(e.data.reshape(n, 1, 1, c).expand(n, h, w, c).contiguous())      # tensor plumbing, no arithmetic
+    if _rg(e):
+        out.requires_grad = True
+
+        def bwd():
+            if out.grad is not None:
+                g = out.grad if out.grad.dtype == F32 else K.cast(out.grad, F32)
+                e.accum(K.cast(K.act_mean_hw_fwd(g, None), F32, scale=float(h * w)))
+        _tape().record(bwd)
+    return out
+
+
 def concat_label_map(x: Var, e: Var, act="relu"):
     """tf.concat([x, tile(e[:,None,None,:])], axis=3) (SNGAN/gan_cifar_resnet.py:282-284), emitted directly as the
     two bf16 operands the next residual block needs: the raw concat (shortcut) and act(concat) (Conv1 input)."""
@@ -834,6 +955,12 @@ def concat_label_map(x: Var, e: Var, act="relu"):
     c2 = e.shape[1]
     ct = c1 + c2
     dev = x.data.device
+    if get_store().is_tf32():
+        # TF32 operand mode: fp32 operands, assembled from the generic ops (concat + stand-alone activation)
+        x32 = x if x.data.dtype == F32 else cast(x, F32)
+        raw32 = concat_channels(x32, tile_hw(e, h, w), out_dtype=F32)
+        act32, _ = norm_act(raw32, stats=None, act=act, out_dtype=F32)
+        return raw32, act32
     raw = torch.empty((n, h, w, ct), dtype=BF16, device=dev)
     actv = torch.empty((n, h, w, ct), dtype=BF16, device=dev)
     K.norm_act_fwd(x.data, n, h, w, c1, None, None, 1, None, None, None, act, False, BF16, out=actv, out_cstride=ct,

@@ -146,6 +146,42 @@ def conv_wgrad(x, dy, dw, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, scal
                                 ptr(scale), c_float(beta), _stream()), "ganb_conv2d_wgrad")
 
 
+# ------------------------------------------------------------------------------------------------ conv (TC, TF32 operands)
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32 value (fp32 storage)."""
+    assert x.dtype == torch.float32
+    y = torch.empty_like(x)
+    check(L().ganb_round_tf32(ptr(x), ptr(y), c_int64(x.numel()), _stream()), "ganb_round_tf32")
+    return y
+
+
+def transpose_tf32(w_hwio: torch.Tensor, taps: int, cin: int, cout: int) -> torch.Tensor:
+    """HWIO fp32 filter [taps, cin, cout] -> [taps, cout, cin], rounded to TF32 (the fprop operand copy)."""
+    wt = torch.empty((taps, cout, cin), dtype=torch.float32, device=w_hwio.device)
+    check(L().ganb_transpose_tf32(ptr(w_hwio), ptr(wt), taps, cin, cout, _stream()), "ganb_transpose_tf32")
+    return wt
+
+
+def conv_igemm_tf32(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, alpha, bias, residual, act, out_dtype,
+                    residual_up2=False, stride=1):
+    assert x.dtype == torch.float32 and wp.dtype == torch.float32
+    y = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
+    check(L().ganb_conv2d_igemm_tf32(ptr(x), ptr(wp), ptr(y), n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l,
+                                     int(flip), ptr(alpha), ptr(bias), ptr(residual), int(bool(residual_up2)),
+                                     act_code(act), BF16 if out_dtype == torch.bfloat16 else F32, _stream()),
+          "ganb_conv2d_igemm_tf32")
+    return y
+
+
+def conv_wgrad_tf32(x, dy, dw, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, scale, beta, stride=1):
+    assert x.dtype == torch.float32 and dy.dtype == torch.float32
+    fn = L().ganb_conv2d_wgrad_tf32_workspace
+    fn.restype = c_int64
+    ws = _ws(fn(n, ho, wo, cin, cout, kh, kw), x.device)
+    check(L().ganb_conv2d_wgrad_tf32(ptr(x), ptr(dy), ptr(dw), ptr(ws), n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t,
+                                     pad_l, ptr(scale), c_float(beta), _stream()), "ganb_conv2d_wgrad_tf32")
+
+
 # ------------------------------------------------------------------------------------------------ sub-pixel UpsampleConv
 def upconv_supported(n, h, w, cin, cout) -> bool:
     return bool(L().ganb_upconv_supported(n, h, w, cin, cout))

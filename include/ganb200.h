@@ -433,6 +433,25 @@ int ganb_depthwise_conv2d_bwd_filter(const void* x, int x_dtype, const void* dy,
                                      int h, int w, int c, int cm, int ho, int wo, int kh, int kw, int stride, int pad_t,
                                      int pad_l, void* stream);
 
+/* TF32 operand mode (north star: "BF16 or TF32 inputs and FP32 accumulation"; tolerance <= 1e-3 relative per layer): the
+ * implicit-GEMM convolution and its filter gradient with fp32 NHWC operands read by tcgen05.mma kind::tf32 -- the
+ * TensorFlow calls replaced are the same tf.nn.conv2d / Conv2DBackpropInput / Conv2DBackpropFilter
+ * (common/ops/conv2d.py:181-187).  Arguments as ganb_conv2d_igemm / ganb_conv2d_wgrad with fp32 x / dy and the filter
+ * copies in fp32: wp = [taps][cout][cin] for fprop (ganb_transpose_tf32 of the HWIO filter), the HWIO filter itself
+ * [taps][cin][cout] with flip_taps = 1 and the roles of cin / cout exchanged for the data gradient.  cin % 4 == 0
+ * (and cout % 4 == 0 for the filter gradient).  The MMA truncates the 13 low mantissa bits: callers round operands to
+ * nearest with ganb_round_tf32 / ganb_transpose_tf32 first. */
+int ganb_conv2d_igemm_tf32(const float* x, const float* wp, void* y, int n, int h, int w, int cin, int ho, int wo,
+                           int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps, const float* alpha,
+                           const float* bias, const float* residual, int residual_up2, int act, int out_dtype,
+                           void* stream);
+int64_t ganb_conv2d_wgrad_tf32_workspace(int n, int ho, int wo, int cin, int cout, int kh, int kw);
+int ganb_conv2d_wgrad_tf32(const float* x, const float* dy, float* dw, void* workspace, int n, int h, int w, int cin,
+                           int ho, int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, const float* scale,
+                           float beta, void* stream);
+int ganb_round_tf32(const float* x, float* y, int64_t count, void* stream);
+int ganb_transpose_tf32(const float* w_hwio, float* wt, int taps, int cin, int cout, void* stream);
+
 /* Small all-reduces over NVLink / NVSwitch peer memory (csrc/peer.cu) for the statistic exchanges of the data-parallel
  * path: cross-GPU BatchNorm moments (reference coupling point common/ops/normalization.py:47) and the
  * [sum dy | sum dy*xhat] pair of its backward pass.  peer_bufs: HOST array of `world` device pointers = this process'

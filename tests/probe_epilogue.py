@@ -30,17 +30,30 @@ def main():
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        if reps > 1:     # launches back to back inside a CUDA graph: no host launch gaps between the short kernels
+            g = torch.cuda.CUDAGraph()
+            s_ = torch.cuda.Stream()
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                with torch.cuda.graph(g):
+                    for _ in range(reps):
+                        fn()
+            torch.cuda.current_stream().wait_stream(s_)
+            run = g.replay
+        else:
+            run = fn
+        run()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
-            fn()
+        run()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / reps * 1e3
         out_mb = n * h * h * cout * (2 if out == BF16 else 4) / 1e6
         in_mb = n * h * h * cin * 2 / 1e6
         gf = 2.0 * n * h * h * cin * k * k * cout / 1e9
-        print(f"{tag:42s} {us:7.1f} us  {gf / us * 1e3 / 1e3:7.1f} TFLOP/s  in+out {in_mb + out_mb:6.1f} MB -> "
+        print(f"{tag:42s} {us:7.1f} us  {gf / us / 1e3:7.1f} TFLOP/s  in+out {in_mb + out_mb:6.1f} MB -> "
               f"{(in_mb + out_mb) / us * 1e3 / 1e3:5.2f} TB/s")
 
 
