@@ -141,13 +141,20 @@ class Trainer:
     lr_schedule = staticmethod(lambda it: lr_decay(it))
 
     def __init__(self, batch_size: int = BATCH_SIZE, seed: int | None = 0, store=None, world_size: int = 1,
-                 grad_allreduce=None, bn_sync: bool = False, peer=None):
+                 grad_allreduce=None, bn_sync: bool = False, peer=None, grad_wire: str = "fp32"):
         """bn_sync: reduce the (conditional) batch-norm statistics of G over all ranks as well (every statistic tower
         then spans the ranks' shares: N GPUs x batch/N reproduce one GPU at the global batch).  Default: per-rank
         statistics, the reference's per-tower semantics.
         peer: a peer.PeerComm -- the statistic exchanges then are single peer-memory kernels inside the captured graphs
         (csrc/peer.cu).  Without it they go through the all-reduce callable in the middle of the passes, and the mode
         runs eagerly (capture() is a no-op)."""
+        if grad_wire not in ("fp32", "bf16"):
+            raise ValueError("grad_wire must be 'fp32' or 'bf16'")
+        # grad_wire='bf16': the flat gradient buffers cross NVLink as bf16 (half the bytes of the all-reduce; the sum of
+        # the ranks' gradients is rounded to 8 mantissa bits, below the noise of their bf16-operand computation) and come
+        # back into the fp32 buffers Adam reads.  The two casts are part of the captured compute / update graphs.
+        self.grad_wire = grad_wire if (world_size > 1 and grad_allreduce is not None) else "fp32"
+        self._wire = {}
         self.store = store or get_store()
         self.bn_sync = bool(bn_sync) and world_size > 1
         self.bn_sync_in_graph = self.bn_sync and peer is not None
@@ -232,6 +239,7 @@ class Trainer:
             loss = F.gan_loss(disc_all, 'hinge_d', n_real=b)
             tape.backward(loss)
         self.d_loss.copy_(loss.data)
+        self._wire_out('Discriminator')
 
     def _preprocess_real(self, b):
         """int pixels -> [-1, 1) + dequantisation noise, CHW -> NHWC (gan_cifar_resnet.py:334-337)."""
@@ -244,7 +252,27 @@ class Trainer:
         if group is not None and group.entries:
             group.refresh()
 
+    # ---- gradient exchange
+    def _wire_out(self, root):
+        """fp32 gradients -> the buffer that is all-reduced (end of a compute graph)."""
+        if self.grad_wire == "bf16":
+            g = self.store.flat[root].grads
+            buf = self._wire.get(root)
+            if buf is None:
+                buf = self._wire[root] = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+            K.cast_into(g, buf)
+
+    def _wire_in(self, root):
+        """all-reduced buffer -> the fp32 gradients Adam reads (start of an update graph)."""
+        if self.grad_wire == "bf16":
+            K.cast_into(self._wire[root], self.store.flat[root].grads)
+
+    def _exchange(self, root):
+        if self.grad_allreduce is not None:
+            self.grad_allreduce(self._wire[root] if self.grad_wire == "bf16" else self.store.flat[root].grads)
+
     def _d_update(self):
+        self._wire_in('Discriminator')
         self.disc_opt.apply(1.0 / self.world_size)
         self.store.bump('Discriminator')
         self._repack('Discriminator')
@@ -282,6 +310,7 @@ class Trainer:
                 loss = F.gan_loss(disc_fake, 'gen')
             tape.backward(loss)
         self.g_loss.copy_(loss.data)
+        self._wire_out('Generator')
 
     def _g_compute(self):
         """Forward + backward of the generator step (gan_cifar_resnet.py:462-498, 523): gradients of gen_cost."""
@@ -292,20 +321,19 @@ class Trainer:
         self._g_rest(tape, self._g_forward(tape))
 
     def _g_update(self):
+        self._wire_in('Generator')
         self.gen_opt.apply(1.0 / self.world_size)
         self.store.bump('Generator')
         self._repack('Generator')
 
     def _d_body(self):
         self._d_compute()
-        if self.grad_allreduce is not None:
-            self.grad_allreduce(self.store.flat['Discriminator'].grads)
+        self._exchange('Discriminator')
         self._d_update()
 
     def _g_body(self):
         self._g_compute()
-        if self.grad_allreduce is not None:
-            self.grad_allreduce(self.store.flat['Generator'].grads)
+        self._exchange('Generator')
         self._g_update()
 
     # ------------------------------------------------------------------------------------------ D+G pair
@@ -348,11 +376,9 @@ class Trainer:
     def _pair_body(self):
         # a collective issued between the halves needs the streams joined, unless it is captured with them
         self._pair_fork(join=self.grad_allreduce is not None and not getattr(self, "capture_collectives", False))
-        if self.grad_allreduce is not None:
-            self.grad_allreduce(self.store.flat['Discriminator'].grads)
+        self._exchange('Discriminator')
         self._pair_join()
-        if self.grad_allreduce is not None:
-            self.grad_allreduce(self.store.flat['Generator'].grads)
+        self._exchange('Generator')
         self._g_update()
 
     def pair_step(self, iteration: int):
@@ -364,9 +390,9 @@ class Trainer:
             gs["pair_full"].replay()
         elif "pair_fork" in gs:
             gs["pair_fork"].replay()
-            self.grad_allreduce(self.store.flat['Discriminator'].grads)
+            self._exchange('Discriminator')
             gs["pair_join"].replay()
-            self.grad_allreduce(self.store.flat['Generator'].grads)
+            self._exchange('Generator')
             gs["g_update"].replay()
         else:
             self._pair_body()
@@ -431,9 +457,7 @@ class Trainer:
             self._graphs[which + "_full"].replay()
         elif (which + "_compute") in self._graphs:
             self._graphs[which + "_compute"].replay()
-            if self.grad_allreduce is not None:
-                root = 'Discriminator' if which == 'd' else 'Generator'
-                self.grad_allreduce(self.store.flat[root].grads)
+            self._exchange('Discriminator' if which == 'd' else 'Generator')
             self._graphs[which + "_update"].replay()
         elif which == 'd':
             self._d_body()

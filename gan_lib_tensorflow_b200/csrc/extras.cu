@@ -189,6 +189,64 @@ mbstd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, co
   }
 }
 
+// ---- cross-GPU variant (the statistic then spans the GLOBAL batch, like a synced batch norm; SURVEY 8(e) collective 3):
+// phase 1 leaves the local [sum_b x | sum_b x^2] per position for an all-reduce, phase 2 turns the global sums into
+// mean / sd; the backward pass all-reduces the scalar g and uses the global batch size and the global mean.
+__global__ void __launch_bounds__(256)
+mbstd_moments_kernel(const float* __restrict__ x, int b, int64_t m, float* __restrict__ sums) {
+  pdl_wait();
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < m; i += gridDim.x * 256LL) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < b; ++k) {
+      const float v = x[k * m + i];
+      s += v;
+      q += v * v;
+    }
+    sums[i] = s;
+    sums[m + i] = q;
+  }
+}
+__global__ void __launch_bounds__(256)
+mbstd_global_sd_kernel(const float* __restrict__ sums, int64_t m, float inv_batch, float eps, float* __restrict__ sd,
+                       float* __restrict__ mean, float* __restrict__ partial) {
+  pdl_wait();
+  __shared__ float sh[8];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < m; i += gridDim.x * 256LL) {
+    const float mu = sums[i] * inv_batch;
+    float var = sums[m + i] * inv_batch - mu * mu;
+    if (var < 0.f) var = 0.f;
+    const float s = sqrtf(var + eps);
+    mean[i] = mu;
+    sd[i] = s;
+    acc += s;
+  }
+  acc = ewarp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+mbstd_bwd_global_kernel(const float* __restrict__ x, const float* __restrict__ dout, const float* __restrict__ sd,
+                        const float* __restrict__ mean, const float* __restrict__ g, int b, float batch_total, int64_t m,
+                        int c, int cs, float* __restrict__ dx) {
+  pdl_wait();
+  const float gs = g[0] / (batch_total * static_cast<float>(m));
+  for (int64_t i = blockIdx.x * 256LL + threadIdx.x; i < m; i += gridDim.x * 256LL) {
+    const float inv = gs / sd[i], mu = mean[i];
+    const int64_t pos = i / c;
+    const int ch = static_cast<int>(i % c);
+    for (int k = 0; k < b; ++k) {
+      const int64_t pix = k * (m / c) + pos;
+      dx[k * m + i] = dout[pix * cs + ch] + (x[k * m + i] - mu) * inv;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ concat / slice
 // dst[pix, off + j] = scale * mask[pix, j] * src[pix, j]   (mask optional): channel concatenation, its backward
 // (a strided slice), and dropout (mask in {0, 1}, scale = 1 / keep_prob) share one kernel.
@@ -311,6 +369,66 @@ extern "C" int ganb_minibatch_std_bwd(const float* x, const float* dout, int b, 
   launch_k(mbstd_bwd_kernel, egrid(m, 256), 256, 0, STREAM, x, dout, static_cast<const float*>(sd), static_cast<const float*>(g), b,
            m, c, cs, dx);
   GANB_CHECK_LAUNCH("mbstd_bwd_kernel");
+  return 0;
+}
+
+// Cross-GPU minibatch-stddev.  workspace (fp32, ganb_minibatch_std_sync_workspace bytes):
+//   [0, 2m) sums = [sum_b x | sum_b x^2] (all-reduced in place by the caller between the phases), [2m, 3m) sd,
+//   [3m, 4m) mean, then 1024 block partials, s, g.
+extern "C" int64_t ganb_minibatch_std_sync_workspace(int h, int w, int c) {
+  return (4LL * h * w * c + 1024 + 8) * 4;
+}
+
+extern "C" int64_t ganb_minibatch_std_sync_g_offset(int h, int w, int c) {
+  return 4LL * h * w * c + 1024 + 1;    // float index of g inside the workspace
+}
+
+extern "C" int ganb_minibatch_std_sync_fwd(const float* x, int b, int h, int w, int c, int cs, float* out, void* workspace,
+                                           int phase, int world, void* stream) {
+  if (!x || !workspace || (phase == 2 && !out)) return fail(GANB_E_BADARG, "minibatch_std_sync_fwd: null buffer");
+  if (phase != 1 && phase != 2) return fail(GANB_E_BADARG, "minibatch_std_sync_fwd: phase must be 1 or 2");
+  if (cs < c + 1 || world < 1) return fail(GANB_E_BADARG, "minibatch_std_sync_fwd: bad cs / world");
+  const int64_t m = static_cast<int64_t>(h) * w * c;
+  float* sums = static_cast<float*>(workspace);
+  float* sd = sums + 2 * m;
+  float* mean = sd + m;
+  float* partial = mean + m;
+  float* s_out = partial + 1024;
+  int nparts = static_cast<int>(ceil_div64(m, 256));
+  if (nparts > 1024) nparts = 1024;
+  if (phase == 1) {
+    launch_k(mbstd_moments_kernel, nparts, 256, 0, STREAM, x, b, m, sums);
+    GANB_CHECK_LAUNCH("mbstd_moments_kernel");
+    return 0;
+  }
+  launch_k(mbstd_global_sd_kernel, nparts, 256, 0, STREAM, static_cast<const float*>(sums), m,
+           1.0f / (static_cast<float>(b) * world), 1e-8f, sd, mean, partial);
+  GANB_CHECK_LAUNCH("mbstd_global_sd_kernel");
+  const int64_t pixels = static_cast<int64_t>(b) * h * w;
+  launch_k(mbstd_concat_kernel, egrid(pixels * cs, 256), 256, 0, STREAM, x, static_cast<const float*>(partial), nparts, pixels, c,
+           cs, m, out, s_out);
+  GANB_CHECK_LAUNCH("mbstd_concat_kernel");
+  return 0;
+}
+
+extern "C" int ganb_minibatch_std_sync_bwd(const float* x, const float* dout, int b, int h, int w, int c, int cs, float* dx,
+                                           void* workspace, int phase, int world, void* stream) {
+  if (!x || !dout || !workspace || (phase == 2 && !dx)) return fail(GANB_E_BADARG, "minibatch_std_sync_bwd: null buffer");
+  if (phase != 1 && phase != 2) return fail(GANB_E_BADARG, "minibatch_std_sync_bwd: phase must be 1 or 2");
+  const int64_t m = static_cast<int64_t>(h) * w * c;
+  float* sums = static_cast<float*>(workspace);
+  float* sd = sums + 2 * m;
+  float* mean = sd + m;
+  float* g = mean + m + 1024 + 1;       // all-reduced by the caller between the phases (1 float)
+  const int64_t pixels = static_cast<int64_t>(b) * h * w;
+  if (phase == 1) {
+    launch_k(mbstd_gsum_kernel, 1, 256, 0, STREAM, dout, pixels, c, cs, g);
+    GANB_CHECK_LAUNCH("mbstd_gsum_kernel");
+    return 0;
+  }
+  launch_k(mbstd_bwd_global_kernel, egrid(m, 256), 256, 0, STREAM, x, dout, static_cast<const float*>(sd),
+           static_cast<const float*>(mean), static_cast<const float*>(g), b, static_cast<float>(b) * world, m, c, cs, dx);
+  GANB_CHECK_LAUNCH("mbstd_bwd_global_kernel");
   return 0;
 }
 

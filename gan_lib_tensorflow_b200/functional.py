@@ -1002,7 +1002,15 @@ def pixel_norm(x: Var, eps: float = 1e-8, act=None, out_dtype=None) -> Var:
 def minibatch_std(x: Var) -> Var:
     """tf.concat([x, tile(mean(sqrt(var_batch(x) + 1e-8)))], axis=3) -- PGGAN/model_nvidia.py:20-28."""
     xin = x if x.data.dtype == F32 else cast(x, F32)
-    y, ws = K.minibatch_std_fwd(xin.data)
+    store = get_store()
+    sync = store.bn_sync if (store.bn_sync is not None and hasattr(store.bn_sync, "allreduce")) else None
+    if sync is not None:
+        # data-parallel run with synced batch statistics: the standard deviation is taken over the GLOBAL batch
+        # ([sum x | sum x^2] per position all-reduced forward, the scalar g backward; SURVEY 8(e) collective 3)
+        key = f"{store.scope_name()}/mbstd/{'x'.join(str(d) for d in xin.shape)}"
+        y, ws = K.minibatch_std_sync_fwd(xin.data, sync, key)
+    else:
+        y, ws = K.minibatch_std_fwd(xin.data)
     out = Var(y)
     if _rg(xin):
         out.requires_grad = True
@@ -1010,7 +1018,10 @@ def minibatch_std(x: Var) -> Var:
         def bwd():
             if out.grad is not None:
                 g = out.grad if out.grad.dtype == F32 else K.cast(out.grad, F32)
-                xin.accum(K.minibatch_std_bwd(xin.data, g, ws))
+                if sync is not None:
+                    xin.accum(K.minibatch_std_sync_bwd(xin.data, g, ws, sync, key))
+                else:
+                    xin.accum(K.minibatch_std_bwd(xin.data, g, ws))
         _tape().record(bwd)
     return out
 

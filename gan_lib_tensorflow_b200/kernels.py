@@ -88,6 +88,13 @@ def cast(x: torch.Tensor, dtype, scale: float = 1.0) -> torch.Tensor:
     return y
 
 
+def cast_into(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """out = scale * x with the dtype of `out` (persistent destination: the bf16 wire copy of a gradient buffer)."""
+    assert x.numel() == out.numel()
+    check(L().ganb_cast(ptr(x), dt(x), ptr(out), dt(out), c_int64(x.numel()), c_float(scale), _stream()), "ganb_cast")
+    return out
+
+
 def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0) -> None:
     """y = a*x + b*y (fp32)."""
     assert x.dtype == torch.float32 and y.dtype == torch.float32 and x.numel() == y.numel()
@@ -515,6 +522,36 @@ def minibatch_std_bwd(x, dout, ws):
     dx = torch.empty_like(x)
     check(L().ganb_minibatch_std_bwd(ptr(x), ptr(dout), b, h, w, c, cs, ptr(dx), ptr(ws), _stream()),
           "ganb_minibatch_std_bwd")
+    return dx
+
+
+def minibatch_std_sync_fwd(x, sync, key, cs=None):
+    """minibatch_std over the GLOBAL batch of a data-parallel run: `sync` is a peer.PeerComm / peer.NcclSync."""
+    b, h, w, c = x.shape
+    cs = cs or (c + 1)
+    m = h * w * c
+    fn = L().ganb_minibatch_std_sync_workspace
+    fn.restype = c_int64
+    ws = torch.empty(int(fn(h, w, c)) // 4, dtype=torch.float32, device=x.device)
+    out = torch.empty((b, h, w, cs), dtype=torch.float32, device=x.device)
+    args = (ptr(x), b, h, w, c, cs, ptr(out), ptr(ws))
+    check(L().ganb_minibatch_std_sync_fwd(*args, 1, sync.world, _stream()), "ganb_minibatch_std_sync_fwd")
+    sync.allreduce(key + "/fwd", ws[:2 * m])
+    check(L().ganb_minibatch_std_sync_fwd(*args, 2, sync.world, _stream()), "ganb_minibatch_std_sync_fwd")
+    return out, ws
+
+
+def minibatch_std_sync_bwd(x, dout, ws, sync, key):
+    b, h, w, c = x.shape
+    cs = dout.shape[-1]
+    dx = torch.empty_like(x)
+    fn = L().ganb_minibatch_std_sync_g_offset
+    fn.restype = c_int64
+    off = int(fn(h, w, c))
+    args = (ptr(x), ptr(dout), b, h, w, c, cs, ptr(dx), ptr(ws))
+    check(L().ganb_minibatch_std_sync_bwd(*args, 1, sync.world, _stream()), "ganb_minibatch_std_sync_bwd")
+    sync.allreduce(key + "/bwd", ws[off:off + 1])
+    check(L().ganb_minibatch_std_sync_bwd(*args, 2, sync.world, _stream()), "ganb_minibatch_std_sync_bwd")
     return dx
 
 

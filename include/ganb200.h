@@ -452,6 +452,19 @@ int ganb_conv2d_wgrad_tf32(const float* x, const float* dy, float* dw, void* wor
 int ganb_round_tf32(const float* x, float* y, int64_t count, void* stream);
 int ganb_transpose_tf32(const float* w_hwio, float* wt, int taps, int cin, int cout, void* stream);
 
+/* Cross-GPU minibatch-stddev (PGGAN/model_nvidia.py:20-28 with the batch statistics taken over the GLOBAL batch of a
+ * data-parallel run; SURVEY 8(e) collective 3).  Two phases around the caller's all-reduce, like ganb_norm_act_bwd_phase:
+ *   fwd phase 1: workspace[0, 2m) = [sum_b x | sum_b x^2] per (h, w, c) position (m = h*w*c)  -> all-reduce (sum)
+ *   fwd phase 2: mean / sd from the global sums (batch b * world), s = mean(sd), out = concat(x, s)
+ *   bwd phase 1: g = sum of dout[..., c] at workspace float offset ganb_minibatch_std_sync_g_offset() -> all-reduce
+ *   bwd phase 2: dx = dout[..., :c] + g * (x - mean) / (b * world * m * sd) */
+int64_t ganb_minibatch_std_sync_workspace(int h, int w, int c);
+int64_t ganb_minibatch_std_sync_g_offset(int h, int w, int c);
+int ganb_minibatch_std_sync_fwd(const float* x, int b, int h, int w, int c, int cs, float* out, void* workspace,
+                                int phase, int world, void* stream);
+int ganb_minibatch_std_sync_bwd(const float* x, const float* dout, int b, int h, int w, int c, int cs, float* dx,
+                                void* workspace, int phase, int world, void* stream);
+
 /* Small all-reduces over NVLink / NVSwitch peer memory (csrc/peer.cu) for the statistic exchanges of the data-parallel
  * path: cross-GPU BatchNorm moments (reference coupling point common/ops/normalization.py:47) and the
  * [sum dy | sum dy*xhat] pair of its backward pass.  peer_bufs: HOST array of `world` device pointers = this process'

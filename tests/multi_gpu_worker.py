@@ -70,12 +70,44 @@ def check_allreduce(peer, rank, world):
     assert rel(rstd, torch.rsqrt(full.var(0, unbiased=False) + 1e-5)) < 1e-5
 
 
+def check_minibatch_std(peer, rank, world):
+    """PGGAN's minibatch-stddev with the statistics over the global batch: `world` ranks x b/world == one rank x b,
+    values and input gradients (PGGAN/model_nvidia.py:20-28)."""
+    from gan_lib_tensorflow_b200 import functional as F
+
+    b, h, w, c = 8, 4, 4, 512
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(b, h, w, c, device="cuda", generator=g)
+    cot = torch.randn(b, h, w, c + 1, device="cuda", generator=g)
+    share = b // world
+
+    def run(xs, cots, sync):
+        store = framework.reset_default_graph("cuda")
+        store.bn_sync = sync
+        xv = F.Var(xs.contiguous(), requires_grad=True)
+        with store.gradient_tape() as tape:
+            out = F.minibatch_std(xv)
+            tape.backward(out, grad=cots.contiguous())
+        torch.cuda.synchronize()
+        framework.set_store(None)
+        return out.data, xv.grad
+
+    o_full, g_full = run(x, cot, None)
+    sl = slice(rank * share, (rank + 1) * share)
+    o_sync, g_sync = run(x[sl], cot[sl], peer)
+    assert rel(o_sync, o_full[sl]) < 1e-6, rel(o_sync, o_full[sl])
+    assert rel(g_sync, g_full[sl]) < 1e-5, rel(g_sync, g_full[sl])
+    o_loc, _ = run(x[sl], cot[sl], None)                    # per-rank statistics give a different scalar
+    assert float((o_loc[..., -1] - o_full[sl][..., -1]).abs().max()) > 1e-4
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     peer = PeerComm()
     check_allreduce(peer, rank, world)
+    check_minibatch_std(peer, rank, world)
 
     B = 64
     rs = np.random.RandomState(0)
