@@ -328,13 +328,109 @@ __device__ __forceinline__ void epilogue_loop(const IgemmParams& p, uint32_t tme
   }
 }
 
+// TMA-store epilogue (shallow-K launches: K = 32 im2col routes, 1x1 shortcuts).  These layers are bound by their output
+// stores: one thread per pixel writes 16 bytes per instruction to its own row, i.e. 32 partial sectors per warp store
+// (2x the ideal L2 sector count, profiles/r02_ncu_igemm_k32.txt).  Here the epilogue warps write their rows into a
+// shared-memory tile in the tensor map's 128-byte swizzle -- conflict-free: 4 wavefronts for 512 bytes -- and ONE bulk
+// tensor store per 128-byte channel group and tile moves full rows; rows / channels outside the tensor are clipped by
+// the TMA unit.  Two 16 KB tiles alternate; a tile is rewritten once the store that read it has finished reading
+// (cp.async.bulk.wait_group.read).  No residual / statistics on this route.
+constexpr int TS_TILE_BYTES = 128 * 128;
+
+template <int BN>
+__device__ __forceinline__ void epilogue_loop_tma(const IgemmParams& p, const CUtensorMap* tmO, uint32_t tmem_base,
+                                                  uint64_t* tfull, uint64_t* tempty, int warp, int lane,
+                                                  uint8_t* stage) {
+  constexpr int ACC_STAGES = 2;
+  constexpr int EPI_T = 128;
+  constexpr int NC = 32;
+  static_assert(BN % 64 == 0, "TMA-store epilogue: 64-channel groups");
+  __shared__ __align__(16) float bias_s[ACC_STAGES][BN];
+  const int q = warp & 3;
+  const int m = q * 32 + lane;
+  const int et = threadIdx.x - 64;
+  const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+  const int group_ch = p.out_bf16 ? 64 : 32;            // channels of one 128-byte row
+  const int groups = BN / group_ch;
+  uint8_t* my_row[2] = {stage + m * 128, stage + TS_TILE_BYTES + m * 128};
+  const uint32_t sw = static_cast<uint32_t>(m & 7);
+  int as = 0, buf = 0;
+  uint32_t aphase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int t = tile;
+    const int tco = t % p.tiles_co; t /= p.tiles_co;
+    const int tw = t % p.tiles_w;   t /= p.tiles_w;
+    const int th = t % p.tiles_h;   t /= p.tiles_h;
+    const int tn = t;
+    if (p.bias) {
+      for (int c = et; c < BN; c += EPI_T) {
+        const int co = tco * BN + c;
+        bias_s[as][c] = co < p.Cout ? __ldg(p.bias + co) : 0.f;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
+    mbar_wait(&tfull[as], aphase);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+    for (int g = 0; g < groups; ++g) {
+      if (tco * BN + g * group_ch >= p.Cout) break;       // whole group outside the tensor (uniform over the CTA)
+      // the tile `buf` was read by the store issued two groups ago: wait until that read is done
+      if (et == 0) bulk_wait_group_read<1>();
+      asm volatile("bar.sync 2, %0;" ::"n"(EPI_T) : "memory");
+      uint8_t* row = my_row[buf];
+      const int chunks = p.out_bf16 ? 2 : 1;
+#pragma unroll 1
+      for (int cc = 0; cc < chunks; ++cc) {
+        const int col = g * group_ch + cc * NC;
+        uint32_t r[NC];
+        tmem_ld_cols<NC>(trow + col, r);
+        tmem_ld_wait();
+        float v[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          float x = __uint_as_float(r[j]) * alpha;
+          if (p.bias) x += bias_s[as][col + j];
+          v[j] = apply_act(x, p.act);
+        }
+        if (p.out_bf16) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {       // 4 x 16 bytes = 32 bf16 channels: units cc*4 .. cc*4+3 of the row
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(v[8 * u], v[8 * u + 1]), q1 = __floats2bfloat162_rn(v[8 * u + 2], v[8 * u + 3]);
+            __nv_bfloat162 q2 = __floats2bfloat162_rn(v[8 * u + 4], v[8 * u + 5]), q3 = __floats2bfloat162_rn(v[8 * u + 6], v[8 * u + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
+            pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
+            *reinterpret_cast<uint4*>(row + (((cc * 4 + u) ^ sw) << 4)) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)         // 8 x 16 bytes = 32 fp32 channels
+            *reinterpret_cast<float4*>(row + ((u ^ sw) << 4)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        }
+      }
+      fence_proxy_async();                    // generic-proxy writes visible to the bulk-copy engine
+      asm volatile("bar.sync 2, %0;" ::"n"(EPI_T) : "memory");
+      if (et == 0) {
+        tma_store_4d(tmO, stage + buf * TS_TILE_BYTES, tco * BN + g * group_ch, tw * p.bw, th * p.bh, tn * p.bn);
+        bulk_commit_group();
+      }
+      buf ^= 1;
+    }
+    tc_fence_before();
+    mbar_arrive(&tempty[as]);
+    if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+  }
+  if (et == 0) bulk_wait_group<0>();          // every store has completed before the CTA exits
+}
+
 // TF32 = true: fp32 operands read by kind::tf32 MMAs (north star: "BF16 or TF32 inputs").  A 128-byte swizzle row then
 // holds 32 channels instead of 64; a stage is still 128 rows x 128 bytes and four K-steps of 32 bytes, so only the
 // channel coordinates of the TMA boxes, the instruction descriptor and the MMA kind differ.
-template <int BN, int STAGES, bool STATS, bool TF32 = false>
+template <int BN, int STAGES, bool STATS, bool TF32 = false, bool TSTORE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const IgemmParams p) {
+                  const IgemmParams p, const __grid_constant__ CUtensorMap tmO) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int ACC_STAGES = 2;
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN) < 32 ? 32 : (ACC_STAGES * BN);
@@ -456,7 +552,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    epilogue_loop<BN, STATS>(p, tmem_base, tfull, tempty, warp, lane, tmem_slot + 4);
+    if constexpr (TSTORE) {
+      if (threadIdx.x == 64) tma_prefetch_desc(&tmO);
+      // staging tiles: 1024-byte aligned, behind the barrier block
+      const uint32_t a = smem_u32(tmem_slot + 4);
+      uint8_t* stage = reinterpret_cast<uint8_t*>(tmem_slot + 4) + ((1024u - (a & 1023u)) & 1023u);
+      epilogue_loop_tma<BN>(p, &tmO, tmem_base, tfull, tempty, warp, lane, stage);
+    } else {
+      epilogue_loop<BN, STATS>(p, tmem_base, tfull, tempty, warp, lane, tmem_slot + 4);
+    }
   }
 
   tc_fence_before();
@@ -1206,24 +1310,31 @@ static int stats_smem(const IgemmParams& p) {
 // SM and their epilogues run side by side.
 template <int BN, int STAGES>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmParams& p, cudaStream_t stream,
-                        int ctas_per_sm = 1) {
-  const int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + stats_smem<BN>(p);
+                        int ctas_per_sm = 1, const CUtensorMap* tmO = nullptr) {
+  int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + stats_smem<BN>(p);
   auto kern = conv_igemm_kernel<BN, STAGES, false>;
-  bool with_stats = false;
+  int variant = 0;
   if constexpr (BN >= 64) {
-    if (p.stats) { kern = conv_igemm_kernel<BN, STAGES, true>; with_stats = true; }
+    if (p.stats) { kern = conv_igemm_kernel<BN, STAGES, true>; variant = 1; }
   }
-  static int configured[2] = {0, 0};
-  if (configured[with_stats] < smem) {
+  if constexpr (STAGES == 2 && BN % 64 == 0) {     // TMA-store epilogue: shallow-K instances only
+    if (tmO && !p.stats) {
+      kern = conv_igemm_kernel<BN, STAGES, false, false, true>;
+      variant = 2;
+      smem += 1024 + 2 * TS_TILE_BYTES;
+    }
+  }
+  static int configured[3] = {0, 0, 0};
+  if (configured[variant] < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(GANB_E_LAUNCH, "igemm smem attribute: %s", cudaGetErrorString(e));
-    configured[with_stats] = smem;
+    configured[variant] = smem;
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
   const int slots = sm_count() * ctas_per_sm;
   int grid = p.num_tiles < slots ? p.num_tiles : slots;
-  launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
+  launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p, variant == 2 ? *tmO : tmA);
   GANB_CHECK_LAUNCH("conv_igemm_kernel");
   return 0;
 }
@@ -1464,8 +1575,27 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
     }
   }
   if (shallow) {
-    if (bn_tile == 64) return launch_igemm<64, 2>(tmA, tmB, p, stream, 2);
-    return launch_igemm<128, 2>(tmA, tmB, p, stream, 2);
+    // TMA-store epilogue where the output is a plain tensor of full 16-byte rows.  OPT-IN (GANB_TMA_STORE=1): correct
+    // (the whole GPU suite passes with it on) but measured 1.4-2x SLOWER than the per-thread 16-byte stores on every
+    // shallow-K layer (21.0 -> 39.9 us, 32.8 -> 68.8 us, 17.3 -> 24.3 us; step 3.14 -> 3.30 ms,
+    // profiles/r02_tma_store_ab.txt) -- like round 1's shared-memory-transposed epilogue: two named barriers, a proxy fence
+    // and a bulk-group wait per 128-byte channel group serialise the four epilogue warps.
+    static const bool tstore_ok = getenv("GANB_TMA_STORE") && getenv("GANB_TMA_STORE")[0] == '1';
+    const int es = p.out_bf16 ? 2 : 4, group_ch = p.out_bf16 ? 64 : 32;
+    CUtensorMap tmO;
+    const CUtensorMap* tmo = nullptr;
+    if (tstore_ok && !residual && (static_cast<int64_t>(cout) * es) % 16 == 0 && cout >= group_ch &&
+        (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+      const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)wo, (uint64_t)ho, (uint64_t)n};
+      const uint64_t strides[3] = {(uint64_t)cout * es, (uint64_t)wo * cout * es, (uint64_t)ho * wo * cout * es};
+      const uint32_t box[4] = {(uint32_t)group_ch, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      int rc = p.out_bf16 ? encode_tmap_bf16(&tmO, y, 4, dims, strides, box, nullptr)
+                          : encode_tmap_f32(&tmO, y, 4, dims, strides, box, nullptr);
+      if (rc) return rc;
+      tmo = &tmO;
+    }
+    if (bn_tile == 64) return launch_igemm<64, 2>(tmA, tmB, p, stream, 2, tmo);
+    return launch_igemm<128, 2>(tmA, tmB, p, stream, 2, tmo);
   }
   switch (bn_tile) {
     case 16: return launch_igemm<16, 8>(tmA, tmB, p, stream);
@@ -1831,7 +1961,7 @@ static int launch_igemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, Ige
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p);
+  launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p, tmA);
   GANB_CHECK_LAUNCH("conv_igemm_kernel<tf32>");
   return 0;
 }
