@@ -11,6 +11,7 @@ Reference structure kept:
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -45,7 +46,10 @@ N_TOWERS = 2  # len(DEVICES) is always 2 in the reference (:73-75)
 # framework.Tape.branch).  Correct (tests pass, gradients bit-identical) but measured SLOWER: 3.30 vs 3.15 ms per pair on
 # one box -- the half-batch kernels lose the CTA-pair route at 16x16 and the tensor-core kernels of the two chains
 # serialise anyway.  Opt-in (GANB_SPLIT_CRITIC=1) for further experiments.
-SPLIT_CRITIC_PASS = __import__("os").environ.get("GANB_SPLIT_CRITIC", "0") == "1"
+SPLIT_CRITIC_PASS = os.environ.get("GANB_SPLIT_CRITIC", "0") == "1"
+# where the generator step's G forward forks off in the pair schedule: "early" = next to the critic step's own generator
+# pass, "late" = behind it, next to the critic's forward + backward (A/B: profiles/r02_pair_fork_ab.txt)
+PAIR_FORK = os.environ.get("GANB_PAIR_FORK", "early")
 
 BF16 = torch.bfloat16
 
@@ -222,13 +226,16 @@ class Trainer:
         self.fake_labels.copy_((torch.rand(self.gen_batch, device=self.store.device) * self.n_classes).to(torch.int32))
 
     # ------------------------------------------------------------------------------------------ steps
-    def _d_compute(self):
-        """Forward + backward of the critic step (gan_cifar_resnet.py:322-381, 524): gradients of disc_cost."""
+    def _d_compute(self, after_fake=None):
+        """Forward + backward of the critic step (gan_cifar_resnet.py:322-381, 524): gradients of disc_cost.
+        `after_fake` (pair schedule) is called once the fake batch of this step has been issued."""
         st = self.store
         b = self.batch
         st.zero_grad('Discriminator')
         with st.stat_towers(self.n_towers):
             fake = self.generator(b, self.real_labels, noise=self.z_d, reuse=True)  # no tape: var_list = disc_params
+        if after_fake is not None:
+            after_fake()
         real = self._preprocess_real(b)
         self.d_in[:b].copy_(real)
         self.d_in[b:].copy_(fake.data)
@@ -354,11 +361,21 @@ class Trainer:
             return
         main = torch.cuda.current_stream()
         aux = framework_aux_stream(main.device)
-        aux.wait_stream(main)
-        with torch.cuda.stream(aux):
-            st.zero_grad('Generator')
-            fake = self._g_forward(tape)
-        self._d_compute()
+        out = []
+
+        def g_forward_on_aux():
+            aux.wait_stream(main)
+            with torch.cuda.stream(aux):
+                st.zero_grad('Generator')
+                out.append(self._g_forward(tape))
+        if PAIR_FORK == "late":
+            # the aux pass starts behind the (no-gradient) generator pass of the critic step: G's tensor-bound forward
+            # then runs next to the critic's forward + backward, a chain of small latency-bound kernels
+            self._d_compute(after_fake=g_forward_on_aux)
+        else:
+            g_forward_on_aux()
+            self._d_compute()
+        fake = out[0]
         if join:          # this half is a CUDA graph of its own (a collective follows): its streams meet at its end
             main.wait_stream(aux)
             aux = None
@@ -444,7 +461,10 @@ class Trainer:
                 self._invalidate_caches(packs=False)
                 before = K.launch_count()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                # GANB_MAIN_PRIORITY=high: the chain of the capturing stream (critic step, backward data gradients) is
+                # scheduled ahead of the side streams' kernels (kernel nodes keep their stream's priority)
+                cap = torch.cuda.Stream(priority=-1) if os.environ.get("GANB_MAIN_PRIORITY") == "high" else None
+                with torch.cuda.graph(g, pool=pool, stream=cap):
                     body()
                 self._graphs[name] = g
                 self.pair_launches += K.launch_count() - before

@@ -115,14 +115,15 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
            spectral_normed=False, update_collection=None, inputs_norm=False, he_init=True,
            mask_type=None, weightnorm=None, biases=True, gain=1., reuse=None,
            residual=None, out_grad_dtype=None, residual_up2=False, out_dtype=None, subpixel_up2=False,
-           bn_stats=False):
+           bn_stats=False, fused_act=None):
     """
     Args mirror common/ops/conv2d.py:31-55 (`reuse` is the extra keyword of conv2d_.py:33, accepted and ignored).
     `residual` (fp32 Var added in the GEMM epilogue; `residual_up2`: given at half resolution) and `out_grad_dtype`
     are extensions used by resnet_block.  `subpixel_up2`: the layer is UpsampleConv (nearest 2x in front of this 3x3
     convolution, common/resnet_block.py:83-97) and `inputs` is the LOW-resolution tensor: evaluated in sub-pixel
     form, output in quad layout (functional.upconv2d).  `bn_stats`: the output feeds a batch-statistics normalisation
-    (the convolution epilogue then also produces its per-channel sums, functional.conv2d).
+    (the convolution epilogue then also produces its per-channel sums, functional.conv2d).  `fused_act`: the nonlinearity
+    behind the layer, applied by the epilogue (functional.conv2d(act=...); the consumer must be a plain Conv2D).
 
     Returns:
       Var of shape (batch_size, out_height, out_width, output_dim), fp32
@@ -158,6 +159,8 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
                 stdev, (filter_size, filter_size, input_dim, channel_multiplier)))
             pointwise_filters = store.get_variable(name='pointwise_filters', initializer=lambda _s: uniform(
                 stdev, (1, 1, input_dim * channel_multiplier, output_dim)))
+        if fused_act is not None and (conv_type != 'conv2d' or subpixel_up2):
+            raise NotImplementedError('fused_act: plain conv2d layers only')
         if conv_type != 'conv2d':
             return _depthwise_types(store, inputs, conv_type, filters, depthwise_filters, pointwise_filters, input_dim,
                                     output_dim, channel_multiplier, stride, padding, spectral_normed,
@@ -193,5 +196,5 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name='Conv2D'
                               **({'out_dtype': out_dtype} if out_dtype is not None else {}))
         return F.conv2d(inputs, filters, _biases, filter_size, filter_size, stride, padding, sn=sn_entry,
                         residual=residual, out_grad_dtype=out_grad_dtype, in_scale=in_scale,
-                        residual_up2=residual_up2, bn_stats=bn_stats,
+                        residual_up2=residual_up2, bn_stats=bn_stats, act=fused_act,
                         **({'out_dtype': out_dtype} if out_dtype is not None else {}))

@@ -195,11 +195,19 @@ def ResidualBlock(inputs, input_dim, output_dim, filter_size, name,
     # h1 is only consumed by N2 + nonlinearity, whose backward can emit the bf16 tensor-core operand directly
     # and which is stored in bf16: it is only read by that kernel (rounding commutes with relu / leaky relu, so
     # without a normalisation in between this is bit-identical to rounding after the activation)
+    # without a normalisation between the two convolutions (critic blocks) the nonlinearity is applied by Conv1's
+    # epilogue and its derivative by Conv2's data-gradient epilogue: no pass over h1 in either direction
+    fuse_act = (kind(name + '.N2') is None and not subpixel and
+                F.conv2d_act_fusable(input_dim, mid_dim, output_dim, filter_size))
     h1 = conv(a1, input_dim, mid_dim, name=name + '.Conv1', he_init=True, out_grad_dtype=_adt(), out_dtype=_adt(),
-              subpixel_up2=subpixel, bn_stats=kind(name + '.N2') in ('cbn', 'bn'))
+              subpixel_up2=subpixel, bn_stats=kind(name + '.N2') in ('cbn', 'bn'),
+              fused_act=activation_fn if fuse_act else None)
 
     # ---- N2 + nonlinearity
-    a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn, n_labels=n_labels)
+    if fuse_act:
+        a2 = h1
+    else:
+        a2, _ = _norm_act(name + '.N2', h1, labels, kind(name + '.N2'), activation_fn, n_labels=n_labels)
 
     # ---- Conv2 (+ residual in the epilogue) [+ mean-pool of the sum]
     if resample == 'down':
@@ -225,10 +233,13 @@ def OptimizedResBlockDisc1(inputs, DIM_D=128, activation_fn='relu',
     shortcut = MeanPoolConv(inputs=inputs, output_dim=DIM_D, filter_size=1, name=name_prefix + '.Shortcut',
                             spectral_normed=spectral_normed, update_collection=update_collection,
                             inputs_norm=inputs_norm, he_init=False, biases=biases)
+    fuse_act = F.conv2d_act_fusable(cin, DIM_D, DIM_D, 3)     # as in ResidualBlock: relu inside Conv1's epilogue
     output = _conv2d.Conv2D(inputs, cin, DIM_D, 3, 1, name_prefix + '.Conv1', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
-                            biases=biases, out_grad_dtype=_adt(), out_dtype=_adt())
-    output, _ = F.norm_act(output, stats=None, act=activation_fn, out_dtype=_adt())
+                            biases=biases, out_grad_dtype=_adt(), out_dtype=_adt(),
+                            fused_act=activation_fn if fuse_act else None)
+    if not fuse_act:
+        output, _ = F.norm_act(output, stats=None, act=activation_fn, out_dtype=_adt())
     output = _conv2d.Conv2D(output, DIM_D, DIM_D, 3, 1, name_prefix + '.Conv2', spectral_normed=spectral_normed,
                             update_collection=update_collection, inputs_norm=inputs_norm, he_init=True,
                             biases=biases, out_grad_dtype=_adt())

@@ -68,6 +68,11 @@ struct IgemmParams {
   // so the rows of one statistic tower are contiguous and bn_stats_finalize_kernel folds them in a fixed order
   // (deterministic).  nullptr: off.
   float* stats;
+  // Derivative of an activation that the PRODUCER of this layer's input applied in its own epilogue (data-gradient
+  // launches): gate = act(pre-activation), bf16, laid out like the output; y *= act'(pre), read off the sign of gate
+  // (relu: gate > 0; leaky relu: gate >= 0 ? 1 : 0.2).  nullptr: off.
+  const __nv_bfloat16* gate;
+  int gate_act;
 };
 
 template <int NC>
@@ -86,6 +91,10 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+
+__device__ __noinline__ float4 tanh4(float4 a) {
+  return make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -186,11 +195,49 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
         v[j / 4].x += b.x; v[j / 4].y += b.y; v[j / 4].z += b.z; v[j / 4].w += b.w;
       }
     }
-    if (p.act) {
+    // one uniform branch per activation AROUND the unrolled loops (a per-element switch costs a branch per element and
+    // doubled the time of the shallow-K layers)
+    if (p.act == GANB_ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < NC / 4; ++j) {
-        v[j].x = apply_act(v[j].x, p.act); v[j].y = apply_act(v[j].y, p.act);
-        v[j].z = apply_act(v[j].z, p.act); v[j].w = apply_act(v[j].w, p.act);
+        v[j].x = v[j].x > 0.f ? v[j].x : 0.f; v[j].y = v[j].y > 0.f ? v[j].y : 0.f;
+        v[j].z = v[j].z > 0.f ? v[j].z : 0.f; v[j].w = v[j].w > 0.f ? v[j].w : 0.f;
+      }
+    } else if (p.act == GANB_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) {
+        v[j].x = v[j].x >= 0.f ? v[j].x : 0.2f * v[j].x; v[j].y = v[j].y >= 0.f ? v[j].y : 0.2f * v[j].y;
+        v[j].z = v[j].z >= 0.f ? v[j].z : 0.2f * v[j].z; v[j].w = v[j].w >= 0.f ? v[j].w : 0.2f * v[j].w;
+      }
+    } else if (p.act == GANB_ACT_TANH) {
+      // unrolled (a rolled loop would index v[] dynamically and push the array into local memory) around an out-of-line
+      // tanh (inlined, its 32 interleaved copies cost every instance of the kernel ~35 registers)
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) v[j] = tanh4(v[j]);
+    }
+    if (p.gate) {
+      if constexpr (NC % 8 == 0) {
+        uint4 g[NC / 8];
+#pragma unroll
+        for (int j = 0; j < NC; j += 8)
+          g[j / 8] = (co_base + j < cout) ? __ldg(reinterpret_cast<const uint4*>(p.gate + off + j)) : make_uint4(0, 0, 0, 0);
+        const float neg = p.gate_act == GANB_ACT_LRELU ? 0.2f : 0.f;
+        const uint32_t zero_is_on = p.gate_act == GANB_ACT_LRELU ? 1u : 0u;   // lrelu'(0) = 1, relu'(0) = 0
+        // bf16 pair: element 2k in the low half, 2k+1 in the high half; "on" = positive (or +-0 for leaky relu)
+        auto gate2 = [&](float& a, float& b, uint32_t w2) {
+          const uint32_t lo = w2 & 0xffffu, hi = w2 >> 16;
+          const bool on_lo = (lo & 0x7fffu) ? !(lo & 0x8000u) : zero_is_on;
+          const bool on_hi = (hi & 0x7fffu) ? !(hi & 0x8000u) : zero_is_on;
+          if (!on_lo) a *= neg;
+          if (!on_hi) b *= neg;
+        };
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+          gate2(v[2 * j].x, v[2 * j].y, g[j].x);
+          gate2(v[2 * j].z, v[2 * j].w, g[j].y);
+          gate2(v[2 * j + 1].x, v[2 * j + 1].y, g[j].z);
+          gate2(v[2 * j + 1].z, v[2 * j + 1].w, g[j].w);
+        }
       }
     }
     if (val) {
@@ -1436,14 +1483,26 @@ static bool igemm_tiling(int ho, int wo, int kh, int kw, int stride, int* bw, in
 static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho, int wo,
                              int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
                              const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
-                             int out_dtype, float* stats, void* stream_);
+                             int out_dtype, float* stats, const void* gate, int gate_act, void* stream_);
 
 extern "C" int ganb_conv2d_igemm(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho,
                                  int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
                                  int flip_taps, const float* alpha, const float* bias, const float* residual,
                                  int residual_up2, int act, int out_dtype, void* stream_) {
   return conv2d_igemm_impl(x, wp, y, n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l, flip_taps, alpha, bias,
-                           residual, residual_up2, act, out_dtype, nullptr, stream_);
+                           residual, residual_up2, act, out_dtype, nullptr, nullptr, 0, stream_);
+}
+
+extern "C" int ganb_conv2d_igemm_gated(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho,
+                                       int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l,
+                                       int flip_taps, const float* alpha, const void* gate_bf16, int gate_act,
+                                       int out_dtype, void* stream_) {
+  if (!gate_bf16 || (gate_act != GANB_ACT_RELU && gate_act != GANB_ACT_LRELU))
+    return fail(GANB_E_BADARG, "conv2d_igemm_gated: gate=%p gate_act=%d (relu / leaky relu)", gate_bf16, gate_act);
+  if (cout % 8 != 0 || (reinterpret_cast<uintptr_t>(gate_bf16) & 15))
+    return fail(GANB_E_UNSUPPORTED, "conv2d_igemm_gated: cout=%d must be a multiple of 8 and the gate 16-byte aligned", cout);
+  return conv2d_igemm_impl(x, wp, y, n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l, flip_taps, alpha, nullptr,
+                           nullptr, 0, GANB_ACT_NONE, out_dtype, nullptr, gate_bf16, gate_act, stream_);
 }
 
 extern "C" int ganb_conv2d_stats_rows(int n, int ho, int wo, int cout, int kh, int kw, int stride, int groups) {
@@ -1464,13 +1523,13 @@ extern "C" int ganb_conv2d_igemm_stats(const void* x, const void* wp, void* y, i
     return fail(GANB_E_UNSUPPORTED, "conv2d_igemm_stats: n=%d ho=%d wo=%d cout=%d groups=%d (see ganb_conv2d_stats_rows)",
                 n, ho, wo, cout, groups);
   return conv2d_igemm_impl(x, wp, y, n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l, flip_taps, alpha, bias,
-                           residual, residual_up2, act, out_dtype, stats, stream_);
+                           residual, residual_up2, act, out_dtype, stats, nullptr, 0, stream_);
 }
 
 static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int h, int w, int cin, int ho, int wo,
                              int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
                              const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
-                             int out_dtype, float* stats, void* stream_) {
+                             int out_dtype, float* stats, const void* gate, int gate_act, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !wp || !y) return fail(GANB_E_BADARG, "conv2d_igemm: null buffer");
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || ho <= 0 || wo <= 0 || cout <= 0 || kh <= 0 || kw <= 0)
@@ -1488,6 +1547,7 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
   // strided convolutions gather every stride-th pixel through the TMA element strides of the per-tap box
   const bool halo = igemm_tiling(ho, wo, kh, kw, stride, &p.bw, &p.bh, &p.bn);
   p.stats = stats;
+  p.gate = static_cast<const __nv_bfloat16*>(gate); p.gate_act = gate_act;
   p.tiles_w = ceil_div(wo, p.bw);
   p.tiles_h = ceil_div(ho, p.bh);
   p.tiles_n = ceil_div(n, p.bn);
@@ -1584,7 +1644,7 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
     const int es = p.out_bf16 ? 2 : 4, group_ch = p.out_bf16 ? 64 : 32;
     CUtensorMap tmO;
     const CUtensorMap* tmo = nullptr;
-    if (tstore_ok && !residual && (static_cast<int64_t>(cout) * es) % 16 == 0 && cout >= group_ch &&
+    if (tstore_ok && !residual && !gate && (static_cast<int64_t>(cout) * es) % 16 == 0 && cout >= group_ch &&
         (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
       const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)wo, (uint64_t)ho, (uint64_t)n};
       const uint64_t strides[3] = {(uint64_t)cout * es, (uint64_t)wo * cout * es, (uint64_t)ho * wo * cout * es};
@@ -1803,6 +1863,7 @@ static int launch_upconv(bool dgrad, const void* a, const void* wp, void* out, i
                          float* stats = nullptr) {
   IgemmParams p;
   p.stats = stats;
+  p.gate = nullptr; p.gate_act = 0;
   p.N = n; p.Ho = h; p.Wo = w; p.Cout = cn;
   p.taps = 4; p.kw = 2; p.stride = 1; p.pad_t = 0; p.pad_l = 0;
   p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1;
@@ -2002,6 +2063,7 @@ extern "C" int ganb_conv2d_igemm_tf32(const float* x, const float* wp, void* y, 
   p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
   pick_box(BM, ho, wo, &p.bw, &p.bh, &p.bn);
   p.stats = nullptr;
+  p.gate = nullptr; p.gate_act = 0;
   p.tiles_w = ceil_div(wo, p.bw);
   p.tiles_h = ceil_div(ho, p.bh);
   p.tiles_n = ceil_div(n, p.bn);

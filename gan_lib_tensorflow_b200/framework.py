@@ -38,12 +38,15 @@ _ALIGN = 64  # floats: every variable starts on a 256-byte boundary inside the f
 class Var:
     """A value on the tape: `data` is a device tensor, `grad` is filled by Tape.backward()."""
 
-    __slots__ = ("data", "grad", "requires_grad", "grad_dtype", "quad", "stats")
+    __slots__ = ("data", "grad", "requires_grad", "grad_dtype", "quad", "stats", "fused_act")
 
     def __init__(self, data: torch.Tensor, requires_grad: bool = False, grad_dtype=None):
         self.data = data
         self.quad = False   # storage is the quad layout of functional.upconv2d (value AND gradient)
         self.stats = None   # kernels.FusedStats left by the producing convolution's epilogue (functional.conv2d)
+        # activation that the producing convolution applied in its epilogue (functional.conv2d(act=...)): `grad` is then
+        # the gradient wrt the PRE-activation, which only a consumer that applies act' itself may deliver (accum(gated=True))
+        self.fused_act = None
         self.grad = None
         self.requires_grad = requires_grad
         self.grad_dtype = grad_dtype  # dtype producers should use for this value's gradient (None: fp32)
@@ -65,8 +68,11 @@ class Var:
     def dtype(self):
         return self.data.dtype
 
-    def accum(self, g: torch.Tensor) -> None:
+    def accum(self, g: torch.Tensor, gated: bool = False) -> None:
         """Adds a gradient contribution (takes ownership of `g` when it is the first one)."""
+        if (self.fused_act is not None) != gated:
+            raise RuntimeError("gradient of a value with an epilogue-fused activation must come from a consumer that "
+                               "applies the activation's derivative (functional.conv2d), and only from such a consumer")
         if self.grad is None:
             self.grad = g
         else:

@@ -198,6 +198,9 @@ def _pads(padding, h, w, kh, kw, stride):
 # us on the dominant layer), but inside the D+G pair schedule the separate statistics kernel runs for free next to the
 # other stream's tensor-core kernel while the longer epilogue holds the tensor pipe: 3.30 vs 3.20 ms per pair, same box
 # (profiles/r02_fused_stats_ab.txt).  Default therefore OFF; GANB_FUSED_STATS=1 turns it on.
+# relu / leaky relu between two convolutions without a normalisation in between (critic blocks) fused into the first
+# one's epilogue, its derivative into the second one's data-gradient epilogue (GANB_FUSED_ACT=0: separate passes)
+FUSED_CONV_ACT = __import__("os").environ.get("GANB_FUSED_ACT", "1") != "0"
 FUSED_BN_STATS = __import__("os").environ.get("GANB_FUSED_STATS", "0") == "1"
 
 
@@ -209,7 +212,7 @@ def _stat_groups(n: int, groups: int | None = None) -> int:
 
 def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: int = 1, padding: str = "SAME",
            sn=None, residual: Var | None = None, out_grad_dtype=None, in_scale: float | None = None,
-           residual_up2: bool = False, out_dtype=F32, bn_stats: bool = False) -> Var:
+           residual_up2: bool = False, out_dtype=F32, bn_stats: bool = False, act: str | None = None) -> Var:
     """NHWC x HWIO cross-correlation (tf.nn.conv2d, common/ops/conv2d.py:181-187) + bias (+ residual), fp32 out.
 
     `sn` is a framework.SNEntry whose 1/sigma multiplies the accumulator (W/sigma is never materialised).
@@ -223,11 +226,29 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
     through TMA element strides; the data gradient is the stride-1 kernel applied to the zero-dilated output
     gradient (correct for any TF padding; the structural zeros cost stride^2 more MMA work than necessary).
 
+    `act` ('relu' / 'lrelu'): the nonlinearity behind the layer is applied by the GEMM epilogue and only act(y) is stored
+    (bf16).  The returned Var is marked (`fused_act`): its gradient is the gradient wrt the PRE-activation, delivered by
+    the consuming conv2d, whose data-gradient epilogue multiplies by act' (read off the sign of its own input).  Used
+    where no normalisation sits between two convolutions (the critic's residual blocks): saves the activation pass and
+    its backward pass; bit-identical for relu (rounding to bf16 commutes with it).
+
     `bn_stats`: the output feeds a batch-statistics normalisation; where the kernel supports it the epilogue also leaves
     the per-tile column sums of y and y^2 (out.stats, consumed by norm_act instead of a separate pass over y)."""
     store = get_store()
     n, h, w, cin = x.shape
     cout = W.data.shape[-1]
+    gate_act = x.fused_act
+    if act is not None or gate_act is not None:
+        # the fused pair is built for the bf16 tensor-core routes only (callers ask conv2d_act_fusable first)
+        ok = act in (None, 'relu', 'lrelu') and FUSED_CONV_ACT and not store.is_tf32(W.root) and stride == 1
+        if act is not None:
+            ok = ok and out_dtype == BF16 and residual is None and not bn_stats and cout % 8 == 0 and \
+                (cin % 8 == 0 or (cin < 8 and small_k(kh * kw, cin) is not None))
+        if gate_act is not None:
+            ok = ok and x.data.dtype == BF16 and cin % 8 == 0 and cout >= 8
+        if not ok:
+            raise NotImplementedError(f"conv2d: fused activation act={act} / gated input {gate_act} on this route "
+                                      f"(cin={cin}, cout={cout}, stride={stride}, out {out_dtype})")
     if store.is_tf32(W.root):
         return _conv2d_tf32(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale, residual_up2,
                             out_dtype)
@@ -263,10 +284,10 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
         if route_in:
             xcol = K.im2col_small(xin.data, n, h, w, cin, ho, wo, kh, kw, pt, pl, +1, kp_in, stride=stride)
             y = K.conv_igemm(xcol, pack.ws, n, ho, wo, kp_in, ho, wo, cout, 1, 1, 0, 0, False, alpha, bias, res,
-                             None, out_dtype, residual_up2=residual_up2)
+                             act, out_dtype, residual_up2=residual_up2)
         else:
-            if res is not None:
-                raise NotImplementedError("residual on the CUDA-core small-channel path")
+            if res is not None or act is not None:
+                raise NotImplementedError("residual / fused activation on the CUDA-core small-channel path")
             y = K.conv_smallcin(xin.data, W.data, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, False, alpha,
                                 bias, None, F32)
     else:
@@ -279,9 +300,10 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                                           bias, res, None, out_dtype, g_stats, residual_up2=residual_up2, stride=stride)
         else:
             y = K.conv_igemm(xin.data, pack.wt, n, h, w, cin, ho, wo, cout, kh, kw, pt, pl, False, alpha, bias, res,
-                             None, out_dtype, residual_up2=residual_up2, stride=stride)
+                             act, out_dtype, residual_up2=residual_up2, stride=stride)
     out = Var(y, grad_dtype=out_grad_dtype)
     out.stats = fused
+    out.fused_act = act
     need_w = W.needs_grad and _tape() is not None
     need_b = b is not None and b.needs_grad and _tape() is not None
     if _rg(xin, residual) or need_w or need_b:
@@ -354,6 +376,9 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                     gy32 = gy if gy.dtype == F32 else K.cast(gy, F32)
                     dx = K.conv_smallcin(gy32, W.data, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl,
                                          True, True, alpha, None, None, gdt)
+                elif gate_act is not None:
+                    dx = K.conv_igemm_gated(gy16, pack.wn, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl,
+                                            True, alpha, xin.data, gate_act, gdt)
                 elif stride == 1:
                     dx = K.conv_igemm(gy16, pack.wn, n, ho, wo, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
                                       alpha, None, None, None, gdt)
@@ -362,9 +387,20 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
                     gyd = K.dilate2d(gy16, stride, hd, wd)
                     dx = K.conv_igemm(gyd, pack.wn, n, hd, wd, cout, h, w, cin, kh, kw, kh - 1 - pt, kw - 1 - pl, True,
                                       alpha, None, None, None, gdt)
-                xin.accum(dx)
+                xin.accum(dx, gated=gate_act is not None)
         tape.record(bwd)
     return out
+
+
+def conv2d_act_fusable(cin1: int, mid: int, cout2: int, k: int, stride: int = 1, root: str | None = None) -> bool:
+    """Can the activation between Conv1 (cin1 -> mid, k x k) and Conv2 (mid -> cout2), both stride-1 plain convolutions of
+    the network being built, be fused into Conv1's epilogue and Conv2's data-gradient epilogue (conv2d(act=...))?  Both
+    must take the bf16 tensor-core routes: Conv1 the TMA route or the im2col route of an RGB-sided layer, Conv2 the
+    TMA route."""
+    if not FUSED_CONV_ACT or get_store().is_tf32(root) or stride != 1:
+        return False
+    producer = cin1 % 8 == 0 or (cin1 < 8 and small_k(k * k, cin1) is not None)
+    return producer and mid % 8 == 0 and mid >= 8 and cout2 >= 8
 
 
 def _conv2d_tf32(x, W, b, kh, kw, stride, padding, sn, residual, out_grad_dtype, in_scale, residual_up2, out_dtype):

@@ -111,6 +111,17 @@ def conv_igemm(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, al
     return y
 
 
+def conv_igemm_gated(x, wp, n, h, w, cin, ho, wo, cout, kh, kw, pad_t, pad_l, flip, alpha, gate, gate_act, out_dtype):
+    """conv_igemm whose result is multiplied by act'(pre), read off gate = act(pre) (bf16, shape of the output): the data
+    gradient through an activation that the producer of the layer's input fused into its epilogue."""
+    assert gate.dtype == torch.bfloat16 and tuple(gate.shape) == (n, ho, wo, cout), (gate.dtype, gate.shape)
+    y = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
+    check(L().ganb_conv2d_igemm_gated(ptr(x), ptr(wp), ptr(y), n, h, w, cin, ho, wo, cout, kh, kw, 1, pad_t, pad_l,
+                                      int(flip), ptr(alpha), ptr(gate), act_code(gate_act),
+                                      BF16 if out_dtype == torch.bfloat16 else F32, _stream()), "ganb_conv2d_igemm_gated")
+    return y
+
+
 class FusedStats:
     """Per-tile column sums (y, y^2) left by a convolution epilogue for the batch norm behind the layer."""
 

@@ -72,6 +72,16 @@ int ganb_conv2d_igemm(const void* x_bf16, const void* wp_bf16, void* y, int n, i
                       int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
                       const float* alpha, const float* bias, const float* residual, int residual_up2, int act,
                       int out_dtype, void* stream);
+/* Data gradient THROUGH an activation that the producer of this layer's input applied in its own epilogue
+ * (ganb_conv2d_igemm with act != 0): the critic's residual blocks have no normalisation between Conv1 and Conv2
+ * (common/resnet_block.py:129-139 with Normalize = identity, SNGAN/gan_cifar_resnet.py:88-109), so
+ * nonlinearity(Conv1(.)) is stored once, by Conv1, and its derivative is applied here instead of by a pass of its own:
+ *     y = act'(pre) * alpha * sum x * wp      (same sum as ganb_conv2d_igemm; no bias / residual)
+ * gate_bf16 = act(pre), laid out like y ([n, ho, wo, cout] bf16); act'(pre) is read off its sign: relu 1 if gate > 0
+ * else 0, leaky relu 1 if gate >= 0 else 0.2.  Requirements of ganb_conv2d_igemm plus cout % 8 == 0. */
+int ganb_conv2d_igemm_gated(const void* x_bf16, const void* wp_bf16, void* y, int n, int h, int w, int cin, int ho,
+                            int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps,
+                            const float* alpha, const void* gate_bf16, int gate_act, int out_dtype, void* stream);
 /* Batch statistics fused into the convolution epilogue (the reference computes them with a separate tf.nn.moments over
  * the layer output, common/ops/normalization.py:29,47): the epilogue leaves, per 128-pixel output tile, the column sums
  * of the STORED output y and of y^2 (after alpha / bias / residual / activation and the rounding to out_dtype) in

@@ -38,6 +38,13 @@ def main():
     for it in range(5):
         run_pair()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(50):
+        run_pair()
+    e1.record()
+    torch.cuda.synchronize()
+    print("unprofiled: %.1f us per pair (50 replays)" % (e0.elapsed_time(e1) * 1e3 / 50))
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for it in range(3):
