@@ -1306,24 +1306,67 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
-// dw = beta*dw + scale * sum_s partial[s]
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int64_t n4,
-                                     int splits, const float* __restrict__ scale, float beta) {
+// dw = beta*dw + scale * sum_s partial[s].  A block owns 256 / G consecutive float4 outputs; its G thread groups take the
+// splits g, g + G, ... and their sums meet in shared memory in a fixed order (deterministic).  Small filters with many
+// splits (the RGB-side layers: 4096 outputs x 148 splits) were latency chains of `splits` dependent-issue loads per thread.
+template <int G>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                            int64_t n4, int splits, const float* __restrict__ scale,
+                                                            float beta) {
   pdl_wait();
+  constexpr int OUT = 256 / G;
+  __shared__ float4 sm[G > 1 ? G : 1][OUT];
+  const int o = threadIdx.x % OUT, g = threadIdx.x / OUT;
   const float sc = scale ? __ldg(scale) : 1.0f;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * OUT; base < n4; base += static_cast<int64_t>(gridDim.x) * OUT) {
+    const int64_t i = base + o;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + s * n4 + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (i < n4) {
+#pragma unroll 4
+      for (int s = g; s < splits; s += G) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + s * n4 + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
-    float4 o = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
-    if (beta != 0.f) {
-      const float4 d = reinterpret_cast<const float4*>(dw)[i];
-      o.x += beta * d.x; o.y += beta * d.y; o.z += beta * d.z; o.w += beta * d.w;
+    if (G > 1) {
+      sm[g][o] = acc;
+      __syncthreads();
+      if (g == 0) {
+#pragma unroll
+        for (int k = 1; k < G; ++k) {
+          const float4 v = sm[k][o];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
     }
-    reinterpret_cast<float4*>(dw)[i] = o;
+    if (g == 0 && i < n4) {
+      float4 r = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+      if (beta != 0.f) {
+        const float4 d = reinterpret_cast<const float4*>(dw)[i];
+        r.x += beta * d.x; r.y += beta * d.y; r.z += beta * d.z; r.w += beta * d.w;
+      }
+      reinterpret_cast<float4*>(dw)[i] = r;
+    }
+    if (G > 1) __syncthreads();
+  }
+}
+
+static cudaError_t launch_splitk_reduce(const float* partial, float* dw, int64_t n4, int splits, const float* scale,
+                                        float beta, cudaStream_t stream) {
+  // enough thread groups per output to put ~2 blocks on every SM, never more groups than splits
+  const int64_t want = 2LL * sm_count() * 256;
+  int g = 1;
+  while (g < 32 && n4 * g * 2 <= want && g * 2 <= splits) g *= 2;
+  if (g == 2) g = 1;
+  if (g == 16) g = 8;
+  const int out = 256 / g;
+  int blocks = static_cast<int>(ceil_div64(n4, out));
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  switch (g) {
+    case 32: return launch_k(splitk_reduce_kernel<32>, blocks, 256, 0, stream, partial, dw, n4, splits, scale, beta);
+    case 8: return launch_k(splitk_reduce_kernel<8>, blocks, 256, 0, stream, partial, dw, n4, splits, scale, beta);
+    case 4: return launch_k(splitk_reduce_kernel<4>, blocks, 256, 0, stream, partial, dw, n4, splits, scale, beta);
+    default: return launch_k(splitk_reduce_kernel<1>, blocks, 256, 0, stream, partial, dw, n4, splits, scale, beta);
   }
 }
 
@@ -1765,9 +1808,7 @@ extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void*
   if (rc) return rc;
   const int64_t total = static_cast<int64_t>(kh) * kw * cin * cout;
   const int64_t n4 = total / 4;  // cout % 8 == 0
-  int blocks = static_cast<int>(ceil_div64(n4, 256));
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  launch_k(splitk_reduce_kernel, blocks, 256, 0, stream, p.partial, dw, n4, p.splits, scale, beta);
+  launch_splitk_reduce(p.partial, dw, n4, p.splits, scale, beta, stream);
   GANB_CHECK_LAUNCH("splitk_reduce_kernel");
   return 0;
 }
@@ -2140,9 +2181,7 @@ extern "C" int ganb_conv2d_wgrad_tf32(const float* x, const float* dy, float* dw
   else rc = launch_wgrad_tf32<128, 3>(tmX, tmDY, p, plan.grid, stream);
   if (rc) return rc;
   const int64_t n4 = static_cast<int64_t>(kh) * kw * cin * cout / 4;
-  int blocks = static_cast<int>(ceil_div64(n4, 256));
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  launch_k(splitk_reduce_kernel, blocks, 256, 0, stream, p.partial, dw, n4, p.splits, scale, beta);
+  launch_splitk_reduce(p.partial, dw, n4, p.splits, scale, beta, stream);
   GANB_CHECK_LAUNCH("splitk_reduce_kernel");
   return 0;
 }

@@ -162,11 +162,14 @@ class DerivedWeight(Variable):
 
 
 SIDE_STREAM = os.environ.get("GANB_SIDE_STREAM", "1") != "0"
+# bias gradients on a side stream of their own (lane 1): measured SLOWER (3.14 vs 3.06-3.11 ms per pair: the extra
+# concurrency takes bandwidth from the data-gradient chain), so they stay queued behind the filter gradients; opt-in
+BIAS_LANE = os.environ.get("GANB_BIAS_LANE", "0") == "1"
 _side_streams = {}
 
 
-def _side_stream(device) -> "torch.cuda.Stream":
-    key = torch.device(device).index or 0
+def _side_stream(device, lane: int = 0) -> "torch.cuda.Stream":
+    key = (torch.device(device).index or 0, lane)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=device)
     return _side_streams[key]
@@ -198,7 +201,7 @@ class Tape:
         self.pending_sn = OrderedDict()  # root -> list of SN entries whose G buffer has been written
         self.pending_derived = []        # DerivedWeight instances used on this tape (weight-norm / masks)
         self.keep = []       # temporaries read by side-stream launches: kept alive until the join
-        self._forked = False
+        self._forked = set()   # side-stream lanes with work in flight
         self.token = 0       # identity of this tape for the spectral-norm evaluation bookkeeping (VariableStore)
         self.sn_gen = {}     # root -> index of the spectral-norm state set in use on this tape
         self.node_stream = {}   # node index -> stream of the branch it was recorded in
@@ -242,23 +245,28 @@ class Tape:
                 main.wait_stream(s)
 
     @contextlib.contextmanager
-    def offchain(self):
-        """Launches issued inside run on the side stream, ordered after everything queued on the current stream."""
+    def offchain(self, lane: int = 0):
+        """Launches issued inside run on a side stream, ordered after everything queued on the current stream.
+        lane 0: filter gradients (tensor-core kernels + their split reductions); lane 1: bias gradients (small
+        bandwidth-bound column sums, which would otherwise queue between the filter-gradient kernels of lane 0)."""
         if not SIDE_STREAM or K.host_logic_only():
             yield
             return
+        if lane and not BIAS_LANE:
+            lane = 0
         main = torch.cuda.current_stream()
-        side = _side_stream(main.device)
+        side = _side_stream(main.device, lane)
         side.wait_stream(main)
-        self._forked = True
+        self._forked.add(lane)
         with torch.cuda.stream(side):
             yield
 
     def join(self) -> None:
         if self._forked:
             main = torch.cuda.current_stream()
-            main.wait_stream(_side_stream(main.device))
-            self._forked = False
+            for lane in sorted(self._forked):
+                main.wait_stream(_side_stream(main.device, lane))
+            self._forked.clear()
         self.keep.clear()
 
     def backward(self, loss: Var, grad: torch.Tensor | None = None) -> None:

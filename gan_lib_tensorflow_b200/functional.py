@@ -362,11 +362,12 @@ def conv2d(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, stride: in
             # ---- off the critical chain: bias and filter gradients (side stream; joined at the end of backward)
             if need_b or need_w:
                 tape.keep.extend(t for t in (gy, gy16, dycol) if t is not None)
-                with tape.offchain():
-                    if need_b:
-                        K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
-                    if need_w:
+                if need_w:
+                    with tape.offchain():
                         _conv_wgrad()
+                if need_b:
+                    with tape.offchain(1):
+                        K.colsum(gy, n * ho * wo, cout, b.grad, 1.0)
             if need_x:
                 gdt = xin.gdtype
                 if route_out:
@@ -600,11 +601,12 @@ def upconv2d(x: Var, W: Variable, b: Variable | None, out_grad_dtype=None, out_d
             gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
             if need_b or need_w:
                 tape.keep.extend((gy, gy16))
-                with tape.offchain():
-                    if need_b:
-                        K.colsum(gy, n * 4 * h * w, cout, b.grad, 1.0)
-                    if need_w:
+                if need_w:
+                    with tape.offchain():
                         K.upconv_wgrad(xin.data, gy16, W.grad, n, h, w, cin, cout, None, 1.0)
+                if need_b:
+                    with tape.offchain(1):
+                        K.colsum(gy, n * 4 * h * w, cout, b.grad, 1.0)
             if xin.requires_grad:
                 xin.accum(K.upconv_dgrad(gy16, pack.we_n, n, h, w, cin, cout, None, xin.gdtype))
         tape.record(bwd)
@@ -713,12 +715,13 @@ def conv2d_transpose(x: Var, W: Variable, b: Variable | None, kh: int, kw: int, 
             gy16 = gy if gy.dtype == BF16 else K.cast(gy, BF16)
             if need_b or need_w:
                 tape.keep.extend((gy, gy16))
-                with tape.offchain():
-                    if need_b:
-                        K.colsum(gy, n * oh * ow, cout, b.grad, 1.0)
-                    if need_w:   # filter gradient of the forward conv: "input" = gy (cout channels), "dy" = x
+                if need_w:   # filter gradient of the forward conv: "input" = gy (cout channels), "dy" = x
+                    with tape.offchain():
                         K.conv_wgrad(gy16, xin.data, W.grad, n, oh, ow, cout, h, w, cin, kh, kw, pt, pl, None, 1.0,
                                      stride=stride)
+                if need_b:
+                    with tape.offchain(1):
+                        K.colsum(gy, n * oh * ow, cout, b.grad, 1.0)
             if xin.requires_grad:
                 dx = K.conv_igemm(gy16, pack.wt, n, oh, ow, cout, h, w, cin, kh, kw, pt, pl, False, None, None, None,
                                   None, xin.gdtype, stride=stride)

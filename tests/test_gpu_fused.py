@@ -121,3 +121,79 @@ def test_generator_with_fused_statistics_matches_the_separate_pass():
     assert n1 == n0 - 6                                 # six bn_stats_partial launches fewer per generator pass
     assert abs(l0 - l1) < 1e-3 * max(1.0, abs(l0))
     assert float((g0 - g1).norm() / g0.norm()) < 2e-2   # bf16 rounding flips downstream of 1e-6 moment differences
+
+
+# ------------------------------------------------------------------------------------------------ activation fused into a conv pair
+@pytest.mark.parametrize("n,h,cin,cout,k,act,out_dtype", [
+    (128, 32, 128, 128, 3, "relu", BF16),      # conv_pair_kernel<128>: D.Block.1.Conv2's data gradient
+    (64, 16, 128, 256, 3, "relu", BF16),       # 256-wide output (label-map block of the critic)
+    (128, 8, 128, 128, 3, "relu", BF16),       # per-tap igemm, 64-wide tiles
+    (16, 8, 64, 72, 3, "lrelu", BF16),         # partial channel tile, leaky relu
+    (8, 16, 32, 128, 1, "lrelu", F32),         # 1x1 filter (shallow-K route), fp32 output
+])
+def test_gated_data_gradient_equals_gradient_times_activation_derivative(n, h, cin, cout, k, act, out_dtype):
+    """ganb_conv2d_igemm_gated(dy, W, gate) == ganb_conv2d_igemm(dy, W) * act'(pre), act' read off gate = act(pre)."""
+    from gan_lib_tensorflow_b200 import kernels as K
+
+    x, wt, _ = _operands(n, h, h, cin, cout, k, seed=3 * n + h)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    pre = torch.randn(n, h, h, cout, device="cuda", generator=g)
+    pre[0, 0, 0, :8] = 0.0                                    # exact zeros: relu'(0) = 0, lrelu'(0) = 1
+    pre[0, 0, 1, :8] = -0.0
+    gate = (torch.relu(pre) if act == "relu" else torch.where(pre >= 0, pre, 0.2 * pre)).to(BF16)
+    pad = k // 2
+    plain = K.conv_igemm(x, wt, n, h, h, cin, h, h, cout, k, k, pad, pad, True, None, None, None, None, F32)
+    gated = K.conv_igemm_gated(x, wt, n, h, h, cin, h, h, cout, k, k, pad, pad, True, None, gate, act, out_dtype)
+    torch.cuda.synchronize()
+    gf = gate.float()
+    if act == "relu":
+        want = torch.where(gf > 0, plain, torch.zeros_like(plain))
+    else:
+        want = torch.where(gf >= 0, plain, 0.2 * plain)
+    assert torch.equal(gated, want.to(out_dtype))
+
+
+@pytest.mark.parametrize("resample,cin,cout,h", [(None, 128, 128, 8), ("down", 256, 128, 16), ("first", 3, 128, 32)])
+def test_fused_block_activation_is_bit_identical_to_separate_passes(resample, cin, cout, h):
+    """A critic residual block with the Conv1 -> relu -> Conv2 activation fused into the two epilogues gives the same
+    bits (output, input gradient, every parameter gradient) as with the separate activation passes."""
+    from gan_lib_tensorflow_b200 import framework, functional as F
+    from gan_lib_tensorflow_b200.common import resnet_block as rb
+
+    def run(fused):
+        old = F.FUSED_CONV_ACT
+        F.FUSED_CONV_ACT = fused
+        try:
+            framework.reset_default_graph("cuda")
+            store = framework.get_store()
+            np.random.seed(5)
+            xs = torch.from_numpy(np.random.RandomState(1).randn(32, h, h, cin).astype("float32")).cuda()
+            launches = {}
+            with store.variable_scope("Discriminator"):
+                with store.gradient_tape() as tape:
+                    x = F.Var(xs, requires_grad=True)
+                    from gan_lib_tensorflow_b200 import kernels as K
+                    before = K.launch_count()
+                    if resample == "first":
+                        y = rb.OptimizedResBlockDisc1(x, DIM_D=cout, spectral_normed=True, name_prefix="D.Block.1")
+                    else:
+                        y = rb.ResidualBlock(x, cin, cout, 3, "D.Block", spectral_normed=True, resample=resample)
+                    for v in store.vars.values():
+                        if v.trainable and v.grad is None:
+                            v.grad = torch.zeros_like(v.data)
+                    cot = torch.from_numpy(np.random.RandomState(2).randn(*y.shape).astype("float32")).cuda()
+                    tape.backward(y, grad=cot.to(y.gdtype))
+                    launches["n"] = K.launch_count() - before
+            torch.cuda.synchronize()
+            grads = {k: v.grad.clone() for k, v in store.vars.items() if v.trainable}
+            return y.data.clone(), x.grad.clone(), grads, launches["n"]
+        finally:
+            F.FUSED_CONV_ACT = old
+
+    y1, dx1, g1, n1 = run(True)
+    y0, dx0, g0, n0 = run(False)
+    assert n1 == n0 - 2                       # one forward and one backward pass fewer
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    assert g1.keys() == g0.keys() and len(g1) >= 4
+    for k in g1:
+        assert torch.equal(g1[k], g0[k]), k
