@@ -46,11 +46,11 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.stop_flag = threading.Event()
-        self.sm, self.sm_max, self.reasons = [], [], set()
+        self.sm, self.sm_max, self.power, self.reasons = [], [], [], set()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag.is_set():
             try:
@@ -63,6 +63,11 @@ class ClockSampler(threading.Thread):
                     for nm, val in zip(names, parts[2:6]):
                         if val.lower().startswith("active"):
                             self.reasons.add(nm)
+                    if len(parts) >= 7:
+                        try:
+                            self.power.append(float(parts[6]))
+                        except ValueError:
+                            pass
             except Exception:  # noqa: BLE001
                 pass
             self.stop_flag.wait(0.2)
@@ -71,8 +76,11 @@ class ClockSampler(threading.Thread):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         s = sorted(self.sm)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": max(self.sm_max), "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2], "sm_max_mhz": max(self.sm_max), "reasons": sorted(self.reasons),
+               "samples": len(s), "sm_mhz_min": s[0]}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm

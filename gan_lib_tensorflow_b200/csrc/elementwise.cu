@@ -7,6 +7,8 @@
 // mean-pool, nearest upsample), SNGAN/gan_cifar_resnet.py:282-284,301,334-337,376-378,492,521-526.
 #include "host_common.h"
 
+#include <stdlib.h>
+
 #include <cuda_bf16.h>
 
 namespace ganb {
@@ -416,6 +418,93 @@ norm_act_bwd_scatter_kernel(const float* __restrict__ sums, int n, int c, int n_
   if (lane == 0) {
     dbeta[i] += a;
     dgamma[i] += b;
+  }
+}
+
+// Stages 1 + 2 in one launch for the training shapes (n <= 256 samples, label tables of <= 32 rows): one block per 16
+// channels keeps the per-sample sums of ALL samples in shared memory, so the group sums and the label scatter follow
+// without a second pass through global memory, and every load of the chunk partials is a coalesced float4 (the two-kernel
+// form reads them 4 bytes per lane with a sample stride: 11 + 4 us per normalisation on the critical chain of the
+// generator's backward pass, 7 of them per step).  Fixed summation orders (deterministic).
+// threads: 4 float4 columns x 64 sample lanes.  dynamic shared memory: A[n][16] | B[n][16] | red1[64][4] f4 | red2 | labels[n]
+__global__ void __launch_bounds__(256)
+norm_act_bwd_finalize_fused_kernel(const float* __restrict__ part, int n, int c, int chunks, int groups,
+                                   const float* __restrict__ gamma, const int* __restrict__ labels, int rows,
+                                   float* __restrict__ sums, float* __restrict__ s1, float* __restrict__ s2,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait();
+  extern __shared__ __align__(16) float fsm[];
+  float* smA = fsm;
+  float* smB = smA + static_cast<size_t>(n) * 16;
+  float4* red1 = reinterpret_cast<float4*>(smB + static_cast<size_t>(n) * 16);
+  float4* red2 = red1 + 256;
+  int* lab = reinterpret_cast<int*>(red2 + 256);
+  const int col = threadIdx.x & 3, lane = threadIdx.x >> 2;
+  const int ch = blockIdx.x * 16 + col * 4;
+  const bool ch_ok = ch < c;                       // c % 4 == 0: a float4 column is inside or outside as a whole
+  for (int i = threadIdx.x; i < n; i += 256) lab[i] = labels ? __ldg(labels + i) : 0;
+  __syncthreads();
+  const int npg = n / groups;
+  for (int g = 0; g < groups; ++g) {
+    float4 acc1 = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc1;
+    for (int ni = g * npg + lane; ni < (g + 1) * npg; ni += 64) {
+      float4 ga = make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (ch_ok) {
+        if (gamma) ga = __ldg(reinterpret_cast<const float4*>(gamma + static_cast<int64_t>(lab[ni]) * c + ch));
+#pragma unroll 4
+        for (int k = 0; k < chunks; ++k) {
+          const float* q = part + (static_cast<int64_t>(ni) * chunks + k) * 2 * c + ch;
+          const float4 va = __ldg(reinterpret_cast<const float4*>(q));
+          const float4 vb = __ldg(reinterpret_cast<const float4*>(q + c));
+          a.x += va.x; a.y += va.y; a.z += va.z; a.w += va.w;
+          b.x += vb.x; b.y += vb.y; b.z += vb.z; b.w += vb.w;
+        }
+        st4(sums + (static_cast<int64_t>(ni) * 2) * c + ch, a);
+        st4(sums + (static_cast<int64_t>(ni) * 2 + 1) * c + ch, b);
+      }
+      st4(smA + ni * 16 + col * 4, a);
+      st4(smB + ni * 16 + col * 4, b);
+      acc1.x += ga.x * a.x; acc1.y += ga.y * a.y; acc1.z += ga.z * a.z; acc1.w += ga.w * a.w;
+      acc2.x += ga.x * b.x; acc2.y += ga.y * b.y; acc2.z += ga.z * b.z; acc2.w += ga.w * b.w;
+    }
+    red1[threadIdx.x] = acc1;     // index = lane * 4 + col
+    red2[threadIdx.x] = acc2;
+    __syncthreads();
+#pragma unroll
+    for (int s = 32; s > 0; s >>= 1) {
+      if (lane < s) {
+        const float4 u = red1[threadIdx.x + s * 4], v = red2[threadIdx.x + s * 4];
+        float4 x = red1[threadIdx.x], y = red2[threadIdx.x];
+        x.x += u.x; x.y += u.y; x.z += u.z; x.w += u.w;
+        y.x += v.x; y.y += v.y; y.z += v.z; y.w += v.w;
+        red1[threadIdx.x] = x;
+        red2[threadIdx.x] = y;
+      }
+      __syncthreads();
+    }
+    if (lane == 0 && ch_ok) {
+      st4(s1 + static_cast<int64_t>(g) * c + ch, red1[col]);
+      st4(s2 + static_cast<int64_t>(g) * c + ch, red2[col]);
+    }
+    __syncthreads();
+  }
+  if (dgamma) {
+    // dgamma[row, ch] += sum_{n: label_n == row} B_n, dbeta with A_n: samples in ascending order
+    for (int i = threadIdx.x; i < rows * 16; i += 256) {
+      const int row = i >> 4, cc = i & 15;
+      const int ch2 = blockIdx.x * 16 + cc;
+      if (ch2 >= c) continue;
+      float a = 0.f, b = 0.f;
+      for (int ni = 0; ni < n; ++ni) {
+        if (lab[ni] == row) {
+          a += smA[ni * 16 + cc];
+          b += smB[ni * 16 + cc];
+        }
+      }
+      dbeta[static_cast<int64_t>(row) * c + ch2] += a;
+      dgamma[static_cast<int64_t>(row) * c + ch2] += b;
+    }
   }
 }
 
@@ -1789,13 +1878,22 @@ static int norm_act_bwd_impl(const void* x, int x_dtype, const void* dz, int dz_
       else if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
       else launch_bwd_reduce<float>(p, grid, STREAM);
       GANB_CHECK_LAUNCH("norm_act_bwd_reduce_kernel");
-      launch_k(norm_act_bwd_finalize_kernel, dim3(ceil_div(c, 8), groups), 256, 0, STREAM, p.part, n, c, p.chunks, groups, gamma,
-                                                                                    labels, sums, s1, s2);
-      GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
-      if (gamma && dgamma && dbeta) {
-        const int rows = (labels && n_rows > 0) ? n_rows : 1;
-        launch_k(norm_act_bwd_scatter_kernel, ceil_div(rows * c, 8), 256, 0, STREAM, sums, n, c, rows, labels, dgamma, dbeta);
-        GANB_CHECK_LAUNCH("norm_act_bwd_scatter_kernel");
+      const bool scatter = gamma && dgamma && dbeta;
+      const int rows = (labels && n_rows > 0) ? n_rows : 1;
+      static const bool fused_ok = !(getenv("GANB_BN_BWD_FUSED") && getenv("GANB_BN_BWD_FUSED")[0] == '0');   // A/B switch
+      if (fused_ok && n <= 256 && rows <= 32) {
+        const size_t smem = static_cast<size_t>(n) * 128 + 2 * 256 * 16 + static_cast<size_t>(n) * 4;
+        launch_k(norm_act_bwd_finalize_fused_kernel, ceil_div(c, 16), 256, smem, STREAM, p.part, n, c, p.chunks, groups,
+                 gamma, labels, rows, sums, s1, s2, scatter ? dgamma : nullptr, scatter ? dbeta : nullptr);
+        GANB_CHECK_LAUNCH("norm_act_bwd_finalize_fused_kernel");
+      } else {
+        launch_k(norm_act_bwd_finalize_kernel, dim3(ceil_div(c, 8), groups), 256, 0, STREAM, p.part, n, c, p.chunks, groups,
+                 gamma, labels, sums, s1, s2);
+        GANB_CHECK_LAUNCH("norm_act_bwd_finalize_kernel");
+        if (scatter) {
+          launch_k(norm_act_bwd_scatter_kernel, ceil_div(rows * c, 8), 256, 0, STREAM, sums, n, c, rows, labels, dgamma, dbeta);
+          GANB_CHECK_LAUNCH("norm_act_bwd_scatter_kernel");
+        }
       }
     }
     p.s1 = s1; p.s2 = s2;

@@ -277,36 +277,68 @@ __global__ void __launch_bounds__(SN_THREADS) sn_bwd_apply_kernel(const ganb_sn_
 }
 
 // ------------------------------------------------------------------------------------------------ pack
+// One block per 64 x 64 (ci x co) tile of one tap: fp32 rows in (256 bytes per warp), bf16 rows out -- 128 bytes per warp for
+// both copies (the 32 x 32 tiles of the first version wrote 64-byte rows: 28 us for the generator's 6 M parameters, a serial
+// tail of every step).
+constexpr int PACK_TILE = 64;
 __global__ void __launch_bounds__(256) pack_weights_kernel(const ganb_pack_layer* __restrict__ layers, int nlayers) {
   pdl_wait();
-  __shared__ float tile[32][33];
+  __shared__ float tile[PACK_TILE][PACK_TILE + 1];
   int l = 0;
   while (l + 1 < nlayers && static_cast<int>(blockIdx.x) >= layers[l + 1].tile_begin) ++l;
   const ganb_pack_layer L = layers[l];
   int local = blockIdx.x - L.tile_begin;
-  const int tiles_co = (L.co + 31) / 32, tiles_ci = (L.ci + 31) / 32;
+  const int tiles_co = (L.co + PACK_TILE - 1) / PACK_TILE, tiles_ci = (L.ci + PACK_TILE - 1) / PACK_TILE;
   const int tco = local % tiles_co; local /= tiles_co;
   const int tci = local % tiles_ci; local /= tiles_ci;
   const int tap = local;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8: a thread owns two adjacent columns
   const int cip = L.ci_pad > L.ci ? L.ci_pad : L.ci;   // channel count of the operand copies (zero rows beyond ci)
   const float* w = L.w + static_cast<int64_t>(tap) * L.ci * L.co;
   __nv_bfloat16* wn = L.wn ? static_cast<__nv_bfloat16*>(L.wn) + static_cast<int64_t>(tap) * cip * L.co : nullptr;
   __nv_bfloat16* wt = L.wt ? static_cast<__nv_bfloat16*>(L.wt) + static_cast<int64_t>(tap) * cip * L.co : nullptr;
-  for (int j = ty; j < 32; j += 8) {
-    const int ci = tci * 32 + j, co = tco * 32 + tx;
-    float v = 0.f;
-    if (ci < L.ci && co < L.co) {
-      v = w[static_cast<int64_t>(ci) * L.co + co];
-      if (wn) wn[static_cast<int64_t>(ci) * L.co + co] = __float2bfloat16_rn(v);
+  const bool co_even = (L.co & 1) == 0, ci_even = (cip & 1) == 0;
+  const bool w_al8 = (reinterpret_cast<uintptr_t>(L.w) & 7) == 0;
+  for (int j = ty; j < PACK_TILE; j += 8) {
+    const int ci = tci * PACK_TILE + j, co = tco * PACK_TILE + 2 * tx;
+    float v0 = 0.f, v1 = 0.f;
+    if (ci < L.ci) {
+      const float* src = w + static_cast<int64_t>(ci) * L.co + co;
+      if (co_even && co + 1 < L.co) {
+        if (w_al8) {      // (a filter is a slice of its network's flat parameter buffer: 4-byte alignment only is guaranteed)
+          const float2 v = *reinterpret_cast<const float2*>(src);
+          v0 = v.x; v1 = v.y;
+        } else {
+          v0 = src[0]; v1 = src[1];
+        }
+        if (wn) *reinterpret_cast<__nv_bfloat162*>(wn + static_cast<int64_t>(ci) * L.co + co) = __floats2bfloat162_rn(v0, v1);
+      } else {
+        if (co < L.co) {
+          v0 = src[0];
+          if (wn) wn[static_cast<int64_t>(ci) * L.co + co] = __float2bfloat16_rn(v0);
+        }
+        if (co + 1 < L.co) {
+          v1 = src[1];
+          if (wn) wn[static_cast<int64_t>(ci) * L.co + co + 1] = __float2bfloat16_rn(v1);
+        }
+      }
     }
-    tile[j][tx] = v;
+    tile[j][2 * tx] = v0;
+    tile[j][2 * tx + 1] = v1;
   }
   __syncthreads();
   if (wt) {
-    for (int j = ty; j < 32; j += 8) {
-      const int co = tco * 32 + j, ci = tci * 32 + tx;
-      if (ci < L.ci && co < L.co) wt[static_cast<int64_t>(co) * cip + ci] = __float2bfloat16_rn(tile[tx][j]);
+    for (int j = ty; j < PACK_TILE; j += 8) {
+      const int co = tco * PACK_TILE + j, ci = tci * PACK_TILE + 2 * tx;
+      if (co >= L.co) continue;
+      __nv_bfloat16* dst = wt + static_cast<int64_t>(co) * cip + ci;
+      const float v0 = tile[2 * tx][j], v1 = tile[2 * tx + 1][j];
+      if (ci_even && ci + 1 < L.ci) {
+        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(v0, v1);
+      } else {
+        if (ci < L.ci) dst[0] = __float2bfloat16_rn(v0);
+        if (ci + 1 < L.ci) dst[1] = __float2bfloat16_rn(v1);
+      }
     }
   }
 }

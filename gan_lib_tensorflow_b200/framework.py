@@ -535,7 +535,7 @@ class PackGroup:
             for e in entries:
                 items.append(K.PackLayerStruct(e.w.data.data_ptr(), e.wn.data_ptr(), e.wt.data_ptr(), e.taps, e.ci,
                                                e.co, tiles, e.ci_pad, 0))
-                tiles += e.taps * (-(-e.ci // 32)) * (-(-e.co // 32))
+                tiles += e.taps * (-(-e.ci // 64)) * (-(-e.co // 64))     # ganb_pack_layer.tile_begin
             self.table = K.struct_array_to_device(items, entries[0].w.data.device)
             self.total_tiles = tiles
             self.table_ptrs = self._ptrs()

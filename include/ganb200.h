@@ -209,7 +209,7 @@ int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, float* dw_hw
  * (either may be NULL).  ci_pad >= ci (0 = ci) is the input-channel count of the operand copies: rows / columns
  * ci..ci_pad-1 are left untouched (the caller zeroes them once), so that a filter with ci % 8 != 0 (the 513-channel
  * convolution behind minibatch_std, PGGAN/model_nvidia.py:223-229) meets the 16-byte rows of the TMA path.
- * tile_begin = prefix sum of taps*ceil(ci/32)*ceil(co/32) over the layers. */
+ * tile_begin = prefix sum of taps*ceil(ci/64)*ceil(co/64) over the layers (one block per 64 x 64 tile of a tap). */
 typedef struct ganb_pack_layer {
   const float* w;
   void* wn;
