@@ -25,6 +25,7 @@ from ..common.ops import linear as linear_ops
 from ..training import AdamState  # noqa: F401  (tf.train.AdamOptimizer over a network's flat buffers)
 from ..framework import Var, get_store
 from ..framework import aux_stream as framework_aux_stream
+from ..framework import _side_stream as framework_side_stream
 
 BATCH_SIZE = 64  # Critic batch size
 GEN_BS_MULTIPLE = 2  # Generator batch size, as a multiple of BATCH_SIZE
@@ -50,6 +51,16 @@ SPLIT_CRITIC_PASS = os.environ.get("GANB_SPLIT_CRITIC", "0") == "1"
 # where the generator step's G forward forks off in the pair schedule: "early" = next to the critic step's own generator
 # pass, "late" = behind it, next to the critic's forward + backward (A/B: profiles/r02_pair_fork_ab.txt)
 PAIR_FORK = os.environ.get("GANB_PAIR_FORK", "early")
+# SM budgets (data-gradient chain, filter-gradient side stream) of the critic's backward pass; "0:0" = every kernel may take
+# the whole GPU (framework.Tape.sm_split)
+CRITIC_BWD_SPLIT = tuple(int(v) for v in os.environ.get("GANB_CRITIC_BWD_SPLIT", "0:0").split(":"))
+if not any(CRITIC_BWD_SPLIT):
+    CRITIC_BWD_SPLIT = None
+# critic power iteration on a side stream next to the generator pass instead of heading the critic chain: no measurable
+# change (3.07 vs 3.07 ms per pair), opt-in
+PREFETCH_SN = os.environ.get("GANB_PREFETCH_SN", "0") == "1"
+# late fork only: SMs for the tensor-core kernels of (generator forward on the aux stream, critic step), "0:0" = no limits
+SM_SPLIT = tuple(int(v) for v in os.environ.get("GANB_SM_SPLIT", "0:0").split(":"))
 
 BF16 = torch.bfloat16
 
@@ -232,10 +243,23 @@ class Trainer:
         st = self.store
         b = self.batch
         st.zero_grad('Discriminator')
+        # the critic's power iteration only reads its weights and u: it runs on the side stream next to the generator pass
+        # below instead of heading the critic's own chain of small kernels (~35 us of sn_fwd_* per step)
+        sn_side = None
+        group = st.sn_groups.get('Discriminator')
+        if PREFETCH_SN and group is not None and not K.host_logic_only():
+            main = torch.cuda.current_stream()
+            sn_side = framework_side_stream(main.device, 2)
+            sn_side.wait_stream(main)
+            with torch.cuda.stream(sn_side):
+                if not group.prefetch(True):
+                    sn_side = None
         with st.stat_towers(self.n_towers):
             fake = self.generator(b, self.real_labels, noise=self.z_d, reuse=True)  # no tape: var_list = disc_params
         if after_fake is not None:
             after_fake()
+        if sn_side is not None:
+            torch.cuda.current_stream().wait_stream(sn_side)
         real = self._preprocess_real(b)
         self.d_in[:b].copy_(real)
         self.d_in[b:].copy_(fake.data)
@@ -244,6 +268,7 @@ class Trainer:
         with st.gradient_tape() as tape, st.frozen_scopes('Generator'):
             disc_all, _ = self.discriminator(Var(self.d_in), self.d_labels, update_collection=None, reuse=True)
             loss = F.gan_loss(disc_all, 'hinge_d', n_real=b)
+            tape.sm_split = CRITIC_BWD_SPLIT
             tape.backward(loss)
         self.d_loss.copy_(loss.data)
         self._wire_out('Discriminator')
@@ -365,13 +390,20 @@ class Trainer:
 
         def g_forward_on_aux():
             aux.wait_stream(main)
-            with torch.cuda.stream(aux):
+            with torch.cuda.stream(aux), K.sm_limit(SM_SPLIT[0] if PAIR_FORK == "late" else 0):
                 st.zero_grad('Generator')
                 out.append(self._g_forward(tape))
+            if PAIR_FORK == "late":
+                limit[0] = K.L().ganb_set_sm_limit(SM_SPLIT[1])     # the critic's kernels from here on
+        limit = [None]
         if PAIR_FORK == "late":
             # the aux pass starts behind the (no-gradient) generator pass of the critic step: G's tensor-bound forward
             # then runs next to the critic's forward + backward, a chain of small latency-bound kernels
-            self._d_compute(after_fake=g_forward_on_aux)
+            try:
+                self._d_compute(after_fake=g_forward_on_aux)
+            finally:
+                if limit[0] is not None:
+                    K.L().ganb_set_sm_limit(limit[0])
         else:
             g_forward_on_aux()
             self._d_compute()

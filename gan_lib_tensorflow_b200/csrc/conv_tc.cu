@@ -1354,14 +1354,14 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 static cudaError_t launch_splitk_reduce(const float* partial, float* dw, int64_t n4, int splits, const float* scale,
                                         float beta, cudaStream_t stream) {
   // enough thread groups per output to put ~2 blocks on every SM, never more groups than splits
-  const int64_t want = 2LL * sm_count() * 256;
+  const int64_t want = 2LL * tc_sm_count() * 256;
   int g = 1;
   while (g < 32 && n4 * g * 2 <= want && g * 2 <= splits) g *= 2;
   if (g == 2) g = 1;
   if (g == 16) g = 8;
   const int out = 256 / g;
   int blocks = static_cast<int>(ceil_div64(n4, out));
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  if (blocks > 4 * tc_sm_count()) blocks = 4 * tc_sm_count();
   switch (g) {
     case 32: return launch_k(splitk_reduce_kernel<32>, blocks, 256, 0, stream, partial, dw, n4, splits, scale, beta);
     case 8: return launch_k(splitk_reduce_kernel<8>, blocks, 256, 0, stream, partial, dw, n4, splits, scale, beta);
@@ -1422,7 +1422,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPar
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
-  const int slots = sm_count() * ctas_per_sm;
+  const int slots = tc_sm_count() * ctas_per_sm;
   int grid = p.num_tiles < slots ? p.num_tiles : slots;
   launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p, variant == 2 ? *tmO : tmA);
   GANB_CHECK_LAUNCH("conv_igemm_kernel");
@@ -1447,7 +1447,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
-  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  int grid = p.num_tiles < tc_sm_count() ? p.num_tiles : tc_sm_count();
   launch_k(kern, grid, HALO_THREADS, smem, stream, tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
   GANB_CHECK_LAUNCH("conv_halo_kernel");
   return 0;
@@ -1466,7 +1466,7 @@ static int launch_halo_narrow(const CUtensorMap& tmA, const CUtensorMap& tmB, Ig
   }
   p.tiles_co = 1;
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  int grid = p.num_tiles < tc_sm_count() ? p.num_tiles : tc_sm_count();
   launch_k(kern, grid, HALO_THREADS, smem, stream, tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
   GANB_CHECK_LAUNCH("conv_halo_narrow_kernel");
   return 0;
@@ -1499,7 +1499,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, IgemmPara
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int pair_tiles = ((m_tiles + 1) / 2) * p.tiles_co * p.og;
   p.num_tiles = pair_tiles;
-  int clusters = sm_count() / 2;
+  int clusters = tc_sm_count() / 2;
   if (clusters > pair_tiles) clusters = pair_tiles;
   launch_k(kern, 2 * clusters, HALO_THREADS, smem, stream, tmA, tmB, p, a_stage_bytes, halo_w, halo_bytes);
   GANB_CHECK_LAUNCH("conv_pair_kernel");
@@ -1616,8 +1616,8 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
     int best_bn = bn_tile;
     for (int bn = bn_tile; bn >= 64; bn >>= 1) {
       const double tiles = static_cast<double>(m_tiles) * ceil_div(cout, bn);
-      const double active = tiles < sm_count() ? tiles : sm_count();
-      const double waves = ceil_div(static_cast<int>(tiles), sm_count());
+      const double active = tiles < tc_sm_count() ? tiles : tc_sm_count();
+      const double waves = ceil_div(static_cast<int>(tiles), tc_sm_count());
       const double t_mma = waves * kit * 4.0 * (bn / 2.0);
       const double rate = 6500.0 < 64.0 * active ? 6500.0 : 64.0 * active;
       const double t_l2 = tiles * kit * (a_bytes + bn * 128.0) / rate;
@@ -1630,7 +1630,7 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
   // CTA pairs (cta_group::2) halve the filter traffic per SM: used when there is at least one wave of pair tiles
   const int pair_bn = cout > 128 ? 256 : 128;
   const bool pair = halo && cout >= 128 && pair_mode() &&
-                    ((m_tiles + 1) / 2) * ceil_div(cout, pair_bn) >= sm_count() / 2;
+                    ((m_tiles + 1) / 2) * ceil_div(cout, pair_bn) >= tc_sm_count() / 2;
   if (pair) bn_tile = pair_bn;
 
   // shallow-K launches (see launch_igemm): two CTAs per SM; BN = 256 would take all 512 TMEM columns, so the channels
@@ -1732,7 +1732,7 @@ static void plan_wgrad(int n, int ho, int wo, int cin, int cout, int kh, int kw,
   p.co_tiles = ceil_div(cout, plan->bn_tile);
   const int units = p.taps * p.ci_tiles * p.co_tiles;
   // one CTA per SM and a single wave: a second, nearly empty wave would idle most of the machine
-  int splits = sm_count() / units;
+  int splits = tc_sm_count() / units;
   if (splits < 1) splits = 1;
   // keep at least 4 pixel blocks per split so the pipeline has something to overlap
   const int max_splits = p.num_pb / 4 > 0 ? p.num_pb / 4 : 1;
@@ -2034,7 +2034,7 @@ extern "C" int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, f
   if (rc) return rc;
   const int64_t plane4 = static_cast<int64_t>(cin) * cout / 4;
   int blocks = static_cast<int>(ceil_div64(9 * plane4, 256));
-  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  if (blocks > 4 * tc_sm_count()) blocks = 4 * tc_sm_count();
   launch_k(upconv_fold_reduce_kernel, blocks, 256, 0, stream, p.partial, dw_hwio, plane4, p.splits, scale, beta);
   GANB_CHECK_LAUNCH("upconv_fold_reduce_kernel");
   return 0;
@@ -2062,7 +2062,7 @@ static int launch_igemm_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, Ige
   }
   p.tiles_co = ceil_div(p.Cout, BN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_co;
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  const int grid = p.num_tiles < tc_sm_count() ? p.num_tiles : tc_sm_count();
   launch_k(kern, grid, NUM_THREADS, smem, stream, tmA, tmB, p, tmA);
   GANB_CHECK_LAUNCH("conv_igemm_kernel<tf32>");
   return 0;

@@ -31,18 +31,30 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   o.hi = __floats2bfloat162_rn(v.z, v.w);
   *reinterpret_cast<bf16x4*>(p) = o;
 }
+// Branch-free forms (none / relu / leaky relu; the host sends tanh to the generic kernels): a per-element switch over the
+// activation codes compiles to a branch per element with the tanh code inline (190 branches in a 2100-instruction
+// kernel body), which -- not the memory system -- paced these kernels at ~0.5 of the HBM roofline.
+struct ActLin {
+  float slope;     // value multiplier on the negative side: none 1, relu 0, leaky relu 0.2
+  bool relu;       // exact +0 on the negative side
+  bool zero_on;    // derivative at y == 0: relu 0, otherwise 1
+  __device__ __forceinline__ explicit ActLin(int act)
+      : slope(act == GANB_ACT_RELU ? 0.f : act == GANB_ACT_LRELU ? 0.2f : 1.f), relu(act == GANB_ACT_RELU),
+        zero_on(act != GANB_ACT_RELU) {}
+  __device__ __forceinline__ float f(float v) const { return fmaxf(v, relu ? 0.f : slope * v); }
+  __device__ __forceinline__ float d(float y) const { return (zero_on ? y >= 0.f : y > 0.f) ? 1.f : slope; }
+};
+
+// tanh out of line: inlined, its code sits behind a branch in every unrolled element of every caller
+__device__ __noinline__ float tanh_ool(float v) { return tanhf(v); }
 __device__ __forceinline__ float act_f(float v, int act) {
-  if (act == GANB_ACT_RELU) return v > 0.f ? v : 0.f;
-  if (act == GANB_ACT_LRELU) return v >= 0.f ? v : 0.2f * v;
-  if (act == GANB_ACT_TANH) return tanhf(v);
-  return v;
+  if (act == GANB_ACT_TANH) return tanh_ool(v);
+  return ActLin(act).f(v);
 }
 // derivative of the activation expressed with the PRE-activation value y
 __device__ __forceinline__ float dact_f(float y, int act) {
-  if (act == GANB_ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == GANB_ACT_LRELU) return y >= 0.f ? 1.f : 0.2f;
-  if (act == GANB_ACT_TANH) { const float t = tanhf(y); return 1.f - t * t; }
-  return 1.f;
+  if (act == GANB_ACT_TANH) { const float t = tanh_ool(y); return 1.f - t * t; }
+  return ActLin(act).d(y);
 }
 #define F4_OP(r, a, expr_x, expr_y, expr_z, expr_w) \
   float4 r = make_float4(expr_x, expr_y, expr_z, expr_w)
@@ -117,31 +129,40 @@ bn_stats_partial_kernel(const TX* __restrict__ x, int rows_per_group, int c, int
   }
 }
 
-// one warp per (group, channel): the 32 lanes split the chunk partials and combine with a fixed shuffle tree
-// (deterministic); 8 channels per 256-thread block.
-__global__ void __launch_bounds__(256)
+// One block per (32 channels, group): 32 thread rows split the chunk partials -- every load is a coalesced 128-byte row of
+// 32 channels, all of a thread's loads are independent (one round trip for <= 256 chunks) -- and meet in shared memory in a
+// fixed order (deterministic).  (One warp per channel with the lanes over the chunks read 4 bytes per 32-byte sector.)
+__global__ void __launch_bounds__(1024)
 bn_stats_finalize_kernel(const float* __restrict__ partial, int c, int groups, int chunks, float inv_count, float eps,
                          float* __restrict__ mean, float* __restrict__ rstd) {
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);  // flat (group, channel)
-  if (i >= groups * c) return;
-  const int g = i / c, ch = i - g * c;
+  __shared__ double ssum[32][33], ssq[32][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
+  const int g = blockIdx.y;
   double s = 0.0, q = 0.0;
+  if (ch < c) {
 #pragma unroll 8
-  for (int k = lane; k < chunks; k += 32) {
-    const float* p = partial + (static_cast<int64_t>(g) * chunks + k) * 2 * c;
-    s += __ldg(p + ch);
-    q += __ldg(p + c + ch);
+    for (int k = ly; k < chunks; k += 32) {
+      const float* p = partial + (static_cast<int64_t>(g) * chunks + k) * 2 * c;
+      s += __ldg(p + ch);
+      q += __ldg(p + c + ch);
+    }
   }
-  s = warp_sum_d(s);
-  q = warp_sum_d(q);
-  if (lane == 0) {
-    const double m = s * inv_count;
-    double var = q * inv_count - m * m;
+  ssum[ly][cx] = s;
+  ssq[ly][cx] = q;
+  __syncthreads();
+  // warp `ly` folds channel `ly`: lanes read the 32 row sums (transposed access, padded: conflict-free), fixed shuffle tree
+  const int chw = blockIdx.x * 32 + ly;
+  double a = ssum[cx][ly], b = ssq[cx][ly];
+  a = warp_sum_d(a);
+  b = warp_sum_d(b);
+  if (cx == 0 && chw < c) {
+    const double m = a * inv_count;
+    double var = b * inv_count - m * m;
     if (var < 0.0) var = 0.0;
-    mean[i] = static_cast<float>(m);
-    rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    mean[g * c + chw] = static_cast<float>(m);
+    rstd[g * c + chw] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
 }
 
@@ -703,6 +724,7 @@ __device__ __forceinline__ int quad_to_nhwc(int q, int w) {
 template <bool UPS>
 __global__ void __launch_bounds__(256) norm_act_fwd_v8_kernel(const NormActFwd p, int pix_per_chunk) {
   pdl_wait();
+  const ActLin al(p.act);
   const int ni = blockIdx.y;
   const int v = p.c >> 3;
   const int cols = min(v, 256);
@@ -752,7 +774,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_v8_kernel(const NormActFwd p
         float a[8];
         cvt8(raw[u], a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = act_f(a[j] * sc[j] + sf[j], p.act);
+        for (int j = 0; j < 8; ++j) a[j] = al.f(a[j] * sc[j] + sf[j]);
         const uint4 y = pack8(a);
         const int64_t pix = static_cast<int64_t>(ni) * hw + (p.quad ? quad_to_nhwc(q, p.w) : q);
         if (!UPS) {
@@ -825,6 +847,7 @@ __device__ __forceinline__ void bwd_sum_dz8(const uint4 (&raw)[UPS ? 4 : 1], flo
 template <bool UPS>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_v8_kernel(const NormActBwd p) {
   pdl_wait();
+  const ActLin al(p.act);
   const int ni = blockIdx.y, chunk = blockIdx.x;
   const int v = p.c >> 3;
   const int lanes = max(1, 256 / min(v, 256));
@@ -864,7 +887,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_v8_kernel(const No
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float xh = a[j] * k.r[j] - k.mr[j];
-            const float dy = dz[j] * dact_f(xh * k.ga[j] + k.be[j], p.act);
+            const float dy = dz[j] * al.d(xh * k.ga[j] + k.be[j]);
             sa[j] += dy;
             sb[j] += dy * xh;
           }
@@ -885,6 +908,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_v8_kernel(const No
 template <bool NORM, bool UPS>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8_kernel(const NormActBwd p, int pix_per_chunk) {
   pdl_wait();
+  const ActLin al(p.act);
   const int ni = blockIdx.y;
   const int v = p.c >> 3;
   const int cols = min(v, 256);
@@ -937,7 +961,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8_kernel(const Nor
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = a[j] * k.r[j] - k.mr[j];
-          const float dy = dz[j] * dact_f(xh * k.ga[j] + k.be[j], p.act);
+          const float dy = dz[j] * al.d(xh * k.ga[j] + k.be[j]);
           dx[j] = NORM ? k.r[j] * (k.ga[j] * dy - t1[j] - xh * t2[j]) : dy;
         }
         if (addp) {
@@ -963,6 +987,7 @@ __device__ __forceinline__ int64_t bwd_dz_off(const NormActBwd& p, int ni, int p
 template <bool NORM>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8p_kernel(const NormActBwd p, int pix_per_chunk) {
   pdl_wait();
+  const ActLin al(p.act);
   extern __shared__ uint4 ring_raw[];
   uint4* ring_x = ring_raw + threadIdx.x;
   uint4* ring_z = ring_x + BWD_STAGES * PIPE_U * 256;
@@ -1028,7 +1053,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8p_kernel(const No
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = a[j] * k.r[j] - k.mr[j];
-          const float dy = dz[j] * dact_f(xh * k.ga[j] + k.be[j], p.act);
+          const float dy = dz[j] * al.d(xh * k.ga[j] + k.be[j]);
           dx[j] = NORM ? k.r[j] * (k.ga[j] * dy - t1[j] - xh * t2[j]) : dy;
         }
         if (addp) {
@@ -1041,6 +1066,85 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v8p_kernel(const No
       }
     }
     cp_async_wait<0>();
+  }
+}
+
+// cp.async-ring variant of norm_act_bwd_reduce_v8_kernel<false> (RED_STAGES iterations of x and dz in flight per thread, no
+// registers held while they fly): the plain-load kernel computes ~320 instructions per thread between two batches of
+// loads with nothing in flight meanwhile (0.49 of the copy bandwidth standalone; reduce + finalize + apply of a 67 MB tensor 85.4 -> 79.6 us with the ring).
+// GANB_BWD_REDUCE_RING=0 selects the plain-load kernel.
+constexpr int RED_STAGES = 3;    // 2 tensors x 3 x 4 x 256 x 16 B = 96 KB per block
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_reduce_v8p_kernel(const NormActBwd p) {
+  pdl_wait();
+  const ActLin al(p.act);
+  extern __shared__ uint4 ring_raw[];
+  uint4* ring_x = ring_raw + threadIdx.x;
+  uint4* ring_z = ring_x + RED_STAGES * PIPE_U * 256;
+  const int ni = blockIdx.y, chunk = blockIdx.x;
+  const int v = p.c >> 3;
+  const int lanes = max(1, 256 / min(v, 256));
+  const int cols_per_pass = 256 / lanes;
+  const int cx = threadIdx.x % cols_per_pass, ry = threadIdx.x / cols_per_pass;
+  const int hw = p.h * p.w;
+  const int p0 = chunk * p.pix_per_chunk, p1 = min(hw, p0 + p.pix_per_chunk);
+  const int g = ni / (p.n / p.groups);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(p.x);
+  const __nv_bfloat16* dzp = static_cast<const __nv_bfloat16*>(p.dz);
+  __shared__ float sh[256][17];
+  for (int cb = 0; cb < v; cb += cols_per_pass) {
+    const int col = cb + cx;
+    float sa[8], sb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sa[j] = 0.f; sb[j] = 0.f; }
+    if (col < v && ry < lanes) {
+      const int c8 = col * 8;
+      BwdConst8 k;
+      bwd_const8<true>(p, ni, g, c8, k);
+      const int step = lanes * PIPE_U;
+      const int iters = (p1 - p0 - ry + step - 1) / step;
+      auto issue = [&](int it) {
+        const int so = (it % RED_STAGES) * PIPE_U * 256;
+#pragma unroll
+        for (int u = 0; u < PIPE_U; ++u) {
+          const int qx = p0 + ry + (it * PIPE_U + u) * lanes;
+          const bool ok = qx < p1;
+          const int qq = ok ? qx : p0;
+          cp_async16(ring_x + so + u * 256, xp + (static_cast<int64_t>(ni) * hw + qq) * p.c + c8, ok);
+          cp_async16(ring_z + so + u * 256, dzp + bwd_dz_off(p, ni, qq, c8), ok);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int it = 0; it < RED_STAGES - 1; ++it) issue(it);
+      for (int it = 0; it < iters; ++it) {
+        issue(it + RED_STAGES - 1);
+        cp_async_wait<RED_STAGES - 1>();
+        const int so = (it % RED_STAGES) * PIPE_U * 256;
+#pragma unroll
+        for (int u = 0; u < PIPE_U; ++u) {
+          // rows beyond p1 were zero-filled: dz = 0 contributes nothing to either sum
+          float a[8], dz[8];
+          cvt8(ring_x[so + u * 256], a);
+          cvt8(ring_z[so + u * 256], dz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = a[j] * k.r[j] - k.mr[j];
+            const float dy = dz[j] * al.d(xh * k.ga[j] + k.be[j]);
+            sa[j] += dy;
+            sb[j] += dy * xh;
+          }
+        }
+      }
+      cp_async_wait<0>();
+    }
+    lanes_sum16(sa, sb, lanes, cols_per_pass, cx, ry, sh);
+    if (ry == 0 && col < v) {
+      float* out = p.part + (static_cast<int64_t>(ni) * p.chunks + chunk) * 2 * p.c;
+      st4(out + col * 8, make_float4(sa[0], sa[1], sa[2], sa[3]));
+      st4(out + col * 8 + 4, make_float4(sa[4], sa[5], sa[6], sa[7]));
+      st4(out + p.c + col * 8, make_float4(sb[0], sb[1], sb[2], sb[3]));
+      st4(out + p.c + col * 8 + 4, make_float4(sb[4], sb[5], sb[6], sb[7]));
+    }
   }
 }
 
@@ -1318,19 +1422,24 @@ colsum_partial_kernel(const TIn* __restrict__ x, int64_t rows, int c, int rows_p
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(256)
+// One block per 32 channels: 32 thread rows split the chunk partials (coalesced 128-byte rows, independent loads) and meet
+// in shared memory in a fixed order (deterministic); see bn_stats_finalize_kernel.
+__global__ void __launch_bounds__(1024)
 colsum_finalize_kernel(const float* __restrict__ partial, int c, int chunks, float beta, float* __restrict__ out) {
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (ch >= c) return;
-  // independent loads are issued eight at a time: the rolled loop paid one L2 round trip per partial (18 in a row
-  // for 592 chunks) and made this 150 KB reduction a 4-5 us kernel, 22 times per training step
+  __shared__ float ssum[32][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
   float s = 0.f;
+  if (ch < c) {
 #pragma unroll 8
-  for (int k = lane; k < chunks; k += 32) s += __ldg(partial + static_cast<int64_t>(k) * c + ch);
-  s = warp_sum_f(s);
-  if (lane == 0) out[ch] = (beta != 0.f ? beta * out[ch] : 0.f) + s;
+    for (int k = ly; k < chunks; k += 32) s += __ldg(partial + static_cast<int64_t>(k) * c + ch);
+  }
+  ssum[ly][cx] = s;
+  __syncthreads();
+  const int chw = blockIdx.x * 32 + ly;
+  const float a = warp_sum_f(ssum[cx][ly]);
+  if (cx == 0 && chw < c) out[chw] = (beta != 0.f ? beta * out[chw] : 0.f) + a;
 }
 
 
@@ -1703,8 +1812,21 @@ extern "C" int64_t ganb_bn_stats_workspace(int n, int hw, int c, int groups) {
 
 // Four blocks per SM are needed to keep HBM busy (two measured 80 % slower); small tensors get at least 128 rows per
 // chunk (the finalize kernels are latency-bound on the number of partials).
+// blocks per SM of the streaming kernels (tuning hooks for tests/probe_bw_kernels.py; read once)
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+// 2 long-running blocks per SM: 23.2 -> 16.4 us for the statistics of a 67 MB tensor, 21.4 -> 16.6 us for its column sums
+// (4 / 8 blocks per SM spend their time in the pipeline prologue and the shared-memory reduction; profiles/r02_bandwidth_kernels.txt)
+static int stats_bps() { static const int v = env_int("GANB_STATS_BPS", 2); return v; }
+static int fwd_bps() { static const int v = env_int("GANB_V8_FWD_BPS", 3); return v; }
+static int bwd_bps() { static const int v = env_int("GANB_V8_BWD_BPS", 2); return v; }
+static bool reduce_ring() { static const int v = env_int("GANB_BWD_REDUCE_RING", 1); return v != 0; }
+static int colsum_bps() { static const int v = env_int("GANB_COLSUM_BPS", 2); return v; }
+
 static int stats_chunks(int rows_per_group, int groups) {
-  int chunks = ceil_div(4 * sm_count(), groups);
+  int chunks = ceil_div(stats_bps() * sm_count(), groups);
   const int max_chunks = ceil_div(rows_per_group, 128);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks > 1024) chunks = 1024;
@@ -1739,7 +1861,7 @@ extern "C" int ganb_bn_stats(const void* x, int x_dtype, int n, int hw, int c, i
     launch_k(bn_stats_partial_kernel<float>, grid, 256, 0, STREAM, static_cast<const float*>(x), rows_per_group, c, used,
                                                               rows_per_chunk, static_cast<float*>(workspace));
   GANB_CHECK_LAUNCH("bn_stats_partial_kernel");
-  launch_k(bn_stats_finalize_kernel, ceil_div(groups * c, 8), 256, 0, STREAM, static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
+  launch_k(bn_stats_finalize_kernel, dim3(ceil_div(c, 32), groups), 1024, 0, STREAM, static_cast<float*>(workspace), c, groups, used, 1.0f / rows_per_group, eps, mean, rstd);
   GANB_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return 0;
 }
@@ -1750,7 +1872,7 @@ extern "C" int ganb_bn_stats_finalize(const float* partial, int c, int groups, i
                                       float* mean, float* rstd, void* stream) {
   if (!partial || !mean || !rstd) return fail(GANB_E_BADARG, "bn_stats_finalize: null buffer");
   if (c <= 0 || groups <= 0 || chunks <= 0 || count <= 0) return fail(GANB_E_BADARG, "bn_stats_finalize: bad shape");
-  launch_k(bn_stats_finalize_kernel, ceil_div(groups * c, 8), 256, 0, STREAM, partial, c, groups, chunks,
+  launch_k(bn_stats_finalize_kernel, dim3(ceil_div(c, 32), groups), 1024, 0, STREAM, partial, c, groups, chunks,
            1.0f / static_cast<float>(count), eps, mean, rstd);
   GANB_CHECK_LAUNCH("bn_stats_finalize_kernel");
   return 0;
@@ -1791,10 +1913,10 @@ extern "C" int ganb_norm_act_fwd(const void* x, int x_dtype, int n, int h, int w
   upsample = p.upsample;
   p.out = out; p.out_bf16 = (out_dtype == GANB_BF16); p.out_cstride = out_cstride > 0 ? out_cstride : c;
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw_bf16); p.raw_cstride = raw_cstride > 0 ? raw_cstride : c;
-  const bool v8 = p.x_bf16 && p.out_bf16 && !p.out_raw && c % 8 == 0 && p.out_cstride % 8 == 0;
+  const bool v8 = p.x_bf16 && p.out_bf16 && !p.out_raw && c % 8 == 0 && p.out_cstride % 8 == 0 && act != GANB_ACT_TANH;
   if (p.quad && (!v8 || (h & 1) || (w & 1)))
     return fail(GANB_E_UNSUPPORTED, "norm_act_fwd: quad-layout input needs bf16 in/out, c %% 8 == 0, even h, w and no raw copy");
-  const int chunks = v8 ? v8_chunks(n, h * w, 3) : bwd_chunks(n, h * w);
+  const int chunks = v8 ? v8_chunks(n, h * w, fwd_bps()) : bwd_chunks(n, h * w);
   const int ppc = ceil_div(h * w, chunks);
   if (v8 && upsample) launch_k(norm_act_fwd_v8_kernel<true>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
   else if (v8) launch_k(norm_act_fwd_v8_kernel<false>, dim3(ceil_div(h * w, ppc), n), 256, 0, STREAM, p, ppc);
@@ -1855,13 +1977,14 @@ static int norm_act_bwd_impl(const void* x, int x_dtype, const void* dz, int dz_
   p.add = add; p.add_bf16 = (add_dtype == GANB_BF16); p.dx = dx; p.dx_bf16 = (dx_dtype == GANB_BF16);
   p.part = nullptr; p.s1 = nullptr; p.s2 = nullptr; p.chunks = 0; p.pix_per_chunk = 0; p.inv_count = 0.f;
   // all-bf16 fast path: 8 channels per thread
-  const bool v8 = p.x_bf16 && p.dz_bf16 && p.dx_bf16 && (!add || p.add_bf16) && c % 8 == 0 && p.dz_cstride % 8 == 0;
+  const bool v8 = p.x_bf16 && p.dz_bf16 && p.dx_bf16 && (!add || p.add_bf16) && c % 8 == 0 && p.dz_cstride % 8 == 0 &&
+                  act != GANB_ACT_TANH;
   if (p.quad && (!v8 || add || (h & 1) || (w & 1)))
     return fail(GANB_E_UNSUPPORTED, "norm_act_bwd: quad-layout input needs the all-bf16 path, even h, w and no added gradient");
   if (mean) {
     if (!workspace) return fail(GANB_E_BADARG, "norm_act_bwd: workspace required with normalisation");
     const int hw = h * w;
-    const int chunks = v8 ? v8_chunks(n, hw, 2) : bwd_chunks(n, hw);
+    const int chunks = v8 ? v8_chunks(n, hw, bwd_bps()) : bwd_chunks(n, hw);
     p.pix_per_chunk = ceil_div(hw, chunks);
     p.chunks = ceil_div(hw, p.pix_per_chunk);
     p.part = static_cast<float*>(workspace);
@@ -1872,8 +1995,17 @@ static int norm_act_bwd_impl(const void* x, int x_dtype, const void* dz, int dz_
     if (phase != 2) {
       const dim3 grid(p.chunks, n);
       if (v8 && upsample) launch_k(norm_act_bwd_reduce_v8_kernel<true>, grid, 256, 0, STREAM, p);
-      // (the cp.async-ring variant of this kernel measured SLOWER than plain loads, 244 vs 211 us per step --
-      // profiles/r01_elementwise_pipe_ab.txt -- while the statistics and apply kernels gained; it is not used)
+      // (round 1's cp.async ring for this kernel measured slower inside the step, profiles/r01_elementwise_pipe_ab.txt; the
+      // round-2 ring below -- three stages, one wave of long blocks -- is faster alone and no slower in the step)
+      else if (v8 && reduce_ring()) {
+        constexpr int smem = 2 * RED_STAGES * PIPE_U * 256 * 16;
+        static bool configured = false;
+        if (!configured) {
+          cudaFuncSetAttribute(norm_act_bwd_reduce_v8p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+          configured = true;
+        }
+        launch_k(norm_act_bwd_reduce_v8p_kernel, grid, 256, smem, STREAM, p);
+      }
       else if (v8) launch_k(norm_act_bwd_reduce_v8_kernel<false>, grid, 256, 0, STREAM, p);
       else if (p.x_bf16) launch_bwd_reduce<__nv_bfloat16>(p, grid, STREAM);
       else launch_bwd_reduce<float>(p, grid, STREAM);
@@ -1901,7 +2033,7 @@ static int norm_act_bwd_impl(const void* x, int x_dtype, const void* dz, int dz_
   }
   if (phase == 1) return mean ? 0 : fail(GANB_E_BADARG, "norm_act_bwd: phase 1 needs normalisation statistics");
   {
-    const int chunks2 = v8 ? v8_chunks(n, h * w, 2) : bwd_chunks(n, h * w);
+    const int chunks2 = v8 ? v8_chunks(n, h * w, bwd_bps()) : bwd_chunks(n, h * w);
     const int ppc = ceil_div(h * w, chunks2);
     const dim3 grid(ceil_div(h * w, ppc), n);
     if (v8) {
@@ -2133,7 +2265,7 @@ static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float*
     return 0;
   }
   const bool narrow = (c % 4 != 0);
-  int chunks = narrow ? sm_count() : 4 * sm_count();
+  int chunks = narrow ? sm_count() : colsum_bps() * sm_count();
   const int64_t max_chunks = ceil_div64(rows, narrow ? 256 : 128);
   if (chunks > max_chunks) chunks = static_cast<int>(max_chunks);
   if (chunks > 1024) chunks = 1024;
@@ -2158,7 +2290,7 @@ static int launch_colsum(const void* xv, int64_t rows, int c, float beta, float*
       launch_k(colsum_partial_kernel<TIn>, used, 256, 0, s, x, rows, c, rows_per_chunk, static_cast<float*>(workspace));
     GANB_CHECK_LAUNCH("colsum_partial_kernel");
   }
-  launch_k(colsum_finalize_kernel, ceil_div(c, 8), 256, 0, s, static_cast<float*>(workspace), c, used, beta, out);
+  launch_k(colsum_finalize_kernel, ceil_div(c, 32), 1024, 0, s, static_cast<float*>(workspace), c, used, beta, out);
   GANB_CHECK_LAUNCH("colsum_finalize_kernel");
   return 0;
 }

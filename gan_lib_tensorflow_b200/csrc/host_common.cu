@@ -44,6 +44,20 @@ int sm_count() {
   return cached;
 }
 
+// Tensor-core kernels are persistent (one CTA per SM, grid = min(tiles, SMs)).  A per-thread limit on the SMs they may
+// take lets two independent passes issued on two streams share the GPU side by side instead of kernel by kernel
+// (ganb_set_sm_limit; used by the D+G pair schedule).  0 = no limit.
+static thread_local int tl_sm_limit = 0;
+int tc_sm_count() {
+  const int n = sm_count();
+  return (tl_sm_limit > 0 && tl_sm_limit < n) ? tl_sm_limit : n;
+}
+extern "C" int ganb_set_sm_limit(int sms) {
+  const int prev = tl_sm_limit;
+  tl_sm_limit = sms > 0 ? sms : 0;
+  return prev;
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,

@@ -14,6 +14,7 @@ int fail(int code, const char* fmt, ...);
 
 // Number of SMs of the current device (cached).
 int sm_count();
+int tc_sm_count();   // sm_count() under the calling thread's ganb_set_sm_limit
 
 // Encodes a tiled TMA descriptor over a bf16 tensor. dims/strides innermost-first; strides in bytes
 // for dims 1..rank-1. Returns 0 or a negative GANB_E_* code.

@@ -202,6 +202,10 @@ class Tape:
         self.pending_derived = []        # DerivedWeight instances used on this tape (weight-norm / masks)
         self.keep = []       # temporaries read by side-stream launches: kept alive until the join
         self._forked = set()   # side-stream lanes with work in flight
+        # (main, side) SM budgets of the tensor-core kernels during backward(): with small layers (the critic) a data-
+        # gradient kernel and a filter-gradient kernel that each take every SM run one after the other; two half-GPU
+        # kernels run side by side and lose little, because such launches are dominated by fixed latencies.  None: off
+        self.sm_split = None
         self.token = 0       # identity of this tape for the spectral-norm evaluation bookkeeping (VariableStore)
         self.sn_gen = {}     # root -> index of the spectral-norm state set in use on this tape
         self.node_stream = {}   # node index -> stream of the branch it was recorded in
@@ -258,7 +262,7 @@ class Tape:
         side = _side_stream(main.device, lane)
         side.wait_stream(main)
         self._forked.add(lane)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), K.sm_limit(self.sm_split[1] if self.sm_split else 0):
             yield
 
     def join(self) -> None:
@@ -273,8 +277,9 @@ class Tape:
         if grad is not None:
             loss.accum(grad)
         if not self.node_stream:
-            for fn in reversed(self.nodes):
-                fn()
+            with K.sm_limit(self.sm_split[0] if self.sm_split else 0):
+                for fn in reversed(self.nodes):
+                    fn()
         else:
             main = torch.cuda.current_stream()
             entered, pending = set(), []          # branch streams already running backward work / not yet joined
@@ -448,6 +453,32 @@ class SNGroup:
                 self.valid_for = key
                 for x in self.entries.values():
                     x.fresh = False
+
+    def prefetch(self, assign: bool) -> bool:
+        """Runs the evaluation that the first acquire() of the coming pass would start, ahead of that pass (on whatever
+        stream is current: the power iteration reads the weights and u only, so it can sit next to unrelated work).
+        The layers' acquire() calls then find their state current.  Returns False when nothing had to run."""
+        if not self.entries:
+            return False
+        ver = self.store.version(self.root)
+        if assign:
+            if self.fresh_for == ver and all(e.fresh for e in self.entries.values()):
+                return False
+            self._run(True)
+            self.store.bump_u(self.root)
+            self.valid_for = None
+            self.fresh_for = ver
+            for x in self.entries.values():
+                x.fresh = True
+            return True
+        key = (ver, self.store.u_version(self.root))
+        if self.valid_for == key:
+            return False
+        self._run(False)
+        self.valid_for = key
+        for x in self.entries.values():
+            x.fresh = False
+        return True
 
     def backward(self, entries) -> None:
         all_entries = list(self.entries.values())

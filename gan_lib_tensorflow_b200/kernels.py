@@ -5,6 +5,7 @@ libganb200 kernel.  All activations are contiguous NHWC.  No wrapper has a CPU o
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from ctypes import c_float, c_int, c_int64, c_void_p
 
@@ -51,6 +52,19 @@ def _stream():
     if host_logic_only():
         return c_void_p(0)
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@contextlib.contextmanager
+def sm_limit(sms: int):
+    """Tensor-core kernels issued inside occupy at most `sms` SMs (0 / None: no limit); see ganb_set_sm_limit."""
+    if not sms or host_logic_only():
+        yield
+        return
+    prev = L().ganb_set_sm_limit(int(sms))
+    try:
+        yield
+    finally:
+        L().ganb_set_sm_limit(prev)
 
 
 def launch_count() -> int:

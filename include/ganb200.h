@@ -47,6 +47,10 @@ int ganb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of CUDA kernels this library has launched in the calling process (launches recorded into a CUDA graph
  * count once, at capture time) */
 int64_t ganb_launch_count(void);
+/* Limits the SMs that the persistent tensor-core kernels launched by the CALLING THREAD may occupy (their grids, split
+ * counts and workspace sizes follow); 0 = all.  Two independent passes issued on two streams under complementary limits
+ * run side by side (the critic step next to the generator's forward pass).  Returns the previous limit. */
+int ganb_set_sm_limit(int sms);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core convolution (tcgen05 / TMEM implicit GEMM, TMA-fed, BF16 inputs, FP32 accumulation).
