@@ -168,13 +168,23 @@ class Trainer:
             if getattr(self, 'last_g', None):      # the kernel folds acgan_scale_G into the term; the script logs it unscaled
                 out.update({'g_loss_gan': self.last_g['g_loss_gan'],
                             'g_loss_acgan': self.last_g['g_loss_acgan_scaled'] / self.scale_g})
-            out.update({'d_loss_gan': self.last_d['d_loss_gan'], 'd_loss_acgan': self.last_d['d_loss_acgan']})
+            d_gan = self.last_d['d_loss_gan']
+            if self.last_d.get('gradient_penalty') is not None:     # the script logs d_loss_gan after `+= gradient_penalty`
+                d_gan = d_gan + self.last_d['gradient_penalty']
+            out.update({'d_loss_gan': d_gan, 'd_loss_acgan': self.last_d['d_loss_acgan']})
             return out
 
         def dev_costs(_step):
             if dev_gen is None:
                 return []
-            return [self.d_loss(*feed(images, labels), *self._noise()).data.clone() for images, labels in dev_gen()]
+            # d_loss() rebinds self.last_d to fresh tensors; the captured graphs keep writing the training scalars into the
+            # ones they were captured with, so those are put back (otherwise every later progress line would show the last
+            # dev batch)
+            keep = self.last_d
+            try:
+                return [self.d_loss(*feed(images, labels), *self._noise()).data.clone() for images, labels in dev_gen()]
+            finally:
+                self.last_d = keep
 
         def samples(_step):
             return self.model.get_generator(fixed_z, fixed_labels, reuse=True).data

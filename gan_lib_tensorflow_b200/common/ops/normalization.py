@@ -21,6 +21,9 @@ def batch_norm(inputs, decay=0.9, epsilon=1e-5, is_training=True, fused=True, ac
                out_dtype=torch.float32, want_raw=False):
     """common/ops/normalization.py:8-24: contrib fused batch norm, always in training mode (batch statistics).
     The moving averages are write-only state in every reference caller and are not maintained yet."""
+    if not is_training:
+        # inference mode would need the moving averages, which no reference caller ever reads (is_training=True everywhere)
+        raise NotImplementedError('batch_norm(is_training=False): moving averages are not maintained')
     store = get_store()
     inputs = F.as_var(inputs)
     with store.variable_scope('BatchNorm'):
