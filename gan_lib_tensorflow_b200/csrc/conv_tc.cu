@@ -73,6 +73,11 @@ struct IgemmParams {
   // (relu: gate > 0; leaky relu: gate >= 0 ? 1 : 0.2).  nullptr: off.
   const __nv_bfloat16* gate;
   int gate_act;
+  // 32-byte (256-bit) stores: the output pointer, the pixel stride and the row length are multiples of 32 bytes, so every
+  // store instruction of a thread fills one whole 32-byte sector (16-byte stores leave the sector to a second instruction:
+  // 2x the L2 write sectors on the store-bound shallow-K layers, profiles/r02_ncu_igemm_k32.txt)
+  int st32;
+  int res32;   // the same for the fp32 residual rows (32-byte loads)
 };
 
 template <int NC>
@@ -91,6 +96,22 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+
+__device__ __forceinline__ void stg32(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                      uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+__device__ __forceinline__ void ldg32(const void* ptr, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 q = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&q);
 }
 
 __device__ __noinline__ float4 tanh4(float4 a) {
@@ -181,10 +202,20 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
                              __uint_as_float(r[j + 2]) * alpha, __uint_as_float(r[j + 3]) * alpha);
     if (p.residual) {
       float4 q[NC / 4];
+      if (p.res32 && NC % 8 == 0) {
 #pragma unroll
-      for (int j = 0; j < NC; j += 4)
-        q[j / 4] = (co_base + j < cout) ? __ldg(reinterpret_cast<const float4*>(p.residual + roff + j))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NC; j += 8) {
+          uint32_t w8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (co_base + j < cout) ldg32(p.residual + roff + j, w8);
+          q[j / 4] = make_float4(__uint_as_float(w8[0]), __uint_as_float(w8[1]), __uint_as_float(w8[2]), __uint_as_float(w8[3]));
+          q[j / 4 + 1] = make_float4(__uint_as_float(w8[4]), __uint_as_float(w8[5]), __uint_as_float(w8[6]), __uint_as_float(w8[7]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; j += 4)
+          q[j / 4] = (co_base + j < cout) ? __ldg(reinterpret_cast<const float4*>(p.residual + roff + j))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int j = 0; j < NC / 4; ++j) { v[j].x += q[j].x; v[j].y += q[j].y; v[j].z += q[j].z; v[j].w += q[j].w; }
     }
@@ -251,7 +282,26 @@ __device__ __forceinline__ void epilogue_row(const IgemmParams& p, const uint32_
         val[j] = t.x; val[j + 1] = t.y; val[j + 2] = t.z; val[j + 3] = t.w;
       }
     }
-    if (p.out_bf16 && (cout % 8 == 0) && (NC % 8 == 0)) {
+    if (p.st32 && p.out_bf16 && (NC % 16 == 0)) {
+      // 32-byte stores: 16 bf16 channels = one whole sector per instruction (st32 implies cout % 16 == 0)
+#pragma unroll
+      for (int j = 0; j < NC; j += 16) {
+        if (co_base + j >= cout) break;
+        const float4 a = v[j / 4], b = v[j / 4 + 1], c = v[j / 4 + 2], d = v[j / 4 + 3];
+        stg32(reinterpret_cast<__nv_bfloat16*>(p.out) + off + j, pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w),
+              pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w), pack_bf16x2(c.x, c.y), pack_bf16x2(c.z, c.w),
+              pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+      }
+    } else if (p.st32 && !p.out_bf16 && (NC % 8 == 0)) {
+      // 32-byte stores: 8 fp32 channels per instruction (st32 implies cout % 8 == 0)
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        if (co_base + j >= cout) break;
+        const float4 a = v[j / 4], b = v[j / 4 + 1];
+        stg32(reinterpret_cast<float*>(p.out) + off + j, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z),
+              __float_as_uint(a.w), __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+      }
+    } else if (p.out_bf16 && (cout % 8 == 0) && (NC % 8 == 0)) {
       // 16-byte stores: 8 bf16 channels per instruction (half the store instructions of the 8-byte form)
 #pragma unroll
       for (int j = 0; j < NC; j += 8) {
@@ -1285,13 +1335,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
       if (ci < p.Cin) {
+        if ((p.Cout & 7) == 0) {
+          // groups of 8 never straddle the edge and every row of the partials starts on a 32-byte boundary: one whole
+          // sector per store instruction (the rows of a warp are Cout * 4 bytes apart)
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int co = co0 + c * 32 + j;
-          if (co < p.Cout) {  // Cout % 8 == 0 so groups of 4 never straddle the edge
-            *reinterpret_cast<float4*>(out + co) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                            __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 8) {
+            const int co = co0 + c * 32 + j;
+            if (co < p.Cout) stg32(out + co, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+          }
+        } else {      // TF32 operand mode admits Cout % 4 == 0
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int co = co0 + c * 32 + j;
+            if (co < p.Cout)
+              *reinterpret_cast<float4*>(out + co) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
           }
         }
       }
@@ -1601,6 +1659,13 @@ static int conv2d_igemm_impl(const void* x, const void* wp, void* y, int n, int 
   if (p.res_up2 && ((ho | wo) & 1)) return fail(GANB_E_BADARG, "conv2d_igemm: upsampled residual needs even ho, wo");
   p.out = y; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
   p.og = 1; p.rg = 1; p.out_cstride = cout;
+  {
+    const int64_t es_ = p.out_bf16 ? 2 : 4;
+    static const bool st32_ok = !(getenv("GANB_ST32") && getenv("GANB_ST32")[0] == '0');   // A/B switch
+    p.st32 = st32_ok && (reinterpret_cast<uintptr_t>(p.out) % 32 == 0) && ((p.Cout * es_) % 32 == 0) &&
+             ((static_cast<int64_t>(p.out_cstride) * es_) % 32 == 0);
+    p.res32 = st32_ok && p.residual && (reinterpret_cast<uintptr_t>(p.residual) % 32 == 0) && (p.Cout % 8 == 0);
+  }
   for (int i = 0; i < 4; ++i) { p.gpad_t[i] = 0; p.gpad_l[i] = 0; }
 
   // choose the N tile with a two-term cost model (cycles): tensor time = waves x k-iterations x MMA cycles of a tile,
@@ -1781,6 +1846,7 @@ extern "C" int ganb_conv2d_wgrad(const void* x, const void* dy, float* dw, void*
   if (stride < 1 || stride > 4) return fail(GANB_E_UNSUPPORTED, "conv2d_wgrad: stride=%d (1..4 supported)", stride);
   WgradParams& p = plan.p;
   p.pad_t = pad_t; p.pad_l = pad_l; p.stride = stride; p.quad = 0;
+  if (reinterpret_cast<uintptr_t>(workspace) & 31) return fail(GANB_E_BADARG, "filter gradient: workspace must be 32-byte aligned");
   p.partial = static_cast<float*>(workspace);
 
   CUtensorMap tmX, tmDY;
@@ -1915,6 +1981,13 @@ static int launch_upconv(bool dgrad, const void* a, const void* wp, void* out, i
   p.out = out; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
   p.og = dgrad ? 1 : 4; p.rg = dgrad ? 4 : 1;
   p.out_cstride = dgrad ? cn : 4 * cn;
+  {
+    const int64_t es_ = p.out_bf16 ? 2 : 4;
+    static const bool st32_ok = !(getenv("GANB_ST32") && getenv("GANB_ST32")[0] == '0');   // A/B switch
+    p.st32 = st32_ok && (reinterpret_cast<uintptr_t>(p.out) % 32 == 0) && ((p.Cout * es_) % 32 == 0) &&
+             ((static_cast<int64_t>(p.out_cstride) * es_) % 32 == 0);
+    p.res32 = st32_ok && p.residual && (reinterpret_cast<uintptr_t>(p.residual) % 32 == 0) && (p.Cout % 8 == 0);
+  }
   for (int g = 0; g < 4; ++g) {
     const int i = g >> 1, j = g & 1;
     p.gpad_t[g] = static_cast<signed char>(dgrad ? i : 1 - i);
@@ -2008,6 +2081,7 @@ extern "C" int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, f
   plan_wgrad(n, h, w, cin, cout, 4, 4, &plan);
   WgradParams& p = plan.p;
   p.kw = 2; p.pad_t = 0; p.pad_l = 0; p.stride = 1; p.quad = 1;
+  if (reinterpret_cast<uintptr_t>(workspace) & 31) return fail(GANB_E_BADARG, "filter gradient: workspace must be 32-byte aligned");
   p.partial = static_cast<float*>(workspace);
   CUtensorMap tmX, tmDY;
   {
@@ -2115,6 +2189,13 @@ extern "C" int ganb_conv2d_igemm_tf32(const float* x, const float* wp, void* y, 
   if (p.res_up2 && ((ho | wo) & 1)) return fail(GANB_E_BADARG, "conv2d_igemm_tf32: upsampled residual needs even ho, wo");
   p.out = y; p.out_bf16 = (out_dtype == GANB_BF16); p.act = act;
   p.og = 1; p.rg = 1; p.out_cstride = cout;
+  {
+    const int64_t es_ = p.out_bf16 ? 2 : 4;
+    static const bool st32_ok = !(getenv("GANB_ST32") && getenv("GANB_ST32")[0] == '0');   // A/B switch
+    p.st32 = st32_ok && (reinterpret_cast<uintptr_t>(p.out) % 32 == 0) && ((p.Cout * es_) % 32 == 0) &&
+             ((static_cast<int64_t>(p.out_cstride) * es_) % 32 == 0);
+    p.res32 = st32_ok && p.residual && (reinterpret_cast<uintptr_t>(p.residual) % 32 == 0) && (p.Cout % 8 == 0);
+  }
   for (int i = 0; i < 4; ++i) { p.gpad_t[i] = 0; p.gpad_l[i] = 0; }
   const int bn_tile = cout <= 16 ? 16 : cout <= 64 ? 64 : 128;
   CUtensorMap tmA, tmB;
@@ -2159,6 +2240,7 @@ extern "C" int ganb_conv2d_wgrad_tf32(const float* x, const float* dy, float* dw
   plan_wgrad(n, ho, wo, cin, cout, kh, kw, &plan, 128);
   WgradParams& p = plan.p;
   p.pad_t = pad_t; p.pad_l = pad_l; p.stride = stride; p.quad = 0;
+  if (reinterpret_cast<uintptr_t>(workspace) & 31) return fail(GANB_E_BADARG, "filter gradient: workspace must be 32-byte aligned");
   p.partial = static_cast<float*>(workspace);
   CUtensorMap tmX, tmDY;
   {

@@ -67,6 +67,8 @@ int ganb_set_sm_limit(int sms);
  * the same kernel into the data gradient of a stride-1 convolution when x := dy, wp := HWIO filter viewed
  * as [kh*kw][cin_fwd][cout_fwd], pad := k-1-pad.
  * Requirements: cin % 8 == 0, x and wp 16-byte aligned. alpha (device scalar), bias, residual may be NULL.
+ * Outputs (and fp32 residuals) whose base address and row length are multiples of 32 bytes are written (read) with
+ * 256-bit accesses, one whole sector per instruction; anything else takes the 16- / 8- / 2-byte forms.
  * stride in 1..4 (strided layers gather through TMA element strides; the data gradient of a strided convolution is
  * this same entry applied to the zero-dilated output gradient, see ganb_dilate2d).
  * residual_up2 = 1: `residual` is [n, ho/2, wo/2, cout] and is read through a nearest-neighbour 2x upsample
@@ -104,7 +106,7 @@ int ganb_bn_stats_finalize(const float* partial, int c, int groups, int chunks, 
 
 /* Filter gradient: partial[split][t][ci][co] = sum over the split's pixels of
  *     x[n, ho*stride + r - pad_t, wo*stride + s - pad_l, ci] * dy[n, ho, wo, co]
- * `workspace` must hold ganb_conv2d_wgrad_workspace() bytes; the reduction over splits, the optional
+ * `workspace` (32-byte aligned) must hold ganb_conv2d_wgrad_workspace() bytes; the reduction over splits, the optional
  * scale and the accumulation into dw (HWIO f32) are done by the same call (second kernel).
  *     dw = beta * dw + scale * sum_split partial
  * Requirements: cin % 8 == 0, cout % 8 == 0. */
