@@ -145,7 +145,12 @@ def run_reference(args, rank: int):
     if rank != 0:
         return 0
     tf_probe = probe_tensorflow()
-    v, cores, sample, ms = cpu_pairs_per_s(args.steps, args.warmup, batch=64)
+    # ~1.5 s per pair on 16 host threads: more than 60 timed pairs would not end "within a few minutes"; the driver's own
+    # K (20) is far below the cap, which only bounds a flag-less run (default K = 300)
+    timed = min(args.steps, 60)
+    v, cores, sample, ms = cpu_pairs_per_s(timed, min(args.warmup, 5), batch=64)
+    if timed != args.steps:
+        sample += f"; --steps {args.steps} capped at {timed} timed pairs"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -420,7 +425,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)      # ~0.9 s timed (+ the same again for the e2e leg): a few clock samples
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-pair-schedule", action="store_true",
