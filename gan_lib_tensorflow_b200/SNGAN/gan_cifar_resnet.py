@@ -10,6 +10,7 @@ Reference structure kept:
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 
@@ -58,6 +59,7 @@ if not any(CRITIC_BWD_SPLIT):
     CRITIC_BWD_SPLIT = None
 # critic power iteration on a side stream next to the generator pass instead of heading the critic chain: no measurable
 # change (3.07 vs 3.07 ms per pair), opt-in
+EMBED_BRANCH = os.environ.get("GANB_EMBED_BRANCH", "1") != "0"   # critic label branch as a Tape branch (A/B switch)
 PREFETCH_SN = os.environ.get("GANB_PREFETCH_SN", "0") == "1"
 # late fork only: SMs for the tensor-core kernels of (generator forward on the aux stream, critic step), "0:0" = no limits
 SM_SPLIT = tuple(int(v) for v in os.environ.get("GANB_SM_SPLIT", "0:0").split(":"))
@@ -110,13 +112,22 @@ def Discriminator(inputs, labels, update_collection=None, reuse=False):
     store = get_store()
     with store.variable_scope("Discriminator", reuse=reuse):
         output = F.reshape(F.as_var(inputs), (-1, 32, 32, 3))
+        # The label branch (embedding + linear layer) only meets the image branch at the concat below.  On a recording tape
+        # it is a Tape branch on a side stream: in the backward pass its three small launches (~50 us of CUDA-core GEMM
+        # and scatter) then run NEXT TO D.Block.1's backward instead of in front of it on the data-gradient chain.
+        tape = store.tape if (EMBED_BRANCH and reuse and not K.host_logic_only()) else None
+        marker = tape.fork() if tape is not None else None
         output = rb.OptimizedResBlockDisc1(output, DIM_D=DIM_D, spectral_normed=True,
                                            update_collection=update_collection, biases=True,
                                            name_prefix='D.Block.1')
         # embedding labels, and concatenate to 'output'.
-        embedding_y = embedding_ops.embed_y(labels, VOCAB_SIZE, EMBEDDING_DIM)
-        embedding_y = linear_ops.Linear(embedding_y, EMBEDDING_DIM, DIM_D, 'D.Embedding_y', spectral_normed=True,
-                                        update_collection=update_collection, biases=True)  # (N, DIM_D)
+        # (a stream of its own: the aux stream carries the generator pass of the pair schedule at this point)
+        with (tape.branch(marker, framework_side_stream(store.device, 3)) if tape is not None else contextlib.nullcontext()):
+            embedding_y = embedding_ops.embed_y(labels, VOCAB_SIZE, EMBEDDING_DIM)
+            embedding_y = linear_ops.Linear(embedding_y, EMBEDDING_DIM, DIM_D, 'D.Embedding_y', spectral_normed=True,
+                                            update_collection=update_collection, biases=True)  # (N, DIM_D)
+        if tape is not None:
+            tape.join_forward(marker)
         pre = F.concat_label_map(output, embedding_y, act='relu')
         output = _block(None, DIM_D * 2, DIM_D, 3, 'D.Block.2', spectral_normed=True,
                         update_collection=update_collection, resample='down', labels=labels, biases=True,
