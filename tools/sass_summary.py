@@ -34,6 +34,10 @@ def main():
             continue
         op = m.group(1)
         per[cur]["_total"] += 1
+        if op.startswith("STG.") and ".256" in op:      # 256-bit stores: one whole 32-byte sector per thread and instruction
+            per[cur]["STG.256"] += 1
+        if op.startswith("LDG.") and ".256" in op:
+            per[cur]["LDG.256"] += 1
         for mn in MNEMONICS:
             if op == mn or op.startswith(mn + "."):
                 if mn == "UTCHMMA" and op.startswith("UTCHMMA.2CTA"):
@@ -47,12 +51,12 @@ def main():
     for (name, cnt), dm in zip(per.items(), demangle):
         short = re.sub(r"\(.*", "", dm).replace("void ", "").replace("ganb::", "")[:86]
         hits = " ".join(f"{k}={v}" for k, v in cnt.items() if k != "_total" and k in
-                        ("UTCHMMA.2CTA", "UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "UBLKCP", "LDGSTS"))
+                        ("UTCHMMA.2CTA", "UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "UBLKCP", "LDGSTS", "STG.256", "LDG.256"))
         for k, v in cnt.items():
             tot[k] += v
         if hits:
             print("%-86s %7d  %s" % (short, cnt["_total"], hits))
-    print("\nlibrary totals: " + "  ".join(f"{k}={tot[k]}" for k in MNEMONICS if tot[k]))
+    print("\nlibrary totals: " + "  ".join(f"{k}={tot[k]}" for k in MNEMONICS + ["STG.256", "LDG.256"] if tot[k]))
     print("kernels without tensor-core / TMA instructions (CUDA-core, bandwidth-bound): %d" %
           sum(1 for c in per.values() if not any(c[k] for k in ("UTCHMMA.2CTA", "UTCHMMA", "UTMALDG", "LDTM"))))
 
