@@ -473,6 +473,38 @@ def test_training_step_call_sequence_and_freezing(host):
     assert P.lr_decay(0) == 1.0 and P.lr_decay(60000) == 0.5
 
 
+def test_critic_blocks_fuse_their_mid_block_relu_into_the_two_convolutions(host):
+    """No normalisation sits between Conv1 and Conv2 of a critic block: Conv1 is launched with act = relu, no activation
+    pass follows it, and Conv2's data gradient is the gated entry; with the switch off the separate passes come back."""
+    store, rec = host
+    from gan_lib_tensorflow_b200 import cabi, functional as F
+    from gan_lib_tensorflow_b200.SNGAN import gan_cifar_resnet as P
+
+    tr = P.Trainer(batch_size=64, seed=0, store=store)
+    rec.calls.clear()
+    tr.d_step(0)
+    names = rec.names()
+    relu = cabi.act_code("relu")
+    igemm = [c for c in rec.calls if c[0] == "ganb_conv2d_igemm"]
+    fused_fwd = [c for c in igemm if c[1][20] == relu]           # (..., residual_up2, act, out_dtype, stream)
+    assert len(fused_fwd) == 4                                    # Conv1 of D.Block.1 .. D.Block.4
+    assert all(c[1][21] == cabi.BF16 for c in fused_fwd)          # act(y) is stored in bf16 only
+    gated = [c for c in rec.calls if c[0] == "ganb_conv2d_igemm_gated"]
+    assert len(gated) == 4 and all(c[1][18] == relu for c in gated)
+    n_act_fwd, n_act_bwd = names.count("ganb_norm_act_fwd"), names.count("ganb_norm_act_bwd")
+    old = F.FUSED_CONV_ACT
+    F.FUSED_CONV_ACT = False
+    try:
+        rec.calls.clear()
+        tr.d_step(1)
+        names = rec.names()
+        assert "ganb_conv2d_igemm_gated" not in names
+        assert not [c for c in rec.calls if c[0] == "ganb_conv2d_igemm" and c[1][20] == relu]
+        assert names.count("ganb_norm_act_fwd") == n_act_fwd + 4 and names.count("ganb_norm_act_bwd") == n_act_bwd + 4
+    finally:
+        F.FUSED_CONV_ACT = old
+
+
 def test_pair_schedule_issues_the_same_calls_as_the_two_steps(host):
     """Trainer.pair_step = d_step + g_step with the generator step's G forward issued first (next to the critic step on
     the GPU): the same multiset of kernel calls, one Adam per optimiser, G's statistics in two towers of 64."""
