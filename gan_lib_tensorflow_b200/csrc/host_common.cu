@@ -26,7 +26,9 @@ bool pdl_enabled() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("GANB_PDL");
-    mode = (e && e[0] == '1') ? 1 : 0;   // measured neutral inside captured graphs (profiles/r01 notes): opt-in
+    // opt-in, and NOT recommended: -0.4 ... -0.5 % inside captured graphs, but one of two 300-pair bench runs on the final
+    // round-2 tree (Tape branches on several streams) did not finish with it on (profiles/r02_schedule_ab.txt, item 9)
+    mode = (e && e[0] == '1') ? 1 : 0;
   }
   return mode == 1;
 }
