@@ -207,6 +207,7 @@ int ganb_upconv_fprop_stats(const void* x_bf16, const void* we_t_bf16, void* y_q
                             int groups, void* stream);
 int ganb_upconv_dgrad(const void* dy_quad_bf16, const void* we_n_bf16, void* dx, int n, int h, int w, int cin, int cout,
                       const float* alpha, int out_dtype, void* stream);
+/* workspace: ganb_upconv_wgrad_workspace() bytes, 32-byte aligned (as for ganb_conv2d_wgrad) */
 int64_t ganb_upconv_wgrad_workspace(int n, int h, int w, int cin, int cout);
 int ganb_upconv_wgrad(const void* x_bf16, const void* dy_quad_bf16, float* dw_hwio, void* workspace, int n, int h, int w,
                       int cin, int cout, const float* scale, float beta, void* stream);
@@ -461,6 +462,7 @@ int ganb_conv2d_igemm_tf32(const float* x, const float* wp, void* y, int n, int 
                            int cout, int kh, int kw, int stride, int pad_t, int pad_l, int flip_taps, const float* alpha,
                            const float* bias, const float* residual, int residual_up2, int act, int out_dtype,
                            void* stream);
+/* workspace: ganb_conv2d_wgrad_tf32_workspace() bytes, 32-byte aligned */
 int64_t ganb_conv2d_wgrad_tf32_workspace(int n, int ho, int wo, int cin, int cout, int kh, int kw);
 int ganb_conv2d_wgrad_tf32(const float* x, const float* dy, float* dw, void* workspace, int n, int h, int w, int cin,
                            int ho, int wo, int cout, int kh, int kw, int stride, int pad_t, int pad_l, const float* scale,
