@@ -426,7 +426,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)      # ~0.9 s timed (+ the same again for the e2e leg): a few clock samples
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=50)      # >= 200 timed steps after 50 warm-up steps
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-pair-schedule", action="store_true",
                     help="replay the critic step and the generator step as separate graphs (round-1 schedule) instead "
